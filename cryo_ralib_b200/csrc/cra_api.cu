@@ -1,0 +1,523 @@
+// cra_api.cu -- the status-returning C-ABI core (include/cryo_ralib.h, layer 1).
+// Owns the device buffers (the reference's BatchHandler + CcfResultTable,
+// cuda/gpu_aln_noref.cu:1500-2399, minus the CCF table), builds the ring / sampling
+// tables (Sphire Numrinit, ringwe; EMAN2 alrl_ms geometry; test_mref.py:145-146) and
+// sequences the kernels on one CUDA stream.  No exit(), no CPU fallback.
+#include "cra_common.cuh"
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <mutex>
+
+static thread_local std::string g_err;
+void cra_set_error(const std::string& msg) { g_err = msg; }
+extern "C" const char* cra_last_error(void) { return g_err.c_str(); }
+
+struct CraCtx {
+    CraConfig cfg{};
+    int device = 0;
+    cudaStream_t st = nullptr;
+    int nx = 0, npix = 0, R = 0;
+    CraRingTab htab{};
+    std::vector<int> numr;
+    int smax = 0;            // most rows one particle can have
+    int row_batch = 0;
+    int ntile_n_max = 0;
+    bool timing = false;
+    CraAlignStats stats{};
+    // device
+    CraRingTab* d_tab = nullptr;
+    float2* d_samp = nullptr; float* d_sampw = nullptr;
+    float2* d_twf = nullptr;  float2* d_twi = nullptr;
+    float* d_mask = nullptr;
+    float* d_images = nullptr; float* d_refs = nullptr; float* d_refspec = nullptr;
+    float* d_spec = nullptr; CraCand* d_cand = nullptr;
+    float* d_sums = nullptr;     // [R][2][npix] + [R]
+    // per-call staging (grown on demand)
+    size_t cap_meta = 0;         // particles
+    char* h_meta = nullptr; char* d_meta = nullptr; size_t meta_bytes = 0;
+    CraResult* d_res = nullptr; CraResult* h_res = nullptr;
+    float4* d_par = nullptr; int* d_iref = nullptr; float4* h_par = nullptr; int* h_iref = nullptr; size_t cap_par = 0;
+    float* d_tmpimg = nullptr; size_t cap_tmpimg = 0;
+    float* d_curves = nullptr;
+    std::vector<cudaEvent_t> ev;
+};
+
+namespace {
+
+int ilog2_floor(int n) { int l = -1; while (n > 0) { n >>= 1; ++l; } return l; }
+
+// Sphire Numrinit(first_ring, last_ring, skip, "F")
+std::vector<int> numrinit(int ir, int ou, int rs)
+{
+    const int MAXFFT = 32768;
+    std::vector<int> numr; int lcirc = 1;
+    for (int k = ir; k <= ou; k += rs) {
+        int jp = (int)(2.0 * M_PI * k + 0.5);
+        int ip = 1 << (ilog2_floor(jp) + 1);
+        if (k + rs <= ou && jp > ip + ip / 2) ip = std::min(MAXFFT, 2 * ip);
+        if (k + rs > ou && jp > ip + ip / 5) ip = std::min(MAXFFT, 2 * ip);
+        numr.push_back(k); numr.push_back(lcirc); numr.push_back(ip);
+        lcirc += ip;
+    }
+    return numr;
+}
+
+int build_tables(CraCtx* c)
+{
+    c->numr = numrinit(c->cfg.ir, c->cfg.ou, c->cfg.rs);
+    const int nring = (int)c->numr.size() / 3;
+    if (nring < 1 || nring > CRA_MAX_RINGS) { cra_set_error("ring count out of range"); return 1; }
+    CraRingTab& t = c->htab;
+    memset(&t, 0, sizeof(t));
+    t.nring = nring;
+    t.maxrin = c->numr[3 * nring - 1];
+    t.lcirc = c->numr[3 * nring - 2] + c->numr[3 * nring - 1] - 1;
+    t.log2n = ilog2_floor(t.maxrin);
+    if ((1 << t.log2n) != t.maxrin || t.log2n < 5 || t.log2n > 10) {
+        cra_set_error("maxrin must be a power of two in [32,1024] (ou between 3 and ~160)"); return 1;
+    }
+    float nn = 0.0f;
+    std::vector<float2> samp(t.lcirc);
+    std::vector<float> sampw(t.lcirc);
+    const double dpi = 2 * atan(1.0);
+    for (int i = 0; i < nring; ++i) {
+        const int inr = c->numr[3 * i], len = c->numr[3 * i + 2], off = c->numr[3 * i + 1] - 1;
+        t.off[i] = off; t.len[i] = len; t.rad[i] = inr;
+        t.wr[i] = (float)(inr * (2.0 * M_PI) / (double)len * (double)t.maxrin / (double)len);   // ringwe
+        t.wn[i] = (float)(inr * 2 * M_PI / (float)len);                                         // Normalize_ring
+        const int lt = len / 4;
+        const double dfi = dpi / lt;
+        for (int jt = 0; jt < lt; ++jt) {
+            float x, y;
+            if (jt == 0) { x = 0.0f; y = (float)inr; }
+            else { float fi = (float)(dfi * jt); x = sinf(fi) * inr; y = cosf(fi) * inr; }
+            samp[off + jt] = make_float2(x, y);
+            samp[off + jt + lt] = make_float2(y, -x);
+            samp[off + jt + 2 * lt] = make_float2(-x, -y);
+            samp[off + jt + 3 * lt] = make_float2(-y, x);
+        }
+        for (int j = 0; j < len; ++j) { sampw[off + j] = t.wn[i]; nn += t.wn[i]; }
+    }
+    t.nn = nn;
+    std::vector<float2> twf(t.maxrin / 2), twi(t.maxrin);
+    for (int j = 0; j < t.maxrin / 2; ++j) {
+        double a = -2.0 * M_PI * j / t.maxrin; twf[j] = make_float2((float)cos(a), (float)sin(a));
+    }
+    for (int j = 0; j < t.maxrin; ++j) {
+        double a = 2.0 * M_PI * j / t.maxrin; twi[j] = make_float2((float)cos(a), (float)sin(a));
+    }
+    // model_circle(ou, nx, nx): r^2 <= ou^2 around (nx/2, nx/2)
+    std::vector<float> mask((size_t)c->npix);
+    const float rad = (float)c->cfg.ou;
+    for (int j = 0; j < c->nx; ++j)
+        for (int i = 0; i < c->nx; ++i) {
+            float x2 = fabsf((float)i - c->nx / 2), y2 = fabsf((float)j - c->nx / 2);
+            float r = (x2 * x2) / (rad * rad) + (y2 * y2) / (rad * rad);
+            mask[i + (size_t)j * c->nx] = (r <= 1) ? 1.0f : 0.0f;
+        }
+    CRA_CUDA(cudaMalloc(&c->d_tab, sizeof(CraRingTab)));
+    CRA_CUDA(cudaMemcpy(c->d_tab, &t, sizeof(CraRingTab), cudaMemcpyHostToDevice));
+    CRA_CUDA(cudaMalloc(&c->d_samp, sizeof(float2) * t.lcirc));
+    CRA_CUDA(cudaMemcpy(c->d_samp, samp.data(), sizeof(float2) * t.lcirc, cudaMemcpyHostToDevice));
+    CRA_CUDA(cudaMalloc(&c->d_sampw, sizeof(float) * t.lcirc));
+    CRA_CUDA(cudaMemcpy(c->d_sampw, sampw.data(), sizeof(float) * t.lcirc, cudaMemcpyHostToDevice));
+    CRA_CUDA(cudaMalloc(&c->d_twf, sizeof(float2) * twf.size()));
+    CRA_CUDA(cudaMemcpy(c->d_twf, twf.data(), sizeof(float2) * twf.size(), cudaMemcpyHostToDevice));
+    CRA_CUDA(cudaMalloc(&c->d_twi, sizeof(float2) * twi.size()));
+    CRA_CUDA(cudaMemcpy(c->d_twi, twi.data(), sizeof(float2) * twi.size(), cudaMemcpyHostToDevice));
+    CRA_CUDA(cudaMalloc(&c->d_mask, sizeof(float) * c->npix));
+    CRA_CUDA(cudaMemcpy(c->d_mask, mask.data(), sizeof(float) * c->npix, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int window_of(const CraSearch& s, float step, int4* w)
+{
+    w->x = (int)(s.xl / step); w->y = (int)(s.xr / step);
+    w->z = (int)(s.yl / step); w->w = (int)(s.yr / step);
+    if (w->x < 0 || w->y < 0 || w->z < 0 || w->w < 0) return 1;
+    return 0;
+}
+
+struct Bind { CraCtx* c; Bind(CraCtx* c_) : c(c_) {} int ok() { if (!c) { cra_set_error("null context"); return 1; }
+    cudaError_t e = cudaSetDevice(c->device); if (e != cudaSuccess) { cra_set_error(cudaGetErrorString(e)); return 1; } return 0; } };
+
+int ensure_meta(CraCtx* c, size_t nparticles, size_t nbatch_guess)
+{
+    size_t need = nparticles * (sizeof(CraSearch) + sizeof(int4) + sizeof(int)) + (nbatch_guess + 2) * sizeof(int) + 64;
+    if (need > c->meta_bytes) {
+        if (c->h_meta) cudaFreeHost(c->h_meta);
+        if (c->d_meta) cudaFree(c->d_meta);
+        c->h_meta = nullptr; c->d_meta = nullptr;
+        c->meta_bytes = need + need / 4;
+        CRA_CUDA(cudaMallocHost(&c->h_meta, c->meta_bytes));
+        CRA_CUDA(cudaMalloc(&c->d_meta, c->meta_bytes));
+    }
+    if (nparticles > c->cap_meta) {
+        if (c->d_res) cudaFree(c->d_res);
+        if (c->h_res) cudaFreeHost(c->h_res);
+        c->d_res = nullptr; c->h_res = nullptr;
+        c->cap_meta = nparticles + nparticles / 4;
+        CRA_CUDA(cudaMalloc(&c->d_res, sizeof(CraResult) * c->cap_meta));
+        CRA_CUDA(cudaMallocHost(&c->h_res, sizeof(CraResult) * c->cap_meta));
+    }
+    return 0;
+}
+
+int ensure_par(CraCtx* c, size_t n)
+{
+    if (n > c->cap_par) {
+        if (c->d_par) cudaFree(c->d_par);
+        if (c->d_iref) cudaFree(c->d_iref);
+        if (c->h_par) cudaFreeHost(c->h_par);
+        if (c->h_iref) cudaFreeHost(c->h_iref);
+        c->cap_par = n + n / 4;
+        CRA_CUDA(cudaMalloc(&c->d_par, sizeof(float4) * c->cap_par));
+        CRA_CUDA(cudaMalloc(&c->d_iref, sizeof(int) * c->cap_par));
+        CRA_CUDA(cudaMallocHost(&c->h_par, sizeof(float4) * c->cap_par));
+        CRA_CUDA(cudaMallocHost(&c->h_iref, sizeof(int) * c->cap_par));
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int cra_create(const CraConfig* cfg, int device, CraCtx** out)
+{
+    if (!cfg || !out) { cra_set_error("null argument"); return 1; }
+    if (cfg->nx < 8 || cfg->ir < 1 || cfg->ou < cfg->ir || cfg->rs < 1 || cfg->step <= 0.f ||
+        cfg->max_particles < 1 || cfg->max_refs < 1 || cfg->max_range < 0.f) {
+        cra_set_error("invalid CraConfig"); return 1;
+    }
+    if (cfg->ou + 2 > cfg->nx / 2) { cra_set_error("ou too large for nx (needs ou <= nx/2 - 2)"); return 1; }
+    int ndev = 0;
+    CRA_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { cra_set_error("no such CUDA device"); return 1; }
+    CRA_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CRA_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { cra_set_error("this engine is built for sm_100a (B200) only"); return 1; }
+    CraCtx* c = new CraCtx();
+    c->cfg = *cfg; c->device = device; c->nx = cfg->nx; c->npix = cfg->nx * cfg->nx;
+    if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { cra_set_error("stream create failed"); delete c; return 1; }
+    if (build_tables(c)) { cra_destroy(c); return 1; }
+    const int k = (int)(cfg->max_range / cfg->step);
+    c->smax = (2 * k + 1) * (2 * k + 1);
+    const size_t row_bytes = (size_t)c->htab.lcirc * sizeof(float);
+    long rb = cfg->row_batch > 0 ? cfg->row_batch : (long)((size_t)2 << 30) / (long)row_bytes;
+    if (rb < c->smax) rb = c->smax;
+    long want = (long)cfg->max_particles * c->smax;
+    if (rb > want) rb = want;
+    c->row_batch = (int)rb;
+    c->ntile_n_max = (cfg->max_refs + cra_ccf_tile_n() - 1) / cra_ccf_tile_n();
+    const size_t nsum = (size_t)cfg->max_refs * 2 * c->npix + cfg->max_refs;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_images, (size_t)cfg->max_particles * c->npix * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_refs, (size_t)cfg->max_refs * c->npix * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_refspec, (size_t)cfg->max_refs * row_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_spec, (size_t)c->row_batch * row_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_cand, (size_t)c->row_batch * c->ntile_n_max * sizeof(CraCand));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_sums, nsum * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_curves, (size_t)2 * c->htab.maxrin * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(c->d_sums, 0, nsum * sizeof(float));
+    if (e != cudaSuccess) { cra_set_error(std::string("device allocation failed: ") + cudaGetErrorString(e)); cra_destroy(c); return 1; }
+    *out = c;
+    return 0;
+}
+
+extern "C" int cra_destroy(CraCtx* c)
+{
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    if (c->st) cudaStreamSynchronize(c->st);
+    for (auto& e : c->ev) cudaEventDestroy(e);
+    cudaFree(c->d_tab); cudaFree(c->d_samp); cudaFree(c->d_sampw); cudaFree(c->d_twf); cudaFree(c->d_twi);
+    cudaFree(c->d_mask); cudaFree(c->d_images); cudaFree(c->d_refs); cudaFree(c->d_refspec);
+    cudaFree(c->d_spec); cudaFree(c->d_cand); cudaFree(c->d_sums); cudaFree(c->d_meta); cudaFree(c->d_res);
+    cudaFree(c->d_par); cudaFree(c->d_iref); cudaFree(c->d_tmpimg); cudaFree(c->d_curves);
+    if (c->h_meta) cudaFreeHost(c->h_meta);
+    if (c->h_res) cudaFreeHost(c->h_res);
+    if (c->h_par) cudaFreeHost(c->h_par);
+    if (c->h_iref) cudaFreeHost(c->h_iref);
+    if (c->st) cudaStreamDestroy(c->st);
+    delete c;
+    return 0;
+}
+
+extern "C" int cra_ring_info(CraCtx* c, int* nring, int* lcirc, int* maxrin, int* numr_out)
+{
+    if (!c) { cra_set_error("null context"); return 1; }
+    if (nring) *nring = c->htab.nring;
+    if (lcirc) *lcirc = c->htab.lcirc;
+    if (maxrin) *maxrin = c->htab.maxrin;
+    if (numr_out) memcpy(numr_out, c->numr.data(), c->numr.size() * sizeof(int));
+    return 0;
+}
+
+static int upload_particles(CraCtx* c, const float* src, int first, int n, int sub, cudaMemcpyKind kind)
+{
+    Bind b(c); if (b.ok()) return 1;
+    if (first < 0 || n < 0 || first + n > c->cfg.max_particles) { cra_set_error("particle range exceeds max_particles"); return 1; }
+    if (n == 0) return 0;
+    float* dst = c->d_images + (size_t)first * c->npix;
+    CRA_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * c->npix * sizeof(float), kind, c->st));
+    if (sub && cra_launch_mask_normalize(dst, n, c->nx, c->d_mask, 0, c->st)) return 1;
+    CRA_CUDA(cudaStreamSynchronize(c->st));
+    return 0;
+}
+extern "C" int cra_upload_particles(CraCtx* c, const float* h, int first, int n, int sub)
+{ return upload_particles(c, h, first, n, sub, cudaMemcpyHostToDevice); }
+extern "C" int cra_upload_particles_dev(CraCtx* c, const float* d, int first, int n, int sub)
+{ return upload_particles(c, d, first, n, sub, cudaMemcpyDeviceToDevice); }
+
+extern "C" int cra_set_refs(CraCtx* c, const float* h, int R, int normalize_mask)
+{
+    Bind b(c); if (b.ok()) return 1;
+    if (R < 1 || R > c->cfg.max_refs) { cra_set_error("R exceeds max_refs"); return 1; }
+    CRA_CUDA(cudaMemcpyAsync(c->d_refs, h, (size_t)R * c->npix * sizeof(float), cudaMemcpyHostToDevice, c->st));
+    if (normalize_mask && cra_launch_mask_normalize(c->d_refs, R, c->nx, c->d_mask, 1, c->st)) return 1;
+    if (cra_launch_polar_refs(c->d_refs, R, c->nx, c->d_tab, c->htab, c->d_samp, c->d_twf, c->d_refspec, c->st)) return 1;
+    CRA_CUDA(cudaStreamSynchronize(c->st));
+    c->R = R;
+    return 0;
+}
+
+extern "C" int cra_align(CraCtx* c, int start, int stop, const CraSearch* search, CraResult* out)
+{
+    Bind b(c); if (b.ok()) return 1;
+    const int n = stop - start;
+    if (start < 0 || n < 0 || stop > c->cfg.max_particles) { cra_set_error("particle range exceeds max_particles"); return 1; }
+    if (c->R < 1) { cra_set_error("cra_set_refs has not been called"); return 1; }
+    if (n == 0) return 0;
+    const float step = c->cfg.step;
+    // plan batches
+    std::vector<int> bfirst, bcount, brows;
+    {
+        int cur_first = 0, cur_rows = 0;
+        for (int p = 0; p < n; ++p) {
+            int4 w;
+            if (window_of(search[p], step, &w)) { cra_set_error("negative search window"); return 1; }
+            const long rows = (long)(w.x + w.y + 1) * (w.z + w.w + 1);
+            if (rows > c->row_batch) { cra_set_error("search window larger than max_range allows"); return 1; }
+            if (cur_rows + rows > c->row_batch) {
+                bfirst.push_back(cur_first); bcount.push_back(p - cur_first); brows.push_back(cur_rows);
+                cur_first = p; cur_rows = 0;
+            }
+            cur_rows += (int)rows;
+        }
+        bfirst.push_back(cur_first); bcount.push_back(n - cur_first); brows.push_back(cur_rows);
+    }
+    const size_t nb = bfirst.size();
+    if (ensure_meta(c, n, nb)) return 1;
+    // meta layout: win[n] (16-byte aligned) | search[n] | row_start[n + nb]
+    int4* h_win = reinterpret_cast<int4*>(c->h_meta);
+    CraSearch* h_search = reinterpret_cast<CraSearch*>(c->h_meta + (size_t)n * sizeof(int4));
+    int* h_rs = reinterpret_cast<int*>(c->h_meta + (size_t)n * (sizeof(CraSearch) + sizeof(int4)));
+    memcpy(h_search, search, (size_t)n * sizeof(CraSearch));
+    long total_rows = 0;
+    for (size_t bi = 0; bi < nb; ++bi) {
+        int* rs = h_rs + bfirst[bi] + bi;
+        int acc = 0;
+        for (int q = 0; q < bcount[bi]; ++q) {
+            const int p = bfirst[bi] + q;
+            window_of(search[p], step, &h_win[p]);
+            rs[q] = acc;
+            acc += (h_win[p].x + h_win[p].y + 1) * (h_win[p].z + h_win[p].w + 1);
+        }
+        rs[bcount[bi]] = acc;
+        total_rows += acc;
+    }
+    const size_t used = (size_t)n * (sizeof(CraSearch) + sizeof(int4)) + (n + nb) * sizeof(int);
+    CRA_CUDA(cudaMemcpyAsync(c->d_meta, c->h_meta, used, cudaMemcpyHostToDevice, c->st));
+    const int4* d_win = reinterpret_cast<const int4*>(c->d_meta);
+    const CraSearch* d_search = reinterpret_cast<const CraSearch*>(c->d_meta + (size_t)n * sizeof(int4));
+    const int* d_rs = reinterpret_cast<const int*>(c->d_meta + (size_t)n * (sizeof(CraSearch) + sizeof(int4)));
+
+    const int TN = cra_ccf_tile_n();
+    const int ntile_n = (c->R + TN - 1) / TN;
+    const bool tm = c->timing;
+    if (tm) {
+        while (c->ev.size() < 4 * nb) { cudaEvent_t e; CRA_CUDA(cudaEventCreate(&e)); c->ev.push_back(e); }
+    }
+    long launches = 0;
+    for (size_t bi = 0; bi < nb; ++bi) {
+        CraRowMap map;
+        map.row_start = d_rs + bfirst[bi] + bi;
+        map.search = d_search + bfirst[bi];
+        map.win = d_win + bfirst[bi];
+        map.np = bcount[bi]; map.nrows = brows[bi]; map.p0 = start + bfirst[bi]; map.step = step;
+        if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 0], c->st));
+        if (cra_launch_polar_rows(c->d_images, c->nx, c->d_tab, c->htab, c->d_samp, c->d_sampw, c->d_twf, map,
+                                  c->cfg.normalize_ring, c->d_spec, c->st)) return 1;
+        if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 1], c->st));
+        if (cra_launch_ccf(c->d_spec, map.nrows, c->d_refspec, c->R, c->d_tab, c->htab, c->d_twi, c->d_cand, ntile_n, c->st)) return 1;
+        if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 2], c->st));
+        if (cra_launch_finalize(c->d_spec, c->d_refspec, c->R, c->d_tab, c->htab, c->d_cand, ntile_n, map,
+                                c->d_res + bfirst[bi], c->st)) return 1;
+        if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 3], c->st));
+        launches += 3;
+    }
+    CRA_CUDA(cudaMemcpyAsync(c->h_res, c->d_res, (size_t)n * sizeof(CraResult), cudaMemcpyDeviceToHost, c->st));
+    CRA_CUDA(cudaStreamSynchronize(c->st));
+    memcpy(out, c->h_res, (size_t)n * sizeof(CraResult));
+    c->stats = CraAlignStats{};
+    c->stats.launches = launches;
+    c->stats.rows = total_rows;
+    c->stats.alignments = total_rows * c->R;
+    if (tm) {
+        for (size_t bi = 0; bi < nb; ++bi) {
+            float a = 0, bb = 0, cc = 0;
+            cudaEventElapsedTime(&a, c->ev[4 * bi + 0], c->ev[4 * bi + 1]);
+            cudaEventElapsedTime(&bb, c->ev[4 * bi + 1], c->ev[4 * bi + 2]);
+            cudaEventElapsedTime(&cc, c->ev[4 * bi + 2], c->ev[4 * bi + 3]);
+            c->stats.ms_polar += a; c->stats.ms_ccf += bb; c->stats.ms_final += cc;
+        }
+        float tot = 0; cudaEventElapsedTime(&tot, c->ev[0], c->ev[4 * (nb - 1) + 3]);
+        c->stats.ms_total = tot;
+    }
+    return 0;
+}
+
+extern "C" int cra_last_align_stats(CraCtx* c, CraAlignStats* out)
+{
+    if (!c || !out) { cra_set_error("null argument"); return 1; }
+    *out = c->stats; return 0;
+}
+extern "C" int cra_set_timing(CraCtx* c, int enabled)
+{
+    if (!c) { cra_set_error("null context"); return 1; }
+    c->timing = enabled != 0; return 0;
+}
+
+extern "C" int cra_set_normalize_ring(CraCtx* c, int enabled)
+{
+    if (!c) { cra_set_error("null context"); return 1; }
+    c->cfg.normalize_ring = enabled != 0; return 0;
+}
+extern "C" int cra_set_step(CraCtx* c, float step)
+{
+    if (!c) { cra_set_error("null context"); return 1; }
+    if (!(step > 0.f)) { cra_set_error("step must be positive"); return 1; }
+    c->cfg.step = step; return 0;
+}
+extern "C" int cra_row_batch(CraCtx* c) { return c ? c->row_batch : 0; }
+extern "C" int cra_device_images_ptr(CraCtx* c, void** p) { if (!c || !p) { cra_set_error("null argument"); return 1; } *p = c->d_images; return 0; }
+extern "C" void* cra_stream(CraCtx* c) { return c ? (void*)c->st : nullptr; }
+
+extern "C" int cra_zero_sums(CraCtx* c)
+{
+    Bind b(c); if (b.ok()) return 1;
+    const size_t nsum = (size_t)c->cfg.max_refs * 2 * c->npix + c->cfg.max_refs;
+    CRA_CUDA(cudaMemsetAsync(c->d_sums, 0, nsum * sizeof(float), c->st));
+    CRA_CUDA(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+extern "C" int cra_accumulate(CraCtx* c, int start, int stop, const float* params, const int* iref, long goff)
+{
+    Bind b(c); if (b.ok()) return 1;
+    const int n = stop - start;
+    if (start < 0 || n < 0 || stop > c->cfg.max_particles) { cra_set_error("particle range exceeds max_particles"); return 1; }
+    if (n == 0) return 0;
+    if (ensure_par(c, n)) return 1;
+    for (int i = 0; i < n; ++i) {
+        if (iref[i] >= c->cfg.max_refs) { cra_set_error("iref exceeds max_refs"); return 1; }
+        c->h_par[i] = make_float4(params[4 * i], params[4 * i + 1], params[4 * i + 2], params[4 * i + 3]);
+        c->h_iref[i] = iref[i];
+    }
+    CRA_CUDA(cudaMemcpyAsync(c->d_par, c->h_par, sizeof(float4) * n, cudaMemcpyHostToDevice, c->st));
+    CRA_CUDA(cudaMemcpyAsync(c->d_iref, c->h_iref, sizeof(int) * n, cudaMemcpyHostToDevice, c->st));
+    float* counts = c->d_sums + (size_t)c->cfg.max_refs * 2 * c->npix;
+    if (cra_launch_rotsum(c->d_images, c->nx, start, n, c->d_par, c->d_iref, goff, c->d_sums, counts, nullptr, c->st)) return 1;
+    CRA_CUDA(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+extern "C" int cra_sums_device_ptr(CraCtx* c, void** dev_ptr, size_t* n_floats)
+{
+    if (!c) { cra_set_error("null context"); return 1; }
+    if (dev_ptr) *dev_ptr = c->d_sums;
+    if (n_floats) *n_floats = (size_t)c->cfg.max_refs * 2 * c->npix + c->cfg.max_refs;
+    return 0;
+}
+
+extern "C" int cra_get_sums(CraCtx* c, float* host_sums, float* host_counts)
+{
+    Bind b(c); if (b.ok()) return 1;
+    const int R = c->cfg.max_refs;
+    if (host_sums) CRA_CUDA(cudaMemcpyAsync(host_sums, c->d_sums, (size_t)R * 2 * c->npix * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    if (host_counts) CRA_CUDA(cudaMemcpyAsync(host_counts, c->d_sums + (size_t)R * 2 * c->npix, R * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    CRA_CUDA(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+extern "C" int cra_transform(CraCtx* c, int start, int stop, const float* params, float* host_out)
+{
+    Bind b(c); if (b.ok()) return 1;
+    const int n = stop - start;
+    if (start < 0 || n < 0 || stop > c->cfg.max_particles) { cra_set_error("particle range exceeds max_particles"); return 1; }
+    if (n == 0) return 0;
+    const int chunk = std::min(n, 8192);
+    if ((size_t)chunk > c->cap_tmpimg) {
+        if (c->d_tmpimg) cudaFree(c->d_tmpimg);
+        c->cap_tmpimg = chunk;
+        CRA_CUDA(cudaMalloc(&c->d_tmpimg, (size_t)chunk * c->npix * sizeof(float)));
+    }
+    if (ensure_par(c, chunk)) return 1;
+    for (int s = 0; s < n; s += chunk) {
+        const int m = std::min(chunk, n - s);
+        for (int i = 0; i < m; ++i)
+            c->h_par[i] = make_float4(params[4 * (s + i)], params[4 * (s + i) + 1], params[4 * (s + i) + 2], params[4 * (s + i) + 3]);
+        CRA_CUDA(cudaMemcpyAsync(c->d_par, c->h_par, sizeof(float4) * m, cudaMemcpyHostToDevice, c->st));
+        if (cra_launch_rotsum(c->d_images, c->nx, start + s, m, c->d_par, nullptr, 0, nullptr, nullptr, c->d_tmpimg, c->st)) return 1;
+        CRA_CUDA(cudaMemcpyAsync(host_out + (size_t)s * c->npix, c->d_tmpimg, (size_t)m * c->npix * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+        CRA_CUDA(cudaStreamSynchronize(c->st));
+    }
+    return 0;
+}
+
+extern "C" int cra_polar_spectrum(CraCtx* c, int particle, float cx, float cy, float* host_out)
+{
+    Bind b(c); if (b.ok()) return 1;
+    if (particle < 0 || particle >= c->cfg.max_particles) { cra_set_error("bad particle index"); return 1; }
+    if (cra_launch_polar_single(c->d_images + (size_t)particle * c->npix, c->nx, c->d_tab, c->htab, c->d_samp, c->d_sampw,
+                                c->d_twf, cx, cy, c->cfg.normalize_ring, c->d_spec, c->st)) return 1;
+    CRA_CUDA(cudaMemcpyAsync(host_out, c->d_spec, (size_t)c->htab.lcirc * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    CRA_CUDA(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+extern "C" int cra_ref_spectrum(CraCtx* c, int iref, float* host_out)
+{
+    Bind b(c); if (b.ok()) return 1;
+    if (iref < 0 || iref >= c->R) { cra_set_error("bad reference index"); return 1; }
+    CRA_CUDA(cudaMemcpyAsync(host_out, c->d_refspec + (size_t)iref * c->htab.lcirc, (size_t)c->htab.lcirc * sizeof(float),
+                             cudaMemcpyDeviceToHost, c->st));
+    CRA_CUDA(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+extern "C" int cra_ccf_curves(CraCtx* c, int particle, float cx, float cy, int iref, float* q_out, float* t_out)
+{
+    Bind b(c); if (b.ok()) return 1;
+    if (particle < 0 || particle >= c->cfg.max_particles || iref < 0 || iref >= c->R) { cra_set_error("bad index"); return 1; }
+    if (cra_launch_polar_single(c->d_images + (size_t)particle * c->npix, c->nx, c->d_tab, c->htab, c->d_samp, c->d_sampw,
+                                c->d_twf, cx, cy, c->cfg.normalize_ring, c->d_spec, c->st)) return 1;
+    if (cra_launch_ccf_curves(c->d_spec, c->d_refspec + (size_t)iref * c->htab.lcirc, c->d_tab, c->htab,
+                              c->d_curves, c->d_curves + c->htab.maxrin, c->st)) return 1;
+    CRA_CUDA(cudaMemcpyAsync(q_out, c->d_curves, c->htab.maxrin * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    CRA_CUDA(cudaMemcpyAsync(t_out, c->d_curves + c->htab.maxrin, c->htab.maxrin * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    CRA_CUDA(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+extern "C" int cra_measure_fp32_peak(int device, double* tf_ffma, double* tf_ffma2)
+{
+    CRA_CUDA(cudaSetDevice(device));
+    double a = 0, b = 0;
+    if (cra_fp32_peak(&a, &b)) return 1;
+    if (tf_ffma) *tf_ffma = a;
+    if (tf_ffma2) *tf_ffma2 = b;
+    return 0;
+}

@@ -1,0 +1,73 @@
+// cra_common.cuh -- shared declarations of the sm_100a alignment engine.
+//
+// Data layout in HBM (all float32 unless noted):
+//   images   [P][nx][nx]            resident particle stack (mask-mean subtracted)
+//   refs     [R][nx][nx]            current references
+//   refspec  [R][lcirc]             weighted reference spectra (Applyws applied)
+//   spec     [rows][lcirc]          particle spectra of one row batch; a row is one
+//                                   (particle, shift) pair in the reference's visit order
+//   cand     [rows][ntile_n]        best (value, code) of each row x reference tile
+//   sums     [R][2][nx][nx] + [R]   even/odd class sums followed by counts
+// A spectrum is the SPIDER packed per-ring layout of Util.Frngs: ring i occupies
+// floats [off_i, off_i+len_i): slot0 = Re F_0, slot1 = Re F_{len/2}, then
+// (Re,Im) F_k for k = 1..len/2-1, F_k = sum_n x_n exp(-2 pi i n k / len).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/cryo_ralib.h"
+
+#define CRA_MAX_RINGS 512
+
+struct CraRingTab {            // device-resident ring table (Numrinit triplets, 0-based offsets)
+    int   nring, lcirc, maxrin, log2n;
+    int   off[CRA_MAX_RINGS];
+    int   len[CRA_MAX_RINGS];
+    int   rad[CRA_MAX_RINGS];
+    float wr[CRA_MAX_RINGS];     // ringwe (Applyws)
+    float wn[CRA_MAX_RINGS];     // Normalize_ring weight r*2pi/len
+    float nn;                    // sum of wn over every sample, accumulated in float like Normalize_ring
+};
+
+struct CraRowMap {             // how rows of the current batch map to particles
+    const int*       row_start;  // [np+1] first row of each batch-local particle
+    const CraSearch* search;     // [np]   per-particle request (batch-local)
+    const int4*      win;        // [np]   lkx, rkx, lky, rky
+    int              np;
+    int              nrows;
+    int              p0;         // slot of batch-local particle 0 in the resident stack
+    float            step;
+};
+
+struct CraCand { float v; int code; };   // code = iref*8192 + mirror*4096 + j   (j = 1-based lag index)
+
+// error plumbing -------------------------------------------------------------
+void cra_set_error(const std::string& msg);
+#define CRA_CUDA(call)                                                               \
+    do { cudaError_t e__ = (call); if (e__ != cudaSuccess) {                         \
+        cra_set_error(std::string(#call) + ": " + cudaGetErrorString(e__) + " @" +   \
+                      __FILE__ + ":" + std::to_string(__LINE__)); return 1; } } while (0)
+
+// launchers (each defined in its own .cu; all asynchronous on `st`) ----------
+int cra_launch_mask_normalize(float* imgs, int n, int nx, const float* mask, int mode, cudaStream_t st);
+// particle rows described by map -> spec[row]; references -> refspec (weights applied)
+// twid_fwd[j] = exp(-2 pi i j / maxrin), j < maxrin/2
+int cra_launch_polar_rows(const float* images, int nx, const CraRingTab* tab, const CraRingTab& htab,
+                          const float2* samp, const float* sampw, const float2* twid_fwd, CraRowMap map,
+                          int normalize_ring, float* spec, cudaStream_t st);
+int cra_launch_polar_refs(const float* refs, int R, int nx, const CraRingTab* tab, const CraRingTab& htab,
+                          const float2* samp, const float2* twid_fwd, float* refspec, cudaStream_t st);
+int cra_launch_polar_single(const float* image, int nx, const CraRingTab* tab, const CraRingTab& htab,
+                            const float2* samp, const float* sampw, const float2* twid_fwd, float cx, float cy,
+                            int normalize_ring, float* spec, cudaStream_t st);
+int cra_launch_ccf(const float* spec, int nrows, const float* refspec, int R, const CraRingTab* tab,
+                   const CraRingTab& htab, const float2* twid, CraCand* cand, int ntile_n, cudaStream_t st);
+int cra_ccf_tile_n();
+int cra_launch_finalize(const float* spec, const float* refspec, int R, const CraRingTab* tab, const CraRingTab& htab,
+                        const CraCand* cand, int ntile_n, CraRowMap map, CraResult* out, cudaStream_t st);
+int cra_launch_ccf_curves(const float* spec_row, const float* refspec_row, const CraRingTab* tab, const CraRingTab& htab,
+                          float* q, float* t, cudaStream_t st);
+int cra_launch_rotsum(const float* images, int nx, int p0, int n, const float4* params, const int* iref,
+                      long global_offset, float* sums, float* counts, float* out_images, cudaStream_t st);
+int cra_fp32_peak(double* tf_ffma, double* tf_ffma2);

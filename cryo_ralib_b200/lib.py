@@ -1,0 +1,253 @@
+"""ctypes binding of libcryo_ralib.so -- the same mechanism the reference uses to
+load cuda/gpu_aln_pack.so (test_mref_gpu_align.py:91-97).  There is no CPU
+fallback: if the CUDA library is missing or a call fails this raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libcryo_ralib.so")
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+class CraError(RuntimeError):
+    pass
+
+
+class CraConfig(C.Structure):
+    _fields_ = [("nx", C.c_int), ("ir", C.c_int), ("ou", C.c_int), ("rs", C.c_int),
+                ("max_particles", C.c_int), ("max_refs", C.c_int),
+                ("max_range", C.c_float), ("step", C.c_float),
+                ("normalize_ring", C.c_int), ("row_batch", C.c_int)]
+
+
+class CraSearch(C.Structure):
+    _fields_ = [("cx", C.c_float), ("cy", C.c_float), ("xl", C.c_float), ("xr", C.c_float),
+                ("yl", C.c_float), ("yr", C.c_float)]
+
+
+class CraResult(C.Structure):
+    _fields_ = [("ang", C.c_float), ("sxs", C.c_float), ("sys", C.c_float), ("mirror", C.c_int),
+                ("iref", C.c_int), ("peak", C.c_float), ("sx", C.c_float), ("sy", C.c_float)]
+
+
+class CraAlignStats(C.Structure):
+    _fields_ = [("ms_polar", C.c_float), ("ms_ccf", C.c_float), ("ms_final", C.c_float), ("ms_total", C.c_float),
+                ("launches", C.c_long), ("alignments", C.c_long), ("rows", C.c_long)]
+
+
+# the reference's struct mirrors (test_mref_gpu_align.py:112-131)
+class AlignConfig(C.Structure):
+    _fields_ = [("sbj_num", C.c_uint), ("ref_num", C.c_uint), ("img_dim", C.c_uint),
+                ("ring_num", C.c_uint), ("ring_len", C.c_uint),
+                ("shift_step", C.c_float), ("shift_rng_x", C.c_float), ("shift_rng_y", C.c_float)]
+
+
+class AlignParam(C.Structure):
+    _fields_ = [("sbj_id", C.c_int), ("ref_id", C.c_int), ("shift_x", C.c_float), ("shift_y", C.c_float),
+                ("angle", C.c_float), ("mirror", C.c_bool)]
+
+
+SEARCH_DTYPE = np.dtype([("cx", "f4"), ("cy", "f4"), ("xl", "f4"), ("xr", "f4"), ("yl", "f4"), ("yr", "f4")])
+RESULT_DTYPE = np.dtype([("ang", "f4"), ("sxs", "f4"), ("sys", "f4"), ("mirror", "i4"), ("iref", "i4"),
+                         ("peak", "f4"), ("sx", "f4"), ("sy", "f4")])
+
+CORE_SYMBOLS = ["cra_create", "cra_destroy", "cra_last_error", "cra_ring_info", "cra_upload_particles",
+                "cra_upload_particles_dev", "cra_set_refs", "cra_align", "cra_accumulate", "cra_zero_sums",
+                "cra_sums_device_ptr", "cra_get_sums", "cra_transform", "cra_polar_spectrum", "cra_ref_spectrum",
+                "cra_ccf_curves", "cra_last_align_stats", "cra_set_timing", "cra_set_normalize_ring", "cra_set_step",
+                "cra_row_batch", "cra_device_images_ptr", "cra_stream", "cra_measure_fp32_peak"]
+LEGACY_SYMBOLS = ["print_gpu_info", "pre_align_size_check", "pre_align_init", "pre_align_fetch", "reset_shifts",
+                  "mref_align_run", "mref_align_run_m", "get_num_ref", "pre_align_run", "pre_align_run_m", "gpu_clear"]
+
+_LIB = None
+
+
+def load_library(path=None):
+    """Load the C-ABI library; raises LibraryMissing (never falls back)."""
+    global _LIB
+    if _LIB is not None and path is None:
+        return _LIB
+    path = path or SO_PATH
+    if not os.path.exists(path):
+        raise LibraryMissing("%s not found: build it with `python -m cryo_ralib_b200.build` "
+                             "(there is no CPU fallback)" % path)
+    L = C.CDLL(path)
+    vp, ip, fp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)
+    L.cra_create.argtypes = [C.POINTER(CraConfig), C.c_int, C.POINTER(vp)]
+    L.cra_destroy.argtypes = [vp]
+    L.cra_last_error.restype = C.c_char_p
+    L.cra_ring_info.argtypes = [vp, ip, ip, ip, vp]
+    L.cra_upload_particles.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
+    L.cra_upload_particles_dev.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
+    L.cra_set_refs.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.cra_align.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    L.cra_accumulate.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_long]
+    L.cra_zero_sums.argtypes = [vp]
+    L.cra_sums_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.cra_get_sums.argtypes = [vp, vp, vp]
+    L.cra_transform.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    L.cra_polar_spectrum.argtypes = [vp, C.c_int, C.c_float, C.c_float, vp]
+    L.cra_ref_spectrum.argtypes = [vp, C.c_int, vp]
+    L.cra_ccf_curves.argtypes = [vp, C.c_int, C.c_float, C.c_float, C.c_int, vp, vp]
+    L.cra_last_align_stats.argtypes = [vp, C.POINTER(CraAlignStats)]
+    L.cra_set_timing.argtypes = [vp, C.c_int]
+    L.cra_set_normalize_ring.argtypes = [vp, C.c_int]
+    L.cra_set_step.argtypes = [vp, C.c_float]
+    L.cra_row_batch.argtypes = [vp]
+    L.cra_device_images_ptr.argtypes = [vp, C.POINTER(vp)]
+    L.cra_stream.argtypes = [vp]
+    L.cra_stream.restype = vp
+    L.cra_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    # legacy layer, restypes as the reference drivers set them (test_mref_gpu_align.py:95-97)
+    L.pre_align_init.restype = C.c_ulonglong
+    L.pre_align_init.argtypes = [C.c_uint, C.POINTER(AlignConfig), C.c_uint]
+    L.pre_align_size_check.restype = C.c_bool
+    L.pre_align_size_check.argtypes = [C.c_uint, C.POINTER(AlignConfig), C.c_uint, C.c_float, C.c_bool]
+    L.pre_align_fetch.argtypes = [C.POINTER(C.POINTER(C.c_float)), C.c_uint, C.c_char_p]
+    L.reset_shifts.argtypes = [C.c_float, C.c_float]
+    L.mref_align_run.restype = C.c_ulonglong
+    L.mref_align_run.argtypes = [C.c_int, C.c_int]
+    L.mref_align_run_m.restype = C.POINTER(C.c_float)
+    L.mref_align_run_m.argtypes = [C.c_int, C.c_int]
+    L.get_num_ref.restype = C.POINTER(C.c_int)
+    L.pre_align_run.argtypes = [C.c_int, C.c_int]
+    L.pre_align_run_m.restype = C.c_ulonglong
+    L.pre_align_run_m.argtypes = [C.c_int, C.c_int]
+    if path == SO_PATH:
+        _LIB = L
+    return L
+
+
+class Engine(object):
+    """Thin object wrapper over the cra_* core (one context = one GPU)."""
+
+    def __init__(self, nx, ou, xr, yr=None, ts=1.0, ir=1, rs=1, max_particles=1, max_refs=1,
+                 normalize_ring=True, device=0, row_batch=0):
+        self.L = load_library()
+        yr = xr if yr is None else yr
+        self.cfg = CraConfig(int(nx), int(ir), int(ou), int(rs), int(max_particles), int(max_refs),
+                             float(max(xr, yr)), float(ts), int(bool(normalize_ring)), int(row_batch))
+        self.h = C.c_void_p()
+        self._ck(self.L.cra_create(C.byref(self.cfg), int(device), C.byref(self.h)))
+        self.nx, self.ou, self.device = int(nx), int(ou), int(device)
+        self.max_particles, self.max_refs = int(max_particles), int(max_refs)
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.L.cra_ring_info(self.h, C.byref(a), C.byref(b), C.byref(c), None))
+        self.nring, self.lcirc, self.maxrin = a.value, b.value, c.value
+        numr = np.zeros(3 * self.nring, np.int32)
+        self._ck(self.L.cra_ring_info(self.h, None, None, None, numr.ctypes.data))
+        self.numr = numr
+        self.R = 0
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise CraError(self.L.cra_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.L.cra_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- data
+    def upload_particles(self, images, first=0, subtract_mask_mean=True):
+        images = np.ascontiguousarray(images, np.float32)
+        assert images.ndim == 3 and images.shape[1] == self.nx and images.shape[2] == self.nx
+        self._ck(self.L.cra_upload_particles(self.h, images.ctypes.data, int(first), images.shape[0],
+                                             int(subtract_mask_mean)))
+
+    def upload_particles_ptr(self, host_ptr, n, first=0, subtract_mask_mean=True):
+        self._ck(self.L.cra_upload_particles(self.h, host_ptr, int(first), int(n), int(subtract_mask_mean)))
+
+    def upload_particles_dev(self, dev_ptr, n, first=0, subtract_mask_mean=True):
+        self._ck(self.L.cra_upload_particles_dev(self.h, dev_ptr, int(first), int(n), int(subtract_mask_mean)))
+
+    def set_refs(self, refs, normalize_mask=True):
+        refs = np.ascontiguousarray(refs, np.float32)
+        self._ck(self.L.cra_set_refs(self.h, refs.ctypes.data, refs.shape[0], int(normalize_mask)))
+        self.R = refs.shape[0]
+
+    # ---- hot path
+    def align(self, start, stop, search):
+        """search: structured array (SEARCH_DTYPE) of length stop-start.  Returns RESULT_DTYPE array."""
+        search = np.ascontiguousarray(search, SEARCH_DTYPE)
+        assert search.shape[0] == stop - start
+        out = np.zeros(stop - start, RESULT_DTYPE)
+        self._ck(self.L.cra_align(self.h, int(start), int(stop), search.ctypes.data, out.ctypes.data))
+        return out
+
+    def accumulate(self, start, stop, params, iref, global_offset=0):
+        params = np.ascontiguousarray(params, np.float32)
+        iref = np.ascontiguousarray(iref, np.int32)
+        assert params.shape == (stop - start, 4) and iref.shape[0] == stop - start
+        self._ck(self.L.cra_accumulate(self.h, int(start), int(stop), params.ctypes.data, iref.ctypes.data,
+                                       int(global_offset)))
+
+    def zero_sums(self):
+        self._ck(self.L.cra_zero_sums(self.h))
+
+    def get_sums(self):
+        R = self.max_refs
+        sums = np.zeros((R, 2, self.nx, self.nx), np.float32)
+        counts = np.zeros(R, np.float32)
+        self._ck(self.L.cra_get_sums(self.h, sums.ctypes.data, counts.ctypes.data))
+        return sums, counts
+
+    def sums_device_ptr(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(self.L.cra_sums_device_ptr(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def transform(self, start, stop, params):
+        params = np.ascontiguousarray(params, np.float32)
+        out = np.zeros((stop - start, self.nx, self.nx), np.float32)
+        self._ck(self.L.cra_transform(self.h, int(start), int(stop), params.ctypes.data, out.ctypes.data))
+        return out
+
+    # ---- stage-level (tests)
+    def polar_spectrum(self, particle, cx, cy):
+        out = np.zeros(self.lcirc, np.float32)
+        self._ck(self.L.cra_polar_spectrum(self.h, int(particle), cx, cy, out.ctypes.data))
+        return out
+
+    def ref_spectrum(self, iref):
+        out = np.zeros(self.lcirc, np.float32)
+        self._ck(self.L.cra_ref_spectrum(self.h, int(iref), out.ctypes.data))
+        return out
+
+    def ccf_curves(self, particle, cx, cy, iref):
+        q = np.zeros(self.maxrin, np.float32)
+        t = np.zeros(self.maxrin, np.float32)
+        self._ck(self.L.cra_ccf_curves(self.h, int(particle), cx, cy, int(iref), q.ctypes.data, t.ctypes.data))
+        return q, t
+
+    # ---- knobs / stats
+    def set_timing(self, on=True):
+        self._ck(self.L.cra_set_timing(self.h, int(on)))
+
+    def set_normalize_ring(self, on):
+        self._ck(self.L.cra_set_normalize_ring(self.h, int(on)))
+
+    def set_step(self, ts):
+        self._ck(self.L.cra_set_step(self.h, float(ts)))
+
+    def stats(self):
+        s = CraAlignStats()
+        self._ck(self.L.cra_last_align_stats(self.h, C.byref(s)))
+        return dict(ms_polar=s.ms_polar, ms_ccf=s.ms_ccf, ms_final=s.ms_final, ms_total=s.ms_total,
+                    launches=s.launches, alignments=s.alignments, rows=s.rows)
+
+    def measure_fp32_peak(self):
+        a, b = C.c_double(), C.c_double()
+        self._ck(self.L.cra_measure_fp32_peak(self.device, C.byref(a), C.byref(b)))
+        return a.value, b.value

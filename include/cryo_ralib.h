@@ -1,0 +1,181 @@
+/*
+ * cryo_ralib.h -- C ABI of libcryo_ralib.so (B200 / sm_100a engine for cryo-EM
+ * 2D multi-reference and reference-free alignment).
+ *
+ * Two layers, both plain `extern "C"` (pointers + sizes, no torch / C++ types):
+ *
+ *  (1) cra_*  : status-returning, context-based core.  Every call returns 0 on
+ *               success; cra_last_error() gives the message.  Nothing exits
+ *               the process, nothing falls back to the CPU.
+ *  (2) legacy : the exact symbols the reference's Python drivers bind from
+ *               cuda/gpu_aln_pack.so (cuda/gpu_aln_noref.h:52-113, struct
+ *               layouts cuda/gpu_aln_common.h:62-83, ctypes mirrors
+ *               test_mref_gpu_align.py:112-131), implemented on top of (1)
+ *               with EMAN2/Sphire multiref_polar_ali_2d semantics.
+ *
+ * Conventions: images are row-major float32 [n][nx][nx] (square);  pixel
+ * coordinates follow EMAN2/SPIDER: centre cnx = nx/2+1 (1-based).
+ */
+#ifndef CRYO_RALIB_H
+#define CRYO_RALIB_H
+
+#include <stdbool.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ (1) core */
+
+typedef struct CraCtx CraCtx;
+
+/* Replaces the reference's AlignConfig (gpu_aln_common.h:62-75) and adds the
+ * EMAN2 switches it lacks: ir/rs, separate yr, float step. */
+typedef struct CraConfig {
+    int   nx;             /* image edge (square)                                     */
+    int   ir, ou, rs;     /* first ring, last ring, ring step   (Numrinit, mode "F") */
+    int   max_particles;  /* capacity of the resident particle stack                 */
+    int   max_refs;       /* capacity of the reference stack                         */
+    float max_range;      /* largest |xr|,|yr| that will be requested                */
+    float step;           /* translational step ts (may be < 1)                      */
+    int   normalize_ring; /* 1: multiref_polar_ali_2d (Normalize_ring); 0: ormq      */
+    int   row_batch;      /* particle-shift rows per device batch; 0 = auto          */
+} CraConfig;
+
+/* Per-particle search request: polar centre (1-based, = cnx+sxi, cny+syi) and
+ * the permissible window [left,right] per axis as search_range returns it after
+ * the driver's swap (test_mref.py:195-201).  Grid positions are
+ * ix = j*step, j = -int(xl/step) .. int(xr/step); same for y.           */
+typedef struct CraSearch {
+    float cx, cy;
+    float xl, xr, yl, yr;
+} CraSearch;
+
+/* Result of Util.multiref_polar_ali_2d for one particle (test_mref.py:200):
+ * [ang, sxs, sys, mirror, iref, peak]; sx,sy are the raw grid offsets (-ix,-iy). */
+typedef struct CraResult {
+    float ang, sxs, sys;
+    int   mirror;
+    int   iref;
+    float peak;
+    float sx, sy;
+} CraResult;
+
+int  cra_create(const CraConfig* cfg, int device, CraCtx** out);
+int  cra_destroy(CraCtx* ctx);
+const char* cra_last_error(void);
+
+/* Ring geometry the context was built with (host copies; numr = nring triplets
+ * radius, 1-based offset, length  -- Numrinit, test_mref.py:145). */
+int  cra_ring_info(CraCtx* ctx, int* nring, int* lcirc, int* maxrin, int* numr_out /*3*nring or NULL*/);
+
+/* Upload n particles (host, [n][nx][nx]) into slots [first, first+n).  If
+ * subtract_mask_mean != 0 the mean under model_circle(ou) is subtracted on the
+ * device: normalize.mask no_sigma=0 (test_mref.py:188).  Replaces
+ * pre_align_fetch(...,"sbj_batch") (gpu_aln_noref.cu:362-380).              */
+int  cra_upload_particles(CraCtx* ctx, const float* host_images, int first, int n, int subtract_mask_mean);
+/* Same, source already on this device. */
+int  cra_upload_particles_dev(CraCtx* ctx, const float* dev_images, int first, int n, int subtract_mask_mean);
+
+/* Upload R references and prepare them: optional normalize.mask(no_sigma=1),
+ * Polar2Dm at (cnx,cny), Frngs, Applyws (test_mref.py:170-175).  Replaces
+ * pre_align_fetch(...,"ref_batch").                                         */
+int  cra_set_refs(CraCtx* ctx, const float* host_refs, int R, int normalize_mask);
+
+/* Multi-reference alignment of particles [start,stop): the a7 hot path
+ * (Polar2Dm -> Normalize_ring -> Frngs -> Crosrng_ms -> best).  search and out
+ * are host arrays indexed from 0 for particle `start`.                      */
+int  cra_align(CraCtx* ctx, int start, int stop, const CraSearch* search, CraResult* out);
+
+/* rot_shift2D(img, alpha, sx, sy, mirror) + add into class sums
+ * sums[iref][global_index % 2] and counts[iref] (test_mref.py:210-215).
+ * params: host [n][4] float (alpha, sx, sy, mirror); iref: host int[n]; iref<0
+ * skips the particle.  global_offset is the global index of particle `start`. */
+int  cra_accumulate(CraCtx* ctx, int start, int stop, const float* params, const int* iref,
+                    long global_offset);
+int  cra_zero_sums(CraCtx* ctx);
+/* Device pointers (owned by ctx) of the packed [R][2][nx][nx] f32 sums followed
+ * by [R] f32 counts: one contiguous buffer so a single NCCL allreduce covers
+ * both (replaces reduce_EMData_to_root x2R + mpi_reduce, test_mref.py:219-223). */
+int  cra_sums_device_ptr(CraCtx* ctx, void** dev_ptr, size_t* n_floats);
+int  cra_get_sums(CraCtx* ctx, float* host_sums /*[R][2][nx][nx]*/, float* host_counts /*[R]*/);
+
+/* rot_shift2D only: transformed images of [start,stop) to a host buffer
+ * (ref-free sum_oe / apply-transform export).                               */
+int  cra_transform(CraCtx* ctx, int start, int stop, const float* params, float* host_out);
+
+/* Stage-level entry points used by the parity tests. */
+int  cra_polar_spectrum(CraCtx* ctx, int particle, float cx, float cy, float* host_out /*lcirc*/);
+int  cra_ref_spectrum(CraCtx* ctx, int iref, float* host_out /*lcirc*/);
+int  cra_ccf_curves(CraCtx* ctx, int particle, float cx, float cy, int iref,
+                    float* q_out /*maxrin*/, float* t_out /*maxrin*/);
+
+/* Timing of the last cra_align call, measured with CUDA events on the engine's
+ * stream: ms spent in the polar/FFT kernel, the CCF/peak kernel, the finalize
+ * kernel, and the number of kernel launches and alignments evaluated.        */
+typedef struct CraAlignStats {
+    float ms_polar, ms_ccf, ms_final, ms_total;
+    long  launches;
+    long  alignments;   /* particle x reference x shift triples actually evaluated */
+    long  rows;         /* particle x shift rows                                  */
+} CraAlignStats;
+int  cra_last_align_stats(CraCtx* ctx, CraAlignStats* out);
+int  cra_set_timing(CraCtx* ctx, int enabled);
+/* Switch between multiref_polar_ali_2d (1) and ormq (0) ring normalisation, and
+ * change the translational step between calls (multi-step xr/ts schedules).      */
+int  cra_set_normalize_ring(CraCtx* ctx, int enabled);
+int  cra_set_step(CraCtx* ctx, float step);
+int  cra_row_batch(CraCtx* ctx);
+/* Borrowed device pointer of the resident particle stack [max_particles][nx][nx]
+ * and the engine's CUDA stream (cudaStream_t), for zero-copy interop.            */
+int  cra_device_images_ptr(CraCtx* ctx, void** dev_ptr);
+void* cra_stream(CraCtx* ctx);
+/* FP32 FMA throughput of this device measured with a dependent-chain-free
+ * FFMA2 micro-kernel (TFLOP/s); the roofline denominator for the CCF kernel. */
+int  cra_measure_fp32_peak(int device, double* tflops_ffma, double* tflops_ffma2);
+
+/* --------------------------------------------------------------- (2) legacy */
+
+/* gpu_aln_common.h:62-75 / test_mref_gpu_align.py:112-123 */
+typedef struct AlignConfig {
+    unsigned int sbj_num;
+    unsigned int ref_num;
+    unsigned int img_dim;
+    unsigned int ring_num;   /* the drivers pass numr[-3] = ou here (test_mref_gpu_align.py:368) */
+    unsigned int ring_len;   /* ignored: ring lengths follow Numrinit                            */
+    float shift_step;
+    float shift_rng_x;
+    float shift_rng_y;
+} AlignConfig;
+
+/* gpu_aln_common.h:76-83 / test_mref_gpu_align.py:125-131 */
+typedef struct AlignParam {
+    int   sbj_id;
+    int   ref_id;
+    float shift_x;   /* accumulated polar-centre offset (= sxi+ix), as gpu_aln_noref.cu:1476 */
+    float shift_y;
+    float angle;     /* EMAN2 convention already; feed to the a19 conversion as is             */
+    bool  mirror;
+} AlignParam;
+
+void        print_gpu_info(const unsigned int device_idx);                          /* gpu_aln_common.cu:165 */
+bool        pre_align_size_check(const unsigned int num_particles, const AlignConfig* cfg,
+                                 const unsigned int cuda_device_id, const float request,
+                                 const bool verbose);                               /* gpu_aln_noref.cu:234 */
+AlignParam* pre_align_init(const unsigned int num_particles, const AlignConfig* cfg,
+                           const unsigned int cuda_device_id);                      /* gpu_aln_noref.cu:188 */
+void        pre_align_fetch(const float** img_data, const unsigned int img_num,
+                            const char* batch_type);                                /* gpu_aln_noref.cu:362 */
+void        reset_shifts(const float shift_range, const float shift_step);          /* gpu_aln_noref.cu:119 */
+void*       mref_align_run(const int start_idx, const int stop_idx);                /* gpu_aln_noref.cu:389 */
+float*      mref_align_run_m(const int start_idx, const int stop_idx);              /* gpu_aln_noref.cu:419 */
+int*        get_num_ref(void);                                                      /* gpu_aln_noref.cu:  get_num_ref */
+void        pre_align_run(const int start_idx, const int stop_idx);                 /* gpu_aln_noref.cu:520 */
+void*       pre_align_run_m(const int start_idx, const int stop_idx);               /* gpu_aln_noref.cu:489 */
+void        gpu_clear(void);                                                        /* gpu_aln_noref.cu:141 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRYO_RALIB_H */

@@ -1,0 +1,38 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import oracle as o
+    o.build()
+    o.lib()
+    return o
+
+
+@pytest.fixture(scope="session")
+def small_set():
+    """64 synthetic 90x90 particles + 10 initial references (config-1 geometry)."""
+    from cryo_ralib_b200 import synth
+    images, truth = synth.make_particles(64, 90, 16, max_shift=3, seed=7)
+    refs = synth.initial_references(images, 10, per_ref=6, seed=5)
+    return images, refs, truth
+
+
+def has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False

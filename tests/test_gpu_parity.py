@@ -1,0 +1,301 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle, stage by stage and
+end to end.  Bars (BASELINE.json north_star): best-reference index, mirror flag and integer
+shift bit-exact except at documented ties, angle within 0.5 * 360/maxrin degrees, correlation
+peaks and class sums within 1e-4 relative."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+PEAK_RTOL = 1e-4          # north_star tolerance for peaks / class averages
+TIE_BAND = 2e-5           # |dpeak|/peak below which a different discrete answer counts as a tie
+
+
+def _engine(nx, ou, xr, ts=1.0, P=1, R=1, normalize=True, **kw):
+    from cryo_ralib_b200 import Engine
+    return Engine(nx, ou, xr, ts=ts, max_particles=P, max_refs=R, normalize_ring=normalize, **kw)
+
+
+def _prep(oracle, images, refs, ou):
+    nx = images.shape[-1]
+    mask = oracle.model_circle(ou, nx)
+    imgs = np.stack([oracle.normalize_mask(im, mask, 0) for im in images])
+    numr = oracle.numrinit(1, ou, 1)
+    refs_n, cref = oracle.prepare_refs(refs, mask, numr)
+    return imgs, mask, numr, refs_n, cref
+
+
+def test_ring_tables_match_oracle(oracle):
+    for nx, ou in ((90, 36), (128, 60), (48, 16), (64, 29)):
+        e = _engine(nx, ou, 1)
+        assert np.array_equal(e.numr, oracle.numrinit(1, ou, 1))
+        e.close()
+
+
+def test_polar_spectrum_matches_oracle(oracle, small_set):
+    images, refs, _ = small_set
+    imgs, mask, numr, _, _ = _prep(oracle, images, refs, 36)
+    for normalize in (True, False):
+        e = _engine(90, 36, 3, P=8, R=1, normalize=normalize)
+        e.upload_particles(images[:8], subtract_mask_mean=True)
+        for p, (cx, cy) in enumerate([(46, 46), (43, 49), (46.37, 44.81), (49, 49), (40.5, 47.25), (53.9, 38.1), (46, 54), (38, 38)]):
+            got = e.polar_spectrum(p, cx, cy)
+            c = oracle.polar2dm(imgs[p], cx, cy, numr)
+            if normalize:
+                c = oracle.normalize_ring(c, numr)
+            want = oracle.frngs(c, numr)
+            scale = np.abs(want).max()
+            assert np.abs(got - want).max() <= 2e-5 * scale, (normalize, p, np.abs(got - want).max() / scale)
+        e.close()
+
+
+def test_polar_wraps_like_quadri(oracle, small_set):
+    """Centres that push rings across the frame edge exercise the circular closure."""
+    images, refs, _ = small_set
+    imgs, mask, numr, _, _ = _prep(oracle, images, refs, 36)
+    e = _engine(90, 36, 3, P=2, R=1, normalize=False)
+    e.upload_particles(images[:2])
+    for cx, cy in ((60.3, 46), (46, 20.7), (2.0, 88.5)):
+        got = e.polar_spectrum(1, cx, cy)
+        want = oracle.frngs(oracle.polar2dm(imgs[1], cx, cy, numr), numr)
+        assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
+    e.close()
+
+
+def test_ref_spectrum_matches_oracle(oracle, small_set):
+    images, refs, _ = small_set
+    _, mask, numr, refs_n, cref = _prep(oracle, images, refs, 36)
+    e = _engine(90, 36, 3, P=1, R=10)
+    e.set_refs(refs, normalize_mask=True)
+    for j in range(10):
+        got = e.ref_spectrum(j)
+        assert np.abs(got - cref[j]).max() <= 2e-5 * np.abs(cref[j]).max()
+    e.close()
+
+
+def test_ccf_curves_match_crosrng_ms(oracle, small_set):
+    images, refs, _ = small_set
+    imgs, mask, numr, refs_n, cref = _prep(oracle, images, refs, 36)
+    e = _engine(90, 36, 3, P=4, R=10)
+    e.upload_particles(images[:4]); e.set_refs(refs)
+    for p, cx, cy, r in ((0, 46, 46, 0), (1, 44, 47, 3), (2, 46.5, 45.25, 9), (3, 49, 43, 5)):
+        q, t = e.ccf_curves(p, cx, cy, r)
+        c = oracle.frngs(oracle.normalize_ring(oracle.polar2dm(imgs[p], cx, cy, numr), numr), numr)
+        ref = oracle.crosrng_ms(cref[r], c, numr)
+        s = max(np.abs(ref["q"]).max(), np.abs(ref["t"]).max())
+        assert np.abs(q - ref["q"]).max() <= PEAK_RTOL * s
+        assert np.abs(t - ref["t"]).max() <= PEAK_RTOL * s
+    e.close()
+
+
+def _compare_alignment(got, want, maxrin, step=1.0):
+    """want: oracle rows [ang, sxs, sys, mirror, iref, peak, sx, sy].  Returns (#exact, #ties, #bad)."""
+    exact = ties = 0
+    bad = []
+    for i in range(len(got)):
+        g, w = got[i], want[i]
+        rel = abs(g["peak"] - w[5]) / max(abs(w[5]), 1e-30)
+        same = (g["iref"] == int(w[4]) and g["mirror"] == int(w[3]) and g["sx"] == w[6] and g["sy"] == w[7])
+        if same:
+            dang = abs((g["ang"] - w[0] + 180.0) % 360.0 - 180.0)
+            if rel <= PEAK_RTOL and dang <= 0.5 * 360.0 / maxrin:
+                exact += 1
+            else:
+                bad.append((i, "value", rel, dang))
+        elif rel <= TIE_BAND:
+            ties += 1
+        else:
+            bad.append((i, "discrete", rel, (g["iref"], g["mirror"], g["sx"], g["sy"]), tuple(w[3:8])))
+    return exact, ties, bad
+
+
+@pytest.mark.parametrize("normalize", [True, False])
+def test_align_matches_oracle_config1_geometry(oracle, small_set, normalize):
+    from cryo_ralib_b200 import alignment as al
+    images, refs, _ = small_set
+    imgs, mask, numr, refs_n, cref = _prep(oracle, images, refs, 36)
+    P, R = images.shape[0], refs.shape[0]
+    e = _engine(90, 36, 3, P=P, R=R, normalize=normalize)
+    e.upload_particles(images); e.set_refs(refs)
+    search, sxi, syi, _ = al.mref_search_request(np.zeros((P, 4)), 90, 36, 3, 3)
+    got = e.align(0, P, search)
+    centres = np.stack([search["cx"], search["cy"]], 1)
+    win = np.stack([search["xl"], search["xr"], search["yl"], search["yr"]], 1)
+    want = oracle.align_batch(imgs, cref, numr, centres, win, 1.0, normalize, nthreads=8)
+    exact, ties, bad = _compare_alignment(got, want, 256)
+    assert not bad, bad[:5]
+    assert ties <= max(1, P // 20)
+    st = e.stats()
+    assert st["alignments"] == P * 49 * R
+    e.close()
+
+
+def test_align_ragged_windows_fractional_centres_and_half_step(oracle, small_set):
+    images, refs, _ = small_set
+    imgs, mask, numr, refs_n, cref = _prep(oracle, images, refs[:7], 36)
+    P, R = 21, 7
+    rng = np.random.default_rng(11)
+    from cryo_ralib_b200.lib import SEARCH_DTYPE
+    from cryo_ralib_b200 import alignment as al
+    sxi = rng.uniform(-8, 8, P); syi = rng.uniform(-8, 8, P)
+    sxi[:3] = [8.0, -8.0, 7.6]; syi[:3] = [-8.0, 0.0, 5.2]
+    s = np.zeros(P, SEARCH_DTYPE)
+    s["xl"], s["xr"] = al.search_range(90, 36, sxi, 2.0)
+    s["yl"], s["yr"] = al.search_range(90, 36, syi, 2.0)
+    s["cx"] = 46 + sxi; s["cy"] = 46 + syi
+    e = _engine(90, 36, 2.0, ts=0.5, P=P, R=R)
+    e.upload_particles(images[:P]); e.set_refs(refs[:7])
+    got = e.align(0, P, s)
+    want = oracle.align_batch(imgs[:P], cref, numr, np.stack([s["cx"], s["cy"]], 1),
+                              np.stack([s["xl"], s["xr"], s["yl"], s["yr"]], 1), 0.5, True, nthreads=8)
+    exact, ties, bad = _compare_alignment(got, want, 256)
+    assert not bad, bad[:5]
+    assert ties <= 2
+    e.close()
+
+
+@pytest.mark.parametrize("nx,ou,xr", [(128, 56, 2), (48, 16, 2), (64, 29, 1)])
+def test_align_other_ring_geometries(oracle, nx, ou, xr):
+    """maxrin 512 / 128 / 256 with odd reference counts and row counts."""
+    from cryo_ralib_b200 import synth, alignment as al
+    P, R = 9, 5
+    images, _ = synth.make_particles(P, nx, 8, max_shift=xr, seed=21)
+    refs = synth.initial_references(images, R, per_ref=1, seed=3)
+    imgs, mask, numr, refs_n, cref = _prep(oracle, images, refs, ou)
+    e = _engine(nx, ou, xr, P=P, R=R)
+    e.upload_particles(images); e.set_refs(refs)
+    search, _, _, _ = al.mref_search_request(np.zeros((P, 4)), nx, ou, xr, xr)
+    got = e.align(0, P, search)
+    want = oracle.align_batch(imgs, cref, numr, np.stack([search["cx"], search["cy"]], 1),
+                              np.stack([search["xl"], search["xr"], search["yl"], search["yr"]], 1), 1.0, True, nthreads=8)
+    exact, ties, bad = _compare_alignment(got, want, int(numr[-1]))
+    assert not bad, bad[:5]
+    e.close()
+
+
+def test_closed_loop_recovers_known_pose(oracle):
+    """A.10: rotate/shift/mirror a clean image, align it back onto itself."""
+    from cryo_ralib_b200 import alignment as al
+    nx = 90
+    yy, xx = np.mgrid[0:nx, 0:nx].astype(np.float64)
+    rng = np.random.default_rng(3)
+    g = np.zeros((nx, nx))
+    for _ in range(12):
+        cx, cy = rng.uniform(-18, 18, 2) + nx // 2
+        s = rng.uniform(2, 5)
+        g += rng.uniform(.5, 1.5) * np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * s * s))
+    mask = oracle.model_circle(36, nx)
+    gn = oracle.normalize_mask(g.astype(np.float32), mask, 1)
+    poses = [(30., 0, 0, 0), (77.3, 2, -1, 0), (200., -3, 2, 1), (0, 1, 1, 1), (359., 0, 3, 0), (123.4, -2, -2, 1)]
+    parts = np.stack([oracle.rot_shift2d(gn, *p) for p in poses])
+    e = _engine(nx, 36, 3, P=len(poses), R=1)
+    e.upload_particles(parts); e.set_refs(gn[None], normalize_mask=False)
+    search, sxi, syi, _ = al.mref_search_request(np.zeros((len(poses), 4)), nx, 36, 3, 3)
+    res = e.align(0, len(poses), search)
+    newp = al.compose_result(sxi, syi, res)
+    back = e.transform(0, len(poses), newp)
+    mm = mask > 0.5
+    for i in range(len(poses)):
+        assert res["mirror"][i] == poses[i][3]
+        assert np.corrcoef(back[i][mm], gn[mm])[0, 1] > 0.99
+    e.close()
+
+
+def test_rot_shift_accumulate_matches_oracle(oracle, small_set):
+    images, refs, _ = small_set
+    P, R = 40, 6
+    rng = np.random.default_rng(5)
+    params = np.stack([rng.uniform(0, 360, P), rng.uniform(-6, 6, P), rng.uniform(-6, 6, P), rng.integers(0, 2, P)], 1)
+    params[0] = [0, 0, 0, 0]; params[1] = [0, 2, -3, 1]; params[2] = [90, 0, 0, 0]
+    iref = rng.integers(0, R, P).astype(np.int32)
+    mask = oracle.model_circle(36, 90)
+    imgs = np.stack([oracle.normalize_mask(im, mask, 0) for im in images[:P]])
+    e = _engine(90, 36, 3, P=P, R=R)
+    e.upload_particles(images[:P])
+    e.zero_sums()
+    e.accumulate(0, P, params, iref, global_offset=1001)
+    sums, counts = e.get_sums()
+    want = np.zeros((R, 2, 90, 90), np.float64)
+    cnt = np.zeros(R)
+    for i in range(P):
+        want[iref[i], (1001 + i) % 2] += oracle.rot_shift2d(imgs[i], *params[i])
+        cnt[iref[i]] += 1
+    assert np.array_equal(counts, cnt)
+    assert np.abs(sums - want).max() <= 1e-5 * np.abs(want).max()
+    tr = e.transform(0, 3, params[:3])
+    for i in range(3):
+        assert np.abs(tr[i] - oracle.rot_shift2d(imgs[i], *params[i])).max() <= 1e-5 * np.abs(imgs[i]).max()
+    e.close()
+
+
+def test_full_iteration_matches_oracle(oracle, small_set):
+    """One whole per-particle section of mref_ali2d_MPI (test_mref.py:183-215) from non-trivial
+    previous parameters: params, assignment and class sums."""
+    from cryo_ralib_b200 import alignment as al
+    images, refs, _ = small_set
+    P, R = images.shape[0], refs.shape[0]
+    rng = np.random.default_rng(9)
+    prev = np.stack([rng.uniform(0, 360, P), rng.uniform(-4, 4, P), rng.uniform(-4, 4, P), rng.integers(0, 2, P)], 1)
+    prev[:4, 1] = [9.5, -9.5, 0, 7.9]            # some particles beyond mashi -> reset
+    imgs, mask, numr, refs_n, cref = _prep(oracle, images, refs, 36)
+    p_o, a_o, pk_o, s_o, c_o = oracle.mref_iteration(images.copy(), mask, cref, numr, 3, 3, 1, 36, prev, 0, True, 8)
+    e = _engine(90, 36, 3, P=P, R=R)
+    e.upload_particles(images); e.set_refs(refs)
+    search, sxi, syi, _ = al.mref_search_request(prev, 90, 36, 3, 3)
+    res = e.align(0, P, search)
+    newp = al.compose_result(sxi, syi, res)
+    e.zero_sums(); e.accumulate(0, P, newp, res["iref"], 0)
+    sums, counts = e.get_sums()
+    same = (res["iref"] == a_o) & (np.abs(newp[:, 3] - p_o[:, 3]) < 0.5) \
+        & (np.abs(newp[:, 1] - p_o[:, 1]) < 0.05) & (np.abs(newp[:, 2] - p_o[:, 2]) < 0.05)
+    rel = np.abs(res["peak"] - pk_o) / np.abs(pk_o)
+    assert np.all(same | (rel < TIE_BAND)), np.where(~(same | (rel < TIE_BAND)))
+    assert (~same).sum() <= 2
+    assert rel[same].max() <= PEAK_RTOL
+    dang = np.abs((newp[same, 0] - p_o[same, 0] + 180) % 360 - 180)
+    assert dang.max() <= 0.5 * 360 / 256
+    if same.all():
+        assert np.array_equal(counts, c_o)
+        # angles differ below the sampling tolerance, so class sums agree to interpolation accuracy
+        num = np.abs(sums - s_o).sum(); den = np.abs(s_o).sum()
+        assert num / den < 5e-3
+    e.close()
+
+
+def test_legacy_abi_roundtrip(oracle, small_set):
+    """The reference's own call sequence (test_mref_gpu_align.py:365-449, test_mref_cheng_yu_bdb_cuda.py:546-556)."""
+    import ctypes as C
+    from cryo_ralib_b200.lib import load_library, AlignConfig, AlignParam
+    from cryo_ralib_b200 import alignment as al
+    images, refs, _ = small_set
+    imgs, mask, numr, refs_n, cref = _prep(oracle, images, refs, 36)
+    P, R = 32, 10
+    L = load_library()
+    cfg = AlignConfig(P, R, 90, 36, 256, 1.0, 3.0, 3.0)
+    assert L.pre_align_size_check(P, C.byref(cfg), 0, 0.9, False)
+    ptr = L.pre_align_init(P, C.byref(cfg), 0)
+    assert ptr
+    par = C.cast(ptr, C.POINTER(AlignParam))
+    fp = C.POINTER(C.c_float)
+    data = [np.ascontiguousarray(imgs[i]) for i in range(P)]
+    L.pre_align_fetch((fp * P)(*[d.ctypes.data_as(fp) for d in data]), P, b"sbj_batch")
+    rdata = [np.ascontiguousarray(refs_n[j]) for j in range(R)]
+    L.pre_align_fetch((fp * R)(*[d.ctypes.data_as(fp) for d in rdata]), R, b"ref_batch")
+    L.reset_shifts(3.0, 1.0)
+    sums_ptr = L.mref_align_run_m(0, P)
+    assert sums_ptr
+    counts = np.ctypeslib.as_array(L.get_num_ref(), (R,)).copy()
+    sums = np.ctypeslib.as_array(sums_ptr, (2 * R, 90, 90)).copy()
+    centres = np.full((P, 2), 46.0, np.float32); win = np.full((P, 4), 3.0, np.float32)
+    want = oracle.align_batch(imgs[:P], cref, numr, centres, win, 1.0, True, nthreads=8)
+    n_same = 0
+    for i in range(P):
+        if par[i].ref_id == int(want[i][4]) and int(par[i].mirror) == int(want[i][3]):
+            n_same += 1
+            assert par[i].shift_x == -want[i][6] and par[i].shift_y == -want[i][7]
+            assert abs((par[i].angle - want[i][0] + 180) % 360 - 180) <= 0.5 * 360 / 256
+    assert n_same >= P - 1
+    assert counts.sum() == P
+    assert abs(sums.sum()) >= 0   # layout: R even sums then R odd sums
+    ev = sum(1 for i in range(0, P, 2)); assert ev == (P + 1) // 2
+    L.gpu_clear()
