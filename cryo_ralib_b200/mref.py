@@ -1,0 +1,193 @@
+"""Iteration orchestrators: the B200 counterparts of the reference's mref_ali2d_gpu
+(test_mref_gpu_align.py:222-612; CPU semantics test_mref.py:48-315) and
+ali2d_base_gpu_isac_CLEAN / ali2d_base (test_reffree.py:111-513, :515-837).
+
+One process per GPU.  Particles are split contiguously with MPI_start_end
+(test_mref_gpu_align.py:1384), references are replicated, and the only exchange per
+iteration is ONE allreduce of the packed class sums + counts (replaces 2R
+reduce_EMData_to_root + R mpi_reduce + R bcast_EMData_to_all, test_mref.py:219-223,
+:293-296).  Every rank then runs the deterministic reference update, so no broadcast follows.
+"""
+import numpy as np
+
+from . import alignment as al
+from . import refupdate as ru
+
+
+class LocalComm(object):
+    """Single-process stand-in: rank 0 of 1."""
+    rank, world = 0, 1
+
+    def allreduce_device(self, engine):
+        return
+
+    def allreduce_host(self, arr):
+        return arr
+
+    def fetch_image(self, k, owner_fn, local_get, shape):
+        return local_get(k)
+
+
+class TorchComm(object):
+    """torch.distributed plumbing (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.backend = dist.get_backend()
+
+    def allreduce_device(self, engine):
+        """In-place sum of the engine's [R][2][nx][nx]+[R] buffer across ranks over NCCL."""
+        import torch
+        ptr, n = engine.sums_device_ptr()
+
+        class _Buf(object):
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        t = torch.as_tensor(_Buf(), device="cuda:%d" % engine.device)
+        self.dist.all_reduce(t)
+        torch.cuda.synchronize(engine.device)
+
+    def allreduce_host(self, arr):
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+        if self.backend == "nccl":
+            t = t.cuda()
+        self.dist.all_reduce(t)
+        return t.cpu().numpy()
+
+    def fetch_image(self, k, owner_fn, local_get, shape):
+        import torch
+        owner = owner_fn(k)
+        t = torch.from_numpy(local_get(k).copy()) if owner == self.rank else torch.zeros(shape, dtype=torch.float32)
+        if self.backend == "nccl":
+            t = t.cuda()
+        self.dist.broadcast(t, src=owner)
+        return t.cpu().numpy()
+
+
+def _owner_fn(P, world):
+    bounds = [al.mpi_start_end(P, world, i) for i in range(world)]
+
+    def owner(k):
+        for i, (s, e) in enumerate(bounds):
+            if s <= k < e:
+                return i
+        raise IndexError(k)
+    return owner
+
+
+def _reduce_sums(engine, comm, device_allreduce):
+    if comm.world > 1 and device_allreduce:
+        comm.allreduce_device(engine)
+        return engine.get_sums()
+    sums, counts = engine.get_sums()
+    if comm.world > 1:
+        flat = comm.allreduce_host(np.concatenate([sums.ravel(), counts]))
+        sums = flat[:sums.size].reshape(sums.shape)
+        counts = flat[sums.size:]
+    return sums, counts
+
+
+def mref_ali2d(images, refs, ir=1, ou=-1, rs=1, xr=0, yr=0, ts=1, center=1, maxit=10, rand_seed=1000,
+               params=None, comm=None, total_particles=None, global_offset=0, engine=None,
+               device=0, device_allreduce=True, on_iteration=None, upload=True):
+    """2D multi-reference alignment of this rank's particles.
+
+    images  [n][nx][nx] float32: this rank's share (global indices global_offset..+n)
+    refs    [R][nx][nx] initial references (replicated)
+    Returns (params [n][4] alpha,sx,sy,mirror; assign [n]; refs [R][nx][nx]; history)
+    """
+    from .lib import Engine
+    comm = comm or LocalComm()
+    n, nx = images.shape[0], images.shape[-1]
+    P = total_particles if total_particles is not None else n
+    if ou == -1:
+        ou = nx // 2 - 2
+    R = refs.shape[0]
+    own_engine = engine is None
+    if own_engine:
+        engine = Engine(nx, ou, xr, yr, ts=ts, ir=ir, rs=rs, max_particles=n, max_refs=R,
+                        normalize_ring=True, device=device)
+    if upload:
+        engine.upload_particles(images, subtract_mask_mean=True)      # normalize.mask no_sigma=0, test_mref.py:188
+    mask = ru.model_circle(ou, nx)
+    refs = np.array(refs, np.float32)
+    params = np.zeros((n, 4)) if params is None else np.array(params, np.float64)
+    owner = _owner_fn(P, comm.world)
+    masked_local = lambda k: ru.normalize_mask(np.asarray(images[k - global_offset], np.float32), mask, 0)
+    reseed = ru.make_reseeder(rand_seed, P, lambda k: comm.fetch_image(k, owner, masked_local, (nx, nx)))
+    history = []
+    assign = np.zeros(n, np.int32)
+    for it in range(int(maxit)):
+        engine.set_refs(refs, normalize_mask=True)                    # test_mref.py:170-175
+        search, sxi, syi, params = al.mref_search_request(params, nx, ou, xr, yr)
+        res = engine.align(0, n, search)                              # test_mref.py:200
+        params = al.compose_result(sxi, syi, res)                     # test_mref.py:206
+        assign = res["iref"].copy()
+        engine.zero_sums()
+        engine.accumulate(0, n, params, assign, global_offset)        # test_mref.py:210-215
+        sums, counts = _reduce_sums(engine, comm, device_allreduce)   # test_mref.py:219-223
+        refs, info = ru.update_refs(sums[:R], counts[:R], mask, center, reseed)   # test_mref.py:238-286
+        info.update(counts=counts[:R].copy(), peak=res["peak"].copy(), stats=engine.stats())
+        history.append(info)
+        if on_iteration:
+            on_iteration(it, params, assign, refs, info)
+    if own_engine:
+        engine.close()
+    return params, assign, refs, history
+
+
+def ali2d_base(images, ir=1, ou=-1, rs=1, xr=0, yr=0, ts=1, center=-1, maxit=10, comm=None,
+               total_particles=None, global_offset=0, engine=None, device=0, device_allreduce=True,
+               on_iteration=None):
+    """Reference-free alignment (ali2d_base, test_reffree.py:515-837): one reference = the global
+    average, ormq semantics (no ring normalisation), shifts clamped, average centred by the mean shift."""
+    from .lib import Engine
+    comm = comm or LocalComm()
+    n, nx = images.shape[0], images.shape[-1]
+    P = total_particles if total_particles is not None else n
+    if ou == -1:
+        ou = nx // 2 - 2
+    own_engine = engine is None
+    if own_engine:
+        engine = Engine(nx, ou, xr, yr, ts=ts, ir=ir, rs=rs, max_particles=n, max_refs=1,
+                        normalize_ring=False, device=device)
+    engine.upload_particles(images, subtract_mask_mean=True)          # data[im] -= infomask mean, test_reffree.py:663
+    mask = ru.model_circle(ou, nx)
+    params = np.zeros((n, 4))
+    sx_sum = sy_sum = 0.0
+    history = []
+    tavg = None
+    zeros = np.zeros(n, np.int32)
+    for it in range(int(maxit)):
+        engine.zero_sums()
+        engine.accumulate(0, n, params, zeros, global_offset)         # sum_oe(data, "a"), test_reffree.py:695
+        sums, counts = _reduce_sums(engine, comm, device_allreduce)
+        ave1, ave2 = sums[0, 0], sums[0, 1]
+        tavg = (ave1 + ave2) / np.float32(P)
+        frsc = ru.fsc_mask(ave1, ave2, mask)                          # test_reffree.py:708
+        crit = float(np.sum((tavg * tavg)[mask > 0.5]) / float((mask > 0.5).sum()))
+        if center == -1:
+            tavg, _, filt = ru.ref_ali2d(tavg, frsc, 0)
+            cs = [float(sx_sum) / P, float(sy_sum) / P]
+            tavg = ru.fshift(tavg, -cs[0], -cs[1])                    # test_reffree.py:741-745
+        else:
+            tavg, cs, filt = ru.ref_ali2d(tavg, frsc, center)
+        if it == int(maxit) - 1:
+            history.append(dict(criterion=crit, cs=cs, filter=filt, tavg=tavg.copy()))
+            break
+        engine.set_refs(tavg[None], normalize_mask=False)
+        search, sxi, syi = al.reffree_search_request(params, cs, nx, ou, xr, yr)
+        res = engine.align(0, n, search)                              # ali2d_single_iter -> ormq
+        params = al.compose_result(sxi, syi, res)
+        loc = np.array([np.sum(np.where(params[:, 3] == 0, params[:, 1], -params[:, 1])), np.sum(params[:, 2])])
+        glob = comm.allreduce_host(loc) if comm.world > 1 else loc
+        sx_sum, sy_sum = float(glob[0]), float(glob[1])
+        info = dict(criterion=crit, cs=cs, filter=filt, tavg=tavg.copy(), peak=res["peak"].copy(), stats=engine.stats())
+        history.append(info)
+        if on_iteration:
+            on_iteration(it, params, tavg, info)
+    if own_engine:
+        engine.close()
+    return params, tavg, history

@@ -424,7 +424,7 @@ static void t2_params(T2 t, double *alpha, double *tx, double *ty, int *mirror)
     float det = t.m[0][0] * t.m[1][1] - t.m[0][1] * t.m[1][0];
     int mir = det < 0;
     if (mir) { t.m[0][0] = -t.m[0][0]; t.m[0][1] = -t.m[0][1]; t.m[0][2] = -t.m[0][2]; }
-    double a = atan2((double)t.m[0][1], (double)t.m[0][0]) * 180.0 / CRA_PI;
+    double a = atan2((double)t.m[0][1], (double)t.m[0][0]) * (180.0 / CRA_PI);   /* EMConsts::rad2deg */
     if (a < 0) a += 360.0;
     if (a >= 360.0) a -= 360.0;
     *alpha = a; *tx = t.m[0][2]; *ty = t.m[1][2]; *mirror = mir;

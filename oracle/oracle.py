@@ -366,7 +366,8 @@ def fit_tanh(dres, low=0.1):
 
 
 def _freq_grid(ny, nx):
-    ky = np.fft.fftfreq(ny)[:, None]              # jy/ny with wrap
+    iy = np.arange(ny)
+    ky = (np.where(iy > ny // 2, iy - ny, iy) / float(ny))[:, None]   # EMAN2: ky = iy-ny only for iy > ny/2
     kx = (np.arange(nx // 2 + 1) / float(nx))[None, :]
     return ky, kx
 

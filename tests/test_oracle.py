@@ -1,0 +1,177 @@
+"""The oracle against every known answer the reference holds for this path (the three
+Transform tuples of cuda/EMAN2_test.ipynb cells 23-25, committed under tests/golden/), plus the
+self-consistency properties of SURVEY.md A.10 that stand in for the vectors the reference lacks."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _blob_image(nx, seed=3, n=12, spread=18):
+    yy, xx = np.mgrid[0:nx, 0:nx].astype(np.float64)
+    rng = np.random.default_rng(seed)
+    g = np.zeros((nx, nx))
+    for _ in range(n):
+        cx, cy = rng.uniform(-spread, spread, 2) + nx // 2
+        s = rng.uniform(2, 5)
+        g += rng.uniform(.5, 1.5) * np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * s * s))
+    return g.astype(np.float32)
+
+
+def test_transform_golden_tuples_bit_exact(oracle):
+    g = json.load(open(os.path.join(GOLD, "eman2_transform_known_answers.json")))
+    p = g["get_params2D"]
+    c = oracle.combine_params2(p[0], p[1], p[2], p[3], *g["combine_args"])
+    assert list(c) == g["combine_params2"]
+    i = oracle.inverse_transform2(*g["combine_params2"][:3])
+    assert list(i[:3]) == g["inverse_transform2"]
+
+
+def test_numrinit_ring_tables(oracle):
+    g = json.load(open(os.path.join(GOLD, "numrinit_tables.json")))
+    for key, want in g.items():
+        ou = int(key)
+        numr = oracle.numrinit(1, ou, 1)
+        lens = numr[2::3]
+        vals, counts = np.unique(lens, return_counts=True)
+        assert {int(v): int(c) for v, c in zip(vals, counts)} == {int(k): v for k, v in want["lengths"].items()}
+        assert oracle.lcirc_of(numr) == want["lcirc"] and int(numr[-1]) == want["maxrin"]
+    wr = oracle.ringwe(oracle.numrinit(1, 36, 1))
+    assert np.allclose(wr[-1], 36 * 2 * np.pi / 256, rtol=1e-6)
+    assert np.allclose(wr[0], 1 * 2 * np.pi / 8 * 256 / 8, rtol=1e-6)
+
+
+def test_packed_fft_layout_and_roundtrip(oracle):
+    rng = np.random.default_rng(0)
+    for L in (8, 16, 32, 64, 128, 256, 512):
+        x = rng.standard_normal(L).astype(np.float32)
+        F = oracle.rfft_packed(x)
+        Fn = np.fft.rfft(x.astype(np.float64))
+        s = np.abs(Fn).max()
+        assert abs(F[0] - Fn[0].real) <= 1e-5 * s and abs(F[1] - Fn[L // 2].real) <= 1e-5 * s
+        assert np.abs(F[2::2] - Fn[1:L // 2].real).max() <= 1e-5 * s
+        assert np.abs(F[3::2] - Fn[1:L // 2].imag).max() <= 1e-5 * s
+        assert np.abs(oracle.irfft_packed(F.astype(np.float64)) - x).max() <= 1e-5
+
+
+def test_crosrng_ms_is_ring_weighted_circular_correlation(oracle):
+    """q[m] = sum_rings wr * sum_n ref[n] img[n-m]; t[m] = same with img[-n-m] (full-length rings)."""
+    numr = np.array([10, 1, 64, 11, 65, 64], np.int32)      # two rings of equal length: no interpolation
+    rng = np.random.default_rng(1)
+    ref = rng.standard_normal(128).astype(np.float32)
+    img = rng.standard_normal(128).astype(np.float32)
+    wr = oracle.ringwe(numr)
+    R = oracle.applyws(oracle.frngs(ref, numr), numr, wr)
+    I = oracle.frngs(img, numr)
+    out = oracle.crosrng_ms(R, I, numr)
+    n = np.arange(64)
+    q = np.zeros(64); t = np.zeros(64)
+    for r in range(2):
+        a, b = ref[64 * r:64 * r + 64].astype(np.float64), img[64 * r:64 * r + 64].astype(np.float64)
+        for m in range(64):
+            q[m] += wr[r] * np.sum(a * b[(n - m) % 64])
+            t[m] += wr[r] * np.sum(a * b[(-n - m) % 64])
+    assert np.abs(out["q"] - q).max() <= 1e-4 * np.abs(q).max()
+    assert np.abs(out["t"] - t).max() <= 1e-4 * np.abs(t).max()
+    assert out["qn"] == out["q"].max() and out["qm"] == out["t"].max()
+    jt = int(np.floor(out["tot"] + 0.5))
+    assert abs(((jt - 1) % 64) - int(np.argmax(out["q"]))) <= 1
+
+
+def test_crosrng_last_maximum_wins(oracle):
+    """'>=' scan: among equal maxima the largest lag index is reported (constant curves)."""
+    numr = np.array([5, 1, 32], np.int32)
+    ref = np.ones(32, np.float32); img = np.ones(32, np.float32)
+    R = oracle.applyws(oracle.frngs(ref, numr), numr, oracle.ringwe(numr))
+    out = oracle.crosrng_ms(R, oracle.frngs(img, numr), numr)
+    assert np.allclose(out["q"], out["q"][0])
+    assert int(round(out["tot"])) == 32 or np.ptp(out["q"]) > 0
+
+
+def test_closed_loop_pose_recovery(oracle):
+    nx = 90
+    mask = oracle.model_circle(36, nx)
+    numr = oracle.numrinit(1, 36, 1)
+    refs, cref = oracle.prepare_refs(_blob_image(nx)[None], mask, numr)
+    gn = refs[0]
+    mm = mask > 0.5
+    for (a, tx, ty, m) in [(30., 0, 0, 0), (77.3, 2, -1, 0), (200., -3, 2, 1), (0, 1, 1, 1), (359., 0, 3, 0)]:
+        p = oracle.normalize_mask(oracle.rot_shift2d(gn, a, tx, ty, m), mask, 0)
+        res = oracle.multiref_polar_ali_2d(p, cref, [3, 3], [3, 3], 1.0, numr, 46., 46.)
+        assert int(res[3]) == m
+        an, sxn, syn, mn = oracle.combine_params2(0, 0, 0, 0, res[0], res[1], res[2], int(res[3]))
+        back = oracle.rot_shift2d(p, an, sxn, syn, mn)
+        assert np.corrcoef(back[mm], gn[mm])[0, 1] > 0.99
+
+
+def test_exact_ring_step_rotation_and_integer_shift(oracle):
+    nx = 90
+    mask = oracle.model_circle(36, nx)
+    numr = oracle.numrinit(1, 36, 1)
+    refs, cref = oracle.prepare_refs(_blob_image(nx, seed=8)[None], mask, numr)
+    gn = refs[0]
+    for k in (1, 17, 100, 255):
+        ang = 360.0 * k / 256
+        p = oracle.rot_shift2d(gn, ang, 0, 0, 0)
+        res = oracle.multiref_polar_ali_2d(p, cref, [2, 2], [2, 2], 1.0, numr, 46., 46.)
+        assert res[6] == 0 and res[7] == 0 and res[3] == 0
+        assert abs((res[0] + ang + 180) % 360 - 180) <= 0.5 * 360 / 256
+    p = oracle.rot_shift2d(gn, 0, 2, -1, 0)
+    res = oracle.multiref_polar_ali_2d(p, cref, [3, 3], [3, 3], 1.0, numr, 46., 46.)
+    assert (res[6], res[7]) == (-2.0, 1.0)
+
+
+def test_rot_shift2d_integer_shift_is_exact_translation_and_mirror(oracle):
+    img = _blob_image(64, seed=2, spread=8)
+    out = oracle.rot_shift2d(img, 0.0, 3, -2, 0)
+    assert np.array_equal(out[10:50, 10:50], img[12:52, 7:47])
+    m = oracle.rot_shift2d(img, 0.0, 0, 0, 1)
+    assert np.array_equal(m[:, 0], img[:, 0]) and np.array_equal(m[:, 1:], img[:, 1:][:, ::-1])
+    odd = _blob_image(63, seed=2, spread=8)
+    assert np.array_equal(oracle.rot_shift2d(odd, 0.0, 0, 0, 1), odd[:, ::-1])
+
+
+def test_search_range_and_mashi(oracle):
+    assert oracle.search_range(90, 36, 0.0, 3) == [3, 3]
+    assert oracle.search_range(90, 36, 8.0, 3) == [3, 0]
+    assert oracle.search_range(90, 36, -7.3, 3) == [pytest.approx(0.7), 3]
+    assert oracle.search_range(128, 60, 0.0, 6) == [3, 3]          # config 4 clips to [3,3]
+
+
+def test_class_sums_even_odd_by_global_index(oracle):
+    from cryo_ralib_b200 import synth
+    images, _ = synth.make_particles(6, 64, 2, max_shift=1, seed=4)
+    mask = oracle.model_circle(28, 64)
+    numr = oracle.numrinit(1, 28, 1)
+    _, cref = oracle.prepare_refs(images[:1].copy(), mask, numr)
+    same = np.repeat(images[:1], 6, axis=0)
+    p, a, pk, sums, counts = oracle.mref_iteration(same.copy(), mask, cref, numr, 1, 1, 1, 28, np.zeros((6, 4)), gofs=3)
+    assert counts[0] == 6 and np.all(a == 0)
+    one = oracle.rot_shift2d(oracle.normalize_mask(images[0], mask, 0), p[0, 0], p[0, 1], p[0, 2], int(p[0, 3]))
+    assert np.allclose(sums[0, 0], 3 * one, rtol=1e-5, atol=1e-5) and np.allclose(sums[0, 1], 3 * one, rtol=1e-5, atol=1e-5)
+    p1, _, _, s1, _ = oracle.mref_iteration(same.copy(), mask, cref, numr, 1, 1, 1, 28, np.zeros((6, 4)), gofs=3, nthreads=3)
+    assert np.array_equal(p, p1) and np.allclose(sums, s1, rtol=1e-6, atol=1e-5)
+
+
+def test_reference_update_pieces(oracle):
+    from cryo_ralib_b200 import synth
+    images, _ = synth.make_particles(60, 64, 2, max_shift=0, snr=2.0, seed=6)
+    a, b = images[0::2].sum(0), images[1::2].sum(0)
+    f = oracle.fsc(a, b)
+    assert f[0][0] == 0.0 and abs(f[0][-1] - 0.5) < 1e-9 and len(f[0]) == 33
+    assert f[1][1] > 0.8 and abs(np.mean(f[1][-8:])) < 0.5
+    assert all(abs(v) <= 1 + 1e-6 for v in f[1])
+    fl, aa = oracle.fit_tanh([list(f[0]), list(f[1]), list(f[2])])
+    assert 0.0 < fl <= 0.5 and aa > 0
+    x = (a + b) / 60
+    s = oracle.fshift(x, 3, -2)
+    assert np.allclose(s, np.roll(np.roll(x, 3, axis=1), -2, axis=0), atol=1e-4 * np.abs(x).max())
+    y, xg = np.mgrid[0:64, 0:64]
+    blob = np.exp(-((xg - 35.5) ** 2 + (y - 29.25) ** 2) / 18.0).astype(np.float32)
+    cs = oracle.phase_cog(blob)
+    assert abs(cs[0] - 3.5) < 0.05 and abs(cs[1] + 2.75) < 0.05
+    lp = oracle.filt_tanl(x, 0.12, 0.2)
+    assert abs(lp.mean() - x.mean()) < 1e-4 and lp.std() < x.std()
