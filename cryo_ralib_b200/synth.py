@@ -30,7 +30,10 @@ def random_rotations(n, rng):
 def render(nx, cx, cy, sigma, amp, xp=np, chunk=4096):
     """Images [n][nx][nx] from blob centres cx,cy [n][B] (pixels relative to nx//2)."""
     n = cx.shape[0]
-    grid = xp.arange(nx, dtype=cx.dtype) - (nx // 2)
+    if xp is np:
+        grid = np.arange(nx, dtype=cx.dtype) - (nx // 2)
+    else:
+        grid = xp.arange(nx, dtype=cx.dtype, device=cx.device) - (nx // 2)
     out = []
     for s in range(0, n, chunk):
         gx = xp.exp(-(grid[None, None, :] - cx[s:s+chunk, :, None]) ** 2 / (2 * sigma[None, :, None] ** 2))

@@ -192,6 +192,32 @@ void cra_o_normalize_ring(float *circ, const int *numr, int nring)
  * of the exponent as long as forward and inverse agree (SURVEY A.9 ix).
  * Arithmetic class follows fftr_q (float) / fftr_d (double).             */
 
+/* twiddle tables, one per power-of-two length (built once; cos/sin of 2 pi k / n, k < n/2) */
+#define CRA_MAXLOG 14
+static double *g_twc[CRA_MAXLOG + 1], *g_tws[CRA_MAXLOG + 1];
+static volatile int g_tw_ready = 0;
+static void ensure_tables(void)
+{
+    if (g_tw_ready) return;
+#ifdef _OPENMP
+#pragma omp critical(cra_tw)
+#endif
+    {
+        if (!g_tw_ready) {
+            for (int lg = 1; lg <= CRA_MAXLOG; ++lg) {
+                int n = 1 << lg;
+                g_twc[lg] = (double *)malloc(sizeof(double) * (n / 2));
+                g_tws[lg] = (double *)malloc(sizeof(double) * (n / 2));
+                for (int k = 0; k < n / 2; ++k) {
+                    g_twc[lg][k] = cos(2.0 * CRA_PI * k / n);
+                    g_tws[lg][k] = sin(2.0 * CRA_PI * k / n);
+                }
+            }
+            g_tw_ready = 1;
+        }
+    }
+}
+
 #define DEF_CFFT(NAME, T)                                                        \
 static void NAME(T *re, T *im, int n, int sign)                                  \
 {                                                                                \
@@ -202,11 +228,12 @@ static void NAME(T *re, T *im, int n, int sign)                                 
         if (i < j) { T t = re[i]; re[i] = re[j]; re[j] = t;                      \
                      t = im[i]; im[i] = im[j]; im[j] = t; }                      \
     }                                                                            \
-    for (int len = 2; len <= n; len <<= 1) {                                     \
+    int lg = 1;                                                                  \
+    for (int len = 2; len <= n; len <<= 1, ++lg) {                               \
         int half = len >> 1;                                                     \
+        const double *tc = g_twc[lg], *ts = g_tws[lg];                           \
         for (int k = 0; k < half; ++k) {                                         \
-            double a = sign * 2.0 * CRA_PI * k / len;                            \
-            T wr = (T)cos(a), wi = (T)sin(a);                                    \
+            T wr = (T)tc[k], wi = (T)(sign * ts[k]);                             \
             for (int s = k; s < n; s += len) {                                   \
                 int e = s + half;                                                \
                 T tr = re[e] * wr - im[e] * wi;                                  \
@@ -220,9 +247,12 @@ static void NAME(T *re, T *im, int n, int sign)                                 
 DEF_CFFT(cfft_f, float)
 DEF_CFFT(cfft_d, double)
 
+static int ilog2_exact(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
+
 /* forward real FFT of x[0..L-1] (float), in place, packed layout */
 static void rfft_packed_f(float *x, int L)
 {
+    ensure_tables();
     int n = L / 2;
     float re[4096], im[4096];   /* L <= 8192 */
     for (int i = 0; i < n; ++i) { re[i] = x[2 * i]; im[i] = x[2 * i + 1]; }
@@ -230,12 +260,12 @@ static void rfft_packed_f(float *x, int L)
     /* split: F_k = (Z_k + conj(Z_{n-k}))/2 + e^{-2 pi i k/L} (Z_k - conj(Z_{n-k}))/(2i) */
     x[0] = re[0] + im[0];
     x[1] = re[0] - im[0];
+    const double *tc = g_twc[ilog2_exact(L)], *ts = g_tws[ilog2_exact(L)];
     for (int k = 1; k < n; ++k) {
         int m = n - k;
         float er = 0.5f * (re[k] + re[m]), ei = 0.5f * (im[k] - im[m]);
         float orr = 0.5f * (im[k] + im[m]), oi = -0.5f * (re[k] - re[m]);
-        double a = -2.0 * CRA_PI * k / L;
-        float wr = (float)cos(a), wi = (float)sin(a);
+        float wr = (float)tc[k], wi = (float)(-ts[k]);
         x[2 * k]     = er + (orr * wr - oi * wi);
         x[2 * k + 1] = ei + (orr * wi + oi * wr);
     }
@@ -244,19 +274,20 @@ static void rfft_packed_f(float *x, int L)
 /* inverse of the above in double: packed spectrum -> real sequence, 1/L scaled */
 static void irfft_packed_d(double *x, int L)
 {
+    ensure_tables();
     int n = L / 2;
     double re[4096], im[4096]; /* L <= 8192 */
     /* Z_k = E_k + i O_k with E_k = (F_k + conj(F_{n-k}))/2, O_k = e^{+2 pi i k/L}(F_k - conj(F_{n-k}))/2 */
     double f0 = x[0], fn = x[1];
     re[0] = 0.5 * (f0 + fn); im[0] = 0.5 * (f0 - fn);
+    const double *tc = g_twc[ilog2_exact(L)], *ts = g_tws[ilog2_exact(L)];
     for (int k = 1; k < n; ++k) {
         int m = n - k;
         double fkr = x[2 * k], fki = x[2 * k + 1];
         double fmr = x[2 * m], fmi = -x[2 * m + 1];          /* conj(F_{n-k}) */
         double er = 0.5 * (fkr + fmr), ei = 0.5 * (fki + fmi);
         double dr = 0.5 * (fkr - fmr), di = 0.5 * (fki - fmi);
-        double a = 2.0 * CRA_PI * k / L;
-        double wr = cos(a), wi = sin(a);
+        double wr = tc[k], wi = ts[k];
         double orr = dr * wr - di * wi, oi = dr * wi + di * wr;
         re[k] = er - oi; im[k] = ei + orr;                    /* E + i O */
     }
@@ -312,8 +343,9 @@ void cra_o_crosrng_ms(const float *circ1, const float *circ2, const int *numr, i
                       double *q_curve, double *t_curve)
 {
     int maxrin = numr[3 * nring - 1];
-    double *q = (double *)calloc((size_t)maxrin + 2, sizeof(double));
-    double *t = (double *)calloc((size_t)maxrin + 2, sizeof(double));
+    double q[8192 + 2], t[8192 + 2];
+    memset(q, 0, sizeof(double) * ((size_t)maxrin + 2));
+    memset(t, 0, sizeof(double) * ((size_t)maxrin + 2));
     for (int i = 0; i < nring; ++i) {
         int len = numr[3 * i + 2], off = numr[3 * i + 1] - 1;
         float t1 = circ1[off] * circ2[off];
@@ -344,7 +376,6 @@ void cra_o_crosrng_ms(const float *circ1, const float *circ2, const int *numr, i
     *qm_o = qm; *tmt_o = (float)jtot + pos;
     if (q_curve) memcpy(q_curve, q, sizeof(double) * maxrin);
     if (t_curve) memcpy(t_curve, t, sizeof(double) * maxrin);
-    free(q); free(t);
 }
 
 /* ------------------------------------------------------------------ */
