@@ -30,6 +30,7 @@ struct CraCtx {
     CraRingTab* d_tab = nullptr;
     float2* d_samp = nullptr; float* d_sampw = nullptr;
     float2* d_twf = nullptr;  float2* d_twi = nullptr;
+    int* d_items = nullptr; CraPolarItems items{};
     float* d_mask = nullptr;
     float* d_images = nullptr; float* d_refs = nullptr; float* d_refspec = nullptr;
     float* d_spec = nullptr; CraCand* d_cand = nullptr;
@@ -41,6 +42,7 @@ struct CraCtx {
     float4* d_par = nullptr; int* d_iref = nullptr; float4* h_par = nullptr; int* h_iref = nullptr; size_t cap_par = 0;
     float* d_tmpimg = nullptr; size_t cap_tmpimg = 0;
     float* d_curves = nullptr;
+    float2* h_group = nullptr;   // pinned staging of one 4-row spectrum group (test entry points)
     std::vector<cudaEvent_t> ev;
 };
 
@@ -85,6 +87,7 @@ int build_tables(CraCtx* c)
     for (int i = 0; i < nring; ++i) {
         const int inr = c->numr[3 * i], len = c->numr[3 * i + 2], off = c->numr[3 * i + 1] - 1;
         t.off[i] = off; t.len[i] = len; t.rad[i] = inr;
+        t.coff[i] = off / 2 + i;                     // sum over previous rings of (len/2 + 1)
         t.wr[i] = (float)(inr * (2.0 * M_PI) / (double)len * (double)t.maxrin / (double)len);   // ringwe
         t.wn[i] = (float)(inr * 2 * M_PI / (float)len);                                         // Normalize_ring
         const int lt = len / 4;
@@ -101,12 +104,29 @@ int build_tables(CraCtx* c)
         for (int j = 0; j < len; ++j) { sampw[off + j] = t.wn[i]; nn += t.wn[i]; }
     }
     t.nn = nn;
-    std::vector<float2> twf(t.maxrin / 2), twi(t.maxrin);
-    for (int j = 0; j < t.maxrin / 2; ++j) {
+    t.nc = t.lcirc / 2 + nring;
+    std::vector<float2> twf(t.maxrin), twi;
+    for (int j = 0; j < t.maxrin; ++j) {
         double a = -2.0 * M_PI * j / t.maxrin; twf[j] = make_float2((float)cos(a), (float)sin(a));
     }
-    for (int j = 0; j < t.maxrin; ++j) {
-        double a = 2.0 * M_PI * j / t.maxrin; twi[j] = make_float2((float)cos(a), (float)sin(a));
+    cra_ccf_twiddles(t.log2n, twi);
+    // flat work lists of the ring FFT passes, longest rings first so that warps stay uniform
+    {
+        std::vector<int> A, B, C;
+        for (int i = nring - 1; i >= 0; --i) {
+            const int n = t.len[i] >> 1;
+            const int lg = ilog2_floor(n), NA = 1 << (lg / 2), NB = n / NA;
+            if (lg < 2 || lg > 9) { cra_set_error("ring length outside [8,1024]"); return 1; }
+            for (int b = 0; b < NB; ++b) A.push_back((i << 16) | b);
+            for (int a = 0; a < NA; ++a) B.push_back((i << 16) | a);
+            for (int k = 0; k <= n / 2; ++k) C.push_back((i << 16) | k);
+        }
+        std::vector<int> all(A); all.insert(all.end(), B.begin(), B.end()); all.insert(all.end(), C.begin(), C.end());
+        CRA_CUDA(cudaMalloc(&c->d_items, sizeof(int) * all.size()));
+        CRA_CUDA(cudaMemcpy(c->d_items, all.data(), sizeof(int) * all.size(), cudaMemcpyHostToDevice));
+        c->items.A = c->d_items; c->items.nA = (int)A.size();
+        c->items.B = c->d_items + A.size(); c->items.nB = (int)B.size();
+        c->items.C = c->d_items + A.size() + B.size(); c->items.nC = (int)C.size();
     }
     // model_circle(ou, nx, nx): r^2 <= ou^2 around (nx/2, nx/2)
     std::vector<float> mask((size_t)c->npix);
@@ -145,7 +165,7 @@ struct Bind { CraCtx* c; Bind(CraCtx* c_) : c(c_) {} int ok() { if (!c) { cra_se
 
 int ensure_meta(CraCtx* c, size_t nparticles, size_t nbatch_guess)
 {
-    size_t need = nparticles * (sizeof(CraSearch) + sizeof(int4) + sizeof(int)) + (nbatch_guess + 2) * sizeof(int) + 64;
+    size_t need = nparticles * (sizeof(CraSearch) + sizeof(int4) + 2 * sizeof(int)) + 2 * (nbatch_guess + 2) * sizeof(int) + 64;
     if (need > c->meta_bytes) {
         if (c->h_meta) cudaFreeHost(c->h_meta);
         if (c->d_meta) cudaFree(c->d_meta);
@@ -204,7 +224,7 @@ extern "C" int cra_create(const CraConfig* cfg, int device, CraCtx** out)
     if (build_tables(c)) { cra_destroy(c); return 1; }
     const int k = (int)(cfg->max_range / cfg->step);
     c->smax = (2 * k + 1) * (2 * k + 1);
-    const size_t row_bytes = (size_t)c->htab.lcirc * sizeof(float);
+    const size_t row_bytes = (size_t)c->htab.nc * sizeof(float2);     // device spectrum of one row
     long rb = cfg->row_batch > 0 ? cfg->row_batch : (long)((size_t)2 << 30) / (long)row_bytes;
     if (rb < c->smax) rb = c->smax;
     long want = (long)cfg->max_particles * c->smax;
@@ -215,8 +235,12 @@ extern "C" int cra_create(const CraConfig* cfg, int device, CraCtx** out)
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = cudaMalloc(&c->d_images, (size_t)cfg->max_particles * c->npix * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_refs, (size_t)cfg->max_refs * c->npix * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_refspec, (size_t)cfg->max_refs * row_bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_spec, (size_t)c->row_batch * row_bytes);
+    const size_t ref_groups = ((size_t)cfg->max_refs + 3) / 4, row_groups = ((size_t)c->row_batch + 3) / 4;
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_refspec, ref_groups * 4 * row_bytes);
+    if (e == cudaSuccess) e = cudaMemset(c->d_refspec, 0, ref_groups * 4 * row_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_spec, row_groups * 4 * row_bytes);
+    if (e == cudaSuccess) e = cudaMemset(c->d_spec, 0, row_groups * 4 * row_bytes);
+    if (e == cudaSuccess) e = cudaMallocHost(&c->h_group, 4 * row_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_cand, (size_t)c->row_batch * c->ntile_n_max * sizeof(CraCand));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_sums, nsum * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_curves, (size_t)2 * c->htab.maxrin * sizeof(float));
@@ -232,6 +256,7 @@ extern "C" int cra_destroy(CraCtx* c)
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
     for (auto& e : c->ev) cudaEventDestroy(e);
+    cudaFree(c->d_items);
     cudaFree(c->d_tab); cudaFree(c->d_samp); cudaFree(c->d_sampw); cudaFree(c->d_twf); cudaFree(c->d_twi);
     cudaFree(c->d_mask); cudaFree(c->d_images); cudaFree(c->d_refs); cudaFree(c->d_refspec);
     cudaFree(c->d_spec); cudaFree(c->d_cand); cudaFree(c->d_sums); cudaFree(c->d_meta); cudaFree(c->d_res);
@@ -240,6 +265,7 @@ extern "C" int cra_destroy(CraCtx* c)
     if (c->h_res) cudaFreeHost(c->h_res);
     if (c->h_par) cudaFreeHost(c->h_par);
     if (c->h_iref) cudaFreeHost(c->h_iref);
+    if (c->h_group) cudaFreeHost(c->h_group);
     if (c->st) cudaStreamDestroy(c->st);
     delete c;
     return 0;
@@ -277,7 +303,7 @@ extern "C" int cra_set_refs(CraCtx* c, const float* h, int R, int normalize_mask
     if (R < 1 || R > c->cfg.max_refs) { cra_set_error("R exceeds max_refs"); return 1; }
     CRA_CUDA(cudaMemcpyAsync(c->d_refs, h, (size_t)R * c->npix * sizeof(float), cudaMemcpyHostToDevice, c->st));
     if (normalize_mask && cra_launch_mask_normalize(c->d_refs, R, c->nx, c->d_mask, 1, c->st)) return 1;
-    if (cra_launch_polar_refs(c->d_refs, R, c->nx, c->d_tab, c->htab, c->d_samp, c->d_twf, c->d_refspec, c->st)) return 1;
+    if (cra_launch_polar_refs(c->d_refs, R, c->nx, c->d_tab, c->htab, c->d_samp, c->d_twf, c->items, c->d_refspec, c->st)) return 1;
     CRA_CUDA(cudaStreamSynchronize(c->st));
     c->R = R;
     return 0;
@@ -310,29 +336,37 @@ extern "C" int cra_align(CraCtx* c, int start, int stop, const CraSearch* search
     }
     const size_t nb = bfirst.size();
     if (ensure_meta(c, n, nb)) return 1;
-    // meta layout: win[n] (16-byte aligned) | search[n] | row_start[n + nb]
+    // meta layout: win[n] (16-byte aligned) | search[n] | row_start[n + nb] | chunk_start[n + nb]
     int4* h_win = reinterpret_cast<int4*>(c->h_meta);
     CraSearch* h_search = reinterpret_cast<CraSearch*>(c->h_meta + (size_t)n * sizeof(int4));
     int* h_rs = reinterpret_cast<int*>(c->h_meta + (size_t)n * (sizeof(CraSearch) + sizeof(int4)));
+    int* h_cs = h_rs + n + nb;
+    const int rpb = cra_polar_rows_per_block();
+    std::vector<int> bchunks(nb);
     memcpy(h_search, search, (size_t)n * sizeof(CraSearch));
     long total_rows = 0;
     for (size_t bi = 0; bi < nb; ++bi) {
         int* rs = h_rs + bfirst[bi] + bi;
-        int acc = 0;
+        int* cs = h_cs + bfirst[bi] + bi;
+        int acc = 0, cacc = 0;
         for (int q = 0; q < bcount[bi]; ++q) {
             const int p = bfirst[bi] + q;
             window_of(search[p], step, &h_win[p]);
-            rs[q] = acc;
-            acc += (h_win[p].x + h_win[p].y + 1) * (h_win[p].z + h_win[p].w + 1);
+            rs[q] = acc; cs[q] = cacc;
+            const int rows = (h_win[p].x + h_win[p].y + 1) * (h_win[p].z + h_win[p].w + 1);
+            cacc += (acc + rows - 1) / rpb - acc / rpb + 1;      // aligned sub-groups this particle touches
+            acc += rows;
         }
-        rs[bcount[bi]] = acc;
+        rs[bcount[bi]] = acc; cs[bcount[bi]] = cacc;
+        bchunks[bi] = cacc;
         total_rows += acc;
     }
-    const size_t used = (size_t)n * (sizeof(CraSearch) + sizeof(int4)) + (n + nb) * sizeof(int);
+    const size_t used = (size_t)n * (sizeof(CraSearch) + sizeof(int4)) + 2 * (n + nb) * sizeof(int);
     CRA_CUDA(cudaMemcpyAsync(c->d_meta, c->h_meta, used, cudaMemcpyHostToDevice, c->st));
     const int4* d_win = reinterpret_cast<const int4*>(c->d_meta);
     const CraSearch* d_search = reinterpret_cast<const CraSearch*>(c->d_meta + (size_t)n * sizeof(int4));
     const int* d_rs = reinterpret_cast<const int*>(c->d_meta + (size_t)n * (sizeof(CraSearch) + sizeof(int4)));
+    const int* d_cs = d_rs + n + nb;
 
     const int TN = cra_ccf_tile_n();
     const int ntile_n = (c->R + TN - 1) / TN;
@@ -344,11 +378,12 @@ extern "C" int cra_align(CraCtx* c, int start, int stop, const CraSearch* search
     for (size_t bi = 0; bi < nb; ++bi) {
         CraRowMap map;
         map.row_start = d_rs + bfirst[bi] + bi;
+        map.chunk_start = d_cs + bfirst[bi] + bi; map.nchunks = bchunks[bi];
         map.search = d_search + bfirst[bi];
         map.win = d_win + bfirst[bi];
         map.np = bcount[bi]; map.nrows = brows[bi]; map.p0 = start + bfirst[bi]; map.step = step;
         if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 0], c->st));
-        if (cra_launch_polar_rows(c->d_images, c->nx, c->d_tab, c->htab, c->d_samp, c->d_sampw, c->d_twf, map,
+        if (cra_launch_polar_rows(c->d_images, c->nx, c->d_tab, c->htab, c->d_samp, c->d_sampw, c->d_twf, c->items, map,
                                   c->cfg.normalize_ring, c->d_spec, c->st)) return 1;
         if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 1], c->st));
         if (cra_launch_ccf(c->d_spec, map.nrows, c->d_refspec, c->R, c->d_tab, c->htab, c->d_twi, c->d_cand, ntile_n, c->st)) return 1;
@@ -477,14 +512,31 @@ extern "C" int cra_transform(CraCtx* c, int start, int stop, const float* params
     return 0;
 }
 
+// device spectrum (row `lane4` of the group staged in h_group) -> SPIDER packed layout
+static void unpack_spectrum(const CraCtx* c, int lane4, float* out)
+{
+    const CraRingTab& t = c->htab;
+    for (int i = 0; i < t.nring; ++i) {
+        const int half = t.len[i] >> 1;
+        float* o = out + t.off[i];
+        for (int k = 0; k <= half; ++k) {
+            const float2 v = c->h_group[((size_t)t.coff[i] + k) * 4 + lane4];
+            if (k == 0) o[0] = v.x;
+            else if (k == half) o[1] = v.x;
+            else { o[2 * k] = v.x; o[2 * k + 1] = v.y; }
+        }
+    }
+}
+
 extern "C" int cra_polar_spectrum(CraCtx* c, int particle, float cx, float cy, float* host_out)
 {
     Bind b(c); if (b.ok()) return 1;
     if (particle < 0 || particle >= c->cfg.max_particles) { cra_set_error("bad particle index"); return 1; }
     if (cra_launch_polar_single(c->d_images + (size_t)particle * c->npix, c->nx, c->d_tab, c->htab, c->d_samp, c->d_sampw,
-                                c->d_twf, cx, cy, c->cfg.normalize_ring, c->d_spec, c->st)) return 1;
-    CRA_CUDA(cudaMemcpyAsync(host_out, c->d_spec, (size_t)c->htab.lcirc * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+                                c->d_twf, c->items, cx, cy, c->cfg.normalize_ring, c->d_spec, c->st)) return 1;
+    CRA_CUDA(cudaMemcpyAsync(c->h_group, c->d_spec, (size_t)c->htab.nc * 4 * sizeof(float2), cudaMemcpyDeviceToHost, c->st));
     CRA_CUDA(cudaStreamSynchronize(c->st));
+    unpack_spectrum(c, 0, host_out);
     return 0;
 }
 
@@ -492,9 +544,10 @@ extern "C" int cra_ref_spectrum(CraCtx* c, int iref, float* host_out)
 {
     Bind b(c); if (b.ok()) return 1;
     if (iref < 0 || iref >= c->R) { cra_set_error("bad reference index"); return 1; }
-    CRA_CUDA(cudaMemcpyAsync(host_out, c->d_refspec + (size_t)iref * c->htab.lcirc, (size_t)c->htab.lcirc * sizeof(float),
-                             cudaMemcpyDeviceToHost, c->st));
+    CRA_CUDA(cudaMemcpyAsync(c->h_group, reinterpret_cast<float2*>(c->d_refspec) + (size_t)(iref >> 2) * c->htab.nc * 4,
+                             (size_t)c->htab.nc * 4 * sizeof(float2), cudaMemcpyDeviceToHost, c->st));
     CRA_CUDA(cudaStreamSynchronize(c->st));
+    unpack_spectrum(c, iref & 3, host_out);
     return 0;
 }
 
@@ -503,8 +556,8 @@ extern "C" int cra_ccf_curves(CraCtx* c, int particle, float cx, float cy, int i
     Bind b(c); if (b.ok()) return 1;
     if (particle < 0 || particle >= c->cfg.max_particles || iref < 0 || iref >= c->R) { cra_set_error("bad index"); return 1; }
     if (cra_launch_polar_single(c->d_images + (size_t)particle * c->npix, c->nx, c->d_tab, c->htab, c->d_samp, c->d_sampw,
-                                c->d_twf, cx, cy, c->cfg.normalize_ring, c->d_spec, c->st)) return 1;
-    if (cra_launch_ccf_curves(c->d_spec, c->d_refspec + (size_t)iref * c->htab.lcirc, c->d_tab, c->htab,
+                                c->d_twf, c->items, cx, cy, c->cfg.normalize_ring, c->d_spec, c->st)) return 1;
+    if (cra_launch_ccf_curves(c->d_spec, 0, c->d_refspec, iref, c->d_tab, c->htab,
                               c->d_curves, c->d_curves + c->htab.maxrin, c->st)) return 1;
     CRA_CUDA(cudaMemcpyAsync(q_out, c->d_curves, c->htab.maxrin * sizeof(float), cudaMemcpyDeviceToHost, c->st));
     CRA_CUDA(cudaMemcpyAsync(t_out, c->d_curves + c->htab.maxrin, c->htab.maxrin * sizeof(float), cudaMemcpyDeviceToHost, c->st));

@@ -5,13 +5,16 @@
 // (cuda/gpu_aln_noref.cu:1009-1143, :2198-2206, :1305-1346, :1393-1494) without ever
 // materialising the particles x refs x shifts x 2 x (maxrin+2) CCF table in HBM.
 //
-// ccf_peak_kernel: one CTA = TM particle-shift rows x TN references.  Thread k owns
-// angular frequency k and keeps, for every (row, ref) pair of the tile, the four
-// real ring sums A=sum c1 d1, B=sum c2 d2, C=sum c1 d2, D=sum c2 d1 in registers
-// (c = weighted reference spectrum, d = particle spectrum).  From them
+// ccf_peak_kernel: one CTA = 4 particle-shift rows x 4 references (16 pairs).  A thread owns
+// one angular frequency k (two for the upper quarter of the band, where fewer rings reach, so
+// the warps of a CTA carry equal ring counts) and keeps, for every pair, the four real ring sums
+//   A = sum c.x d.x, B = sum c.y d.y, C = sum c.x d.y, D = sum c.y d.x
+// in registers (c = weighted reference spectrum, d = particle spectrum, both in the device
+// layout of cra_common.cuh: 4 rows / 4 refs interleaved, so each ring step is four 128-bit
+// loads, prefetched one ring ahead).  From them
 //   q_k = (A+B) + i(D-C)   (straight,  ref * conj(img))
 //   t_k = (A-B) - i(C+D)   (mirrored,  conj(ref) * conj(img))
-// and the Hermitian-packed W = q + i t goes to shared memory, where one length-maxrin
+// and the Hermitian-extended W = q + i t goes to shared memory, where one length-maxrin
 // complex inverse FFT per pair (two register passes N1 x N2) yields q[m] + i t[m].
 // The argmax over m (">=": last maximum wins, as the reference), the straight/mirror
 // choice and the best-over-references rule are applied in registers/shuffles; only one
@@ -22,75 +25,21 @@
 // the winning lag in double precision for prb1d, and emits the 6-tuple of
 // multiref_polar_ali_2d.
 #include "cra_common.cuh"
+#include "cra_fft.cuh"
 #include <math.h>
+#include <string.h>
 
 namespace {
 
-constexpr int TM = 4;   // rows per CTA
+constexpr int TM = 4;   // rows per CTA  (= interleave factor of the device spectrum)
 constexpr int TN = 4;   // references per CTA
 constexpr int NP = TM * TN;
 
-__host__ __device__ constexpr float tw_cos(int j)   // cos(2 pi j / 32), j < 16
-{
-    return j == 0 ? 1.0f : j == 1 ? 9.807852804e-01f : j == 2 ? 9.238795325e-01f : j == 3 ? 8.314696123e-01f
-         : j == 4 ? 7.071067812e-01f : j == 5 ? 5.555702330e-01f : j == 6 ? 3.826834324e-01f : j == 7 ? 1.950903220e-01f
-         : j == 8 ? 0.0f : j == 9 ? -1.950903220e-01f : j == 10 ? -3.826834324e-01f : j == 11 ? -5.555702330e-01f
-         : j == 12 ? -7.071067812e-01f : j == 13 ? -8.314696123e-01f : j == 14 ? -9.238795325e-01f : -9.807852804e-01f;
-}
-__host__ __device__ constexpr float tw_sin(int j)   // sin(2 pi j / 32), j < 16
-{
-    return j == 0 ? 0.0f : j == 1 ? 1.950903220e-01f : j == 2 ? 3.826834324e-01f : j == 3 ? 5.555702330e-01f
-         : j == 4 ? 7.071067812e-01f : j == 5 ? 8.314696123e-01f : j == 6 ? 9.238795325e-01f : j == 7 ? 9.807852804e-01f
-         : j == 8 ? 1.0f : j == 9 ? 9.807852804e-01f : j == 10 ? 9.238795325e-01f : j == 11 ? 8.314696123e-01f
-         : j == 12 ? 7.071067812e-01f : j == 13 ? 5.555702330e-01f : j == 14 ? 3.826834324e-01f : 1.950903220e-01f;
-}
-__host__ __device__ constexpr int ilog2c(int n) { return n <= 1 ? 0 : 1 + ilog2c(n >> 1); }
-__host__ __device__ constexpr int brevc(int i, int bits) { return bits == 0 ? 0 : ((i & 1) << (bits - 1)) | brevc(i >> 1, bits - 1); }
+// ring table of the active configuration (uniform-datapath reads in the hot loop)
+__constant__ int c_coff[CRA_MAX_RINGS];
+__constant__ int c_half[CRA_MAX_RINGS];   // len/2
 
-// In-register R-point DFT with kernel exp(+2 pi i n k / R) (inverse sign), R <= 32.
-// Template recursion over the radix-2 stages keeps every register index a constant.
-template <int R, int LEN>
-struct FftStage {
-    static __device__ __forceinline__ void run(float2 (&x)[R])
-    {
-        constexpr int HALF = LEN / 2;
-#pragma unroll
-        for (int g = 0; g < R / LEN; ++g) {
-#pragma unroll
-            for (int k = 0; k < HALF; ++k) {
-                constexpr int TS = 32 / LEN;
-                const int tj = k * TS;
-                const int i0 = g * LEN + k, i1 = i0 + HALF;
-                float2 u = x[i0], b = x[i1], v;
-                if (tj == 0) v = b;
-                else if (tj == 8) v = make_float2(-b.y, b.x);
-                else {
-                    const float wr = tw_cos(tj), wi = tw_sin(tj);
-                    v = make_float2(b.x * wr - b.y * wi, b.x * wi + b.y * wr);
-                }
-                x[i0] = make_float2(u.x + v.x, u.y + v.y);
-                x[i1] = make_float2(u.x - v.x, u.y - v.y);
-            }
-        }
-        FftStage<R, LEN * 2>::run(x);
-    }
-};
-template <int R>
-struct FftStage<R, 2 * R> { static __device__ __forceinline__ void run(float2 (&)[R]) {} };
-
-template <int R>
-__device__ __forceinline__ void fft_reg(float2 (&x)[R])
-{
-    constexpr int LG = ilog2c(R);
-#pragma unroll
-    for (int i = 0; i < R; ++i) {
-        int j = 0;
-#pragma unroll
-        for (int b = 0; b < LG; ++b) j |= ((i >> b) & 1) << (LG - 1 - b);
-        if (i < j) { float2 t = x[i]; x[i] = x[j]; x[j] = t; }
-    }
-    FftStage<R, 2>::run(x);
-}
+using crafft::fft_reg;
 
 template <int LOG2N>
 struct Shape {
@@ -99,8 +48,10 @@ struct Shape {
     static constexpr int L2 = LOG2N - L1;
     static constexpr int N1 = 1 << L1;
     static constexpr int N2 = 1 << L2;
-    static constexpr int NT = (N / 2 < 32) ? 32 : N / 2;     // threads per CTA
-    static constexpr int PS = N1 * (N2 + 1);                 // padded float2 stride of one pair
+    static constexpr int NQ = N / 4;                          // threads owning one frequency
+    static constexpr int NW = 3 * N / 8;                      // working threads (upper quarter: two frequencies each)
+    static constexpr int NT = ((NW + 31) / 32) * 32 < 32 ? 32 : ((NW + 31) / 32) * 32;
+    static constexpr int PS = N1 * (N2 + 1);                  // padded float2 stride of one pair
 };
 
 __device__ __forceinline__ bool better(float v, int m, float bv, int bm)
@@ -108,93 +59,114 @@ __device__ __forceinline__ bool better(float v, int m, float bv, int bm)
     return (v > bv) || (v == bv && m > bm);
 }
 
+struct Acc { float A[TM][TN], B[TM][TN], C[TM][TN], D[TM][TN]; };
+
+__device__ __forceinline__ void ring_fma(Acc& a, const float4 (&d)[2], const float4 (&c)[2])
+{
+    const float dx[TM] = {d[0].x, d[0].z, d[1].x, d[1].z}, dy[TM] = {d[0].y, d[0].w, d[1].y, d[1].w};
+    const float cx[TN] = {c[0].x, c[0].z, c[1].x, c[1].z}, cy[TN] = {c[0].y, c[0].w, c[1].y, c[1].w};
+#pragma unroll
+    for (int m = 0; m < TM; ++m)
+#pragma unroll
+        for (int n = 0; n < TN; ++n) {
+            a.A[m][n] = fmaf(cx[n], dx[m], a.A[m][n]);
+            a.B[m][n] = fmaf(cy[n], dy[m], a.B[m][n]);
+            a.C[m][n] = fmaf(cx[n], dy[m], a.C[m][n]);
+            a.D[m][n] = fmaf(cy[n], dx[m], a.D[m][n]);
+        }
+}
+
+// Ring sums of all 16 pairs at frequency k, then W[k] and W[N-k] to shared memory.
+// dq / cq point at element 0 of the row group / ref group (float4 = two interleaved float2).
 template <int LOG2N>
-__global__ void __launch_bounds__(Shape<LOG2N>::NT)
-ccf_peak_kernel(const float* __restrict__ spec, int nrows, const float* __restrict__ refspec, int R,
-                const CraRingTab* __restrict__ tab, const float2* __restrict__ twid,
-                CraCand* __restrict__ cand, int ntile_n)
+__device__ __forceinline__ void contract_freq(int k, int nring, const float4* __restrict__ dq,
+                                              const float4* __restrict__ cq, float2* __restrict__ s_w)
 {
     using S = Shape<LOG2N>;
-    constexpr int N = S::N, N1 = S::N1, N2 = S::N2, NT = S::NT, PS = S::PS;
+    constexpr int N = S::N, N2 = S::N2, PS = S::PS;
+    Acc a;
+#pragma unroll
+    for (int m = 0; m < TM; ++m)
+#pragma unroll
+        for (int n = 0; n < TN; ++n) { a.A[m][n] = 0.f; a.B[m][n] = 0.f; a.C[m][n] = 0.f; a.D[m][n] = 0.f; }
+
+    // rings in descending length: stop at the first ring that no longer reaches frequency k
+    int i = nring - 1;
+    float4 d0[2], c0[2], d1[2], c1[2];
+    {
+        const int e = (c_coff[i] + k) * 2;
+        d0[0] = __ldg(dq + e); d0[1] = __ldg(dq + e + 1); c0[0] = __ldg(cq + e); c0[1] = __ldg(cq + e + 1);
+    }
+    for (;;) {
+        const bool m1 = (i >= 1) && (k <= c_half[i - 1]);
+        if (m1) {
+            const int e = (c_coff[i - 1] + k) * 2;
+            d1[0] = __ldg(dq + e); d1[1] = __ldg(dq + e + 1); c1[0] = __ldg(cq + e); c1[1] = __ldg(cq + e + 1);
+        }
+        ring_fma(a, d0, c0);
+        if (!m1) break;
+        const bool m0 = (i >= 2) && (k <= c_half[i - 2]);
+        if (m0) {
+            const int e = (c_coff[i - 2] + k) * 2;
+            d0[0] = __ldg(dq + e); d0[1] = __ldg(dq + e + 1); c0[0] = __ldg(cq + e); c0[1] = __ldg(cq + e + 1);
+        }
+        ring_fma(a, d1, c1);
+        if (!m0) break;
+        i -= 2;
+    }
+    const int kk = (N - k) & (N - 1);
+    const int i0 = (k >> S::L2) * (N2 + 1) + (k & (N2 - 1));
+    const int i1 = (kk >> S::L2) * (N2 + 1) + (kk & (N2 - 1));
+#pragma unroll
+    for (int m = 0; m < TM; ++m)
+#pragma unroll
+        for (int n = 0; n < TN; ++n) {
+            float2* w = s_w + (m * TN + n) * PS;
+            const float A = a.A[m][n], B = a.B[m][n], C = a.C[m][n], D = a.D[m][n];
+            w[i0] = make_float2(A + B + C + D, A - B + D - C);
+            if (k != 0) w[i1] = make_float2(A + B - C - D, A - B + C - D);
+        }
+}
+
+template <int LOG2N>
+__global__ void __launch_bounds__(Shape<LOG2N>::NT)
+ccf_peak_kernel(const float4* __restrict__ spec, int nrows, const float4* __restrict__ refspec, int R,
+                int nring, int nc, const float2* __restrict__ twid, CraCand* __restrict__ cand, int ntile_n)
+{
+    using S = Shape<LOG2N>;
+    constexpr int N = S::N, N1 = S::N1, N2 = S::N2, NT = S::NT, PS = S::PS, NQ = S::NQ, NW = S::NW;
     extern __shared__ __align__(16) float2 s_dyn[];
     float2* s_w = s_dyn;                 // NP * PS
-    float2* s_tw = s_dyn + NP * PS;      // N : exp(+2 pi i j / N)
-    __shared__ int s_off[CRA_MAX_RINGS];
-    __shared__ int s_len[CRA_MAX_RINGS];
+    float2* s_tw = s_dyn + NP * PS;      // N : s_tw[j*N2 + n2] = exp(+2 pi i n2 j / N)
     __shared__ CraCand s_pair[NP];
 
     const int tid = threadIdx.x;
     const int tn = blockIdx.x % ntile_n;
     const int tm = blockIdx.x / ntile_n;
-    const int nring = tab->nring;
-    const int lcirc = tab->lcirc;
-    for (int i = tid; i < nring; i += NT) { s_off[i] = tab->off[i]; s_len[i] = tab->len[i]; }
     for (int i = tid; i < N; i += NT) s_tw[i] = twid[i];
-    __syncthreads();
 
-    const float* drow[TM];
-    const float* cref[TN];
-#pragma unroll
-    for (int m = 0; m < TM; ++m) { int r = tm * TM + m; if (r > nrows - 1) r = nrows - 1; drow[m] = spec + (size_t)r * lcirc; }
-#pragma unroll
-    for (int n = 0; n < TN; ++n) { int r = tn * TN + n; if (r > R - 1) r = R - 1; cref[n] = refspec + (size_t)r * lcirc; }
+    const float4* dq = spec + (size_t)tm * nc * 2;        // nc float2x4 = nc*2 float4 per group
+    const float4* cq = refspec + (size_t)tn * nc * 2;
 
-    const int k = tid;
-    if (k < N / 2) {
-        float A[TM][TN], B[TM][TN], Cc[TM][TN], D[TM][TN];
-#pragma unroll
-        for (int m = 0; m < TM; ++m)
-#pragma unroll
-            for (int n = 0; n < TN; ++n) { A[m][n] = 0.f; B[m][n] = 0.f; Cc[m][n] = 0.f; D[m][n] = 0.f; }
-
-        for (int i = 0; i < nring; ++i) {
-            const int len = s_len[i];
-            if (k < (len >> 1)) {
-                const int o = s_off[i] + 2 * k;
-                float2 d[TM], c[TN];
-#pragma unroll
-                for (int m = 0; m < TM; ++m) d[m] = __ldg(reinterpret_cast<const float2*>(drow[m] + o));
-#pragma unroll
-                for (int n = 0; n < TN; ++n) c[n] = __ldg(reinterpret_cast<const float2*>(cref[n] + o));
-                // thread 0: slot1 is the Nyquist term, which only full-length rings keep in place
-                const float bsel = (k != 0 || len == N) ? 1.0f : 0.0f;
-#pragma unroll
-                for (int m = 0; m < TM; ++m)
-#pragma unroll
-                    for (int n = 0; n < TN; ++n) {
-                        A[m][n] = fmaf(c[n].x, d[m].x, A[m][n]);
-                        B[m][n] = fmaf(c[n].y * bsel, d[m].y, B[m][n]);
-                        Cc[m][n] = fmaf(c[n].x, d[m].y, Cc[m][n]);
-                        D[m][n] = fmaf(c[n].y, d[m].x, D[m][n]);
-                    }
-            } else if (k == (len >> 1) && len != N) {
-                // Nyquist of a short ring: real term at frequency len/2 (Crosrng_ms q(numr3i+1))
-                const int o = s_off[i] + 1;
-#pragma unroll
-                for (int m = 0; m < TM; ++m) {
-                    const float dv = __ldg(drow[m] + o);
-#pragma unroll
-                    for (int n = 0; n < TN; ++n) A[m][n] = fmaf(__ldg(cref[n] + o), dv, A[m][n]);
-                }
+    if (tid < NW) {
+        contract_freq<LOG2N>(tid, nring, dq, cq, s_w);
+        if (tid >= NQ) contract_freq<LOG2N>(tid + N / 8, nring, dq, cq, s_w);
+    }
+    // frequency N/2 (real): only full-length rings reach it; one pair per lane of the last warp
+    {
+        const int l = tid - (NT - 32);
+        if (l >= 0 && l < NP) {
+            const int m = l / TN, n = l % TN;
+            const float2* d2 = reinterpret_cast<const float2*>(dq);
+            const float2* c2 = reinterpret_cast<const float2*>(cq);
+            float a = 0.f;
+            for (int i = nring - 1; i >= 0 && c_half[i] == N / 2; --i) {
+                const int e = (c_coff[i] + N / 2) * 4;
+                a = fmaf(__ldg(c2 + e + n).x, __ldg(d2 + e + m).x, a);
             }
+            const int h = N / 2;
+            s_w[l * PS + (h >> S::L2) * (N2 + 1) + (h & (N2 - 1))] = make_float2(a, a);
         }
-        // W = q + i t, Hermitian-extended to N points
-#pragma unroll
-        for (int m = 0; m < TM; ++m)
-#pragma unroll
-            for (int n = 0; n < TN; ++n) {
-                float2* w = s_w + (m * TN + n) * PS;
-                const float a = A[m][n], b = B[m][n], c = Cc[m][n], d = D[m][n];
-                if (k == 0) {
-                    w[0] = make_float2(a, a);
-                    const int h = N / 2;
-                    w[(h >> S::L2) * (N2 + 1) + (h & (N2 - 1))] = make_float2(b, b);
-                } else {
-                    const int kk = N - k;
-                    w[(k >> S::L2) * (N2 + 1) + (k & (N2 - 1))] = make_float2(a + b + c + d, a - b + d - c);
-                    w[(kk >> S::L2) * (N2 + 1) + (kk & (N2 - 1))] = make_float2(a + b - c - d, a - b + c - d);
-                }
-            }
     }
     __syncthreads();
 
@@ -205,10 +177,11 @@ ccf_peak_kernel(const float* __restrict__ spec, int nrows, const float* __restri
         float2 x[N1];
 #pragma unroll
         for (int j = 0; j < N1; ++j) x[j] = w[j * (N2 + 1)];
-        fft_reg<N1>(x);
+        fft_reg<N1, 1>(x);
 #pragma unroll
         for (int j = 0; j < N1; ++j) {
-            const float2 t = s_tw[(n2 * j) & (N - 1)];
+            if (j == 0) { w[0] = x[0]; continue; }
+            const float2 t = s_tw[j * N2 + n2];
             w[j * (N2 + 1)] = make_float2(x[j].x * t.x - x[j].y * t.y, x[j].x * t.y + x[j].y * t.x);
         }
     }
@@ -221,7 +194,7 @@ ccf_peak_kernel(const float* __restrict__ spec, int nrows, const float* __restri
         float2 x[N2];
 #pragma unroll
         for (int j = 0; j < N2; ++j) x[j] = w[j];
-        fft_reg<N2>(x);
+        fft_reg<N2, 1>(x);
         float bq = -INFINITY, bt = -INFINITY; int mq = -1, mt = -1;
 #pragma unroll
         for (int j = 0; j < N2; ++j) {
@@ -264,38 +237,27 @@ ccf_peak_kernel(const float* __restrict__ spec, int nrows, const float* __restri
     }
 }
 
-// Ring sums of one (row, ref) pair at frequency k (0 < k < N/2), incl. short-ring Nyquist.
-__device__ void pair_freq(const float* __restrict__ d, const float* __restrict__ c, const CraRingTab* tab,
-                          int k, int N, float& zq_r, float& zq_i, float& zt_r, float& zt_i)
+// ---- scalar helpers on the device spectrum layout (finalize / test entry) -------------------
+__device__ __forceinline__ float2 spec_at(const float2* __restrict__ base, int nc, int row, int e)
+{
+    return base[((size_t)(row >> 2) * nc + e) * 4 + (row & 3)];
+}
+
+// q_k and t_k of one (row, ref) pair at frequency k, 0 <= k <= N/2
+__device__ void pair_freq(const float2* __restrict__ spec, int row, const float2* __restrict__ refspec, int ref,
+                          const CraRingTab* __restrict__ tab, int k, float& zq_r, float& zq_i, float& zt_r, float& zt_i)
 {
     float A = 0.f, B = 0.f, C = 0.f, D = 0.f;
-    for (int i = 0; i < tab->nring; ++i) {
-        const int len = tab->len[i];
-        if (k < (len >> 1)) {
-            const int o = tab->off[i] + 2 * k;
-            const float c1 = c[o], c2 = c[o + 1], d1 = d[o], d2 = d[o + 1];
-            A = fmaf(c1, d1, A); B = fmaf(c2, d2, B); C = fmaf(c1, d2, C); D = fmaf(c2, d1, D);
-        } else if (k == (len >> 1) && len != N) {
-            const int o = tab->off[i] + 1;
-            A = fmaf(c[o], d[o], A);
-        }
+    for (int i = tab->nring - 1; i >= 0 && k <= (tab->len[i] >> 1); --i) {
+        const int e = tab->coff[i] + k;
+        const float2 c = spec_at(refspec, tab->nc, ref, e), d = spec_at(spec, tab->nc, row, e);
+        A = fmaf(c.x, d.x, A); B = fmaf(c.y, d.y, B); C = fmaf(c.x, d.y, C); D = fmaf(c.y, d.x, D);
     }
     zq_r = A + B; zq_i = D - C; zt_r = A - B; zt_i = -C - D;
 }
-__device__ void pair_dc_nyq(const float* __restrict__ d, const float* __restrict__ c, const CraRingTab* tab,
-                            int N, float& dc, float& nyq)
-{
-    float a = 0.f, b = 0.f;
-    for (int i = 0; i < tab->nring; ++i) {
-        const int o = tab->off[i];
-        a = fmaf(c[o], d[o], a);
-        if (tab->len[i] == N) b = fmaf(c[o + 1], d[o + 1], b);
-    }
-    dc = a; nyq = b;
-}
 
 __global__ void __launch_bounds__(128)
-finalize_kernel(const float* __restrict__ spec, const float* __restrict__ refspec, int R,
+finalize_kernel(const float2* __restrict__ spec, const float2* __restrict__ refspec, int R,
                 const CraRingTab* __restrict__ tab, const CraCand* __restrict__ cand, int ntile_n,
                 CraRowMap map, CraResult* __restrict__ out)
 {
@@ -327,20 +289,19 @@ finalize_kernel(const float* __restrict__ spec, const float* __restrict__ refspe
     const int mirror = (bcode >> 12) & 1;
     const int jtot = bcode & 4095;              // 1-based lag of the maximum
     const int N = tab->maxrin;
-    const float* d = spec + (size_t)row * tab->lcirc;
-    const float* c = refspec + (size_t)iref * tab->lcirc;
 
     double t7[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (int k = 1 + lane; k < N / 2; k += 32) {
+    for (int k = lane; k <= N / 2; k += 32) {
         float qr, qi, tr, ti;
-        pair_freq(d, c, tab, k, N, qr, qi, tr, ti);
+        pair_freq(spec, row, refspec, iref, tab, k, qr, qi, tr, ti);
         const double zr = mirror ? tr : qr, zi = mirror ? ti : qi;
+        const double wgt = (k == 0 || k == N / 2) ? 1.0 : 2.0;
 #pragma unroll
         for (int s = 0; s < 7; ++s) {
             const int m = (jtot - 1 + s - 3 + N) % N;                 // 0-based lag
             const int ph = (int)(((long long)k * m) % N);
             double sn, cs; sincospi(2.0 * (double)ph / (double)N, &sn, &cs);
-            t7[s] += 2.0 * (zr * cs - zi * sn);
+            t7[s] += wgt * (zr * cs - zi * sn);
         }
     }
 #pragma unroll
@@ -348,12 +309,8 @@ finalize_kernel(const float* __restrict__ spec, const float* __restrict__ refspe
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) t7[s] += __shfl_xor_sync(0xffffffffu, t7[s], o);
     if (lane == 0) {
-        float dc, nyq; pair_dc_nyq(d, c, tab, N, dc, nyq);
 #pragma unroll
-        for (int s = 0; s < 7; ++s) {
-            const int m = (jtot - 1 + s - 3 + N) % N;
-            t7[s] = (t7[s] + dc + ((m & 1) ? -(double)nyq : (double)nyq)) / (double)N;
-        }
+        for (int s = 0; s < 7; ++s) t7[s] /= (double)N;
         const double c2 = 49. * t7[0] + 6. * t7[1] - 21. * t7[2] - 32. * t7[3] - 27. * t7[4] - 6. * t7[5] + 31. * t7[6];
         const double c3 = 5. * t7[0] - 3. * t7[2] - 4. * t7[3] - 3. * t7[4] + 5. * t7[6];
         float pos = 0.0f;
@@ -373,37 +330,52 @@ finalize_kernel(const float* __restrict__ spec, const float* __restrict__ refspe
     }
 }
 
-// Test entry: full q/t curves of one pair by direct evaluation (block of N threads).
-__global__ void ccf_curves_kernel(const float* __restrict__ d, const float* __restrict__ c,
+// Test entry: full q/t curves of one pair by direct evaluation.
+__global__ void ccf_curves_kernel(const float2* __restrict__ spec, int row, const float2* __restrict__ refspec, int ref,
                                   const CraRingTab* __restrict__ tab, float* __restrict__ q, float* __restrict__ t)
 {
-    extern __shared__ float4 s_z[];   // N/2 entries: (qr, qi, tr, ti)
+    extern __shared__ float4 s_z[];   // N/2+1 entries: (qr, qi, tr, ti)
     const int N = tab->maxrin;
-    __shared__ float s_dc, s_nyq;
-    for (int k = threadIdx.x; k < N / 2; k += blockDim.x) {
-        float4 z = make_float4(0, 0, 0, 0);
-        if (k > 0) pair_freq(d, c, tab, k, N, z.x, z.y, z.z, z.w);
+    for (int k = threadIdx.x; k <= N / 2; k += blockDim.x) {
+        float4 z;
+        pair_freq(spec, row, refspec, ref, tab, k, z.x, z.y, z.z, z.w);
         s_z[k] = z;
     }
-    if (threadIdx.x == 0) pair_dc_nyq(d, c, tab, N, s_dc, s_nyq);
     __syncthreads();
     for (int m = threadIdx.x; m < N; m += blockDim.x) {
         double aq = 0, at = 0;
-        for (int k = 1; k < N / 2; ++k) {
+        for (int k = 0; k <= N / 2; ++k) {
             const int ph = (int)(((long long)k * m) % N);
             double sn, cs; sincospi(2.0 * (double)ph / (double)N, &sn, &cs);
             const float4 z = s_z[k];
-            aq += 2.0 * (z.x * cs - z.y * sn);
-            at += 2.0 * (z.z * cs - z.w * sn);
+            const double wgt = (k == 0 || k == N / 2) ? 1.0 : 2.0;
+            aq += wgt * (z.x * cs - z.y * sn);
+            at += wgt * (z.z * cs - z.w * sn);
         }
-        const double ny = (m & 1) ? -(double)s_nyq : (double)s_nyq;
-        q[m] = (float)((aq + s_dc + ny) / N);
-        t[m] = (float)((at + s_dc + ny) / N);
+        q[m] = (float)(aq / N);
+        t[m] = (float)(at / N);
     }
 }
 
+// upload the ring table to constant memory when it differs from the resident one
+int bind_ring_table(const CraRingTab& h, cudaStream_t st)
+{
+    static int cur_coff[CRA_MAX_RINGS], cur_half[CRA_MAX_RINGS], cur_n = -1, cur_dev = -1;
+    int half[CRA_MAX_RINGS];
+    for (int i = 0; i < h.nring; ++i) half[i] = h.len[i] >> 1;
+    int dev = 0; cudaGetDevice(&dev);
+    if (cur_n == h.nring && cur_dev == dev && memcmp(cur_coff, h.coff, sizeof(int) * h.nring) == 0 &&
+        memcmp(cur_half, half, sizeof(int) * h.nring) == 0) return 0;
+    CRA_CUDA(cudaStreamSynchronize(st));
+    CRA_CUDA(cudaMemcpyToSymbol(c_coff, h.coff, sizeof(int) * h.nring));
+    CRA_CUDA(cudaMemcpyToSymbol(c_half, half, sizeof(int) * h.nring));
+    memcpy(cur_coff, h.coff, sizeof(int) * h.nring); memcpy(cur_half, half, sizeof(int) * h.nring);
+    cur_n = h.nring; cur_dev = dev;
+    return 0;
+}
+
 template <int LOG2N>
-int launch_ccf_t(const float* spec, int nrows, const float* refspec, int R, const CraRingTab* tab,
+int launch_ccf_t(const float* spec, int nrows, const float* refspec, int R, const CraRingTab& h,
                  const float2* twid, CraCand* cand, int ntile_n, cudaStream_t st)
 {
     using S = Shape<LOG2N>;
@@ -417,7 +389,9 @@ int launch_ccf_t(const float* spec, int nrows, const float* refspec, int R, cons
     const long nblk = ntile_m * ntile_n;
     if (nblk <= 0) return 0;
     if (nblk > 2147483647L) { cra_set_error("ccf grid too large; lower row_batch"); return 1; }
-    ccf_peak_kernel<LOG2N><<<(unsigned)nblk, S::NT, smem, st>>>(spec, nrows, refspec, R, tab, twid, cand, ntile_n);
+    ccf_peak_kernel<LOG2N><<<(unsigned)nblk, S::NT, smem, st>>>(reinterpret_cast<const float4*>(spec), nrows,
+                                                                reinterpret_cast<const float4*>(refspec), R,
+                                                                h.nring, h.nc, twid, cand, ntile_n);
     CRA_CUDA(cudaGetLastError());
     return 0;
 }
@@ -426,16 +400,30 @@ int launch_ccf_t(const float* spec, int nrows, const float* refspec, int R, cons
 
 int cra_ccf_tile_n() { return TN; }
 
+// twiddle table layout the CCF kernel expects: tw[j*N2 + n2] = exp(+2 pi i n2 j / N)
+void cra_ccf_twiddles(int log2n, std::vector<float2>& tw)
+{
+    const int N = 1 << log2n, L1 = log2n / 2, N1 = 1 << L1, N2 = N / N1;
+    tw.resize(N);
+    for (int j = 0; j < N1; ++j)
+        for (int n2 = 0; n2 < N2; ++n2) {
+            const double a = 2.0 * M_PI * (double)((n2 * j) % N) / N;
+            tw[j * N2 + n2] = make_float2((float)cos(a), (float)sin(a));
+        }
+}
+
 int cra_launch_ccf(const float* spec, int nrows, const float* refspec, int R, const CraRingTab* tab,
                    const CraRingTab& htab, const float2* twid, CraCand* cand, int ntile_n, cudaStream_t st)
 {
+    (void)tab;
+    if (bind_ring_table(htab, st)) return 1;
     switch (htab.log2n) {
-        case 5:  return launch_ccf_t<5>(spec, nrows, refspec, R, tab, twid, cand, ntile_n, st);
-        case 6:  return launch_ccf_t<6>(spec, nrows, refspec, R, tab, twid, cand, ntile_n, st);
-        case 7:  return launch_ccf_t<7>(spec, nrows, refspec, R, tab, twid, cand, ntile_n, st);
-        case 8:  return launch_ccf_t<8>(spec, nrows, refspec, R, tab, twid, cand, ntile_n, st);
-        case 9:  return launch_ccf_t<9>(spec, nrows, refspec, R, tab, twid, cand, ntile_n, st);
-        case 10: return launch_ccf_t<10>(spec, nrows, refspec, R, tab, twid, cand, ntile_n, st);
+        case 5:  return launch_ccf_t<5>(spec, nrows, refspec, R, htab, twid, cand, ntile_n, st);
+        case 6:  return launch_ccf_t<6>(spec, nrows, refspec, R, htab, twid, cand, ntile_n, st);
+        case 7:  return launch_ccf_t<7>(spec, nrows, refspec, R, htab, twid, cand, ntile_n, st);
+        case 8:  return launch_ccf_t<8>(spec, nrows, refspec, R, htab, twid, cand, ntile_n, st);
+        case 9:  return launch_ccf_t<9>(spec, nrows, refspec, R, htab, twid, cand, ntile_n, st);
+        case 10: return launch_ccf_t<10>(spec, nrows, refspec, R, htab, twid, cand, ntile_n, st);
         default: cra_set_error("maxrin must be a power of two in [32, 1024]"); return 1;
     }
 }
@@ -446,15 +434,18 @@ int cra_launch_finalize(const float* spec, const float* refspec, int R, const Cr
     (void)htab;
     if (map.np <= 0) return 0;
     const int wpb = 4;
-    finalize_kernel<<<(map.np + wpb - 1) / wpb, wpb * 32, 0, st>>>(spec, refspec, R, tab, cand, ntile_n, map, out);
+    finalize_kernel<<<(map.np + wpb - 1) / wpb, wpb * 32, 0, st>>>(reinterpret_cast<const float2*>(spec),
+                                                                  reinterpret_cast<const float2*>(refspec), R, tab, cand,
+                                                                  ntile_n, map, out);
     CRA_CUDA(cudaGetLastError());
     return 0;
 }
 
-int cra_launch_ccf_curves(const float* spec_row, const float* refspec_row, const CraRingTab* tab, const CraRingTab& htab,
-                          float* q, float* t, cudaStream_t st)
+int cra_launch_ccf_curves(const float* spec, int row, const float* refspec, int ref, const CraRingTab* tab,
+                          const CraRingTab& htab, float* q, float* t, cudaStream_t st)
 {
-    ccf_curves_kernel<<<1, 256, (htab.maxrin / 2) * sizeof(float4), st>>>(spec_row, refspec_row, tab, q, t);
+    ccf_curves_kernel<<<1, 256, (htab.maxrin / 2 + 1) * sizeof(float4), st>>>(reinterpret_cast<const float2*>(spec), row,
+                                                                            reinterpret_cast<const float2*>(refspec), ref, tab, q, t);
     CRA_CUDA(cudaGetLastError());
     return 0;
 }

@@ -3,14 +3,20 @@
 // Data layout in HBM (all float32 unless noted):
 //   images   [P][nx][nx]            resident particle stack (mask-mean subtracted)
 //   refs     [R][nx][nx]            current references
-//   refspec  [R][lcirc]             weighted reference spectra (Applyws applied)
-//   spec     [rows][lcirc]          particle spectra of one row batch; a row is one
-//                                   (particle, shift) pair in the reference's visit order
+//   refspec  [R/4][nc][4] float2    weighted reference spectra (Applyws applied), same layout
+//   spec     [rows/4][nc][4] float2 particle spectra of one row batch; a row is one (particle,
+//                                   shift) pair in the reference's visit order.  Four consecutive
+//                                   rows are interleaved per complex element so the contraction
+//                                   fetches 4 rows with two 128-bit loads (see "device spectrum")
 //   cand     [rows][ntile_n]        best (value, code) of each row x reference tile
 //   sums     [R][2][nx][nx] + [R]   even/odd class sums followed by counts
-// A spectrum is the SPIDER packed per-ring layout of Util.Frngs: ring i occupies
+// Host-visible spectra use the SPIDER packed per-ring layout of Util.Frngs: ring i occupies
 // floats [off_i, off_i+len_i): slot0 = Re F_0, slot1 = Re F_{len/2}, then
 // (Re,Im) F_k for k = 1..len/2-1, F_k = sum_n x_n exp(-2 pi i n k / len).
+// The DEVICE spectrum un-packs that: ring i holds len_i/2+1 complex values F_0..F_{len/2}
+// (imaginary parts of F_0 and F_{len/2} are 0) at complex offset coff_i; nc = lcirc/2 + nring.
+// With it Crosrng_ms needs no special cases: every (ring, k <= len/2) is one complex MAC, and
+// the Nyquist term of a short ring lands on frequency len/2 exactly as q(numr3i+1) does.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -25,13 +31,27 @@ struct CraRingTab {            // device-resident ring table (Numrinit triplets,
     int   off[CRA_MAX_RINGS];
     int   len[CRA_MAX_RINGS];
     int   rad[CRA_MAX_RINGS];
+    int   coff[CRA_MAX_RINGS];   // complex offset of ring i in the device spectrum
+    int   nc;                    // complex elements per device spectrum = lcirc/2 + nring
     float wr[CRA_MAX_RINGS];     // ringwe (Applyws)
     float wn[CRA_MAX_RINGS];     // Normalize_ring weight r*2pi/len
     float nn;                    // sum of wn over every sample, accumulated in float like Normalize_ring
 };
 
+#ifndef CRA_POLAR_RPB
+#define CRA_POLAR_RPB 2        // shift rows resampled per CTA of the polar kernel (1, 2 or 4)
+#endif
+
+struct CraPolarItems {         // flat work lists of the ring FFT passes (device pointers)
+    const int* A; int nA;      // (ring << 16 | column b)   pass A: NA-point DFTs
+    const int* B; int nB;      // (ring << 16 | row ka)     pass B: NB-point DFTs
+    const int* C; int nC;      // (ring << 16 | k)          pass C: split + store, k <= len/4
+};
+
 struct CraRowMap {             // how rows of the current batch map to particles
     const int*       row_start;  // [np+1] first row of each batch-local particle
+    const int*       chunk_start;// [np+1] first polar CTA of each batch-local particle
+    int              nchunks;
     const CraSearch* search;     // [np]   per-particle request (batch-local)
     const int4*      win;        // [np]   lkx, rkx, lky, rky
     int              np;
@@ -52,22 +72,24 @@ void cra_set_error(const std::string& msg);
 // launchers (each defined in its own .cu; all asynchronous on `st`) ----------
 int cra_launch_mask_normalize(float* imgs, int n, int nx, const float* mask, int mode, cudaStream_t st);
 // particle rows described by map -> spec[row]; references -> refspec (weights applied)
-// twid_fwd[j] = exp(-2 pi i j / maxrin), j < maxrin/2
+// twid_fwd[j] = exp(-2 pi i j / maxrin), j < maxrin
+int cra_polar_rows_per_block();
 int cra_launch_polar_rows(const float* images, int nx, const CraRingTab* tab, const CraRingTab& htab,
-                          const float2* samp, const float* sampw, const float2* twid_fwd, CraRowMap map,
-                          int normalize_ring, float* spec, cudaStream_t st);
+                          const float2* samp, const float* sampw, const float2* twid_fwd, const CraPolarItems& items,
+                          CraRowMap map, int normalize_ring, float* spec, cudaStream_t st);
 int cra_launch_polar_refs(const float* refs, int R, int nx, const CraRingTab* tab, const CraRingTab& htab,
-                          const float2* samp, const float2* twid_fwd, float* refspec, cudaStream_t st);
+                          const float2* samp, const float2* twid_fwd, const CraPolarItems& items, float* refspec, cudaStream_t st);
 int cra_launch_polar_single(const float* image, int nx, const CraRingTab* tab, const CraRingTab& htab,
-                            const float2* samp, const float* sampw, const float2* twid_fwd, float cx, float cy,
-                            int normalize_ring, float* spec, cudaStream_t st);
+                            const float2* samp, const float* sampw, const float2* twid_fwd, const CraPolarItems& items,
+                            float cx, float cy, int normalize_ring, float* spec, cudaStream_t st);
 int cra_launch_ccf(const float* spec, int nrows, const float* refspec, int R, const CraRingTab* tab,
                    const CraRingTab& htab, const float2* twid, CraCand* cand, int ntile_n, cudaStream_t st);
 int cra_ccf_tile_n();
 int cra_launch_finalize(const float* spec, const float* refspec, int R, const CraRingTab* tab, const CraRingTab& htab,
                         const CraCand* cand, int ntile_n, CraRowMap map, CraResult* out, cudaStream_t st);
-int cra_launch_ccf_curves(const float* spec_row, const float* refspec_row, const CraRingTab* tab, const CraRingTab& htab,
-                          float* q, float* t, cudaStream_t st);
+int cra_launch_ccf_curves(const float* spec, int row, const float* refspec, int ref, const CraRingTab* tab,
+                          const CraRingTab& htab, float* q, float* t, cudaStream_t st);
+void cra_ccf_twiddles(int log2n, std::vector<float2>& tw);
 int cra_launch_rotsum(const float* images, int nx, int p0, int n, const float4* params, const int* iref,
                       long global_offset, float* sums, float* counts, float* out_images, cudaStream_t st);
 int cra_fp32_peak(double* tf_ffma, double* tf_ffma2);

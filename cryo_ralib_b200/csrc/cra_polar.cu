@@ -4,13 +4,22 @@
 // :200-201 -> EMAN2 Util::multiref_polar_ali_2d inner loop (particles).
 // Replaces cu_resample_to_polar + cuFFT R2C (cuda/gpu_aln_noref.cu:818-879, :1816).
 //
-// One CTA per row (= one particle at one shift, or one reference).  The image tile
-// is staged in shared memory with 128-bit coalesced loads, the 6-tap quadratic
-// interpolation gathers from shared memory, ring sums are reduced with warp
-// shuffles, and every ring is transformed in shared memory by one warp.
+// One CTA per (particle, aligned sub-group of RPB consecutive shift rows).  The image tile
+// is staged once in shared memory with 128-bit coalesced loads and serves all rows of the
+// sub-group; the 6-tap quadratic interpolation gathers from shared memory; the ring sums of
+// Normalize_ring are reduced with warp shuffles.  Every ring is then transformed in shared
+// memory by two register passes (NA x NB points, radix-2 butterflies with immediate
+// twiddles) over flat work lists that keep all threads busy regardless of ring length, and the
+// real-FFT split, Normalize_ring's affine map (applied to the spectrum: FFT is linear) or
+// the Applyws weights, and the store into the interleaved device spectrum are one final pass
+// with 16/32-byte vector stores.
 #include "cra_common.cuh"
+#include "cra_fft.cuh"
 
 namespace {
+
+using crafft::cmul;
+using crafft::fft_reg;
 
 constexpr int kPolarThreads = 256;
 
@@ -40,53 +49,19 @@ __device__ __forceinline__ float quadri_smem(float x, float y, int nx, const flo
     return f0 + dx0 * (c1 + (dx0 - 1.0f) * c2 + dy0 * c5) + dy0 * (c3 + (dy0 - 1.0f) * c4);
 }
 
-__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+// same arithmetic, for sample points whose 3x3 neighbourhood is known to lie inside the frame
+__device__ __forceinline__ float quadri_inside(float x, float y, int nx, const float* __restrict__ f)
 {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-
-// In-place packed real FFT of one ring (len floats at c, 8-byte aligned) by one warp.
-// tw[j] = exp(-2 pi i j / maxrin), j < maxrin/2.
-__device__ void ring_rfft_warp(float* c, int len, int maxrin, const float2* __restrict__ tw, int lane)
-{
-    float2* z = reinterpret_cast<float2*>(c);
-    const int n = len >> 1;
-    const int lg = 31 - __clz(n);
-    for (int i = lane; i < n; i += 32) {
-        int j = (int)(__brev((unsigned)i) >> (32 - lg));
-        if (i < j) { float2 t = z[i]; z[i] = z[j]; z[j] = t; }
-    }
-    __syncwarp();
-    for (int len2 = 2; len2 <= n; len2 <<= 1) {
-        const int half = len2 >> 1;
-        const int tstep = maxrin / len2;
-        for (int b = lane; b < (n >> 1); b += 32) {
-            int k = b & (half - 1);
-            int s = ((b - k) << 1) + k;
-            int e = s + half;
-            float2 w = tw[k * tstep];
-            float2 u = z[s], v = cmul(z[e], w);
-            z[s] = make_float2(u.x + v.x, u.y + v.y);
-            z[e] = make_float2(u.x - v.x, u.y - v.y);
-        }
-        __syncwarp();
-    }
-    // split: F_k = E_k + w_k O_k, F_{n-k} = conj(E_k - w_k O_k)
-    const int tstep = maxrin / len;
-    for (int k = 1 + lane; k <= (n >> 1); k += 32) {
-        int m = n - k;
-        float2 a = z[k], b = z[m];
-        float2 E = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
-        float2 O = make_float2(0.5f * (a.y + b.y), -0.5f * (a.x - b.x));
-        float2 P = cmul(O, tw[k * tstep]);
-        z[k] = make_float2(E.x + P.x, E.y + P.y);
-        z[m] = make_float2(E.x - P.x, -(E.y - P.y));
-    }
-    if (lane == 0) {
-        float2 a = z[0];
-        z[0] = make_float2(a.x + a.y, a.x - a.y);
-    }
-    __syncwarp();
+    const int i = (int)x, j = (int)y;
+    const float dx0 = x - (float)i, dy0 = y - (float)j;
+    const float* p = f + (j - 1) * nx + (i - 1);
+    const float f0 = p[0];
+    const float c1 = p[1] - f0;
+    const float c2 = (c1 - f0 + p[-1]) * 0.5f;
+    const float c3 = p[nx] - f0;
+    const float c4 = (c3 - f0 + p[-nx]) * 0.5f;
+    const float c5 = p[nx + 1] - f0 - c1 - c3;
+    return f0 + dx0 * (c1 + (dx0 - 1.0f) * c2 + dy0 * c5) + dy0 * (c3 + (dy0 - 1.0f) * c4);
 }
 
 __device__ __forceinline__ float warp_sum(float v)
@@ -96,49 +71,89 @@ __device__ __forceinline__ float warp_sum(float v)
     return v;
 }
 
-// mode: 0 = particle rows (optional Normalize_ring), 1 = references (Applyws)
-template <int MODE>
+// pass A of the n = NA*NB point forward FFT of one ring: column b, NA-point DFT, twiddle
+template <int NA, int NB>
+__device__ __forceinline__ void pass_a(float2* __restrict__ z, int b, float2 base)
+{
+    float2 x[NA];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) x[a] = z[a * NB + b];
+    fft_reg<NA, -1>(x);
+    z[b] = x[0];
+    float2 p = base;
+#pragma unroll
+    for (int a = 1; a < NA; ++a) {
+        z[a * NB + b] = cmul(x[a], p);
+        if (a + 1 < NA) p = cmul(p, base);
+    }
+}
+// pass B: row ka, NB-point DFT in place; output X[ka + NA*kb] stays at z[ka*NB + kb]
+template <int NA, int NB>
+__device__ __forceinline__ void pass_b(float2* __restrict__ z, int ka)
+{
+    float2 x[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) x[b] = z[ka * NB + b];
+    fft_reg<NB, -1>(x);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) z[ka * NB + b] = x[b];
+}
+
+struct Chunk { int part, row0, nrow; };
+
+// MODE: 0 = particle rows (optional Normalize_ring), 1 = references (Applyws)
+template <int MODE, int RPB>
 __global__ void __launch_bounds__(kPolarThreads)
 polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __restrict__ tab,
                  const float2* __restrict__ samp, const float* __restrict__ sampw,
-                 const float2* __restrict__ twid, CraRowMap map, float fix_cx, float fix_cy,
-                 int normalize_ring, float* __restrict__ spec)
+                 const float2* __restrict__ twid, CraPolarItems items, CraRowMap map,
+                 float fix_cx, float fix_cy, int normalize_ring, float* __restrict__ spec)
 {
     extern __shared__ __align__(16) float smem[];
     const int npix = nx * nx;
     const int lcirc = tab->lcirc;
+    const int lcp = (lcirc + 3) & ~3;
     const int maxrin = tab->maxrin;
     float* s_img = smem;                                     // npix (padded to 4)
-    float* s_circ = smem + ((npix + 3) & ~3);                // lcirc
-    float2* s_tw = reinterpret_cast<float2*>(s_circ + ((lcirc + 3) & ~3));   // maxrin/2
-    __shared__ float s_red[2][kPolarThreads / 32];
-    __shared__ int s_part;
-    __shared__ float s_cx, s_cy;
+    float* s_circ = smem + ((npix + 3) & ~3);                // RPB * lcp
+    float2* s_tw = reinterpret_cast<float2*>(s_circ + RPB * lcp);   // maxrin : exp(-2 pi i j / maxrin)
+    __shared__ float s_red[kPolarThreads / 32][2 * RPB];
+    __shared__ Chunk s_chunk;
+    __shared__ float s_cx[RPB], s_cy[RPB], s_avg[RPB], s_isg[RPB];
 
-    const int row = blockIdx.x;
     const int tid = threadIdx.x;
     if (tid == 0) {
-        if (MODE == 1) {                       // reference j at the image centre
-            s_part = row; s_cx = (float)(nx / 2 + 1); s_cy = s_cx;
+        Chunk c;
+        if (MODE == 1) {                       // reference j at the image centre, one row
+            c.part = blockIdx.x; c.row0 = blockIdx.x; c.nrow = 1;
+            s_cx[0] = (float)(nx / 2 + 1); s_cy[0] = s_cx[0];
         } else if (map.row_start == nullptr) { // single explicit centre (tests)
-            s_part = map.p0; s_cx = fix_cx; s_cy = fix_cy;
+            c.part = map.p0; c.row0 = 0; c.nrow = 1; s_cx[0] = fix_cx; s_cy[0] = fix_cy;
         } else {
-            int lo = 0, hi = map.np;           // last p with row_start[p] <= row
-            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (map.row_start[mid] <= row) lo = mid; else hi = mid; }
-            int li = row - map.row_start[lo];
-            int4 w = map.win[lo];
-            int wx = w.x + w.y + 1;
-            int i = li / wx - w.z;             // y index, outer loop of multiref_polar_ali_2d
-            int j = li % wx - w.x;             // x index, inner loop
-            float iy = i * map.step, ix = j * map.step;
-            s_part = map.p0 + lo;
-            s_cx = map.search[lo].cx + ix;
-            s_cy = map.search[lo].cy + iy;
+            const int b = blockIdx.x;
+            int lo = 0, hi = map.np;           // last p with chunk_start[p] <= b
+            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (map.chunk_start[mid] <= b) lo = mid; else hi = mid; }
+            const int rs = map.row_start[lo], re = map.row_start[lo + 1];
+            const int g = rs / RPB + (b - map.chunk_start[lo]);
+            c.part = map.p0 + lo;
+            c.row0 = max(rs, g * RPB);
+            c.nrow = min(re, (g + 1) * RPB) - c.row0;
+            const int4 w = map.win[lo];
+            const int wx = w.x + w.y + 1;
+            for (int r = 0; r < c.nrow; ++r) {
+                const int li = c.row0 + r - rs;
+                const int i = li / wx - w.z;   // y index, outer loop of multiref_polar_ali_2d
+                const int j = li % wx - w.x;   // x index, inner loop
+                s_cx[r] = map.search[lo].cx + j * map.step;
+                s_cy[r] = map.search[lo].cy + i * map.step;
+            }
         }
+        s_chunk = c;
     }
-    for (int i = tid; i < maxrin / 2; i += kPolarThreads) s_tw[i] = twid[i];
+    for (int i = tid; i < maxrin; i += kPolarThreads) s_tw[i] = twid[i];
     __syncthreads();
-    const float* img = images + (size_t)s_part * npix;
+    const Chunk ck = s_chunk;
+    const float* img = images + (size_t)ck.part * npix;
     if ((npix & 3) == 0) {
         const float4* g4 = reinterpret_cast<const float4*>(img);
         float4* s4 = reinterpret_cast<float4*>(s_img);
@@ -148,50 +163,152 @@ polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __r
     }
     __syncthreads();
 
-    const float cx = s_cx, cy = s_cy;
-    float av = 0.f, sq = 0.f;
-    for (int i = tid; i < lcirc; i += kPolarThreads) {
-        float2 p = samp[i];
-        float v = quadri_smem(p.x + cx, p.y + cy, nx, s_img);
-        s_circ[i] = v;
-        if (MODE == 0) { float w = sampw[i]; av += v * w; sq += v * v * w; }
-    }
-    if (MODE == 0 && normalize_ring) {
-        av = warp_sum(av); sq = warp_sum(sq);
-        if ((tid & 31) == 0) { s_red[0][tid >> 5] = av; s_red[1][tid >> 5] = sq; }
-        __syncthreads();
-        float a = 0.f, s = 0.f;
+    // ---- resample every row of the sub-group -------------------------------------------------
+    const float rmax = (float)tab->rad[tab->nring - 1];
+    float av[RPB], sq[RPB];
 #pragma unroll
-        for (int w = 0; w < kPolarThreads / 32; ++w) { a += s_red[0][w]; s += s_red[1][w]; }
-        const float nn = tab->nn;
-        const float avg = a / nn;
-        const float sgm = sqrtf((s - a * a / nn) / nn);
-        for (int i = tid; i < lcirc; i += kPolarThreads) s_circ[i] = (s_circ[i] - avg) / sgm;
-    }
-    __syncthreads();
-
-    // one warp per ring, longest rings first
-    const int warp = tid >> 5, lane = tid & 31, nwarp = kPolarThreads / 32;
-    for (int r = tab->nring - 1 - warp; r >= 0; r -= nwarp) {
-        const int len = tab->len[r];
-        float* c = s_circ + tab->off[r];
-        ring_rfft_warp(c, len, maxrin, s_tw, lane);
-        if (MODE == 1) {
-            const float w = tab->wr[r];
-            for (int i = lane; i < len; i += 32) {
-                float ww = (i == 1 && len != maxrin) ? 0.5f * w : w;
-                c[i] *= ww;
+    for (int r = 0; r < RPB; ++r) { av[r] = 0.f; sq[r] = 0.f; }
+#pragma unroll
+    for (int r = 0; r < RPB; ++r) {
+        if (r < ck.nrow) {
+            const float cx = s_cx[r], cy = s_cy[r];
+            float* circ = s_circ + r * lcp;
+            const bool inside = (cx - rmax >= 2.0f) && (cx + rmax <= (float)(nx - 1)) &&
+                                (cy - rmax >= 2.0f) && (cy + rmax <= (float)(nx - 1));
+            if (inside) {
+                for (int i = tid; i < lcirc; i += kPolarThreads) {
+                    const float2 p = __ldg(samp + i);
+                    const float v = quadri_inside(p.x + cx, p.y + cy, nx, s_img);
+                    circ[i] = v;
+                    if (MODE == 0) { const float w = __ldg(sampw + i); av[r] += v * w; sq[r] += v * v * w; }
+                }
+            } else {
+                for (int i = tid; i < lcirc; i += kPolarThreads) {
+                    const float2 p = __ldg(samp + i);
+                    const float v = quadri_smem(p.x + cx, p.y + cy, nx, s_img);
+                    circ[i] = v;
+                    if (MODE == 0) { const float w = __ldg(sampw + i); av[r] += v * w; sq[r] += v * v * w; }
+                }
             }
         }
     }
+    if (MODE == 0 && normalize_ring) {
+#pragma unroll
+        for (int r = 0; r < RPB; ++r) { av[r] = warp_sum(av[r]); sq[r] = warp_sum(sq[r]); }
+        if ((tid & 31) == 0) {
+#pragma unroll
+            for (int r = 0; r < RPB; ++r) { s_red[tid >> 5][2 * r] = av[r]; s_red[tid >> 5][2 * r + 1] = sq[r]; }
+        }
+    }
     __syncthreads();
-    float* out = spec + (size_t)row * lcirc;
-    if ((lcirc & 3) == 0) {
-        const float4* s4 = reinterpret_cast<const float4*>(s_circ);
-        float4* o4 = reinterpret_cast<float4*>(out);
-        for (int i = tid; i < (lcirc >> 2); i += kPolarThreads) o4[i] = s4[i];
-    } else {
-        for (int i = tid; i < lcirc; i += kPolarThreads) out[i] = s_circ[i];
+    if (tid < RPB) {
+        float avg = 0.f, isg = 1.f;
+        if (MODE == 0 && normalize_ring) {
+            float a = 0.f, s = 0.f;
+#pragma unroll
+            for (int w = 0; w < kPolarThreads / 32; ++w) { a += s_red[w][2 * tid]; s += s_red[w][2 * tid + 1]; }
+            const float nn = tab->nn;
+            avg = a / nn;
+            isg = 1.0f / sqrtf((s - a * a / nn) / nn);
+        }
+        s_avg[tid] = avg; s_isg[tid] = isg;
+    }
+
+    // ---- ring FFTs: pass A -------------------------------------------------------------------
+    for (int it = tid; it < items.nA * ck.nrow; it += kPolarThreads) {
+        const int r = it / items.nA, item = __ldg(items.A + (it - r * items.nA));
+        const int ring = item >> 16, b = item & 0xffff;
+        const int len = tab->len[ring];
+        float2* z = reinterpret_cast<float2*>(s_circ + r * lcp + tab->off[ring]);
+        const int lg = 31 - __clz(len >> 1);
+        const float2 base = s_tw[b * (maxrin / (len >> 1))];     // exp(-2 pi i b / n)
+        switch (lg) {
+            case 2: pass_a<2, 2>(z, b, base); break;
+            case 3: pass_a<2, 4>(z, b, base); break;
+            case 4: pass_a<4, 4>(z, b, base); break;
+            case 5: pass_a<4, 8>(z, b, base); break;
+            case 6: pass_a<8, 8>(z, b, base); break;
+            case 7: pass_a<8, 16>(z, b, base); break;
+            case 8: pass_a<16, 16>(z, b, base); break;
+            default: pass_a<16, 32>(z, b, base); break;
+        }
+    }
+    __syncthreads();
+    // ---- pass B ------------------------------------------------------------------------------
+    for (int it = tid; it < items.nB * ck.nrow; it += kPolarThreads) {
+        const int r = it / items.nB, item = __ldg(items.B + (it - r * items.nB));
+        const int ring = item >> 16, ka = item & 0xffff;
+        const int len = tab->len[ring];
+        float2* z = reinterpret_cast<float2*>(s_circ + r * lcp + tab->off[ring]);
+        const int lg = 31 - __clz(len >> 1);
+        switch (lg) {
+            case 2: pass_b<2, 2>(z, ka); break;
+            case 3: pass_b<2, 4>(z, ka); break;
+            case 4: pass_b<4, 4>(z, ka); break;
+            case 5: pass_b<4, 8>(z, ka); break;
+            case 6: pass_b<8, 8>(z, ka); break;
+            case 7: pass_b<8, 16>(z, ka); break;
+            case 8: pass_b<16, 16>(z, ka); break;
+            default: pass_b<16, 32>(z, ka); break;
+        }
+    }
+    __syncthreads();
+    // ---- pass C: real-FFT split, Normalize_ring / Applyws, store ------------------------------
+    // Z_k of the half-length complex FFT sits at z[(k % NA)*NB + k / NA];
+    // F_k = E_k + w_k O_k, F_{n-k} = conj(E_k - w_k O_k), w_k = exp(-2 pi i k / len)
+    const bool vec = (ck.nrow == RPB) && (ck.row0 % RPB == 0);
+    float2* const out0 = reinterpret_cast<float2*>(spec) + (size_t)(ck.row0 >> 2) * tab->nc * 4 + (ck.row0 & 3);
+    for (int it = tid; it < items.nC; it += kPolarThreads) {
+        const int item = __ldg(items.C + it);
+        const int ring = item >> 16, k = item & 0xffff;
+        const int len = tab->len[ring], n = len >> 1;
+        const int lg = 31 - __clz(n);
+        const int la = lg >> 1, NA = 1 << la, NB = n >> la;
+        const int m = (k == 0) ? 0 : n - k;
+        const int pk = (k & (NA - 1)) * NB + (k >> la), pm = (m & (NA - 1)) * NB + (m >> la);
+        const float2 wk = s_tw[k * (maxrin / len)];
+        float wgt = 1.0f, wnyq = 1.0f;
+        if (MODE == 1) { wgt = tab->wr[ring]; wnyq = (len != maxrin) ? 0.5f * wgt : wgt; }
+        float2 fk[RPB], fm[RPB];
+#pragma unroll
+        for (int r = 0; r < RPB; ++r) {
+            fk[r] = make_float2(0.f, 0.f); fm[r] = fk[r];
+            if (r < ck.nrow) {
+                const float2* z = reinterpret_cast<const float2*>(s_circ + r * lcp + tab->off[ring]);
+                const float2 a = z[pk], b = z[pm];
+                const float sc = s_isg[r];
+                if (k == 0) {
+                    float dc = a.x + a.y, ny = a.x - a.y;
+                    if (MODE == 0) { dc = (dc - s_avg[r] * (float)len) * sc; ny *= sc; }
+                    fk[r] = make_float2(dc * wgt, 0.f);
+                    fm[r] = make_float2(ny * wnyq, 0.f);           // F_n: the ring's Nyquist term
+                } else {
+                    const float2 E = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
+                    const float2 O = make_float2(0.5f * (a.y + b.y), -0.5f * (a.x - b.x));
+                    const float2 P = cmul(O, wk);
+                    const float s2 = (MODE == 0) ? sc : wgt;
+                    fk[r] = make_float2((E.x + P.x) * s2, (E.y + P.y) * s2);
+                    fm[r] = make_float2((E.x - P.x) * s2, -(E.y - P.y) * s2);
+                }
+            }
+        }
+        float2* ok = out0 + (size_t)(tab->coff[ring] + k) * 4;
+        float2* om = out0 + (size_t)(tab->coff[ring] + ((k == 0) ? n : m)) * 4;
+        if (vec && RPB == 4) {
+            *reinterpret_cast<float4*>(ok) = make_float4(fk[0].x, fk[0].y, fk[1 % RPB].x, fk[1 % RPB].y);
+            *reinterpret_cast<float4*>(ok + 2) = make_float4(fk[2 % RPB].x, fk[2 % RPB].y, fk[3 % RPB].x, fk[3 % RPB].y);
+            if (om != ok) {
+                *reinterpret_cast<float4*>(om) = make_float4(fm[0].x, fm[0].y, fm[1 % RPB].x, fm[1 % RPB].y);
+                *reinterpret_cast<float4*>(om + 2) = make_float4(fm[2 % RPB].x, fm[2 % RPB].y, fm[3 % RPB].x, fm[3 % RPB].y);
+            }
+        } else if (vec && RPB == 2) {
+            *reinterpret_cast<float4*>(ok) = make_float4(fk[0].x, fk[0].y, fk[1 % RPB].x, fk[1 % RPB].y);
+            if (om != ok) *reinterpret_cast<float4*>(om) = make_float4(fm[0].x, fm[0].y, fm[1 % RPB].x, fm[1 % RPB].y);
+        } else {
+#pragma unroll
+            for (int r = 0; r < RPB; ++r)
+                if (r < ck.nrow) { ok[r] = fk[r]; if (om != ok) om[r] = fm[r]; }
+        }
     }
 }
 
@@ -224,14 +341,35 @@ mask_normalize_kernel(float* __restrict__ imgs, int npix, const float* __restric
     for (int i = threadIdx.x; i < npix; i += blockDim.x) img[i] = (img[i] - mean) / sig;
 }
 
+template <int RPB>
 size_t polar_smem_bytes(int nx, const CraRingTab& h)
 {
     size_t npix = ((size_t)nx * nx + 3) & ~(size_t)3;
     size_t lc = ((size_t)h.lcirc + 3) & ~(size_t)3;
-    return (npix + lc) * sizeof(float) + (size_t)(h.maxrin / 2) * sizeof(float2);
+    return (npix + RPB * lc) * sizeof(float) + (size_t)h.maxrin * sizeof(float2);
+}
+
+template <int MODE, int RPB>
+int launch_polar(const float* images, int nx, const CraRingTab* tab, const CraRingTab& htab,
+                 const float2* samp, const float* sampw, const float2* twid, const CraPolarItems& items,
+                 CraRowMap map, float cx, float cy, int normalize_ring, float* spec, int nblocks, cudaStream_t st)
+{
+    if (nblocks <= 0) return 0;
+    size_t smem = polar_smem_bytes<RPB>(nx, htab);
+    static size_t configured = 0;
+    if (smem > configured) {
+        CRA_CUDA(cudaFuncSetAttribute(polar_fft_kernel<MODE, RPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    polar_fft_kernel<MODE, RPB><<<nblocks, kPolarThreads, smem, st>>>(images, nx, tab, samp, sampw, twid, items, map,
+                                                                     cx, cy, normalize_ring, spec);
+    CRA_CUDA(cudaGetLastError());
+    return 0;
 }
 
 }  // namespace
+
+int cra_polar_rows_per_block() { return CRA_POLAR_RPB; }
 
 int cra_launch_mask_normalize(float* imgs, int n, int nx, const float* mask, int mode, cudaStream_t st)
 {
@@ -241,43 +379,26 @@ int cra_launch_mask_normalize(float* imgs, int n, int nx, const float* mask, int
     return 0;
 }
 
-template <int MODE>
-static int launch_polar(const float* images, int nx, const CraRingTab* tab, const CraRingTab& htab,
-                        const float2* samp, const float* sampw, const float2* twid,
-                        CraRowMap map, float cx, float cy, int normalize_ring, float* spec, int nblocks, cudaStream_t st)
-{
-    if (nblocks <= 0) return 0;
-    size_t smem = polar_smem_bytes(nx, htab);
-    static size_t configured = 0;
-    if (smem > configured) {
-        CRA_CUDA(cudaFuncSetAttribute(polar_fft_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
-    polar_fft_kernel<MODE><<<nblocks, kPolarThreads, smem, st>>>(images, nx, tab, samp, sampw, twid, map,
-                                                                cx, cy, normalize_ring, spec);
-    CRA_CUDA(cudaGetLastError());
-    return 0;
-}
-
 int cra_launch_polar_rows(const float* images, int nx, const CraRingTab* tab, const CraRingTab& htab,
-                          const float2* samp, const float* sampw, const float2* twid, CraRowMap map,
-                          int normalize_ring, float* spec, cudaStream_t st)
+                          const float2* samp, const float* sampw, const float2* twid, const CraPolarItems& items,
+                          CraRowMap map, int normalize_ring, float* spec, cudaStream_t st)
 {
-    return launch_polar<0>(images, nx, tab, htab, samp, sampw, twid, map, 0.f, 0.f, normalize_ring, spec, map.nrows, st);
+    return launch_polar<0, CRA_POLAR_RPB>(images, nx, tab, htab, samp, sampw, twid, items, map, 0.f, 0.f,
+                                          normalize_ring, spec, map.nchunks, st);
 }
 
 int cra_launch_polar_refs(const float* refs, int R, int nx, const CraRingTab* tab, const CraRingTab& htab,
-                          const float2* samp, const float2* twid, float* refspec, cudaStream_t st)
+                          const float2* samp, const float2* twid, const CraPolarItems& items, float* refspec, cudaStream_t st)
 {
     CraRowMap map{};
-    return launch_polar<1>(refs, nx, tab, htab, samp, nullptr, twid, map, 0.f, 0.f, 0, refspec, R, st);
+    return launch_polar<1, 1>(refs, nx, tab, htab, samp, nullptr, twid, items, map, 0.f, 0.f, 0, refspec, R, st);
 }
 
 int cra_launch_polar_single(const float* image, int nx, const CraRingTab* tab, const CraRingTab& htab,
-                            const float2* samp, const float* sampw, const float2* twid, float cx, float cy,
-                            int normalize_ring, float* spec, cudaStream_t st)
+                            const float2* samp, const float* sampw, const float2* twid, const CraPolarItems& items,
+                            float cx, float cy, int normalize_ring, float* spec, cudaStream_t st)
 {
     CraRowMap map{};
     map.row_start = nullptr; map.p0 = 0;
-    return launch_polar<0>(image, nx, tab, htab, samp, sampw, twid, map, cx, cy, normalize_ring, spec, 1, st);
+    return launch_polar<0, 1>(image, nx, tab, htab, samp, sampw, twid, items, map, cx, cy, normalize_ring, spec, 1, st);
 }
