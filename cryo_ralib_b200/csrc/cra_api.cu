@@ -28,7 +28,7 @@ struct CraCtx {
     CraAlignStats stats{};
     // device
     CraRingTab* d_tab = nullptr;
-    float2* d_samp = nullptr; float* d_sampw = nullptr;
+    float4* d_samp = nullptr; float* d_sampw = nullptr;
     float2* d_twf = nullptr;  float2* d_twi = nullptr;
     int* d_items = nullptr; CraPolarItems items{};
     float* d_mask = nullptr;
@@ -81,7 +81,8 @@ int build_tables(CraCtx* c)
         cra_set_error("maxrin must be a power of two in [32,1024] (ou between 3 and ~160)"); return 1;
     }
     float nn = 0.0f;
-    std::vector<float2> samp(t.lcirc);
+    std::vector<float4> samp(t.lcirc);
+    int pacc = 0;
     std::vector<float> sampw(t.lcirc);
     const double dpi = 2 * atan(1.0);
     for (int i = 0; i < nring; ++i) {
@@ -96,15 +97,26 @@ int build_tables(CraCtx* c)
             float x, y;
             if (jt == 0) { x = 0.0f; y = (float)inr; }
             else { float fi = (float)(dfi * jt); x = sinf(fi) * inr; y = cosf(fi) * inr; }
-            samp[off + jt] = make_float2(x, y);
-            samp[off + jt + lt] = make_float2(y, -x);
-            samp[off + jt + 2 * lt] = make_float2(-x, -y);
-            samp[off + jt + 3 * lt] = make_float2(-y, x);
+            samp[off + jt] = make_float4(x, y, 0.f, 0.f);
+            samp[off + jt + lt] = make_float4(y, -x, 0.f, 0.f);
+            samp[off + jt + 2 * lt] = make_float4(-x, -y, 0.f, 0.f);
+            samp[off + jt + 3 * lt] = make_float4(-y, x, 0.f, 0.f);
         }
-        for (int j = 0; j < len; ++j) { sampw[off + j] = t.wn[i]; nn += t.wn[i]; }
+        // padded smem placement: the ring is n = len/2 complex values in rows of NB (+1 pad)
+        const int n = len >> 1, lgn = ilog2_floor(n), NA = 1 << (lgn / 2), NB = n / NA;
+        t.poff[i] = pacc;
+        pacc += NA * (NB + 1);
+        for (int j = 0; j < len; ++j) {
+            sampw[off + j] = t.wn[i]; nn += t.wn[i];
+            const int p = j >> 1;
+            const int slot = 2 * (t.poff[i] + p + p / NB) + (j & 1);
+            samp[off + j].z = t.wn[i];
+            memcpy(&samp[off + j].w, &slot, sizeof(int));
+        }
     }
     t.nn = nn;
     t.nc = t.lcirc / 2 + nring;
+    t.lcpad = (2 * pacc + 3) & ~3;
     std::vector<float2> twf(t.maxrin), twi;
     for (int j = 0; j < t.maxrin; ++j) {
         double a = -2.0 * M_PI * j / t.maxrin; twf[j] = make_float2((float)cos(a), (float)sin(a));
@@ -139,8 +151,8 @@ int build_tables(CraCtx* c)
         }
     CRA_CUDA(cudaMalloc(&c->d_tab, sizeof(CraRingTab)));
     CRA_CUDA(cudaMemcpy(c->d_tab, &t, sizeof(CraRingTab), cudaMemcpyHostToDevice));
-    CRA_CUDA(cudaMalloc(&c->d_samp, sizeof(float2) * t.lcirc));
-    CRA_CUDA(cudaMemcpy(c->d_samp, samp.data(), sizeof(float2) * t.lcirc, cudaMemcpyHostToDevice));
+    CRA_CUDA(cudaMalloc(&c->d_samp, sizeof(float4) * t.lcirc));
+    CRA_CUDA(cudaMemcpy(c->d_samp, samp.data(), sizeof(float4) * t.lcirc, cudaMemcpyHostToDevice));
     CRA_CUDA(cudaMalloc(&c->d_sampw, sizeof(float) * t.lcirc));
     CRA_CUDA(cudaMemcpy(c->d_sampw, sampw.data(), sizeof(float) * t.lcirc, cudaMemcpyHostToDevice));
     CRA_CUDA(cudaMalloc(&c->d_twf, sizeof(float2) * twf.size()));
@@ -520,7 +532,7 @@ static void unpack_spectrum(const CraCtx* c, int lane4, float* out)
         const int half = t.len[i] >> 1;
         float* o = out + t.off[i];
         for (int k = 0; k <= half; ++k) {
-            const float2 v = c->h_group[((size_t)t.coff[i] + k) * 4 + lane4];
+            const float2 v = c->h_group[cra_spec_idx(t.coff[i], half, lane4, k)];
             if (k == 0) o[0] = v.x;
             else if (k == half) o[1] = v.x;
             else { o[2 * k] = v.x; o[2 * k + 1] = v.y; }

@@ -90,30 +90,35 @@ __device__ __forceinline__ void contract_freq(int k, int nring, const float4* __
 #pragma unroll
         for (int n = 0; n < TN; ++n) { a.A[m][n] = 0.f; a.B[m][n] = 0.f; a.C[m][n] = 0.f; a.D[m][n] = 0.f; }
 
-    // rings in descending length: stop at the first ring that no longer reaches frequency k
+    // rings in descending length: stop at the first ring that no longer reaches frequency k.
+    // Operands are prefetched two rings ahead through three register buffers.
+#define CRA_HAS(j) ((j) >= 0 && k < c_half[(j) < 0 ? 0 : (j)])
+#define CRA_LOAD(D, C, j)                                                                        \
+    { const int e_ = 2 * c_coff[j] + k, p_ = c_half[j] + 1;                                      \
+      D[0] = __ldg(dq + e_); D[1] = __ldg(dq + e_ + p_); C[0] = __ldg(cq + e_); C[1] = __ldg(cq + e_ + p_); }
     int i = nring - 1;
-    float4 d0[2], c0[2], d1[2], c1[2];
-    {
-        const int e = (c_coff[i] + k) * 2;
-        d0[0] = __ldg(dq + e); d0[1] = __ldg(dq + e + 1); c0[0] = __ldg(cq + e); c0[1] = __ldg(cq + e + 1);
-    }
+    float4 d0[2], c0[2], d1[2], c1[2], d2[2], c2[2];
+    CRA_LOAD(d0, c0, i);
+    bool h1 = CRA_HAS(i - 1);
+    if (h1) CRA_LOAD(d1, c1, i - 1);
     for (;;) {
-        const bool m1 = (i >= 1) && (k <= c_half[i - 1]);
-        if (m1) {
-            const int e = (c_coff[i - 1] + k) * 2;
-            d1[0] = __ldg(dq + e); d1[1] = __ldg(dq + e + 1); c1[0] = __ldg(cq + e); c1[1] = __ldg(cq + e + 1);
-        }
+        const bool h2 = h1 && CRA_HAS(i - 2);
+        if (h2) CRA_LOAD(d2, c2, i - 2);
         ring_fma(a, d0, c0);
-        if (!m1) break;
-        const bool m0 = (i >= 2) && (k <= c_half[i - 2]);
-        if (m0) {
-            const int e = (c_coff[i - 2] + k) * 2;
-            d0[0] = __ldg(dq + e); d0[1] = __ldg(dq + e + 1); c0[0] = __ldg(cq + e); c0[1] = __ldg(cq + e + 1);
-        }
+        if (!h1) break;
+        const bool h3 = h2 && CRA_HAS(i - 3);
+        if (h3) CRA_LOAD(d0, c0, i - 3);
         ring_fma(a, d1, c1);
-        if (!m0) break;
-        i -= 2;
+        if (!h2) break;
+        const bool h4 = h3 && CRA_HAS(i - 4);
+        if (h4) CRA_LOAD(d1, c1, i - 4);
+        ring_fma(a, d2, c2);
+        if (!h3) break;
+        h1 = h4;
+        i -= 3;
     }
+#undef CRA_HAS
+#undef CRA_LOAD
     const int kk = (N - k) & (N - 1);
     const int i0 = (k >> S::L2) * (N2 + 1) + (k & (N2 - 1));
     const int i1 = (kk >> S::L2) * (N2 + 1) + (kk & (N2 - 1));
@@ -152,20 +157,57 @@ ccf_peak_kernel(const float4* __restrict__ spec, int nrows, const float4* __rest
         contract_freq<LOG2N>(tid, nring, dq, cq, s_w);
         if (tid >= NQ) contract_freq<LOG2N>(tid + N / 8, nring, dq, cq, s_w);
     }
-    // frequency N/2 (real): only full-length rings reach it; one pair per lane of the last warp
+    // Real-valued ring elements.  (i) frequency N/2: only full-length rings reach it; one pair per
+    // lane of the last warp.  (ii) the Nyquist term of every shorter ring (frequency len/2 < N/2,
+    // Crosrng_ms q(numr3i+1)): summed per length class by the lanes of warp 1 % nwarps, the least
+    // loaded warp, and folded into W after the barrier.
+    __shared__ float s_nyq[NP][8];
+    const int nl = tid - ((NT >= 64) ? 32 : 0);
+    const bool nyq_lane = (nl >= 0 && nl < 32);
     {
+        const float2* d2 = reinterpret_cast<const float2*>(dq);
+        const float2* c2 = reinterpret_cast<const float2*>(cq);
         const int l = tid - (NT - 32);
         if (l >= 0 && l < NP) {
             const int m = l / TN, n = l % TN;
-            const float2* d2 = reinterpret_cast<const float2*>(dq);
-            const float2* c2 = reinterpret_cast<const float2*>(cq);
             float a = 0.f;
-            for (int i = nring - 1; i >= 0 && c_half[i] == N / 2; --i) {
-                const int e = (c_coff[i] + N / 2) * 4;
-                a = fmaf(__ldg(c2 + e + n).x, __ldg(d2 + e + m).x, a);
-            }
+            for (int i = nring - 1; i >= 0 && c_half[i] == N / 2; --i)
+                a = fmaf(__ldg(c2 + cra_spec_idx(c_coff[i], N / 2, n, N / 2)).x,
+                         __ldg(d2 + cra_spec_idx(c_coff[i], N / 2, m, N / 2)).x, a);
             const int h = N / 2;
             s_w[l * PS + (h >> S::L2) * (N2 + 1) + (h & (N2 - 1))] = make_float2(a, a);
+        }
+        if (nyq_lane) {
+            const int pair = nl & (NP - 1), part = nl / NP, m = pair / TN, n = pair % TN;
+            int cls = -1, cur = -1; float a = 0.f;
+            for (int i = 0; i < nring && c_half[i] < N / 2; ++i) {
+                const int h = c_half[i];
+                if (h != cur) {
+                    if (cls >= 0 && (cls & 1) == part) s_nyq[pair][cls & 7] = a;
+                    cur = h; ++cls; a = 0.f;
+                }
+                if ((cls & 1) == part)
+                    a = fmaf(__ldg(c2 + cra_spec_idx(c_coff[i], h, n, h)).x, __ldg(d2 + cra_spec_idx(c_coff[i], h, m, h)).x, a);
+            }
+            if (cls >= 0 && (cls & 1) == part) s_nyq[pair][cls & 7] = a;
+        }
+    }
+    __syncthreads();
+    if (nyq_lane) {
+        const int pair = nl & (NP - 1), part = nl / NP;
+        float2* w = s_w + pair * PS;
+        int cls = -1, cur = -1;
+        for (int i = 0; i < nring && c_half[i] < N / 2; ++i) {
+            const int h = c_half[i];
+            if (h == cur) continue;
+            cur = h; ++cls;
+            if ((cls & 1) != part) continue;
+            const float a = s_nyq[pair][cls & 7];
+            const int hh = N - h;
+            float2* p0 = w + (h >> S::L2) * (N2 + 1) + (h & (N2 - 1));
+            float2* p1 = w + (hh >> S::L2) * (N2 + 1) + (hh & (N2 - 1));
+            float2 v = *p0; v.x += a; v.y += a; *p0 = v;
+            v = *p1; v.x += a; v.y += a; *p1 = v;
         }
     }
     __syncthreads();
@@ -238,9 +280,9 @@ ccf_peak_kernel(const float4* __restrict__ spec, int nrows, const float4* __rest
 }
 
 // ---- scalar helpers on the device spectrum layout (finalize / test entry) -------------------
-__device__ __forceinline__ float2 spec_at(const float2* __restrict__ base, int nc, int row, int e)
+__device__ __forceinline__ float2 spec_at(const float2* __restrict__ base, int nc, int row, int coff, int half, int k)
 {
-    return base[((size_t)(row >> 2) * nc + e) * 4 + (row & 3)];
+    return base[(size_t)(row >> 2) * nc * 4 + cra_spec_idx(coff, half, row, k)];
 }
 
 // q_k and t_k of one (row, ref) pair at frequency k, 0 <= k <= N/2
@@ -249,8 +291,8 @@ __device__ void pair_freq(const float2* __restrict__ spec, int row, const float2
 {
     float A = 0.f, B = 0.f, C = 0.f, D = 0.f;
     for (int i = tab->nring - 1; i >= 0 && k <= (tab->len[i] >> 1); --i) {
-        const int e = tab->coff[i] + k;
-        const float2 c = spec_at(refspec, tab->nc, ref, e), d = spec_at(spec, tab->nc, row, e);
+        const int co = tab->coff[i], hf = tab->len[i] >> 1;
+        const float2 c = spec_at(refspec, tab->nc, ref, co, hf, k), d = spec_at(spec, tab->nc, row, co, hf, k);
         A = fmaf(c.x, d.x, A); B = fmaf(c.y, d.y, B); C = fmaf(c.x, d.y, C); D = fmaf(c.y, d.x, D);
     }
     zq_r = A + B; zq_i = D - C; zt_r = A - B; zt_i = -C - D;

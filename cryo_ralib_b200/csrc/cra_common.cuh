@@ -4,10 +4,12 @@
 //   images   [P][nx][nx]            resident particle stack (mask-mean subtracted)
 //   refs     [R][nx][nx]            current references
 //   refspec  [R/4][nc][4] float2    weighted reference spectra (Applyws applied), same layout
-//   spec     [rows/4][nc][4] float2 particle spectra of one row batch; a row is one (particle,
+//   spec     [rows/4][2*nc] float4  particle spectra of one row batch; a row is one (particle,
 //                                   shift) pair in the reference's visit order.  Four consecutive
-//                                   rows are interleaved per complex element so the contraction
-//                                   fetches 4 rows with two 128-bit loads (see "device spectrum")
+//                                   rows form a group; per ring the group stores two planes of
+//                                   len/2+1 float4, plane 0 = rows (0,1), plane 1 = rows (2,3), so
+//                                   the contraction fetches 4 rows with two fully coalesced
+//                                   128-bit loads (see "device spectrum")
 //   cand     [rows][ntile_n]        best (value, code) of each row x reference tile
 //   sums     [R][2][nx][nx] + [R]   even/odd class sums followed by counts
 // Host-visible spectra use the SPIDER packed per-ring layout of Util.Frngs: ring i occupies
@@ -33,6 +35,8 @@ struct CraRingTab {            // device-resident ring table (Numrinit triplets,
     int   rad[CRA_MAX_RINGS];
     int   coff[CRA_MAX_RINGS];   // complex offset of ring i in the device spectrum
     int   nc;                    // complex elements per device spectrum = lcirc/2 + nring
+    int   poff[CRA_MAX_RINGS];   // float2 offset of ring i in the polar kernel's padded smem buffer
+    int   lcpad;                 // floats per padded smem ring buffer (rows of NB complex + 1 pad)
     float wr[CRA_MAX_RINGS];     // ringwe (Applyws)
     float wn[CRA_MAX_RINGS];     // Normalize_ring weight r*2pi/len
     float nn;                    // sum of wn over every sample, accumulated in float like Normalize_ring
@@ -60,6 +64,12 @@ struct CraRowMap {             // how rows of the current batch map to particles
     float            step;
 };
 
+// float2 index, inside a 4-row group, of (row r, ring with complex offset coff and len/2 = half, k)
+__host__ __device__ __forceinline__ size_t cra_spec_idx(int coff, int half, int r, int k)
+{
+    return ((size_t)2 * coff + (size_t)((r & 3) >> 1) * (half + 1) + k) * 2 + (r & 1);
+}
+
 struct CraCand { float v; int code; };   // code = iref*8192 + mirror*4096 + j   (j = 1-based lag index)
 
 // error plumbing -------------------------------------------------------------
@@ -75,12 +85,12 @@ int cra_launch_mask_normalize(float* imgs, int n, int nx, const float* mask, int
 // twid_fwd[j] = exp(-2 pi i j / maxrin), j < maxrin
 int cra_polar_rows_per_block();
 int cra_launch_polar_rows(const float* images, int nx, const CraRingTab* tab, const CraRingTab& htab,
-                          const float2* samp, const float* sampw, const float2* twid_fwd, const CraPolarItems& items,
+                          const float4* samp, const float* sampw, const float2* twid_fwd, const CraPolarItems& items,
                           CraRowMap map, int normalize_ring, float* spec, cudaStream_t st);
 int cra_launch_polar_refs(const float* refs, int R, int nx, const CraRingTab* tab, const CraRingTab& htab,
-                          const float2* samp, const float2* twid_fwd, const CraPolarItems& items, float* refspec, cudaStream_t st);
+                          const float4* samp, const float2* twid_fwd, const CraPolarItems& items, float* refspec, cudaStream_t st);
 int cra_launch_polar_single(const float* image, int nx, const CraRingTab* tab, const CraRingTab& htab,
-                            const float2* samp, const float* sampw, const float2* twid_fwd, const CraPolarItems& items,
+                            const float4* samp, const float* sampw, const float2* twid_fwd, const CraPolarItems& items,
                             float cx, float cy, int normalize_ring, float* spec, cudaStream_t st);
 int cra_launch_ccf(const float* spec, int nrows, const float* refspec, int R, const CraRingTab* tab,
                    const CraRingTab& htab, const float2* twid, CraCand* cand, int ntile_n, cudaStream_t st);

@@ -77,26 +77,27 @@ __device__ __forceinline__ void pass_a(float2* __restrict__ z, int b, float2 bas
 {
     float2 x[NA];
 #pragma unroll
-    for (int a = 0; a < NA; ++a) x[a] = z[a * NB + b];
+    for (int a = 0; a < NA; ++a) x[a] = z[a * (NB + 1) + b];
     fft_reg<NA, -1>(x);
     z[b] = x[0];
     float2 p = base;
 #pragma unroll
     for (int a = 1; a < NA; ++a) {
-        z[a * NB + b] = cmul(x[a], p);
+        z[a * (NB + 1) + b] = cmul(x[a], p);
         if (a + 1 < NA) p = cmul(p, base);
     }
 }
-// pass B: row ka, NB-point DFT in place; output X[ka + NA*kb] stays at z[ka*NB + kb]
+// pass B: row ka, NB-point DFT in place; output X[ka + NA*kb] stays at z[ka*(NB+1) + kb]
+// (rows of the ring buffer are padded by one complex so that both passes are conflict-free)
 template <int NA, int NB>
 __device__ __forceinline__ void pass_b(float2* __restrict__ z, int ka)
 {
     float2 x[NB];
 #pragma unroll
-    for (int b = 0; b < NB; ++b) x[b] = z[ka * NB + b];
+    for (int b = 0; b < NB; ++b) x[b] = z[ka * (NB + 1) + b];
     fft_reg<NB, -1>(x);
 #pragma unroll
-    for (int b = 0; b < NB; ++b) z[ka * NB + b] = x[b];
+    for (int b = 0; b < NB; ++b) z[ka * (NB + 1) + b] = x[b];
 }
 
 struct Chunk { int part, row0, nrow; };
@@ -105,14 +106,14 @@ struct Chunk { int part, row0, nrow; };
 template <int MODE, int RPB>
 __global__ void __launch_bounds__(kPolarThreads)
 polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __restrict__ tab,
-                 const float2* __restrict__ samp, const float* __restrict__ sampw,
+                 const float4* __restrict__ samp, const float* __restrict__ sampw,
                  const float2* __restrict__ twid, CraPolarItems items, CraRowMap map,
                  float fix_cx, float fix_cy, int normalize_ring, float* __restrict__ spec)
 {
     extern __shared__ __align__(16) float smem[];
     const int npix = nx * nx;
     const int lcirc = tab->lcirc;
-    const int lcp = (lcirc + 3) & ~3;
+    const int lcp = tab->lcpad;
     const int maxrin = tab->maxrin;
     float* s_img = smem;                                     // npix (padded to 4)
     float* s_circ = smem + ((npix + 3) & ~3);                // RPB * lcp
@@ -177,17 +178,17 @@ polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __r
                                 (cy - rmax >= 2.0f) && (cy + rmax <= (float)(nx - 1));
             if (inside) {
                 for (int i = tid; i < lcirc; i += kPolarThreads) {
-                    const float2 p = __ldg(samp + i);
+                    const float4 p = __ldg(samp + i);            // x, y, Normalize_ring weight, smem slot
                     const float v = quadri_inside(p.x + cx, p.y + cy, nx, s_img);
-                    circ[i] = v;
-                    if (MODE == 0) { const float w = __ldg(sampw + i); av[r] += v * w; sq[r] += v * v * w; }
+                    circ[__float_as_int(p.w)] = v;
+                    if (MODE == 0) { av[r] += v * p.z; sq[r] += v * v * p.z; }
                 }
             } else {
                 for (int i = tid; i < lcirc; i += kPolarThreads) {
-                    const float2 p = __ldg(samp + i);
+                    const float4 p = __ldg(samp + i);
                     const float v = quadri_smem(p.x + cx, p.y + cy, nx, s_img);
-                    circ[i] = v;
-                    if (MODE == 0) { const float w = __ldg(sampw + i); av[r] += v * w; sq[r] += v * v * w; }
+                    circ[__float_as_int(p.w)] = v;
+                    if (MODE == 0) { av[r] += v * p.z; sq[r] += v * v * p.z; }
                 }
             }
         }
@@ -219,7 +220,7 @@ polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __r
         const int r = it / items.nA, item = __ldg(items.A + (it - r * items.nA));
         const int ring = item >> 16, b = item & 0xffff;
         const int len = tab->len[ring];
-        float2* z = reinterpret_cast<float2*>(s_circ + r * lcp + tab->off[ring]);
+        float2* z = reinterpret_cast<float2*>(s_circ + r * lcp) + tab->poff[ring];
         const int lg = 31 - __clz(len >> 1);
         const float2 base = s_tw[b * (maxrin / (len >> 1))];     // exp(-2 pi i b / n)
         switch (lg) {
@@ -239,7 +240,7 @@ polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __r
         const int r = it / items.nB, item = __ldg(items.B + (it - r * items.nB));
         const int ring = item >> 16, ka = item & 0xffff;
         const int len = tab->len[ring];
-        float2* z = reinterpret_cast<float2*>(s_circ + r * lcp + tab->off[ring]);
+        float2* z = reinterpret_cast<float2*>(s_circ + r * lcp) + tab->poff[ring];
         const int lg = 31 - __clz(len >> 1);
         switch (lg) {
             case 2: pass_b<2, 2>(z, ka); break;
@@ -254,10 +255,10 @@ polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __r
     }
     __syncthreads();
     // ---- pass C: real-FFT split, Normalize_ring / Applyws, store ------------------------------
-    // Z_k of the half-length complex FFT sits at z[(k % NA)*NB + k / NA];
+    // Z_k of the half-length complex FFT sits at z[(k % NA)*(NB+1) + k / NA];
     // F_k = E_k + w_k O_k, F_{n-k} = conj(E_k - w_k O_k), w_k = exp(-2 pi i k / len)
     const bool vec = (ck.nrow == RPB) && (ck.row0 % RPB == 0);
-    float2* const out0 = reinterpret_cast<float2*>(spec) + (size_t)(ck.row0 >> 2) * tab->nc * 4 + (ck.row0 & 3);
+    float2* const grp = reinterpret_cast<float2*>(spec) + (size_t)(ck.row0 >> 2) * tab->nc * 4;
     for (int it = tid; it < items.nC; it += kPolarThreads) {
         const int item = __ldg(items.C + it);
         const int ring = item >> 16, k = item & 0xffff;
@@ -265,7 +266,7 @@ polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __r
         const int lg = 31 - __clz(n);
         const int la = lg >> 1, NA = 1 << la, NB = n >> la;
         const int m = (k == 0) ? 0 : n - k;
-        const int pk = (k & (NA - 1)) * NB + (k >> la), pm = (m & (NA - 1)) * NB + (m >> la);
+        const int pk = (k & (NA - 1)) * (NB + 1) + (k >> la), pm = (m & (NA - 1)) * (NB + 1) + (m >> la);
         const float2 wk = s_tw[k * (maxrin / len)];
         float wgt = 1.0f, wnyq = 1.0f;
         if (MODE == 1) { wgt = tab->wr[ring]; wnyq = (len != maxrin) ? 0.5f * wgt : wgt; }
@@ -274,7 +275,7 @@ polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __r
         for (int r = 0; r < RPB; ++r) {
             fk[r] = make_float2(0.f, 0.f); fm[r] = fk[r];
             if (r < ck.nrow) {
-                const float2* z = reinterpret_cast<const float2*>(s_circ + r * lcp + tab->off[ring]);
+                const float2* z = reinterpret_cast<const float2*>(s_circ + r * lcp) + tab->poff[ring];
                 const float2 a = z[pk], b = z[pm];
                 const float sc = s_isg[r];
                 if (k == 0) {
@@ -292,22 +293,26 @@ polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __r
                 }
             }
         }
-        float2* ok = out0 + (size_t)(tab->coff[ring] + k) * 4;
-        float2* om = out0 + (size_t)(tab->coff[ring] + ((k == 0) ? n : m)) * 4;
+        const int coff = tab->coff[ring], km = (k == 0) ? n : m;     // n = len/2: the Nyquist slot
         if (vec && RPB == 4) {
-            *reinterpret_cast<float4*>(ok) = make_float4(fk[0].x, fk[0].y, fk[1 % RPB].x, fk[1 % RPB].y);
-            *reinterpret_cast<float4*>(ok + 2) = make_float4(fk[2 % RPB].x, fk[2 % RPB].y, fk[3 % RPB].x, fk[3 % RPB].y);
-            if (om != ok) {
-                *reinterpret_cast<float4*>(om) = make_float4(fm[0].x, fm[0].y, fm[1 % RPB].x, fm[1 % RPB].y);
-                *reinterpret_cast<float4*>(om + 2) = make_float4(fm[2 % RPB].x, fm[2 % RPB].y, fm[3 % RPB].x, fm[3 % RPB].y);
+            float4* o0 = reinterpret_cast<float4*>(grp) + 2 * coff, *o1 = o0 + (n + 1);
+            o0[k] = make_float4(fk[0].x, fk[0].y, fk[1 % RPB].x, fk[1 % RPB].y);
+            o1[k] = make_float4(fk[2 % RPB].x, fk[2 % RPB].y, fk[3 % RPB].x, fk[3 % RPB].y);
+            if (km != k) {
+                o0[km] = make_float4(fm[0].x, fm[0].y, fm[1 % RPB].x, fm[1 % RPB].y);
+                o1[km] = make_float4(fm[2 % RPB].x, fm[2 % RPB].y, fm[3 % RPB].x, fm[3 % RPB].y);
             }
         } else if (vec && RPB == 2) {
-            *reinterpret_cast<float4*>(ok) = make_float4(fk[0].x, fk[0].y, fk[1 % RPB].x, fk[1 % RPB].y);
-            if (om != ok) *reinterpret_cast<float4*>(om) = make_float4(fm[0].x, fm[0].y, fm[1 % RPB].x, fm[1 % RPB].y);
+            float4* o = reinterpret_cast<float4*>(grp) + 2 * coff + ((ck.row0 & 3) >> 1) * (n + 1);
+            o[k] = make_float4(fk[0].x, fk[0].y, fk[1 % RPB].x, fk[1 % RPB].y);
+            if (km != k) o[km] = make_float4(fm[0].x, fm[0].y, fm[1 % RPB].x, fm[1 % RPB].y);
         } else {
 #pragma unroll
             for (int r = 0; r < RPB; ++r)
-                if (r < ck.nrow) { ok[r] = fk[r]; if (om != ok) om[r] = fm[r]; }
+                if (r < ck.nrow) {
+                    grp[cra_spec_idx(coff, n, ck.row0 + r, k)] = fk[r];
+                    if (km != k) grp[cra_spec_idx(coff, n, ck.row0 + r, km)] = fm[r];
+                }
         }
     }
 }
@@ -345,13 +350,13 @@ template <int RPB>
 size_t polar_smem_bytes(int nx, const CraRingTab& h)
 {
     size_t npix = ((size_t)nx * nx + 3) & ~(size_t)3;
-    size_t lc = ((size_t)h.lcirc + 3) & ~(size_t)3;
+    size_t lc = (size_t)h.lcpad;
     return (npix + RPB * lc) * sizeof(float) + (size_t)h.maxrin * sizeof(float2);
 }
 
 template <int MODE, int RPB>
 int launch_polar(const float* images, int nx, const CraRingTab* tab, const CraRingTab& htab,
-                 const float2* samp, const float* sampw, const float2* twid, const CraPolarItems& items,
+                 const float4* samp, const float* sampw, const float2* twid, const CraPolarItems& items,
                  CraRowMap map, float cx, float cy, int normalize_ring, float* spec, int nblocks, cudaStream_t st)
 {
     if (nblocks <= 0) return 0;
@@ -380,7 +385,7 @@ int cra_launch_mask_normalize(float* imgs, int n, int nx, const float* mask, int
 }
 
 int cra_launch_polar_rows(const float* images, int nx, const CraRingTab* tab, const CraRingTab& htab,
-                          const float2* samp, const float* sampw, const float2* twid, const CraPolarItems& items,
+                          const float4* samp, const float* sampw, const float2* twid, const CraPolarItems& items,
                           CraRowMap map, int normalize_ring, float* spec, cudaStream_t st)
 {
     return launch_polar<0, CRA_POLAR_RPB>(images, nx, tab, htab, samp, sampw, twid, items, map, 0.f, 0.f,
@@ -388,14 +393,14 @@ int cra_launch_polar_rows(const float* images, int nx, const CraRingTab* tab, co
 }
 
 int cra_launch_polar_refs(const float* refs, int R, int nx, const CraRingTab* tab, const CraRingTab& htab,
-                          const float2* samp, const float2* twid, const CraPolarItems& items, float* refspec, cudaStream_t st)
+                          const float4* samp, const float2* twid, const CraPolarItems& items, float* refspec, cudaStream_t st)
 {
     CraRowMap map{};
     return launch_polar<1, 1>(refs, nx, tab, htab, samp, nullptr, twid, items, map, 0.f, 0.f, 0, refspec, R, st);
 }
 
 int cra_launch_polar_single(const float* image, int nx, const CraRingTab* tab, const CraRingTab& htab,
-                            const float2* samp, const float* sampw, const float2* twid, const CraPolarItems& items,
+                            const float4* samp, const float* sampw, const float2* twid, const CraPolarItems& items,
                             float cx, float cy, int normalize_ring, float* spec, cudaStream_t st)
 {
     CraRowMap map{};
