@@ -12,7 +12,8 @@ CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libcryo_ralib.so")
 SOURCES = ["cra_api.cu", "cra_polar.cu", "cra_ccf.cu", "cra_rotsum.cu", "cra_compat.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+EXTRA = os.environ.get("CRA_NVCC_EXTRA", "").split()
+FLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"]
 
 

@@ -81,8 +81,8 @@ int build_tables(CraCtx* c)
         cra_set_error("maxrin must be a power of two in [32,1024] (ou between 3 and ~160)"); return 1;
     }
     float nn = 0.0f;
-    std::vector<float4> samp(t.lcirc);
-    int pacc = 0;
+    std::vector<float4> samp(t.lcirc / 4);   // one quarter of every ring: x, y, ring, jt
+    int pacc = 0, qacc = 0;
     std::vector<float> sampw(t.lcirc);
     const double dpi = 2 * atan(1.0);
     for (int i = 0; i < nring; ++i) {
@@ -97,22 +97,15 @@ int build_tables(CraCtx* c)
             float x, y;
             if (jt == 0) { x = 0.0f; y = (float)inr; }
             else { float fi = (float)(dfi * jt); x = sinf(fi) * inr; y = cosf(fi) * inr; }
-            samp[off + jt] = make_float4(x, y, 0.f, 0.f);
-            samp[off + jt + lt] = make_float4(y, -x, 0.f, 0.f);
-            samp[off + jt + 2 * lt] = make_float4(-x, -y, 0.f, 0.f);
-            samp[off + jt + 3 * lt] = make_float4(-y, x, 0.f, 0.f);
+            float4 e = make_float4(x, y, 0.f, 0.f);
+            memcpy(&e.z, &i, sizeof(int)); memcpy(&e.w, &jt, sizeof(int));
+            samp[qacc++] = e;
         }
         // padded smem placement: the ring is n = len/2 complex values in rows of NB (+1 pad)
         const int n = len >> 1, lgn = ilog2_floor(n), NA = 1 << (lgn / 2), NB = n / NA;
         t.poff[i] = pacc;
         pacc += NA * (NB + 1);
-        for (int j = 0; j < len; ++j) {
-            sampw[off + j] = t.wn[i]; nn += t.wn[i];
-            const int p = j >> 1;
-            const int slot = 2 * (t.poff[i] + p + p / NB) + (j & 1);
-            samp[off + j].z = t.wn[i];
-            memcpy(&samp[off + j].w, &slot, sizeof(int));
-        }
+        for (int j = 0; j < len; ++j) { sampw[off + j] = t.wn[i]; nn += t.wn[i]; }
     }
     t.nn = nn;
     t.nc = t.lcirc / 2 + nring;
@@ -151,8 +144,8 @@ int build_tables(CraCtx* c)
         }
     CRA_CUDA(cudaMalloc(&c->d_tab, sizeof(CraRingTab)));
     CRA_CUDA(cudaMemcpy(c->d_tab, &t, sizeof(CraRingTab), cudaMemcpyHostToDevice));
-    CRA_CUDA(cudaMalloc(&c->d_samp, sizeof(float4) * t.lcirc));
-    CRA_CUDA(cudaMemcpy(c->d_samp, samp.data(), sizeof(float4) * t.lcirc, cudaMemcpyHostToDevice));
+    CRA_CUDA(cudaMalloc(&c->d_samp, sizeof(float4) * samp.size()));
+    CRA_CUDA(cudaMemcpy(c->d_samp, samp.data(), sizeof(float4) * samp.size(), cudaMemcpyHostToDevice));
     CRA_CUDA(cudaMalloc(&c->d_sampw, sizeof(float) * t.lcirc));
     CRA_CUDA(cudaMemcpy(c->d_sampw, sampw.data(), sizeof(float) * t.lcirc, cudaMemcpyHostToDevice));
     CRA_CUDA(cudaMalloc(&c->d_twf, sizeof(float2) * twf.size()));

@@ -26,7 +26,7 @@
 #include <vector>
 #include "../../include/cryo_ralib.h"
 
-#define CRA_MAX_RINGS 512
+#define CRA_MAX_RINGS 192
 
 struct CraRingTab {            // device-resident ring table (Numrinit triplets, 0-based offsets)
     int   nring, lcirc, maxrin, log2n;

@@ -121,6 +121,7 @@ polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __r
     __shared__ float s_red[kPolarThreads / 32][2 * RPB];
     __shared__ Chunk s_chunk;
     __shared__ float s_cx[RPB], s_cy[RPB], s_avg[RPB], s_isg[RPB];
+    __shared__ int4 s_ring[CRA_MAX_RINGS];
 
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -152,6 +153,10 @@ polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __r
         s_chunk = c;
     }
     for (int i = tid; i < maxrin; i += kPolarThreads) s_tw[i] = twid[i];
+    for (int i = tid; i < tab->nring; i += kPolarThreads) {
+        const int n = tab->len[i] >> 1, lg = 31 - __clz(n);
+        s_ring[i] = make_int4(tab->poff[i], lg - (lg >> 1), tab->len[i] >> 2, __float_as_int(tab->wn[i]));
+    }
     __syncthreads();
     const Chunk ck = s_chunk;
     const float* img = images + (size_t)ck.part * npix;
@@ -165,30 +170,44 @@ polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __r
     __syncthreads();
 
     // ---- resample every row of the sub-group -------------------------------------------------
+    // The table holds one quarter of every ring (alrl_ms builds the other three by symmetry:
+    // (x,y) -> (y,-x) -> (-x,-y) -> (-y,x)); 23 KB for ou=36, so it stays L1-resident.
     const float rmax = (float)tab->rad[tab->nring - 1];
     float av[RPB], sq[RPB];
-#pragma unroll
-    for (int r = 0; r < RPB; ++r) { av[r] = 0.f; sq[r] = 0.f; }
+    bool all_inside = true;
 #pragma unroll
     for (int r = 0; r < RPB; ++r) {
+        av[r] = 0.f; sq[r] = 0.f;
         if (r < ck.nrow) {
             const float cx = s_cx[r], cy = s_cy[r];
-            float* circ = s_circ + r * lcp;
-            const bool inside = (cx - rmax >= 2.0f) && (cx + rmax <= (float)(nx - 1)) &&
-                                (cy - rmax >= 2.0f) && (cy + rmax <= (float)(nx - 1));
-            if (inside) {
-                for (int i = tid; i < lcirc; i += kPolarThreads) {
-                    const float4 p = __ldg(samp + i);            // x, y, Normalize_ring weight, smem slot
-                    const float v = quadri_inside(p.x + cx, p.y + cy, nx, s_img);
-                    circ[__float_as_int(p.w)] = v;
-                    if (MODE == 0) { av[r] += v * p.z; sq[r] += v * v * p.z; }
-                }
-            } else {
-                for (int i = tid; i < lcirc; i += kPolarThreads) {
-                    const float4 p = __ldg(samp + i);
-                    const float v = quadri_smem(p.x + cx, p.y + cy, nx, s_img);
-                    circ[__float_as_int(p.w)] = v;
-                    if (MODE == 0) { av[r] += v * p.z; sq[r] += v * v * p.z; }
+            all_inside = all_inside && (cx - rmax >= 2.0f) && (cx + rmax <= (float)(nx - 1)) &&
+                         (cy - rmax >= 2.0f) && (cy + rmax <= (float)(nx - 1));
+        }
+    }
+    const int nq = lcirc >> 2;
+    for (int q = tid; q < nq; q += kPolarThreads) {
+        const float4 e = __ldg(samp + q);                 // x, y, ring, jt
+        const int4 rp = s_ring[__float_as_int(e.z)];      // poff, log2 NB, len/4, Normalize_ring weight
+        const int jt = __float_as_int(e.w);
+        const float wn = __int_as_float(rp.w);
+        const float ox[4] = {e.x, e.y, -e.x, -e.y}, oy[4] = {e.y, -e.x, -e.y, e.x};
+        int slot[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int j = jt + m * rp.z, p = j >> 1;
+            slot[m] = 2 * (rp.x + p + (p >> rp.y)) + (j & 1);
+        }
+#pragma unroll
+        for (int r = 0; r < RPB; ++r) {
+            if (r < ck.nrow) {
+                const float cx = s_cx[r], cy = s_cy[r];
+                float* circ = s_circ + r * lcp;
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    const float v = all_inside ? quadri_inside(ox[m] + cx, oy[m] + cy, nx, s_img)
+                                               : quadri_smem(ox[m] + cx, oy[m] + cy, nx, s_img);
+                    circ[slot[m]] = v;
+                    if (MODE == 0) { av[r] += v * wn; sq[r] += v * v * wn; }
                 }
             }
         }

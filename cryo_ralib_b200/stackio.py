@@ -1,0 +1,59 @@
+"""Minimal image-stack I/O for the drivers: .npy and MRC2014 mode-2 (.mrc/.mrcs) stacks in,
+per-iteration reference stacks and text parameter rows out.  EMAN2 HDF/BDB containers are the
+reference's formats (test_mref.py:155, :285, :304-313) and are out of scope here."""
+import os
+import struct
+
+import numpy as np
+
+
+def read_stack(path):
+    ext = os.path.splitext(path)[1].lower()
+    if ext == ".npy":
+        a = np.load(path)
+    elif ext in (".mrc", ".mrcs", ".st"):
+        with open(path, "rb") as f:
+            hdr = f.read(1024)
+            nx, ny, nz, mode = struct.unpack("<4i", hdr[:16])
+            nsymbt = struct.unpack("<i", hdr[92:96])[0]
+            if mode != 2:
+                raise ValueError("only MRC mode 2 (float32) stacks are supported, got mode %d" % mode)
+            f.seek(1024 + nsymbt)
+            a = np.frombuffer(f.read(4 * nx * ny * nz), "<f4").reshape(nz, ny, nx)
+    else:
+        raise ValueError("unsupported stack format '%s' (use .npy or .mrcs)" % ext)
+    a = np.ascontiguousarray(a, np.float32)
+    if a.ndim == 2:
+        a = a[None]
+    if a.ndim != 3 or a.shape[1] != a.shape[2]:
+        raise ValueError("stack must be [n][nx][nx] with square images")
+    return a
+
+
+def write_stack(path, a):
+    a = np.ascontiguousarray(a, np.float32)
+    ext = os.path.splitext(path)[1].lower()
+    if ext == ".npy":
+        np.save(path, a)
+        return
+    nz, ny, nx = a.shape
+    hdr = bytearray(1024)
+    struct.pack_into("<4i", hdr, 0, nx, ny, nz, 2)
+    struct.pack_into("<3i", hdr, 28, nx, ny, nz)
+    struct.pack_into("<3f", hdr, 40, float(nx), float(ny), float(nz))
+    struct.pack_into("<3f", hdr, 52, 90.0, 90.0, 90.0)
+    struct.pack_into("<3i", hdr, 64, 1, 2, 3)
+    struct.pack_into("<3f", hdr, 76, float(a.min()), float(a.max()), float(a.mean()))
+    hdr[208:212] = b"MAP "
+    hdr[212:216] = bytes([0x44, 0x44, 0, 0])
+    with open(path, "wb") as f:
+        f.write(bytes(hdr))
+        f.write(a.tobytes())
+
+
+def write_params(path, params, assign=None, first_index=0):
+    """Rows 'idx angle sx sy mirror class' (the layout src/utils_ralib.py:31-32 parses)."""
+    with open(path, "w") as f:
+        for i, p in enumerate(params):
+            cls = int(assign[i]) if assign is not None else 0
+            f.write("%d %.6f %.6f %.6f %d %d\n" % (first_index + i, p[0], p[1], p[2], int(p[3]), cls))

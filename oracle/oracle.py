@@ -484,3 +484,65 @@ def mref_ali2d(images, refs, ir=1, ou=-1, rs=1, xr=0, yr=0, ts=1, center=1, maxi
         history.append(dict(params=params.copy(), assign=assign.copy(), peak=peak.copy(),
                             sums=sums, counts=counts.copy(), refs=refs.copy(), info=info))
     return params, assign, refs, history
+
+
+def fsc_mask(img1, img2, mask):
+    """sp_statistics.fsc_mask (test_reffree.py:708)."""
+    m = mask > 0.5
+    a = (img1 - np.float32(img1[m].astype(np.float64).mean())) * mask
+    b = (img2 - np.float32(img2[m].astype(np.float64).mean())) * mask
+    return fsc(a, b)
+
+
+def ali2d_base(images, ir=1, ou=-1, rs=1, xr=0, yr=0, ts=1, center=-1, maxit=10, nthreads=1):
+    """Reference-free alignment, CPU twin (ali2d_base, test_reffree.py:515-837; the per-particle
+    step is Sphire's ali2d_single_iter -> ormq: no ring normalisation, clamped shifts, the
+    average's centre shift cs folded into the parameters)."""
+    images = np.array(images, np.float32)
+    P, nx = images.shape[0], images.shape[-1]
+    if ou == -1:
+        ou = nx // 2 - 2
+    mask = model_circle(ou, nx)
+    numr = numrinit(ir, ou, rs)
+    wr = ringwe(numr)
+    imgs = np.stack([normalize_mask(im, mask, 0) for im in images])
+    params = np.zeros((P, 4))
+    cnx = nx // 2 + 1
+    mashi = cnx - ou - 2
+    sx_sum = sy_sum = 0.0
+    history = []
+    tavg = None
+    for it in range(int(maxit)):
+        ave = np.zeros((2, nx, nx), np.float32)
+        for i in range(P):
+            ave[i % 2] += rot_shift2d(imgs[i], params[i, 0], params[i, 1], params[i, 2], int(params[i, 3]))
+        tavg = (ave[0] + ave[1]) / np.float32(P)
+        frsc = fsc_mask(ave[0], ave[1], mask)
+        if center == -1:
+            tavg, _, filt = ref_ali2d(mask, 0, tavg, frsc)
+            cs = [float(sx_sum) / P, float(sy_sum) / P]
+            tavg = fshift(tavg, -cs[0], -cs[1])
+        else:
+            tavg, cs, filt = ref_ali2d(mask, center, tavg, frsc)
+        history.append(dict(cs=cs, filter=filt, tavg=tavg.copy()))
+        if it == int(maxit) - 1:
+            break
+        cimage = applyws(frngs(polar2dm(tavg, float(cnx), float(cnx), numr), numr), numr, wr)[None]
+        centres = np.zeros((P, 2), np.float32); win = np.zeros((P, 4), np.float32)
+        sxi = np.zeros(P); syi = np.zeros(P)
+        for i in range(P):
+            a, sx, sy, _ = combine_params2(params[i, 0], params[i, 1], params[i, 2], int(params[i, 3]), 0.0, -cs[0], -cs[1], 0)
+            _, x, y, _ = inverse_transform2(a, sx, sy)
+            x = min(max(x, -mashi), mashi); y = min(max(y, -mashi), mashi)
+            sxi[i], syi[i] = x, y
+            tx = search_range(nx, ou, x, xr); ty = search_range(nx, ou, y, yr)
+            centres[i] = (cnx + x, cnx + y); win[i] = (tx[0], tx[1], ty[0], ty[1])
+        out = align_batch(imgs, cimage, numr, centres, win, ts, False, nthreads)
+        sx_sum = sy_sum = 0.0
+        for i in range(P):
+            a, sx, sy, m = combine_params2(0.0, -sxi[i], -syi[i], 0, out[i, 0], out[i, 1], out[i, 2], int(out[i, 3]))
+            params[i] = (a, sx, sy, m)
+            sx_sum += sx if m == 0 else -sx
+            sy_sum += sy
+        history[-1]["peak"] = out[:, 5].copy()
+    return params, tavg, history
