@@ -52,6 +52,12 @@ struct Shape {
     static constexpr int NW = 3 * N / 8;                      // working threads (upper quarter: two frequencies each)
     static constexpr int NT = ((NW + 31) / 32) * 32 < 32 ? 32 : ((NW + 31) / 32) * 32;
     static constexpr int PS = N1 * (N2 + 1);                  // padded float2 stride of one pair
+    // sub-tiles per CTA (row groups x reference groups), bounded by shared memory for the W buffers
+    // (measured on B200: 2x2 sub-tiles relying on L1 sharing alone are slower than 1x1 -- 26.3 vs
+    //  19.6 ms per 1e7 alignments -- so sharing is done explicitly by the staged kernel instead)
+    static constexpr int SUBM = 1;
+    static constexpr int SUBN = 1;
+    static constexpr int NSUB = SUBM * SUBN;
 };
 
 __device__ __forceinline__ bool better(float v, int m, float bv, int bm)
@@ -133,22 +139,34 @@ __device__ __forceinline__ void contract_freq(int k, int nring, const float4* __
         }
 }
 
+// A CTA runs SUBM x SUBN independent 16-pair sub-tiles (each NT threads) side by side: 2 row groups
+// x 2 reference groups.  They walk the rings in step, so the row spectra fetched by one sub-tile are
+// L1 hits for its neighbour and the L2 -> SM traffic per pair halves (the kernel is L2-bandwidth
+// bound otherwise: 188 KB of operands per 16 pairs).
 template <int LOG2N>
-__global__ void __launch_bounds__(Shape<LOG2N>::NT)
+__global__ void __launch_bounds__(Shape<LOG2N>::NT * Shape<LOG2N>::NSUB)
 ccf_peak_kernel(const float4* __restrict__ spec, int nrows, const float4* __restrict__ refspec, int R,
-                int nring, int nc, const float2* __restrict__ twid, CraCand* __restrict__ cand, int ntile_n)
+                int nring, int nc, const float2* __restrict__ twid, CraCand* __restrict__ cand, int ntile_n,
+                int ntile_m, int ncta_n)
 {
     using S = Shape<LOG2N>;
     constexpr int N = S::N, N1 = S::N1, N2 = S::N2, NT = S::NT, PS = S::PS, NQ = S::NQ, NW = S::NW;
+    constexpr int SUBM = S::SUBM, SUBN = S::SUBN, NSUB = S::NSUB;
     extern __shared__ __align__(16) float2 s_dyn[];
-    float2* s_w = s_dyn;                 // NP * PS
-    float2* s_tw = s_dyn + NP * PS;      // N : s_tw[j*N2 + n2] = exp(+2 pi i n2 j / N)
-    __shared__ CraCand s_pair[NP];
+    const int sub = threadIdx.x / NT;
+    float2* s_w = s_dyn + sub * (NP * PS);          // NP * PS per sub-tile
+    float2* s_tw = s_dyn + NSUB * (NP * PS);        // N : s_tw[j*N2 + n2] = exp(+2 pi i n2 j / N)
+    __shared__ CraCand s_pair_all[NSUB][NP];
+    CraCand* s_pair = s_pair_all[sub];
 
-    const int tid = threadIdx.x;
-    const int tn = blockIdx.x % ntile_n;
-    const int tm = blockIdx.x / ntile_n;
-    for (int i = tid; i < N; i += NT) s_tw[i] = twid[i];
+    const int tid = threadIdx.x - sub * NT;
+    // reference groups fastest so that concurrently resident CTAs share row groups in L2
+    int tn = (blockIdx.x % ncta_n) * SUBN + (sub % SUBN);
+    int tm = (blockIdx.x / ncta_n) * SUBM + (sub / SUBN);
+    const bool live = (tn < ntile_n) && (tm < ntile_m);
+    if (tn >= ntile_n) tn = ntile_n - 1;            // idle sub-tiles still take part in the barriers
+    if (tm >= ntile_m) tm = ntile_m - 1;
+    for (int i = threadIdx.x; i < N; i += NT * NSUB) s_tw[i] = twid[i];
 
     const float4* dq = spec + (size_t)tm * nc * 2;        // nc float2x4 = nc*2 float4 per group
     const float4* cq = refspec + (size_t)tn * nc * 2;
@@ -161,7 +179,8 @@ ccf_peak_kernel(const float4* __restrict__ spec, int nrows, const float4* __rest
     // lane of the last warp.  (ii) the Nyquist term of every shorter ring (frequency len/2 < N/2,
     // Crosrng_ms q(numr3i+1)): summed per length class by the lanes of warp 1 % nwarps, the least
     // loaded warp, and folded into W after the barrier.
-    __shared__ float s_nyq[NP][8];
+    __shared__ float s_nyq_all[NSUB][NP][8];
+    float (*s_nyq)[8] = s_nyq_all[sub];
     const int nl = tid - ((NT >= 64) ? 32 : 0);
     const bool nyq_lane = (nl >= 0 && nl < 32);
     {
@@ -212,6 +231,10 @@ ccf_peak_kernel(const float4* __restrict__ spec, int nrows, const float4* __rest
     }
     __syncthreads();
 
+#ifdef CRA_EXP_SKIP_FFT
+    if (tid < TM && live && tm * TM + tid < nrows) { CraCand cc; cc.v = s_w[tid].x; cc.code = 1; cand[(size_t)(tm * TM + tid) * ntile_n + tn] = cc; }
+    return;
+#endif
     // pass 1: for each (pair, n2): N1-point DFT over n1 (stride N2), twiddle by w_N^(n2*k1)
     for (int item = tid; item < NP * N2; item += NT) {
         const int pair = item / N2, n2 = item % N2;
@@ -257,7 +280,7 @@ ccf_peak_kernel(const float4* __restrict__ spec, int nrows, const float4* __rest
             const float sc = 1.0f / (float)N;
             const float qn = bq * sc, qm = bt * sc;
             CraCand cd;
-            if (row < nrows && ref < R) {
+            if (live && row < nrows && ref < R) {
                 if (qn >= qm) { cd.v = qn; cd.code = ref * 8192 + (mq + 1); }
                 else          { cd.v = qm; cd.code = ref * 8192 + 4096 + (mt + 1); }
             } else { cd.v = -INFINITY; cd.code = -1; }
@@ -265,7 +288,7 @@ ccf_peak_kernel(const float4* __restrict__ spec, int nrows, const float4* __rest
         }
     }
     __syncthreads();
-    if (tid < TM) {
+    if (tid < TM && live) {
         const int row = tm * TM + tid;
         if (row < nrows) {
             CraCand best; best.v = -INFINITY; best.code = -1;
@@ -421,19 +444,22 @@ int launch_ccf_t(const float* spec, int nrows, const float* refspec, int R, cons
                  const float2* twid, CraCand* cand, int ntile_n, cudaStream_t st)
 {
     using S = Shape<LOG2N>;
-    const size_t smem = ((size_t)NP * S::PS + S::N) * sizeof(float2);
+    constexpr int SUBM = S::SUBM, SUBN = S::SUBN, NSUB = S::NSUB;
+    const size_t smem = ((size_t)NSUB * NP * S::PS + S::N) * sizeof(float2);
     static bool configured = false;
     if (!configured) {
         CRA_CUDA(cudaFuncSetAttribute(ccf_peak_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     const long ntile_m = (nrows + TM - 1) / TM;
-    const long nblk = ntile_m * ntile_n;
+    const long ncta_m = (ntile_m + SUBM - 1) / SUBM, ncta_n = (ntile_n + SUBN - 1) / SUBN;
+    const long nblk = ncta_m * ncta_n;
     if (nblk <= 0) return 0;
     if (nblk > 2147483647L) { cra_set_error("ccf grid too large; lower row_batch"); return 1; }
-    ccf_peak_kernel<LOG2N><<<(unsigned)nblk, S::NT, smem, st>>>(reinterpret_cast<const float4*>(spec), nrows,
-                                                                reinterpret_cast<const float4*>(refspec), R,
-                                                                h.nring, h.nc, twid, cand, ntile_n);
+    ccf_peak_kernel<LOG2N><<<(unsigned)nblk, S::NT * NSUB, smem, st>>>(reinterpret_cast<const float4*>(spec), nrows,
+                                                                       reinterpret_cast<const float4*>(refspec), R,
+                                                                       h.nring, h.nc, twid, cand, ntile_n,
+                                                                       (int)ntile_m, (int)ncta_n);
     CRA_CUDA(cudaGetLastError());
     return 0;
 }

@@ -234,6 +234,9 @@ polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __r
         s_avg[tid] = avg; s_isg[tid] = isg;
     }
 
+#ifdef CRA_EXP_SKIP_RINGFFT
+    return;
+#endif
     // ---- ring FFTs: pass A -------------------------------------------------------------------
     for (int it = tid; it < items.nA * ck.nrow; it += kPolarThreads) {
         const int r = it / items.nA, item = __ldg(items.A + (it - r * items.nA));
