@@ -28,6 +28,7 @@
 #include "cra_fft.cuh"
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -302,6 +303,251 @@ ccf_peak_kernel(const float4* __restrict__ spec, int nrows, const float4* __rest
     }
 }
 
+// =============================================================================================
+// Staged variant (maxrin <= 256): persistent CTAs, 2 x 2 sub-tiles (8 rows x 8 references = 64
+// pairs), one thread per frequency and sub-tile.  The ring data of the CTA's two row groups and two
+// reference groups is streamed ring-stage by ring-stage into shared memory with cp.async.bulk
+// (TMA bulk copies completing on mbarriers, NSTAGE deep) by one elected thread and consumed by all
+// four sub-tiles, so every operand byte crosses L2 -> SM once per 64 pairs instead of once per 16
+// (the 1x1 kernel moves 188 KB per 16 pairs, ~5.7 TB/s at its speed) and the load latency is hidden
+// by the pipeline rather than by occupancy.
+constexpr int G_SUBM = 2, G_SUBN = 2, G_NSUB = 4, G_NSTAGE = 3, G_MAXST = CRA_MAX_RINGS;
+__constant__ int c_st_hi[G_MAXST];    // highest ring index of the stage (rings are consumed downwards)
+__constant__ int c_st_lo[G_MAXST];    // lowest ring index of the stage
+__constant__ int c_st_off[G_MAXST];   // float4 offset of the stage inside a group (= 2*coff[lo])
+__constant__ int c_st_cnt[G_MAXST];   // float4 count of the stage
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{ asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
+                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int LOG2N>
+struct GShape {
+    using S = Shape<LOG2N>;
+    static constexpr int N = S::N;
+    static constexpr int NTS = (N / 2 < 32) ? 32 : N / 2;           // threads per sub-tile: one per frequency
+    static constexpr int NTHREADS = NTS * G_NSUB;
+    static constexpr int CAP = ((2 * (N / 2 + 1) + 8 + 3) / 4) * 4;   // float4 per group per stage (>= one full ring)
+    static constexpr size_t W_F2 = (size_t)G_NSUB * NP * S::PS;       // float2
+    static constexpr size_t ST_F4 = (size_t)G_NSTAGE * (G_SUBM + G_SUBN) * CAP;
+    static constexpr size_t SMEM = W_F2 * sizeof(float2) + ST_F4 * sizeof(float4) + (size_t)N * sizeof(float2) + 64;
+};
+
+template <int LOG2N>
+__global__ void __launch_bounds__(GShape<LOG2N>::NTHREADS, 1)
+ccf_staged_kernel(const float4* __restrict__ spec, int nrows, const float4* __restrict__ refspec, int R,
+                  int nring, int nc, int nst, const float2* __restrict__ twid, CraCand* __restrict__ cand,
+                  int ntile_n, int ntile_m, int ncta_n, int ntiles)
+{
+    using S = Shape<LOG2N>;
+    using G = GShape<LOG2N>;
+    constexpr int N = S::N, N1 = S::N1, N2 = S::N2, PS = S::PS, NTS = G::NTS, NTH = G::NTHREADS, CAP = G::CAP;
+    extern __shared__ __align__(128) unsigned char g_smem[];
+    float4* s_st = reinterpret_cast<float4*>(g_smem);                                   // stages first: 16 B aligned
+    float2* s_wall = reinterpret_cast<float2*>(g_smem + G::ST_F4 * sizeof(float4));
+    float2* s_tw = s_wall + G::W_F2;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tw + N);                            // full[NSTAGE], empty[NSTAGE]
+    __shared__ CraCand s_pair[G_NSUB * NP];
+
+    const int sub = threadIdx.x / NTS;
+    const int k = threadIdx.x - sub * NTS;              // this thread's frequency
+    const int sa = sub / G_SUBN, sb = sub % G_SUBN;     // row group / ref group inside the CTA tile
+    const int lane = threadIdx.x & 31;
+    const bool producer = (threadIdx.x == NTH - 32);    // lane 0 of the last warp (highest frequencies: least work)
+    float2* s_w = s_wall + (size_t)sub * NP * PS;
+    uint64_t* full = s_bar; uint64_t* empty = s_bar + G_NSTAGE;
+
+    for (int i = threadIdx.x; i < N; i += NTH) s_tw[i] = twid[i];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < G_NSTAGE; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NTH / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const long total_st = (long)my_tiles * nst;
+
+    // issue the bulk copies of global stage g (tile g / nst of this CTA, local stage g % nst)
+    auto issue = [&](long g) {
+        const int c = (int)(g / nst), j = (int)(g - (long)c * nst);
+        const int tile = (int)blockIdx.x + c * (int)gridDim.x;
+        const int tmb = (tile / ncta_n) * G_SUBM, tnb = (tile % ncta_n) * G_SUBN;
+        const int slot = (int)(g % G_NSTAGE);
+        const unsigned bytes = (unsigned)c_st_cnt[j] * 16u;
+        mbar_expect_tx(full + slot, bytes * (G_SUBM + G_SUBN));
+        float4* dst = s_st + (size_t)slot * (G_SUBM + G_SUBN) * CAP;
+#pragma unroll
+        for (int a = 0; a < G_SUBM; ++a) {
+            int tm = tmb + a; if (tm >= ntile_m) tm = ntile_m - 1;
+            bulk_g2s(dst + a * CAP, spec + (size_t)tm * nc * 2 + c_st_off[j], bytes, full + slot);
+        }
+#pragma unroll
+        for (int b = 0; b < G_SUBN; ++b) {
+            int tn = tnb + b; if (tn >= ntile_n) tn = ntile_n - 1;
+            bulk_g2s(dst + (G_SUBM + b) * CAP, refspec + (size_t)tn * nc * 2 + c_st_off[j], bytes, full + slot);
+        }
+    };
+    if (producer)
+        for (long g = 0; g < G_NSTAGE && g < total_st; ++g) issue(g);
+
+    long g = 0;
+    for (int c = 0; c < my_tiles; ++c) {
+        const int tile = (int)blockIdx.x + c * (int)gridDim.x;
+        const int tm = (tile / ncta_n) * G_SUBM + sa, tn = (tile % ncta_n) * G_SUBN + sb;
+        const bool live = (tm < ntile_m) && (tn < ntile_n);
+        Acc a;
+#pragma unroll
+        for (int m = 0; m < TM; ++m)
+#pragma unroll
+            for (int n = 0; n < TN; ++n) { a.A[m][n] = 0.f; a.B[m][n] = 0.f; a.C[m][n] = 0.f; a.D[m][n] = 0.f; }
+
+        for (int j = 0; j < nst; ++j, ++g) {
+            const int slot = (int)(g % G_NSTAGE);
+            const unsigned par = (unsigned)((g / G_NSTAGE) & 1);
+            mbar_wait(full + slot, par);
+            const float4* dq = s_st + ((size_t)slot * (G_SUBM + G_SUBN) + sa) * CAP - c_st_off[j];
+            const float4* cq = s_st + ((size_t)slot * (G_SUBM + G_SUBN) + G_SUBM + sb) * CAP - c_st_off[j];
+            for (int i = c_st_hi[j]; i >= c_st_lo[j]; --i) {
+                const int half = c_half[i];
+                if (k > half || k >= N / 2) continue;
+                const int e = 2 * c_coff[i] + k, p = half + 1;
+                float4 d[2], cc[2];
+                d[0] = dq[e]; d[1] = dq[e + p]; cc[0] = cq[e]; cc[1] = cq[e + p];
+                if (k == 0) {
+                    // thread 0 also carries the real frequency N/2 of full-length rings in its
+                    // "imaginary" lanes: A = sum at k=0, B = sum at k=N/2 (cross terms are unused)
+                    if (half == N / 2) {
+                        const float4 d0 = dq[e + half], d1 = dq[e + p + half], c0 = cq[e + half], c1 = cq[e + p + half];
+                        d[0].y = d0.x; d[0].w = d0.z; d[1].y = d1.x; d[1].w = d1.z;
+                        cc[0].y = c0.x; cc[0].w = c0.z; cc[1].y = c1.x; cc[1].w = c1.z;
+                    } else {
+                        d[0].y = 0.f; d[0].w = 0.f; d[1].y = 0.f; d[1].w = 0.f;
+                        cc[0].y = 0.f; cc[0].w = 0.f; cc[1].y = 0.f; cc[1].w = 0.f;
+                    }
+                    ring_fma(a, d, cc);
+                } else if (k < half) {
+                    ring_fma(a, d, cc);
+                } else {
+                    // k == half < N/2: the (real) Nyquist term of a short ring, Crosrng_ms q(numr3i+1)
+                    const float dx[TM] = {d[0].x, d[0].z, d[1].x, d[1].z}, cx[TN] = {cc[0].x, cc[0].z, cc[1].x, cc[1].z};
+#pragma unroll
+                    for (int m = 0; m < TM; ++m)
+#pragma unroll
+                        for (int n = 0; n < TN; ++n) a.A[m][n] = fmaf(cx[n], dx[m], a.A[m][n]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + slot);
+            if (producer && g + G_NSTAGE < total_st) {
+                mbar_wait(empty + slot, par);
+                issue(g + G_NSTAGE);
+            }
+        }
+
+        // W = q + i t (Hermitian-extended); the previous tile's FFT reads ended at the barrier below
+        if (k < N / 2) {
+            const int kk = (N - k) & (N - 1);
+            const int i0 = (k >> S::L2) * (N2 + 1) + (k & (N2 - 1));
+            const int i1 = (kk >> S::L2) * (N2 + 1) + (kk & (N2 - 1));
+            const int h = N / 2, ih = (h >> S::L2) * (N2 + 1) + (h & (N2 - 1));
+#pragma unroll
+            for (int m = 0; m < TM; ++m)
+#pragma unroll
+                for (int n = 0; n < TN; ++n) {
+                    float2* w = s_w + (m * TN + n) * PS;
+                    const float A = a.A[m][n], B = a.B[m][n], C = a.C[m][n], D = a.D[m][n];
+                    if (k == 0) { w[0] = make_float2(A, A); w[ih] = make_float2(B, B); }
+                    else { w[i0] = make_float2(A + B + C + D, A - B + D - C); w[i1] = make_float2(A + B - C - D, A - B + C - D); }
+                }
+        }
+        __syncthreads();
+        // pass 1
+        for (int item = threadIdx.x; item < G_NSUB * NP * N2; item += NTH) {
+            const int pair = item / N2, n2 = item % N2;
+            float2* w = s_wall + (size_t)pair * PS + n2;
+            float2 x[N1];
+#pragma unroll
+            for (int q = 0; q < N1; ++q) x[q] = w[q * (N2 + 1)];
+            fft_reg<N1, 1>(x);
+#pragma unroll
+            for (int q = 0; q < N1; ++q) {
+                if (q == 0) { w[0] = x[0]; continue; }
+                const float2 t = s_tw[q * N2 + n2];
+                w[q * (N2 + 1)] = make_float2(x[q].x * t.x - x[q].y * t.y, x[q].x * t.y + x[q].y * t.x);
+            }
+        }
+        __syncthreads();
+        // pass 2 + argmax
+        for (int item = threadIdx.x; item < G_NSUB * NP * N1; item += NTH) {
+            const int pair = item / N1, k1 = item % N1;
+            const float2* w = s_wall + (size_t)pair * PS + k1 * (N2 + 1);
+            float2 x[N2];
+#pragma unroll
+            for (int q = 0; q < N2; ++q) x[q] = w[q];
+            fft_reg<N2, 1>(x);
+            float bq = -INFINITY, bt = -INFINITY; int mq = -1, mt = -1;
+#pragma unroll
+            for (int q = 0; q < N2; ++q) {
+                const int m = k1 + N1 * q;
+                if (x[q].x >= bq) { bq = x[q].x; mq = m; }
+                if (x[q].y >= bt) { bt = x[q].y; mt = m; }
+            }
+#pragma unroll
+            for (int o = N1 >> 1; o > 0; o >>= 1) {
+                float oq = __shfl_xor_sync(0xffffffffu, bq, o); int omq = __shfl_xor_sync(0xffffffffu, mq, o);
+                float ot = __shfl_xor_sync(0xffffffffu, bt, o); int omt = __shfl_xor_sync(0xffffffffu, mt, o);
+                if (better(oq, omq, bq, mq)) { bq = oq; mq = omq; }
+                if (better(ot, omt, bt, mt)) { bt = ot; mt = omt; }
+            }
+            if (k1 == 0) {
+                const int psub = pair / NP, pl = pair % NP;
+                const int prow = ((tile / ncta_n) * G_SUBM + psub / G_SUBN) * TM + pl / TN;
+                const int pref = ((tile % ncta_n) * G_SUBN + psub % G_SUBN) * TN + pl % TN;
+                const float sc = 1.0f / (float)N;
+                const float qn = bq * sc, qm = bt * sc;
+                CraCand cd;
+                if (prow < nrows && pref < R) {
+                    if (qn >= qm) { cd.v = qn; cd.code = pref * 8192 + (mq + 1); }
+                    else          { cd.v = qm; cd.code = pref * 8192 + 4096 + (mt + 1); }
+                } else { cd.v = -INFINITY; cd.code = -1; }
+                s_pair[pair] = cd;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < G_NSUB * TM) {
+            const int psub = threadIdx.x / TM, m = threadIdx.x % TM;
+            const int gm = (tile / ncta_n) * G_SUBM + psub / G_SUBN, gn = (tile % ncta_n) * G_SUBN + psub % G_SUBN;
+            const int row = gm * TM + m;
+            if (gm < ntile_m && gn < ntile_n && row < nrows) {
+                CraCand best; best.v = -INFINITY; best.code = -1;
+#pragma unroll
+                for (int n = 0; n < TN; ++n) {
+                    const CraCand cnd = s_pair[psub * NP + m * TN + n];
+                    if (cnd.code >= 0 && cnd.v >= best.v) best = cnd;
+                }
+                cand[(size_t)row * ntile_n + gn] = best;
+            }
+        }
+        (void)live;
+        // No barrier needed here: W and s_pair are next written after barriers that every thread
+        // reaches only once it has finished reading them.
+    }
+}
+
 // ---- scalar helpers on the device spectrum layout (finalize / test entry) -------------------
 __device__ __forceinline__ float2 spec_at(const float2* __restrict__ base, int nc, int row, int coff, int half, int k)
 {
@@ -464,6 +710,46 @@ int launch_ccf_t(const float* spec, int nrows, const float* refspec, int R, cons
     return 0;
 }
 
+// host side of the staged kernel: stage table (rings packed downwards into CAP-sized stages)
+template <int LOG2N>
+int launch_ccf_staged(const float* spec, int nrows, const float* refspec, int R, const CraRingTab& h,
+                      const float2* twid, CraCand* cand, int ntile_n, cudaStream_t st)
+{
+    using G = GShape<LOG2N>;
+    static int cached_nring = -1, cached_nst = 0, cached_dev = -1, sm_count = 0;
+    int dev = 0; cudaGetDevice(&dev);
+    if (cached_nring != h.nring || cached_dev != dev) {
+        int hi[G_MAXST], lo[G_MAXST], off[G_MAXST], cnt[G_MAXST], nst = 0;
+        int i = h.nring - 1;
+        while (i >= 0) {
+            int top = i, used = 0;
+            while (i >= 0 && used + 2 * ((h.len[i] >> 1) + 1) <= G::CAP) { used += 2 * ((h.len[i] >> 1) + 1); --i; }
+            if (used == 0) { cra_set_error("ring larger than a stage"); return 1; }
+            hi[nst] = top; lo[nst] = i + 1; off[nst] = 2 * h.coff[i + 1]; cnt[nst] = used; ++nst;
+        }
+        CRA_CUDA(cudaStreamSynchronize(st));
+        CRA_CUDA(cudaMemcpyToSymbol(c_st_hi, hi, sizeof(int) * nst));
+        CRA_CUDA(cudaMemcpyToSymbol(c_st_lo, lo, sizeof(int) * nst));
+        CRA_CUDA(cudaMemcpyToSymbol(c_st_off, off, sizeof(int) * nst));
+        CRA_CUDA(cudaMemcpyToSymbol(c_st_cnt, cnt, sizeof(int) * nst));
+        CRA_CUDA(cudaFuncSetAttribute(ccf_staged_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+        CRA_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+        cached_nring = h.nring; cached_nst = nst; cached_dev = dev;
+    }
+    const long ntile_m = (nrows + TM - 1) / TM;
+    const long ncta_m = (ntile_m + G_SUBM - 1) / G_SUBM, ncta_n = (ntile_n + G_SUBN - 1) / G_SUBN;
+    const long ntiles = ncta_m * ncta_n;
+    if (ntiles <= 0) return 0;
+    if (ntiles > 2147483647L) { cra_set_error("ccf grid too large; lower row_batch"); return 1; }
+    const int grid = (int)(ntiles < sm_count ? ntiles : sm_count);
+    ccf_staged_kernel<LOG2N><<<grid, G::NTHREADS, G::SMEM, st>>>(reinterpret_cast<const float4*>(spec), nrows,
+                                                                reinterpret_cast<const float4*>(refspec), R, h.nring, h.nc,
+                                                                cached_nst, twid, cand, ntile_n, (int)ntile_m, (int)ncta_n,
+                                                                (int)ntiles);
+    CRA_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace
 
 int cra_ccf_tile_n() { return TN; }
@@ -485,6 +771,16 @@ int cra_launch_ccf(const float* spec, int nrows, const float* refspec, int R, co
 {
     (void)tab;
     if (bind_ring_table(htab, st)) return 1;
+    static const int use_staged = getenv("CRA_CCF_STAGED") ? atoi(getenv("CRA_CCF_STAGED")) : 0;
+    if (use_staged) {
+        switch (htab.log2n) {
+            case 5: return launch_ccf_staged<5>(spec, nrows, refspec, R, htab, twid, cand, ntile_n, st);
+            case 6: return launch_ccf_staged<6>(spec, nrows, refspec, R, htab, twid, cand, ntile_n, st);
+            case 7: return launch_ccf_staged<7>(spec, nrows, refspec, R, htab, twid, cand, ntile_n, st);
+            case 8: return launch_ccf_staged<8>(spec, nrows, refspec, R, htab, twid, cand, ntile_n, st);
+            default: break;   // maxrin >= 512: W buffers of 64 pairs exceed shared memory
+        }
+    }
     switch (htab.log2n) {
         case 5:  return launch_ccf_t<5>(spec, nrows, refspec, R, htab, twid, cand, ntile_n, st);
         case 6:  return launch_ccf_t<6>(spec, nrows, refspec, R, htab, twid, cand, ntile_n, st);

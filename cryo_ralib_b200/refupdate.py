@@ -115,6 +115,7 @@ def fit_tanh(dres, low=0.1):
     """sp_filter.fit_tanh: (cut-off, fall-off) of the tanh low-pass that best fits 2f/(1+f)."""
     freq = np.array(dres[0], np.float64)
     val = np.array(dres[1], np.float64)
+    val = np.where(val == -1.0, -1.0 + 1e-12, val)          # 2f/(1+f) pole; EMAN2 would raise here
     full = 2 * val / (1.0 + val)
     below = np.where(full[1:] < low)[0]
     if below.size:
