@@ -311,7 +311,7 @@ ccf_peak_kernel(const float4* __restrict__ spec, int nrows, const float4* __rest
 // four sub-tiles, so every operand byte crosses L2 -> SM once per 64 pairs instead of once per 16
 // (the 1x1 kernel moves 188 KB per 16 pairs, ~5.7 TB/s at its speed) and the load latency is hidden
 // by the pipeline rather than by occupancy.
-constexpr int G_SUBM = 2, G_SUBN = 2, G_NSUB = 4, G_NSTAGE = 3, G_MAXST = CRA_MAX_RINGS;
+constexpr int G_SUBM = 2, G_SUBN = 2, G_NSUB = 4, G_NSTAGE = 9, G_MAXST = CRA_MAX_RINGS;
 __constant__ int c_st_hi[G_MAXST];    // highest ring index of the stage (rings are consumed downwards)
 __constant__ int c_st_lo[G_MAXST];    // lowest ring index of the stage
 __constant__ int c_st_off[G_MAXST];   // float4 offset of the stage inside a group (= 2*coff[lo])
@@ -342,9 +342,9 @@ struct GShape {
     static constexpr int NTS = (N / 2 < 32) ? 32 : N / 2;           // threads per sub-tile: one per frequency
     static constexpr int NTHREADS = NTS * G_NSUB;
     static constexpr int CAP = ((2 * (N / 2 + 1) + 8 + 3) / 4) * 4;   // float4 per group per stage (>= one full ring)
-    static constexpr size_t W_F2 = (size_t)G_NSUB * NP * S::PS;       // float2
+    static constexpr size_t W_F2 = (size_t)G_SUBN * NP * S::PS;       // float2: W of one row group (2 sub-tiles) at a time
     static constexpr size_t ST_F4 = (size_t)G_NSTAGE * (G_SUBM + G_SUBN) * CAP;
-    static constexpr size_t SMEM = W_F2 * sizeof(float2) + ST_F4 * sizeof(float4) + (size_t)N * sizeof(float2) + 64;
+    static constexpr size_t SMEM = W_F2 * sizeof(float2) + ST_F4 * sizeof(float4) + (size_t)N * sizeof(float2) + 2 * G_NSTAGE * sizeof(uint64_t) + 16;
 };
 
 template <int LOG2N>
@@ -368,7 +368,6 @@ ccf_staged_kernel(const float4* __restrict__ spec, int nrows, const float4* __re
     const int sa = sub / G_SUBN, sb = sub % G_SUBN;     // row group / ref group inside the CTA tile
     const int lane = threadIdx.x & 31;
     const bool producer = (threadIdx.x == NTH - 32);    // lane 0 of the last warp (highest frequencies: least work)
-    float2* s_w = s_wall + (size_t)sub * NP * PS;
     uint64_t* full = s_bar; uint64_t* empty = s_bar + G_NSTAGE;
 
     for (int i = threadIdx.x; i < N; i += NTH) s_tw[i] = twid[i];
@@ -458,78 +457,83 @@ ccf_staged_kernel(const float4* __restrict__ spec, int nrows, const float4* __re
             }
         }
 
-        // W = q + i t (Hermitian-extended); the previous tile's FFT reads ended at the barrier below
-        if (k < N / 2) {
-            const int kk = (N - k) & (N - 1);
-            const int i0 = (k >> S::L2) * (N2 + 1) + (k & (N2 - 1));
-            const int i1 = (kk >> S::L2) * (N2 + 1) + (kk & (N2 - 1));
-            const int h = N / 2, ih = (h >> S::L2) * (N2 + 1) + (h & (N2 - 1));
+        // Inverse FFT + peak search in two rounds (row group 0, then row group 1) so that the W
+        // buffer holds 32 pairs and the rest of shared memory can go to the operand pipeline; the
+        // accumulators of the waiting sub-tiles simply stay in their registers.
+        for (int rnd = 0; rnd < G_SUBM; ++rnd) {
+            if (sa == rnd && k < N / 2) {
+                float2* s_w = s_wall + (size_t)sb * NP * PS;
+                const int kk = (N - k) & (N - 1);
+                const int i0 = (k >> S::L2) * (N2 + 1) + (k & (N2 - 1));
+                const int i1 = (kk >> S::L2) * (N2 + 1) + (kk & (N2 - 1));
+                const int h = N / 2, ih = (h >> S::L2) * (N2 + 1) + (h & (N2 - 1));
 #pragma unroll
-            for (int m = 0; m < TM; ++m)
+                for (int m = 0; m < TM; ++m)
 #pragma unroll
-                for (int n = 0; n < TN; ++n) {
-                    float2* w = s_w + (m * TN + n) * PS;
-                    const float A = a.A[m][n], B = a.B[m][n], C = a.C[m][n], D = a.D[m][n];
-                    if (k == 0) { w[0] = make_float2(A, A); w[ih] = make_float2(B, B); }
-                    else { w[i0] = make_float2(A + B + C + D, A - B + D - C); w[i1] = make_float2(A + B - C - D, A - B + C - D); }
+                    for (int n = 0; n < TN; ++n) {
+                        float2* w = s_w + (m * TN + n) * PS;
+                        const float A = a.A[m][n], B = a.B[m][n], C = a.C[m][n], D = a.D[m][n];
+                        if (k == 0) { w[0] = make_float2(A, A); w[ih] = make_float2(B, B); }
+                        else { w[i0] = make_float2(A + B + C + D, A - B + D - C); w[i1] = make_float2(A + B - C - D, A - B + C - D); }
+                    }
+            }
+            __syncthreads();
+            // pass 1
+            for (int item = threadIdx.x; item < G_SUBN * NP * N2; item += NTH) {
+                const int pair = item / N2, n2 = item % N2;
+                float2* w = s_wall + (size_t)pair * PS + n2;
+                float2 x[N1];
+#pragma unroll
+                for (int q = 0; q < N1; ++q) x[q] = w[q * (N2 + 1)];
+                fft_reg<N1, 1>(x);
+#pragma unroll
+                for (int q = 0; q < N1; ++q) {
+                    if (q == 0) { w[0] = x[0]; continue; }
+                    const float2 t = s_tw[q * N2 + n2];
+                    w[q * (N2 + 1)] = make_float2(x[q].x * t.x - x[q].y * t.y, x[q].x * t.y + x[q].y * t.x);
                 }
+            }
+            __syncthreads();
+            // pass 2 + argmax
+            for (int item = threadIdx.x; item < G_SUBN * NP * N1; item += NTH) {
+                const int pair = item / N1, k1 = item % N1;
+                const float2* w = s_wall + (size_t)pair * PS + k1 * (N2 + 1);
+                float2 x[N2];
+#pragma unroll
+                for (int q = 0; q < N2; ++q) x[q] = w[q];
+                fft_reg<N2, 1>(x);
+                float bq = -INFINITY, bt = -INFINITY; int mq = -1, mt = -1;
+#pragma unroll
+                for (int q = 0; q < N2; ++q) {
+                    const int m = k1 + N1 * q;
+                    if (x[q].x >= bq) { bq = x[q].x; mq = m; }
+                    if (x[q].y >= bt) { bt = x[q].y; mt = m; }
+                }
+#pragma unroll
+                for (int o = N1 >> 1; o > 0; o >>= 1) {
+                    float oq = __shfl_xor_sync(0xffffffffu, bq, o); int omq = __shfl_xor_sync(0xffffffffu, mq, o);
+                    float ot = __shfl_xor_sync(0xffffffffu, bt, o); int omt = __shfl_xor_sync(0xffffffffu, mt, o);
+                    if (better(oq, omq, bq, mq)) { bq = oq; mq = omq; }
+                    if (better(ot, omt, bt, mt)) { bt = ot; mt = omt; }
+                }
+                if (k1 == 0) {
+                    const int psb = pair / NP, pl = pair % NP;
+                    const int prow = ((tile / ncta_n) * G_SUBM + rnd) * TM + pl / TN;
+                    const int pref = ((tile % ncta_n) * G_SUBN + psb) * TN + pl % TN;
+                    const float sc = 1.0f / (float)N;
+                    const float qn = bq * sc, qm = bt * sc;
+                    CraCand cd;
+                    if (prow < nrows && pref < R) {
+                        if (qn >= qm) { cd.v = qn; cd.code = pref * 8192 + (mq + 1); }
+                        else          { cd.v = qm; cd.code = pref * 8192 + 4096 + (mt + 1); }
+                    } else { cd.v = -INFINITY; cd.code = -1; }
+                    s_pair[rnd * G_SUBN * NP + pair] = cd;
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        // pass 1
-        for (int item = threadIdx.x; item < G_NSUB * NP * N2; item += NTH) {
-            const int pair = item / N2, n2 = item % N2;
-            float2* w = s_wall + (size_t)pair * PS + n2;
-            float2 x[N1];
-#pragma unroll
-            for (int q = 0; q < N1; ++q) x[q] = w[q * (N2 + 1)];
-            fft_reg<N1, 1>(x);
-#pragma unroll
-            for (int q = 0; q < N1; ++q) {
-                if (q == 0) { w[0] = x[0]; continue; }
-                const float2 t = s_tw[q * N2 + n2];
-                w[q * (N2 + 1)] = make_float2(x[q].x * t.x - x[q].y * t.y, x[q].x * t.y + x[q].y * t.x);
-            }
-        }
-        __syncthreads();
-        // pass 2 + argmax
-        for (int item = threadIdx.x; item < G_NSUB * NP * N1; item += NTH) {
-            const int pair = item / N1, k1 = item % N1;
-            const float2* w = s_wall + (size_t)pair * PS + k1 * (N2 + 1);
-            float2 x[N2];
-#pragma unroll
-            for (int q = 0; q < N2; ++q) x[q] = w[q];
-            fft_reg<N2, 1>(x);
-            float bq = -INFINITY, bt = -INFINITY; int mq = -1, mt = -1;
-#pragma unroll
-            for (int q = 0; q < N2; ++q) {
-                const int m = k1 + N1 * q;
-                if (x[q].x >= bq) { bq = x[q].x; mq = m; }
-                if (x[q].y >= bt) { bt = x[q].y; mt = m; }
-            }
-#pragma unroll
-            for (int o = N1 >> 1; o > 0; o >>= 1) {
-                float oq = __shfl_xor_sync(0xffffffffu, bq, o); int omq = __shfl_xor_sync(0xffffffffu, mq, o);
-                float ot = __shfl_xor_sync(0xffffffffu, bt, o); int omt = __shfl_xor_sync(0xffffffffu, mt, o);
-                if (better(oq, omq, bq, mq)) { bq = oq; mq = omq; }
-                if (better(ot, omt, bt, mt)) { bt = ot; mt = omt; }
-            }
-            if (k1 == 0) {
-                const int psub = pair / NP, pl = pair % NP;
-                const int prow = ((tile / ncta_n) * G_SUBM + psub / G_SUBN) * TM + pl / TN;
-                const int pref = ((tile % ncta_n) * G_SUBN + psub % G_SUBN) * TN + pl % TN;
-                const float sc = 1.0f / (float)N;
-                const float qn = bq * sc, qm = bt * sc;
-                CraCand cd;
-                if (prow < nrows && pref < R) {
-                    if (qn >= qm) { cd.v = qn; cd.code = pref * 8192 + (mq + 1); }
-                    else          { cd.v = qm; cd.code = pref * 8192 + 4096 + (mt + 1); }
-                } else { cd.v = -INFINITY; cd.code = -1; }
-                s_pair[pair] = cd;
-            }
-        }
-        __syncthreads();
         if (threadIdx.x < G_NSUB * TM) {
-            const int psub = threadIdx.x / TM, m = threadIdx.x % TM;
+            const int psub = threadIdx.x / TM, m = threadIdx.x % TM;          // psub = rnd * SUBN + ref group
             const int gm = (tile / ncta_n) * G_SUBM + psub / G_SUBN, gn = (tile % ncta_n) * G_SUBN + psub % G_SUBN;
             const int row = gm * TM + m;
             if (gm < ntile_m && gn < ntile_n && row < nrows) {
