@@ -32,8 +32,11 @@
 
 namespace {
 
-constexpr int TM = 4;   // rows per CTA  (= interleave factor of the device spectrum)
-constexpr int TN = 4;   // references per CTA
+constexpr int RG = 1;        // row groups (of 4 rows) per CTA: each thread keeps RG x 4 x TNT pairs in registers
+constexpr int RH = 1;        // thread sets per CTA, each owning TN/RH references of the tile (more warps per SM)
+constexpr int TNT = 4 / RH;  // references per thread
+constexpr int TM = 4 * RG;   // rows per CTA
+constexpr int TN = 4;        // references per CTA
 constexpr int NP = TM * TN;
 
 // ring table of the active configuration (uniform-datapath reads in the hot loop)
@@ -51,11 +54,13 @@ struct Shape {
     static constexpr int N2 = 1 << L2;
     static constexpr int NQ = N / 4;                          // threads owning one frequency
     static constexpr int NW = 3 * N / 8;                      // working threads (upper quarter: two frequencies each)
-    static constexpr int NT = ((NW + 31) / 32) * 32 < 32 ? 32 : ((NW + 31) / 32) * 32;
+    static constexpr int NT1 = ((NW + 31) / 32) * 32 < 32 ? 32 : ((NW + 31) / 32) * 32;   // threads of one set
+    static constexpr int NT = NT1 * RH;
     static constexpr int PS = N1 * (N2 + 1);                  // padded float2 stride of one pair
     // sub-tiles per CTA (row groups x reference groups), bounded by shared memory for the W buffers
     // (measured on B200: 2x2 sub-tiles relying on L1 sharing alone are slower than 1x1 -- 26.3 vs
-    //  19.6 ms per 1e7 alignments -- so sharing is done explicitly by the staged kernel instead)
+    //  19.6 ms per 1e7 alignments; a cp.async.bulk/mbarrier staged 2x2 variant was also correct but
+    //  slower, 37 ms -- see DESIGN.md 3.2.  Operand reuse is raised in registers instead: RG = 2.)
     static constexpr int SUBM = 1;
     static constexpr int SUBN = 1;
     static constexpr int NSUB = SUBM * SUBN;
@@ -66,16 +71,27 @@ __device__ __forceinline__ bool better(float v, int m, float bv, int bm)
     return (v > bv) || (v == bv && m > bm);
 }
 
-struct Acc { float A[TM][TN], B[TM][TN], C[TM][TN], D[TM][TN]; };
+struct Acc { float A[TM][TNT], B[TM][TNT], C[TM][TNT], D[TM][TNT]; };
+constexpr int NCP = (TNT + 1) / 2;   // reference planes (float4 = 2 refs) a thread loads
 
-__device__ __forceinline__ void ring_fma(Acc& a, const float4 (&d)[2], const float4 (&c)[2])
+__device__ __forceinline__ void ring_fma(Acc& a, const float4 (&d)[2 * RG], const float4 (&c)[NCP])
 {
-    const float dx[TM] = {d[0].x, d[0].z, d[1].x, d[1].z}, dy[TM] = {d[0].y, d[0].w, d[1].y, d[1].w};
-    const float cx[TN] = {c[0].x, c[0].z, c[1].x, c[1].z}, cy[TN] = {c[0].y, c[0].w, c[1].y, c[1].w};
+    float dx[TM], dy[TM];
+#pragma unroll
+    for (int g = 0; g < RG; ++g) {
+        dx[4 * g + 0] = d[2 * g].x; dy[4 * g + 0] = d[2 * g].y; dx[4 * g + 1] = d[2 * g].z; dy[4 * g + 1] = d[2 * g].w;
+        dx[4 * g + 2] = d[2 * g + 1].x; dy[4 * g + 2] = d[2 * g + 1].y; dx[4 * g + 3] = d[2 * g + 1].z; dy[4 * g + 3] = d[2 * g + 1].w;
+    }
+    float cx[TNT], cy[TNT];
+#pragma unroll
+    for (int g = 0; g < NCP; ++g) {
+        cx[2 * g] = c[g].x; cy[2 * g] = c[g].y;
+        if (2 * g + 1 < TNT) { cx[2 * g + 1] = c[g].z; cy[2 * g + 1] = c[g].w; }
+    }
 #pragma unroll
     for (int m = 0; m < TM; ++m)
 #pragma unroll
-        for (int n = 0; n < TN; ++n) {
+        for (int n = 0; n < TNT; ++n) {
             a.A[m][n] = fmaf(cx[n], dx[m], a.A[m][n]);
             a.B[m][n] = fmaf(cy[n], dy[m], a.B[m][n]);
             a.C[m][n] = fmaf(cx[n], dy[m], a.C[m][n]);
@@ -84,9 +100,10 @@ __device__ __forceinline__ void ring_fma(Acc& a, const float4 (&d)[2], const flo
 }
 
 // Ring sums of all 16 pairs at frequency k, then W[k] and W[N-k] to shared memory.
-// dq / cq point at element 0 of the row group / ref group (float4 = two interleaved float2).
+// dq / cq point at element 0 of the first row group / the ref group (float4 = two interleaved
+// float2); gstride is the float4 distance between consecutive row groups.
 template <int LOG2N>
-__device__ __forceinline__ void contract_freq(int k, int nring, const float4* __restrict__ dq,
+__device__ __forceinline__ void contract_freq(int k, int rh, int nring, const float4* __restrict__ dq, size_t gstride,
                                               const float4* __restrict__ cq, float2* __restrict__ s_w)
 {
     using S = Shape<LOG2N>;
@@ -95,16 +112,19 @@ __device__ __forceinline__ void contract_freq(int k, int nring, const float4* __
 #pragma unroll
     for (int m = 0; m < TM; ++m)
 #pragma unroll
-        for (int n = 0; n < TN; ++n) { a.A[m][n] = 0.f; a.B[m][n] = 0.f; a.C[m][n] = 0.f; a.D[m][n] = 0.f; }
+        for (int n = 0; n < TNT; ++n) { a.A[m][n] = 0.f; a.B[m][n] = 0.f; a.C[m][n] = 0.f; a.D[m][n] = 0.f; }
 
     // rings in descending length: stop at the first ring that no longer reaches frequency k.
     // Operands are prefetched two rings ahead through three register buffers.
 #define CRA_HAS(j) ((j) >= 0 && k < c_half[(j) < 0 ? 0 : (j)])
 #define CRA_LOAD(D, C, j)                                                                        \
     { const int e_ = 2 * c_coff[j] + k, p_ = c_half[j] + 1;                                      \
-      D[0] = __ldg(dq + e_); D[1] = __ldg(dq + e_ + p_); C[0] = __ldg(cq + e_); C[1] = __ldg(cq + e_ + p_); }
+      _Pragma("unroll") for (int g_ = 0; g_ < RG; ++g_) {                                        \
+          D[2 * g_] = __ldg(dq + g_ * gstride + e_); D[2 * g_ + 1] = __ldg(dq + g_ * gstride + e_ + p_); } \
+      _Pragma("unroll") for (int g_ = 0; g_ < NCP; ++g_)                                          \
+          C[g_] = __ldg(cq + e_ + (RH == 1 ? g_ : rh) * p_); }
     int i = nring - 1;
-    float4 d0[2], c0[2], d1[2], c1[2], d2[2], c2[2];
+    float4 d0[2 * RG], c0[NCP], d1[2 * RG], c1[NCP], d2[2 * RG], c2[NCP];
     CRA_LOAD(d0, c0, i);
     bool h1 = CRA_HAS(i - 1);
     if (h1) CRA_LOAD(d1, c1, i - 1);
@@ -132,8 +152,8 @@ __device__ __forceinline__ void contract_freq(int k, int nring, const float4* __
 #pragma unroll
     for (int m = 0; m < TM; ++m)
 #pragma unroll
-        for (int n = 0; n < TN; ++n) {
-            float2* w = s_w + (m * TN + n) * PS;
+        for (int n = 0; n < TNT; ++n) {
+            float2* w = s_w + (m * TN + rh * TNT + n) * PS;
             const float A = a.A[m][n], B = a.B[m][n], C = a.C[m][n], D = a.D[m][n];
             w[i0] = make_float2(A + B + C + D, A - B + D - C);
             if (k != 0) w[i1] = make_float2(A + B - C - D, A - B + C - D);
@@ -151,7 +171,7 @@ ccf_peak_kernel(const float4* __restrict__ spec, int nrows, const float4* __rest
                 int ntile_m, int ncta_n)
 {
     using S = Shape<LOG2N>;
-    constexpr int N = S::N, N1 = S::N1, N2 = S::N2, NT = S::NT, PS = S::PS, NQ = S::NQ, NW = S::NW;
+    constexpr int N = S::N, N1 = S::N1, N2 = S::N2, NT = S::NT, NT1 = S::NT1, PS = S::PS, NQ = S::NQ, NW = S::NW;
     constexpr int SUBM = S::SUBM, SUBN = S::SUBN, NSUB = S::NSUB;
     extern __shared__ __align__(16) float2 s_dyn[];
     const int sub = threadIdx.x / NT;
@@ -169,12 +189,18 @@ ccf_peak_kernel(const float4* __restrict__ spec, int nrows, const float4* __rest
     if (tm >= ntile_m) tm = ntile_m - 1;
     for (int i = threadIdx.x; i < N; i += NT * NSUB) s_tw[i] = twid[i];
 
-    const float4* dq = spec + (size_t)tm * nc * 2;        // nc float2x4 = nc*2 float4 per group
+    // row groups tm*RG .. tm*RG+RG-1 (the last CTA may run past the batch: reuse the last group)
+    const int ngroups = (nrows + 3) >> 2;
+    const size_t gstride = (tm * RG + RG - 1 < ngroups) ? (size_t)nc * 2 : 0;
+    const float4* dq = spec + (size_t)tm * RG * nc * 2;   // nc float2x4 = nc*2 float4 per group
     const float4* cq = refspec + (size_t)tn * nc * 2;
 
-    if (tid < NW) {
-        contract_freq<LOG2N>(tid, nring, dq, cq, s_w);
-        if (tid >= NQ) contract_freq<LOG2N>(tid + N / 8, nring, dq, cq, s_w);
+    {
+        const int rh = tid / NT1, t1 = tid - rh * NT1;      // thread set (reference half) and its frequency slot
+        if (t1 < NW) {
+            contract_freq<LOG2N>(t1, rh, nring, dq, gstride, cq, s_w);
+            if (t1 >= NQ) contract_freq<LOG2N>(t1 + N / 8, rh, nring, dq, gstride, cq, s_w);
+        }
     }
     // Real-valued ring elements.  (i) frequency N/2: only full-length rings reach it; one pair per
     // lane of the last warp.  (ii) the Nyquist term of every shorter ring (frequency len/2 < N/2,
@@ -188,54 +214,55 @@ ccf_peak_kernel(const float4* __restrict__ spec, int nrows, const float4* __rest
         const float2* d2 = reinterpret_cast<const float2*>(dq);
         const float2* c2 = reinterpret_cast<const float2*>(cq);
         const int l = tid - (NT - 32);
-        if (l >= 0 && l < NP) {
-            const int m = l / TN, n = l % TN;
-            float a = 0.f;
-            for (int i = nring - 1; i >= 0 && c_half[i] == N / 2; --i)
-                a = fmaf(__ldg(c2 + cra_spec_idx(c_coff[i], N / 2, n, N / 2)).x,
-                         __ldg(d2 + cra_spec_idx(c_coff[i], N / 2, m, N / 2)).x, a);
-            const int h = N / 2;
-            s_w[l * PS + (h >> S::L2) * (N2 + 1) + (h & (N2 - 1))] = make_float2(a, a);
+        if (l >= 0 && l < 32) {
+            for (int pair = l; pair < NP; pair += 32) {
+                const int m = pair / TN, n = pair % TN;
+                const float2* dm = d2 + (size_t)(m >> 2) * gstride * 2;
+                float a = 0.f;
+                for (int i = nring - 1; i >= 0 && c_half[i] == N / 2; --i)
+                    a = fmaf(__ldg(c2 + cra_spec_idx(c_coff[i], N / 2, n, N / 2)).x,
+                             __ldg(dm + cra_spec_idx(c_coff[i], N / 2, m, N / 2)).x, a);
+                const int h = N / 2;
+                s_w[pair * PS + (h >> S::L2) * (N2 + 1) + (h & (N2 - 1))] = make_float2(a, a);
+            }
         }
         if (nyq_lane) {
-            const int pair = nl & (NP - 1), part = nl / NP, m = pair / TN, n = pair % TN;
-            int cls = -1, cur = -1; float a = 0.f;
-            for (int i = 0; i < nring && c_half[i] < N / 2; ++i) {
-                const int h = c_half[i];
-                if (h != cur) {
-                    if (cls >= 0 && (cls & 1) == part) s_nyq[pair][cls & 7] = a;
-                    cur = h; ++cls; a = 0.f;
+            for (int pair = nl; pair < NP; pair += 32) {
+                const int m = pair / TN, n = pair % TN;
+                const float2* dm = d2 + (size_t)(m >> 2) * gstride * 2;
+                int cls = -1, cur = -1; float a = 0.f;
+                for (int i = 0; i < nring && c_half[i] < N / 2; ++i) {
+                    const int h = c_half[i];
+                    if (h != cur) {
+                        if (cls >= 0) s_nyq[pair][cls & 7] = a;
+                        cur = h; ++cls; a = 0.f;
+                    }
+                    a = fmaf(__ldg(c2 + cra_spec_idx(c_coff[i], h, n, h)).x, __ldg(dm + cra_spec_idx(c_coff[i], h, m, h)).x, a);
                 }
-                if ((cls & 1) == part)
-                    a = fmaf(__ldg(c2 + cra_spec_idx(c_coff[i], h, n, h)).x, __ldg(d2 + cra_spec_idx(c_coff[i], h, m, h)).x, a);
+                if (cls >= 0) s_nyq[pair][cls & 7] = a;
             }
-            if (cls >= 0 && (cls & 1) == part) s_nyq[pair][cls & 7] = a;
         }
     }
     __syncthreads();
     if (nyq_lane) {
-        const int pair = nl & (NP - 1), part = nl / NP;
-        float2* w = s_w + pair * PS;
-        int cls = -1, cur = -1;
-        for (int i = 0; i < nring && c_half[i] < N / 2; ++i) {
-            const int h = c_half[i];
-            if (h == cur) continue;
-            cur = h; ++cls;
-            if ((cls & 1) != part) continue;
-            const float a = s_nyq[pair][cls & 7];
-            const int hh = N - h;
-            float2* p0 = w + (h >> S::L2) * (N2 + 1) + (h & (N2 - 1));
-            float2* p1 = w + (hh >> S::L2) * (N2 + 1) + (hh & (N2 - 1));
-            float2 v = *p0; v.x += a; v.y += a; *p0 = v;
-            v = *p1; v.x += a; v.y += a; *p1 = v;
+        for (int pair = nl; pair < NP; pair += 32) {
+            float2* w = s_w + pair * PS;
+            int cls = -1, cur = -1;
+            for (int i = 0; i < nring && c_half[i] < N / 2; ++i) {
+                const int h = c_half[i];
+                if (h == cur) continue;
+                cur = h; ++cls;
+                const float a = s_nyq[pair][cls & 7];
+                const int hh = N - h;
+                float2* p0 = w + (h >> S::L2) * (N2 + 1) + (h & (N2 - 1));
+                float2* p1 = w + (hh >> S::L2) * (N2 + 1) + (hh & (N2 - 1));
+                float2 v = *p0; v.x += a; v.y += a; *p0 = v;
+                v = *p1; v.x += a; v.y += a; *p1 = v;
+            }
         }
     }
     __syncthreads();
 
-#ifdef CRA_EXP_SKIP_FFT
-    if (tid < TM && live && tm * TM + tid < nrows) { CraCand cc; cc.v = s_w[tid].x; cc.code = 1; cand[(size_t)(tm * TM + tid) * ntile_n + tn] = cc; }
-    return;
-#endif
     // pass 1: for each (pair, n2): N1-point DFT over n1 (stride N2), twiddle by w_N^(n2*k1)
     for (int item = tid; item < NP * N2; item += NT) {
         const int pair = item / N2, n2 = item % N2;
@@ -300,255 +327,6 @@ ccf_peak_kernel(const float4* __restrict__ spec, int nrows, const float4* __rest
             }
             cand[(size_t)row * ntile_n + tn] = best;
         }
-    }
-}
-
-// =============================================================================================
-// Staged variant (maxrin <= 256): persistent CTAs, 2 x 2 sub-tiles (8 rows x 8 references = 64
-// pairs), one thread per frequency and sub-tile.  The ring data of the CTA's two row groups and two
-// reference groups is streamed ring-stage by ring-stage into shared memory with cp.async.bulk
-// (TMA bulk copies completing on mbarriers, NSTAGE deep) by one elected thread and consumed by all
-// four sub-tiles, so every operand byte crosses L2 -> SM once per 64 pairs instead of once per 16
-// (the 1x1 kernel moves 188 KB per 16 pairs, ~5.7 TB/s at its speed) and the load latency is hidden
-// by the pipeline rather than by occupancy.
-constexpr int G_SUBM = 2, G_SUBN = 2, G_NSUB = 4, G_NSTAGE = 9, G_MAXST = CRA_MAX_RINGS;
-__constant__ int c_st_hi[G_MAXST];    // highest ring index of the stage (rings are consumed downwards)
-__constant__ int c_st_lo[G_MAXST];    // lowest ring index of the stage
-__constant__ int c_st_off[G_MAXST];   // float4 offset of the stage inside a group (= 2*coff[lo])
-__constant__ int c_st_cnt[G_MAXST];   // float4 count of the stage
-
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
-{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{ asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
-{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
-{
-    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
-                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-template <int LOG2N>
-struct GShape {
-    using S = Shape<LOG2N>;
-    static constexpr int N = S::N;
-    static constexpr int NTS = (N / 2 < 32) ? 32 : N / 2;           // threads per sub-tile: one per frequency
-    static constexpr int NTHREADS = NTS * G_NSUB;
-    static constexpr int CAP = ((2 * (N / 2 + 1) + 8 + 3) / 4) * 4;   // float4 per group per stage (>= one full ring)
-    static constexpr size_t W_F2 = (size_t)G_SUBN * NP * S::PS;       // float2: W of one row group (2 sub-tiles) at a time
-    static constexpr size_t ST_F4 = (size_t)G_NSTAGE * (G_SUBM + G_SUBN) * CAP;
-    static constexpr size_t SMEM = W_F2 * sizeof(float2) + ST_F4 * sizeof(float4) + (size_t)N * sizeof(float2) + 2 * G_NSTAGE * sizeof(uint64_t) + 16;
-};
-
-template <int LOG2N>
-__global__ void __launch_bounds__(GShape<LOG2N>::NTHREADS, 1)
-ccf_staged_kernel(const float4* __restrict__ spec, int nrows, const float4* __restrict__ refspec, int R,
-                  int nring, int nc, int nst, const float2* __restrict__ twid, CraCand* __restrict__ cand,
-                  int ntile_n, int ntile_m, int ncta_n, int ntiles)
-{
-    using S = Shape<LOG2N>;
-    using G = GShape<LOG2N>;
-    constexpr int N = S::N, N1 = S::N1, N2 = S::N2, PS = S::PS, NTS = G::NTS, NTH = G::NTHREADS, CAP = G::CAP;
-    extern __shared__ __align__(128) unsigned char g_smem[];
-    float4* s_st = reinterpret_cast<float4*>(g_smem);                                   // stages first: 16 B aligned
-    float2* s_wall = reinterpret_cast<float2*>(g_smem + G::ST_F4 * sizeof(float4));
-    float2* s_tw = s_wall + G::W_F2;
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tw + N);                            // full[NSTAGE], empty[NSTAGE]
-    __shared__ CraCand s_pair[G_NSUB * NP];
-
-    const int sub = threadIdx.x / NTS;
-    const int k = threadIdx.x - sub * NTS;              // this thread's frequency
-    const int sa = sub / G_SUBN, sb = sub % G_SUBN;     // row group / ref group inside the CTA tile
-    const int lane = threadIdx.x & 31;
-    const bool producer = (threadIdx.x == NTH - 32);    // lane 0 of the last warp (highest frequencies: least work)
-    uint64_t* full = s_bar; uint64_t* empty = s_bar + G_NSTAGE;
-
-    for (int i = threadIdx.x; i < N; i += NTH) s_tw[i] = twid[i];
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < G_NSTAGE; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NTH / 32); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const long total_st = (long)my_tiles * nst;
-
-    // issue the bulk copies of global stage g (tile g / nst of this CTA, local stage g % nst)
-    auto issue = [&](long g) {
-        const int c = (int)(g / nst), j = (int)(g - (long)c * nst);
-        const int tile = (int)blockIdx.x + c * (int)gridDim.x;
-        const int tmb = (tile / ncta_n) * G_SUBM, tnb = (tile % ncta_n) * G_SUBN;
-        const int slot = (int)(g % G_NSTAGE);
-        const unsigned bytes = (unsigned)c_st_cnt[j] * 16u;
-        mbar_expect_tx(full + slot, bytes * (G_SUBM + G_SUBN));
-        float4* dst = s_st + (size_t)slot * (G_SUBM + G_SUBN) * CAP;
-#pragma unroll
-        for (int a = 0; a < G_SUBM; ++a) {
-            int tm = tmb + a; if (tm >= ntile_m) tm = ntile_m - 1;
-            bulk_g2s(dst + a * CAP, spec + (size_t)tm * nc * 2 + c_st_off[j], bytes, full + slot);
-        }
-#pragma unroll
-        for (int b = 0; b < G_SUBN; ++b) {
-            int tn = tnb + b; if (tn >= ntile_n) tn = ntile_n - 1;
-            bulk_g2s(dst + (G_SUBM + b) * CAP, refspec + (size_t)tn * nc * 2 + c_st_off[j], bytes, full + slot);
-        }
-    };
-    if (producer)
-        for (long g = 0; g < G_NSTAGE && g < total_st; ++g) issue(g);
-
-    long g = 0;
-    for (int c = 0; c < my_tiles; ++c) {
-        const int tile = (int)blockIdx.x + c * (int)gridDim.x;
-        const int tm = (tile / ncta_n) * G_SUBM + sa, tn = (tile % ncta_n) * G_SUBN + sb;
-        const bool live = (tm < ntile_m) && (tn < ntile_n);
-        Acc a;
-#pragma unroll
-        for (int m = 0; m < TM; ++m)
-#pragma unroll
-            for (int n = 0; n < TN; ++n) { a.A[m][n] = 0.f; a.B[m][n] = 0.f; a.C[m][n] = 0.f; a.D[m][n] = 0.f; }
-
-        for (int j = 0; j < nst; ++j, ++g) {
-            const int slot = (int)(g % G_NSTAGE);
-            const unsigned par = (unsigned)((g / G_NSTAGE) & 1);
-            mbar_wait(full + slot, par);
-            const float4* dq = s_st + ((size_t)slot * (G_SUBM + G_SUBN) + sa) * CAP - c_st_off[j];
-            const float4* cq = s_st + ((size_t)slot * (G_SUBM + G_SUBN) + G_SUBM + sb) * CAP - c_st_off[j];
-            for (int i = c_st_hi[j]; i >= c_st_lo[j]; --i) {
-                const int half = c_half[i];
-                if (k > half || k >= N / 2) continue;
-                const int e = 2 * c_coff[i] + k, p = half + 1;
-                float4 d[2], cc[2];
-                d[0] = dq[e]; d[1] = dq[e + p]; cc[0] = cq[e]; cc[1] = cq[e + p];
-                if (k == 0) {
-                    // thread 0 also carries the real frequency N/2 of full-length rings in its
-                    // "imaginary" lanes: A = sum at k=0, B = sum at k=N/2 (cross terms are unused)
-                    if (half == N / 2) {
-                        const float4 d0 = dq[e + half], d1 = dq[e + p + half], c0 = cq[e + half], c1 = cq[e + p + half];
-                        d[0].y = d0.x; d[0].w = d0.z; d[1].y = d1.x; d[1].w = d1.z;
-                        cc[0].y = c0.x; cc[0].w = c0.z; cc[1].y = c1.x; cc[1].w = c1.z;
-                    } else {
-                        d[0].y = 0.f; d[0].w = 0.f; d[1].y = 0.f; d[1].w = 0.f;
-                        cc[0].y = 0.f; cc[0].w = 0.f; cc[1].y = 0.f; cc[1].w = 0.f;
-                    }
-                    ring_fma(a, d, cc);
-                } else if (k < half) {
-                    ring_fma(a, d, cc);
-                } else {
-                    // k == half < N/2: the (real) Nyquist term of a short ring, Crosrng_ms q(numr3i+1)
-                    const float dx[TM] = {d[0].x, d[0].z, d[1].x, d[1].z}, cx[TN] = {cc[0].x, cc[0].z, cc[1].x, cc[1].z};
-#pragma unroll
-                    for (int m = 0; m < TM; ++m)
-#pragma unroll
-                        for (int n = 0; n < TN; ++n) a.A[m][n] = fmaf(cx[n], dx[m], a.A[m][n]);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + slot);
-            if (producer && g + G_NSTAGE < total_st) {
-                mbar_wait(empty + slot, par);
-                issue(g + G_NSTAGE);
-            }
-        }
-
-        // Inverse FFT + peak search in two rounds (row group 0, then row group 1) so that the W
-        // buffer holds 32 pairs and the rest of shared memory can go to the operand pipeline; the
-        // accumulators of the waiting sub-tiles simply stay in their registers.
-        for (int rnd = 0; rnd < G_SUBM; ++rnd) {
-            if (sa == rnd && k < N / 2) {
-                float2* s_w = s_wall + (size_t)sb * NP * PS;
-                const int kk = (N - k) & (N - 1);
-                const int i0 = (k >> S::L2) * (N2 + 1) + (k & (N2 - 1));
-                const int i1 = (kk >> S::L2) * (N2 + 1) + (kk & (N2 - 1));
-                const int h = N / 2, ih = (h >> S::L2) * (N2 + 1) + (h & (N2 - 1));
-#pragma unroll
-                for (int m = 0; m < TM; ++m)
-#pragma unroll
-                    for (int n = 0; n < TN; ++n) {
-                        float2* w = s_w + (m * TN + n) * PS;
-                        const float A = a.A[m][n], B = a.B[m][n], C = a.C[m][n], D = a.D[m][n];
-                        if (k == 0) { w[0] = make_float2(A, A); w[ih] = make_float2(B, B); }
-                        else { w[i0] = make_float2(A + B + C + D, A - B + D - C); w[i1] = make_float2(A + B - C - D, A - B + C - D); }
-                    }
-            }
-            __syncthreads();
-            // pass 1
-            for (int item = threadIdx.x; item < G_SUBN * NP * N2; item += NTH) {
-                const int pair = item / N2, n2 = item % N2;
-                float2* w = s_wall + (size_t)pair * PS + n2;
-                float2 x[N1];
-#pragma unroll
-                for (int q = 0; q < N1; ++q) x[q] = w[q * (N2 + 1)];
-                fft_reg<N1, 1>(x);
-#pragma unroll
-                for (int q = 0; q < N1; ++q) {
-                    if (q == 0) { w[0] = x[0]; continue; }
-                    const float2 t = s_tw[q * N2 + n2];
-                    w[q * (N2 + 1)] = make_float2(x[q].x * t.x - x[q].y * t.y, x[q].x * t.y + x[q].y * t.x);
-                }
-            }
-            __syncthreads();
-            // pass 2 + argmax
-            for (int item = threadIdx.x; item < G_SUBN * NP * N1; item += NTH) {
-                const int pair = item / N1, k1 = item % N1;
-                const float2* w = s_wall + (size_t)pair * PS + k1 * (N2 + 1);
-                float2 x[N2];
-#pragma unroll
-                for (int q = 0; q < N2; ++q) x[q] = w[q];
-                fft_reg<N2, 1>(x);
-                float bq = -INFINITY, bt = -INFINITY; int mq = -1, mt = -1;
-#pragma unroll
-                for (int q = 0; q < N2; ++q) {
-                    const int m = k1 + N1 * q;
-                    if (x[q].x >= bq) { bq = x[q].x; mq = m; }
-                    if (x[q].y >= bt) { bt = x[q].y; mt = m; }
-                }
-#pragma unroll
-                for (int o = N1 >> 1; o > 0; o >>= 1) {
-                    float oq = __shfl_xor_sync(0xffffffffu, bq, o); int omq = __shfl_xor_sync(0xffffffffu, mq, o);
-                    float ot = __shfl_xor_sync(0xffffffffu, bt, o); int omt = __shfl_xor_sync(0xffffffffu, mt, o);
-                    if (better(oq, omq, bq, mq)) { bq = oq; mq = omq; }
-                    if (better(ot, omt, bt, mt)) { bt = ot; mt = omt; }
-                }
-                if (k1 == 0) {
-                    const int psb = pair / NP, pl = pair % NP;
-                    const int prow = ((tile / ncta_n) * G_SUBM + rnd) * TM + pl / TN;
-                    const int pref = ((tile % ncta_n) * G_SUBN + psb) * TN + pl % TN;
-                    const float sc = 1.0f / (float)N;
-                    const float qn = bq * sc, qm = bt * sc;
-                    CraCand cd;
-                    if (prow < nrows && pref < R) {
-                        if (qn >= qm) { cd.v = qn; cd.code = pref * 8192 + (mq + 1); }
-                        else          { cd.v = qm; cd.code = pref * 8192 + 4096 + (mt + 1); }
-                    } else { cd.v = -INFINITY; cd.code = -1; }
-                    s_pair[rnd * G_SUBN * NP + pair] = cd;
-                }
-            }
-            __syncthreads();
-        }
-        if (threadIdx.x < G_NSUB * TM) {
-            const int psub = threadIdx.x / TM, m = threadIdx.x % TM;          // psub = rnd * SUBN + ref group
-            const int gm = (tile / ncta_n) * G_SUBM + psub / G_SUBN, gn = (tile % ncta_n) * G_SUBN + psub % G_SUBN;
-            const int row = gm * TM + m;
-            if (gm < ntile_m && gn < ntile_n && row < nrows) {
-                CraCand best; best.v = -INFINITY; best.code = -1;
-#pragma unroll
-                for (int n = 0; n < TN; ++n) {
-                    const CraCand cnd = s_pair[psub * NP + m * TN + n];
-                    if (cnd.code >= 0 && cnd.v >= best.v) best = cnd;
-                }
-                cand[(size_t)row * ntile_n + gn] = best;
-            }
-        }
-        (void)live;
-        // No barrier needed here: W and s_pair are next written after barriers that every thread
-        // reaches only once it has finished reading them.
     }
 }
 
@@ -714,46 +492,6 @@ int launch_ccf_t(const float* spec, int nrows, const float* refspec, int R, cons
     return 0;
 }
 
-// host side of the staged kernel: stage table (rings packed downwards into CAP-sized stages)
-template <int LOG2N>
-int launch_ccf_staged(const float* spec, int nrows, const float* refspec, int R, const CraRingTab& h,
-                      const float2* twid, CraCand* cand, int ntile_n, cudaStream_t st)
-{
-    using G = GShape<LOG2N>;
-    static int cached_nring = -1, cached_nst = 0, cached_dev = -1, sm_count = 0;
-    int dev = 0; cudaGetDevice(&dev);
-    if (cached_nring != h.nring || cached_dev != dev) {
-        int hi[G_MAXST], lo[G_MAXST], off[G_MAXST], cnt[G_MAXST], nst = 0;
-        int i = h.nring - 1;
-        while (i >= 0) {
-            int top = i, used = 0;
-            while (i >= 0 && used + 2 * ((h.len[i] >> 1) + 1) <= G::CAP) { used += 2 * ((h.len[i] >> 1) + 1); --i; }
-            if (used == 0) { cra_set_error("ring larger than a stage"); return 1; }
-            hi[nst] = top; lo[nst] = i + 1; off[nst] = 2 * h.coff[i + 1]; cnt[nst] = used; ++nst;
-        }
-        CRA_CUDA(cudaStreamSynchronize(st));
-        CRA_CUDA(cudaMemcpyToSymbol(c_st_hi, hi, sizeof(int) * nst));
-        CRA_CUDA(cudaMemcpyToSymbol(c_st_lo, lo, sizeof(int) * nst));
-        CRA_CUDA(cudaMemcpyToSymbol(c_st_off, off, sizeof(int) * nst));
-        CRA_CUDA(cudaMemcpyToSymbol(c_st_cnt, cnt, sizeof(int) * nst));
-        CRA_CUDA(cudaFuncSetAttribute(ccf_staged_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
-        CRA_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        cached_nring = h.nring; cached_nst = nst; cached_dev = dev;
-    }
-    const long ntile_m = (nrows + TM - 1) / TM;
-    const long ncta_m = (ntile_m + G_SUBM - 1) / G_SUBM, ncta_n = (ntile_n + G_SUBN - 1) / G_SUBN;
-    const long ntiles = ncta_m * ncta_n;
-    if (ntiles <= 0) return 0;
-    if (ntiles > 2147483647L) { cra_set_error("ccf grid too large; lower row_batch"); return 1; }
-    const int grid = (int)(ntiles < sm_count ? ntiles : sm_count);
-    ccf_staged_kernel<LOG2N><<<grid, G::NTHREADS, G::SMEM, st>>>(reinterpret_cast<const float4*>(spec), nrows,
-                                                                reinterpret_cast<const float4*>(refspec), R, h.nring, h.nc,
-                                                                cached_nst, twid, cand, ntile_n, (int)ntile_m, (int)ncta_n,
-                                                                (int)ntiles);
-    CRA_CUDA(cudaGetLastError());
-    return 0;
-}
-
 }  // namespace
 
 int cra_ccf_tile_n() { return TN; }
@@ -775,16 +513,6 @@ int cra_launch_ccf(const float* spec, int nrows, const float* refspec, int R, co
 {
     (void)tab;
     if (bind_ring_table(htab, st)) return 1;
-    static const int use_staged = getenv("CRA_CCF_STAGED") ? atoi(getenv("CRA_CCF_STAGED")) : 0;
-    if (use_staged) {
-        switch (htab.log2n) {
-            case 5: return launch_ccf_staged<5>(spec, nrows, refspec, R, htab, twid, cand, ntile_n, st);
-            case 6: return launch_ccf_staged<6>(spec, nrows, refspec, R, htab, twid, cand, ntile_n, st);
-            case 7: return launch_ccf_staged<7>(spec, nrows, refspec, R, htab, twid, cand, ntile_n, st);
-            case 8: return launch_ccf_staged<8>(spec, nrows, refspec, R, htab, twid, cand, ntile_n, st);
-            default: break;   // maxrin >= 512: W buffers of 64 pairs exceed shared memory
-        }
-    }
     switch (htab.log2n) {
         case 5:  return launch_ccf_t<5>(spec, nrows, refspec, R, htab, twid, cand, ntile_n, st);
         case 6:  return launch_ccf_t<6>(spec, nrows, refspec, R, htab, twid, cand, ntile_n, st);
