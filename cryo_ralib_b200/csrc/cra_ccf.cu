@@ -71,31 +71,33 @@ __device__ __forceinline__ bool better(float v, int m, float bv, int bm)
     return (v > bv) || (v == bv && m > bm);
 }
 
-struct Acc { float A[TM][TNT], B[TM][TNT], C[TM][TNT], D[TM][TNT]; };
+// ring sums as packed pairs: ab = (A, B) = sum c (.) d,  cd = (C, D) = sum c (.) swap(d)
+struct Acc { float2 ab[TM][TNT], cd[TM][TNT]; };
 constexpr int NCP = (TNT + 1) / 2;   // reference planes (float4 = 2 refs) a thread loads
 
 __device__ __forceinline__ void ring_fma(Acc& a, const float4 (&d)[2 * RG], const float4 (&c)[NCP])
 {
-    float dx[TM], dy[TM];
+    float2 dv[TM], cv[TNT];
 #pragma unroll
     for (int g = 0; g < RG; ++g) {
-        dx[4 * g + 0] = d[2 * g].x; dy[4 * g + 0] = d[2 * g].y; dx[4 * g + 1] = d[2 * g].z; dy[4 * g + 1] = d[2 * g].w;
-        dx[4 * g + 2] = d[2 * g + 1].x; dy[4 * g + 2] = d[2 * g + 1].y; dx[4 * g + 3] = d[2 * g + 1].z; dy[4 * g + 3] = d[2 * g + 1].w;
+        dv[4 * g + 0] = make_float2(d[2 * g].x, d[2 * g].y); dv[4 * g + 1] = make_float2(d[2 * g].z, d[2 * g].w);
+        dv[4 * g + 2] = make_float2(d[2 * g + 1].x, d[2 * g + 1].y); dv[4 * g + 3] = make_float2(d[2 * g + 1].z, d[2 * g + 1].w);
     }
-    float cx[TNT], cy[TNT];
 #pragma unroll
     for (int g = 0; g < NCP; ++g) {
-        cx[2 * g] = c[g].x; cy[2 * g] = c[g].y;
-        if (2 * g + 1 < TNT) { cx[2 * g + 1] = c[g].z; cy[2 * g + 1] = c[g].w; }
+        cv[2 * g] = make_float2(c[g].x, c[g].y);
+        if (2 * g + 1 < TNT) cv[2 * g + 1] = make_float2(c[g].z, c[g].w);
     }
 #pragma unroll
     for (int m = 0; m < TM; ++m)
 #pragma unroll
         for (int n = 0; n < TNT; ++n) {
-            a.A[m][n] = fmaf(cx[n], dx[m], a.A[m][n]);
-            a.B[m][n] = fmaf(cy[n], dy[m], a.B[m][n]);
-            a.C[m][n] = fmaf(cx[n], dy[m], a.C[m][n]);
-            a.D[m][n] = fmaf(cy[n], dx[m], a.D[m][n]);
+            // scalar FFMA on purpose: scripts/fma_probe.cu measures 53 TFLOP/s for this tile with FFMA
+            // and 50 with FFMA2 on B200 -- packed math only pays where issue slots are the limit
+            a.ab[m][n].x = fmaf(cv[n].x, dv[m].x, a.ab[m][n].x);   // A
+            a.ab[m][n].y = fmaf(cv[n].y, dv[m].y, a.ab[m][n].y);   // B
+            a.cd[m][n].x = fmaf(cv[n].x, dv[m].y, a.cd[m][n].x);   // C
+            a.cd[m][n].y = fmaf(cv[n].y, dv[m].x, a.cd[m][n].y);   // D
         }
 }
 
@@ -112,17 +114,28 @@ __device__ __forceinline__ void contract_freq(int k, int rh, int nring, const fl
 #pragma unroll
     for (int m = 0; m < TM; ++m)
 #pragma unroll
-        for (int n = 0; n < TNT; ++n) { a.A[m][n] = 0.f; a.B[m][n] = 0.f; a.C[m][n] = 0.f; a.D[m][n] = 0.f; }
+        for (int n = 0; n < TNT; ++n) { a.ab[m][n] = make_float2(0.f, 0.f); a.cd[m][n] = make_float2(0.f, 0.f); }
 
     // rings in descending length: stop at the first ring that no longer reaches frequency k.
     // Operands are prefetched two rings ahead through three register buffers.
+// timing experiments only (never defined in a shipped build): drop the operand loads
+#ifdef CRA_EXP_NOROW
+#define CRA_EXP_ROWLOAD(ptr) make_float4(1.0f + (float)e_, 0.5f, 0.25f + (float)p_, 2.0f)
+#else
+#define CRA_EXP_ROWLOAD(ptr) __ldg(ptr)
+#endif
+#ifdef CRA_EXP_NOREF
+#define CRA_EXP_REFLOAD(ptr, alt) (alt)
+#else
+#define CRA_EXP_REFLOAD(ptr, alt) __ldg(ptr)
+#endif
 #define CRA_HAS(j) ((j) >= 0 && k < c_half[(j) < 0 ? 0 : (j)])
 #define CRA_LOAD(D, C, j)                                                                        \
     { const int e_ = 2 * c_coff[j] + k, p_ = c_half[j] + 1;                                      \
       _Pragma("unroll") for (int g_ = 0; g_ < RG; ++g_) {                                        \
-          D[2 * g_] = __ldg(dq + g_ * gstride + e_); D[2 * g_ + 1] = __ldg(dq + g_ * gstride + e_ + p_); } \
+          D[2 * g_] = CRA_EXP_ROWLOAD(dq + g_ * gstride + e_); D[2 * g_ + 1] = CRA_EXP_ROWLOAD(dq + g_ * gstride + e_ + p_); } \
       _Pragma("unroll") for (int g_ = 0; g_ < NCP; ++g_)                                          \
-          C[g_] = __ldg(cq + e_ + (RH == 1 ? g_ : rh) * p_); }
+          C[g_] = CRA_EXP_REFLOAD(cq + e_ + (RH == 1 ? g_ : rh) * p_, D[g_]); }
     int i = nring - 1;
     float4 d0[2 * RG], c0[NCP], d1[2 * RG], c1[NCP], d2[2 * RG], c2[NCP];
     CRA_LOAD(d0, c0, i);
@@ -154,9 +167,12 @@ __device__ __forceinline__ void contract_freq(int k, int rh, int nring, const fl
 #pragma unroll
         for (int n = 0; n < TNT; ++n) {
             float2* w = s_w + (m * TN + rh * TNT + n) * PS;
-            const float A = a.A[m][n], B = a.B[m][n], C = a.C[m][n], D = a.D[m][n];
-            w[i0] = make_float2(A + B + C + D, A - B + D - C);
-            if (k != 0) w[i1] = make_float2(A + B - C - D, A - B + C - D);
+            const float2 ab = a.ab[m][n], cd = a.cd[m][n];
+            // s = (A+B, A-B), t = (C+D, D-C);  W[k] = s + t,  W[N-k] = s - t
+            const float2 sv = __ffma2_rn(make_float2(ab.y, ab.y), make_float2(1.0f, -1.0f), make_float2(ab.x, ab.x));
+            const float2 tv = __ffma2_rn(make_float2(cd.x, cd.x), make_float2(1.0f, -1.0f), make_float2(cd.y, cd.y));
+            w[i0] = crafft::cadd(sv, tv);
+            if (k != 0) w[i1] = crafft::csub(sv, tv);
         }
 }
 
@@ -214,32 +230,57 @@ ccf_peak_kernel(const float4* __restrict__ spec, int nrows, const float4* __rest
         const float2* d2 = reinterpret_cast<const float2*>(dq);
         const float2* c2 = reinterpret_cast<const float2*>(cq);
         const int l = tid - (NT - 32);
+        // Both loops issue their loads in batches of 8 rings: done one ring at a time they are a serial
+        // chain of L2 round trips (16-20 x ~600 clk) on which the whole CTA then waits at the barrier.
         if (l >= 0 && l < 32) {
+            int nfull = 0;
+            for (int i = nring - 1; i >= 0 && c_half[i] == N / 2; --i) ++nfull;
             for (int pair = l; pair < NP; pair += 32) {
                 const int m = pair / TN, n = pair % TN;
                 const float2* dm = d2 + (size_t)(m >> 2) * gstride * 2;
                 float a = 0.f;
-                for (int i = nring - 1; i >= 0 && c_half[i] == N / 2; --i)
-                    a = fmaf(__ldg(c2 + cra_spec_idx(c_coff[i], N / 2, n, N / 2)).x,
-                             __ldg(dm + cra_spec_idx(c_coff[i], N / 2, m, N / 2)).x, a);
+                for (int base = 0; base < nfull; base += 8) {
+                    float cvv[8], dvv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const bool ok = base + u < nfull;
+                        const int i = ok ? nring - 1 - (base + u) : nring - 1;
+                        cvv[u] = ok ? __ldg(c2 + cra_spec_idx(c_coff[i], N / 2, n, N / 2)).x : 0.f;
+                        dvv[u] = ok ? __ldg(dm + cra_spec_idx(c_coff[i], N / 2, m, N / 2)).x : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) a = fmaf(cvv[u], dvv[u], a);
+                }
                 const int h = N / 2;
                 s_w[pair * PS + (h >> S::L2) * (N2 + 1) + (h & (N2 - 1))] = make_float2(a, a);
             }
         }
         if (nyq_lane) {
-            for (int pair = nl; pair < NP; pair += 32) {
-                const int m = pair / TN, n = pair % TN;
+            int nshort = 0;
+            while (nshort < nring && c_half[nshort] < N / 2) ++nshort;
+            for (int pair = nl; pair < NP; pair += 32)
+#pragma unroll
+                for (int cl = 0; cl < 8; ++cl) s_nyq[pair][cl] = 0.f;
+            __syncwarp();
+            // lane = (pair, ring parity): products of its rings go to the ring's length class
+            for (int item = nl; item < 2 * NP; item += 32) {
+                const int pair = item % NP, par = item / NP, m = pair / TN, n = pair % TN;
                 const float2* dm = d2 + (size_t)(m >> 2) * gstride * 2;
-                int cls = -1, cur = -1; float a = 0.f;
-                for (int i = 0; i < nring && c_half[i] < N / 2; ++i) {
-                    const int h = c_half[i];
-                    if (h != cur) {
-                        if (cls >= 0) s_nyq[pair][cls & 7] = a;
-                        cur = h; ++cls; a = 0.f;
+                for (int base = par; base < nshort; base += 16) {
+                    float cvv[8], dvv[8]; int cls[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = base + 2 * u;
+                        const bool ok = i < nshort;
+                        const int h = c_half[ok ? i : 0];
+                        cls[u] = (29 - __clz(h)) & 7;                       // log2(half) - 2
+                        cvv[u] = ok ? __ldg(c2 + cra_spec_idx(c_coff[ok ? i : 0], h, n, h)).x : 0.f;
+                        dvv[u] = ok ? __ldg(dm + cra_spec_idx(c_coff[ok ? i : 0], h, m, h)).x : 0.f;
                     }
-                    a = fmaf(__ldg(c2 + cra_spec_idx(c_coff[i], h, n, h)).x, __ldg(dm + cra_spec_idx(c_coff[i], h, m, h)).x, a);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (base + 2 * u < nshort) atomicAdd(&s_nyq[pair][cls[u]], cvv[u] * dvv[u]);
                 }
-                if (cls >= 0) s_nyq[pair][cls & 7] = a;
             }
         }
     }
@@ -247,12 +288,12 @@ ccf_peak_kernel(const float4* __restrict__ spec, int nrows, const float4* __rest
     if (nyq_lane) {
         for (int pair = nl; pair < NP; pair += 32) {
             float2* w = s_w + pair * PS;
-            int cls = -1, cur = -1;
+            int cur = -1;
             for (int i = 0; i < nring && c_half[i] < N / 2; ++i) {
                 const int h = c_half[i];
                 if (h == cur) continue;
-                cur = h; ++cls;
-                const float a = s_nyq[pair][cls & 7];
+                cur = h;
+                const float a = s_nyq[pair][(29 - __clz(h)) & 7];
                 const int hh = N - h;
                 float2* p0 = w + (h >> S::L2) * (N2 + 1) + (h & (N2 - 1));
                 float2* p1 = w + (hh >> S::L2) * (N2 + 1) + (hh & (N2 - 1));
@@ -275,7 +316,7 @@ ccf_peak_kernel(const float4* __restrict__ spec, int nrows, const float4* __rest
         for (int j = 0; j < N1; ++j) {
             if (j == 0) { w[0] = x[0]; continue; }
             const float2 t = s_tw[j * N2 + n2];
-            w[j * (N2 + 1)] = make_float2(x[j].x * t.x - x[j].y * t.y, x[j].x * t.y + x[j].y * t.x);
+            w[j * (N2 + 1)] = crafft::cmul(x[j], t);
         }
     }
     __syncthreads();
@@ -512,6 +553,13 @@ int cra_launch_ccf(const float* spec, int nrows, const float* refspec, int R, co
                    const CraRingTab& htab, const float2* twid, CraCand* cand, int ntile_n, cudaStream_t st)
 {
     (void)tab;
+    // reference-resident persistent variant (cra_ccf_rr.cu): experimental, off by default (slower)
+    static const int use_rr = getenv("CRA_CCF_RR") ? atoi(getenv("CRA_CCF_RR")) : 0;
+    if (use_rr && TM == 4) {
+        bool ran = false;
+        if (cra_launch_ccf_rr(spec, nrows, refspec, R, htab, twid, cand, ntile_n, st, &ran)) return 1;
+        if (ran) return 0;
+    }
     if (bind_ring_table(htab, st)) return 1;
     switch (htab.log2n) {
         case 5:  return launch_ccf_t<5>(spec, nrows, refspec, R, htab, twid, cand, ntile_n, st);

@@ -95,6 +95,8 @@ int cra_launch_polar_single(const float* image, int nx, const CraRingTab* tab, c
 int cra_launch_ccf(const float* spec, int nrows, const float* refspec, int R, const CraRingTab* tab,
                    const CraRingTab& htab, const float2* twid, CraCand* cand, int ntile_n, cudaStream_t st);
 int cra_ccf_tile_n();
+int cra_launch_ccf_rr(const float* spec, int nrows, const float* refspec, int R, const CraRingTab& htab,
+                      const float2* twid, CraCand* cand, int ntile_n, cudaStream_t st, bool* ran);
 int cra_launch_finalize(const float* spec, const float* refspec, int R, const CraRingTab* tab, const CraRingTab& htab,
                         const CraCand* cand, int ntile_n, CraRowMap map, CraResult* out, cudaStream_t st);
 int cra_launch_ccf_curves(const float* spec, int row, const float* refspec, int ref, const CraRingTab* tab,

@@ -21,6 +21,18 @@ __host__ __device__ constexpr float tw_sin(int j)   // sin(2 pi j / 32), j < 16
 }
 __host__ __device__ constexpr int ilog2c(int n) { return n <= 1 ? 0 : 1 + ilog2c(n >> 1); }
 
+// Packed FP32 helpers: sm_100 FFMA2 / FADD2 / FMUL2 work on (lo, hi) register pairs, and ptxas
+// folds swapped (.LO_HI) and broadcast (.F32) operands into the instruction, so a complex
+// add is one instruction and a complex multiply two.
+__device__ __forceinline__ float2 swp(float2 a) { return make_float2(a.y, a.x); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }
+// a * (wr + i wi)
+__device__ __forceinline__ float2 cmul_w(float2 a, float wr, float wi)
+{
+    return __ffma2_rn(swp(a), make_float2(-wi, wi), __fmul2_rn(a, make_float2(wr, wr)));
+}
+
 // SGN = +1: kernel exp(+2 pi i n k / R) (inverse);  SGN = -1: exp(-2 pi i n k / R) (forward)
 template <int R, int LEN, int SGN>
 struct FftStage {
@@ -34,15 +46,20 @@ struct FftStage {
                 constexpr int TS = 32 / LEN;
                 const int tj = k * TS;
                 const int i0 = g * LEN + k, i1 = i0 + HALF;
-                float2 u = x[i0], b = x[i1], v;
-                if (tj == 0) v = b;
-                else if (tj == 8) v = (SGN > 0) ? make_float2(-b.y, b.x) : make_float2(b.y, -b.x);
-                else {
-                    const float wr = tw_cos(tj), wi = SGN * tw_sin(tj);
-                    v = make_float2(b.x * wr - b.y * wi, b.x * wi + b.y * wr);
+                const float2 u = x[i0], b = x[i1];
+                if (tj == 0) {
+                    x[i0] = cadd(u, b);
+                    x[i1] = csub(u, b);
+                } else if (tj == 8) {
+                    // v = (+-i) b = SGN * (-b.y, b.x);  u +- v folded into one packed FMA each
+                    const float2 sb = swp(b);
+                    x[i0] = __ffma2_rn(sb, make_float2(-(float)SGN, (float)SGN), u);
+                    x[i1] = __ffma2_rn(sb, make_float2((float)SGN, -(float)SGN), u);
+                } else {
+                    const float2 v = cmul_w(b, tw_cos(tj), SGN * tw_sin(tj));
+                    x[i0] = cadd(u, v);
+                    x[i1] = csub(u, v);
                 }
-                x[i0] = make_float2(u.x + v.x, u.y + v.y);
-                x[i1] = make_float2(u.x - v.x, u.y - v.y);
             }
         }
         FftStage<R, LEN * 2, SGN>::run(x);
@@ -67,7 +84,7 @@ __device__ __forceinline__ void fft_reg(float2 (&x)[R])
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b)
 {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+    return __ffma2_rn(swp(a), make_float2(-b.y, b.y), __fmul2_rn(a, make_float2(b.x, b.x)));
 }
 
 }  // namespace crafft
