@@ -7,6 +7,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <mutex>
 
@@ -44,6 +45,13 @@ struct CraCtx {
     float* d_curves = nullptr;
     float2* h_group = nullptr;   // pinned staging of one 4-row spectrum group (test entry points)
     std::vector<cudaEvent_t> ev;
+    // contraction path: CRA_FMT_FRAG = tensor-core kernel on split-bf16 fragments (default),
+    // CRA_FMT_F32 = FP32 FMA kernel on the float2 spectrum (CRA_CCF=simt)
+    int fmt = CRA_FMT_FRAG;
+    CraFragTab frag{};
+    std::vector<int> h_koff, h_chunk_k;
+    int* d_fragtab = nullptr;
+    size_t row_bytes = 0;        // device spectrum bytes of one row in the active format
 };
 
 namespace {
@@ -109,6 +117,23 @@ int build_tables(CraCtx* c)
     }
     t.nn = nn;
     t.nc = t.lcirc / 2 + nring;
+    // fragment layout: chunks of 16 rings per frequency, longest rings first (cra_common.cuh)
+    {
+        const int nk = t.maxrin / 2 + 1;
+        c->h_koff.assign(nk + 1, 0); c->h_chunk_k.clear();
+        for (int k = 0; k < nk; ++k) {
+            int Kk = 0;
+            for (int i = 0; i < nring; ++i) if ((t.len[i] >> 1) >= k) ++Kk;
+            const int nchk = (Kk + 15) / 16;
+            for (int cc = 0; cc < nchk; ++cc) c->h_chunk_k.push_back((k << 4) | cc);
+            c->h_koff[k + 1] = c->h_koff[k] + nchk;
+        }
+        c->frag.nk = nk; c->frag.nch = c->h_koff[nk];
+        std::vector<int> all(c->h_koff); all.insert(all.end(), c->h_chunk_k.begin(), c->h_chunk_k.end());
+        CRA_CUDA(cudaMalloc(&c->d_fragtab, sizeof(int) * all.size()));
+        CRA_CUDA(cudaMemcpy(c->d_fragtab, all.data(), sizeof(int) * all.size(), cudaMemcpyHostToDevice));
+        c->frag.koff = c->d_fragtab; c->frag.chunk_k = c->d_fragtab + (nk + 1);
+    }
     t.lcpad = (2 * pacc + 3) & ~3;
     std::vector<float2> twf(t.maxrin), twi;
     for (int j = 0; j < t.maxrin; ++j) {
@@ -226,16 +251,24 @@ extern "C" int cra_create(const CraConfig* cfg, int device, CraCtx** out)
     CraCtx* c = new CraCtx();
     c->cfg = *cfg; c->device = device; c->nx = cfg->nx; c->npix = cfg->nx * cfg->nx;
     if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { cra_set_error("stream create failed"); delete c; return 1; }
+    {
+        const char* e = getenv("CRA_CCF");
+        if (e && strcmp(e, "simt") == 0) c->fmt = CRA_FMT_F32;
+        else if (e && strcmp(e, "mma") != 0 && e[0]) { cra_set_error("CRA_CCF must be 'mma' or 'simt'"); cra_destroy(c); return 1; }
+    }
     if (build_tables(c)) { cra_destroy(c); return 1; }
     const int k = (int)(cfg->max_range / cfg->step);
     c->smax = (2 * k + 1) * (2 * k + 1);
-    const size_t row_bytes = (size_t)c->htab.nc * sizeof(float2);     // device spectrum of one row
+    const size_t row_bytes = (c->fmt == CRA_FMT_FRAG) ? cra_frag_row_bytes(c->frag.nch)
+                                                      : (size_t)c->htab.nc * sizeof(float2);     // device spectrum of one row
+    c->row_bytes = row_bytes;
     long rb = cfg->row_batch > 0 ? cfg->row_batch : (long)((size_t)2 << 30) / (long)row_bytes;
     if (rb < c->smax) rb = c->smax;
     long want = (long)cfg->max_particles * c->smax;
     if (rb > want) rb = want;
     c->row_batch = (int)rb;
-    c->ntile_n_max = (cfg->max_refs + cra_ccf_tile_n() - 1) / cra_ccf_tile_n();
+    c->ntile_n_max = (c->fmt == CRA_FMT_FRAG) ? cra_ccf_mma_num_tiles(cfg->max_refs, c->htab.log2n)
+                                              : (cfg->max_refs + cra_ccf_tile_n() - 1) / cra_ccf_tile_n();
     const size_t nsum = (size_t)cfg->max_refs * 2 * c->npix + cfg->max_refs;
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = cudaMalloc(&c->d_images, (size_t)cfg->max_particles * c->npix * sizeof(float));
@@ -261,7 +294,7 @@ extern "C" int cra_destroy(CraCtx* c)
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
     for (auto& e : c->ev) cudaEventDestroy(e);
-    cudaFree(c->d_items);
+    cudaFree(c->d_items); cudaFree(c->d_fragtab);
     cudaFree(c->d_tab); cudaFree(c->d_samp); cudaFree(c->d_sampw); cudaFree(c->d_twf); cudaFree(c->d_twi);
     cudaFree(c->d_mask); cudaFree(c->d_images); cudaFree(c->d_refs); cudaFree(c->d_refspec);
     cudaFree(c->d_spec); cudaFree(c->d_cand); cudaFree(c->d_sums); cudaFree(c->d_meta); cudaFree(c->d_res);
@@ -308,7 +341,8 @@ extern "C" int cra_set_refs(CraCtx* c, const float* h, int R, int normalize_mask
     if (R < 1 || R > c->cfg.max_refs) { cra_set_error("R exceeds max_refs"); return 1; }
     CRA_CUDA(cudaMemcpyAsync(c->d_refs, h, (size_t)R * c->npix * sizeof(float), cudaMemcpyHostToDevice, c->st));
     if (normalize_mask && cra_launch_mask_normalize(c->d_refs, R, c->nx, c->d_mask, 1, c->st)) return 1;
-    if (cra_launch_polar_refs(c->d_refs, R, c->nx, c->d_tab, c->htab, c->d_samp, c->d_twf, c->items, c->d_refspec, c->st)) return 1;
+    if (cra_launch_polar_refs(c->d_refs, R, c->nx, c->d_tab, c->htab, c->d_samp, c->d_twf, c->items, c->d_refspec,
+                              c->fmt, c->frag, c->st)) return 1;
     CRA_CUDA(cudaStreamSynchronize(c->st));
     c->R = R;
     return 0;
@@ -374,7 +408,7 @@ extern "C" int cra_align(CraCtx* c, int start, int stop, const CraSearch* search
     const int* d_cs = d_rs + n + nb;
 
     const int TN = cra_ccf_tile_n();
-    const int ntile_n = (c->R + TN - 1) / TN;
+    const int ntile_n = (c->fmt == CRA_FMT_FRAG) ? cra_ccf_mma_num_tiles(c->R, c->htab.log2n) : (c->R + TN - 1) / TN;
     const bool tm = c->timing;
     if (tm) {
         while (c->ev.size() < 4 * nb) { cudaEvent_t e; CRA_CUDA(cudaEventCreate(&e)); c->ev.push_back(e); }
@@ -389,12 +423,16 @@ extern "C" int cra_align(CraCtx* c, int start, int stop, const CraSearch* search
         map.np = bcount[bi]; map.nrows = brows[bi]; map.p0 = start + bfirst[bi]; map.step = step;
         if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 0], c->st));
         if (cra_launch_polar_rows(c->d_images, c->nx, c->d_tab, c->htab, c->d_samp, c->d_sampw, c->d_twf, c->items, map,
-                                  c->cfg.normalize_ring, c->d_spec, c->st)) return 1;
+                                  c->cfg.normalize_ring, c->d_spec, c->fmt, c->frag, c->st)) return 1;
         if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 1], c->st));
-        if (cra_launch_ccf(c->d_spec, map.nrows, c->d_refspec, c->R, c->d_tab, c->htab, c->d_twi, c->d_cand, ntile_n, c->st)) return 1;
+        if (c->fmt == CRA_FMT_FRAG) {
+            if (cra_launch_ccf_mma(reinterpret_cast<const unsigned char*>(c->d_spec), map.nrows,
+                                   reinterpret_cast<const unsigned char*>(c->d_refspec), c->R, c->htab, c->frag, c->h_koff,
+                                   c->d_twi, c->d_cand, ntile_n, c->st)) return 1;
+        } else if (cra_launch_ccf(c->d_spec, map.nrows, c->d_refspec, c->R, c->d_tab, c->htab, c->d_twi, c->d_cand, ntile_n, c->st)) return 1;
         if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 2], c->st));
         if (cra_launch_finalize(c->d_spec, c->d_refspec, c->R, c->d_tab, c->htab, c->d_cand, ntile_n, map,
-                                c->d_res + bfirst[bi], c->st)) return 1;
+                                c->d_res + bfirst[bi], c->fmt, c->frag, c->st)) return 1;
         if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 3], c->st));
         launches += 3;
     }
@@ -517,15 +555,24 @@ extern "C" int cra_transform(CraCtx* c, int start, int stop, const float* params
     return 0;
 }
 
-// device spectrum (row `lane4` of the group staged in h_group) -> SPIDER packed layout
+// device spectrum staged in h_group -> SPIDER packed layout.  F32: row `lane4` of the 4-row group;
+// FRAG: the staged row itself (value = bf16 hi + bf16 lo).
 static void unpack_spectrum(const CraCtx* c, int lane4, float* out)
 {
     const CraRingTab& t = c->htab;
+    const unsigned char* fb = reinterpret_cast<const unsigned char*>(c->h_group);
     for (int i = 0; i < t.nring; ++i) {
         const int half = t.len[i] >> 1;
         float* o = out + t.off[i];
         for (int k = 0; k <= half; ++k) {
-            const float2 v = c->h_group[cra_spec_idx(t.coff[i], half, lane4, k)];
+            float2 v;
+            if (c->fmt == CRA_FMT_FRAG) {
+                const int s = t.nring - 1 - i, gc = c->h_koff[k] + (s >> 4), tq = (s & 15) >> 2, j = s & 3;
+                const unsigned short* u = reinterpret_cast<const unsigned short*>(fb + (size_t)gc * 128 + tq * 32);
+                auto bf = [](unsigned short h) { unsigned int b = (unsigned int)h << 16; float f; memcpy(&f, &b, 4); return f; };
+                v.x = bf(u[j]) + bf(u[4 + j]);
+                v.y = bf(u[8 + j]) + bf(u[12 + j]);
+            } else v = c->h_group[cra_spec_idx(t.coff[i], half, lane4, k)];
             if (k == 0) o[0] = v.x;
             else if (k == half) o[1] = v.x;
             else { o[2 * k] = v.x; o[2 * k + 1] = v.y; }
@@ -538,8 +585,9 @@ extern "C" int cra_polar_spectrum(CraCtx* c, int particle, float cx, float cy, f
     Bind b(c); if (b.ok()) return 1;
     if (particle < 0 || particle >= c->cfg.max_particles) { cra_set_error("bad particle index"); return 1; }
     if (cra_launch_polar_single(c->d_images + (size_t)particle * c->npix, c->nx, c->d_tab, c->htab, c->d_samp, c->d_sampw,
-                                c->d_twf, c->items, cx, cy, c->cfg.normalize_ring, c->d_spec, c->st)) return 1;
-    CRA_CUDA(cudaMemcpyAsync(c->h_group, c->d_spec, (size_t)c->htab.nc * 4 * sizeof(float2), cudaMemcpyDeviceToHost, c->st));
+                                c->d_twf, c->items, cx, cy, c->cfg.normalize_ring, c->d_spec, c->fmt, c->frag, c->st)) return 1;
+    const size_t bytes = (c->fmt == CRA_FMT_FRAG) ? c->row_bytes : 4 * c->row_bytes;
+    CRA_CUDA(cudaMemcpyAsync(c->h_group, c->d_spec, bytes, cudaMemcpyDeviceToHost, c->st));
     CRA_CUDA(cudaStreamSynchronize(c->st));
     unpack_spectrum(c, 0, host_out);
     return 0;
@@ -549,8 +597,11 @@ extern "C" int cra_ref_spectrum(CraCtx* c, int iref, float* host_out)
 {
     Bind b(c); if (b.ok()) return 1;
     if (iref < 0 || iref >= c->R) { cra_set_error("bad reference index"); return 1; }
-    CRA_CUDA(cudaMemcpyAsync(c->h_group, reinterpret_cast<float2*>(c->d_refspec) + (size_t)(iref >> 2) * c->htab.nc * 4,
-                             (size_t)c->htab.nc * 4 * sizeof(float2), cudaMemcpyDeviceToHost, c->st));
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(c->d_refspec);
+    if (c->fmt == CRA_FMT_FRAG)
+        CRA_CUDA(cudaMemcpyAsync(c->h_group, src + (size_t)iref * c->row_bytes, c->row_bytes, cudaMemcpyDeviceToHost, c->st));
+    else
+        CRA_CUDA(cudaMemcpyAsync(c->h_group, src + (size_t)(iref >> 2) * 4 * c->row_bytes, 4 * c->row_bytes, cudaMemcpyDeviceToHost, c->st));
     CRA_CUDA(cudaStreamSynchronize(c->st));
     unpack_spectrum(c, iref & 3, host_out);
     return 0;
@@ -561,9 +612,9 @@ extern "C" int cra_ccf_curves(CraCtx* c, int particle, float cx, float cy, int i
     Bind b(c); if (b.ok()) return 1;
     if (particle < 0 || particle >= c->cfg.max_particles || iref < 0 || iref >= c->R) { cra_set_error("bad index"); return 1; }
     if (cra_launch_polar_single(c->d_images + (size_t)particle * c->npix, c->nx, c->d_tab, c->htab, c->d_samp, c->d_sampw,
-                                c->d_twf, c->items, cx, cy, c->cfg.normalize_ring, c->d_spec, c->st)) return 1;
+                                c->d_twf, c->items, cx, cy, c->cfg.normalize_ring, c->d_spec, c->fmt, c->frag, c->st)) return 1;
     if (cra_launch_ccf_curves(c->d_spec, 0, c->d_refspec, iref, c->d_tab, c->htab,
-                              c->d_curves, c->d_curves + c->htab.maxrin, c->st)) return 1;
+                              c->d_curves, c->d_curves + c->htab.maxrin, c->fmt, c->frag, c->st)) return 1;
     CRA_CUDA(cudaMemcpyAsync(q_out, c->d_curves, c->htab.maxrin * sizeof(float), cudaMemcpyDeviceToHost, c->st));
     CRA_CUDA(cudaMemcpyAsync(t_out, c->d_curves + c->htab.maxrin, c->htab.maxrin * sizeof(float), cudaMemcpyDeviceToHost, c->st));
     CRA_CUDA(cudaStreamSynchronize(c->st));

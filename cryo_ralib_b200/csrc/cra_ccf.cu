@@ -390,10 +390,38 @@ __device__ void pair_freq(const float2* __restrict__ spec, int row, const float2
     zq_r = A + B; zq_i = D - C; zt_r = A - B; zt_i = -C - D;
 }
 
+// ---- the same on the fragment layout (CRA_FMT_FRAG): value = bf16 hi + bf16 lo -------------------
+__device__ __forceinline__ float frag_val(const uint4& u, int j)
+{
+    const unsigned h = (j < 2) ? u.x : u.y, l = (j < 2) ? u.z : u.w;
+    const unsigned sh = (j & 1) ? 0u : 16u;
+    return __uint_as_float((h << sh) & 0xffff0000u) + __uint_as_float((l << sh) & 0xffff0000u);
+}
+
+__device__ void pair_freq_frag(const unsigned char* __restrict__ rowp, const unsigned char* __restrict__ refp,
+                               const CraFragTab& frag, int k, float& zq_r, float& zq_i, float& zt_r, float& zt_i)
+{
+    float A = 0.f, B = 0.f, C = 0.f, D = 0.f;
+    const int c1 = frag.koff[k + 1];
+    for (int gc = frag.koff[k]; gc < c1; ++gc)
+        for (int t = 0; t < 4; ++t) {
+            const uint4* dp = reinterpret_cast<const uint4*>(rowp + (size_t)gc * 128 + t * 32);
+            const uint4* cp = reinterpret_cast<const uint4*>(refp + (size_t)gc * 128 + t * 32);
+            const uint4 dre = dp[0], dim = dp[1], cre = cp[0], cim = cp[1];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float dx = frag_val(dre, j), dy = frag_val(dim, j), cx = frag_val(cre, j), cy = frag_val(cim, j);
+                A = fmaf(cx, dx, A); B = fmaf(cy, dy, B); C = fmaf(cx, dy, C); D = fmaf(cy, dx, D);
+            }
+        }
+    zq_r = A + B; zq_i = D - C; zt_r = A - B; zt_i = -C - D;
+}
+
+template <int FMT>
 __global__ void __launch_bounds__(128)
 finalize_kernel(const float2* __restrict__ spec, const float2* __restrict__ refspec, int R,
                 const CraRingTab* __restrict__ tab, const CraCand* __restrict__ cand, int ntile_n,
-                CraRowMap map, CraResult* __restrict__ out)
+                CraRowMap map, CraResult* __restrict__ out, CraFragTab frag)
 {
     const int lane = threadIdx.x & 31;
     const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -427,7 +455,11 @@ finalize_kernel(const float2* __restrict__ spec, const float2* __restrict__ refs
     double t7[7] = {0, 0, 0, 0, 0, 0, 0};
     for (int k = lane; k <= N / 2; k += 32) {
         float qr, qi, tr, ti;
-        pair_freq(spec, row, refspec, iref, tab, k, qr, qi, tr, ti);
+        if (FMT == CRA_FMT_FRAG) {
+            const size_t rb = cra_frag_row_bytes(frag.nch);
+            pair_freq_frag(reinterpret_cast<const unsigned char*>(spec) + (size_t)row * rb,
+                           reinterpret_cast<const unsigned char*>(refspec) + (size_t)iref * rb, frag, k, qr, qi, tr, ti);
+        } else pair_freq(spec, row, refspec, iref, tab, k, qr, qi, tr, ti);
         const double zr = mirror ? tr : qr, zi = mirror ? ti : qi;
         const double wgt = (k == 0 || k == N / 2) ? 1.0 : 2.0;
 #pragma unroll
@@ -465,14 +497,19 @@ finalize_kernel(const float2* __restrict__ spec, const float2* __restrict__ refs
 }
 
 // Test entry: full q/t curves of one pair by direct evaluation.
+template <int FMT>
 __global__ void ccf_curves_kernel(const float2* __restrict__ spec, int row, const float2* __restrict__ refspec, int ref,
-                                  const CraRingTab* __restrict__ tab, float* __restrict__ q, float* __restrict__ t)
+                                  const CraRingTab* __restrict__ tab, float* __restrict__ q, float* __restrict__ t, CraFragTab frag)
 {
     extern __shared__ float4 s_z[];   // N/2+1 entries: (qr, qi, tr, ti)
     const int N = tab->maxrin;
     for (int k = threadIdx.x; k <= N / 2; k += blockDim.x) {
         float4 z;
-        pair_freq(spec, row, refspec, ref, tab, k, z.x, z.y, z.z, z.w);
+        if (FMT == CRA_FMT_FRAG) {
+            const size_t rb = cra_frag_row_bytes(frag.nch);
+            pair_freq_frag(reinterpret_cast<const unsigned char*>(spec) + (size_t)row * rb,
+                           reinterpret_cast<const unsigned char*>(refspec) + (size_t)ref * rb, frag, k, z.x, z.y, z.z, z.w);
+        } else pair_freq(spec, row, refspec, ref, tab, k, z.x, z.y, z.z, z.w);
         s_z[k] = z;
     }
     __syncthreads();
@@ -573,23 +610,28 @@ int cra_launch_ccf(const float* spec, int nrows, const float* refspec, int R, co
 }
 
 int cra_launch_finalize(const float* spec, const float* refspec, int R, const CraRingTab* tab, const CraRingTab& htab,
-                        const CraCand* cand, int ntile_n, CraRowMap map, CraResult* out, cudaStream_t st)
+                        const CraCand* cand, int ntile_n, CraRowMap map, CraResult* out, int fmt, const CraFragTab& frag,
+                        cudaStream_t st)
 {
     (void)htab;
     if (map.np <= 0) return 0;
     const int wpb = 4;
-    finalize_kernel<<<(map.np + wpb - 1) / wpb, wpb * 32, 0, st>>>(reinterpret_cast<const float2*>(spec),
-                                                                  reinterpret_cast<const float2*>(refspec), R, tab, cand,
-                                                                  ntile_n, map, out);
+    const float2* s2 = reinterpret_cast<const float2*>(spec); const float2* r2 = reinterpret_cast<const float2*>(refspec);
+    if (fmt == CRA_FMT_FRAG)
+        finalize_kernel<CRA_FMT_FRAG><<<(map.np + wpb - 1) / wpb, wpb * 32, 0, st>>>(s2, r2, R, tab, cand, ntile_n, map, out, frag);
+    else
+        finalize_kernel<CRA_FMT_F32><<<(map.np + wpb - 1) / wpb, wpb * 32, 0, st>>>(s2, r2, R, tab, cand, ntile_n, map, out, frag);
     CRA_CUDA(cudaGetLastError());
     return 0;
 }
 
 int cra_launch_ccf_curves(const float* spec, int row, const float* refspec, int ref, const CraRingTab* tab,
-                          const CraRingTab& htab, float* q, float* t, cudaStream_t st)
+                          const CraRingTab& htab, float* q, float* t, int fmt, const CraFragTab& frag, cudaStream_t st)
 {
-    ccf_curves_kernel<<<1, 256, (htab.maxrin / 2 + 1) * sizeof(float4), st>>>(reinterpret_cast<const float2*>(spec), row,
-                                                                            reinterpret_cast<const float2*>(refspec), ref, tab, q, t);
+    const float2* s2 = reinterpret_cast<const float2*>(spec); const float2* r2 = reinterpret_cast<const float2*>(refspec);
+    const size_t sm = (htab.maxrin / 2 + 1) * sizeof(float4);
+    if (fmt == CRA_FMT_FRAG) ccf_curves_kernel<CRA_FMT_FRAG><<<1, 256, sm, st>>>(s2, row, r2, ref, tab, q, t, frag);
+    else ccf_curves_kernel<CRA_FMT_F32><<<1, 256, sm, st>>>(s2, row, r2, ref, tab, q, t, frag);
     CRA_CUDA(cudaGetLastError());
     return 0;
 }

@@ -1,0 +1,336 @@
+// cra_ccf_mma.cu -- Crosrng_ms ring contraction on the tensor cores, fused with the inverse FFT
+// and the peak search (EMAN2 Util::Crosrng_ms + the best-of loop of Util::multiref_polar_ali_2d;
+// reference call site test_mref.py:200-201; replaces cu_ccf_mult_m + cuFFT C2R + cu_max_idx_batch,
+// cuda/gpu_aln_noref.cu:1009-1143, :2198-2206, :1305-1346).
+//
+// For every angular frequency k the contraction over rings is a small real GEMM
+//     [ (row, re) ; (row, im) ]  x  [ (ref, re) , (ref, im) ]        K = rings reaching k  (<= nring)
+// whose four products per (row, ref) are the ring sums A = sum c.x d.x, D = sum c.y d.x,
+// C = sum c.x d.y, B = sum c.y d.y of Crosrng_ms (c = weighted reference spectrum, d = particle
+// spectrum):  q_k = (A+B) + i(D-C),  t_k = (A-B) - i(C+D).  maxrin/2+1 independent GEMMs with
+// K <= 36 are far too small for tcgen05 (M >= 64 per instruction and the 2 KB of q/t spectrum per
+// pair must stay on chip for the inverse FFT, which caps a tile at ~100 pairs per SM), so they run as
+// warp-level mma.sync.m16n8k16 (bf16, fp32 accumulate) with operands straight from L2 in
+// fragment order (cra_common.cuh, CRA_FMT_FRAG): one 256-bit load is a thread's A fragment, one
+// 128-bit load its B fragment.  FP32 accuracy comes from the split a = a_hi + a_lo:
+// a.b ~= a_hi b_hi + a_hi b_lo + a_lo b_hi (3 MMAs; the dropped a_lo b_lo term is 2^-18 relative).
+//
+// One CTA = 8 rows (particle x shift) x up to 4*NJ references; 16 warps share the frequencies
+// (host-balanced lists in constant memory), each warp keeps one frequency's 8 x 4*NJ tile in
+// registers, and writes the Hermitian-extended W = q + i t to shared memory when the last ring
+// chunk of that frequency is done.  Then the whole CTA runs one length-maxrin complex inverse FFT
+// per pair (two register passes), the ">=" argmax, the straight/mirror choice and the
+// best-over-references rule, and stores one (value, code) candidate per row.
+#include "cra_common.cuh"
+#include "cra_fft.cuh"
+#include <math.h>
+#include <string.h>
+#include <stdlib.h>
+
+namespace {
+
+constexpr int kWarps = 16;
+constexpr int kThreads = kWarps * 32;
+constexpr int kMaxItems = 320;          // chunk items per warp (constant memory)
+
+// per-warp work lists: gc | k << 13 | last << 23   (gc = chunk index within a row)
+__constant__ int c_items[kWarps][kMaxItems];
+__constant__ int c_nitems[kWarps];
+
+using crafft::fft_reg;
+
+template <int LOG2N>
+struct MShape {
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int L1 = LOG2N / 2;
+    static constexpr int L2 = LOG2N - L1;
+    static constexpr int N1 = 1 << L1;
+    static constexpr int N2 = 1 << L2;
+    static constexpr int PS = N1 * (N2 + 1) + ((N1 * (N2 + 1)) % 2 == 0 ? 1 : 0);   // odd float2 stride of one pair
+    // rows and reference quads per CTA, bounded by shared memory for W (PS * 8 bytes per pair)
+    static constexpr int ROWS = (LOG2N >= 10) ? 4 : 8;
+    static constexpr int NJ = (LOG2N <= 8) ? 3 : 1;
+    static constexpr int RS = 4 * NJ;                   // pair slots per row
+    static constexpr int NP = ROWS * RS;
+};
+
+__device__ __forceinline__ void mma_bf16(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+struct Frag8 { unsigned w[8]; };
+__device__ __forceinline__ Frag8 ldg256(const unsigned char* p)
+{
+    Frag8 f;
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(f.w[0]), "=r"(f.w[1]), "=r"(f.w[2]), "=r"(f.w[3]), "=r"(f.w[4]), "=r"(f.w[5]), "=r"(f.w[6]), "=r"(f.w[7])
+                 : "l"(p));
+    return f;
+}
+
+__device__ __forceinline__ bool better(float v, int m, float bv, int bm)
+{   // ">=" scan order semantics: larger value wins, ties go to the later index
+    return (v > bv) || (v == bv && m > bm);
+}
+
+template <int NJ>
+struct Operands { Frag8 a; uint4 b[NJ]; };
+
+template <int LOG2N>
+__global__ void __launch_bounds__(kThreads, 1)
+ccf_mma_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned char* __restrict__ refspec, int R,
+               size_t row_bytes, const float2* __restrict__ twid, CraCand* __restrict__ cand,
+               int nquad, int ncta_n)
+{
+    using S = MShape<LOG2N>;
+    constexpr int N = S::N, N1 = S::N1, N2 = S::N2, PS = S::PS, NJ = S::NJ, RS = S::RS, ROWS = S::ROWS, NP = S::NP;
+    extern __shared__ __align__(16) float2 s_dyn[];
+    float2* s_w = s_dyn;                      // NP * PS
+    float2* s_tw = s_dyn + NP * PS;           // N : s_tw[j*N2 + n2] = exp(+2 pi i n2 j / N)
+    __shared__ CraCand s_pair[NP];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    // reference tile fastest so that concurrently resident CTAs share the row spectra in L2
+    const int cn = blockIdx.x % ncta_n, cm = blockIdx.x / ncta_n;
+    const int qbase = nquad / ncta_n, qrem = nquad % ncta_n;
+    const int nj = qbase + (cn < qrem ? 1 : 0);                 // reference quads of this CTA (<= NJ)
+    const int q0 = cn * qbase + min(cn, qrem);
+    const int row0 = cm * ROWS;
+    for (int i = tid; i < N; i += kThreads) s_tw[i] = twid[i];
+
+    // ---- contraction: this warp's frequencies, chunk by chunk ---------------------------------
+    {
+        int rrow = row0 + (ROWS == 8 ? g : (g & 3));
+        if (rrow >= nrows) rrow = nrows - 1;
+        const unsigned char* pa = spec + (size_t)rrow * row_bytes + t * 32;
+        const unsigned char* pb[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int jj = (j < nj) ? j : 0;
+            pb[j] = refspec + (size_t)(4 * (q0 + jj) + (g >> 1)) * row_bytes + t * 32 + (g & 1) * 16;
+        }
+        float acc_h[NJ][4], acc_l[NJ][4];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { acc_h[j][e] = 0.f; acc_l[j][e] = 0.f; }
+
+        const int nit = c_nitems[warp];
+        const int* items = c_items[warp];
+
+#define CRA_LOAD_OPS(O, item)                                                            \
+        { const size_t off_ = (size_t)((item) & 8191) * 128;                             \
+          O.a = ldg256(pa + off_);                                                       \
+          _Pragma("unroll") for (int j_ = 0; j_ < NJ; ++j_)                              \
+              if (j_ < nj) O.b[j_] = __ldg(reinterpret_cast<const uint4*>(pb[j_] + off_)); }
+#define CRA_COMPUTE(O, item)                                                             \
+        { _Pragma("unroll") for (int j_ = 0; j_ < NJ; ++j_)                              \
+              if (j_ < nj) {                                                             \
+                  mma_bf16(acc_l[j_], O.a.w[0], O.a.w[4], O.a.w[1], O.a.w[5], O.b[j_].z, O.b[j_].w);   /* a_hi b_lo */ \
+                  mma_bf16(acc_l[j_], O.a.w[2], O.a.w[6], O.a.w[3], O.a.w[7], O.b[j_].x, O.b[j_].y);   /* a_lo b_hi */ \
+                  mma_bf16(acc_h[j_], O.a.w[0], O.a.w[4], O.a.w[1], O.a.w[5], O.b[j_].x, O.b[j_].y);   /* a_hi b_hi */ \
+              }                                                                          \
+          if ((item) >> 23) flush_freq(((item) >> 13) & 1023); }
+
+        auto flush_freq = [&](int k) {
+            const int kk = (N - k) & (N - 1);
+            const int i0 = (k >> S::L2) * (N2 + 1) + (k & (N2 - 1));
+            const int i1 = (kk >> S::L2) * (N2 + 1) + (kk & (N2 - 1));
+            const bool wr = (ROWS == 8) || (g < 4);
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                if (j < nj) {
+                    // c0 = A (re.re), c1 = D (row re . ref im), c2 = C (row im . ref re), c3 = B (im.im)
+                    const float A = acc_h[j][0] + acc_l[j][0], D = acc_h[j][1] + acc_l[j][1];
+                    const float C = acc_h[j][2] + acc_l[j][2], B = acc_h[j][3] + acc_l[j][3];
+                    // s = (A+B, A-B), tv = (C+D, D-C);  W[k] = s + tv,  W[N-k] = s - tv
+                    const float sx = A + B, sy = A - B, tx = C + D, ty = D - C;
+                    if (wr) {
+                        float2* w = s_w + (g * RS + 4 * j + t) * PS;
+                        w[i0] = make_float2(sx + tx, sy + ty);
+                        if (k != 0 && k != N / 2) w[i1] = make_float2(sx - tx, sy - ty);
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { acc_h[j][e] = 0.f; acc_l[j][e] = 0.f; }
+            }
+        };
+
+        Operands<NJ> o0, o1;
+        if (nit > 0) CRA_LOAD_OPS(o0, items[0]);
+        for (int i = 0; i < nit; i += 2) {
+            const int e0 = items[i];
+            const bool h1 = i + 1 < nit;
+            const int e1 = h1 ? items[i + 1] : 0;
+            if (h1) CRA_LOAD_OPS(o1, e1);
+            CRA_COMPUTE(o0, e0);
+            if (!h1) break;
+            if (i + 2 < nit) CRA_LOAD_OPS(o0, items[i + 2]);
+            CRA_COMPUTE(o1, e1);
+        }
+#undef CRA_LOAD_OPS
+#undef CRA_COMPUTE
+    }
+    __syncthreads();
+
+    // ---- inverse FFT of every pair, pass 1: (pair, n2): N1-point DFT over n1, twiddle ----------
+    const int npr = 4 * nj;                   // live pair slots per row
+    const int nlive = ROWS * npr;
+    for (int item = tid; item < nlive * N2; item += kThreads) {
+        const int pi = item / N2, n2 = item - pi * N2;
+        const int pr = pi / npr, pc = pi - pr * npr;
+        float2* w = s_w + (pr * RS + pc) * PS + n2;
+        float2 x[N1];
+#pragma unroll
+        for (int j = 0; j < N1; ++j) x[j] = w[j * (N2 + 1)];
+        fft_reg<N1, 1>(x);
+#pragma unroll
+        for (int j = 0; j < N1; ++j) {
+            if (j == 0) { w[0] = x[0]; continue; }
+            const float2 tw = s_tw[j * N2 + n2];
+            w[j * (N2 + 1)] = crafft::cmul(x[j], tw);
+        }
+    }
+    __syncthreads();
+
+    // ---- pass 2: (pair, k1): N2-point DFT over n2 -> X[k1 + N1*k2]; argmax over lags ------------
+    for (int item = tid; item < nlive * N1; item += kThreads) {
+        const int pi = item / N1, k1 = item - pi * N1;
+        const int pr = pi / npr, pc = pi - pr * npr;
+        const int slot = pr * RS + pc;
+        const float2* w = s_w + slot * PS + k1 * (N2 + 1);
+        float2 x[N2];
+#pragma unroll
+        for (int j = 0; j < N2; ++j) x[j] = w[j];
+        fft_reg<N2, 1>(x);
+        float bq = -INFINITY, bt = -INFINITY; int mq = -1, mt = -1;
+#pragma unroll
+        for (int j = 0; j < N2; ++j) {
+            const int m = k1 + N1 * j;
+            if (x[j].x >= bq) { bq = x[j].x; mq = m; }
+            if (x[j].y >= bt) { bt = x[j].y; mt = m; }
+        }
+        // the N1 lanes of one pair are consecutive and aligned inside a warp (N1 <= 32)
+#pragma unroll
+        for (int o = N1 >> 1; o > 0; o >>= 1) {
+            float oq = __shfl_xor_sync(0xffffffffu, bq, o); int omq = __shfl_xor_sync(0xffffffffu, mq, o);
+            float ot = __shfl_xor_sync(0xffffffffu, bt, o); int omt = __shfl_xor_sync(0xffffffffu, mt, o);
+            if (better(oq, omq, bq, mq)) { bq = oq; mq = omq; }
+            if (better(ot, omt, bt, mt)) { bt = ot; mt = omt; }
+        }
+        if (k1 == 0) {
+            const int row = row0 + pr, ref = 4 * q0 + pc;
+            const float sc = 1.0f / (float)N;
+            const float qn = bq * sc, qm = bt * sc;
+            CraCand cd;
+            if (row < nrows && ref < R) {
+                if (qn >= qm) { cd.v = qn; cd.code = ref * 8192 + (mq + 1); }
+                else          { cd.v = qm; cd.code = ref * 8192 + 4096 + (mt + 1); }
+            } else { cd.v = -INFINITY; cd.code = -1; }
+            s_pair[slot] = cd;
+        }
+    }
+    __syncthreads();
+    if (tid < ROWS) {
+        const int row = row0 + tid;
+        if (row < nrows) {
+            CraCand best; best.v = -INFINITY; best.code = -1;
+            for (int n = 0; n < npr; ++n) {
+                const CraCand c = s_pair[tid * RS + n];
+                if (c.code >= 0 && c.v >= best.v) best = c;
+            }
+            cand[(size_t)row * ncta_n + cn] = best;
+        }
+    }
+}
+
+struct Sched { std::vector<int> koff; int nring = -1, maxrin = -1, dev = -1; std::vector<int> len; };
+Sched g_sched;
+
+// Balance the frequencies over the warps (longest-processing-time first) and upload the lists.
+int bind_schedule(const CraRingTab& h, const std::vector<int>& koff, cudaStream_t st)
+{
+    int dev = 0; cudaGetDevice(&dev);
+    std::vector<int> len(h.len, h.len + h.nring);
+    if (g_sched.nring == h.nring && g_sched.maxrin == h.maxrin && g_sched.dev == dev && g_sched.len == len) return 0;
+    const int nk = h.maxrin / 2 + 1;
+    std::vector<std::vector<int>> lists(kWarps);
+    std::vector<int> load(kWarps, 0);
+    int maxc = 0;
+    for (int k = 0; k < nk; ++k) maxc = std::max(maxc, koff[k + 1] - koff[k]);
+    for (int c = maxc; c >= 1; --c)
+        for (int k = 0; k < nk; ++k) {
+            if (koff[k + 1] - koff[k] != c) continue;
+            int w = 0;
+            for (int i = 1; i < kWarps; ++i) if (load[i] < load[w]) w = i;
+            for (int j = 0; j < c; ++j) lists[w].push_back((koff[k] + j) | (k << 13) | ((j == c - 1) ? (1 << 23) : 0));
+            load[w] += c;
+        }
+    static int h_items[kWarps][kMaxItems]; int h_n[kWarps];
+    memset(h_items, 0, sizeof(h_items));
+    for (int w = 0; w < kWarps; ++w) {
+        if ((int)lists[w].size() > kMaxItems || koff[nk] > 8191 || nk > 1024) { cra_set_error("ring table too large for the tensor-core CCF schedule"); return 1; }
+        h_n[w] = (int)lists[w].size();
+        for (size_t i = 0; i < lists[w].size(); ++i) h_items[w][i] = lists[w][i];
+    }
+    CRA_CUDA(cudaStreamSynchronize(st));
+    CRA_CUDA(cudaMemcpyToSymbol(c_items, h_items, sizeof(h_items)));
+    CRA_CUDA(cudaMemcpyToSymbol(c_nitems, h_n, sizeof(h_n)));
+    g_sched.nring = h.nring; g_sched.maxrin = h.maxrin; g_sched.dev = dev; g_sched.len = len;
+    return 0;
+}
+
+template <int LOG2N>
+int launch_t(const unsigned char* spec, int nrows, const unsigned char* refspec, int R, size_t row_bytes,
+             const float2* twid, CraCand* cand, int ntile_n, cudaStream_t st)
+{
+    using S = MShape<LOG2N>;
+    const size_t smem = ((size_t)S::NP * S::PS + S::N) * sizeof(float2);
+    static bool configured = false;
+    if (!configured) {
+        CRA_CUDA(cudaFuncSetAttribute(ccf_mma_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int nquad = (R + 3) / 4;
+    const long ncta_m = (nrows + S::ROWS - 1) / S::ROWS;
+    const long nblk = ncta_m * ntile_n;
+    if (nblk <= 0) return 0;
+    if (nblk > 2147483647L) { cra_set_error("ccf grid too large; lower row_batch"); return 1; }
+    ccf_mma_kernel<LOG2N><<<(unsigned)nblk, kThreads, smem, st>>>(spec, nrows, refspec, R, row_bytes, twid, cand, nquad, ntile_n);
+    CRA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int LOG2N> int num_tiles_t(int R) { const int nq = (R + 3) / 4; return (nq + MShape<LOG2N>::NJ - 1) / MShape<LOG2N>::NJ; }
+
+}  // namespace
+
+// reference tiles (candidates per row) the kernel produces for R references
+int cra_ccf_mma_num_tiles(int R, int log2n)
+{
+    switch (log2n) {
+        case 5: return num_tiles_t<5>(R);   case 6: return num_tiles_t<6>(R);   case 7: return num_tiles_t<7>(R);
+        case 8: return num_tiles_t<8>(R);   case 9: return num_tiles_t<9>(R);   default: return num_tiles_t<10>(R);
+    }
+}
+
+int cra_launch_ccf_mma(const unsigned char* spec, int nrows, const unsigned char* refspec, int R, const CraRingTab& htab,
+                       const CraFragTab& frag, const std::vector<int>& h_koff, const float2* twid, CraCand* cand,
+                       int ntile_n, cudaStream_t st)
+{
+    if (bind_schedule(htab, h_koff, st)) return 1;
+    const size_t rb = cra_frag_row_bytes(frag.nch);
+    switch (htab.log2n) {
+        case 5:  return launch_t<5>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, st);
+        case 6:  return launch_t<6>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, st);
+        case 7:  return launch_t<7>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, st);
+        case 8:  return launch_t<8>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, st);
+        case 9:  return launch_t<9>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, st);
+        case 10: return launch_t<10>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, st);
+        default: cra_set_error("maxrin must be a power of two in [32, 1024]"); return 1;
+    }
+}

@@ -70,6 +70,25 @@ __host__ __device__ __forceinline__ size_t cra_spec_idx(int coff, int half, int 
     return ((size_t)2 * coff + (size_t)((r & 3) >> 1) * (half + 1) + k) * 2 + (r & 1);
 }
 
+// ---- fragment spectrum ("F16" format, CRA_FMT_FRAG) --------------------------------------------
+// Operand layout of the tensor-core contraction (cra_ccf_mma.cu).  For every angular frequency
+// k <= maxrin/2 the rings that reach it (len/2 >= k; K_k of them, longest first: slot s <-> ring
+// nring-1-s) are cut into chunks of 16 slots (zero padded).  One chunk of one row (or reference)
+// is 128 bytes: 4 quads t x [re unit | im unit]; a 16-byte unit holds the 4 slots 16c+4t .. +3 of
+// that part as bf16 hi x4 then bf16 lo x4, value = hi + lo (split-bf16: ~17 significant bits).
+// A thread of mma.sync.m16n8k16 therefore fetches its A (row) fragment with one 256-bit load and
+// its B (reference) fragment with one 128-bit load.  Chunks are stored k-major: chunk index
+// koff[k] + c; a row is nch * 128 bytes.
+#define CRA_FMT_F32  0          // planar-pair float2 layout above (FP32 FMA contraction)
+#define CRA_FMT_FRAG 1          // fragment layout (tensor-core contraction)
+struct CraFragTab {
+    int nk;                      // maxrin/2 + 1
+    int nch;                     // chunks per row
+    const int* koff;             // [nk+1] first chunk of frequency k (device)
+    const int* chunk_k;          // [nch]  k << 4 | c (device)
+};
+__host__ __device__ __forceinline__ size_t cra_frag_row_bytes(int nch) { return (size_t)nch * 128; }
+
 struct CraCand { float v; int code; };   // code = iref*8192 + mirror*4096 + j   (j = 1-based lag index)
 
 // error plumbing -------------------------------------------------------------
@@ -86,21 +105,28 @@ int cra_launch_mask_normalize(float* imgs, int n, int nx, const float* mask, int
 int cra_polar_rows_per_block();
 int cra_launch_polar_rows(const float* images, int nx, const CraRingTab* tab, const CraRingTab& htab,
                           const float4* samp, const float* sampw, const float2* twid_fwd, const CraPolarItems& items,
-                          CraRowMap map, int normalize_ring, float* spec, cudaStream_t st);
+                          CraRowMap map, int normalize_ring, float* spec, int fmt, const CraFragTab& frag, cudaStream_t st);
 int cra_launch_polar_refs(const float* refs, int R, int nx, const CraRingTab* tab, const CraRingTab& htab,
-                          const float4* samp, const float2* twid_fwd, const CraPolarItems& items, float* refspec, cudaStream_t st);
+                          const float4* samp, const float2* twid_fwd, const CraPolarItems& items, float* refspec,
+                          int fmt, const CraFragTab& frag, cudaStream_t st);
 int cra_launch_polar_single(const float* image, int nx, const CraRingTab* tab, const CraRingTab& htab,
                             const float4* samp, const float* sampw, const float2* twid_fwd, const CraPolarItems& items,
-                            float cx, float cy, int normalize_ring, float* spec, cudaStream_t st);
+                            float cx, float cy, int normalize_ring, float* spec, int fmt, const CraFragTab& frag,
+                            cudaStream_t st);
+int cra_launch_ccf_mma(const unsigned char* spec, int nrows, const unsigned char* refspec, int R, const CraRingTab& htab,
+                       const CraFragTab& frag, const std::vector<int>& h_koff, const float2* twid, CraCand* cand,
+                       int ntile_n, cudaStream_t st);
+int cra_ccf_mma_num_tiles(int R, int log2n);
 int cra_launch_ccf(const float* spec, int nrows, const float* refspec, int R, const CraRingTab* tab,
                    const CraRingTab& htab, const float2* twid, CraCand* cand, int ntile_n, cudaStream_t st);
 int cra_ccf_tile_n();
 int cra_launch_ccf_rr(const float* spec, int nrows, const float* refspec, int R, const CraRingTab& htab,
                       const float2* twid, CraCand* cand, int ntile_n, cudaStream_t st, bool* ran);
 int cra_launch_finalize(const float* spec, const float* refspec, int R, const CraRingTab* tab, const CraRingTab& htab,
-                        const CraCand* cand, int ntile_n, CraRowMap map, CraResult* out, cudaStream_t st);
+                        const CraCand* cand, int ntile_n, CraRowMap map, CraResult* out, int fmt, const CraFragTab& frag,
+                        cudaStream_t st);
 int cra_launch_ccf_curves(const float* spec, int row, const float* refspec, int ref, const CraRingTab* tab,
-                          const CraRingTab& htab, float* q, float* t, cudaStream_t st);
+                          const CraRingTab& htab, float* q, float* t, int fmt, const CraFragTab& frag, cudaStream_t st);
 void cra_ccf_twiddles(int log2n, std::vector<float2>& tw);
 int cra_launch_rotsum(const float* images, int nx, int p0, int n, const float4* params, const int* iref,
                       long global_offset, float* sums, float* counts, float* out_images, cudaStream_t st);

@@ -15,8 +15,21 @@
 // with 16/32-byte vector stores.
 #include "cra_common.cuh"
 #include "cra_fft.cuh"
+#include <cuda_bf16.h>
 
 namespace {
+
+// split-bf16 of four values: (hi01, hi23, lo01, lo23), value = hi + lo
+__device__ __forceinline__ uint4 split_bf16x4(float v0, float v1, float v2, float v3)
+{
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(v0, v1), h23 = __floats2bfloat162_rn(v2, v3);
+    const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+    const __nv_bfloat162 l01 = __floats2bfloat162_rn(v0 - f01.x, v1 - f01.y), l23 = __floats2bfloat162_rn(v2 - f23.x, v3 - f23.y);
+    uint4 o;
+    o.x = *reinterpret_cast<const unsigned int*>(&h01); o.y = *reinterpret_cast<const unsigned int*>(&h23);
+    o.z = *reinterpret_cast<const unsigned int*>(&l01); o.w = *reinterpret_cast<const unsigned int*>(&l23);
+    return o;
+}
 
 using crafft::cmul;
 using crafft::fft_reg;
@@ -103,12 +116,13 @@ __device__ __forceinline__ void pass_b(float2* __restrict__ z, int ka)
 struct Chunk { int part, row0, nrow; };
 
 // MODE: 0 = particle rows (optional Normalize_ring), 1 = references (Applyws)
-template <int MODE, int RPB>
+// FMT: CRA_FMT_F32 = planar-pair float2 device spectrum, CRA_FMT_FRAG = split-bf16 fragment layout
+template <int MODE, int RPB, int FMT>
 __global__ void __launch_bounds__(kPolarThreads)
 polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __restrict__ tab,
                  const float4* __restrict__ samp, const float* __restrict__ sampw,
                  const float2* __restrict__ twid, CraPolarItems items, CraRowMap map,
-                 float fix_cx, float fix_cy, int normalize_ring, float* __restrict__ spec)
+                 float fix_cx, float fix_cy, int normalize_ring, float* __restrict__ spec, CraFragTab frag)
 {
     extern __shared__ __align__(16) float smem[];
     const int npix = nx * nx;
@@ -315,6 +329,17 @@ polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __r
                 }
             }
         }
+        if (FMT == CRA_FMT_FRAG) {
+            // back into the ring buffer in place: slot pos(k) <- F_k, pos(n-k) <- F_{n-k}; pos(0) <- (F_0, F_n)
+#pragma unroll
+            for (int r = 0; r < RPB; ++r)
+                if (r < ck.nrow) {
+                    float2* z = reinterpret_cast<float2*>(s_circ + r * lcp) + tab->poff[ring];
+                    if (k == 0) z[pk] = make_float2(fk[r].x, fm[r].x);
+                    else { z[pk] = fk[r]; if (pm != pk) z[pm] = fm[r]; }
+                }
+            continue;
+        }
         const int coff = tab->coff[ring], km = (k == 0) ? n : m;     // n = len/2: the Nyquist slot
         if (vec && RPB == 4) {
             float4* o0 = reinterpret_cast<float4*>(grp) + 2 * coff, *o1 = o0 + (n + 1);
@@ -335,6 +360,41 @@ polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __r
                     grp[cra_spec_idx(coff, n, ck.row0 + r, k)] = fk[r];
                     if (km != k) grp[cra_spec_idx(coff, n, ck.row0 + r, km)] = fm[r];
                 }
+        }
+    }
+    if (FMT == CRA_FMT_FRAG) {
+        // ---- pass D: gather the 4 ring slots of every (chunk, quad) and store the split-bf16 units ----
+        __syncthreads();
+        const int nch = frag.nch, nring = tab->nring;
+        const int per_row = nch * 4;
+        unsigned char* const base = reinterpret_cast<unsigned char*>(spec) + (size_t)ck.row0 * nch * 128;
+        for (int it = tid; it < per_row * ck.nrow; it += kPolarThreads) {
+            const int r = it / per_row, u = it - r * per_row;
+            const int gc = u >> 2, t = u & 3;
+            const int kc = __ldg(frag.chunk_k + gc);
+            const int k = kc >> 4, s0 = 16 * (kc & 15) + 4 * t;
+            const float2* zrow = reinterpret_cast<const float2*>(s_circ + r * lcp);
+            float re[4], im[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ring = nring - 1 - (s0 + j);
+                float2 v = make_float2(0.f, 0.f);
+                if (ring >= 0) {
+                    const int4 rp = s_ring[ring];
+                    const int n = rp.z * 2;                      // len/2
+                    if (k <= n) {
+                        const float2* z = zrow + rp.x;
+                        const int la = (31 - __clz(n)) - rp.y;   // log2 NA
+                        if (k == 0) v = make_float2(z[0].x, 0.f);
+                        else if (k == n) v = make_float2(z[0].y, 0.f);
+                        else v = z[(k & ((1 << la) - 1)) * ((1 << rp.y) + 1) + (k >> la)];
+                    }
+                }
+                re[j] = v.x; im[j] = v.y;
+            }
+            uint4* o = reinterpret_cast<uint4*>(base + (size_t)r * nch * 128 + (size_t)gc * 128 + t * 32);
+            o[0] = split_bf16x4(re[0], re[1], re[2], re[3]);
+            o[1] = split_bf16x4(im[0], im[1], im[2], im[3]);
         }
     }
 }
@@ -376,22 +436,36 @@ size_t polar_smem_bytes(int nx, const CraRingTab& h)
     return (npix + RPB * lc) * sizeof(float) + (size_t)h.maxrin * sizeof(float2);
 }
 
-template <int MODE, int RPB>
-int launch_polar(const float* images, int nx, const CraRingTab* tab, const CraRingTab& htab,
-                 const float4* samp, const float* sampw, const float2* twid, const CraPolarItems& items,
-                 CraRowMap map, float cx, float cy, int normalize_ring, float* spec, int nblocks, cudaStream_t st)
+template <int MODE, int RPB, int FMT>
+int launch_polar_f(const float* images, int nx, const CraRingTab* tab, const CraRingTab& htab,
+                   const float4* samp, const float* sampw, const float2* twid, const CraPolarItems& items,
+                   CraRowMap map, float cx, float cy, int normalize_ring, float* spec, const CraFragTab& frag,
+                   int nblocks, cudaStream_t st)
 {
     if (nblocks <= 0) return 0;
     size_t smem = polar_smem_bytes<RPB>(nx, htab);
     static size_t configured = 0;
     if (smem > configured) {
-        CRA_CUDA(cudaFuncSetAttribute(polar_fft_kernel<MODE, RPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CRA_CUDA(cudaFuncSetAttribute(polar_fft_kernel<MODE, RPB, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    polar_fft_kernel<MODE, RPB><<<nblocks, kPolarThreads, smem, st>>>(images, nx, tab, samp, sampw, twid, items, map,
-                                                                     cx, cy, normalize_ring, spec);
+    polar_fft_kernel<MODE, RPB, FMT><<<nblocks, kPolarThreads, smem, st>>>(images, nx, tab, samp, sampw, twid, items, map,
+                                                                          cx, cy, normalize_ring, spec, frag);
     CRA_CUDA(cudaGetLastError());
     return 0;
+}
+
+template <int MODE, int RPB>
+int launch_polar(const float* images, int nx, const CraRingTab* tab, const CraRingTab& htab,
+                 const float4* samp, const float* sampw, const float2* twid, const CraPolarItems& items,
+                 CraRowMap map, float cx, float cy, int normalize_ring, float* spec, int fmt, const CraFragTab& frag,
+                 int nblocks, cudaStream_t st)
+{
+    if (fmt == CRA_FMT_FRAG)
+        return launch_polar_f<MODE, RPB, CRA_FMT_FRAG>(images, nx, tab, htab, samp, sampw, twid, items, map, cx, cy,
+                                                       normalize_ring, spec, frag, nblocks, st);
+    return launch_polar_f<MODE, RPB, CRA_FMT_F32>(images, nx, tab, htab, samp, sampw, twid, items, map, cx, cy,
+                                                  normalize_ring, spec, frag, nblocks, st);
 }
 
 }  // namespace
@@ -408,24 +482,26 @@ int cra_launch_mask_normalize(float* imgs, int n, int nx, const float* mask, int
 
 int cra_launch_polar_rows(const float* images, int nx, const CraRingTab* tab, const CraRingTab& htab,
                           const float4* samp, const float* sampw, const float2* twid, const CraPolarItems& items,
-                          CraRowMap map, int normalize_ring, float* spec, cudaStream_t st)
+                          CraRowMap map, int normalize_ring, float* spec, int fmt, const CraFragTab& frag, cudaStream_t st)
 {
     return launch_polar<0, CRA_POLAR_RPB>(images, nx, tab, htab, samp, sampw, twid, items, map, 0.f, 0.f,
-                                          normalize_ring, spec, map.nchunks, st);
+                                          normalize_ring, spec, fmt, frag, map.nchunks, st);
 }
 
 int cra_launch_polar_refs(const float* refs, int R, int nx, const CraRingTab* tab, const CraRingTab& htab,
-                          const float4* samp, const float2* twid, const CraPolarItems& items, float* refspec, cudaStream_t st)
+                          const float4* samp, const float2* twid, const CraPolarItems& items, float* refspec,
+                          int fmt, const CraFragTab& frag, cudaStream_t st)
 {
     CraRowMap map{};
-    return launch_polar<1, 1>(refs, nx, tab, htab, samp, nullptr, twid, items, map, 0.f, 0.f, 0, refspec, R, st);
+    return launch_polar<1, 1>(refs, nx, tab, htab, samp, nullptr, twid, items, map, 0.f, 0.f, 0, refspec, fmt, frag, R, st);
 }
 
 int cra_launch_polar_single(const float* image, int nx, const CraRingTab* tab, const CraRingTab& htab,
                             const float4* samp, const float* sampw, const float2* twid, const CraPolarItems& items,
-                            float cx, float cy, int normalize_ring, float* spec, cudaStream_t st)
+                            float cx, float cy, int normalize_ring, float* spec, int fmt, const CraFragTab& frag,
+                            cudaStream_t st)
 {
     CraRowMap map{};
     map.row_start = nullptr; map.p0 = 0;
-    return launch_polar<0, 1>(image, nx, tab, htab, samp, sampw, twid, items, map, cx, cy, normalize_ring, spec, 1, st);
+    return launch_polar<0, 1>(image, nx, tab, htab, samp, sampw, twid, items, map, cx, cy, normalize_ring, spec, fmt, frag, 1, st);
 }
