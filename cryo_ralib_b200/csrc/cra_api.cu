@@ -52,6 +52,12 @@ struct CraCtx {
     std::vector<int> h_koff, h_chunk_k;
     int* d_fragtab = nullptr;
     size_t row_bytes = 0;        // device spectrum bytes of one row in the active format
+    CraGroupPlan plan{};         // grouped row kernel (cra_polar_grp.cu); plan.rmax == 0: unavailable
+    void* d_plan = nullptr;
+    bool use_group = true;       // CRA_POLAR=general forces the general kernel
+    int last_rows = 0, last_group = 0;   // rows / kernel of the last batch (cra_batch_row_spectrum)
+    float2* d_norm = nullptr;    // [row_batch] deferred Normalize_ring (avg, 1/sigma), cra_common.cuh
+    float* d_tref = nullptr;     // [max_refs]  sum_rings len * weighted reference DC
 };
 
 namespace {
@@ -72,6 +78,77 @@ std::vector<int> numrinit(int ir, int ou, int rs)
         lcirc += ip;
     }
     return numr;
+}
+
+// Phases of the grouped row kernel: consecutive 4-ring units (longest rings first) packed while
+// their padded ring buffers fit the footprint of the largest unit.
+int build_group_plan(CraCtx* c)
+{
+    const CraRingTab& t = c->htab;
+    const int nring = t.nring, nunit = (nring + 3) / 4;
+    auto padded = [&](int ring) { const int n = t.len[ring] >> 1, lg = ilog2_floor(n), NA = 1 << (lg / 2), NB = n / NA; return NA * (NB + 1); };
+    std::vector<int> usize(nunit, 0), unk(nunit, 0);
+    for (int u = 0; u < nunit; ++u) {
+        for (int j = 0; j < 4; ++j) { const int ring = nring - 1 - (4 * u + j); if (ring >= 0) usize[u] += padded(ring); }
+        unk[u] = (t.len[nring - 1 - 4 * u] >> 1) + 1;
+    }
+    const int cap = *std::max_element(usize.begin(), usize.end());          // float2 per row
+    // item list positions: lists run over rings nring-1 .. 0 (build_tables), the sample table over rings 0 .. nring-1
+    std::vector<int> aoff(nring + 1, 0), boff(nring + 1, 0), coff(nring + 1, 0), qoff(nring + 1, 0);
+    for (int s = 0; s < nring; ++s) {
+        const int ring = nring - 1 - s, n = t.len[ring] >> 1, lg = ilog2_floor(n), NA = 1 << (lg / 2), NB = n / NA;
+        aoff[s + 1] = aoff[s] + NB; boff[s + 1] = boff[s] + NA; coff[s + 1] = coff[s] + n / 2 + 1;
+    }
+    for (int i = 0; i < nring; ++i) qoff[i + 1] = qoff[i] + t.len[i] / 4;
+    std::vector<CraPhase> phases;
+    std::vector<int> ppoff(nring, 0);
+    auto magic = [](int n) { return n > 0 ? (1 << 24) / n + 1 : 1; };
+    for (int u = 0; u < nunit;) {
+        int u1 = u, used = 0;
+        while (u1 < nunit && used + usize[u1] <= cap) { used += usize[u1]; ++u1; }
+        const int s0 = 4 * u, s1 = std::min(4 * u1, nring);                 // slots [s0, s1)
+        int acc = 0;
+        for (int s = s0; s < s1; ++s) { const int ring = nring - 1 - s; ppoff[ring] = acc; acc += padded(ring); }
+        CraPhase p{};
+        p.u0 = u; p.u1 = u1;
+        p.a0 = aoff[s0]; p.a1 = aoff[s1]; p.b0 = boff[s0]; p.b1 = boff[s1]; p.c0 = coff[s0]; p.c1 = coff[s1];
+        p.q0 = qoff[nring - s1]; p.q1 = qoff[nring - s0];                   // rings nring-s1 .. nring-1-s0
+        for (int uu = u; uu < u1; ++uu) p.upr += unk[uu];
+        p.magicA = magic(p.a1 - p.a0); p.magicB = magic(p.b1 - p.b0); p.magicC = magic(p.c1 - p.c0); p.magicD = magic(p.upr);
+        // fastdiv is exact while n * n * CRA_GRP_RMAX < 2^24
+        const long worst = std::max({p.a1 - p.a0, p.b1 - p.b0, p.c1 - p.c0, p.upr});
+        if (worst * worst * CRA_GRP_RMAX >= (1L << 24)) { c->plan.rmax = 0; return 0; }
+        phases.push_back(p);
+        u = u1;
+    }
+    c->plan.stride = (2 * cap + 3) & ~3;
+    c->plan.nphase = (int)phases.size();
+    // rows per CTA: as many as fit two CTAs per SM (fewer image reloads, shared index math), else one CTA
+    int dev = 0; cudaGetDevice(&dev);
+    int smem_sm = 0, smem_blk = 0;
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    auto fits = [&](int rmax, int ncta) {
+        CraGroupPlan q = c->plan; q.rmax = rmax;
+        const size_t need = cra_polar_group_smem(c->nx, t.maxrin, q) + 5400;   // + static shared + 1 KB reserved per CTA
+        return need <= (size_t)smem_blk && need * ncta <= (size_t)smem_sm;
+    };
+    int rmax = 0;
+    for (int r = CRA_GRP_RMAX; r >= 7 && !rmax; --r) if (fits(r, 2)) rmax = r;
+    for (int r = CRA_GRP_RMAX; r >= 1 && !rmax; --r) if (fits(r, 1)) rmax = r;
+    c->plan.rmax = rmax;
+    if (!rmax) return 0;
+    const size_t bytes = sizeof(CraPhase) * phases.size() + sizeof(int) * (nring + nunit);
+    std::vector<char> blob(bytes);
+    memcpy(blob.data(), phases.data(), sizeof(CraPhase) * phases.size());
+    memcpy(blob.data() + sizeof(CraPhase) * phases.size(), ppoff.data(), sizeof(int) * nring);
+    memcpy(blob.data() + sizeof(CraPhase) * phases.size() + sizeof(int) * nring, unk.data(), sizeof(int) * nunit);
+    CRA_CUDA(cudaMalloc(&c->d_plan, bytes));
+    CRA_CUDA(cudaMemcpy(c->d_plan, blob.data(), bytes, cudaMemcpyHostToDevice));
+    c->plan.phases = reinterpret_cast<const CraPhase*>(c->d_plan);
+    c->plan.ppoff = reinterpret_cast<const int*>(reinterpret_cast<const char*>(c->d_plan) + sizeof(CraPhase) * phases.size());
+    c->plan.unit_nk = c->plan.ppoff + nring;
+    return 0;
 }
 
 int build_tables(CraCtx* c)
@@ -179,7 +256,7 @@ int build_tables(CraCtx* c)
     CRA_CUDA(cudaMemcpy(c->d_twi, twi.data(), sizeof(float2) * twi.size(), cudaMemcpyHostToDevice));
     CRA_CUDA(cudaMalloc(&c->d_mask, sizeof(float) * c->npix));
     CRA_CUDA(cudaMemcpy(c->d_mask, mask.data(), sizeof(float) * c->npix, cudaMemcpyHostToDevice));
-    return 0;
+    return build_group_plan(c);
 }
 
 int window_of(const CraSearch& s, float step, int4* w)
@@ -255,6 +332,9 @@ extern "C" int cra_create(const CraConfig* cfg, int device, CraCtx** out)
         const char* e = getenv("CRA_CCF");
         if (e && strcmp(e, "simt") == 0) c->fmt = CRA_FMT_F32;
         else if (e && strcmp(e, "mma") != 0 && e[0]) { cra_set_error("CRA_CCF must be 'mma' or 'simt'"); cra_destroy(c); return 1; }
+        const char* pk = getenv("CRA_POLAR");
+        if (pk && strcmp(pk, "general") == 0) c->use_group = false;
+        else if (pk && strcmp(pk, "group") != 0 && pk[0]) { cra_set_error("CRA_POLAR must be 'group' or 'general'"); cra_destroy(c); return 1; }
     }
     if (build_tables(c)) { cra_destroy(c); return 1; }
     const int k = (int)(cfg->max_range / cfg->step);
@@ -280,6 +360,9 @@ extern "C" int cra_create(const CraConfig* cfg, int device, CraCtx** out)
     if (e == cudaSuccess) e = cudaMemset(c->d_spec, 0, row_groups * 4 * row_bytes);
     if (e == cudaSuccess) e = cudaMallocHost(&c->h_group, 4 * row_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_cand, (size_t)c->row_batch * c->ntile_n_max * sizeof(CraCand));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_norm, ((size_t)c->row_batch + 4) * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_tref, ref_groups * 4 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(c->d_tref, 0, ref_groups * 4 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_sums, nsum * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_curves, (size_t)2 * c->htab.maxrin * sizeof(float));
     if (e == cudaSuccess) e = cudaMemset(c->d_sums, 0, nsum * sizeof(float));
@@ -294,7 +377,7 @@ extern "C" int cra_destroy(CraCtx* c)
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
     for (auto& e : c->ev) cudaEventDestroy(e);
-    cudaFree(c->d_items); cudaFree(c->d_fragtab);
+    cudaFree(c->d_items); cudaFree(c->d_fragtab); cudaFree(c->d_norm); cudaFree(c->d_tref); cudaFree(c->d_plan);
     cudaFree(c->d_tab); cudaFree(c->d_samp); cudaFree(c->d_sampw); cudaFree(c->d_twf); cudaFree(c->d_twi);
     cudaFree(c->d_mask); cudaFree(c->d_images); cudaFree(c->d_refs); cudaFree(c->d_refspec);
     cudaFree(c->d_spec); cudaFree(c->d_cand); cudaFree(c->d_sums); cudaFree(c->d_meta); cudaFree(c->d_res);
@@ -342,7 +425,7 @@ extern "C" int cra_set_refs(CraCtx* c, const float* h, int R, int normalize_mask
     CRA_CUDA(cudaMemcpyAsync(c->d_refs, h, (size_t)R * c->npix * sizeof(float), cudaMemcpyHostToDevice, c->st));
     if (normalize_mask && cra_launch_mask_normalize(c->d_refs, R, c->nx, c->d_mask, 1, c->st)) return 1;
     if (cra_launch_polar_refs(c->d_refs, R, c->nx, c->d_tab, c->htab, c->d_samp, c->d_twf, c->items, c->d_refspec,
-                              c->fmt, c->frag, c->st)) return 1;
+                              c->fmt, c->frag, c->d_tref, c->st)) return 1;
     CRA_CUDA(cudaStreamSynchronize(c->st));
     c->R = R;
     return 0;
@@ -382,18 +465,32 @@ extern "C" int cra_align(CraCtx* c, int start, int stop, const CraSearch* search
     int* h_cs = h_rs + n + nb;
     const int rpb = cra_polar_rows_per_block();
     std::vector<int> bchunks(nb);
+    std::vector<char> bgroup(nb, 0);
     memcpy(h_search, search, (size_t)n * sizeof(CraSearch));
     long total_rows = 0;
+    // the grouped row kernel needs a whole-pixel step and every 3x3 tap neighbourhood inside the frame
+    const bool group_cfg = c->fmt == CRA_FMT_FRAG && c->use_group && c->plan.rmax > 0 && step == floorf(step) && step < 1024.f;
+    const float rmaxf = (float)c->htab.rad[c->htab.nring - 1], lo_ok = 2.0f + rmaxf, hi_ok = (float)(c->nx - 1) - rmaxf;
     for (size_t bi = 0; bi < nb; ++bi) {
         int* rs = h_rs + bfirst[bi] + bi;
         int* cs = h_cs + bfirst[bi] + bi;
+        bool grp = group_cfg;
+        for (int q = 0; q < bcount[bi] && grp; ++q) {
+            const int p = bfirst[bi] + q;
+            int4 w; window_of(search[p], step, &w);
+            const CraSearch& sp = search[p];
+            grp = (sp.cx - w.x * step >= lo_ok) && (sp.cx + w.y * step <= hi_ok) &&
+                  (sp.cy - w.z * step >= lo_ok) && (sp.cy + w.w * step <= hi_ok);
+        }
+        bgroup[bi] = grp;
         int acc = 0, cacc = 0;
         for (int q = 0; q < bcount[bi]; ++q) {
             const int p = bfirst[bi] + q;
             window_of(search[p], step, &h_win[p]);
             rs[q] = acc; cs[q] = cacc;
             const int rows = (h_win[p].x + h_win[p].y + 1) * (h_win[p].z + h_win[p].w + 1);
-            cacc += (acc + rows - 1) / rpb - acc / rpb + 1;      // aligned sub-groups this particle touches
+            if (grp) cacc += (rows + c->plan.rmax - 1) / c->plan.rmax;   // balanced row blocks of <= rmax rows
+            else cacc += (acc + rows - 1) / rpb - acc / rpb + 1;          // aligned sub-groups this particle touches
             acc += rows;
         }
         rs[bcount[bi]] = acc; cs[bcount[bi]] = cacc;
@@ -422,19 +519,23 @@ extern "C" int cra_align(CraCtx* c, int start, int stop, const CraSearch* search
         map.win = d_win + bfirst[bi];
         map.np = bcount[bi]; map.nrows = brows[bi]; map.p0 = start + bfirst[bi]; map.step = step;
         if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 0], c->st));
-        if (cra_launch_polar_rows(c->d_images, c->nx, c->d_tab, c->htab, c->d_samp, c->d_sampw, c->d_twf, c->items, map,
-                                  c->cfg.normalize_ring, c->d_spec, c->fmt, c->frag, c->st)) return 1;
+        if (bgroup[bi]) {
+            if (cra_launch_polar_group(c->d_images, c->nx, c->d_tab, c->htab, c->d_samp, c->d_twf, c->items, c->plan, map,
+                                       c->cfg.normalize_ring, c->d_spec, c->frag, c->d_norm, c->st)) return 1;
+        } else if (cra_launch_polar_rows(c->d_images, c->nx, c->d_tab, c->htab, c->d_samp, c->d_sampw, c->d_twf, c->items, map,
+                                         c->cfg.normalize_ring, c->d_spec, c->fmt, c->frag, c->d_norm, c->st)) return 1;
         if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 1], c->st));
         if (c->fmt == CRA_FMT_FRAG) {
             if (cra_launch_ccf_mma(reinterpret_cast<const unsigned char*>(c->d_spec), map.nrows,
                                    reinterpret_cast<const unsigned char*>(c->d_refspec), c->R, c->htab, c->frag, c->h_koff,
-                                   c->d_twi, c->d_cand, ntile_n, c->st)) return 1;
+                                   c->d_twi, c->d_cand, ntile_n, c->d_norm, c->d_tref, c->st)) return 1;
         } else if (cra_launch_ccf(c->d_spec, map.nrows, c->d_refspec, c->R, c->d_tab, c->htab, c->d_twi, c->d_cand, ntile_n, c->st)) return 1;
         if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 2], c->st));
         if (cra_launch_finalize(c->d_spec, c->d_refspec, c->R, c->d_tab, c->htab, c->d_cand, ntile_n, map,
                                 c->d_res + bfirst[bi], c->fmt, c->frag, c->st)) return 1;
         if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 3], c->st));
         launches += 3;
+        c->last_rows = map.nrows; c->last_group = bgroup[bi];
     }
     CRA_CUDA(cudaMemcpyAsync(c->h_res, c->d_res, (size_t)n * sizeof(CraResult), cudaMemcpyDeviceToHost, c->st));
     CRA_CUDA(cudaStreamSynchronize(c->st));
@@ -557,7 +658,7 @@ extern "C" int cra_transform(CraCtx* c, int start, int stop, const float* params
 
 // device spectrum staged in h_group -> SPIDER packed layout.  F32: row `lane4` of the 4-row group;
 // FRAG: the staged row itself (value = bf16 hi + bf16 lo).
-static void unpack_spectrum(const CraCtx* c, int lane4, float* out)
+static void unpack_spectrum(const CraCtx* c, int lane4, float* out, bool row_layout)
 {
     const CraRingTab& t = c->htab;
     const unsigned char* fb = reinterpret_cast<const unsigned char*>(c->h_group);
@@ -570,8 +671,14 @@ static void unpack_spectrum(const CraCtx* c, int lane4, float* out)
                 const int s = t.nring - 1 - i, gc = c->h_koff[k] + (s >> 4), tq = (s & 15) >> 2, j = s & 3;
                 const unsigned short* u = reinterpret_cast<const unsigned short*>(fb + (size_t)gc * 128 + tq * 32);
                 auto bf = [](unsigned short h) { unsigned int b = (unsigned int)h << 16; float f; memcpy(&f, &b, 4); return f; };
-                v.x = bf(u[j]) + bf(u[4 + j]);
-                v.y = bf(u[8 + j]) + bf(u[12 + j]);
+                if (row_layout) {     // hi{re01, im01, re23, im23}, lo{same}
+                    const int w = 4 * (j >> 1) + (j & 1);
+                    v.x = bf(u[w]) + bf(u[8 + w]);
+                    v.y = bf(u[2 + w]) + bf(u[10 + w]);
+                } else {              // [re unit | im unit], unit = hi x4, lo x4
+                    v.x = bf(u[j]) + bf(u[4 + j]);
+                    v.y = bf(u[8 + j]) + bf(u[12 + j]);
+                }
             } else v = c->h_group[cra_spec_idx(t.coff[i], half, lane4, k)];
             if (k == 0) o[0] = v.x;
             else if (k == half) o[1] = v.x;
@@ -585,11 +692,30 @@ extern "C" int cra_polar_spectrum(CraCtx* c, int particle, float cx, float cy, f
     Bind b(c); if (b.ok()) return 1;
     if (particle < 0 || particle >= c->cfg.max_particles) { cra_set_error("bad particle index"); return 1; }
     if (cra_launch_polar_single(c->d_images + (size_t)particle * c->npix, c->nx, c->d_tab, c->htab, c->d_samp, c->d_sampw,
-                                c->d_twf, c->items, cx, cy, c->cfg.normalize_ring, c->d_spec, c->fmt, c->frag, c->st)) return 1;
+                                c->d_twf, c->items, cx, cy, c->cfg.normalize_ring, c->d_spec, c->fmt, c->frag, c->d_norm, c->st)) return 1;
     const size_t bytes = (c->fmt == CRA_FMT_FRAG) ? c->row_bytes : 4 * c->row_bytes;
     CRA_CUDA(cudaMemcpyAsync(c->h_group, c->d_spec, bytes, cudaMemcpyDeviceToHost, c->st));
     CRA_CUDA(cudaStreamSynchronize(c->st));
-    unpack_spectrum(c, 0, host_out);
+    unpack_spectrum(c, 0, host_out, true);
+    return 0;
+}
+
+extern "C" int cra_batch_row_spectrum(CraCtx* c, int row, float* host_out, int* which_kernel)
+{
+    Bind b(c); if (b.ok()) return 1;
+    if (c->fmt != CRA_FMT_FRAG) { cra_set_error("cra_batch_row_spectrum needs the fragment format"); return 1; }
+    if (row < 0 || row >= c->last_rows) { cra_set_error("row outside the last batch"); return 1; }
+    float2 nm;
+    CRA_CUDA(cudaMemcpyAsync(c->h_group, reinterpret_cast<const unsigned char*>(c->d_spec) + (size_t)row * c->row_bytes,
+                             c->row_bytes, cudaMemcpyDeviceToHost, c->st));
+    CRA_CUDA(cudaMemcpyAsync(&nm, c->d_norm + row, sizeof(float2), cudaMemcpyDeviceToHost, c->st));
+    CRA_CUDA(cudaStreamSynchronize(c->st));
+    unpack_spectrum(c, 0, host_out, true);
+    // deferred Normalize_ring: DC bin of every ring -= avg * len, everything * 1/sigma
+    const CraRingTab& t = c->htab;
+    for (int i = 0; i < t.nring; ++i) host_out[t.off[i]] -= nm.x * (float)t.len[i];
+    for (int i = 0; i < t.lcirc; ++i) host_out[i] *= nm.y;
+    if (which_kernel) *which_kernel = c->last_group;
     return 0;
 }
 
@@ -603,7 +729,7 @@ extern "C" int cra_ref_spectrum(CraCtx* c, int iref, float* host_out)
     else
         CRA_CUDA(cudaMemcpyAsync(c->h_group, src + (size_t)(iref >> 2) * 4 * c->row_bytes, 4 * c->row_bytes, cudaMemcpyDeviceToHost, c->st));
     CRA_CUDA(cudaStreamSynchronize(c->st));
-    unpack_spectrum(c, iref & 3, host_out);
+    unpack_spectrum(c, iref & 3, host_out, false);
     return 0;
 }
 
@@ -612,7 +738,7 @@ extern "C" int cra_ccf_curves(CraCtx* c, int particle, float cx, float cy, int i
     Bind b(c); if (b.ok()) return 1;
     if (particle < 0 || particle >= c->cfg.max_particles || iref < 0 || iref >= c->R) { cra_set_error("bad index"); return 1; }
     if (cra_launch_polar_single(c->d_images + (size_t)particle * c->npix, c->nx, c->d_tab, c->htab, c->d_samp, c->d_sampw,
-                                c->d_twf, c->items, cx, cy, c->cfg.normalize_ring, c->d_spec, c->fmt, c->frag, c->st)) return 1;
+                                c->d_twf, c->items, cx, cy, c->cfg.normalize_ring, c->d_spec, c->fmt, c->frag, c->d_norm, c->st)) return 1;
     if (cra_launch_ccf_curves(c->d_spec, 0, c->d_refspec, iref, c->d_tab, c->htab,
                               c->d_curves, c->d_curves + c->htab.maxrin, c->fmt, c->frag, c->st)) return 1;
     CRA_CUDA(cudaMemcpyAsync(q_out, c->d_curves, c->htab.maxrin * sizeof(float), cudaMemcpyDeviceToHost, c->st));

@@ -11,8 +11,8 @@
 // K <= 36 are far too small for tcgen05 (M >= 64 per instruction and the 2 KB of q/t spectrum per
 // pair must stay on chip for the inverse FFT, which caps a tile at ~100 pairs per SM), so they run as
 // warp-level mma.sync.m16n8k16 (bf16, fp32 accumulate) with operands straight from L2 in
-// fragment order (cra_common.cuh, CRA_FMT_FRAG): one 256-bit load is a thread's A fragment, one
-// 128-bit load its B fragment.  FP32 accuracy comes from the split a = a_hi + a_lo:
+// fragment order (cra_common.cuh, CRA_FMT_FRAG): one 256-bit load is a thread's A fragment (hi
+// registers then lo registers, already in mma operand order), one 128-bit load its B fragment.  FP32 accuracy comes from the split a = a_hi + a_lo:
 // a.b ~= a_hi b_hi + a_hi b_lo + a_lo b_hi (3 MMAs; the dropped a_lo b_lo term is 2^-18 relative).
 //
 // One CTA = 8 rows (particle x shift) x up to 4*NJ references; 16 warps share the frequencies
@@ -83,7 +83,7 @@ template <int LOG2N>
 __global__ void __launch_bounds__(kThreads, 1)
 ccf_mma_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned char* __restrict__ refspec, int R,
                size_t row_bytes, const float2* __restrict__ twid, CraCand* __restrict__ cand,
-               int nquad, int ncta_n)
+               int nquad, int ncta_n, const float2* __restrict__ norm, const float* __restrict__ tref, int exp_flags)
 {
     using S = MShape<LOG2N>;
     constexpr int N = S::N, N1 = S::N1, N2 = S::N2, PS = S::PS, NJ = S::NJ, RS = S::RS, ROWS = S::ROWS, NP = S::NP;
@@ -103,6 +103,9 @@ ccf_mma_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned
     for (int i = tid; i < N; i += kThreads) s_tw[i] = twid[i];
 
     // ---- contraction: this warp's frequencies, chunk by chunk ---------------------------------
+    if (!(exp_flags & 8))
+    // All NJ quads are always multiplied (a tile with fewer live quads re-reads its quad 0; the
+    // dead pair slots are skipped by the FFT passes below): no predication around the MMAs.
     {
         int rrow = row0 + (ROWS == 8 ? g : (g & 3));
         if (rrow >= nrows) rrow = nrows - 1;
@@ -124,16 +127,15 @@ ccf_mma_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned
 
 #define CRA_LOAD_OPS(O, item)                                                            \
         { const size_t off_ = (size_t)((item) & 8191) * 128;                             \
-          O.a = ldg256(pa + off_);                                                       \
-          _Pragma("unroll") for (int j_ = 0; j_ < NJ; ++j_)                              \
-              if (j_ < nj) O.b[j_] = __ldg(reinterpret_cast<const uint4*>(pb[j_] + off_)); }
+          if (!(exp_ & 2)) O.a = ldg256(pa + off_);                                      \
+          if (!(exp_ & 1)) { _Pragma("unroll") for (int j_ = 0; j_ < NJ; ++j_)           \
+              O.b[j_] = __ldg(reinterpret_cast<const uint4*>(pb[j_] + off_)); } }
 #define CRA_COMPUTE(O, item)                                                             \
-        { _Pragma("unroll") for (int j_ = 0; j_ < NJ; ++j_)                              \
-              if (j_ < nj) {                                                             \
-                  mma_bf16(acc_l[j_], O.a.w[0], O.a.w[4], O.a.w[1], O.a.w[5], O.b[j_].z, O.b[j_].w);   /* a_hi b_lo */ \
-                  mma_bf16(acc_l[j_], O.a.w[2], O.a.w[6], O.a.w[3], O.a.w[7], O.b[j_].x, O.b[j_].y);   /* a_lo b_hi */ \
-                  mma_bf16(acc_h[j_], O.a.w[0], O.a.w[4], O.a.w[1], O.a.w[5], O.b[j_].x, O.b[j_].y);   /* a_hi b_hi */ \
-              }                                                                          \
+        { _Pragma("unroll") for (int j_ = 0; j_ < NJ; ++j_) {                            \
+              mma_bf16(acc_l[j_], O.a.w[0], O.a.w[1], O.a.w[2], O.a.w[3], O.b[j_].z, O.b[j_].w);   /* a_hi b_lo */ \
+              mma_bf16(acc_l[j_], O.a.w[4], O.a.w[5], O.a.w[6], O.a.w[7], O.b[j_].x, O.b[j_].y);   /* a_lo b_hi */ \
+              mma_bf16(acc_h[j_], O.a.w[0], O.a.w[1], O.a.w[2], O.a.w[3], O.b[j_].x, O.b[j_].y);   /* a_hi b_hi */ \
+          }                                                                              \
           if ((item) >> 23) flush_freq(((item) >> 13) & 1023); }
 
         auto flush_freq = [&](int k) {
@@ -141,41 +143,55 @@ ccf_mma_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned
             const int i0 = (k >> S::L2) * (N2 + 1) + (k & (N2 - 1));
             const int i1 = (kk >> S::L2) * (N2 + 1) + (kk & (N2 - 1));
             const bool wr = (ROWS == 8) || (g < 4);
+            const bool two = (k != 0 && k != N / 2);
+            float2* w = s_w + (g * RS + t) * PS;
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
-                if (j < nj) {
-                    // c0 = A (re.re), c1 = D (row re . ref im), c2 = C (row im . ref re), c3 = B (im.im)
-                    const float A = acc_h[j][0] + acc_l[j][0], D = acc_h[j][1] + acc_l[j][1];
-                    const float C = acc_h[j][2] + acc_l[j][2], B = acc_h[j][3] + acc_l[j][3];
-                    // s = (A+B, A-B), tv = (C+D, D-C);  W[k] = s + tv,  W[N-k] = s - tv
-                    const float sx = A + B, sy = A - B, tx = C + D, ty = D - C;
-                    if (wr) {
-                        float2* w = s_w + (g * RS + 4 * j + t) * PS;
-                        w[i0] = make_float2(sx + tx, sy + ty);
-                        if (k != 0 && k != N / 2) w[i1] = make_float2(sx - tx, sy - ty);
-                    }
+                // c0 = A (re.re), c1 = D (row re . ref im), c2 = C (row im . ref re), c3 = B (im.im)
+                const float A = acc_h[j][0] + acc_l[j][0], D = acc_h[j][1] + acc_l[j][1];
+                const float C = acc_h[j][2] + acc_l[j][2], B = acc_h[j][3] + acc_l[j][3];
+                // s = (A+B, A-B), tv = (C+D, D-C);  W[k] = s + tv,  W[N-k] = s - tv
+                const float sx = A + B, sy = A - B, tx = C + D, ty = D - C;
+                if (wr) {
+                    w[4 * j * PS + i0] = make_float2(sx + tx, sy + ty);
+                    if (two) w[4 * j * PS + i1] = make_float2(sx - tx, sy - ty);
                 }
 #pragma unroll
                 for (int e = 0; e < 4; ++e) { acc_h[j][e] = 0.f; acc_l[j][e] = 0.f; }
             }
         };
 
-        Operands<NJ> o0, o1;
+        // three operand sets rotate: two chunk loads are always in flight behind the one being multiplied
+        Operands<NJ> o0, o1, o2;
+        const int exp_ = exp_flags;
+        if (exp_) {   // timing experiments only (CRA_EXP): operands preloaded once, then partly reused
+            const int e_ = 0;
+            o0.a = ldg256(pa); o1.a = o0.a; o2.a = o0.a;
+            _Pragma("unroll") for (int j_ = 0; j_ < NJ; ++j_) { o0.b[j_] = __ldg(reinterpret_cast<const uint4*>(pb[j_])); o1.b[j_] = o0.b[j_]; o2.b[j_] = o0.b[j_]; }
+            (void)e_;
+        }
         if (nit > 0) CRA_LOAD_OPS(o0, items[0]);
-        for (int i = 0; i < nit; i += 2) {
+        if (nit > 1) CRA_LOAD_OPS(o1, items[1]);
+        for (int i = 0; i < nit; i += 3) {
             const int e0 = items[i];
-            const bool h1 = i + 1 < nit;
-            const int e1 = h1 ? items[i + 1] : 0;
-            if (h1) CRA_LOAD_OPS(o1, e1);
+            if (i + 2 < nit) CRA_LOAD_OPS(o2, items[i + 2]);
             CRA_COMPUTE(o0, e0);
-            if (!h1) break;
-            if (i + 2 < nit) CRA_LOAD_OPS(o0, items[i + 2]);
+            if (i + 1 >= nit) break;
+            const int e1 = items[i + 1];
+            if (i + 3 < nit) CRA_LOAD_OPS(o0, items[i + 3]);
             CRA_COMPUTE(o1, e1);
+            if (i + 2 >= nit) break;
+            const int e2 = items[i + 2];
+            if (i + 4 < nit) CRA_LOAD_OPS(o1, items[i + 4]);
+            CRA_COMPUTE(o2, e2);
         }
 #undef CRA_LOAD_OPS
 #undef CRA_COMPUTE
     }
     __syncthreads();
+    if (exp_flags & 4) return;
+    if (exp_flags & 8) {      // timing experiment: skip the contraction's W (stale shared memory is transformed)
+    }
 
     // ---- inverse FFT of every pair, pass 1: (pair, n2): N1-point DFT over n1, twiddle ----------
     const int npr = 4 * nj;                   // live pair slots per row
@@ -224,10 +240,13 @@ ccf_mma_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned
         }
         if (k1 == 0) {
             const int row = row0 + pr, ref = 4 * q0 + pc;
-            const float sc = 1.0f / (float)N;
-            const float qn = bq * sc, qm = bt * sc;
             CraCand cd;
             if (row < nrows && ref < R) {
+                // deferred Normalize_ring (cra_common.cuh): the row spectrum is stored un-normalised;
+                // (x - avg)/sigma only moves the DC bins, i.e. shifts every lag by -avg * tref[ref]
+                const float2 nm = norm[row];
+                const float sc = nm.y / (float)N, dc = nm.x * tref[ref];
+                const float qn = (bq - dc) * sc, qm = (bt - dc) * sc;
                 if (qn >= qm) { cd.v = qn; cd.code = ref * 8192 + (mq + 1); }
                 else          { cd.v = qm; cd.code = ref * 8192 + 4096 + (mt + 1); }
             } else { cd.v = -INFINITY; cd.code = -1; }
@@ -286,7 +305,7 @@ int bind_schedule(const CraRingTab& h, const std::vector<int>& koff, cudaStream_
 
 template <int LOG2N>
 int launch_t(const unsigned char* spec, int nrows, const unsigned char* refspec, int R, size_t row_bytes,
-             const float2* twid, CraCand* cand, int ntile_n, cudaStream_t st)
+             const float2* twid, CraCand* cand, int ntile_n, const float2* norm, const float* tref, cudaStream_t st)
 {
     using S = MShape<LOG2N>;
     const size_t smem = ((size_t)S::NP * S::PS + S::N) * sizeof(float2);
@@ -300,7 +319,7 @@ int launch_t(const unsigned char* spec, int nrows, const unsigned char* refspec,
     const long nblk = ncta_m * ntile_n;
     if (nblk <= 0) return 0;
     if (nblk > 2147483647L) { cra_set_error("ccf grid too large; lower row_batch"); return 1; }
-    ccf_mma_kernel<LOG2N><<<(unsigned)nblk, kThreads, smem, st>>>(spec, nrows, refspec, R, row_bytes, twid, cand, nquad, ntile_n);
+    ccf_mma_kernel<LOG2N><<<(unsigned)nblk, kThreads, smem, st>>>(spec, nrows, refspec, R, row_bytes, twid, cand, nquad, ntile_n, norm, tref, getenv("CRA_EXP") ? atoi(getenv("CRA_EXP")) : 0);
     CRA_CUDA(cudaGetLastError());
     return 0;
 }
@@ -320,17 +339,17 @@ int cra_ccf_mma_num_tiles(int R, int log2n)
 
 int cra_launch_ccf_mma(const unsigned char* spec, int nrows, const unsigned char* refspec, int R, const CraRingTab& htab,
                        const CraFragTab& frag, const std::vector<int>& h_koff, const float2* twid, CraCand* cand,
-                       int ntile_n, cudaStream_t st)
+                       int ntile_n, const float2* norm, const float* tref, cudaStream_t st)
 {
     if (bind_schedule(htab, h_koff, st)) return 1;
     const size_t rb = cra_frag_row_bytes(frag.nch);
     switch (htab.log2n) {
-        case 5:  return launch_t<5>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, st);
-        case 6:  return launch_t<6>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, st);
-        case 7:  return launch_t<7>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, st);
-        case 8:  return launch_t<8>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, st);
-        case 9:  return launch_t<9>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, st);
-        case 10: return launch_t<10>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, st);
+        case 5:  return launch_t<5>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, norm, tref, st);
+        case 6:  return launch_t<6>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, norm, tref, st);
+        case 7:  return launch_t<7>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, norm, tref, st);
+        case 8:  return launch_t<8>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, norm, tref, st);
+        case 9:  return launch_t<9>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, norm, tref, st);
+        case 10: return launch_t<10>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, norm, tref, st);
         default: cra_set_error("maxrin must be a power of two in [32, 1024]"); return 1;
     }
 }

@@ -52,6 +52,27 @@ struct CraPolarItems {         // flat work lists of the ring FFT passes (device
     const int* C; int nC;      // (ring << 16 | k)          pass C: split + store, k <= len/4
 };
 
+// ---- grouped row kernel (cra_polar_grp.cu) -----------------------------------------------------
+#ifndef CRA_GRP_RMAX
+#define CRA_GRP_RMAX 17        // most shift rows one CTA of the grouped row kernel resamples together
+#endif
+struct CraPhase {              // one walk of the CTA over a set of consecutive 4-ring units
+    int q0, q1;                // quarter-ring sample range in samp[]
+    int a0, a1, b0, b1, c0, c1;// item ranges in CraPolarItems A / B / C
+    int u0, u1;                // ring units [u0, u1): unit u = slots 4u..4u+3, slot s <-> ring nring-1-s
+    int upr;                   // pass-D lanes per row = sum over the units of (longest half length + 1)
+    int magicA, magicB, magicC, magicD;   // floor(2^24 / n) + 1 for n = items A, B, C, upr (fastdiv)
+    int pad;
+};
+struct CraGroupPlan {
+    const CraPhase* phases;    // device
+    int nphase;
+    const int* ppoff;          // [nring] float2 offset of ring i inside its phase's row buffer (device)
+    const int* unit_nk;        // [units] longest half length + 1 of unit u (device)
+    int stride;                // floats per row of the phase buffer
+    int rmax;                  // rows per CTA (<= CRA_GRP_RMAX), chosen for shared-memory fit
+};
+
 struct CraRowMap {             // how rows of the current batch map to particles
     const int*       row_start;  // [np+1] first row of each batch-local particle
     const int*       chunk_start;// [np+1] first polar CTA of each batch-local particle
@@ -76,9 +97,17 @@ __host__ __device__ __forceinline__ size_t cra_spec_idx(int coff, int half, int 
 // nring-1-s) are cut into chunks of 16 slots (zero padded).  One chunk of one row (or reference)
 // is 128 bytes: 4 quads t x [re unit | im unit]; a 16-byte unit holds the 4 slots 16c+4t .. +3 of
 // that part as bf16 hi x4 then bf16 lo x4, value = hi + lo (split-bf16: ~17 significant bits).
-// A thread of mma.sync.m16n8k16 therefore fetches its A (row) fragment with one 256-bit load and
-// its B (reference) fragment with one 128-bit load.  Chunks are stored k-major: chunk index
-// koff[k] + c; a row is nch * 128 bytes.
+// That is the REFERENCE layout (B operand: one 128-bit load per thread).  PARTICLE ROWS use the A-operand
+// order instead: the 32 bytes of quad t are 8 words  hi{re s0s1, im s0s1, re s2s3, im s2s3} then
+// lo{same}  (s0..s3 = slots 16c+4t..+3, first slot in the low half-word), so that one 256-bit load
+// is a thread's A fragment with the hi and lo registers already in mma operand order.
+// Chunks are stored k-major: chunk index koff[k] + c; a row is nch * 128 bytes.
+//
+// Deferred Normalize_ring: the row kernels may store the spectrum of the RAW polar image and put
+// (avg, 1/sigma) of Normalize_ring into norm[row].  (x - avg)/sigma only changes the DC bin of each
+// ring by -avg*len, so every lag of a (row, ref) correlation moves by the same -avg * tref[ref],
+// tref[ref] = sum_rings len * (weighted reference DC); the CCF kernel applies
+// value = (raw - avg * tref) / sigma when it emits a candidate.  norm = (0, 1) means "already normalised".
 #define CRA_FMT_F32  0          // planar-pair float2 layout above (FP32 FMA contraction)
 #define CRA_FMT_FRAG 1          // fragment layout (tensor-core contraction)
 struct CraFragTab {
@@ -103,19 +132,26 @@ int cra_launch_mask_normalize(float* imgs, int n, int nx, const float* mask, int
 // particle rows described by map -> spec[row]; references -> refspec (weights applied)
 // twid_fwd[j] = exp(-2 pi i j / maxrin), j < maxrin
 int cra_polar_rows_per_block();
+// norm: [rows] (avg, 1/sigma) written by the row kernels (FRAG format only, may be null otherwise);
+// tref: [R] written by the reference kernel (FRAG format only)
 int cra_launch_polar_rows(const float* images, int nx, const CraRingTab* tab, const CraRingTab& htab,
                           const float4* samp, const float* sampw, const float2* twid_fwd, const CraPolarItems& items,
-                          CraRowMap map, int normalize_ring, float* spec, int fmt, const CraFragTab& frag, cudaStream_t st);
+                          CraRowMap map, int normalize_ring, float* spec, int fmt, const CraFragTab& frag,
+                          float2* norm, cudaStream_t st);
 int cra_launch_polar_refs(const float* refs, int R, int nx, const CraRingTab* tab, const CraRingTab& htab,
                           const float4* samp, const float2* twid_fwd, const CraPolarItems& items, float* refspec,
-                          int fmt, const CraFragTab& frag, cudaStream_t st);
+                          int fmt, const CraFragTab& frag, float* tref, cudaStream_t st);
 int cra_launch_polar_single(const float* image, int nx, const CraRingTab* tab, const CraRingTab& htab,
                             const float4* samp, const float* sampw, const float2* twid_fwd, const CraPolarItems& items,
                             float cx, float cy, int normalize_ring, float* spec, int fmt, const CraFragTab& frag,
-                            cudaStream_t st);
+                            float2* norm, cudaStream_t st);
+size_t cra_polar_group_smem(int nx, int maxrin, const CraGroupPlan& plan);
+int cra_launch_polar_group(const float* images, int nx, const CraRingTab* tab, const CraRingTab& htab,
+                           const float4* samp, const float2* twid_fwd, const CraPolarItems& items, const CraGroupPlan& plan,
+                           CraRowMap map, int normalize_ring, float* spec, const CraFragTab& frag, float2* norm, cudaStream_t st);
 int cra_launch_ccf_mma(const unsigned char* spec, int nrows, const unsigned char* refspec, int R, const CraRingTab& htab,
                        const CraFragTab& frag, const std::vector<int>& h_koff, const float2* twid, CraCand* cand,
-                       int ntile_n, cudaStream_t st);
+                       int ntile_n, const float2* norm, const float* tref, cudaStream_t st);
 int cra_ccf_mma_num_tiles(int R, int log2n);
 int cra_launch_ccf(const float* spec, int nrows, const float* refspec, int R, const CraRingTab* tab,
                    const CraRingTab& htab, const float2* twid, CraCand* cand, int ntile_n, cudaStream_t st);

@@ -20,6 +20,21 @@
 namespace {
 
 // split-bf16 of four values: (hi01, hi23, lo01, lo23), value = hi + lo
+// A-operand order of a particle row (cra_common.cuh): hi{re01, im01, re23, im23}, lo{same}
+__device__ __forceinline__ void split_row_unit(const float (&re)[4], const float (&im)[4], uint4& hi, uint4& lo)
+{
+    const __nv_bfloat162 hr01 = __floats2bfloat162_rn(re[0], re[1]), hi01 = __floats2bfloat162_rn(im[0], im[1]);
+    const __nv_bfloat162 hr23 = __floats2bfloat162_rn(re[2], re[3]), hi23 = __floats2bfloat162_rn(im[2], im[3]);
+    const float2 fr01 = __bfloat1622float2(hr01), fi01 = __bfloat1622float2(hi01);
+    const float2 fr23 = __bfloat1622float2(hr23), fi23 = __bfloat1622float2(hi23);
+    const __nv_bfloat162 lr01 = __floats2bfloat162_rn(re[0] - fr01.x, re[1] - fr01.y), li01 = __floats2bfloat162_rn(im[0] - fi01.x, im[1] - fi01.y);
+    const __nv_bfloat162 lr23 = __floats2bfloat162_rn(re[2] - fr23.x, re[3] - fr23.y), li23 = __floats2bfloat162_rn(im[2] - fi23.x, im[3] - fi23.y);
+    hi.x = *reinterpret_cast<const unsigned int*>(&hr01); hi.y = *reinterpret_cast<const unsigned int*>(&hi01);
+    hi.z = *reinterpret_cast<const unsigned int*>(&hr23); hi.w = *reinterpret_cast<const unsigned int*>(&hi23);
+    lo.x = *reinterpret_cast<const unsigned int*>(&lr01); lo.y = *reinterpret_cast<const unsigned int*>(&li01);
+    lo.z = *reinterpret_cast<const unsigned int*>(&lr23); lo.w = *reinterpret_cast<const unsigned int*>(&li23);
+}
+
 __device__ __forceinline__ uint4 split_bf16x4(float v0, float v1, float v2, float v3)
 {
     const __nv_bfloat162 h01 = __floats2bfloat162_rn(v0, v1), h23 = __floats2bfloat162_rn(v2, v3);
@@ -122,7 +137,8 @@ __global__ void __launch_bounds__(kPolarThreads)
 polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __restrict__ tab,
                  const float4* __restrict__ samp, const float* __restrict__ sampw,
                  const float2* __restrict__ twid, CraPolarItems items, CraRowMap map,
-                 float fix_cx, float fix_cy, int normalize_ring, float* __restrict__ spec, CraFragTab frag)
+                 float fix_cx, float fix_cy, int normalize_ring, float* __restrict__ spec, CraFragTab frag,
+                 float2* __restrict__ norm, float* __restrict__ tref)
 {
     extern __shared__ __align__(16) float smem[];
     const int npix = nx * nx;
@@ -393,8 +409,23 @@ polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __r
                 re[j] = v.x; im[j] = v.y;
             }
             uint4* o = reinterpret_cast<uint4*>(base + (size_t)r * nch * 128 + (size_t)gc * 128 + t * 32);
-            o[0] = split_bf16x4(re[0], re[1], re[2], re[3]);
-            o[1] = split_bf16x4(im[0], im[1], im[2], im[3]);
+            if (MODE == 1) {           // reference (B operand) layout: [re unit | im unit]
+                o[0] = split_bf16x4(re[0], re[1], re[2], re[3]);
+                o[1] = split_bf16x4(im[0], im[1], im[2], im[3]);
+            } else {                   // particle row (A operand) layout: hi words then lo words
+                uint4 hi, lo;
+                split_row_unit(re, im, hi, lo);
+                o[0] = hi; o[1] = lo;
+            }
+        }
+        if (MODE == 0 && norm != nullptr && tid < ck.nrow) norm[ck.row0 + tid] = make_float2(0.f, 1.f);   // normalised above
+        if (MODE == 1 && tref != nullptr && tid < 32) {
+            // tref = sum over rings of len * (weighted DC), fixed summation order (cra_common.cuh)
+            const float2* zrow = reinterpret_cast<const float2*>(s_circ);
+            float a = 0.f;
+            for (int i = tid; i < nring; i += 32) a += (float)tab->len[i] * zrow[tab->poff[i]].x;
+            a = warp_sum(a);
+            if (tid == 0) tref[ck.row0] = a;
         }
     }
 }
@@ -440,7 +471,7 @@ template <int MODE, int RPB, int FMT>
 int launch_polar_f(const float* images, int nx, const CraRingTab* tab, const CraRingTab& htab,
                    const float4* samp, const float* sampw, const float2* twid, const CraPolarItems& items,
                    CraRowMap map, float cx, float cy, int normalize_ring, float* spec, const CraFragTab& frag,
-                   int nblocks, cudaStream_t st)
+                   float2* norm, float* tref, int nblocks, cudaStream_t st)
 {
     if (nblocks <= 0) return 0;
     size_t smem = polar_smem_bytes<RPB>(nx, htab);
@@ -450,7 +481,7 @@ int launch_polar_f(const float* images, int nx, const CraRingTab* tab, const Cra
         configured = smem;
     }
     polar_fft_kernel<MODE, RPB, FMT><<<nblocks, kPolarThreads, smem, st>>>(images, nx, tab, samp, sampw, twid, items, map,
-                                                                          cx, cy, normalize_ring, spec, frag);
+                                                                          cx, cy, normalize_ring, spec, frag, norm, tref);
     CRA_CUDA(cudaGetLastError());
     return 0;
 }
@@ -459,13 +490,13 @@ template <int MODE, int RPB>
 int launch_polar(const float* images, int nx, const CraRingTab* tab, const CraRingTab& htab,
                  const float4* samp, const float* sampw, const float2* twid, const CraPolarItems& items,
                  CraRowMap map, float cx, float cy, int normalize_ring, float* spec, int fmt, const CraFragTab& frag,
-                 int nblocks, cudaStream_t st)
+                 float2* norm, float* tref, int nblocks, cudaStream_t st)
 {
     if (fmt == CRA_FMT_FRAG)
         return launch_polar_f<MODE, RPB, CRA_FMT_FRAG>(images, nx, tab, htab, samp, sampw, twid, items, map, cx, cy,
-                                                       normalize_ring, spec, frag, nblocks, st);
+                                                       normalize_ring, spec, frag, norm, tref, nblocks, st);
     return launch_polar_f<MODE, RPB, CRA_FMT_F32>(images, nx, tab, htab, samp, sampw, twid, items, map, cx, cy,
-                                                  normalize_ring, spec, frag, nblocks, st);
+                                                  normalize_ring, spec, frag, nullptr, nullptr, nblocks, st);
 }
 
 }  // namespace
@@ -482,26 +513,29 @@ int cra_launch_mask_normalize(float* imgs, int n, int nx, const float* mask, int
 
 int cra_launch_polar_rows(const float* images, int nx, const CraRingTab* tab, const CraRingTab& htab,
                           const float4* samp, const float* sampw, const float2* twid, const CraPolarItems& items,
-                          CraRowMap map, int normalize_ring, float* spec, int fmt, const CraFragTab& frag, cudaStream_t st)
+                          CraRowMap map, int normalize_ring, float* spec, int fmt, const CraFragTab& frag,
+                          float2* norm, cudaStream_t st)
 {
     return launch_polar<0, CRA_POLAR_RPB>(images, nx, tab, htab, samp, sampw, twid, items, map, 0.f, 0.f,
-                                          normalize_ring, spec, fmt, frag, map.nchunks, st);
+                                          normalize_ring, spec, fmt, frag, norm, nullptr, map.nchunks, st);
 }
 
 int cra_launch_polar_refs(const float* refs, int R, int nx, const CraRingTab* tab, const CraRingTab& htab,
                           const float4* samp, const float2* twid, const CraPolarItems& items, float* refspec,
-                          int fmt, const CraFragTab& frag, cudaStream_t st)
+                          int fmt, const CraFragTab& frag, float* tref, cudaStream_t st)
 {
     CraRowMap map{};
-    return launch_polar<1, 1>(refs, nx, tab, htab, samp, nullptr, twid, items, map, 0.f, 0.f, 0, refspec, fmt, frag, R, st);
+    return launch_polar<1, 1>(refs, nx, tab, htab, samp, nullptr, twid, items, map, 0.f, 0.f, 0, refspec, fmt, frag,
+                              nullptr, tref, R, st);
 }
 
 int cra_launch_polar_single(const float* image, int nx, const CraRingTab* tab, const CraRingTab& htab,
                             const float4* samp, const float* sampw, const float2* twid, const CraPolarItems& items,
                             float cx, float cy, int normalize_ring, float* spec, int fmt, const CraFragTab& frag,
-                            cudaStream_t st)
+                            float2* norm, cudaStream_t st)
 {
     CraRowMap map{};
     map.row_start = nullptr; map.p0 = 0;
-    return launch_polar<0, 1>(image, nx, tab, htab, samp, sampw, twid, items, map, cx, cy, normalize_ring, spec, fmt, frag, 1, st);
+    return launch_polar<0, 1>(image, nx, tab, htab, samp, sampw, twid, items, map, cx, cy, normalize_ring, spec, fmt, frag,
+                              norm, nullptr, 1, st);
 }

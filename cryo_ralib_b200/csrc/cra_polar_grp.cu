@@ -1,0 +1,377 @@
+// cra_polar_grp.cu -- the production row kernel of stage 1+2: Util.Polar2Dm (alrl_ms + quadri),
+// the sums of Normalize_ring and the per-ring real FFT (Util.Frngs) for EVERY shift of a particle
+// at once.  Reference call site: test_mref.py:200-201 -> the (iy, ix) double loop of EMAN2
+// Util::multiref_polar_ali_2d; replaces the per-shift relaunch of cu_resample_to_polar + cuFFT R2C
+// (cuda/gpu_aln_noref.cu:818-879, :1775-1816).
+//
+// When the search step is a whole number of pixels every shift of a particle samples the image at
+// the same sub-pixel phase: the six quadri weights of a ring sample depend on the fractional part
+// of (centre + sample offset) only, so they are computed ONCE per sample and applied to up to
+// RMAX shift rows, whose taps differ by an integer pixel offset.  One CTA owns (particle, block of
+// <= rmax shift rows): the image tile is staged once in shared memory and the CTA walks the rings
+// in PHASES of 4-ring units (the unit of the fragment layout, cra_common.cuh) so that the ring
+// buffers of all its rows fit beside the image:
+//   interpolate (weights shared, Normalize_ring sums in registers) -> ring FFT pass A -> pass B
+//   -> real-FFT split (index math shared by the rows) -> split-bf16 + 32-byte unit stores.
+// Normalize_ring is deferred (cra_common.cuh): the spectrum of the raw polar image is stored and
+// (avg, 1/sigma) goes to norm[row]; the CCF kernel applies it when it emits a candidate.
+// Requirements checked by the host (cra_api.cu): integral step, every 3x3 neighbourhood inside
+// the frame (always true under search_range); otherwise the general kernel of cra_polar.cu runs.
+#include "cra_common.cuh"
+#include "cra_fft.cuh"
+#include <cuda_bf16.h>
+
+namespace {
+
+using crafft::cmul;
+using crafft::fft_reg;
+
+constexpr int kThreads = 256;
+constexpr int RMAX = CRA_GRP_RMAX;
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// A-operand order of a particle row (cra_common.cuh): hi{re01, im01, re23, im23}, lo{same}
+__device__ __forceinline__ void split_row_unit(const float (&re)[4], const float (&im)[4], uint4& hi, uint4& lo)
+{
+    const __nv_bfloat162 hr01 = __floats2bfloat162_rn(re[0], re[1]), hi01 = __floats2bfloat162_rn(im[0], im[1]);
+    const __nv_bfloat162 hr23 = __floats2bfloat162_rn(re[2], re[3]), hi23 = __floats2bfloat162_rn(im[2], im[3]);
+    const float2 fr01 = __bfloat1622float2(hr01), fi01 = __bfloat1622float2(hi01);
+    const float2 fr23 = __bfloat1622float2(hr23), fi23 = __bfloat1622float2(hi23);
+    const __nv_bfloat162 lr01 = __floats2bfloat162_rn(re[0] - fr01.x, re[1] - fr01.y), li01 = __floats2bfloat162_rn(im[0] - fi01.x, im[1] - fi01.y);
+    const __nv_bfloat162 lr23 = __floats2bfloat162_rn(re[2] - fr23.x, re[3] - fr23.y), li23 = __floats2bfloat162_rn(im[2] - fi23.x, im[3] - fi23.y);
+    hi.x = *reinterpret_cast<const unsigned int*>(&hr01); hi.y = *reinterpret_cast<const unsigned int*>(&hi01);
+    hi.z = *reinterpret_cast<const unsigned int*>(&hr23); hi.w = *reinterpret_cast<const unsigned int*>(&hi23);
+    lo.x = *reinterpret_cast<const unsigned int*>(&lr01); lo.y = *reinterpret_cast<const unsigned int*>(&li01);
+    lo.z = *reinterpret_cast<const unsigned int*>(&lr23); lo.w = *reinterpret_cast<const unsigned int*>(&li23);
+}
+
+template <int NA, int NB>
+__device__ __forceinline__ void pass_a(float2* __restrict__ z, int b, float2 base)
+{
+    float2 x[NA];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) x[a] = z[a * (NB + 1) + b];
+    fft_reg<NA, -1>(x);
+    z[b] = x[0];
+    float2 p = base;
+#pragma unroll
+    for (int a = 1; a < NA; ++a) {
+        z[a * (NB + 1) + b] = cmul(x[a], p);
+        if (a + 1 < NA) p = cmul(p, base);
+    }
+}
+template <int NA, int NB>
+__device__ __forceinline__ void pass_b(float2* __restrict__ z, int ka)
+{
+    float2 x[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) x[b] = z[ka * (NB + 1) + b];
+    fft_reg<NB, -1>(x);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) z[ka * (NB + 1) + b] = x[b];
+}
+
+// floor(w / d) for w * magic < 2^32, magic = floor(2^24 / d) + 1 (host side, exact for the ranges used here)
+__device__ __forceinline__ int fastdiv(int w, int magic) { return (int)(((unsigned)w * (unsigned)magic) >> 24); }
+
+// row sets that balance "lanes = n * nset, each lane loops ceil(nr / nset) rows" over the CTA
+__device__ __forceinline__ int pick_nset(int n, int nr)
+{
+    int best = 1, bestc = 1 << 30;
+    for (int s = 1; s <= nr; ++s) {
+        const int c = ((n * s + kThreads - 1) / kThreads) * ((nr + s - 1) / s);
+        if (c < bestc) { bestc = c; best = s; }
+    }
+    return best;
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* __restrict__ tab,
+                   const float4* __restrict__ samp, const float2* __restrict__ twid, CraPolarItems items,
+                   CraGroupPlan plan, CraRowMap map, int normalize_ring, unsigned char* __restrict__ spec,
+                   CraFragTab frag, float2* __restrict__ norm)
+{
+    extern __shared__ __align__(16) float smem[];
+    const int npix = nx * nx;
+    const int maxrin = tab->maxrin, nring = tab->nring;
+    const int stride = plan.stride;                            // floats per row of the phase buffer
+    float* s_img = smem;                                       // npix (padded to 4)
+    float* s_buf = smem + ((npix + 3) & ~3);                   // rmax * stride
+    float2* s_tw = reinterpret_cast<float2*>(s_buf + plan.rmax * stride);   // maxrin : exp(-2 pi i j / maxrin)
+    __shared__ float s_red[kThreads / 32][2 * RMAX];
+    __shared__ int s_rowoff[RMAX];
+    __shared__ int s_blk[4];                                   // particle (batch local), first local row, rows
+    __shared__ float s_base[2];
+    __shared__ int4 s_ring[CRA_MAX_RINGS];                     // phase-local float2 offset, log2 NB, len/4, wn
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        const int b = blockIdx.x;
+        int lo = 0, hi = map.np;               // last p with chunk_start[p] <= b
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (map.chunk_start[mid] <= b) lo = mid; else hi = mid; }
+        const int rows = map.row_start[lo + 1] - map.row_start[lo];
+        const int nblk = map.chunk_start[lo + 1] - map.chunk_start[lo];
+        const int bi = b - map.chunk_start[lo];
+        const int r_lo = (int)(((long)bi * rows) / nblk), r_hi = (int)(((long)(bi + 1) * rows) / nblk);
+        s_blk[0] = lo; s_blk[1] = r_lo; s_blk[2] = r_hi - r_lo; s_blk[3] = map.row_start[lo] + r_lo;
+        const int4 w = map.win[lo];
+        const int wx = w.x + w.y + 1;
+        const int istep = (int)map.step;
+        s_base[0] = map.search[lo].cx - (float)w.x * map.step;
+        s_base[1] = map.search[lo].cy - (float)w.z * map.step;
+        for (int r = 0; r < r_hi - r_lo; ++r) {
+            const int li = r_lo + r;
+            s_rowoff[r] = (li / wx) * istep * nx + (li % wx) * istep;
+        }
+    }
+    for (int i = tid; i < maxrin; i += kThreads) s_tw[i] = twid[i];
+    for (int i = tid; i < nring; i += kThreads) {
+        const int n = tab->len[i] >> 1, lg = 31 - __clz(n);
+        s_ring[i] = make_int4(__ldg(plan.ppoff + i), lg - (lg >> 1), tab->len[i] >> 2, __float_as_int(tab->wn[i]));
+    }
+    __syncthreads();
+    const int nr = s_blk[2];
+    const int grow0 = s_blk[3];                                // first row of this block in the batch
+    {
+        const float* img = images + (size_t)(map.p0 + s_blk[0]) * npix;
+        if ((npix & 3) == 0) {
+            const float4* g4 = reinterpret_cast<const float4*>(img);
+            float4* s4 = reinterpret_cast<float4*>(s_img);
+            for (int i = tid; i < (npix >> 2); i += kThreads) s4[i] = __ldg(g4 + i);
+        } else {
+            for (int i = tid; i < npix; i += kThreads) s_img[i] = __ldg(img + i);
+        }
+    }
+    const float bx = s_base[0], by = s_base[1];
+    float av[RMAX], sq[RMAX];
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) { av[r] = 0.f; sq[r] = 0.f; }
+    __syncthreads();
+
+    for (int ph = 0; ph < plan.nphase; ++ph) {
+        const CraPhase P = plan.phases[ph];
+        // ---- interpolate the phase's rings for every row: weights once per sample ----------------
+        for (int q = P.q0 + tid; q < P.q1; q += kThreads) {
+            const float4 e = __ldg(samp + q);                 // x, y, ring, jt (first quarter of the ring)
+            const int4 rp = s_ring[__float_as_int(e.z)];
+            const int jt = __float_as_int(e.w);
+            const float wn = __int_as_float(rp.w);
+            const float ox[4] = {e.x, e.y, -e.x, -e.y}, oy[4] = {e.y, -e.x, -e.y, e.x};
+            float w0[4], w1[4], w2[4], w3[4], w4[4], w5[4];
+            int pix[4], slot[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int j = jt + m * rp.z, p = j >> 1;
+                slot[m] = 2 * (rp.x + p + (p >> rp.y)) + (j & 1);
+                const float X = ox[m] + bx, Y = oy[m] + by;
+                const int ix = (int)X, iy = (int)Y;
+                const float dx = X - (float)ix, dy = Y - (float)iy;
+                // quadri: f0 + dx (c1 + (dx-1) c2 + dy c5) + dy (c3 + (dy-1) c4) as six tap weights
+                const float a2 = 0.5f * dx * (dx - 1.0f), b2 = 0.5f * dy * (dy - 1.0f), ab = dx * dy;
+                w1[m] = dx + a2 - ab;          // (i+1, j)
+                w2[m] = a2;                    // (i-1, j)
+                w3[m] = dy + b2 - ab;          // (i, j+1)
+                w4[m] = b2;                    // (i, j-1)
+                w5[m] = ab;                    // (i+1, j+1)
+                w0[m] = 1.0f - dx - dy - 2.0f * a2 - 2.0f * b2 + ab;
+                pix[m] = (iy - 1) * nx + (ix - 1);
+            }
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                if (r < nr) {
+                    const int ro = s_rowoff[r];
+                    float* dst = s_buf + r * stride;
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        const float* p = s_img + (pix[m] + ro);
+                        float v = w0[m] * p[0];
+                        v = fmaf(w1[m], p[1], v);
+                        v = fmaf(w2[m], p[-1], v);
+                        v = fmaf(w3[m], p[nx], v);
+                        v = fmaf(w4[m], p[-nx], v);
+                        v = fmaf(w5[m], p[nx + 1], v);
+                        dst[slot[m]] = v;
+                        s1 += v; s2 = fmaf(v, v, s2);
+                    }
+                    av[r] = fmaf(s1, wn, av[r]); sq[r] = fmaf(s2, wn, sq[r]);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- ring FFTs, pass A: (row, ring, column b) flattened ---------------------------------
+        {
+            const int nA = P.a1 - P.a0;
+            for (int w = tid; w < nA * nr; w += kThreads) {
+                const int r = fastdiv(w, P.magicA), item = __ldg(items.A + P.a0 + (w - r * nA));
+                const int ring = item >> 16, b = item & 0xffff;
+                const int4 rp = s_ring[ring];
+                const int half = rp.z * 2;                             // complex points of the ring
+                float2* z = reinterpret_cast<float2*>(s_buf + r * stride) + rp.x;
+                const int lg = 31 - __clz(half);
+                const float2 base = s_tw[b * (maxrin / half)];         // exp(-2 pi i b / n)
+                switch (lg) {
+                    case 2: pass_a<2, 2>(z, b, base); break;
+                    case 3: pass_a<2, 4>(z, b, base); break;
+                    case 4: pass_a<4, 4>(z, b, base); break;
+                    case 5: pass_a<4, 8>(z, b, base); break;
+                    case 6: pass_a<8, 8>(z, b, base); break;
+                    case 7: pass_a<8, 16>(z, b, base); break;
+                    case 8: pass_a<16, 16>(z, b, base); break;
+                    default: pass_a<16, 32>(z, b, base); break;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- pass B ------------------------------------------------------------------------------
+        {
+            const int nB = P.b1 - P.b0;
+            for (int w = tid; w < nB * nr; w += kThreads) {
+                const int r = fastdiv(w, P.magicB), item = __ldg(items.B + P.b0 + (w - r * nB));
+                const int ring = item >> 16, ka = item & 0xffff;
+                const int4 rp = s_ring[ring];
+                float2* z = reinterpret_cast<float2*>(s_buf + r * stride) + rp.x;
+                const int lg = 31 - __clz(rp.z * 2);
+                switch (lg) {
+                    case 2: pass_b<2, 2>(z, ka); break;
+                    case 3: pass_b<2, 4>(z, ka); break;
+                    case 4: pass_b<4, 4>(z, ka); break;
+                    case 5: pass_b<4, 8>(z, ka); break;
+                    case 6: pass_b<8, 8>(z, ka); break;
+                    case 7: pass_b<8, 16>(z, ka); break;
+                    case 8: pass_b<16, 16>(z, ka); break;
+                    default: pass_b<16, 32>(z, ka); break;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- pass C: real-FFT split in place; index math once per (ring, k), rows inside ---------
+        // Z_k of the half-length complex FFT sits at z[(k % NA)*(NB+1) + k / NA];
+        // F_k = E_k + w_k O_k, F_{n-k} = conj(E_k - w_k O_k), w_k = exp(-2 pi i k / len);
+        // slot pos(0) <- (F_0, F_n): both real
+        {
+            const int nC = P.c1 - P.c0;
+            const int nset = pick_nset(nC, nr);
+            for (int x = tid; x < nC * nset; x += kThreads) {
+                const int set = fastdiv(x, P.magicC), item = __ldg(items.C + P.c0 + (x - set * nC));
+                const int ring = item >> 16, k = item & 0xffff;
+                const int4 rp = s_ring[ring];
+                const int n = rp.z * 2, len = rp.z * 4;
+                const int lb = rp.y, NA = n >> lb, la = 31 - __clz(NA), NB1 = (1 << lb) + 1;
+                const int m = (k == 0) ? 0 : n - k;
+                const int pk = rp.x + (k & (NA - 1)) * NB1 + (k >> la), pm = rp.x + (m & (NA - 1)) * NB1 + (m >> la);
+                const float2 wk = s_tw[k * (maxrin / len)];
+                for (int r = set; r < nr; r += nset) {
+                    float2* z = reinterpret_cast<float2*>(s_buf + r * stride);
+                    const float2 a = z[pk], b = z[pm];
+                    if (k == 0) {
+                        z[pk] = make_float2(a.x + a.y, a.x - a.y);
+                    } else {
+                        const float2 E = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
+                        const float2 O = make_float2(0.5f * (a.y + b.y), -0.5f * (a.x - b.x));
+                        const float2 Pk = cmul(O, wk);
+                        z[pk] = make_float2(E.x + Pk.x, E.y + Pk.y);
+                        if (pm != pk) z[pm] = make_float2(E.x - Pk.x, -(E.y - Pk.y));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- pass D: one (k, unit) per lane, rows inside: gather 4 ring slots, split, store -------
+        {
+            const int upr = P.upr;
+            const int nset = pick_nset(upr, nr);
+            const size_t rb = (size_t)frag.nch * 128;
+            for (int x = tid; x < upr * nset; x += kThreads) {
+                const int set = fastdiv(x, P.magicD);
+                int k = x - set * upr, u = P.u0;
+                while (k >= __ldg(plan.unit_nk + u)) { k -= __ldg(plan.unit_nk + u); ++u; }
+                int idx[4], sel[4];                                    // sel: 0 complex, 1 re = .x, 2 re = .y, 3 zero
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int ring = nring - 1 - (4 * u + j);
+                    idx[j] = 0; sel[j] = 3;
+                    if (ring >= 0) {
+                        const int4 rp = s_ring[ring];
+                        const int n = rp.z * 2;
+                        if (k <= n) {
+                            const int lb = rp.y, NA = n >> lb, la = 31 - __clz(NA);
+                            if (k == 0) { idx[j] = rp.x; sel[j] = 1; }
+                            else if (k == n) { idx[j] = rp.x; sel[j] = 2; }
+                            else { idx[j] = rp.x + (k & (NA - 1)) * ((1 << lb) + 1) + (k >> la); sel[j] = 0; }
+                        }
+                    }
+                }
+                unsigned char* o = spec + (size_t)(grow0 + set) * rb + (size_t)(__ldg(frag.koff + k) + (u >> 2)) * 128 + (u & 3) * 32;
+                for (int r = set; r < nr; r += nset) {
+                    const float2* z = reinterpret_cast<const float2*>(s_buf + r * stride);
+                    float re[4], im[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 v = z[idx[j]];
+                        re[j] = (sel[j] == 3) ? 0.f : ((sel[j] == 2) ? v.y : v.x);
+                        im[j] = (sel[j] == 0) ? v.y : 0.f;
+                    }
+                    uint4 hi, lo;
+                    split_row_unit(re, im, hi, lo);
+                    uint4* o4 = reinterpret_cast<uint4*>(o);
+                    o4[0] = hi; o4[1] = lo;
+                    o += (size_t)nset * rb;
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- Normalize_ring sums -> norm[row] = (avg, 1/sigma) ---------------------------------------
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) { av[r] = warp_sum(av[r]); sq[r] = warp_sum(sq[r]); }
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) { s_red[tid >> 5][2 * r] = av[r]; s_red[tid >> 5][2 * r + 1] = sq[r]; }
+    }
+    __syncthreads();
+    if (tid < nr) {
+        float avg = 0.f, isg = 1.f;
+        if (normalize_ring) {
+            float a = 0.f, s = 0.f;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) { a += s_red[w][2 * tid]; s += s_red[w][2 * tid + 1]; }
+            const float nn = tab->nn;
+            avg = a / nn;
+            isg = 1.0f / sqrtf((s - a * a / nn) / nn);
+        }
+        norm[grow0 + tid] = make_float2(avg, isg);
+    }
+}
+
+}  // namespace
+
+size_t cra_polar_group_smem(int nx, int maxrin, const CraGroupPlan& plan)
+{
+    const size_t npix = ((size_t)nx * nx + 3) & ~(size_t)3;
+    return (npix + (size_t)plan.rmax * plan.stride) * sizeof(float) + (size_t)maxrin * sizeof(float2);
+}
+
+int cra_launch_polar_group(const float* images, int nx, const CraRingTab* tab, const CraRingTab& htab,
+                           const float4* samp, const float2* twid, const CraPolarItems& items, const CraGroupPlan& plan,
+                           CraRowMap map, int normalize_ring, float* spec, const CraFragTab& frag, float2* norm, cudaStream_t st)
+{
+    if (map.nchunks <= 0) return 0;
+    const size_t smem = cra_polar_group_smem(nx, htab.maxrin, plan);
+    static size_t configured = 0;
+    if (smem > configured) {
+        CRA_CUDA(cudaFuncSetAttribute(polar_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    polar_group_kernel<<<map.nchunks, kThreads, smem, st>>>(images, nx, tab, samp, twid, items, plan, map, normalize_ring,
+                                                           reinterpret_cast<unsigned char*>(spec), frag, norm);
+    CRA_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -58,7 +58,7 @@ RESULT_DTYPE = np.dtype([("ang", "f4"), ("sxs", "f4"), ("sys", "f4"), ("mirror",
 
 CORE_SYMBOLS = ["cra_create", "cra_destroy", "cra_last_error", "cra_ring_info", "cra_upload_particles",
                 "cra_upload_particles_dev", "cra_set_refs", "cra_align", "cra_accumulate", "cra_zero_sums",
-                "cra_sums_device_ptr", "cra_get_sums", "cra_transform", "cra_polar_spectrum", "cra_ref_spectrum",
+                "cra_sums_device_ptr", "cra_get_sums", "cra_transform", "cra_polar_spectrum", "cra_ref_spectrum", "cra_batch_row_spectrum",
                 "cra_ccf_curves", "cra_last_align_stats", "cra_set_timing", "cra_set_normalize_ring", "cra_set_step",
                 "cra_row_batch", "cra_device_images_ptr", "cra_stream", "cra_measure_fp32_peak"]
 LEGACY_SYMBOLS = ["print_gpu_info", "pre_align_size_check", "pre_align_init", "pre_align_fetch", "reset_shifts",
@@ -93,6 +93,7 @@ def load_library(path=None):
     L.cra_transform.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     L.cra_polar_spectrum.argtypes = [vp, C.c_int, C.c_float, C.c_float, vp]
     L.cra_ref_spectrum.argtypes = [vp, C.c_int, vp]
+    L.cra_batch_row_spectrum.argtypes = [vp, C.c_int, vp, ip]
     L.cra_ccf_curves.argtypes = [vp, C.c_int, C.c_float, C.c_float, C.c_int, vp, vp]
     L.cra_last_align_stats.argtypes = [vp, C.POINTER(CraAlignStats)]
     L.cra_set_timing.argtypes = [vp, C.c_int]
@@ -219,6 +220,13 @@ class Engine(object):
         out = np.zeros(self.lcirc, np.float32)
         self._ck(self.L.cra_polar_spectrum(self.h, int(particle), cx, cy, out.ctypes.data))
         return out
+
+    def batch_row_spectrum(self, row):
+        """Spectrum of one row of the last batch align() processed, and which row kernel wrote it."""
+        out = np.zeros(self.lcirc, np.float32)
+        k = C.c_int()
+        self._ck(self.L.cra_batch_row_spectrum(self.h, int(row), out.ctypes.data, C.byref(k)))
+        return out, k.value
 
     def ref_spectrum(self, iref):
         out = np.zeros(self.lcirc, np.float32)

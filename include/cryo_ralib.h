@@ -108,6 +108,10 @@ int  cra_transform(CraCtx* ctx, int start, int stop, const float* params, float*
 /* Stage-level entry points used by the parity tests. */
 int  cra_polar_spectrum(CraCtx* ctx, int particle, float cx, float cy, float* host_out /*lcirc*/);
 int  cra_ref_spectrum(CraCtx* ctx, int iref, float* host_out /*lcirc*/);
+/* Spectrum (Normalize_ring applied) of row `row` of the LAST row batch cra_align processed, as the
+ * production row kernel left it: rows run particle by particle in the visit order of
+ * multiref_polar_ali_2d (y outer, x inner).  which_kernel: 1 = grouped row kernel, 0 = general. */
+int  cra_batch_row_spectrum(CraCtx* ctx, int row, float* host_out /*lcirc*/, int* which_kernel);
 int  cra_ccf_curves(CraCtx* ctx, int particle, float cx, float cy, int iref,
                     float* q_out /*maxrin*/, float* t_out /*maxrin*/);
 

@@ -49,6 +49,40 @@ def test_polar_spectrum_matches_oracle(oracle, small_set):
         e.close()
 
 
+def test_grouped_row_kernel_spectra_match_oracle(oracle, small_set):
+    """Every shift row the production (grouped, weight-sharing) row kernel writes, against the oracle's
+    Polar2Dm + Normalize_ring + Frngs at that centre; ragged windows and off-grid centres included."""
+    from cryo_ralib_b200.lib import SEARCH_DTYPE
+    images, refs, _ = small_set
+    imgs, mask, numr, _, _ = _prep(oracle, images, refs, 36)
+    P = 6
+    for normalize in (True, False):
+        e = _engine(90, 36, 3, P=P, R=4, normalize=normalize)
+        e.upload_particles(images[:P], subtract_mask_mean=True)
+        e.set_refs(refs[:4], normalize_mask=True)
+        search = np.zeros(P, SEARCH_DTYPE)
+        search["cx"] = [46, 46.37, 44.2, 48.75, 46, 43.5]
+        search["cy"] = [46, 44.81, 47.9, 45.25, 46, 48.5]
+        search["xl"] = [3, 3, 2, 3, 0, 1]; search["xr"] = [3, 3, 3, 1, 0, 3]
+        search["yl"] = [3, 3, 3, 2, 0, 3]; search["yr"] = [3, 2, 3, 3, 0, 0]
+        e.align(0, P, search)
+        row = 0
+        for p in range(P):
+            s = search[p]
+            for iy in range(-int(s["yl"]), int(s["yr"]) + 1):
+                for ix in range(-int(s["xl"]), int(s["xr"]) + 1):
+                    got, kern = e.batch_row_spectrum(row)
+                    assert kern == 1, "the grouped row kernel should have handled this batch"
+                    c = oracle.polar2dm(imgs[p], float(s["cx"]) + ix, float(s["cy"]) + iy, numr)
+                    if normalize:
+                        c = oracle.normalize_ring(c, numr)
+                    want = oracle.frngs(c, numr)
+                    scale = np.abs(want).max()
+                    assert np.abs(got - want).max() <= 2e-5 * scale, (normalize, p, ix, iy, np.abs(got - want).max() / scale)
+                    row += 1
+        e.close()
+
+
 def test_polar_wraps_like_quadri(oracle, small_set):
     """Centres that push rings across the frame edge exercise the circular closure."""
     images, refs, _ = small_set
