@@ -90,14 +90,14 @@ int build_group_plan(CraCtx* c)
     std::vector<int> usize(nunit, 0), unk(nunit, 0);
     for (int u = 0; u < nunit; ++u) {
         for (int j = 0; j < 4; ++j) { const int ring = nring - 1 - (4 * u + j); if (ring >= 0) usize[u] += padded(ring); }
-        unk[u] = (t.len[nring - 1 - 4 * u] >> 1) + 1;
+        unk[u] = t.len[nring - 1 - 4 * u] >> 1;
     }
     const int cap = *std::max_element(usize.begin(), usize.end());          // float2 per row
     // item list positions: lists run over rings nring-1 .. 0 (build_tables), the sample table over rings 0 .. nring-1
     std::vector<int> aoff(nring + 1, 0), boff(nring + 1, 0), coff(nring + 1, 0), qoff(nring + 1, 0);
     for (int s = 0; s < nring; ++s) {
         const int ring = nring - 1 - s, n = t.len[ring] >> 1, lg = ilog2_floor(n), NA = 1 << (lg / 2), NB = n / NA;
-        aoff[s + 1] = aoff[s] + NB; boff[s + 1] = boff[s] + NA; coff[s + 1] = coff[s] + n / 2 + 1;
+        aoff[s + 1] = aoff[s] + NB; boff[s + 1] = boff[s] + NA; coff[s + 1] = coff[s] + n / 2;
     }
     for (int i = 0; i < nring; ++i) qoff[i + 1] = qoff[i] + t.len[i] / 4;
     std::vector<CraPhase> phases;
@@ -114,6 +114,18 @@ int build_group_plan(CraCtx* c)
         p.a0 = aoff[s0]; p.a1 = aoff[s1]; p.b0 = boff[s0]; p.b1 = boff[s1]; p.c0 = coff[s0]; p.c1 = coff[s1];
         p.q0 = qoff[nring - s1]; p.q1 = qoff[nring - s0];                   // rings nring-s1 .. nring-1-s0
         for (int uu = u; uu < u1; ++uu) p.upr += unk[uu];
+        auto pick = [](int n, int nr, int setup, int per_row) {
+            int best = 1; long bestc = 1L << 40;
+            for (int sset = 1; sset <= nr; ++sset) {
+                const long cst = (long)((n * sset + 255) / 256) * (setup + (long)((nr + sset - 1) / sset) * per_row);
+                if (cst < bestc) { bestc = cst; best = sset; }
+            }
+            return (unsigned char)best;
+        };
+        for (int nr = 0; nr <= CRA_GRP_RMAX; ++nr) {
+            p.nsetC[nr] = pick(p.c1 - p.c0, std::max(nr, 1), 40, 24);
+            p.nsetD[nr] = pick(p.upr, std::max(nr, 1), 70, 50);
+        }
         p.magicA = magic(p.a1 - p.a0); p.magicB = magic(p.b1 - p.b0); p.magicC = magic(p.c1 - p.c0); p.magicD = magic(p.upr);
         // fastdiv is exact while n * n * CRA_GRP_RMAX < 2^24
         const long worst = std::max({p.a1 - p.a0, p.b1 - p.b0, p.c1 - p.c0, p.upr});
@@ -219,7 +231,7 @@ int build_tables(CraCtx* c)
     cra_ccf_twiddles(t.log2n, twi);
     // flat work lists of the ring FFT passes, longest rings first so that warps stay uniform
     {
-        std::vector<int> A, B, C;
+        std::vector<int> A, B, C, Cg;
         for (int i = nring - 1; i >= 0; --i) {
             const int n = t.len[i] >> 1;
             const int lg = ilog2_floor(n), NA = 1 << (lg / 2), NB = n / NA;
@@ -227,13 +239,16 @@ int build_tables(CraCtx* c)
             for (int b = 0; b < NB; ++b) A.push_back((i << 16) | b);
             for (int a = 0; a < NA; ++a) B.push_back((i << 16) | a);
             for (int k = 0; k <= n / 2; ++k) C.push_back((i << 16) | k);
+            for (int k = 1; k <= n / 2; ++k) Cg.push_back((i << 16) | k);
         }
         std::vector<int> all(A); all.insert(all.end(), B.begin(), B.end()); all.insert(all.end(), C.begin(), C.end());
+        all.insert(all.end(), Cg.begin(), Cg.end());
         CRA_CUDA(cudaMalloc(&c->d_items, sizeof(int) * all.size()));
         CRA_CUDA(cudaMemcpy(c->d_items, all.data(), sizeof(int) * all.size(), cudaMemcpyHostToDevice));
         c->items.A = c->d_items; c->items.nA = (int)A.size();
         c->items.B = c->d_items + A.size(); c->items.nB = (int)B.size();
         c->items.C = c->d_items + A.size() + B.size(); c->items.nC = (int)C.size();
+        c->items.Cg = c->items.C + C.size(); c->items.nCg = (int)Cg.size();
     }
     // model_circle(ou, nx, nx): r^2 <= ou^2 around (nx/2, nx/2)
     std::vector<float> mask((size_t)c->npix);

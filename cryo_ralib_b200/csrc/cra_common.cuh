@@ -50,6 +50,7 @@ struct CraPolarItems {         // flat work lists of the ring FFT passes (device
     const int* A; int nA;      // (ring << 16 | column b)   pass A: NA-point DFTs
     const int* B; int nB;      // (ring << 16 | row ka)     pass B: NB-point DFTs
     const int* C; int nC;      // (ring << 16 | k)          pass C: split + store, k <= len/4
+    const int* Cg; int nCg;    // same without the k = 0 items (grouped row kernel)
 };
 
 // ---- grouped row kernel (cra_polar_grp.cu) -----------------------------------------------------
@@ -58,17 +59,19 @@ struct CraPolarItems {         // flat work lists of the ring FFT passes (device
 #endif
 struct CraPhase {              // one walk of the CTA over a set of consecutive 4-ring units
     int q0, q1;                // quarter-ring sample range in samp[]
-    int a0, a1, b0, b1, c0, c1;// item ranges in CraPolarItems A / B / C
+    int a0, a1, b0, b1, c0, c1;// item ranges in CraPolarItems A / B / Cg
     int u0, u1;                // ring units [u0, u1): unit u = slots 4u..4u+3, slot s <-> ring nring-1-s
-    int upr;                   // pass-D lanes per row = sum over the units of (longest half length + 1)
+    int upr;                   // pass-D lanes per row = sum over the units of their longest half length
     int magicA, magicB, magicC, magicD;   // floor(2^24 / n) + 1 for n = items A, B, C, upr (fastdiv)
-    int pad;
+    // row sets of passes C / D for a block of nr rows: lanes = n * nset, each lane loops ceil(nr/nset) rows;
+    // the value that minimises ceil(n*nset/256) * (lane set-up + ceil(nr/nset) * per-row cost)
+    unsigned char nsetC[CRA_GRP_RMAX + 1], nsetD[CRA_GRP_RMAX + 1];
 };
 struct CraGroupPlan {
     const CraPhase* phases;    // device
     int nphase;
     const int* ppoff;          // [nring] float2 offset of ring i inside its phase's row buffer (device)
-    const int* unit_nk;        // [units] longest half length + 1 of unit u (device)
+    const int* unit_nk;        // [units] longest half length (len/2 of its first slot) of unit u (device)
     int stride;                // floats per row of the phase buffer
     int rmax;                  // rows per CTA (<= CRA_GRP_RMAX), chosen for shared-memory fit
 };

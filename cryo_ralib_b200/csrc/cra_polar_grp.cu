@@ -80,17 +80,6 @@ __device__ __forceinline__ void pass_b(float2* __restrict__ z, int ka)
 // floor(w / d) for w * magic < 2^32, magic = floor(2^24 / d) + 1 (host side, exact for the ranges used here)
 __device__ __forceinline__ int fastdiv(int w, int magic) { return (int)(((unsigned)w * (unsigned)magic) >> 24); }
 
-// row sets that balance "lanes = n * nset, each lane loops ceil(nr / nset) rows" over the CTA
-__device__ __forceinline__ int pick_nset(int n, int nr)
-{
-    int best = 1, bestc = 1 << 30;
-    for (int s = 1; s <= nr; ++s) {
-        const int c = ((n * s + kThreads - 1) / kThreads) * ((nr + s - 1) / s);
-        if (c < bestc) { bestc = c; best = s; }
-    }
-    return best;
-}
-
 __global__ void __launch_bounds__(kThreads, 2)
 polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* __restrict__ tab,
                    const float4* __restrict__ samp, const float2* __restrict__ twid, CraPolarItems items,
@@ -254,76 +243,104 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
         // ---- pass C: real-FFT split in place; index math once per (ring, k), rows inside ---------
         // Z_k of the half-length complex FFT sits at z[(k % NA)*(NB+1) + k / NA];
         // F_k = E_k + w_k O_k, F_{n-k} = conj(E_k - w_k O_k), w_k = exp(-2 pi i k / len);
-        // slot pos(0) <- (F_0, F_n): both real
+        // slot pos(0) <- (F_0, F_n): both real.  Main lanes: k = 1 .. n/2 of every ring (list Cg);
+        // the k = 0 items are a short flat (ring, row) loop.
         {
             const int nC = P.c1 - P.c0;
-            const int nset = pick_nset(nC, nr);
+            const int nset = __ldg(&plan.phases[ph].nsetC[nr]);
             for (int x = tid; x < nC * nset; x += kThreads) {
-                const int set = fastdiv(x, P.magicC), item = __ldg(items.C + P.c0 + (x - set * nC));
+                const int set = fastdiv(x, P.magicC), item = __ldg(items.Cg + P.c0 + (x - set * nC));
                 const int ring = item >> 16, k = item & 0xffff;
                 const int4 rp = s_ring[ring];
                 const int n = rp.z * 2, len = rp.z * 4;
                 const int lb = rp.y, NA = n >> lb, la = 31 - __clz(NA), NB1 = (1 << lb) + 1;
-                const int m = (k == 0) ? 0 : n - k;
+                const int m = n - k;
                 const int pk = rp.x + (k & (NA - 1)) * NB1 + (k >> la), pm = rp.x + (m & (NA - 1)) * NB1 + (m >> la);
                 const float2 wk = s_tw[k * (maxrin / len)];
+                float2* z = reinterpret_cast<float2*>(s_buf + set * stride);
                 for (int r = set; r < nr; r += nset) {
-                    float2* z = reinterpret_cast<float2*>(s_buf + r * stride);
                     const float2 a = z[pk], b = z[pm];
-                    if (k == 0) {
-                        z[pk] = make_float2(a.x + a.y, a.x - a.y);
-                    } else {
-                        const float2 E = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
-                        const float2 O = make_float2(0.5f * (a.y + b.y), -0.5f * (a.x - b.x));
-                        const float2 Pk = cmul(O, wk);
-                        z[pk] = make_float2(E.x + Pk.x, E.y + Pk.y);
-                        if (pm != pk) z[pm] = make_float2(E.x - Pk.x, -(E.y - Pk.y));
-                    }
+                    const float2 E = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
+                    const float2 O = make_float2(0.5f * (a.y + b.y), -0.5f * (a.x - b.x));
+                    const float2 Pk = cmul(O, wk);
+                    z[pk] = make_float2(E.x + Pk.x, E.y + Pk.y);
+                    if (pm != pk) z[pm] = make_float2(E.x - Pk.x, -(E.y - Pk.y));
+                    z += nset * (stride >> 1);
                 }
+            }
+            const int s0 = 4 * P.u0, nsl = min(4 * P.u1, nring) - s0;          // ring slots of the phase
+            for (int x = tid; x < nsl * nr; x += kThreads) {
+                const int r = x / nsl, ring = nring - 1 - (s0 + (x - r * nsl));
+                float2* z = reinterpret_cast<float2*>(s_buf + r * stride) + s_ring[ring].x;
+                const float2 a = z[0];
+                z[0] = make_float2(a.x + a.y, a.x - a.y);
             }
         }
         __syncthreads();
-        // ---- pass D: one (k, unit) per lane, rows inside: gather 4 ring slots, split, store -------
+        // ---- pass D: one (k < longest half length, unit) per lane, rows inside: gather the 4 ring
+        // slots, split to bf16 hi/lo, store the 32-byte unit.  The unit's top frequency (real, only
+        // its longest rings reach it) is a short flat (unit, row) loop.
         {
             const int upr = P.upr;
-            const int nset = pick_nset(upr, nr);
+            const int nset = __ldg(&plan.phases[ph].nsetD[nr]);
             const size_t rb = (size_t)frag.nch * 128;
             for (int x = tid; x < upr * nset; x += kThreads) {
                 const int set = fastdiv(x, P.magicD);
                 int k = x - set * upr, u = P.u0;
                 while (k >= __ldg(plan.unit_nk + u)) { k -= __ldg(plan.unit_nk + u); ++u; }
-                int idx[4], sel[4];                                    // sel: 0 complex, 1 re = .x, 2 re = .y, 3 zero
+                // value of slot j = (v.x * mx + v.y * my, v.y * mi) of z[idx]: complex (1,0,1), F_0 = .x of
+                // pos(0) (1,0,0), F_n = .y of pos(0) (0,1,0), ring too short or absent (0,0,0)
+                int idx[4]; float mx[4], my[4], mi[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int ring = nring - 1 - (4 * u + j);
-                    idx[j] = 0; sel[j] = 3;
+                    idx[j] = 0; mx[j] = 0.f; my[j] = 0.f; mi[j] = 0.f;
                     if (ring >= 0) {
                         const int4 rp = s_ring[ring];
                         const int n = rp.z * 2;
                         if (k <= n) {
                             const int lb = rp.y, NA = n >> lb, la = 31 - __clz(NA);
-                            if (k == 0) { idx[j] = rp.x; sel[j] = 1; }
-                            else if (k == n) { idx[j] = rp.x; sel[j] = 2; }
-                            else { idx[j] = rp.x + (k & (NA - 1)) * ((1 << lb) + 1) + (k >> la); sel[j] = 0; }
+                            idx[j] = rp.x;
+                            if (k == 0) mx[j] = 1.f;
+                            else if (k == n) my[j] = 1.f;
+                            else { idx[j] = rp.x + (k & (NA - 1)) * ((1 << lb) + 1) + (k >> la); mx[j] = 1.f; mi[j] = 1.f; }
                         }
                     }
                 }
                 unsigned char* o = spec + (size_t)(grow0 + set) * rb + (size_t)(__ldg(frag.koff + k) + (u >> 2)) * 128 + (u & 3) * 32;
+                const float2* z = reinterpret_cast<const float2*>(s_buf + set * stride);
                 for (int r = set; r < nr; r += nset) {
-                    const float2* z = reinterpret_cast<const float2*>(s_buf + r * stride);
                     float re[4], im[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float2 v = z[idx[j]];
-                        re[j] = (sel[j] == 3) ? 0.f : ((sel[j] == 2) ? v.y : v.x);
-                        im[j] = (sel[j] == 0) ? v.y : 0.f;
+                        re[j] = fmaf(v.y, my[j], v.x * mx[j]);
+                        im[j] = v.y * mi[j];
                     }
                     uint4 hi, lo;
                     split_row_unit(re, im, hi, lo);
                     uint4* o4 = reinterpret_cast<uint4*>(o);
                     o4[0] = hi; o4[1] = lo;
                     o += (size_t)nset * rb;
+                    z += nset * (stride >> 1);
                 }
+            }
+            const int nu = P.u1 - P.u0;
+            for (int x = tid; x < nu * nr; x += kThreads) {
+                const int r = x / nu, u = P.u0 + (x - r * nu);
+                const int k = __ldg(plan.unit_nk + u);                         // the unit's longest half length
+                const float2* z = reinterpret_cast<const float2*>(s_buf + r * stride);
+                float re[4], im[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int ring = nring - 1 - (4 * u + j);
+                    re[j] = 0.f; im[j] = 0.f;
+                    if (ring >= 0) { const int4 rp = s_ring[ring]; if (rp.z * 2 == k) re[j] = z[rp.x].y; }
+                }
+                uint4 hi, lo;
+                split_row_unit(re, im, hi, lo);
+                uint4* o4 = reinterpret_cast<uint4*>(spec + (size_t)(grow0 + r) * rb + (size_t)(__ldg(frag.koff + k) + (u >> 2)) * 128 + (u & 3) * 32);
+                o4[0] = hi; o4[1] = lo;
             }
         }
         __syncthreads();
