@@ -142,7 +142,7 @@ int build_group_plan(CraCtx* c)
     cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     auto fits = [&](int rmax, int ncta) {
         CraGroupPlan q = c->plan; q.rmax = rmax;
-        const size_t need = cra_polar_group_smem(c->nx, t.maxrin, q) + 5400;   // + static shared + 1 KB reserved per CTA
+        const size_t need = cra_polar_group_smem(c->nx, t.maxrin, q) + 6200;   // + static shared + 1 KB reserved per CTA
         return need <= (size_t)smem_blk && need * ncta <= (size_t)smem_sm;
     };
     int rmax = 0;
@@ -483,9 +483,10 @@ extern "C" int cra_align(CraCtx* c, int start, int stop, const CraSearch* search
     std::vector<char> bgroup(nb, 0);
     memcpy(h_search, search, (size_t)n * sizeof(CraSearch));
     long total_rows = 0;
-    // the grouped row kernel needs a whole-pixel step and every 3x3 tap neighbourhood inside the frame
+    // the grouped row kernel needs a whole-pixel step and every sample in [1, nx + 1) (its tile has a
+    // one-pixel periodic border; search_range keeps samples in [2, nx])
     const bool group_cfg = c->fmt == CRA_FMT_FRAG && c->use_group && c->plan.rmax > 0 && step == floorf(step) && step < 1024.f;
-    const float rmaxf = (float)c->htab.rad[c->htab.nring - 1], lo_ok = 2.0f + rmaxf, hi_ok = (float)(c->nx - 1) - rmaxf;
+    const float rmaxf = (float)c->htab.rad[c->htab.nring - 1], lo_ok = 1.0f + rmaxf, hi_ok = (float)c->nx + 0.5f - rmaxf;
     for (size_t bi = 0; bi < nb; ++bi) {
         int* rs = h_rs + bfirst[bi] + bi;
         int* cs = h_cs + bfirst[bi] + bi;

@@ -31,11 +31,17 @@ namespace {
 
 constexpr int kWarps = 16;
 constexpr int kThreads = kWarps * 32;
-constexpr int kMaxItems = 320;          // chunk items per warp (constant memory)
+constexpr int kMaxItems = 320;
+constexpr int kPfDist = 40;             // row blocks between an L2 prefetch and its use (~148 CTAs in flight / tiles per block)          // chunk items per warp (constant memory)
 
-// per-warp work lists: gc | k << 13 | last << 23   (gc = chunk index within a row)
-__constant__ int c_items[kWarps][kMaxItems];
-__constant__ int c_nitems[kWarps];
+// per-warp work lists: gc | last << 23   (gc = chunk index within a row); the frequencies a warp
+// completes, in order, as packed shared-memory positions of W[k] and W[N-k]: i0 | i1 << 12 | (k != 0, N/2) << 24
+constexpr int kMaxFreq = 64;
+// The lists live in global memory and are staged in shared memory by every CTA: a register-indexed
+// constant load (LDC) per chunk stalled the warps for ~40 % of the contraction (ncu, round 1).
+__device__ int g_items[kWarps][kMaxItems];
+__device__ int g_nitems[kWarps];
+__device__ int g_flush[kWarps][kMaxFreq];
 
 using crafft::fft_reg;
 
@@ -83,13 +89,15 @@ template <int LOG2N>
 __global__ void __launch_bounds__(kThreads, 1)
 ccf_mma_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned char* __restrict__ refspec, int R,
                size_t row_bytes, const float2* __restrict__ twid, CraCand* __restrict__ cand,
-               int nquad, int ncta_n, const float2* __restrict__ norm, const float* __restrict__ tref, int exp_flags)
+               int nquad, int ncta_n, const float2* __restrict__ norm, const float* __restrict__ tref, int istride, int fstride)
 {
     using S = MShape<LOG2N>;
     constexpr int N = S::N, N1 = S::N1, N2 = S::N2, PS = S::PS, NJ = S::NJ, RS = S::RS, ROWS = S::ROWS, NP = S::NP;
     extern __shared__ __align__(16) float2 s_dyn[];
     float2* s_w = s_dyn;                      // NP * PS
     float2* s_tw = s_dyn + NP * PS;           // N : s_tw[j*N2 + n2] = exp(+2 pi i n2 j / N)
+    int* s_items = reinterpret_cast<int*>(s_tw + N);            // kWarps * istride chunk items
+    int* s_flush = s_items + kWarps * istride;                  // kWarps * fstride completed frequencies
     __shared__ CraCand s_pair[NP];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -101,9 +109,26 @@ ccf_mma_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned
     const int q0 = cn * qbase + min(cn, qrem);
     const int row0 = cm * ROWS;
     for (int i = tid; i < N; i += kThreads) s_tw[i] = twid[i];
+    {
+        const int nit = g_nitems[warp];
+        for (int i = lane; i < nit; i += 32) s_items[warp * istride + i] = g_items[warp][i];
+        for (int i = lane; i < fstride; i += 32) s_flush[warp * fstride + i] = g_flush[warp][i];
+        __syncwarp();
+    }
 
+    // The row spectra were written by the row kernel a whole batch ago and sit in HBM: the first
+    // reference tile of a row block pulls the block that will be needed kPfDist blocks later into L2.
+    if (cn == 0) {
+        const long r0 = (long)(cm + kPfDist) * ROWS;
+        if (r0 < nrows) {
+            const long r1 = min((long)nrows, r0 + ROWS);
+            const unsigned char* p0 = spec + (size_t)r0 * row_bytes;
+            const size_t nline = (size_t)(r1 - r0) * row_bytes / 128;
+            for (size_t i = tid; i < nline; i += kThreads)
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(p0 + i * 128));
+        }
+    }
     // ---- contraction: this warp's frequencies, chunk by chunk ---------------------------------
-    if (!(exp_flags & 8))
     // All NJ quads are always multiplied (a tile with fewer live quads re-reads its quad 0; the
     // dead pair slots are skipped by the FFT passes below): no predication around the MMAs.
     {
@@ -116,60 +141,54 @@ ccf_mma_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned
             const int jj = (j < nj) ? j : 0;
             pb[j] = refspec + (size_t)(4 * (q0 + jj) + (g >> 1)) * row_bytes + t * 32 + (g & 1) * 16;
         }
-        float acc_h[NJ][4], acc_l[NJ][4];
+        float acc[NJ][4];
 #pragma unroll
         for (int j = 0; j < NJ; ++j)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { acc_h[j][e] = 0.f; acc_l[j][e] = 0.f; }
+            for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
 
-        const int nit = c_nitems[warp];
-        const int* items = c_items[warp];
+        const int nit = g_nitems[warp];
+        const int* items = s_items + warp * istride;
+        const int* fl = s_flush + warp * fstride;
+        const bool wr = (ROWS == 8) || (g < 4);
+        float2* const wbase = s_w + (g * RS + t) * PS;
 
+        // a.b ~= a_hi b_lo + a_lo b_hi + a_hi b_hi, small terms first, one FP32 accumulator
 #define CRA_LOAD_OPS(O, item)                                                            \
         { const size_t off_ = (size_t)((item) & 8191) * 128;                             \
-          if (!(exp_ & 2)) O.a = ldg256(pa + off_);                                      \
-          if (!(exp_ & 1)) { _Pragma("unroll") for (int j_ = 0; j_ < NJ; ++j_)           \
-              O.b[j_] = __ldg(reinterpret_cast<const uint4*>(pb[j_] + off_)); } }
+          O.a = ldg256(pa + off_);                                                       \
+          _Pragma("unroll") for (int j_ = 0; j_ < NJ; ++j_)                              \
+              O.b[j_] = __ldg(reinterpret_cast<const uint4*>(pb[j_] + off_)); }
 #define CRA_COMPUTE(O, item)                                                             \
-        { _Pragma("unroll") for (int j_ = 0; j_ < NJ; ++j_) {                            \
-              mma_bf16(acc_l[j_], O.a.w[0], O.a.w[1], O.a.w[2], O.a.w[3], O.b[j_].z, O.b[j_].w);   /* a_hi b_lo */ \
-              mma_bf16(acc_l[j_], O.a.w[4], O.a.w[5], O.a.w[6], O.a.w[7], O.b[j_].x, O.b[j_].y);   /* a_lo b_hi */ \
-              mma_bf16(acc_h[j_], O.a.w[0], O.a.w[1], O.a.w[2], O.a.w[3], O.b[j_].x, O.b[j_].y);   /* a_hi b_hi */ \
-          }                                                                              \
-          if ((item) >> 23) flush_freq(((item) >> 13) & 1023); }
+        { _Pragma("unroll") for (int j_ = 0; j_ < NJ; ++j_)                              \
+              mma_bf16(acc[j_], O.a.w[0], O.a.w[1], O.a.w[2], O.a.w[3], O.b[j_].z, O.b[j_].w);   /* a_hi b_lo */ \
+          _Pragma("unroll") for (int j_ = 0; j_ < NJ; ++j_)                              \
+              mma_bf16(acc[j_], O.a.w[4], O.a.w[5], O.a.w[6], O.a.w[7], O.b[j_].x, O.b[j_].y);   /* a_lo b_hi */ \
+          _Pragma("unroll") for (int j_ = 0; j_ < NJ; ++j_)                              \
+              mma_bf16(acc[j_], O.a.w[0], O.a.w[1], O.a.w[2], O.a.w[3], O.b[j_].x, O.b[j_].y);   /* a_hi b_hi */ \
+          if ((item) >> 23) flush_freq(); }
 
-        auto flush_freq = [&](int k) {
-            const int kk = (N - k) & (N - 1);
-            const int i0 = (k >> S::L2) * (N2 + 1) + (k & (N2 - 1));
-            const int i1 = (kk >> S::L2) * (N2 + 1) + (kk & (N2 - 1));
-            const bool wr = (ROWS == 8) || (g < 4);
-            const bool two = (k != 0 && k != N / 2);
-            float2* w = s_w + (g * RS + t) * PS;
+        auto flush_freq = [&]() {
+            const int f = *fl++;
+            const int i0 = f & 4095, i1 = (f >> 12) & 4095;
+            const bool two = (f >> 24) != 0;
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
                 // c0 = A (re.re), c1 = D (row re . ref im), c2 = C (row im . ref re), c3 = B (im.im)
-                const float A = acc_h[j][0] + acc_l[j][0], D = acc_h[j][1] + acc_l[j][1];
-                const float C = acc_h[j][2] + acc_l[j][2], B = acc_h[j][3] + acc_l[j][3];
+                const float A = acc[j][0], D = acc[j][1], C = acc[j][2], B = acc[j][3];
                 // s = (A+B, A-B), tv = (C+D, D-C);  W[k] = s + tv,  W[N-k] = s - tv
                 const float sx = A + B, sy = A - B, tx = C + D, ty = D - C;
                 if (wr) {
-                    w[4 * j * PS + i0] = make_float2(sx + tx, sy + ty);
-                    if (two) w[4 * j * PS + i1] = make_float2(sx - tx, sy - ty);
+                    wbase[4 * j * PS + i0] = make_float2(sx + tx, sy + ty);
+                    if (two) wbase[4 * j * PS + i1] = make_float2(sx - tx, sy - ty);
                 }
 #pragma unroll
-                for (int e = 0; e < 4; ++e) { acc_h[j][e] = 0.f; acc_l[j][e] = 0.f; }
+                for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
             }
         };
 
         // three operand sets rotate: two chunk loads are always in flight behind the one being multiplied
         Operands<NJ> o0, o1, o2;
-        const int exp_ = exp_flags;
-        if (exp_) {   // timing experiments only (CRA_EXP): operands preloaded once, then partly reused
-            const int e_ = 0;
-            o0.a = ldg256(pa); o1.a = o0.a; o2.a = o0.a;
-            _Pragma("unroll") for (int j_ = 0; j_ < NJ; ++j_) { o0.b[j_] = __ldg(reinterpret_cast<const uint4*>(pb[j_])); o1.b[j_] = o0.b[j_]; o2.b[j_] = o0.b[j_]; }
-            (void)e_;
-        }
         if (nit > 0) CRA_LOAD_OPS(o0, items[0]);
         if (nit > 1) CRA_LOAD_OPS(o1, items[1]);
         for (int i = 0; i < nit; i += 3) {
@@ -189,9 +208,6 @@ ccf_mma_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned
 #undef CRA_COMPUTE
     }
     __syncthreads();
-    if (exp_flags & 4) return;
-    if (exp_flags & 8) {      // timing experiment: skip the contraction's W (stale shared memory is transformed)
-    }
 
     // ---- inverse FFT of every pair, pass 1: (pair, n2): N1-point DFT over n1, twiddle ----------
     const int npr = 4 * nj;                   // live pair slots per row
@@ -267,7 +283,7 @@ ccf_mma_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned
     }
 }
 
-struct Sched { std::vector<int> koff; int nring = -1, maxrin = -1, dev = -1; std::vector<int> len; };
+struct Sched { std::vector<int> koff; int nring = -1, maxrin = -1, dev = -1, istride = 0, fstride = 0; std::vector<int> len; };
 Sched g_sched;
 
 // Balance the frequencies over the warps (longest-processing-time first) and upload the lists.
@@ -277,7 +293,7 @@ int bind_schedule(const CraRingTab& h, const std::vector<int>& koff, cudaStream_
     std::vector<int> len(h.len, h.len + h.nring);
     if (g_sched.nring == h.nring && g_sched.maxrin == h.maxrin && g_sched.dev == dev && g_sched.len == len) return 0;
     const int nk = h.maxrin / 2 + 1;
-    std::vector<std::vector<int>> lists(kWarps);
+    std::vector<std::vector<int>> lists(kWarps), freqs(kWarps);
     std::vector<int> load(kWarps, 0);
     int maxc = 0;
     for (int k = 0; k < nk; ++k) maxc = std::max(maxc, koff[k + 1] - koff[k]);
@@ -286,19 +302,33 @@ int bind_schedule(const CraRingTab& h, const std::vector<int>& koff, cudaStream_
             if (koff[k + 1] - koff[k] != c) continue;
             int w = 0;
             for (int i = 1; i < kWarps; ++i) if (load[i] < load[w]) w = i;
-            for (int j = 0; j < c; ++j) lists[w].push_back((koff[k] + j) | (k << 13) | ((j == c - 1) ? (1 << 23) : 0));
+            for (int j = 0; j < c; ++j) lists[w].push_back((koff[k] + j) | ((j == c - 1) ? (1 << 23) : 0));
+            freqs[w].push_back(k);
             load[w] += c;
         }
     static int h_items[kWarps][kMaxItems]; int h_n[kWarps];
-    memset(h_items, 0, sizeof(h_items));
+    static int h_flush[kWarps][kMaxFreq];
+    memset(h_items, 0, sizeof(h_items)); memset(h_flush, 0, sizeof(h_flush));
+    const int L2 = h.log2n - h.log2n / 2, N2 = 1 << L2, N = h.maxrin;       // MShape: k -> (k >> L2) * (N2 + 1) + (k & (N2 - 1))
     for (int w = 0; w < kWarps; ++w) {
-        if ((int)lists[w].size() > kMaxItems || koff[nk] > 8191 || nk > 1024) { cra_set_error("ring table too large for the tensor-core CCF schedule"); return 1; }
+        if ((int)lists[w].size() > kMaxItems || (int)freqs[w].size() > kMaxFreq || koff[nk] > 8191 || nk > 1024) { cra_set_error("ring table too large for the tensor-core CCF schedule"); return 1; }
         h_n[w] = (int)lists[w].size();
         for (size_t i = 0; i < lists[w].size(); ++i) h_items[w][i] = lists[w][i];
+        for (size_t i = 0; i < freqs[w].size(); ++i) {
+            const int k = freqs[w][i], kk = (N - k) & (N - 1);
+            const int i0 = (k >> L2) * (N2 + 1) + (k & (N2 - 1)), i1 = (kk >> L2) * (N2 + 1) + (kk & (N2 - 1));
+            h_flush[w][i] = i0 | (i1 << 12) | ((k != 0 && k != N / 2) ? (1 << 24) : 0);
+        }
     }
     CRA_CUDA(cudaStreamSynchronize(st));
-    CRA_CUDA(cudaMemcpyToSymbol(c_items, h_items, sizeof(h_items)));
-    CRA_CUDA(cudaMemcpyToSymbol(c_nitems, h_n, sizeof(h_n)));
+    CRA_CUDA(cudaMemcpyToSymbol(g_items, h_items, sizeof(h_items)));
+    CRA_CUDA(cudaMemcpyToSymbol(g_nitems, h_n, sizeof(h_n)));
+    CRA_CUDA(cudaMemcpyToSymbol(g_flush, h_flush, sizeof(h_flush)));
+    g_sched.istride = 0; g_sched.fstride = 0;
+    for (int w = 0; w < kWarps; ++w) {
+        g_sched.istride = std::max(g_sched.istride, (int)lists[w].size());
+        g_sched.fstride = std::max(g_sched.fstride, (int)freqs[w].size());
+    }
     g_sched.nring = h.nring; g_sched.maxrin = h.maxrin; g_sched.dev = dev; g_sched.len = len;
     return 0;
 }
@@ -308,18 +338,18 @@ int launch_t(const unsigned char* spec, int nrows, const unsigned char* refspec,
              const float2* twid, CraCand* cand, int ntile_n, const float2* norm, const float* tref, cudaStream_t st)
 {
     using S = MShape<LOG2N>;
-    const size_t smem = ((size_t)S::NP * S::PS + S::N) * sizeof(float2);
-    static bool configured = false;
-    if (!configured) {
+    const size_t smem = ((size_t)S::NP * S::PS + S::N) * sizeof(float2) + (size_t)kWarps * (g_sched.istride + g_sched.fstride) * sizeof(int);
+    static size_t configured = 0;
+    if (smem > configured) {
         CRA_CUDA(cudaFuncSetAttribute(ccf_mma_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured = smem;
     }
     const int nquad = (R + 3) / 4;
     const long ncta_m = (nrows + S::ROWS - 1) / S::ROWS;
     const long nblk = ncta_m * ntile_n;
     if (nblk <= 0) return 0;
     if (nblk > 2147483647L) { cra_set_error("ccf grid too large; lower row_batch"); return 1; }
-    ccf_mma_kernel<LOG2N><<<(unsigned)nblk, kThreads, smem, st>>>(spec, nrows, refspec, R, row_bytes, twid, cand, nquad, ntile_n, norm, tref, getenv("CRA_EXP") ? atoi(getenv("CRA_EXP")) : 0);
+    ccf_mma_kernel<LOG2N><<<(unsigned)nblk, kThreads, smem, st>>>(spec, nrows, refspec, R, row_bytes, twid, cand, nquad, ntile_n, norm, tref, g_sched.istride, g_sched.fstride);
     CRA_CUDA(cudaGetLastError());
     return 0;
 }

@@ -15,8 +15,10 @@
 //   -> real-FFT split (index math shared by the rows) -> split-bf16 + 32-byte unit stores.
 // Normalize_ring is deferred (cra_common.cuh): the spectrum of the raw polar image is stored and
 // (avg, 1/sigma) goes to norm[row]; the CCF kernel applies it when it emits a candidate.
-// Requirements checked by the host (cra_api.cu): integral step, every 3x3 neighbourhood inside
-// the frame (always true under search_range); otherwise the general kernel of cra_polar.cu runs.
+// The shared-memory tile carries a one-pixel periodic border (quadri's circular closure), so any
+// sample with 1 <= x, y < nx + 1 needs no wrap logic; search_range keeps every sample in [2, nx].
+// Requirements checked by the host (cra_api.cu): integral step and that sample range; otherwise
+// the general kernel of cra_polar.cu runs.
 #include "cra_common.cuh"
 #include "cra_fft.cuh"
 #include <cuda_bf16.h>
@@ -28,6 +30,7 @@ using crafft::fft_reg;
 
 constexpr int kThreads = 256;
 constexpr int RMAX = CRA_GRP_RMAX;
+constexpr int kFragCap = 128;   // beyond it a sample keeps its shared-weight value (never seen: <1 expected per phase)
 
 __device__ __forceinline__ float warp_sum(float v)
 {
@@ -90,11 +93,16 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
     const int npix = nx * nx;
     const int maxrin = tab->maxrin, nring = tab->nring;
     const int stride = plan.stride;                            // floats per row of the phase buffer
-    float* s_img = smem;                                       // npix (padded to 4)
-    float* s_buf = smem + ((npix + 3) & ~3);                   // rmax * stride
+    const int pitch = nx + 2;                                  // tile with a one-pixel periodic border
+    float* s_img = smem;                                       // pitch * pitch (padded to 4)
+    float* s_buf = smem + ((pitch * pitch + 3) & ~3);          // rmax * stride
     float2* s_tw = reinterpret_cast<float2*>(s_buf + plan.rmax * stride);   // maxrin : exp(-2 pi i j / maxrin)
     __shared__ float s_red[kThreads / 32][2 * RMAX];
     __shared__ int s_rowoff[RMAX];
+    __shared__ float2 s_rowc[RMAX];
+    __shared__ float s_fix[2 * RMAX];
+    __shared__ int s_frag[kFragCap];                           // queued fragile samples of the phase: q * 4 + m
+    __shared__ int s_nfrag;                          // Normalize_ring sum corrections of the fragile samples                            // the reference's own centre of every row
     __shared__ int s_blk[4];                                   // particle (batch local), first local row, rows
     __shared__ float s_base[2];
     __shared__ int4 s_ring[CRA_MAX_RINGS];                     // phase-local float2 offset, log2 NB, len/4, wn
@@ -116,10 +124,14 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
         s_base[1] = map.search[lo].cy - (float)w.z * map.step;
         for (int r = 0; r < r_hi - r_lo; ++r) {
             const int li = r_lo + r;
-            s_rowoff[r] = (li / wx) * istep * nx + (li % wx) * istep;
+            s_rowoff[r] = (li / wx) * istep * pitch + (li % wx) * istep;
+            s_rowc[r] = make_float2(map.search[lo].cx + (float)(li % wx - w.x) * map.step,
+                                    map.search[lo].cy + (float)(li / wx - w.z) * map.step);
         }
     }
     for (int i = tid; i < maxrin; i += kThreads) s_tw[i] = twid[i];
+    if (tid < 2 * RMAX) s_fix[tid] = 0.f;
+    if (tid == 0) s_nfrag = 0;
     for (int i = tid; i < nring; i += kThreads) {
         const int n = tab->len[i] >> 1, lg = 31 - __clz(n);
         s_ring[i] = make_int4(__ldg(plan.ppoff + i), lg - (lg >> 1), tab->len[i] >> 2, __float_as_int(tab->wn[i]));
@@ -128,13 +140,16 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
     const int nr = s_blk[2];
     const int grow0 = s_blk[3];                                // first row of this block in the batch
     {
+        // padded (Y, X), 0 <= X, Y <= nx+1, holds pixel ((Y-1) mod nx, (X-1) mod nx): 1-based pixel (i, j) sits at (j, i)
         const float* img = images + (size_t)(map.p0 + s_blk[0]) * npix;
-        if ((npix & 3) == 0) {
-            const float4* g4 = reinterpret_cast<const float4*>(img);
-            float4* s4 = reinterpret_cast<float4*>(s_img);
-            for (int i = tid; i < (npix >> 2); i += kThreads) s4[i] = __ldg(g4 + i);
-        } else {
-            for (int i = tid; i < npix; i += kThreads) s_img[i] = __ldg(img + i);
+        for (int Y = tid >> 5; Y < pitch; Y += kThreads / 32) {
+            const int sy = (Y == 0) ? nx - 1 : ((Y == nx + 1) ? 0 : Y - 1);
+            const float* src = img + sy * nx;
+            float* dst = s_img + Y * pitch;
+            for (int X = tid & 31; X < pitch; X += 32) {
+                const int sx = (X == 0) ? nx - 1 : ((X == nx + 1) ? 0 : X - 1);
+                dst[X] = __ldg(src + sx);
+            }
         }
     }
     const float bx = s_base[0], by = s_base[1];
@@ -154,6 +169,8 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
             const float ox[4] = {e.x, e.y, -e.x, -e.y}, oy[4] = {e.y, -e.x, -e.y, e.x};
             float w0[4], w1[4], w2[4], w3[4], w4[4], w5[4];
             int pix[4], slot[4];
+            int fragile = 0;       // samples so close to a pixel boundary that float rounding of the per-row
+                                   // position (x = offset + centre, as Polar2Dm forms it) could pick another cell
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
                 const int j = jt + m * rp.z, p = j >> 1;
@@ -161,6 +178,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                 const float X = ox[m] + bx, Y = oy[m] + by;
                 const int ix = (int)X, iy = (int)Y;
                 const float dx = X - (float)ix, dy = Y - (float)iy;
+                if (dx < 1e-4f || dx > 0.9999f || dy < 1e-4f || dy > 0.9999f) fragile |= 1 << m;
                 // quadri: f0 + dx (c1 + (dx-1) c2 + dy c5) + dy (c3 + (dy-1) c4) as six tap weights
                 const float a2 = 0.5f * dx * (dx - 1.0f), b2 = 0.5f * dy * (dy - 1.0f), ab = dx * dy;
                 w1[m] = dx + a2 - ab;          // (i+1, j)
@@ -169,7 +187,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                 w4[m] = b2;                    // (i, j-1)
                 w5[m] = ab;                    // (i+1, j+1)
                 w0[m] = 1.0f - dx - dy - 2.0f * a2 - 2.0f * b2 + ab;
-                pix[m] = (iy - 1) * nx + (ix - 1);
+                pix[m] = iy * pitch + ix;
             }
 #pragma unroll
             for (int r = 0; r < RMAX; ++r) {
@@ -183,14 +201,53 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                         float v = w0[m] * p[0];
                         v = fmaf(w1[m], p[1], v);
                         v = fmaf(w2[m], p[-1], v);
-                        v = fmaf(w3[m], p[nx], v);
-                        v = fmaf(w4[m], p[-nx], v);
-                        v = fmaf(w5[m], p[nx + 1], v);
+                        v = fmaf(w3[m], p[pitch], v);
+                        v = fmaf(w4[m], p[-pitch], v);
+                        v = fmaf(w5[m], p[pitch + 1], v);
                         dst[slot[m]] = v;
                         s1 += v; s2 = fmaf(v, v, s2);
                     }
                     av[r] = fmaf(s1, wn, av[r]); sq[r] = fmaf(s2, wn, sq[r]);
                 }
+            }
+            if (fragile) {         // rare: queue those samples; the CTA redoes them together below
+#pragma unroll
+                for (int m = 0; m < 4; ++m)
+                    if (fragile & (1 << m)) {
+                        const int at = atomicAdd(&s_nfrag, 1);
+                        if (at < kFragCap) s_frag[at] = q * 4 + m;
+                    }
+            }
+        }
+        __syncthreads();
+        // ---- fragile samples, row by row exactly as the reference positions them (x = offset + centre) ----
+        {
+            const int nf = min(s_nfrag, kFragCap);
+            for (int x = tid; x < nf * nr; x += kThreads) {
+                const int en = x / nr, r = x - en * nr;
+                const int code = s_frag[en], q = code >> 2, m = code & 3;
+                const float4 e = __ldg(samp + q);
+                const int4 rp = s_ring[__float_as_int(e.z)];
+                const float wn = __int_as_float(rp.w);
+                const float fx = (m == 0) ? e.x : (m == 1) ? e.y : (m == 2) ? -e.x : -e.y;
+                const float fy = (m == 0) ? e.y : (m == 1) ? -e.x : (m == 2) ? -e.y : e.x;
+                const int j = __float_as_int(e.w) + m * rp.z, pp = j >> 1;
+                const int sl = 2 * (rp.x + pp + (pp >> rp.y)) + (j & 1);
+                const float2 c = s_rowc[r];
+                const float X = fx + c.x, Y = fy + c.y;
+                const int ix = (int)X, iy = (int)Y;
+                const float dx = X - (float)ix, dy = Y - (float)iy;
+                const float* p = s_img + iy * pitch + ix;
+                const float f0 = p[0];
+                const float c1 = p[1] - f0, c2 = (c1 - f0 + p[-1]) * 0.5f;
+                const float c3 = p[pitch] - f0, c4 = (c3 - f0 + p[-pitch]) * 0.5f;
+                const float c5 = p[pitch + 1] - f0 - c1 - c3;
+                const float v = f0 + dx * (c1 + (dx - 1.0f) * c2 + dy * c5) + dy * (c3 + (dy - 1.0f) * c4);
+                float* dst = s_buf + r * stride;
+                const float old = dst[sl];
+                dst[sl] = v;
+                atomicAdd(&s_fix[2 * r], (v - old) * wn);
+                atomicAdd(&s_fix[2 * r + 1], (v * v - old * old) * wn);
             }
         }
         __syncthreads();
@@ -343,6 +400,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                 o4[0] = hi; o4[1] = lo;
             }
         }
+        if (tid == 0) s_nfrag = 0;             // read above before two barriers, next written after this phase's last one
         __syncthreads();
     }
 
@@ -357,7 +415,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
     if (tid < nr) {
         float avg = 0.f, isg = 1.f;
         if (normalize_ring) {
-            float a = 0.f, s = 0.f;
+            float a = s_fix[2 * tid], s = s_fix[2 * tid + 1];
 #pragma unroll
             for (int w = 0; w < kThreads / 32; ++w) { a += s_red[w][2 * tid]; s += s_red[w][2 * tid + 1]; }
             const float nn = tab->nn;
@@ -372,7 +430,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
 
 size_t cra_polar_group_smem(int nx, int maxrin, const CraGroupPlan& plan)
 {
-    const size_t npix = ((size_t)nx * nx + 3) & ~(size_t)3;
+    const size_t npix = ((size_t)(nx + 2) * (nx + 2) + 3) & ~(size_t)3;     // tile with the periodic border
     return (npix + (size_t)plan.rmax * plan.stride) * sizeof(float) + (size_t)maxrin * sizeof(float2);
 }
 
