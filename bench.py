@@ -215,15 +215,29 @@ def main():
     goff = rank * P
     params0 = np.zeros((P, 4))
 
+    NCHUNK = 8        # e2e: the stack is uploaded in chunks on the copy stream, each aligned as soon as it landed
+    bounds = [al.mpi_start_end(P, NCHUNK, i) for i in range(NCHUNK)]
+    bounds = [(s, e) for s, e in bounds if e > s]
+
     def step(resident, params):
         """One iteration of the per-particle section; returns (new params, assign, stats)."""
         if not resident:
-            eng.upload_particles_ptr(host_images.data_ptr(), P, subtract_mask_mean=True)
+            base = host_images.data_ptr()
+            for s, e in bounds:
+                eng.upload_particles_async(base + s * nx * nx * 4, e - s, first=s, subtract_mask_mean=True)
         eng.set_refs(refs, normalize_mask=True)
         search, sxi, syi, params = al.mref_search_request(params, nx, ou, xr, yr)
-        res = eng.align(0, P, search)
+        if resident:
+            res = eng.align(0, P, search)
+            st = eng.stats()
+        else:
+            parts, st = [], None
+            for s, e in bounds:
+                parts.append(eng.align(s, e, search[s:e]))
+                t = eng.stats()
+                st = t if st is None else {k: st[k] + t[k] for k in st}
+            res = np.concatenate(parts)
         newp = al.compose_result(sxi, syi, res)
-        st = eng.stats()
         eng.zero_sums()
         eng.accumulate(0, P, newp, res["iref"], goff)
         if world > 1:

@@ -10,7 +10,7 @@ import math
 
 import numpy as np
 
-from .lib import SEARCH_DTYPE
+from .lib import SEARCH_DTYPE, RESULT_DTYPE
 
 f32 = np.float32
 
@@ -98,9 +98,32 @@ def inverse_transform2(alpha, tx=0.0, ty=0.0, mirror=0):
     return _params(r.astype(f32))
 
 
-def mref_search_request(params, nx, ou, xr, yr):
+def _native():
+    """The C-ABI library's batched versions of the two per-particle bookkeeping steps
+    (csrc/cra_host.cu), or None when the library has not been built."""
+    try:
+        from .lib import load_library
+        return load_library()
+    except Exception:
+        return None
+
+
+def mref_search_request(params, nx, ou, xr, yr, native=True):
     """test_mref.py:184-198 for every particle.  params [P][4] (alpha, sx, sy, mirror), float64.
-    Returns (search array, sxi, syi, params possibly reset to zero)."""
+    Returns (search array, sxi, syi, params possibly reset to zero).  Runs in the native library
+    (cra_mref_search_request) when it is loadable; the numpy body below is the same arithmetic and
+    the one the golden Transform tests pin."""
+    L = _native() if native else None
+    if L is not None:
+        params = np.array(params, np.float64, order="C").reshape(-1, 4)
+        n = params.shape[0]
+        s = np.zeros(n, SEARCH_DTYPE)
+        sxi = np.zeros(n, np.float64)
+        syi = np.zeros(n, np.float64)
+        if L.cra_mref_search_request(n, params.ctypes.data, int(nx), int(ou), float(xr), float(yr),
+                                     s.ctypes.data, sxi.ctypes.data, syi.ctypes.data) != 0:
+            raise RuntimeError(L.cra_last_error().decode())
+        return s, sxi, syi, params
     params = np.array(params, np.float64)
     cnx = nx // 2 + 1
     mashi = cnx - ou - 2
@@ -136,8 +159,17 @@ def reffree_search_request(params, cs, nx, ou, xr, yr):
     return s, sxi, syi
 
 
-def compose_result(sxi, syi, res):
+def compose_result(sxi, syi, res, native=True):
     """test_mref.py:206: combine_params2(0,-sxi,-syi,0, ang,sxs,sys,mirror) -> [P][4] float64."""
+    L = _native() if native else None
+    if L is not None and res.dtype == RESULT_DTYPE:
+        sxi = np.ascontiguousarray(sxi, np.float64)
+        syi = np.ascontiguousarray(syi, np.float64)
+        res = np.ascontiguousarray(res)
+        out = np.zeros((res.shape[0], 4), np.float64)
+        if L.cra_compose_result(res.shape[0], sxi.ctypes.data, syi.ctypes.data, res.ctypes.data, out.ctypes.data) != 0:
+            raise RuntimeError(L.cra_last_error().decode())
+        return out
     z = np.zeros_like(sxi)
     a, sx, sy, m = combine_params2(z, -sxi, -syi, z.astype(int), res["ang"].astype(np.float64),
                                    res["sxs"].astype(np.float64), res["sys"].astype(np.float64), res["mirror"])

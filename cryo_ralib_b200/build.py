@@ -10,11 +10,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libcryo_ralib.so")
-SOURCES = ["cra_api.cu", "cra_polar.cu", "cra_polar_grp.cu", "cra_ccf.cu", "cra_ccf_mma.cu", "cra_ccf_rr.cu", "cra_rotsum.cu", "cra_compat.cu"]
+SOURCES = ["cra_api.cu", "cra_polar.cu", "cra_polar_grp.cu", "cra_ccf.cu", "cra_ccf_mma.cu", "cra_ccf_rr.cu", "cra_rotsum.cu", "cra_compat.cu", "cra_host.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 EXTRA = os.environ.get("CRA_NVCC_EXTRA", "").split()
 FLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-Xcompiler", "-fopenmp", "-ccbin", "/usr/bin/g++"]
 
 
 def _stale():
@@ -42,7 +42,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed on %s" % s)
-    cmd = [NVCC, "-shared", "-o", SO] + objs + ["-ccbin", "/usr/bin/g++", "-lcudart"]
+    cmd = [NVCC, "-shared", "-o", SO] + objs + ["-ccbin", "/usr/bin/g++", "-lcudart", "-lgomp"]
     subprocess.check_call(cmd)
     return SO
 

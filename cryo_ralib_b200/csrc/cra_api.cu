@@ -19,6 +19,10 @@ struct CraCtx {
     CraConfig cfg{};
     int device = 0;
     cudaStream_t st = nullptr;
+    cudaStream_t st_copy = nullptr;                            // asynchronous particle uploads
+    struct Pending { int first, n; cudaEvent_t ev; };
+    std::vector<Pending> pending;                              // uploads not yet ordered before the main stream
+    std::vector<cudaEvent_t> ev_pool;
     int nx = 0, npix = 0, R = 0;
     CraRingTab htab{};
     std::vector<int> numr;
@@ -282,6 +286,20 @@ int window_of(const CraSearch& s, float step, int4* w)
     return 0;
 }
 
+// order the main stream after every queued upload that overlaps particles [first, first + n)
+int wait_uploads(CraCtx* c, int first, int n)
+{
+    for (size_t i = 0; i < c->pending.size();) {
+        CraCtx::Pending& p = c->pending[i];
+        if (p.first < first + n && first < p.first + p.n) {
+            CRA_CUDA(cudaStreamWaitEvent(c->st, p.ev, 0));
+            c->ev_pool.push_back(p.ev);
+            c->pending.erase(c->pending.begin() + i);
+        } else ++i;
+    }
+    return 0;
+}
+
 struct Bind { CraCtx* c; Bind(CraCtx* c_) : c(c_) {} int ok() { if (!c) { cra_set_error("null context"); return 1; }
     cudaError_t e = cudaSetDevice(c->device); if (e != cudaSuccess) { cra_set_error(cudaGetErrorString(e)); return 1; } return 0; } };
 
@@ -390,8 +408,12 @@ extern "C" int cra_destroy(CraCtx* c)
 {
     if (!c) return 0;
     cudaSetDevice(c->device);
+    if (c->st_copy) cudaStreamSynchronize(c->st_copy);
     if (c->st) cudaStreamSynchronize(c->st);
     for (auto& e : c->ev) cudaEventDestroy(e);
+    for (auto& p : c->pending) cudaEventDestroy(p.ev);
+    for (auto& e : c->ev_pool) cudaEventDestroy(e);
+    if (c->st_copy) cudaStreamDestroy(c->st_copy);
     cudaFree(c->d_items); cudaFree(c->d_fragtab); cudaFree(c->d_norm); cudaFree(c->d_tref); cudaFree(c->d_plan);
     cudaFree(c->d_tab); cudaFree(c->d_samp); cudaFree(c->d_sampw); cudaFree(c->d_twf); cudaFree(c->d_twi);
     cudaFree(c->d_mask); cudaFree(c->d_images); cudaFree(c->d_refs); cudaFree(c->d_refspec);
@@ -422,6 +444,7 @@ static int upload_particles(CraCtx* c, const float* src, int first, int n, int s
     Bind b(c); if (b.ok()) return 1;
     if (first < 0 || n < 0 || first + n > c->cfg.max_particles) { cra_set_error("particle range exceeds max_particles"); return 1; }
     if (n == 0) return 0;
+    if (wait_uploads(c, first, n)) return 1;
     float* dst = c->d_images + (size_t)first * c->npix;
     CRA_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * c->npix * sizeof(float), kind, c->st));
     if (sub && cra_launch_mask_normalize(dst, n, c->nx, c->d_mask, 0, c->st)) return 1;
@@ -430,6 +453,32 @@ static int upload_particles(CraCtx* c, const float* src, int first, int n, int s
 }
 extern "C" int cra_upload_particles(CraCtx* c, const float* h, int first, int n, int sub)
 { return upload_particles(c, h, first, n, sub, cudaMemcpyHostToDevice); }
+
+extern "C" int cra_upload_particles_async(CraCtx* c, const float* h, int first, int n, int sub)
+{
+    Bind b(c); if (b.ok()) return 1;
+    if (first < 0 || n < 0 || first + n > c->cfg.max_particles) { cra_set_error("particle range exceeds max_particles"); return 1; }
+    if (n == 0) return 0;
+    if (!c->st_copy) CRA_CUDA(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
+    // the slots may still be read by work already queued on the main stream
+    cudaEvent_t e0;
+    if (c->ev_pool.empty()) CRA_CUDA(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming)); else { e0 = c->ev_pool.back(); c->ev_pool.pop_back(); }
+    CRA_CUDA(cudaEventRecord(e0, c->st));
+    CRA_CUDA(cudaStreamWaitEvent(c->st_copy, e0, 0));
+    float* dst = c->d_images + (size_t)first * c->npix;
+    CRA_CUDA(cudaMemcpyAsync(dst, h, (size_t)n * c->npix * sizeof(float), cudaMemcpyHostToDevice, c->st_copy));
+    if (sub && cra_launch_mask_normalize(dst, n, c->nx, c->d_mask, 0, c->st_copy)) return 1;
+    CRA_CUDA(cudaEventRecord(e0, c->st_copy));
+    c->pending.push_back({first, n, e0});
+    return 0;
+}
+
+extern "C" int cra_upload_wait(CraCtx* c)
+{
+    Bind b(c); if (b.ok()) return 1;
+    if (c->st_copy) CRA_CUDA(cudaStreamSynchronize(c->st_copy));
+    return 0;
+}
 extern "C" int cra_upload_particles_dev(CraCtx* c, const float* d, int first, int n, int sub)
 { return upload_particles(c, d, first, n, sub, cudaMemcpyDeviceToDevice); }
 
@@ -453,6 +502,7 @@ extern "C" int cra_align(CraCtx* c, int start, int stop, const CraSearch* search
     if (start < 0 || n < 0 || stop > c->cfg.max_particles) { cra_set_error("particle range exceeds max_particles"); return 1; }
     if (c->R < 1) { cra_set_error("cra_set_refs has not been called"); return 1; }
     if (n == 0) return 0;
+    if (wait_uploads(c, start, n)) return 1;
     const float step = c->cfg.step;
     // plan batches
     std::vector<int> bfirst, bcount, brows;
@@ -615,6 +665,7 @@ extern "C" int cra_accumulate(CraCtx* c, int start, int stop, const float* param
     const int n = stop - start;
     if (start < 0 || n < 0 || stop > c->cfg.max_particles) { cra_set_error("particle range exceeds max_particles"); return 1; }
     if (n == 0) return 0;
+    if (wait_uploads(c, start, n)) return 1;
     if (ensure_par(c, n)) return 1;
     for (int i = 0; i < n; ++i) {
         if (iref[i] >= c->cfg.max_refs) { cra_set_error("iref exceeds max_refs"); return 1; }
@@ -653,6 +704,7 @@ extern "C" int cra_transform(CraCtx* c, int start, int stop, const float* params
     const int n = stop - start;
     if (start < 0 || n < 0 || stop > c->cfg.max_particles) { cra_set_error("particle range exceeds max_particles"); return 1; }
     if (n == 0) return 0;
+    if (wait_uploads(c, start, n)) return 1;
     const int chunk = std::min(n, 8192);
     if ((size_t)chunk > c->cap_tmpimg) {
         if (c->d_tmpimg) cudaFree(c->d_tmpimg);
@@ -707,6 +759,7 @@ extern "C" int cra_polar_spectrum(CraCtx* c, int particle, float cx, float cy, f
 {
     Bind b(c); if (b.ok()) return 1;
     if (particle < 0 || particle >= c->cfg.max_particles) { cra_set_error("bad particle index"); return 1; }
+    if (wait_uploads(c, particle, 1)) return 1;
     if (cra_launch_polar_single(c->d_images + (size_t)particle * c->npix, c->nx, c->d_tab, c->htab, c->d_samp, c->d_sampw,
                                 c->d_twf, c->items, cx, cy, c->cfg.normalize_ring, c->d_spec, c->fmt, c->frag, c->d_norm, c->st)) return 1;
     const size_t bytes = (c->fmt == CRA_FMT_FRAG) ? c->row_bytes : 4 * c->row_bytes;
@@ -753,6 +806,7 @@ extern "C" int cra_ccf_curves(CraCtx* c, int particle, float cx, float cy, int i
 {
     Bind b(c); if (b.ok()) return 1;
     if (particle < 0 || particle >= c->cfg.max_particles || iref < 0 || iref >= c->R) { cra_set_error("bad index"); return 1; }
+    if (wait_uploads(c, particle, 1)) return 1;
     if (cra_launch_polar_single(c->d_images + (size_t)particle * c->npix, c->nx, c->d_tab, c->htab, c->d_samp, c->d_sampw,
                                 c->d_twf, c->items, cx, cy, c->cfg.normalize_ring, c->d_spec, c->fmt, c->frag, c->d_norm, c->st)) return 1;
     if (cra_launch_ccf_curves(c->d_spec, 0, c->d_refspec, iref, c->d_tab, c->htab,

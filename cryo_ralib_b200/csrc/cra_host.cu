@@ -1,0 +1,110 @@
+// cra_host.cu -- the per-particle bookkeeping of the reference's Python loop, batched in native
+// code (test_mref.py:184-198 and :206; sp_utilities.combine_params2 / inverse_transform2 on EMAN2's
+// float32 2-D Transform, sp_alignment.search_range).  Pure host arithmetic: no CUDA calls, so the
+// CPU tests can compare it bit for bit with cryo_ralib_b200/alignment.py, whose Transform algebra is
+// pinned on the reference's golden values (cuda/EMAN2_test.ipynb cells 23-25).
+// Every float operation is written as its own statement in the order the numpy restatement
+// evaluates it (compile with FP contraction off), so the results match to the last bit wherever
+// libm's cos/sin/atan2 agree with numpy's.
+#include "cra_common.cuh"
+#include <math.h>
+
+namespace {
+
+struct M23 { float m[2][3]; };
+
+inline M23 make_t(double alpha_deg, double tx, double ty, int mirror)
+{
+    const double a = alpha_deg * M_PI / 180.0;
+    const float c = (float)cos(a), s = (float)sin(a);
+    M23 t;
+    t.m[0][0] = c;  t.m[0][1] = s; t.m[0][2] = (float)tx;
+    t.m[1][0] = -s; t.m[1][1] = c; t.m[1][2] = (float)ty;
+    if (mirror) { t.m[0][0] = -t.m[0][0]; t.m[0][1] = -t.m[0][1]; t.m[0][2] = -t.m[0][2]; }
+    return t;
+}
+
+inline M23 mul_t(const M23& a, const M23& b)      // a * b, float32 products and sums, left to right
+{
+    M23 r;
+    for (int i = 0; i < 2; ++i) {
+        volatile float p, q, u;
+        p = a.m[i][0] * b.m[0][0]; q = a.m[i][1] * b.m[1][0]; r.m[i][0] = p + q;
+        p = a.m[i][0] * b.m[0][1]; q = a.m[i][1] * b.m[1][1]; r.m[i][1] = p + q;
+        p = a.m[i][0] * b.m[0][2]; q = a.m[i][1] * b.m[1][2]; u = p + q; r.m[i][2] = u + a.m[i][2];
+    }
+    return r;
+}
+
+inline void params_t(M23 t, double* alpha, double* sx, double* sy, int* mirror)
+{
+    volatile float p = t.m[0][0] * t.m[1][1], q = t.m[0][1] * t.m[1][0];
+    const float det = p - q;
+    const int mir = det < 0.0f;
+    if (mir) { t.m[0][0] = -t.m[0][0]; t.m[0][1] = -t.m[0][1]; t.m[0][2] = -t.m[0][2]; }
+    double a = atan2((double)t.m[0][1], (double)t.m[0][0]) * (180.0 / M_PI);
+    if (a < 0.0) a += 360.0;
+    if (a >= 360.0) a -= 360.0;
+    *alpha = a; *sx = (double)t.m[0][2]; *sy = (double)t.m[1][2]; *mirror = mir;
+}
+
+inline M23 invert_t(const M23& t)                  // Transform::invert: double arithmetic on the float entries
+{
+    const double m00 = t.m[0][0], m01 = t.m[0][1], m02 = t.m[0][2], m10 = t.m[1][0], m11 = t.m[1][1], m12 = t.m[1][2];
+    const double det = m00 * m11 - m01 * m10;
+    const double r00 = m11 / det, r01 = -m01 / det, r10 = -m10 / det, r11 = m00 / det;
+    const double r02 = -(r00 * m02 + r01 * m12), r12 = -(r10 * m02 + r11 * m12);
+    M23 r;
+    r.m[0][0] = (float)r00; r.m[0][1] = (float)r01; r.m[0][2] = (float)r02;
+    r.m[1][0] = (float)r10; r.m[1][1] = (float)r11; r.m[1][2] = (float)r12;
+    return r;
+}
+
+inline void search_range(int n, int radius, double shift, double rng, float* left, float* right)
+{
+    const int cn = n / 2 + 1;
+    double ql = cn + shift - radius - 2; if (ql < 0.0) ql = 0.0;
+    double qe = n - cn - shift - radius; if (qe < 0.0) qe = 0.0;
+    *left = (float)(ql < rng ? ql : rng); *right = (float)(qe < rng ? qe : rng);
+}
+
+}  // namespace
+
+// test_mref.py:184-198 for n particles.  params [n][4] double (alpha, sx, sy, mirror) is reset to zero
+// in place where the inverted shift exceeds mashi = cnx - ou - 2.
+extern "C" int cra_mref_search_request(int n, double* params, int nx, int ou, double xr, double yr,
+                                       CraSearch* search, double* sxi_out, double* syi_out)
+{
+    if (n < 0 || !params || !search || !sxi_out || !syi_out) { cra_set_error("null argument"); return 1; }
+    const int cnx = nx / 2 + 1, mashi = cnx - ou - 2;
+#pragma omp parallel for schedule(static) if (n > 4096)
+    for (int i = 0; i < n; ++i) {
+        double a, sxi, syi; int mir;
+        params_t(invert_t(make_t(params[4 * i], params[4 * i + 1], params[4 * i + 2], 0)), &a, &sxi, &syi, &mir);
+        if (fabs(sxi) > mashi || fabs(syi) > mashi) {
+            sxi = 0.0; syi = 0.0;
+            params[4 * i] = params[4 * i + 1] = params[4 * i + 2] = params[4 * i + 3] = 0.0;
+        }
+        CraSearch s;
+        search_range(nx, ou, sxi, xr, &s.xl, &s.xr);
+        search_range(nx, ou, syi, yr, &s.yl, &s.yr);
+        s.cx = (float)(cnx + sxi); s.cy = (float)(cnx + syi);
+        search[i] = s; sxi_out[i] = sxi; syi_out[i] = syi;
+    }
+    return 0;
+}
+
+// test_mref.py:206: combine_params2(0, -sxi, -syi, 0, ang, sxs, sys, mirror) -> params_out [n][4] double
+extern "C" int cra_compose_result(int n, const double* sxi, const double* syi, const CraResult* res, double* params_out)
+{
+    if (n < 0 || !sxi || !syi || !res || !params_out) { cra_set_error("null argument"); return 1; }
+#pragma omp parallel for schedule(static) if (n > 4096)
+    for (int i = 0; i < n; ++i) {
+        const M23 t1 = make_t(0.0, -sxi[i], -syi[i], 0);
+        const M23 t2 = make_t((double)res[i].ang, (double)res[i].sxs, (double)res[i].sys, res[i].mirror);
+        double a, sx, sy; int mir;
+        params_t(mul_t(t2, t1), &a, &sx, &sy, &mir);
+        params_out[4 * i] = a; params_out[4 * i + 1] = sx; params_out[4 * i + 2] = sy; params_out[4 * i + 3] = (double)mir;
+    }
+    return 0;
+}

@@ -57,7 +57,8 @@ RESULT_DTYPE = np.dtype([("ang", "f4"), ("sxs", "f4"), ("sys", "f4"), ("mirror",
                          ("peak", "f4"), ("sx", "f4"), ("sy", "f4")])
 
 CORE_SYMBOLS = ["cra_create", "cra_destroy", "cra_last_error", "cra_ring_info", "cra_upload_particles",
-                "cra_upload_particles_dev", "cra_set_refs", "cra_align", "cra_accumulate", "cra_zero_sums",
+                "cra_upload_particles_dev", "cra_upload_particles_async", "cra_upload_wait", "cra_mref_search_request",
+                "cra_compose_result", "cra_set_refs", "cra_align", "cra_accumulate", "cra_zero_sums",
                 "cra_sums_device_ptr", "cra_get_sums", "cra_transform", "cra_polar_spectrum", "cra_ref_spectrum", "cra_batch_row_spectrum",
                 "cra_ccf_curves", "cra_last_align_stats", "cra_set_timing", "cra_set_normalize_ring", "cra_set_step",
                 "cra_row_batch", "cra_device_images_ptr", "cra_stream", "cra_measure_fp32_peak"]
@@ -84,6 +85,10 @@ def load_library(path=None):
     L.cra_ring_info.argtypes = [vp, ip, ip, ip, vp]
     L.cra_upload_particles.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
     L.cra_upload_particles_dev.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
+    L.cra_upload_particles_async.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
+    L.cra_upload_wait.argtypes = [vp]
+    L.cra_mref_search_request.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_double, C.c_double, vp, vp, vp]
+    L.cra_compose_result.argtypes = [C.c_int, vp, vp, vp, vp]
     L.cra_set_refs.argtypes = [vp, vp, C.c_int, C.c_int]
     L.cra_align.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     L.cra_accumulate.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_long]
@@ -169,6 +174,14 @@ class Engine(object):
 
     def upload_particles_ptr(self, host_ptr, n, first=0, subtract_mask_mean=True):
         self._ck(self.L.cra_upload_particles(self.h, host_ptr, int(first), int(n), int(subtract_mask_mean)))
+
+    def upload_particles_async(self, host_ptr, n, first=0, subtract_mask_mean=True):
+        """Queue a pinned-host upload on the copy stream; align()/accumulate() of an overlapping particle
+        range wait for it on the device.  The buffer must stay valid until upload_wait()."""
+        self._ck(self.L.cra_upload_particles_async(self.h, host_ptr, int(first), int(n), int(subtract_mask_mean)))
+
+    def upload_wait(self):
+        self._ck(self.L.cra_upload_wait(self.h))
 
     def upload_particles_dev(self, dev_ptr, n, first=0, subtract_mask_mean=True):
         self._ck(self.L.cra_upload_particles_dev(self.h, dev_ptr, int(first), int(n), int(subtract_mask_mean)))

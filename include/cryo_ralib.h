@@ -78,6 +78,14 @@ int  cra_upload_particles(CraCtx* ctx, const float* host_images, int first, int 
 /* Same, source already on this device. */
 int  cra_upload_particles_dev(CraCtx* ctx, const float* dev_images, int first, int n, int subtract_mask_mean);
 
+/* Asynchronous variant: the copy (and the mask-mean subtraction) is queued on the context's copy
+ * stream and returns at once; cra_align / cra_accumulate / cra_transform on a particle range wait,
+ * on the device, only for the uploads that overlap it, so the upload of the next chunk runs under
+ * the alignment of the current one.  host_images must be pinned and stay valid until
+ * cra_upload_wait (or a later call that consumed the range) returns.                            */
+int  cra_upload_particles_async(CraCtx* ctx, const float* host_images, int first, int n, int subtract_mask_mean);
+int  cra_upload_wait(CraCtx* ctx);
+
 /* Upload R references and prepare them: optional normalize.mask(no_sigma=1),
  * Polar2Dm at (cnx,cny), Frngs, Applyws (test_mref.py:170-175).  Replaces
  * pre_align_fetch(...,"ref_batch").                                         */
@@ -87,6 +95,15 @@ int  cra_set_refs(CraCtx* ctx, const float* host_refs, int R, int normalize_mask
  * (Polar2Dm -> Normalize_ring -> Frngs -> Crosrng_ms -> best).  search and out
  * are host arrays indexed from 0 for particle `start`.                      */
 int  cra_align(CraCtx* ctx, int start, int stop, const CraSearch* search, CraResult* out);
+
+/* Host bookkeeping of the reference's per-particle Python loop, batched (no device work):
+ * cra_mref_search_request = get_params2D -> inverse_transform2 -> mashi reset -> search_range x2
+ * (test_mref.py:184-198); params [n][4] double (alpha, sx, sy, mirror) is reset in place where the
+ * reference resets it.  cra_compose_result = combine_params2(0,-sxi,-syi,0, ang,sxs,sys,mirror)
+ * (test_mref.py:206) -> params_out [n][4] double.                                              */
+int  cra_mref_search_request(int n, double* params, int nx, int ou, double xr, double yr,
+                             CraSearch* search, double* sxi_out, double* syi_out);
+int  cra_compose_result(int n, const double* sxi, const double* syi, const CraResult* res, double* params_out);
 
 /* rot_shift2D(img, alpha, sx, sy, mirror) + add into class sums
  * sums[iref][global_index % 2] and counts[iref] (test_mref.py:210-215).

@@ -97,6 +97,30 @@ def test_search_request_matches_reference_loop(oracle):
     assert np.allclose(newp[:, 1], -sxi, atol=1e-6) and np.allclose(newp[:, 2], -syi, atol=1e-6)
 
 
+def test_native_bookkeeping_equals_numpy_restatement():
+    """csrc/cra_host.cu (what the drivers call) against the numpy Transform algebra the golden values pin:
+    search requests bit for bit, composed parameters bit for bit except the last ulp of the angle."""
+    from cryo_ralib_b200 import alignment as al
+    from cryo_ralib_b200.lib import RESULT_DTYPE
+    rng = np.random.default_rng(5)
+    n = 20000
+    params = np.stack([rng.uniform(0, 360, n), rng.uniform(-9, 9, n), rng.uniform(-9, 9, n),
+                       rng.integers(0, 2, n).astype(float)], 1)
+    params[:50] = 0.0
+    a = al.mref_search_request(params, 90, 36, 3, 2, native=True)
+    b = al.mref_search_request(params, 90, 36, 3, 2, native=False)
+    for f in a[0].dtype.names:
+        assert np.array_equal(a[0][f], b[0][f]), f
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    res = np.zeros(n, RESULT_DTYPE)
+    res["ang"] = rng.uniform(0, 360, n); res["sxs"] = rng.uniform(-4, 4, n); res["sys"] = rng.uniform(-4, 4, n)
+    res["mirror"] = rng.integers(0, 2, n)
+    c = al.compose_result(a[1], a[2], res, native=True)
+    d = al.compose_result(a[1], a[2], res, native=False)
+    assert np.array_equal(c[:, 1:], d[:, 1:])
+    assert np.abs(c[:, 0] - d[:, 0]).max() < 1e-12
+
+
 def test_mpi_start_end_partitions():
     from cryo_ralib_b200 import alignment as al
     for n, p in ((10000, 8), (100001, 3), (7, 8), (50, 1)):
