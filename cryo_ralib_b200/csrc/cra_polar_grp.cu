@@ -142,14 +142,28 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
     {
         // padded (Y, X), 0 <= X, Y <= nx+1, holds pixel ((Y-1) mod nx, (X-1) mod nx): 1-based pixel (i, j) sits at (j, i)
         const float* img = images + (size_t)(map.p0 + s_blk[0]) * npix;
-        for (int Y = tid >> 5; Y < pitch; Y += kThreads / 32) {
-            const int sy = (Y == 0) ? nx - 1 : ((Y == nx + 1) ? 0 : Y - 1);
-            const float* src = img + sy * nx;
-            float* dst = s_img + Y * pitch;
-            for (int X = tid & 31; X < pitch; X += 32) {
-                const int sx = (X == 0) ? nx - 1 : ((X == nx + 1) ? 0 : X - 1);
-                dst[X] = __ldg(src + sx);
+        if ((npix & 3) == 0) {                 // interior: the image as one stream of 128-bit loads
+            const float4* g4 = reinterpret_cast<const float4*>(img);
+            for (int i = tid; i < (npix >> 2); i += kThreads) {
+                const float4 v = __ldg(g4 + i);
+                const float e[4] = {v.x, v.y, v.z, v.w};
+                int y = (4 * i) / nx, x = 4 * i - y * nx;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    s_img[(y + 1) * pitch + x + 1] = e[k];
+                    if (++x == nx) { x = 0; ++y; }
+                }
             }
+        } else {
+            for (int i = tid; i < npix; i += kThreads) { const int y = i / nx; s_img[(y + 1) * pitch + (i - y * nx) + 1] = __ldg(img + i); }
+        }
+        for (int b = tid; b < 2 * pitch + 2 * nx; b += kThreads) {      // the periodic border, straight from global
+            int Y, X;
+            if (b < 2 * pitch) { Y = (b < pitch) ? 0 : nx + 1; X = (b < pitch) ? b : b - pitch; }
+            else { const int c = b - 2 * pitch; Y = 1 + (c >> 1); X = (c & 1) ? nx + 1 : 0; }
+            const int sy = (Y == 0) ? nx - 1 : ((Y == nx + 1) ? 0 : Y - 1);
+            const int sx = (X == 0) ? nx - 1 : ((X == nx + 1) ? 0 : X - 1);
+            s_img[Y * pitch + X] = __ldg(img + sy * nx + sx);
         }
     }
     const float bx = s_base[0], by = s_base[1];
