@@ -52,6 +52,7 @@ struct CraCtx {
     // contraction path: CRA_FMT_FRAG = tensor-core kernel on split-bf16 fragments (default),
     // CRA_FMT_F32 = FP32 FMA kernel on the float2 spectrum (CRA_CCF=simt)
     int fmt = CRA_FMT_FRAG;
+    bool use_tm = true;          // W staged in tensor memory (cra_ccf_tm.cu); CRA_CCF=mma keeps it in shared memory
     CraFragTab frag{};
     std::vector<int> h_koff, h_chunk_k;
     int* d_fragtab = nullptr;
@@ -364,7 +365,8 @@ extern "C" int cra_create(const CraConfig* cfg, int device, CraCtx** out)
     {
         const char* e = getenv("CRA_CCF");
         if (e && strcmp(e, "simt") == 0) c->fmt = CRA_FMT_F32;
-        else if (e && strcmp(e, "mma") != 0 && e[0]) { cra_set_error("CRA_CCF must be 'mma' or 'simt'"); cra_destroy(c); return 1; }
+        else if (e && strcmp(e, "mma") == 0) c->use_tm = false;
+        else if (e && strcmp(e, "tm") != 0 && e[0]) { cra_set_error("CRA_CCF must be 'tm', 'mma' or 'simt'"); cra_destroy(c); return 1; }
         const char* pk = getenv("CRA_POLAR");
         if (pk && strcmp(pk, "general") == 0) c->use_group = false;
         else if (pk && strcmp(pk, "group") != 0 && pk[0]) { cra_set_error("CRA_POLAR must be 'group' or 'general'"); cra_destroy(c); return 1; }
@@ -380,7 +382,9 @@ extern "C" int cra_create(const CraConfig* cfg, int device, CraCtx** out)
     long want = (long)cfg->max_particles * c->smax;
     if (rb > want) rb = want;
     c->row_batch = (int)rb;
-    c->ntile_n_max = (c->fmt == CRA_FMT_FRAG) ? cra_ccf_mma_num_tiles(cfg->max_refs, c->htab.log2n)
+    if (!cra_ccf_tm_supported(c->htab.log2n)) c->use_tm = false;
+    c->ntile_n_max = (c->fmt == CRA_FMT_FRAG) ? (c->use_tm ? cra_ccf_tm_num_tiles(cfg->max_refs, c->htab.log2n)
+                                                           : cra_ccf_mma_num_tiles(cfg->max_refs, c->htab.log2n))
                                               : (cfg->max_refs + cra_ccf_tile_n() - 1) / cra_ccf_tile_n();
     const size_t nsum = (size_t)cfg->max_refs * 2 * c->npix + cfg->max_refs;
     cudaError_t e = cudaSuccess;
@@ -571,7 +575,8 @@ extern "C" int cra_align(CraCtx* c, int start, int stop, const CraSearch* search
     const int* d_cs = d_rs + n + nb;
 
     const int TN = cra_ccf_tile_n();
-    const int ntile_n = (c->fmt == CRA_FMT_FRAG) ? cra_ccf_mma_num_tiles(c->R, c->htab.log2n) : (c->R + TN - 1) / TN;
+    const int ntile_n = (c->fmt == CRA_FMT_FRAG) ? (c->use_tm ? cra_ccf_tm_num_tiles(c->R, c->htab.log2n)
+                                                              : cra_ccf_mma_num_tiles(c->R, c->htab.log2n)) : (c->R + TN - 1) / TN;
     const bool tm = c->timing;
     if (tm) {
         while (c->ev.size() < 4 * nb) { cudaEvent_t e; CRA_CUDA(cudaEventCreate(&e)); c->ev.push_back(e); }
@@ -591,7 +596,11 @@ extern "C" int cra_align(CraCtx* c, int start, int stop, const CraSearch* search
         } else if (cra_launch_polar_rows(c->d_images, c->nx, c->d_tab, c->htab, c->d_samp, c->d_sampw, c->d_twf, c->items, map,
                                          c->cfg.normalize_ring, c->d_spec, c->fmt, c->frag, c->d_norm, c->st)) return 1;
         if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 1], c->st));
-        if (c->fmt == CRA_FMT_FRAG) {
+        if (c->fmt == CRA_FMT_FRAG && c->use_tm) {
+            if (cra_launch_ccf_tm(reinterpret_cast<const unsigned char*>(c->d_spec), map.nrows,
+                                  reinterpret_cast<const unsigned char*>(c->d_refspec), c->R, c->htab, c->frag, c->h_koff,
+                                  c->d_twi, c->d_cand, ntile_n, c->d_norm, c->d_tref, c->st)) return 1;
+        } else if (c->fmt == CRA_FMT_FRAG) {
             if (cra_launch_ccf_mma(reinterpret_cast<const unsigned char*>(c->d_spec), map.nrows,
                                    reinterpret_cast<const unsigned char*>(c->d_refspec), c->R, c->htab, c->frag, c->h_koff,
                                    c->d_twi, c->d_cand, ntile_n, c->d_norm, c->d_tref, c->st)) return 1;

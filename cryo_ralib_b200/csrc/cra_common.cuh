@@ -156,6 +156,12 @@ int cra_launch_ccf_mma(const unsigned char* spec, int nrows, const unsigned char
                        const CraFragTab& frag, const std::vector<int>& h_koff, const float2* twid, CraCand* cand,
                        int ntile_n, const float2* norm, const float* tref, cudaStream_t st);
 int cra_ccf_mma_num_tiles(int R, int log2n);
+// the same contraction with W staged in tensor memory, two CTAs per SM (cra_ccf_tm.cu)
+bool cra_ccf_tm_supported(int log2n);
+int cra_ccf_tm_num_tiles(int R, int log2n);
+int cra_launch_ccf_tm(const unsigned char* spec, int nrows, const unsigned char* refspec, int R, const CraRingTab& htab,
+                      const CraFragTab& frag, const std::vector<int>& h_koff, const float2* twid, CraCand* cand,
+                      int ntile_n, const float2* norm, const float* tref, cudaStream_t st);
 int cra_launch_ccf(const float* spec, int nrows, const float* refspec, int R, const CraRingTab* tab,
                    const CraRingTab& htab, const float2* twid, CraCand* cand, int ntile_n, cudaStream_t st);
 int cra_ccf_tile_n();
