@@ -99,6 +99,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
     float2* s_tw = reinterpret_cast<float2*>(s_buf + plan.rmax * stride);   // maxrin : exp(-2 pi i j / maxrin)
     __shared__ float s_red[kThreads / 32][2 * RMAX];
     __shared__ int s_rowoff[RMAX];
+    __shared__ unsigned s_samemask;                            // bit r: row r sits one pixel right of row r-1
     __shared__ float2 s_rowc[RMAX];
     __shared__ float s_fix[2 * RMAX];
     __shared__ int s_frag[kFragCap];                           // queued fragile samples of the phase: q * 4 + m
@@ -122,6 +123,10 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
         const int istep = (int)map.step;
         s_base[0] = map.search[lo].cx - (float)w.x * map.step;
         s_base[1] = map.search[lo].cy - (float)w.z * map.step;
+        unsigned same = 0;
+        for (int r = 1; r < r_hi - r_lo; ++r)
+            if (istep == 1 && (r_lo + r) % wx != 0) same |= 1u << r;
+        s_samemask = same;
         for (int r = 0; r < r_hi - r_lo; ++r) {
             const int li = r_lo + r;
             s_rowoff[r] = (li / wx) * istep * pitch + (li % wx) * istep;
@@ -167,6 +172,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
         }
     }
     const float bx = s_base[0], by = s_base[1];
+    const unsigned samemask = s_samemask;
     float av[RMAX], sq[RMAX];
 #pragma unroll
     for (int r = 0; r < RMAX; ++r) { av[r] = 0.f; sq[r] = 0.f; }
@@ -181,47 +187,50 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
             const int jt = __float_as_int(e.w);
             const float wn = __int_as_float(rp.w);
             const float ox[4] = {e.x, e.y, -e.x, -e.y}, oy[4] = {e.y, -e.x, -e.y, e.x};
-            float w0[4], w1[4], w2[4], w3[4], w4[4], w5[4];
-            int pix[4], slot[4];
             int fragile = 0;       // samples so close to a pixel boundary that float rounding of the per-row
                                    // position (x = offset + centre, as Polar2Dm forms it) could pick another cell
+            int ro[RMAX];
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) ro[r] = (r < nr) ? s_rowoff[r] : 0;
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
-                const int j = jt + m * rp.z, p = j >> 1;
-                slot[m] = 2 * (rp.x + p + (p >> rp.y)) + (j & 1);
+                const int j = jt + m * rp.z, pj = j >> 1;
+                const int slot = 2 * (rp.x + pj + (pj >> rp.y)) + (j & 1);
                 const float X = ox[m] + bx, Y = oy[m] + by;
                 const int ix = (int)X, iy = (int)Y;
                 const float dx = X - (float)ix, dy = Y - (float)iy;
                 if (dx < 1e-4f || dx > 0.9999f || dy < 1e-4f || dy > 0.9999f) fragile |= 1 << m;
                 // quadri: f0 + dx (c1 + (dx-1) c2 + dy c5) + dy (c3 + (dy-1) c4) as six tap weights
                 const float a2 = 0.5f * dx * (dx - 1.0f), b2 = 0.5f * dy * (dy - 1.0f), ab = dx * dy;
-                w1[m] = dx + a2 - ab;          // (i+1, j)
-                w2[m] = a2;                    // (i-1, j)
-                w3[m] = dy + b2 - ab;          // (i, j+1)
-                w4[m] = b2;                    // (i, j-1)
-                w5[m] = ab;                    // (i+1, j+1)
-                w0[m] = 1.0f - dx - dy - 2.0f * a2 - 2.0f * b2 + ab;
-                pix[m] = iy * pitch + ix;
-            }
+                const float w1 = dx + a2 - ab;          // (i+1, j)
+                const float w2 = a2;                    // (i-1, j)
+                const float w3 = dy + b2 - ab;          // (i, j+1)
+                const float w4 = b2;                    // (i, j-1)
+                const float w5 = ab;                    // (i+1, j+1)
+                const float w0 = 1.0f - dx - dy - 2.0f * a2 - 2.0f * b2 + ab;
+                const float* p0 = s_img + (iy * pitch + ix);
+                float* dst = s_buf + slot;
+                // a row that continues the window line of the previous one (one pixel to the right) reuses
+                // three of its taps: (i-1,j) <- (i,j), (i,j) <- (i+1,j), (i,j+1) <- (i+1,j+1)
+                float fl = 0.f, fc = 0.f, fr = 0.f, uc = 0.f, ur = 0.f;
 #pragma unroll
-            for (int r = 0; r < RMAX; ++r) {
-                if (r < nr) {
-                    const int ro = s_rowoff[r];
-                    float* dst = s_buf + r * stride;
-                    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-                    for (int m = 0; m < 4; ++m) {
-                        const float* p = s_img + (pix[m] + ro);
-                        float v = w0[m] * p[0];
-                        v = fmaf(w1[m], p[1], v);
-                        v = fmaf(w2[m], p[-1], v);
-                        v = fmaf(w3[m], p[pitch], v);
-                        v = fmaf(w4[m], p[-pitch], v);
-                        v = fmaf(w5[m], p[pitch + 1], v);
-                        dst[slot[m]] = v;
-                        s1 += v; s2 = fmaf(v, v, s2);
+                for (int r = 0; r < RMAX; ++r) {
+                    if (r < nr) {
+                        const float* p = p0 + ro[r];
+                        const bool cont = (samemask >> r) & 1;
+                        fl = fc; fc = fr; uc = ur;
+                        if (!cont) { fl = p[-1]; fc = p[0]; uc = p[pitch]; }
+                        fr = p[1]; ur = p[pitch + 1];
+                        float v = w0 * fc;
+                        v = fmaf(w1, fr, v);
+                        v = fmaf(w2, fl, v);
+                        v = fmaf(w3, uc, v);
+                        v = fmaf(w4, p[-pitch], v);
+                        v = fmaf(w5, ur, v);
+                        dst[r * stride] = v;
+                        const float tv = v * wn;
+                        av[r] += tv; sq[r] = fmaf(tv, v, sq[r]);
                     }
-                    av[r] = fmaf(s1, wn, av[r]); sq[r] = fmaf(s2, wn, sq[r]);
                 }
             }
             if (fragile) {         // rare: queue those samples; the CTA redoes them together below

@@ -30,3 +30,9 @@ for it in range(3):
 newp = al.compose_result(sxi, syi, res)
 t = time.time(); e.zero_sums(); e.accumulate(0, P, newp, res["iref"], 0); print("accumulate s:", time.time() - t)
 print("assign histogram:", np.bincount(res["iref"], minlength=R)[:10])
+# second iteration: fractional centres and ragged windows, as every iteration after the first sees them
+search2, sxi2, syi2, _ = al.mref_search_request(newp, nx, ou, xr, xr)
+for it in range(2):
+    res2 = e.align(0, P, search2)
+    st = e.stats()
+    print("iter2", json.dumps(st))
