@@ -139,6 +139,7 @@ int build_group_plan(CraCtx* c)
         u = u1;
     }
     c->plan.stride = (2 * cap + 3) & ~3;
+    c->plan.nring = nring;
     c->plan.nphase = (int)phases.size();
     // rows per CTA: as many as fit two CTAs per SM (fewer image reloads, shared index math), else one CTA
     int dev = 0; cudaGetDevice(&dev);
@@ -147,7 +148,7 @@ int build_group_plan(CraCtx* c)
     cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     auto fits = [&](int rmax, int ncta) {
         CraGroupPlan q = c->plan; q.rmax = rmax;
-        const size_t need = cra_polar_group_smem(c->nx, t.maxrin, q) + 6200;   // + static shared + 1 KB reserved per CTA
+        const size_t need = cra_polar_group_smem(c->nx, t.maxrin, q) + 3700;   // + static shared + 1 KB reserved per CTA
         return need <= (size_t)smem_blk && need * ncta <= (size_t)smem_sm;
     };
     int rmax = 0;

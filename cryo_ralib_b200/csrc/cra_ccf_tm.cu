@@ -50,7 +50,7 @@ struct TShape {
     static constexpr int N1 = 1 << L1;
     static constexpr int N2 = 1 << L2;
     static constexpr int PS = N1 * (N2 + 1) + ((N1 * (N2 + 1)) % 2 == 0 ? 1 : 0);   // odd float2 stride of one pair
-    static constexpr int NJ = (LOG2N <= 8) ? 2 : 1;     // reference quads per CTA
+    static constexpr int NJ = 2;                        // reference quads per CTA (maxrin 512: all 512 columns, one CTA per SM)
     static constexpr int RQ = N2 / 4;                   // residues per quadrant
     static constexpr int JCOLS = N / 2;                 // TMEM columns of one pair slot in one quadrant = RQ * N1 * 2
     static constexpr int COLS = (NJ * JCOLS < 32) ? 32 : NJ * JCOLS;

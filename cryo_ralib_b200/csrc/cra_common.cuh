@@ -74,6 +74,7 @@ struct CraGroupPlan {
     const int* unit_nk;        // [units] longest half length (len/2 of its first slot) of unit u (device)
     int stride;                // floats per row of the phase buffer
     int rmax;                  // rows per CTA (<= CRA_GRP_RMAX), chosen for shared-memory fit
+    int nring;
 };
 
 struct CraRowMap {             // how rows of the current batch map to particles

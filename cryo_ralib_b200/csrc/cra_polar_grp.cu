@@ -30,7 +30,7 @@ using crafft::fft_reg;
 
 constexpr int kThreads = 256;
 constexpr int RMAX = CRA_GRP_RMAX;
-constexpr int kFragCap = 128;   // beyond it a sample keeps its shared-weight value (never seen: <1 expected per phase)
+constexpr int kFragCap = 24;    // per warp and phase; beyond it a sample keeps its shared-weight value (<0.1 expected)
 
 __device__ __forceinline__ float warp_sum(float v)
 {
@@ -97,16 +97,18 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
     float* s_img = smem;                                       // pitch * pitch (padded to 4)
     float* s_buf = smem + ((pitch * pitch + 3) & ~3);          // rmax * stride
     float2* s_tw = reinterpret_cast<float2*>(s_buf + plan.rmax * stride);   // maxrin : exp(-2 pi i j / maxrin)
+    int4* s_ring = reinterpret_cast<int4*>(s_tw + maxrin);    // nring : phase-local float2 offset, log2 NB, len/4, wn
+    int* s_koff = reinterpret_cast<int*>(s_ring + nring);     // maxrin/2 + 2 : first chunk of frequency k
+    int* s_unk = s_koff + (maxrin / 2 + 2);                   // units : longest half length of unit u
     __shared__ float s_red[kThreads / 32][2 * RMAX];
     __shared__ int s_rowoff[RMAX];
     __shared__ unsigned s_samemask;                            // bit r: row r sits one pixel right of row r-1
     __shared__ float2 s_rowc[RMAX];
     __shared__ float s_fix[2 * RMAX];
-    __shared__ int s_frag[kFragCap];                           // queued fragile samples of the phase: q * 4 + m
-    __shared__ int s_nfrag;                          // Normalize_ring sum corrections of the fragile samples                            // the reference's own centre of every row
+    __shared__ int s_frag[kThreads / 32][kFragCap];            // per warp: queued fragile samples of the phase, q * 4 + m
+    __shared__ int s_nfrag[kThreads / 32];                          // Normalize_ring sum corrections of the fragile samples                            // the reference's own centre of every row
     __shared__ int s_blk[4];                                   // particle (batch local), first local row, rows
     __shared__ float s_base[2];
-    __shared__ int4 s_ring[CRA_MAX_RINGS];                     // phase-local float2 offset, log2 NB, len/4, wn
 
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -136,7 +138,9 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
     }
     for (int i = tid; i < maxrin; i += kThreads) s_tw[i] = twid[i];
     if (tid < 2 * RMAX) s_fix[tid] = 0.f;
-    if (tid == 0) s_nfrag = 0;
+    if (tid < kThreads / 32) s_nfrag[tid] = 0;
+    for (int i = tid; i < maxrin / 2 + 2; i += kThreads) s_koff[i] = __ldg(frag.koff + i);
+    for (int i = tid; i < (nring + 3) / 4; i += kThreads) s_unk[i] = __ldg(plan.unit_nk + i);
     for (int i = tid; i < nring; i += kThreads) {
         const int n = tab->len[i] >> 1, lg = 31 - __clz(n);
         s_ring[i] = make_int4(__ldg(plan.ppoff + i), lg - (lg >> 1), tab->len[i] >> 2, __float_as_int(tab->wn[i]));
@@ -233,22 +237,24 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                     }
                 }
             }
-            if (fragile) {         // rare: queue those samples; the CTA redoes them together below
+            if (fragile) {         // rare: queue those samples; the warp redoes them together below
 #pragma unroll
                 for (int m = 0; m < 4; ++m)
                     if (fragile & (1 << m)) {
-                        const int at = atomicAdd(&s_nfrag, 1);
-                        if (at < kFragCap) s_frag[at] = q * 4 + m;
+                        const int at = atomicAdd(&s_nfrag[tid >> 5], 1);
+                        if (at < kFragCap) s_frag[tid >> 5][at] = q * 4 + m;
                     }
             }
         }
-        __syncthreads();
-        // ---- fragile samples, row by row exactly as the reference positions them (x = offset + centre) ----
+        // ---- fragile samples, row by row exactly as the reference positions them (x = offset + centre);
+        // each warp repairs the samples it wrote itself, so no CTA barrier is needed in between ----
+        __syncwarp();
         {
-            const int nf = min(s_nfrag, kFragCap);
-            for (int x = tid; x < nf * nr; x += kThreads) {
+            const int wid = tid >> 5;
+            const int nf = min(s_nfrag[wid], kFragCap);
+            for (int x = tid & 31; x < nf * nr; x += 32) {
                 const int en = x / nr, r = x - en * nr;
-                const int code = s_frag[en], q = code >> 2, m = code & 3;
+                const int code = s_frag[wid][en], q = code >> 2, m = code & 3;
                 const float4 e = __ldg(samp + q);
                 const int4 rp = s_ring[__float_as_int(e.z)];
                 const float wn = __int_as_float(rp.w);
@@ -367,7 +373,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
             for (int x = tid; x < upr * nset; x += kThreads) {
                 const int set = fastdiv(x, P.magicD);
                 int k = x - set * upr, u = P.u0;
-                while (k >= __ldg(plan.unit_nk + u)) { k -= __ldg(plan.unit_nk + u); ++u; }
+                while (k >= s_unk[u]) { k -= s_unk[u]; ++u; }
                 // value of slot j = (v.x * mx + v.y * my, v.y * mi) of z[idx]: complex (1,0,1), F_0 = .x of
                 // pos(0) (1,0,0), F_n = .y of pos(0) (0,1,0), ring too short or absent (0,0,0)
                 int idx[4]; float mx[4], my[4], mi[4];
@@ -387,7 +393,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                         }
                     }
                 }
-                unsigned char* o = spec + (size_t)(grow0 + set) * rb + (size_t)(__ldg(frag.koff + k) + (u >> 2)) * 128 + (u & 3) * 32;
+                unsigned char* o = spec + (size_t)(grow0 + set) * rb + (size_t)(s_koff[k] + (u >> 2)) * 128 + (u & 3) * 32;
                 const float2* z = reinterpret_cast<const float2*>(s_buf + set * stride);
                 for (int r = set; r < nr; r += nset) {
                     float re[4], im[4];
@@ -408,7 +414,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
             const int nu = P.u1 - P.u0;
             for (int x = tid; x < nu * nr; x += kThreads) {
                 const int r = x / nu, u = P.u0 + (x - r * nu);
-                const int k = __ldg(plan.unit_nk + u);                         // the unit's longest half length
+                const int k = s_unk[u];                                        // the unit's longest half length
                 const float2* z = reinterpret_cast<const float2*>(s_buf + r * stride);
                 float re[4], im[4];
 #pragma unroll
@@ -419,11 +425,11 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                 }
                 uint4 hi, lo;
                 split_row_unit(re, im, hi, lo);
-                uint4* o4 = reinterpret_cast<uint4*>(spec + (size_t)(grow0 + r) * rb + (size_t)(__ldg(frag.koff + k) + (u >> 2)) * 128 + (u & 3) * 32);
+                uint4* o4 = reinterpret_cast<uint4*>(spec + (size_t)(grow0 + r) * rb + (size_t)(s_koff[k] + (u >> 2)) * 128 + (u & 3) * 32);
                 o4[0] = hi; o4[1] = lo;
             }
         }
-        if (tid == 0) s_nfrag = 0;             // read above before two barriers, next written after this phase's last one
+        if (tid < kThreads / 32) s_nfrag[tid] = 0;             // read above before two barriers, next written after this phase's last one
         __syncthreads();
     }
 
@@ -454,7 +460,9 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
 size_t cra_polar_group_smem(int nx, int maxrin, const CraGroupPlan& plan)
 {
     const size_t npix = ((size_t)(nx + 2) * (nx + 2) + 3) & ~(size_t)3;     // tile with the periodic border
-    return (npix + (size_t)plan.rmax * plan.stride) * sizeof(float) + (size_t)maxrin * sizeof(float2);
+    // + twiddles, ring table (<= CRA_MAX_RINGS int4), chunk offsets, unit lengths
+    return (npix + (size_t)plan.rmax * plan.stride) * sizeof(float) + (size_t)maxrin * sizeof(float2)
+         + (size_t)plan.nring * sizeof(int4) + (size_t)(maxrin / 2 + 2 + (plan.nring + 3) / 4) * sizeof(int);
 }
 
 int cra_launch_polar_group(const float* images, int nx, const CraRingTab* tab, const CraRingTab& htab,
