@@ -138,6 +138,27 @@ def mref_ali2d(images, refs, ir=1, ou=-1, rs=1, xr=0, yr=0, ts=1, center=1, maxi
     return params, assign, refs, history
 
 
+def search_schedule(xr, yr, ts):
+    """The reference parses --xr/--yr/--ts with get_input_from_string (test_reffree.py:173-174):
+    "4 2 1 1" / [4, 2, 1, 1] / 4 -> one (xr, yr, ts) per step; yr = -1 copies xr, a shorter list repeats
+    its last entry.  The shipped driver then pins N_step = 0 (test_reffree.py:310, :686); ali2d_base
+    here runs the whole schedule as Sphire's ali2d_base does."""
+    def lst(v):
+        if isinstance(v, str):
+            return [float(x) for x in v.split()]
+        try:
+            return [float(x) for x in v]
+        except TypeError:
+            return [float(v)]
+    xs, ys, tss = lst(xr), lst(yr), lst(ts)
+    if len(ys) == 1 and ys[0] == -1:
+        ys = list(xs)
+    n = len(xs)
+    ys = ys + [ys[-1]] * (n - len(ys))
+    tss = tss + [tss[-1]] * (n - len(tss))
+    return [(xs[i], ys[i], tss[i]) for i in range(n)]
+
+
 def ali2d_base(images, ir=1, ou=-1, rs=1, xr=0, yr=0, ts=1, center=-1, maxit=10, comm=None,
                total_particles=None, global_offset=0, engine=None, device=0, device_allreduce=True,
                on_iteration=None):
@@ -149,9 +170,13 @@ def ali2d_base(images, ir=1, ou=-1, rs=1, xr=0, yr=0, ts=1, center=-1, maxit=10,
     P = total_particles if total_particles is not None else n
     if ou == -1:
         ou = nx // 2 - 2
+    sched = search_schedule(xr, yr, ts)
     own_engine = engine is None
     if own_engine:
-        engine = Engine(nx, ou, xr, yr, ts=ts, ir=ir, rs=rs, max_particles=n, max_refs=1,
+        # sized for the largest window of the schedule: most positions per axis = max(range / step)
+        ts_min = min(t for _, _, t in sched)
+        kmax = max(int(max(x, y) / t) for x, y, t in sched)
+        engine = Engine(nx, ou, kmax * ts_min, kmax * ts_min, ts=ts_min, ir=ir, rs=rs, max_particles=n, max_refs=1,
                         normalize_ring=False, device=device)
     engine.upload_particles(images, subtract_mask_mean=True)          # data[im] -= infomask mean, test_reffree.py:663
     mask = ru.model_circle(ou, nx)
@@ -160,7 +185,10 @@ def ali2d_base(images, ir=1, ou=-1, rs=1, xr=0, yr=0, ts=1, center=-1, maxit=10,
     history = []
     tavg = None
     zeros = np.zeros(n, np.int32)
-    for it in range(int(maxit)):
+    total = len(sched) * int(maxit)
+    for it in range(total):
+        xr, yr, ts = sched[it // int(maxit)]                          # for N_step: for Iter (Sphire ali2d_base)
+        engine.set_step(ts)
         engine.zero_sums()
         engine.accumulate(0, n, params, zeros, global_offset)         # sum_oe(data, "a"), test_reffree.py:695
         sums, counts = _reduce_sums(engine, comm, device_allreduce)
@@ -174,7 +202,7 @@ def ali2d_base(images, ir=1, ou=-1, rs=1, xr=0, yr=0, ts=1, center=-1, maxit=10,
             tavg = ru.fshift(tavg, -cs[0], -cs[1])                    # test_reffree.py:741-745
         else:
             tavg, cs, filt = ru.ref_ali2d(tavg, frsc, center)
-        if it == int(maxit) - 1:
+        if it == total - 1:
             history.append(dict(criterion=crit, cs=cs, filter=filt, tavg=tavg.copy()))
             break
         engine.set_refs(tavg[None], normalize_mask=False)

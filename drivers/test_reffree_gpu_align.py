@@ -22,6 +22,8 @@ def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("stack"); ap.add_argument("outdir"); ap.add_argument("maskfile", nargs="?")
     add_alignment_flags(ap, reffree=True)
+    ap.add_argument("--first_step_only", action="store_true",
+                    help="use only entry 0 of the --xr/--yr/--ts lists, as the reference driver does")
     args = ap.parse_args(argv)
     from cryo_ralib_b200 import stackio, alignment as al
     from cryo_ralib_b200.lib import load_library
@@ -42,13 +44,19 @@ def main(argv=None):
     log = Log(args.outdir, rank)
     images = stackio.read_stack(args.stack)
     P, nx = images.shape[0], images.shape[-1]
-    xr = first_of(args.xr); yr = first_of(args.yr) if first_of(args.yr) >= 0 else xr; ts = first_of(args.ts)
+    from cryo_ralib_b200.mref import search_schedule
+    # the whole "--xr 4 2 1 --ts 2 1 0.5" schedule (Sphire ali2d_base); --first_step_only reproduces the
+    # reference driver, which pins N_step = 0 (test_reffree.py:310, :686)
+    sched = search_schedule(args.xr, args.yr, args.ts)
+    if args.first_step_only:
+        sched = sched[:1]
+    xr = [x for x, _, _ in sched]; yr = [y for _, y, _ in sched]; ts = [t for _, _, t in sched]
     ou = args.ou if args.ou != -1 else nx // 2 - 2
     maxit = args.maxit if args.maxit > 0 else 10
-    if ou + max(xr, yr) > (nx - 1) // 2:
+    if ou + max(max(xr), max(yr)) > (nx - 1) // 2:
         raise SystemExit("Shift or radius is too large - particle crosses image boundary")   # test_reffree.py:603
     s, e = al.mpi_start_end(P, world, rank)
-    log.add("ali2d_base: %d particles %dx%d, ir=%d ou=%d rs=%d xr=%g yr=%g ts=%g center=%d maxit=%d, %d GPU(s)"
+    log.add("ali2d_base: %d particles %dx%d, ir=%d ou=%d rs=%d xr=%s yr=%s ts=%s center=%d maxit=%d per step, %d GPU(s)"
             % (P, nx, nx, args.ir, ou, args.rs, xr, yr, ts, args.center, maxit, world))
     raw, filt = [], []
     t0 = [time.time()]

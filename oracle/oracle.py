@@ -494,6 +494,25 @@ def fsc_mask(img1, img2, mask):
     return fsc(a, b)
 
 
+def _schedule(xr, yr, ts):
+    """get_input_from_string semantics: "4 2 1" / [4, 2, 1] / 4 -> per-step (xr, yr, ts); yr = -1 copies xr,
+    a shorter ts list repeats its last entry."""
+    def lst(v):
+        if isinstance(v, str):
+            return [float(x) for x in v.split()]
+        try:
+            return [float(x) for x in v]
+        except TypeError:
+            return [float(v)]
+    xs, ys, tss = lst(xr), lst(yr), lst(ts)
+    if len(ys) == 1 and ys[0] == -1:
+        ys = list(xs)
+    n = len(xs)
+    ys = ys + [ys[-1]] * (n - len(ys))
+    tss = tss + [tss[-1]] * (n - len(tss))
+    return [(xs[i], ys[i], tss[i]) for i in range(n)]
+
+
 def ali2d_base(images, ir=1, ou=-1, rs=1, xr=0, yr=0, ts=1, center=-1, maxit=10, nthreads=1):
     """Reference-free alignment, CPU twin (ali2d_base, test_reffree.py:515-837; the per-particle
     step is Sphire's ali2d_single_iter -> ormq: no ring normalisation, clamped shifts, the
@@ -512,7 +531,12 @@ def ali2d_base(images, ir=1, ou=-1, rs=1, xr=0, yr=0, ts=1, center=-1, maxit=10,
     sx_sum = sy_sum = 0.0
     history = []
     tavg = None
-    for it in range(int(maxit)):
+    # Sphire ali2d_base: for N_step in range(len(xrng)): for Iter in range(max_iter) -- the shipped
+    # driver pins N_step = 0 (test_reffree.py:686); sequences run the whole schedule
+    sched = _schedule(xr, yr, ts)
+    total = len(sched) * int(maxit)
+    for it in range(total):
+        xr, yr, ts = sched[it // int(maxit)]
         ave = np.zeros((2, nx, nx), np.float32)
         for i in range(P):
             ave[i % 2] += rot_shift2d(imgs[i], params[i, 0], params[i, 1], params[i, 2], int(params[i, 3]))
@@ -525,7 +549,7 @@ def ali2d_base(images, ir=1, ou=-1, rs=1, xr=0, yr=0, ts=1, center=-1, maxit=10,
         else:
             tavg, cs, filt = ref_ali2d(mask, center, tavg, frsc)
         history.append(dict(cs=cs, filter=filt, tavg=tavg.copy()))
-        if it == int(maxit) - 1:
+        if it == total - 1:
             break
         cimage = applyws(frngs(polar2dm(tavg, float(cnx), float(cnx), numr), numr), numr, wr)[None]
         centres = np.zeros((P, 2), np.float32); win = np.zeros((P, 4), np.float32)

@@ -365,3 +365,21 @@ def test_reffree_iterations_match_oracle(oracle, small_set):
     assert same.mean() >= 0.9
     assert np.allclose(h_g[0]["cs"], h_o[0]["cs"], atol=1e-6)
     assert np.abs(t_g - t_o).sum() / np.abs(t_o).sum() < 0.05
+
+
+def test_reffree_multi_step_schedule_matches_oracle(oracle, small_set):
+    """--xr "2 1" --ts "1 0.5": the search schedule of Sphire's ali2d_base; the second
+    step runs the sub-pixel path (general row kernel), the first the grouped one."""
+    from cryo_ralib_b200.mref import ali2d_base, search_schedule
+    assert search_schedule("4 2 1 1", "-1", "2 1 0.5 0.25") == [(4, 4, 2), (2, 2, 1), (1, 1, 0.5), (1, 1, 0.25)]
+    assert search_schedule(3, 2, 1) == [(3, 2, 1)] and search_schedule("3 1", "2", "1") == [(3, 2, 1), (1, 2, 1)]
+    images, _, _ = small_set
+    p_o, t_o, h_o = oracle.ali2d_base(images[:32], ou=36, xr="2 1", yr="-1", ts="1 0.5", center=-1, maxit=2, nthreads=8)
+    p_g, t_g, h_g = ali2d_base(images[:32], ou=36, xr="2 1", yr="-1", ts="1 0.5", center=-1, maxit=2)
+    assert len(h_g) == len(h_o) == 4
+    for k in range(3):
+        rel = np.abs(h_g[k]["peak"] - h_o[k]["peak"]) / np.abs(h_o[k]["peak"])
+        assert np.median(rel) < PEAK_RTOL
+    same = (np.abs(p_g[:, 3] - p_o[:, 3]) < 0.5) & (np.abs(p_g[:, 1] - p_o[:, 1]) < 0.05) & (np.abs(p_g[:, 2] - p_o[:, 2]) < 0.05)
+    assert same.mean() >= 0.85
+    assert np.abs(t_g - t_o).sum() / np.abs(t_o).sum() < 0.05
