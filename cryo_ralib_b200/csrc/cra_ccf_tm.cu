@@ -26,7 +26,10 @@
 
 namespace {
 
-constexpr int kWarps = 8;
+#ifndef CRA_TM_WARPS
+#define CRA_TM_WARPS 8
+#endif
+constexpr int kWarps = CRA_TM_WARPS;      // a multiple of 4: kWarps / 4 warps share each TMEM quadrant
 constexpr int kThreads = kWarps * 32;
 constexpr int kMaxItems = 640;          // chunk items per warp
 constexpr int kMaxFreq = 160;           // frequencies per warp
@@ -226,6 +229,7 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
             }
         };
 
+#if CRA_TM_WARPS <= 8
         // four operand sets rotate: three chunk loads are always in flight behind the one being multiplied
         Operands<NJ> o0, o1, o2, o3;
         if (nit > 0) CRA_LOAD_OPS(o0, items[0]);
@@ -248,6 +252,25 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
             if (i + 6 < nit) CRA_LOAD_OPS(o2, items[i + 6]);
             CRA_COMPUTE(o3, e3);
         }
+#else
+        // three operand sets (register budget of the wider CTA)
+        Operands<NJ> o0, o1, o2;
+        if (nit > 0) CRA_LOAD_OPS(o0, items[0]);
+        if (nit > 1) CRA_LOAD_OPS(o1, items[1]);
+        for (int i = 0; i < nit; i += 3) {
+            const int e0 = items[i];
+            if (i + 2 < nit) CRA_LOAD_OPS(o2, items[i + 2]);
+            CRA_COMPUTE(o0, e0);
+            if (i + 1 >= nit) break;
+            const int e1 = items[i + 1];
+            if (i + 3 < nit) CRA_LOAD_OPS(o0, items[i + 3]);
+            CRA_COMPUTE(o1, e1);
+            if (i + 2 >= nit) break;
+            const int e2 = items[i + 2];
+            if (i + 4 < nit) CRA_LOAD_OPS(o1, items[i + 4]);
+            CRA_COMPUTE(o2, e2);
+        }
+#endif
 #undef CRA_LOAD_OPS
 #undef CRA_COMPUTE
     }
@@ -373,7 +396,7 @@ int bind_schedule(const CraRingTab& h, const std::vector<int>& koff, cudaStream_
         if ((int)qres[q].size() != RQ) { cra_set_error("tensor-memory CCF kernel: residue assignment failed"); return 1; }
         for (int i = 0; i < RQ; ++i) { h_res[q][i] = qres[q][i]; ridx[qres[q][i]] = i; rquad[qres[q][i]] = q; }
     }
-    // frequencies of quadrant q -> its warps q and q + 4 (longest-processing-time first)
+    // frequencies of quadrant q -> its warps q, q + 4, ... (longest-processing-time first)
     std::vector<std::vector<int>> lists(kWarps), flush(kWarps);
     std::vector<int> load(kWarps, 0);
     int maxc = 0;
@@ -382,7 +405,8 @@ int bind_schedule(const CraRingTab& h, const std::vector<int>& koff, cudaStream_
         for (int k = 0; k < nk; ++k) {
             if (nch(k) != c) continue;
             const int n2 = k & (N2 - 1), q = rquad[n2];
-            const int w = (load[q] <= load[q + 4]) ? q : q + 4;
+            int w = q;
+            for (int ww = q + 4; ww < kWarps; ww += 4) if (load[ww] < load[w]) w = ww;
             for (int j = 0; j < c; ++j) lists[w].push_back((koff[k] + j) | ((j == c - 1) ? (1 << 23) : 0));
             const int kk = (N - k) & (N - 1);
             const int col0 = (ridx[n2] * N1 + (k >> L2)) * 2;
