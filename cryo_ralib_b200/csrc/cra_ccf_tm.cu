@@ -230,26 +230,28 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
         };
 
 #if CRA_TM_WARPS <= 8
-        // four operand sets rotate: three chunk loads are always in flight behind the one being multiplied
+        // Four operand sets, loaded two chunks at a time.  ptxas keeps every operand LDG on one hardware
+        // scoreboard and drains it before the oldest set is used (profiles/README.md), so what a load gets
+        // to hide behind is the work issued between its batch and the next drain: issuing the loads in
+        // pairs (drain, load chunks i+2 and i+3, multiply chunks i and i+1) doubles that window.
         Operands<NJ> o0, o1, o2, o3;
         if (nit > 0) CRA_LOAD_OPS(o0, items[0]);
         if (nit > 1) CRA_LOAD_OPS(o1, items[1]);
-        if (nit > 2) CRA_LOAD_OPS(o2, items[2]);
         for (int i = 0; i < nit; i += 4) {
             const int e0 = items[i];
+            const int e1 = (i + 1 < nit) ? items[i + 1] : 0;
+            if (i + 2 < nit) CRA_LOAD_OPS(o2, items[i + 2]);
             if (i + 3 < nit) CRA_LOAD_OPS(o3, items[i + 3]);
             CRA_COMPUTE(o0, e0);
             if (i + 1 >= nit) break;
-            const int e1 = items[i + 1];
-            if (i + 4 < nit) CRA_LOAD_OPS(o0, items[i + 4]);
             CRA_COMPUTE(o1, e1);
             if (i + 2 >= nit) break;
             const int e2 = items[i + 2];
+            const int e3 = (i + 3 < nit) ? items[i + 3] : 0;
+            if (i + 4 < nit) CRA_LOAD_OPS(o0, items[i + 4]);
             if (i + 5 < nit) CRA_LOAD_OPS(o1, items[i + 5]);
             CRA_COMPUTE(o2, e2);
             if (i + 3 >= nit) break;
-            const int e3 = items[i + 3];
-            if (i + 6 < nit) CRA_LOAD_OPS(o2, items[i + 6]);
             CRA_COMPUTE(o3, e3);
         }
 #else
