@@ -373,6 +373,16 @@ extern "C" int cra_create(const CraConfig* cfg, int device, CraCtx** out)
         else if (pk && strcmp(pk, "group") != 0 && pk[0]) { cra_set_error("CRA_POLAR must be 'group' or 'general'"); cra_destroy(c); return 1; }
     }
     if (build_tables(c)) { cra_destroy(c); return 1; }
+    {   // the references (and sub-pixel steps) go through the general row kernel: image + one whole polar row in shared memory
+        int smem_blk = 0;
+        cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+        const size_t need = cra_polar_general_smem(c->nx, c->htab) + 4096;
+        if (need > (size_t)smem_blk) {
+            cra_set_error("box too large for this build: image + one polar row need " + std::to_string(need / 1024) +
+                          " KB of shared memory (limit " + std::to_string(smem_blk / 1024) + " KB); reduce nx or ou");
+            cra_destroy(c); return 1;
+        }
+    }
     const int k = (int)(cfg->max_range / cfg->step);
     c->smax = (2 * k + 1) * (2 * k + 1);
     const size_t row_bytes = (c->fmt == CRA_FMT_FRAG) ? cra_frag_row_bytes(c->frag.nch)

@@ -136,6 +136,7 @@ int cra_launch_mask_normalize(float* imgs, int n, int nx, const float* mask, int
 // particle rows described by map -> spec[row]; references -> refspec (weights applied)
 // twid_fwd[j] = exp(-2 pi i j / maxrin), j < maxrin
 int cra_polar_rows_per_block();
+size_t cra_polar_general_smem(int nx, const CraRingTab& htab);
 // norm: [rows] (avg, 1/sigma) written by the row kernels (FRAG format only, may be null otherwise);
 // tref: [R] written by the reference kernel (FRAG format only)
 int cra_launch_polar_rows(const float* images, int nx, const CraRingTab* tab, const CraRingTab& htab,

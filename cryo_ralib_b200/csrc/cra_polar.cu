@@ -503,6 +503,9 @@ int launch_polar(const float* images, int nx, const CraRingTab* tab, const CraRi
 
 int cra_polar_rows_per_block() { return CRA_POLAR_RPB; }
 
+// dynamic shared memory the general kernel needs for one row (references, test entries)
+size_t cra_polar_general_smem(int nx, const CraRingTab& htab) { return polar_smem_bytes<1>(nx, htab); }
+
 int cra_launch_mask_normalize(float* imgs, int n, int nx, const float* mask, int mode, cudaStream_t st)
 {
     if (n <= 0) return 0;

@@ -191,9 +191,9 @@ def test_align_ragged_windows_fractional_centres_and_half_step(oracle, small_set
     e.close()
 
 
-@pytest.mark.parametrize("nx,ou,xr", [(128, 56, 2), (48, 16, 2), (64, 29, 1)])
+@pytest.mark.parametrize("nx,ou,xr", [(128, 56, 2), (48, 16, 2), (64, 29, 1), (160, 70, 1), (32, 9, 2)])
 def test_align_other_ring_geometries(oracle, nx, ou, xr):
-    """maxrin 512 / 128 / 256 with odd reference counts and row counts."""
+    """maxrin 512 / 128 / 256 / 512 on a large box / 64 with odd reference counts and row counts."""
     from cryo_ralib_b200 import synth, alignment as al
     P, R = 9, 5
     images, _ = synth.make_particles(P, nx, 8, max_shift=xr, seed=21)
@@ -208,6 +208,13 @@ def test_align_other_ring_geometries(oracle, nx, ou, xr):
     exact, ties, bad = _compare_alignment(got, want, int(numr[-1]))
     assert not bad, bad[:5]
     e.close()
+
+
+def test_box_beyond_shared_memory_is_refused_cleanly():
+    """nx=180, ou=84 (maxrin 1024): image + one polar row exceed a CTA's shared memory; cra_create says so."""
+    from cryo_ralib_b200.lib import CraError
+    with pytest.raises(CraError, match="box too large"):
+        _engine(180, 84, 1)
 
 
 def test_closed_loop_recovers_known_pose(oracle):
