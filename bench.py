@@ -318,7 +318,7 @@ def main():
                              ms_per_step=ms_e2e / args.steps),
                     gpu_launches=int(agg["launches"]),
                     clocks=clocks,
-                    roofline=dict(kernel="ccf_mma_kernel (Crosrng_ms contraction on mma.sync split-bf16 x3 + inverse FFT + peak search)",
+                    roofline=dict(kernel="ccf_tm_kernel (Crosrng_ms contraction on mma.sync split-bf16 x3, W in tensor memory, + inverse FFT + peak search)",
                                   bound="tensor", achieved=ccf_tflops, peak=tensor_peak, unit="TFLOP/s",
                                   frac=ccf_tflops / tensor_peak,
                                   traffic=prof.get("ccf_dram_bytes_per_launch"),
@@ -329,7 +329,7 @@ def main():
                                        "see roofline_fp32_equiv and DESIGN.md 3.2 for the ceilings that actually bind",
                                   flops_per_alignment=fpa, avg_launch_ms=agg["ms_ccf"] / max(agg["ccf_launches"], 1),
                                   share_of_step=agg["ms_ccf"] / ms_res),
-                    roofline_fp32_equiv=dict(kernel="ccf_mma_kernel", bound="fp32", achieved=ccf_tflops, peak=fp32, unit="TFLOP/s",
+                    roofline_fp32_equiv=dict(kernel="ccf_tm_kernel", bound="fp32", achieved=ccf_tflops, peak=fp32, unit="TFLOP/s",
                                              frac=ccf_tflops / fp32 if fp32 else None,
                                              note="same algorithmic flops over the FFMA micro-benchmark measured in this run "
                                                   "(what an FP32 SIMT implementation could reach at best)"),

@@ -1,4 +1,5 @@
-"""Quick device probe: FP32 peak micro-benchmark + stage timings on a config-2-shaped slice."""
+"""Quick device probe: FP32 peak micro-benchmark + stage timings on a config-2-shaped slice.
+usage: gpu_probe.py [P] [R] [nx] [ou] [xr]"""
 import json
 import sys
 import time
@@ -10,7 +11,9 @@ from cryo_ralib_b200 import Engine, synth, alignment as al  # noqa: E402
 
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 R = int(sys.argv[2]) if len(sys.argv) > 2 else 50
-nx, ou, xr = 90, 36, 3
+nx = int(sys.argv[3]) if len(sys.argv) > 3 else 90
+ou = int(sys.argv[4]) if len(sys.argv) > 4 else 36
+xr = int(sys.argv[5]) if len(sys.argv) > 5 else 3
 images, _ = synth.make_particles(P, nx, 64, seed=2025)
 refs = synth.initial_references(images, R, seed=99)
 e = Engine(nx, ou, xr, max_particles=P, max_refs=R)
