@@ -53,6 +53,8 @@ struct CraCtx {
     // CRA_FMT_F32 = FP32 FMA kernel on the float2 spectrum (CRA_CCF=simt)
     int fmt = CRA_FMT_FRAG;
     bool use_tm = true;          // W staged in tensor memory (cra_ccf_tm.cu); CRA_CCF=mma keeps it in shared memory
+    bool use_um = false;         // contraction on tcgen05.mma (cra_ccf_um.cu); CRA_CCF=um, maxrin 256
+    unsigned char* d_refimg = nullptr;   // UMMA reference operand images
     CraFragTab frag{};
     std::vector<int> h_koff, h_chunk_k;
     int* d_fragtab = nullptr;
@@ -367,7 +369,8 @@ extern "C" int cra_create(const CraConfig* cfg, int device, CraCtx** out)
         const char* e = getenv("CRA_CCF");
         if (e && strcmp(e, "simt") == 0) c->fmt = CRA_FMT_F32;
         else if (e && strcmp(e, "mma") == 0) c->use_tm = false;
-        else if (e && strcmp(e, "tm") != 0 && e[0]) { cra_set_error("CRA_CCF must be 'tm', 'mma' or 'simt'"); cra_destroy(c); return 1; }
+        else if (e && strcmp(e, "um") == 0) c->use_um = true;
+        else if (e && strcmp(e, "tm") != 0 && e[0]) { cra_set_error("CRA_CCF must be 'um', 'tm', 'mma' or 'simt'"); cra_destroy(c); return 1; }
         const char* pk = getenv("CRA_POLAR");
         if (pk && strcmp(pk, "general") == 0) c->use_group = false;
         else if (pk && strcmp(pk, "group") != 0 && pk[0]) { cra_set_error("CRA_POLAR must be 'group' or 'general'"); cra_destroy(c); return 1; }
@@ -394,7 +397,9 @@ extern "C" int cra_create(const CraConfig* cfg, int device, CraCtx** out)
     if (rb > want) rb = want;
     c->row_batch = (int)rb;
     if (!cra_ccf_tm_supported(c->htab.log2n)) c->use_tm = false;
-    c->ntile_n_max = (c->fmt == CRA_FMT_FRAG) ? (c->use_tm ? cra_ccf_tm_num_tiles(cfg->max_refs, c->htab.log2n)
+    if (c->fmt != CRA_FMT_FRAG || !cra_ccf_um_supported(c->htab.log2n)) c->use_um = false;
+    c->ntile_n_max = (c->fmt == CRA_FMT_FRAG) ? (c->use_um ? cra_ccf_um_num_tiles(cfg->max_refs)
+                                                 : c->use_tm ? cra_ccf_tm_num_tiles(cfg->max_refs, c->htab.log2n)
                                                            : cra_ccf_mma_num_tiles(cfg->max_refs, c->htab.log2n))
                                               : (cfg->max_refs + cra_ccf_tile_n() - 1) / cra_ccf_tile_n();
     const size_t nsum = (size_t)cfg->max_refs * 2 * c->npix + cfg->max_refs;
@@ -411,6 +416,7 @@ extern "C" int cra_create(const CraConfig* cfg, int device, CraCtx** out)
     if (e == cudaSuccess) e = cudaMalloc(&c->d_norm, ((size_t)c->row_batch + 4) * sizeof(float2));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_tref, ref_groups * 4 * sizeof(float));
     if (e == cudaSuccess) e = cudaMemset(c->d_tref, 0, ref_groups * 4 * sizeof(float));
+    if (e == cudaSuccess && c->use_um) e = cudaMalloc(&c->d_refimg, cra_ccf_um_refimg_bytes(cfg->max_refs, c->frag.nch));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_sums, nsum * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_curves, (size_t)2 * c->htab.maxrin * sizeof(float));
     if (e == cudaSuccess) e = cudaMemset(c->d_sums, 0, nsum * sizeof(float));
@@ -429,7 +435,7 @@ extern "C" int cra_destroy(CraCtx* c)
     for (auto& p : c->pending) cudaEventDestroy(p.ev);
     for (auto& e : c->ev_pool) cudaEventDestroy(e);
     if (c->st_copy) cudaStreamDestroy(c->st_copy);
-    cudaFree(c->d_items); cudaFree(c->d_fragtab); cudaFree(c->d_norm); cudaFree(c->d_tref); cudaFree(c->d_plan);
+    cudaFree(c->d_items); cudaFree(c->d_fragtab); cudaFree(c->d_norm); cudaFree(c->d_tref); cudaFree(c->d_plan); cudaFree(c->d_refimg);
     cudaFree(c->d_tab); cudaFree(c->d_samp); cudaFree(c->d_sampw); cudaFree(c->d_twf); cudaFree(c->d_twi);
     cudaFree(c->d_mask); cudaFree(c->d_images); cudaFree(c->d_refs); cudaFree(c->d_refspec);
     cudaFree(c->d_spec); cudaFree(c->d_cand); cudaFree(c->d_sums); cudaFree(c->d_meta); cudaFree(c->d_res);
@@ -505,6 +511,7 @@ extern "C" int cra_set_refs(CraCtx* c, const float* h, int R, int normalize_mask
     if (normalize_mask && cra_launch_mask_normalize(c->d_refs, R, c->nx, c->d_mask, 1, c->st)) return 1;
     if (cra_launch_polar_refs(c->d_refs, R, c->nx, c->d_tab, c->htab, c->d_samp, c->d_twf, c->items, c->d_refspec,
                               c->fmt, c->frag, c->d_tref, c->st)) return 1;
+    if (c->use_um && cra_ccf_um_pack_refs(reinterpret_cast<const unsigned char*>(c->d_refspec), R, c->frag, c->d_refimg, c->st)) return 1;
     CRA_CUDA(cudaStreamSynchronize(c->st));
     c->R = R;
     return 0;
@@ -586,7 +593,8 @@ extern "C" int cra_align(CraCtx* c, int start, int stop, const CraSearch* search
     const int* d_cs = d_rs + n + nb;
 
     const int TN = cra_ccf_tile_n();
-    const int ntile_n = (c->fmt == CRA_FMT_FRAG) ? (c->use_tm ? cra_ccf_tm_num_tiles(c->R, c->htab.log2n)
+    const int ntile_n = (c->fmt == CRA_FMT_FRAG) ? (c->use_um ? cra_ccf_um_num_tiles(c->R)
+                                                    : c->use_tm ? cra_ccf_tm_num_tiles(c->R, c->htab.log2n)
                                                               : cra_ccf_mma_num_tiles(c->R, c->htab.log2n)) : (c->R + TN - 1) / TN;
     const bool tm = c->timing;
     if (tm) {
@@ -607,7 +615,10 @@ extern "C" int cra_align(CraCtx* c, int start, int stop, const CraSearch* search
         } else if (cra_launch_polar_rows(c->d_images, c->nx, c->d_tab, c->htab, c->d_samp, c->d_sampw, c->d_twf, c->items, map,
                                          c->cfg.normalize_ring, c->d_spec, c->fmt, c->frag, c->d_norm, c->st)) return 1;
         if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 1], c->st));
-        if (c->fmt == CRA_FMT_FRAG && c->use_tm) {
+        if (c->fmt == CRA_FMT_FRAG && c->use_um) {
+            if (cra_launch_ccf_um(reinterpret_cast<const unsigned char*>(c->d_spec), map.nrows, c->d_refimg, c->R, c->htab, c->frag,
+                                  c->h_koff, c->d_twi, c->d_cand, ntile_n, c->d_norm, c->d_tref, c->st)) return 1;
+        } else if (c->fmt == CRA_FMT_FRAG && c->use_tm) {
             if (cra_launch_ccf_tm(reinterpret_cast<const unsigned char*>(c->d_spec), map.nrows,
                                   reinterpret_cast<const unsigned char*>(c->d_refspec), c->R, c->htab, c->frag, c->h_koff,
                                   c->d_twi, c->d_cand, ntile_n, c->d_norm, c->d_tref, c->st)) return 1;

@@ -164,6 +164,14 @@ int cra_ccf_tm_num_tiles(int R, int log2n);
 int cra_launch_ccf_tm(const unsigned char* spec, int nrows, const unsigned char* refspec, int R, const CraRingTab& htab,
                       const CraFragTab& frag, const std::vector<int>& h_koff, const float2* twid, CraCand* cand,
                       int ntile_n, const float2* norm, const float* tref, cudaStream_t st);
+// the contraction on tcgen05.mma, W streamed through tensor memory class by class (cra_ccf_um.cu; maxrin 256)
+bool cra_ccf_um_supported(int log2n);
+int cra_ccf_um_num_tiles(int R);
+size_t cra_ccf_um_refimg_bytes(int max_refs, int nch);
+int cra_ccf_um_pack_refs(const unsigned char* refspec, int R, const CraFragTab& frag, unsigned char* img, cudaStream_t st);
+int cra_launch_ccf_um(const unsigned char* spec, int nrows, const unsigned char* refimg, int R, const CraRingTab& htab,
+                      const CraFragTab& frag, const std::vector<int>& h_koff, const float2* twid, CraCand* cand,
+                      int ntile_n, const float2* norm, const float* tref, cudaStream_t st);
 int cra_launch_ccf(const float* spec, int nrows, const float* refspec, int R, const CraRingTab* tab,
                    const CraRingTab& htab, const float2* twid, CraCand* cand, int ntile_n, cudaStream_t st);
 int cra_ccf_tile_n();
