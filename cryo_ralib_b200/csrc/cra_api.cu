@@ -398,6 +398,7 @@ extern "C" int cra_create(const CraConfig* cfg, int device, CraCtx** out)
     c->row_batch = (int)rb;
     if (!cra_ccf_tm_supported(c->htab.log2n)) c->use_tm = false;
     if (c->fmt != CRA_FMT_FRAG || !cra_ccf_um_supported(c->htab.log2n)) c->use_um = false;
+    c->frag.unit_rows = c->use_um ? 1 : 0;
     c->ntile_n_max = (c->fmt == CRA_FMT_FRAG) ? (c->use_um ? cra_ccf_um_num_tiles(cfg->max_refs)
                                                  : c->use_tm ? cra_ccf_tm_num_tiles(cfg->max_refs, c->htab.log2n)
                                                            : cra_ccf_mma_num_tiles(cfg->max_refs, c->htab.log2n))
@@ -770,7 +771,7 @@ static void unpack_spectrum(const CraCtx* c, int lane4, float* out, bool row_lay
                 const int s = t.nring - 1 - i, gc = c->h_koff[k] + (s >> 4), tq = (s & 15) >> 2, j = s & 3;
                 const unsigned short* u = reinterpret_cast<const unsigned short*>(fb + (size_t)gc * 128 + tq * 32);
                 auto bf = [](unsigned short h) { unsigned int b = (unsigned int)h << 16; float f; memcpy(&f, &b, 4); return f; };
-                if (row_layout) {     // hi{re01, im01, re23, im23}, lo{same}
+                if (row_layout && !c->frag.unit_rows) {     // hi{re01, im01, re23, im23}, lo{same}
                     const int w = 4 * (j >> 1) + (j & 1);
                     v.x = bf(u[w]) + bf(u[8 + w]);
                     v.y = bf(u[2 + w]) + bf(u[10 + w]);

@@ -409,7 +409,8 @@ __device__ void pair_freq_frag(const unsigned char* __restrict__ rowp, const uns
             const uint4* cp = reinterpret_cast<const uint4*>(refp + (size_t)gc * 128 + t * 32);
             // row: A-operand order hi{re01, im01, re23, im23}, lo{same}; reference: [re unit | im unit]
             const uint4 dhi = dp[0], dlo = dp[1], cre = cp[0], cim = cp[1];
-            const uint4 dre = make_uint4(dhi.x, dhi.z, dlo.x, dlo.z), dim = make_uint4(dhi.y, dhi.w, dlo.y, dlo.w);
+            const uint4 dre = frag.unit_rows ? dhi : make_uint4(dhi.x, dhi.z, dlo.x, dlo.z);
+            const uint4 dim = frag.unit_rows ? dlo : make_uint4(dhi.y, dhi.w, dlo.y, dlo.w);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float dx = frag_val(dre, j), dy = frag_val(dim, j), cx = frag_val(cre, j), cy = frag_val(cim, j);

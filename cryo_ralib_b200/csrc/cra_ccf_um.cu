@@ -21,12 +21,27 @@
 // accumulator layout), double buffered against the consumer warps.  With the m16n8-like
 // tcgen05.ld.16x256b every consumer thread receives W[k] and W[N-k] of ITS pair (row 8q + lane/4,
 // reference lane%4), runs the two N1-point DFTs of the class in registers and parks the result Y in
-// its own TMEM lane (residues < N2/2, 32x32b) or its own shared-memory column (the others).  Pass 2
-// (N2-point DFTs over the residues), the ">=" argmax, the straight/mirror choice and the best
-// reference are then thread-local.  Operands: producer warps read the fragment spectra as the row
-// kernels wrote them (cra_common.cuh), permute words into the UMMA K-major core-matrix layout and
-// hand stages to the MMA warp through mbarriers; the reference operand is a prebuilt 1 KB image per
-// (4-reference tile, chunk).  One CTA per SM: 8 consumer + 8 producer warps + 1 MMA warp.
+// its own TMEM lane (12 of the 16 residues, 32x32b, 384 columns) or its own shared-memory column (the
+// other 4).  Pass 2 (N2-point DFTs over the residues), the ">=" argmax, the straight/mirror choice and
+// the best reference are then thread-local.
+// Operands.  With CRA_CCF=um the row kernels write particle rows in the reference layout
+// (CraFragTab::unit_rows, cra_common.cuh): a 16-byte unit [hi x4 | lo x4] of one (row, part) is one
+// row of a UMMA K-major core matrix, so a producer warp moves it with one 16-byte cp.async, no
+// registers held (the CUTLASS sm100 cp.async mainloop pattern: completion arrives on the stage's
+// mbarrier, no proxy fence).  The reference operand is a prebuilt 1 KB image per (4-reference tile,
+// chunk).  One thread issuing every MMA paces the contraction (~55 SASS instructions per chunk), so the
+// frequency slots of a class are dealt to FOUR independent pipelines (producer warp + MMA warp +
+// 7-stage ring each): different slots are different accumulator columns and need no ordering.
+// One CTA per SM: 8 consumer warps + 4 producer warps + 4 MMA warps, 207 KB of shared memory, all 512
+// TMEM columns.
+// Status (profiles/README.md): parity suite green; 10.6 ms per 5.0M alignments against 4.8 ms of the
+// mma.sync kernel (cra_ccf_tm.cu), which stays the default.  ncu: tensor pipe 4.5 %, L2->SM 63 GB per
+// launch = 12 KB per pair at 51 % of the L2 throughput peak: a 128-pair tile re-reads its 32 rows for
+// every 4 references, and that operand delivery binds, as it does for the mma.sync kernel (34 GB).
+// What would lift it: cluster multicast of the row operand (TMA 5-D tensor map box = one chunk of
+// 32 rows in core-matrix order, multicast to the CTAs of a cluster that share the row tile).
+// CRA_UM_DBG bits (timing experiments, not valid kernels): 1 no MMAs, 8 no pass 1, 16 one pass-2
+// iteration, 32 clock64 timestamps of CTA 200 printed by the launcher.
 #include "cra_common.cuh"
 #include "cra_fft.cuh"
 #include <cuda_bf16.h>
@@ -39,24 +54,24 @@
 namespace {
 
 constexpr int LOG2N = 8, N = 256, N1 = 16, N2 = 16;
-constexpr int kConsWarps = 8, kProdWarps = 8;
-constexpr int kThreads = (kConsWarps + kProdWarps + 1) * 32;     // 544
-constexpr int kStages = 4;                  // shared-memory operand stages
-constexpr int kCps = 2;                     // chunks per stage
-constexpr int kDepth = 4;                   // stages a producer thread keeps in flight in registers
+constexpr int kConsWarps = 8;
+constexpr int kPipes = 4;                   // independent operand pipelines: one producer warp + one MMA warp each
+constexpr int kThreads = (kConsWarps + 2 * kPipes) * 32;         // 512
+constexpr int kStages = 7;                  // shared-memory operand stages per pipeline (one chunk each)
 constexpr int kABytes = 4096, kBBytes = 1024;          // per chunk
-constexpr int kStageBytes = kCps * (kABytes + kBBytes);
-constexpr int kMaxItems = 1024;
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kMaxItems = 256;              // chunks per pipeline
 constexpr int kTmemCols = 512;
 constexpr int kYCol = 128;                  // first TMEM column of the Y store (D tiles: columns 0..127)
+constexpr int kYT = 12;                     // residues whose Y lives in TMEM (12 x 16 x 2 = 384 columns); the other 4 in shared memory
 constexpr int kPfDist = 36;                 // row tiles between an L2 prefetch and its use (~11 row tiles are resident at a time)
 constexpr unsigned kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 17) | (4u << 24);   // f32 acc, bf16 x bf16, K-major, N = 8, M = 64
 
 // work list, chunk by chunk in class order:
 //   bits 0..6 TMEM column of the frequency slot (slot * 8) | 7..19 chunk index gc | 20 class buffer (TMEM lane 16)
 //   | 24 first chunk of its frequency | 25 last chunk of its class | 26 first chunk of its class | 27 valid
-__device__ int g_items[kMaxItems];
-__device__ int g_nitems;
+__device__ int g_items[kPipes][kMaxItems];
+__device__ int g_nitems[kPipes];
 __device__ long long g_dbg[32];
 #define UM_T(i) do { if ((dbg & 32) && blockIdx.x == 200) g_dbg[i] = clock64(); } while (0)
 
@@ -78,22 +93,37 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* b)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(b)) : "memory");
 }
-__device__ int g_waitmode;
 __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity)
 {
     const unsigned a = smem_u32(b);
-    unsigned done = 0;
-    long spins = 0;
-    const int mode = g_waitmode;
+    unsigned done = 0, spins = 0;
     while (!done) {
-        if (mode == 0)
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(a), "r"(parity) : "memory");
-        else
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
-        if (!done && ++spins > (1L << 26)) __trap();       // a lost arrival must not hang the device
+        if (!done && ++spins > (1u << 26)) __trap();       // a lost arrival must not hang the device
     }
+}
+// the same for a warp that can afford to be late: a failed poll backs off, so that the consumer warps waiting for a
+// class do not take the issue slots of the producer and MMA warps that share their schedulers
+__device__ __forceinline__ void mbar_wait_relaxed(unsigned long long* b, unsigned parity)
+{
+    const unsigned a = smem_u32(b);
+    unsigned done = 0, spins = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(256);
+        if (++spins > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(unsigned long long* b)      // arrives once this thread's copies have landed
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(b)) : "memory");
 }
 __device__ __forceinline__ bool elect_one()
 {
@@ -149,6 +179,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(unsigned taddr, float2 (&x)[8
 #pragma unroll
     for (int i = 0; i < 8; ++i) x[i] = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x8(unsigned taddr, float2 (&x)[4])
+{
+    unsigned r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+}
 __device__ __forceinline__ void tmem_st2(unsigned taddr, float2 v)
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" :: "r"(taddr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)) : "memory");
@@ -158,21 +197,11 @@ __device__ __forceinline__ void cons_sync()      // the consumer warps only
     asm volatile("bar.sync 1, %0;" :: "n"(kConsWarps * 32) : "memory");
 }
 
-struct Frag8 { unsigned w[8]; };
-__device__ __forceinline__ Frag8 ldg256(const unsigned char* p)
-{
-    Frag8 f;
-    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(f.w[0]), "=r"(f.w[1]), "=r"(f.w[2]), "=r"(f.w[3]), "=r"(f.w[4]), "=r"(f.w[5]), "=r"(f.w[6]), "=r"(f.w[7])
-                 : "l"(p));
-    return f;
-}
-
 // Y of residue n2, output k1: TMEM column (n2 < 8) or shared-memory float2 index (n2 >= 8) of this pair
 __device__ __forceinline__ void store_y(unsigned ybase, float2* sy, int n2, int k1, float2 v)
 {
-    if (n2 < N2 / 2) tmem_st2(ybase + (k1 * (N2 / 2) + n2) * 2, v);
-    else sy[(k1 * (N2 / 2) + (n2 - N2 / 2)) * 128] = v;
+    if (n2 < kYT) tmem_st2(ybase + (k1 * kYT + n2) * 2, v);
+    else sy[(k1 * (N2 - kYT) + (n2 - kYT)) * 128] = v;
 }
 // pass 1 of one residue: x[n1] = W[n1 N2 + n2] -> N1-point inverse DFT, twiddle, park
 __device__ __forceinline__ void pass1(float2 (&x)[N1], int n2, unsigned ybase, float2* sy, const float2* __restrict__ s_tw)
@@ -188,14 +217,14 @@ __device__ __forceinline__ void pass1(float2 (&x)[N1], int n2, unsigned ybase, f
 __global__ void __launch_bounds__(kThreads, 1)
 ccf_um_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned char* __restrict__ refimg, int R,
               size_t row_bytes, int nch, const float2* __restrict__ twid, CraCand* __restrict__ cand, int ncta_n,
-              const float2* __restrict__ norm, const float* __restrict__ tref, int nitems, int cls_n2_packed_lo, int cls_n2_packed_hi, int dbg)
+              const float2* __restrict__ norm, const float* __restrict__ tref, int istride, int cls_n2_packed_lo, int cls_n2_packed_hi, int dbg)
 {
     extern __shared__ __align__(1024) unsigned char s_raw[];
-    unsigned char* s_stage = s_raw;                                            // kStages * kStageBytes
-    float2* s_y = reinterpret_cast<float2*>(s_raw + kStages * kStageBytes);    // 8 * 16 * 128 float2 = 128 KB
-    float2* s_tw = s_y + (N2 / 2) * N1 * 128;                                  // N
-    int* s_items = reinterpret_cast<int*>(s_tw + N);                           // nitems (padded to kCps)
-    __shared__ __align__(8) unsigned long long s_full[kStages], s_empty[kStages], s_dfull[2], s_dempty[2];
+    unsigned char* s_stage = s_raw;                                            // kPipes * kStages * kStageBytes
+    float2* s_y = reinterpret_cast<float2*>(s_raw + kPipes * kStages * kStageBytes);    // 4 * 16 * 128 float2 = 64 KB
+    float2* s_tw = s_y + (N2 - kYT) * N1 * 128;                                // N
+    int* s_items = reinterpret_cast<int*>(s_tw + N);                           // kPipes * istride
+    __shared__ __align__(8) unsigned long long s_full[kPipes][kStages], s_empty[kPipes][kStages], s_dfull[2], s_dempty[2];
     __shared__ float4 s_merge[128];
     __shared__ unsigned s_tmem;
 
@@ -210,13 +239,13 @@ ccf_um_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 32) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&s_full[s], kProdWarps); mbar_init(&s_empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&s_dfull[b], 1); mbar_init(&s_dempty[b], 4); }
+        for (int p = 0; p < kPipes; ++p)
+            for (int s = 0; s < kStages; ++s) { mbar_init(&s_full[p][s], 32); mbar_init(&s_empty[p][s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&s_dfull[b], kPipes); mbar_init(&s_dempty[b], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < N; i += kThreads) s_tw[i] = twid[i];
-    const int nit_pad = (nitems + kCps - 1) / kCps * kCps;
-    for (int i = tid; i < nit_pad; i += kThreads) s_items[i] = (i < nitems) ? g_items[i] : 0;
+    for (int i = tid; i < kPipes * istride; i += kThreads) s_items[i] = g_items[i / istride][i % istride];
     if (cn == 0) {                            // pull a future row tile into L2: the spectra were written a whole batch earlier
         const long r0 = (long)(cm + kPfDist) * 32;
         if (r0 < nrows) {
@@ -232,7 +261,6 @@ ccf_um_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem = s_tmem;
     if (tid == 0) UM_T(1);
-    const int nsi = nit_pad / kCps;           // stage iterations
 
     if (warp < kConsWarps) {
         // ================= consumers: pass 1 class by class, then pass 2 + argmax ====================
@@ -244,7 +272,7 @@ ccf_um_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
         unsigned dph = 0;
         for (int pos = grp; pos < 9; pos += 2) {
             const int n2 = ((pos < 8 ? cls_n2_packed_lo >> (4 * pos) : cls_n2_packed_hi) & 15);
-            if (lane == 0) mbar_wait(&s_dfull[grp], dph);
+            if (lane == 0) mbar_wait_relaxed(&s_dfull[grp], dph);
             dph ^= 1;
             __syncwarp();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -317,10 +345,13 @@ ccf_um_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
             const int k1 = grp * (N1 / 2) + kk;
             float2 x[N2];
             {
-                float2 lo[8];
-                tmem_ld_32x32b_x16(ybase + k1 * N2, lo);
+                float2 lo[8], mid[4];
+                tmem_ld_32x32b_x16(ybase + k1 * (2 * kYT), lo);
+                tmem_ld_32x32b_x8(ybase + k1 * (2 * kYT) + 16, mid);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { x[j] = lo[j]; x[8 + j] = sy[(k1 * (N2 / 2) + j) * 128]; }
+                for (int j = 0; j < 8; ++j) x[j] = lo[j];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { x[8 + j] = mid[j]; x[12 + j] = sy[(k1 * (N2 - kYT) + j) * 128]; }
             }
             fft_reg<N2, 1>(x);
             float lq = -INFINITY, lt = -INFINITY; int lmq = -1, lmt = -1;
@@ -366,104 +397,95 @@ ccf_um_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
                 cand[(size_t)row * ncta_n + cn] = cd;
             }
         }
-    } else if (warp < kConsWarps + kProdWarps) {
+    } else if (warp < kConsWarps + kPipes) {
         // ================= producers: fragment spectra -> UMMA core matrices ==========================
-        const int pw = warp - kConsWarps;
-        const int c = pw >> 2, j = pw & 3;                      // chunk within the stage, ring quad of the chunk
-        int rrow = row0 + lane;
-        if (rrow >= nrows) rrow = nrows - 1;
-        const unsigned char* pa = spec + (size_t)rrow * row_bytes + j * 32;
-        const unsigned char* pb = refimg + (size_t)cn * nch * kBBytes + (j * 32 + lane) * 16;     // j < 2 only
-        // destination of the two 16-byte pieces (row, re) / (row, im): [s2][kc][mg = 2q + part][u8]
-        const int q = lane >> 3, u8 = lane & 7;
-        const unsigned dst_re = (unsigned)(c * kABytes + (j * 8 + 2 * q) * 128 + u8 * 16);
-        const unsigned dst_b = (unsigned)(kCps * kABytes + c * kBBytes + (j * 32 + lane) * 16);
-        Frag8 fa[kDepth]; uint4 fb[kDepth];
+        // A 16-byte unit of the fragment layout ([hi x4 | lo x4] of one (row, part), cra_common.cuh) is one
+        // core-matrix row: cp.async copies it straight to its place, no registers held, so the depth in flight
+        // is the number of shared-memory stages.  Adjacent lanes read the two halves of one 32-byte sector.
+        const int pipe = warp - kConsWarps;
+        // one instruction = 4 rows x the 8 units of their chunk: every 8 lanes read one whole 128-byte line
+        const int piece = lane & 7, j = piece >> 1, part = piece & 1;
+        const unsigned char* psrc[8];
 #pragma unroll
-        for (int d = 0; d < kDepth; ++d) {
-            if (d < nsi) {
-                const int gc = (s_items[d * kCps + c] >> 7) & 8191;
-                fa[d] = ldg256(pa + (size_t)gc * 128);
-                if (j < 2) fb[d] = __ldg(reinterpret_cast<const uint4*>(pb + (size_t)gc * kBBytes));
-            }
+        for (int n = 0; n < 8; ++n) {
+            int rrow = row0 + 4 * n + (lane >> 3);
+            if (rrow >= nrows) rrow = nrows - 1;
+            psrc[n] = spec + (size_t)rrow * row_bytes + piece * 16;
         }
+        const unsigned char* pb = refimg + (size_t)cn * nch * kBBytes + lane * 16;
+        const unsigned sbase = smem_u32(s_stage) + pipe * kStages * kStageBytes;
+        // row rt = 4 n + lane/8: octet q = n >> 1, u8 = 4 (n & 1) + lane/8
+        const unsigned dst_a = (unsigned)((j * 8 + part) * 128 + (lane >> 3) * 16);      // + (n >> 1) * 256 + (n & 1) * 64
+        const unsigned dst_b = (unsigned)(kABytes + lane * 16);
+        const int nit = g_nitems[pipe];
+        const int* items = s_items + pipe * istride;
         unsigned eph = 1;                                       // a fresh barrier: waiting on the previous phase passes
-        for (int it0 = 0; it0 < nsi; it0 += kDepth) {
+        for (int it = 0; it < nit; ++it) {
+            const int s = it % kStages;
+            if (pipe == 0 && lane == 0 && it == 24) UM_T(16);
+            if (lane == 0) mbar_wait(&s_empty[pipe][s], eph);
+            if (pipe == 0 && lane == 0 && it == 24) UM_T(17);
+            if (s == kStages - 1) eph ^= 1;
+            __syncwarp();
+            const unsigned st = sbase + s * kStageBytes;
+            const size_t goff = (size_t)((items[it] >> 7) & 8191) * 128;
 #pragma unroll
-            for (int d = 0; d < kDepth; ++d) {
-                const int it = it0 + d;
-                if (it < nsi) {
-                    const int s = it % kStages;
-                    if (lane == 0) mbar_wait(&s_empty[s], eph);      // one poller per warp: 256 threads on one mbarrier serialise
-                    if (s == kStages - 1) eph ^= 1;
-                    __syncwarp();
-                    unsigned char* st = s_stage + s * kStageBytes;
-                    const Frag8 f = fa[d];
-                    *reinterpret_cast<uint4*>(st + dst_re) = make_uint4(f.w[0], f.w[2], f.w[4], f.w[6]);
-                    *reinterpret_cast<uint4*>(st + dst_re + 128) = make_uint4(f.w[1], f.w[3], f.w[5], f.w[7]);
-                    if (j < 2) *reinterpret_cast<uint4*>(st + dst_b) = fb[d];
-                    if (!(dbg & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&s_full[s]);
-                    const int nx = it + kDepth;
-                    if (nx < nsi && !(dbg & 2)) {
-                        const int gc = (s_items[nx * kCps + c] >> 7) & 8191;
-                        fa[d] = ldg256(pa + (size_t)gc * 128);
-                        if (j < 2) fb[d] = __ldg(reinterpret_cast<const uint4*>(pb + (size_t)gc * kBBytes));
-                    }
-                }
-            }
+            for (int n = 0; n < 8; ++n) cp_async16(st + (n >> 1) * 256 + (n & 1) * 64 + dst_a, psrc[n] + goff);
+            cp_async16(st + dst_b, pb + goff * (kBBytes / 128));
+            cp_async16(st + dst_b + 512, pb + goff * (kBBytes / 128) + 512);
+            cp_async_arrive(&s_full[pipe][s]);
+            if (pipe == 0 && lane == 0 && it == 24) UM_T(18);
+            if (pipe == 0 && lane == 0 && it == 20) UM_T(20);
         }
         if (tid == kConsWarps * 32) UM_T(11);
     } else {
-        // ================= MMA issuer ==================================================================
-        // One thread issues every tcgen05.mma of the tile (four per chunk), so its instruction stream is
-        // the pace of the contraction: descriptors are a constant plus an immediate, the stage loop is unrolled.
-        {
-            unsigned fph = 0, dph0 = 1, dph1 = 1;
-            const unsigned sbase = smem_u32(s_stage);
-            const unsigned long long adesc = umma_desc(sbase, 1024, 128);
-            const unsigned long long bdesc = umma_desc(sbase + kCps * kABytes, 128, 256);
-            for (int it0 = 0; it0 < nsi; it0 += kStages) {
+        // ================= MMA issuers =================================================================
+        // One thread issues the tcgen05.mma of a chunk (four of them), and its instruction stream is the pace
+        // of the contraction, so the chunks of a class are dealt to kPipes warps by frequency slot: different
+        // slots are different accumulator columns, no ordering between the warps is needed.
+        const int pipe = warp - kConsWarps - kPipes;
+        unsigned fph = 0, dph0 = 1, dph1 = 1;
+        const unsigned sbase = smem_u32(s_stage) + pipe * kStages * kStageBytes;
+        const unsigned long long adesc = umma_desc(sbase, 1024, 128);
+        const unsigned long long bdesc = umma_desc(sbase + kABytes, 128, 256);
+        const int nit = g_nitems[pipe];
+        const int* items = s_items + pipe * istride;
+        for (int it0 = 0; it0 < nit; it0 += kStages) {
 #pragma unroll
-                for (int s = 0; s < kStages; ++s) {
-                    const int it = it0 + s;
-                    if (it >= nsi) break;
-                    mbar_wait(&s_full[s], fph);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-                    for (int c = 0; c < kCps; ++c) {
-                        const int item = s_items[it * kCps + c];
-                        if (item & (1 << 27)) {
-                            if (item & (1 << 26)) {                 // first chunk of a class: its buffer must have been drained
-                                if (item & (1 << 20)) { mbar_wait(&s_dempty[1], dph1); dph1 ^= 1; }
-                                else { mbar_wait(&s_dempty[0], dph0); dph0 ^= 1; }
-                                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            }
-                            const unsigned d_tmem = tmem + (item & 0x10007f);
-                            const unsigned long long a0 = adesc + (unsigned)((s * kStageBytes + c * kABytes) >> 4);
-                            const unsigned long long b0 = bdesc + (unsigned)((s * kStageBytes + c * kBBytes) >> 4);
-                            if (elect_one()) {
-                                if (!(dbg & 1)) {
-                                    umma_bf16(d_tmem, a0, b0, (item & (1 << 24)) ? 0u : 1u);
-                                    umma_bf16(d_tmem, a0, b0 + (256 >> 4), 1u);
-                                    umma_bf16(d_tmem, a0 + (2048 >> 4), b0 + (512 >> 4), 1u);
-                                    umma_bf16(d_tmem, a0 + (2048 >> 4), b0 + (768 >> 4), 1u);
-                                }
-                                if (item & (1 << 25)) umma_commit(&s_dfull[(item >> 20) & 1]);
-                            }
-                            __syncwarp();
-                        }
-                    }
-                    if (elect_one()) umma_commit(&s_empty[s]);
-                    __syncwarp();
-                    if (lane == 0 && it == 0) UM_T(8);
-                    if (lane == 0 && it == 50) UM_T(9);
+            for (int s = 0; s < kStages; ++s) {
+                const int it = it0 + s;
+                if (it >= nit) break;
+                const int item = items[it];
+                if (item & (1 << 26)) {                 // first chunk of a class: its buffer must have been drained
+                    if (item & (1 << 20)) { mbar_wait(&s_dempty[1], dph1); dph1 ^= 1; }
+                    else { mbar_wait(&s_dempty[0], dph0); dph0 ^= 1; }
                 }
-                fph ^= 1;
+                if (pipe == 0 && lane == 0 && it == 20) UM_T(13);
+                mbar_wait(&s_full[pipe][s], fph);
+                if (pipe == 0 && lane == 0 && it == 20) UM_T(14);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned d_tmem = tmem + (item & 0x10007f);
+                const unsigned long long a0 = adesc + (unsigned)((s * kStageBytes) >> 4);
+                const unsigned long long b0 = bdesc + (unsigned)((s * kStageBytes) >> 4);
+                if (elect_one()) {
+                    if (!(dbg & 1)) {
+                        umma_bf16(d_tmem, a0, b0, (item & (1 << 24)) ? 0u : 1u);
+                        umma_bf16(d_tmem, a0, b0 + (256 >> 4), 1u);
+                        umma_bf16(d_tmem, a0 + (2048 >> 4), b0 + (512 >> 4), 1u);
+                        umma_bf16(d_tmem, a0 + (2048 >> 4), b0 + (768 >> 4), 1u);
+                    }
+                    umma_commit(&s_empty[pipe][s]);
+                    if (item & (1 << 25)) umma_commit(&s_dfull[(item >> 20) & 1]);
+                }
+                __syncwarp();
+                if (pipe == 0 && lane == 0 && it == 20) UM_T(15);
+                if (pipe == 0 && lane == 0 && it == 21) UM_T(19);
+                if (pipe == 0 && lane == 0 && it == 0) UM_T(8);
+                if (pipe == 0 && lane == 0 && it == 25) UM_T(9);
             }
-            if (lane == 0) UM_T(10);
+            fph ^= 1;
         }
+        if (pipe == 0 && lane == 0) UM_T(10);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -510,17 +532,19 @@ __global__ void um_pack_refs_kernel(const unsigned char* __restrict__ refspec, i
     for (int i = 0; i < 4; ++i) { o0[i] = hi[i]; o0[4 + i] = hi[i]; o1[i] = lo[i]; o1[4 + i] = z; }
 }
 
-struct Sched { int nring = -1, maxrin = -1, dev = -1, nitems = 0, lo = 0, hi = 0; std::vector<int> len; };
+struct Sched { int nring = -1, maxrin = -1, dev = -1, istride = 0, lo = 0, hi = 0; std::vector<int> len; };
 Sched g_sched;
 
-// class order: position parity = consumer group; the two single-residue classes both go to group 0
+// class order: position parity = consumer group; the two single-residue classes both go to group 0.
+// Within a class the frequency slots are dealt to the pipelines (heaviest first, least loaded pipeline).
 int bind_schedule(const CraRingTab& h, const std::vector<int>& koff, cudaStream_t st)
 {
     int dev = 0; cudaGetDevice(&dev);
     std::vector<int> len(h.len, h.len + h.nring);
     if (g_sched.nring == h.nring && g_sched.maxrin == h.maxrin && g_sched.dev == dev && g_sched.len == len) return 0;
     const int cls[9] = {0, 1, 8, 2, 3, 4, 5, 6, 7};
-    std::vector<int> items;
+    std::vector<int> items[kPipes];
+    long load[kPipes] = {0};
     int lo = 0, hi = 0;
     for (int pos = 0; pos < 9; ++pos) {
         const int n2 = cls[pos];
@@ -529,23 +553,37 @@ int bind_schedule(const CraRingTab& h, const std::vector<int>& koff, cudaStream_
         if (n2 == 0) for (int j = 0; j <= 8; ++j) ks.push_back(16 * j);
         else if (n2 == 8) for (int j = 0; j < 8; ++j) ks.push_back(8 + 16 * j);
         else { for (int j = 0; j < 8; ++j) ks.push_back(n2 + 16 * j); for (int j = 0; j < 8; ++j) ks.push_back(16 - n2 + 16 * j); }
-        const size_t first_item = items.size();
-        for (size_t s = 0; s < ks.size(); ++s) {
+        std::vector<int> order(ks.size());
+        for (size_t i = 0; i < ks.size(); ++i) order[i] = (int)i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return koff[ks[a] + 1] - koff[ks[a]] > koff[ks[b] + 1] - koff[ks[b]]; });
+        size_t first_item[kPipes];
+        for (int p = 0; p < kPipes; ++p) first_item[p] = items[p].size();
+        for (int s : order) {
             const int k = ks[s], c0 = koff[k], c1 = koff[k + 1];
             if (c1 <= c0) { cra_set_error("UMMA CCF kernel: a frequency without rings"); return 1; }
+            int p = 0;
+            for (int pp = 1; pp < kPipes; ++pp) if (load[pp] < load[p]) p = pp;
             for (int gc = c0; gc < c1; ++gc)
-                items.push_back(((int)s * 8) | (gc << 7) | ((pos & 1) << 20) | ((gc == c0) ? (1 << 24) : 0) | (1 << 27));
+                items[p].push_back((s * 8) | (gc << 7) | ((pos & 1) << 20) | ((gc == c0) ? (1 << 24) : 0) | (1 << 27));
+            load[p] += c1 - c0;
         }
-        items[first_item] |= 1 << 26;
-        items.back() |= 1 << 25;
+        for (int p = 0; p < kPipes; ++p) {
+            if (items[p].size() == first_item[p]) { cra_set_error("UMMA CCF kernel: a pipeline without work in a class"); return 1; }
+            items[p][first_item[p]] |= 1 << 26;
+            items[p].back() |= 1 << 25;
+        }
     }
-    if ((int)items.size() > kMaxItems - kCps || koff[N / 2 + 1] > 8191) { cra_set_error("ring table too large for the UMMA CCF schedule"); return 1; }
+    int istride = 0;
+    for (int p = 0; p < kPipes; ++p) istride = std::max(istride, (int)items[p].size());
+    if (istride > kMaxItems || koff[N / 2 + 1] > 8191) { cra_set_error("ring table too large for the UMMA CCF schedule"); return 1; }
+    static int h_items[kPipes][kMaxItems]; int h_n[kPipes];
+    memset(h_items, 0, sizeof(h_items));
+    for (int p = 0; p < kPipes; ++p) { h_n[p] = (int)items[p].size(); for (size_t i = 0; i < items[p].size(); ++i) h_items[p][i] = items[p][i]; }
     CRA_CUDA(cudaStreamSynchronize(st));
-    const int n = (int)items.size();
-    CRA_CUDA(cudaMemcpyToSymbol(g_items, items.data(), n * sizeof(int)));
-    CRA_CUDA(cudaMemcpyToSymbol(g_nitems, &n, sizeof(int)));
+    CRA_CUDA(cudaMemcpyToSymbol(g_items, h_items, sizeof(h_items)));
+    CRA_CUDA(cudaMemcpyToSymbol(g_nitems, h_n, sizeof(h_n)));
     g_sched.nring = h.nring; g_sched.maxrin = h.maxrin; g_sched.dev = dev; g_sched.len = len;
-    g_sched.nitems = n; g_sched.lo = lo; g_sched.hi = hi;
+    g_sched.istride = istride; g_sched.lo = lo; g_sched.hi = hi;
     return 0;
 }
 
@@ -570,21 +608,19 @@ int cra_launch_ccf_um(const unsigned char* spec, int nrows, const unsigned char*
 {
     if (htab.log2n != LOG2N) { cra_set_error("UMMA CCF kernel: maxrin must be 256"); return 1; }
     if (bind_schedule(htab, h_koff, st)) return 1;
-    const int nit_pad = (g_sched.nitems + kCps - 1) / kCps * kCps;
-    const size_t smem = (size_t)kStages * kStageBytes + (size_t)(N2 / 2) * N1 * 128 * sizeof(float2) + N * sizeof(float2) +
-                        (size_t)nit_pad * sizeof(int);
+    const size_t smem = (size_t)kPipes * kStages * kStageBytes + (size_t)(N2 - kYT) * N1 * 128 * sizeof(float2) + N * sizeof(float2) +
+                        (size_t)kPipes * g_sched.istride * sizeof(int);
     static size_t configured = 0;
     if (smem > configured) {
         CRA_CUDA(cudaFuncSetAttribute(ccf_um_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    { const int wm = (getenv("CRA_UM_DBG") && (atoi(getenv("CRA_UM_DBG")) & 64)) ? 1 : 0; cudaMemcpyToSymbol(g_waitmode, &wm, sizeof(int)); }
     const long ncta_m = (nrows + 31) / 32;
     const long nblk = ncta_m * ntile_n;
     if (nblk <= 0) return 0;
     if (nblk > 2147483647L) { cra_set_error("ccf grid too large; lower row_batch"); return 1; }
     ccf_um_kernel<<<(unsigned)nblk, kThreads, smem, st>>>(spec, nrows, refimg, R, cra_frag_row_bytes(frag.nch), frag.nch, twid, cand,
-                                                          ntile_n, norm, tref, g_sched.nitems, g_sched.lo, g_sched.hi,
+                                                          ntile_n, norm, tref, g_sched.istride, g_sched.lo, g_sched.hi,
                                                           getenv("CRA_UM_DBG") ? atoi(getenv("CRA_UM_DBG")) : 0);
     CRA_CUDA(cudaGetLastError());
     if (getenv("CRA_UM_DBG") && (atoi(getenv("CRA_UM_DBG")) & 32)) {

@@ -119,6 +119,8 @@ struct CraFragTab {
     int nch;                     // chunks per row
     const int* koff;             // [nk+1] first chunk of frequency k (device)
     const int* chunk_k;          // [nch]  k << 4 | c (device)
+    int unit_rows;               // 1: particle rows use the reference layout [re unit | im unit] (tcgen05 kernel,
+                                 // a unit = one UMMA core-matrix row); 0: the mma.sync A-operand order above
 };
 __host__ __device__ __forceinline__ size_t cra_frag_row_bytes(int nch) { return (size_t)nch * 128; }
 

@@ -409,7 +409,7 @@ polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __r
                 re[j] = v.x; im[j] = v.y;
             }
             uint4* o = reinterpret_cast<uint4*>(base + (size_t)r * nch * 128 + (size_t)gc * 128 + t * 32);
-            if (MODE == 1) {           // reference (B operand) layout: [re unit | im unit]
+            if (MODE == 1 || frag.unit_rows) {           // reference (B operand) layout: [re unit | im unit]
                 o[0] = split_bf16x4(re[0], re[1], re[2], re[3]);
                 o[1] = split_bf16x4(im[0], im[1], im[2], im[3]);
             } else {                   // particle row (A operand) layout: hi words then lo words

@@ -54,6 +54,30 @@ __device__ __forceinline__ void split_row_unit(const float (&re)[4], const float
     lo.z = *reinterpret_cast<const unsigned int*>(&lr23); lo.w = *reinterpret_cast<const unsigned int*>(&li23);
 }
 
+// split-bf16 of four values: (hi01, hi23, lo01, lo23), value = hi + lo: one 16-byte unit of the fragment layout
+__device__ __forceinline__ uint4 split_bf16x4(float v0, float v1, float v2, float v3)
+{
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(v0, v1), h23 = __floats2bfloat162_rn(v2, v3);
+    const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+    const __nv_bfloat162 l01 = __floats2bfloat162_rn(v0 - f01.x, v1 - f01.y), l23 = __floats2bfloat162_rn(v2 - f23.x, v3 - f23.y);
+    uint4 o;
+    o.x = *reinterpret_cast<const unsigned int*>(&h01); o.y = *reinterpret_cast<const unsigned int*>(&h23);
+    o.z = *reinterpret_cast<const unsigned int*>(&l01); o.w = *reinterpret_cast<const unsigned int*>(&l23);
+    return o;
+}
+// one 32-byte quad of a particle row in the active row layout (cra_common.cuh)
+__device__ __forceinline__ void store_row_quad(uint4* o4, const float (&re)[4], const float (&im)[4], int unit_rows)
+{
+    if (unit_rows) {
+        o4[0] = split_bf16x4(re[0], re[1], re[2], re[3]);
+        o4[1] = split_bf16x4(im[0], im[1], im[2], im[3]);
+    } else {
+        uint4 hi, lo;
+        split_row_unit(re, im, hi, lo);
+        o4[0] = hi; o4[1] = lo;
+    }
+}
+
 template <int NA, int NB>
 __device__ __forceinline__ void pass_a(float2* __restrict__ z, int b, float2 base)
 {
@@ -403,10 +427,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                         re[j] = fmaf(v.y, my[j], v.x * mx[j]);
                         im[j] = v.y * mi[j];
                     }
-                    uint4 hi, lo;
-                    split_row_unit(re, im, hi, lo);
-                    uint4* o4 = reinterpret_cast<uint4*>(o);
-                    o4[0] = hi; o4[1] = lo;
+                    store_row_quad(reinterpret_cast<uint4*>(o), re, im, frag.unit_rows);
                     o += (size_t)nset * rb;
                     z += nset * (stride >> 1);
                 }
@@ -423,10 +444,8 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                     re[j] = 0.f; im[j] = 0.f;
                     if (ring >= 0) { const int4 rp = s_ring[ring]; if (rp.z * 2 == k) re[j] = z[rp.x].y; }
                 }
-                uint4 hi, lo;
-                split_row_unit(re, im, hi, lo);
-                uint4* o4 = reinterpret_cast<uint4*>(spec + (size_t)(grow0 + r) * rb + (size_t)(s_koff[k] + (u >> 2)) * 128 + (u & 3) * 32);
-                o4[0] = hi; o4[1] = lo;
+                store_row_quad(reinterpret_cast<uint4*>(spec + (size_t)(grow0 + r) * rb + (size_t)(s_koff[k] + (u >> 2)) * 128 + (u & 3) * 32),
+                               re, im, frag.unit_rows);
             }
         }
         if (tid < kThreads / 32) s_nfrag[tid] = 0;             // read above before two barriers, next written after this phase's last one

@@ -167,6 +167,39 @@ def test_align_matches_oracle_config1_geometry(oracle, small_set, normalize):
     e.close()
 
 
+def test_tcgen05_ccf_kernel_matches_oracle_and_default_path(oracle, small_set, monkeypatch):
+    """CRA_CCF=um: the contraction on tcgen05.mma (cra_ccf_um.cu, maxrin 256) against the oracle and against
+    the default kernel: discrete answers identical outside the tie band, peaks within 1e-4 relative."""
+    from cryo_ralib_b200 import alignment as al
+    images, refs, _ = small_set
+    imgs, mask, numr, refs_n, cref = _prep(oracle, images, refs, 36)
+    P, R = images.shape[0], refs.shape[0]
+    from cryo_ralib_b200.lib import SEARCH_DTYPE
+    sxi = np.linspace(-7.3, 7.6, P); syi = np.linspace(6.7, -7.9, P)          # fractional centres, ragged windows
+    search = np.zeros(P, SEARCH_DTYPE)
+    search["xl"], search["xr"] = al.search_range(90, 36, sxi, 3.0)
+    search["yl"], search["yr"] = al.search_range(90, 36, syi, 3.0)
+    search["cx"] = 46 + sxi; search["cy"] = 46 + syi
+    res = {}
+    for mode in ("um", "tm"):
+        monkeypatch.setenv("CRA_CCF", mode)
+        e = _engine(90, 36, 3, P=P, R=R)
+        e.upload_particles(images); e.set_refs(refs)
+        res[mode] = e.align(0, P, search)
+        e.close()
+    centres = np.stack([search["cx"], search["cy"]], 1)
+    win = np.stack([search["xl"], search["xr"], search["yl"], search["yr"]], 1)
+    want = oracle.align_batch(imgs, cref, numr, centres, win, 1.0, True, nthreads=8)
+    for mode in ("um", "tm"):
+        exact, ties, bad = _compare_alignment(res[mode], want, 256)
+        assert not bad, (mode, bad[:5])
+        assert ties <= max(1, P // 20)
+    same = (res["um"]["iref"] == res["tm"]["iref"]) & (res["um"]["mirror"] == res["tm"]["mirror"])
+    assert same.mean() > 0.95
+    rel = np.abs(res["um"]["peak"] - res["tm"]["peak"]) / np.abs(res["tm"]["peak"])
+    assert rel[same].max() < 1e-5
+
+
 def test_align_ragged_windows_fractional_centres_and_half_step(oracle, small_set):
     images, refs, _ = small_set
     imgs, mask, numr, refs_n, cref = _prep(oracle, images, refs[:7], 36)
