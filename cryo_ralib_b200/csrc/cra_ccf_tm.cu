@@ -22,6 +22,7 @@
 #include <math.h>
 #include <string.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <algorithm>
 
 namespace {
@@ -128,7 +129,8 @@ template <int LOG2N>
 __global__ void __launch_bounds__(kThreads, 2)
 ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned char* __restrict__ refspec, int R,
               size_t row_bytes, const float2* __restrict__ twid, CraCand* __restrict__ cand,
-              int nquad, int ncta_n, const float2* __restrict__ norm, const float* __restrict__ tref, int istride, int fstride)
+              int nquad, int ncta_n, const float2* __restrict__ norm, const float* __restrict__ tref, int istride, int fstride,
+              long ntiles)
 {
     using S = TShape<LOG2N>;
     constexpr int N = S::N, N1 = S::N1, N2 = S::N2, PS = S::PS, NJ = S::NJ, RQ = S::RQ, JCOLS = S::JCOLS;
@@ -143,12 +145,7 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int quad = warp & 3;                                  // TMEM lane quadrant of this warp
-    // reference tile fastest so that concurrently resident CTAs share the row spectra in L2
-    const int cn = blockIdx.x % ncta_n, cm = blockIdx.x / ncta_n;
     const int qbase = nquad / ncta_n, qrem = nquad % ncta_n;
-    const int nj = qbase + (cn < qrem ? 1 : 0);                 // reference quads of this CTA (<= NJ)
-    const int q0 = cn * qbase + min(cn, qrem);
-    const int row0 = cm * 8;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -161,6 +158,22 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
         for (int i = lane; i < nit; i += 32) s_items[warp * istride + i] = g_items[warp][i];
         for (int i = lane; i < fstride; i += 32) s_flush[warp * fstride + i] = g_flush[warp][i];
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // this thread's TMEM lane: bits 31:16 lane, 15:0 column
+    const unsigned tbase = s_tmem + ((unsigned)(quad * 32) << 16);
+
+    // Persistent CTA: the work lists, the twiddles and the TMEM allocation above are set up once, then
+    // the CTA walks the tiles with the grid stride.  Reference tile fastest, so that the CTAs resident
+    // at any moment share the row spectra in L2.
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < (int)ntiles; tile += gridDim.x) {
+    {
+    const int cm = tile / ncta_n, cn = tile - cm * ncta_n;
+    const int nj = qbase + (cn < qrem ? 1 : 0);                 // reference quads of this tile (<= NJ)
+    const int q0 = cn * qbase + min(cn, qrem);
+    const int row0 = (int)(cm * 8);
     if (cn == 0) {                            // pull a future row block into L2 (see cra_ccf_mma.cu)
         const long r0 = (long)(cm + kPfDist) * 8;
         if (r0 < nrows) {
@@ -171,11 +184,8 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(p0 + i * 128));
         }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    // the previous tile's tcgen05.ld (pass 1) were ordered before its barriers
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // this thread's TMEM lane: bits 31:16 lane, 15:0 column
-    const unsigned tbase = s_tmem + ((unsigned)(quad * 32) << 16);
 
     // ---- contraction: this warp's frequencies, chunk by chunk ---------------------------------
     {
@@ -280,6 +290,14 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    {
+    // tile scalars re-derived here instead of kept in registers across the contraction
+    int tile2 = tile; asm volatile("" : "+r"(tile2));
+    const int cm = tile2 / ncta_n, cn = tile2 - cm * ncta_n;
+    const int nj = qbase + (cn < qrem ? 1 : 0);
+    const int q0 = cn * qbase + min(cn, qrem);
+    const int row0 = cm * 8;
 
     // ---- inverse FFT, one reference quad (32 pairs: lane = pair) at a time -----------------------
     for (int j = 0; j < nj; ++j) {
@@ -297,6 +315,7 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
                 w[k1 * (N2 + 1)] = crafft::cmul(x[k1], tw);
             }
         }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         // pass 2: (pair, k1): N2-point DFT over n2 -> X[k1 + N1*k2]; argmax over lags
         for (int item = tid; item < 32 * N1; item += kThreads) {
@@ -349,6 +368,8 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
             cand[(size_t)row * ncta_n + cn] = best;
         }
     }
+    }
+    }   // tile loop
     // every tcgen05.ld has completed (wait::ld) before the barriers above
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(s_tmem), "n"(S::COLS) : "memory");
@@ -455,8 +476,33 @@ int launch_t(const unsigned char* spec, int nrows, const unsigned char* refspec,
     const long nblk = ncta_m * ntile_n;
     if (nblk <= 0) return 0;
     if (nblk > 2147483647L) { cra_set_error("ccf grid too large; lower row_batch"); return 1; }
-    ccf_tm_kernel<LOG2N><<<(unsigned)nblk, kThreads, smem, st>>>(spec, nrows, refspec, R, row_bytes, twid, cand, nquad, ntile_n,
-                                                                norm, tref, g_sched.istride, g_sched.fstride);
+    static int resident = 0;                     // CTAs the device holds at once (2 per SM: TMEM and shared memory)
+    if (!resident) {
+        int dev = 0, nsm = 0, per = 0;
+        CRA_CUDA(cudaGetDevice(&dev));
+        CRA_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+        // CTAs one SM holds: registers, shared memory (+1 KB reserved per CTA) and the 512 TMEM columns.  The
+        // occupancy API answers 1 for this kernel at 128 registers although two CTAs are co-resident
+        // (measured: a 2-per-SM persistent grid runs at the two-CTA rate), so the limits are taken directly.
+        CRA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, ccf_tm_kernel<LOG2N>, kThreads, smem));
+        cudaFuncAttributes fa; CRA_CUDA(cudaFuncGetAttributes(&fa, ccf_tm_kernel<LOG2N>));
+        int regs_sm = 0, smem_sm = 0;
+        CRA_CUDA(cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev));
+        CRA_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+        const int by_regs = regs_sm / (((fa.numRegs + 7) / 8 * 8) * kThreads);
+        const int by_smem = (int)((size_t)smem_sm / (smem + fa.sharedSizeBytes + 1024));
+        per = std::max(per, std::min(std::min(by_regs, by_smem), 2));
+        if (getenv("CRA_TM_DEBUG")) fprintf(stderr, "ccf_tm: CTAs per SM %d (regs %d -> %d, smem -> %d)\n", per, fa.numRegs, by_regs, by_smem);
+        if (getenv("CRA_TM_PER")) per = atoi(getenv("CRA_TM_PER"));
+        if (per < 1) per = 1;
+        if (per * S::COLS > 512) per = 512 / S::COLS;      // tensor memory: 512 columns per SM
+        resident = nsm * per;
+    }
+    const char* np = getenv("CRA_TM_PERSIST");
+    const long grid = (np && np[0] == '0') ? nblk : std::min<long>(nblk, resident);
+    if (getenv("CRA_TM_DEBUG")) fprintf(stderr, "ccf_tm: tiles %ld grid %ld resident %d smem %zu\n", nblk, grid, resident, smem);
+    ccf_tm_kernel<LOG2N><<<(unsigned)grid, kThreads, smem, st>>>(spec, nrows, refspec, R, row_bytes, twid, cand, nquad, ntile_n,
+                                                                norm, tref, g_sched.istride, g_sched.fstride, nblk);
     CRA_CUDA(cudaGetLastError());
     return 0;
 }
