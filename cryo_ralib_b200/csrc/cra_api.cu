@@ -408,15 +408,16 @@ extern "C" int cra_create(const CraConfig* cfg, int device, CraCtx** out)
     if (e == cudaSuccess) e = cudaMalloc(&c->d_images, (size_t)cfg->max_particles * c->npix * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_refs, (size_t)cfg->max_refs * c->npix * sizeof(float));
     const size_t ref_groups = ((size_t)cfg->max_refs + 3) / 4, row_groups = ((size_t)c->row_batch + 3) / 4;
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_refspec, ref_groups * 4 * row_bytes);
-    if (e == cudaSuccess) e = cudaMemset(c->d_refspec, 0, ref_groups * 4 * row_bytes);
+    // one extra quad: a class-bound launch (cra_align_bound) bases the 4-reference operand loads at any reference
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_refspec, (ref_groups + 1) * 4 * row_bytes);
+    if (e == cudaSuccess) e = cudaMemset(c->d_refspec, 0, (ref_groups + 1) * 4 * row_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_spec, row_groups * 4 * row_bytes);
     if (e == cudaSuccess) e = cudaMemset(c->d_spec, 0, row_groups * 4 * row_bytes);
     if (e == cudaSuccess) e = cudaMallocHost(&c->h_group, 4 * row_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_cand, (size_t)c->row_batch * c->ntile_n_max * sizeof(CraCand));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_norm, ((size_t)c->row_batch + 4) * sizeof(float2));
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_tref, ref_groups * 4 * sizeof(float));
-    if (e == cudaSuccess) e = cudaMemset(c->d_tref, 0, ref_groups * 4 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_tref, (ref_groups + 1) * 4 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(c->d_tref, 0, (ref_groups + 1) * 4 * sizeof(float));
     if (e == cudaSuccess && c->use_um) e = cudaMalloc(&c->d_refimg, cra_ccf_um_refimg_bytes(cfg->max_refs, c->frag.nch));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_sums, nsum * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_curves, (size_t)2 * c->htab.maxrin * sizeof(float));
@@ -504,11 +505,9 @@ extern "C" int cra_upload_wait(CraCtx* c)
 extern "C" int cra_upload_particles_dev(CraCtx* c, const float* d, int first, int n, int sub)
 { return upload_particles(c, d, first, n, sub, cudaMemcpyDeviceToDevice); }
 
-extern "C" int cra_set_refs(CraCtx* c, const float* h, int R, int normalize_mask)
+// d_refs[0..R) -> (normalize.mask no_sigma=1) -> Polar2Dm + Frngs + Applyws -> refspec, tref
+static int prepare_refs(CraCtx* c, int R, int normalize_mask)
 {
-    Bind b(c); if (b.ok()) return 1;
-    if (R < 1 || R > c->cfg.max_refs) { cra_set_error("R exceeds max_refs"); return 1; }
-    CRA_CUDA(cudaMemcpyAsync(c->d_refs, h, (size_t)R * c->npix * sizeof(float), cudaMemcpyHostToDevice, c->st));
     if (normalize_mask && cra_launch_mask_normalize(c->d_refs, R, c->nx, c->d_mask, 1, c->st)) return 1;
     if (cra_launch_polar_refs(c->d_refs, R, c->nx, c->d_tab, c->htab, c->d_samp, c->d_twf, c->items, c->d_refspec,
                               c->fmt, c->frag, c->d_tref, c->st)) return 1;
@@ -518,13 +517,57 @@ extern "C" int cra_set_refs(CraCtx* c, const float* h, int R, int normalize_mask
     return 0;
 }
 
-extern "C" int cra_align(CraCtx* c, int start, int stop, const CraSearch* search, CraResult* out)
+extern "C" int cra_set_refs(CraCtx* c, const float* h, int R, int normalize_mask)
+{
+    Bind b(c); if (b.ok()) return 1;
+    if (R < 1 || R > c->cfg.max_refs) { cra_set_error("R exceeds max_refs"); return 1; }
+    CRA_CUDA(cudaMemcpyAsync(c->d_refs, h, (size_t)R * c->npix * sizeof(float), cudaMemcpyHostToDevice, c->st));
+    return prepare_refs(c, R, normalize_mask);
+}
+
+extern "C" int cra_refs_from_sums(CraCtx* c, int normalize_mask)
+{
+    Bind b(c); if (b.ok()) return 1;
+    if (c->R < 1) { cra_set_error("cra_set_refs has not been called"); return 1; }
+    const float* counts = c->d_sums + (size_t)c->cfg.max_refs * 2 * c->npix;
+    if (cra_launch_class_average(c->d_sums, counts, c->d_refs, c->R, c->nx, c->st)) return 1;
+    return prepare_refs(c, c->R, normalize_mask);
+}
+
+extern "C" int cra_filter_refs(CraCtx* c, float cutoff, float falloff, int normalize_mask)
+{
+    Bind b(c); if (b.ok()) return 1;
+    if (c->R < 1) { cra_set_error("cra_set_refs has not been called"); return 1; }
+    if (cra_launch_tanl_filter(c->d_refs, c->R, c->nx, cutoff, falloff, c->st)) return 1;
+    return prepare_refs(c, c->R, normalize_mask);
+}
+
+extern "C" int cra_get_refs(CraCtx* c, float* host_refs)
+{
+    Bind b(c); if (b.ok()) return 1;
+    if (c->R < 1 || !host_refs) { cra_set_error("no references / null buffer"); return 1; }
+    CRA_CUDA(cudaMemcpyAsync(host_refs, c->d_refs, (size_t)c->R * c->npix * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    CRA_CUDA(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+// class_of == nullptr: every particle against every reference (Util.multiref_polar_ali_2d).
+// class_of != nullptr: particle p against reference class_of[p] only (gpu_isac's class-bound
+// ref_free_alignment_2D, cuda/gpu_aln_noref.cu:743-782): the row kernel runs per batch as usual,
+// the CCF and finalize kernels run once per run of consecutive particles of one class, on that
+// run's rows and with the reference operands based at that class.
+static int align_impl(CraCtx* c, int start, int stop, const CraSearch* search, const int* class_of, CraResult* out)
 {
     Bind b(c); if (b.ok()) return 1;
     const int n = stop - start;
     if (start < 0 || n < 0 || stop > c->cfg.max_particles) { cra_set_error("particle range exceeds max_particles"); return 1; }
     if (c->R < 1) { cra_set_error("cra_set_refs has not been called"); return 1; }
     if (n == 0) return 0;
+    if (class_of) {
+        if (c->fmt != CRA_FMT_FRAG || c->use_um) { cra_set_error("class-bound alignment needs the fragment layout with the tm / mma kernels (default)"); return 1; }
+        for (int p = 0; p < n; ++p)
+            if (class_of[p] < 0 || class_of[p] >= c->R) { cra_set_error("class_of entry outside the reference list"); return 1; }
+    }
     if (wait_uploads(c, start, n)) return 1;
     const float step = c->cfg.step;
     // plan batches
@@ -616,6 +659,35 @@ extern "C" int cra_align(CraCtx* c, int start, int stop, const CraSearch* search
         } else if (cra_launch_polar_rows(c->d_images, c->nx, c->d_tab, c->htab, c->d_samp, c->d_sampw, c->d_twf, c->items, map,
                                          c->cfg.normalize_ring, c->d_spec, c->fmt, c->frag, c->d_norm, c->st)) return 1;
         if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 1], c->st));
+        if (class_of) {
+            const unsigned char* specb = reinterpret_cast<const unsigned char*>(c->d_spec);
+            const unsigned char* refb = reinterpret_cast<const unsigned char*>(c->d_refspec);
+            const int* rs = h_rs + bfirst[bi] + bi;                 // batch-local first row of each particle
+            for (int a = 0; a < bcount[bi];) {
+                const int cls = class_of[bfirst[bi] + a];
+                int e = a + 1;
+                while (e < bcount[bi] && class_of[bfirst[bi] + e] == cls) ++e;
+                const int r0 = rs[a], nr = rs[e] - rs[a];
+                const unsigned char* ref1 = refb + (size_t)cls * c->row_bytes;
+                if (nr > 0) {
+                    if (c->use_tm) {
+                        if (cra_launch_ccf_tm(specb + (size_t)r0 * c->row_bytes, nr, ref1, 1, c->htab, c->frag, c->h_koff, c->d_twi,
+                                              c->d_cand + r0, 1, c->d_norm + r0, c->d_tref + cls, c->st)) return 1;
+                    } else if (cra_launch_ccf_mma(specb + (size_t)r0 * c->row_bytes, nr, ref1, 1, c->htab, c->frag, c->h_koff, c->d_twi,
+                                                  c->d_cand + r0, 1, c->d_norm + r0, c->d_tref + cls, c->st)) return 1;
+                }
+                CraRowMap sub = map;
+                sub.row_start += a; sub.search += a; sub.win += a; sub.np = e - a; sub.p0 += a;
+                if (cra_launch_finalize(c->d_spec, reinterpret_cast<const float*>(ref1), 1, c->d_tab, c->htab, c->d_cand, 1, sub,
+                                        c->d_res + bfirst[bi] + a, c->fmt, c->frag, c->st)) return 1;
+                launches += 2;
+                a = e;
+            }
+            if (tm) { CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 2], c->st)); CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 3], c->st)); }
+            launches += 1;
+            c->last_rows = map.nrows; c->last_group = bgroup[bi];
+            continue;
+        }
         if (c->fmt == CRA_FMT_FRAG && c->use_um) {
             if (cra_launch_ccf_um(reinterpret_cast<const unsigned char*>(c->d_spec), map.nrows, c->d_refimg, c->R, c->htab, c->frag,
                                   c->h_koff, c->d_twi, c->d_cand, ntile_n, c->d_norm, c->d_tref, c->st)) return 1;
@@ -638,10 +710,11 @@ extern "C" int cra_align(CraCtx* c, int start, int stop, const CraSearch* search
     CRA_CUDA(cudaMemcpyAsync(c->h_res, c->d_res, (size_t)n * sizeof(CraResult), cudaMemcpyDeviceToHost, c->st));
     CRA_CUDA(cudaStreamSynchronize(c->st));
     memcpy(out, c->h_res, (size_t)n * sizeof(CraResult));
+    if (class_of) for (int p = 0; p < n; ++p) out[p].iref = class_of[p];     // the kernels saw reference 0 of their run
     c->stats = CraAlignStats{};
     c->stats.launches = launches;
     c->stats.rows = total_rows;
-    c->stats.alignments = total_rows * c->R;
+    c->stats.alignments = class_of ? total_rows : total_rows * c->R;
     if (tm) {
         for (size_t bi = 0; bi < nb; ++bi) {
             float a = 0, bb = 0, cc = 0;
@@ -654,6 +727,15 @@ extern "C" int cra_align(CraCtx* c, int start, int stop, const CraSearch* search
         c->stats.ms_total = tot;
     }
     return 0;
+}
+
+extern "C" int cra_align(CraCtx* c, int start, int stop, const CraSearch* search, CraResult* out)
+{ return align_impl(c, start, stop, search, nullptr, out); }
+
+extern "C" int cra_align_bound(CraCtx* c, int start, int stop, const CraSearch* search, const int* class_of, CraResult* out)
+{
+    if (!class_of) { cra_set_error("class_of is null"); return 1; }
+    return align_impl(c, start, stop, search, class_of, out);
 }
 
 extern "C" int cra_last_align_stats(CraCtx* c, CraAlignStats* out)

@@ -188,3 +188,6 @@ void cra_ccf_twiddles(int log2n, std::vector<float2>& tw);
 int cra_launch_rotsum(const float* images, int nx, int p0, int n, const float4* params, const int* iref,
                       long global_offset, float* sums, float* counts, float* out_images, cudaStream_t st);
 int cra_fp32_peak(double* tf_ffma, double* tf_ffma2);
+// references from class sums, tangent low-pass of nx x nx images in place (cra_refavg.cu)
+int cra_launch_class_average(const float* sums, const float* counts, float* refs, int R, int nx, cudaStream_t st);
+int cra_launch_tanl_filter(float* imgs, int n, int nx, float fl, float aa, cudaStream_t st);

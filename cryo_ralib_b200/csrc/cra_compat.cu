@@ -30,6 +30,7 @@ struct Legacy {
     std::vector<CraResult> res;
     std::vector<float> par;
     std::vector<int> iref;
+    std::vector<int> cid;             // class of every particle (ref_free_alignment_2D_init), empty otherwise
 } g;
 
 void fail(const char* where)
@@ -65,7 +66,7 @@ void search_range(int n, int radius, double shift, double range, float* l, float
 // One alignment pass over particles [start,stop) of the fetched batch.
 //   multiref: Normalize_ring on, out-of-range shifts reset (test_mref.py:190-193)
 //   !multiref: ormq semantics, shifts clamped (ali2d_single_iter)
-int run_alignment(int start, int stop, bool multiref)
+int run_alignment(int start, int stop, bool multiref, bool bound = false)
 {
     if (!g.ctx) { cra_set_error("pre_align_init has not been called"); return 1; }
     const int n = stop - start;
@@ -92,7 +93,10 @@ int run_alignment(int start, int stop, bool multiref)
     }
     if (cra_set_normalize_ring(g.ctx, multiref ? 1 : 0)) return 1;
     if (cra_set_step(g.ctx, g.step)) return 1;
-    if (cra_align(g.ctx, 0, n, g.search.data(), g.res.data())) return 1;
+    if (bound) {
+        if (g.cid.size() != g.num_particles) { cra_set_error("ref_free_alignment_2D_init has not been called"); return 1; }
+        if (cra_align_bound(g.ctx, 0, n, g.search.data(), g.cid.data() + start, g.res.data())) return 1;
+    } else if (cra_align(g.ctx, 0, n, g.search.data(), g.res.data())) return 1;
     for (int i = 0; i < n; ++i) {
         AlignParam& p = g.params[start + i];
         const CraResult& r = g.res[i];
@@ -165,6 +169,7 @@ extern "C" void gpu_clear(void)
     if (g.d_trans) { cudaFree(g.d_trans); g.d_trans = nullptr; g.trans_n = 0; }
     if (g.m_sums) { cudaFree(g.m_sums); g.m_sums = nullptr; }
     if (g.m_counts) { cudaFree(g.m_counts); g.m_counts = nullptr; }
+    g.cid.clear();
     g.num_particles = 0;
 }
 
@@ -273,4 +278,44 @@ extern "C" void* pre_align_run_m(const int start_idx, const int stop_idx)
 {
     if (run_alignment(start_idx, stop_idx, false) || transform_batch(start_idx, stop_idx, true, false)) { fail("pre_align_run_m"); return nullptr; }
     return g.d_trans;
+}
+
+// ---- gpu_isac's class-bound reference-free alignment (gpu_aln_noref.cu:559-782) ------------------
+
+extern "C" bool ref_free_alignment_2D_size_check(const AlignConfig* cfg, const unsigned int cuda_device_id,
+                                                 const float request, const bool verbose)
+{
+    return cfg ? pre_align_size_check(cfg->sbj_num, cfg, cuda_device_id, request, verbose) : false;
+}
+
+extern "C" AlignParam* ref_free_alignment_2D_init(const AlignConfig* cfg, const float** sbj_data_list,
+                                                  const float** ref_data_list, const int* sbj_cid_list,
+                                                  const unsigned int cuda_device_id)
+{
+    if (!cfg || !sbj_data_list || !ref_data_list || !sbj_cid_list) { fprintf(stderr, "[cryo_ralib] ref_free_alignment_2D_init: bad arguments\n"); return nullptr; }
+    for (unsigned i = 0; i < cfg->sbj_num; ++i)
+        if (sbj_cid_list[i] < 0 || (unsigned)sbj_cid_list[i] >= cfg->ref_num) { fprintf(stderr, "[cryo_ralib] ref_free_alignment_2D_init: class id outside the reference list\n"); return nullptr; }
+    if (!pre_align_init(cfg->sbj_num, cfg, cuda_device_id)) return nullptr;
+    pre_align_fetch(sbj_data_list, cfg->sbj_num, "sbj_batch");
+    pre_align_fetch(ref_data_list, cfg->ref_num, "ref_batch");
+    g.cid.assign(sbj_cid_list, sbj_cid_list + cfg->sbj_num);
+    for (unsigned i = 0; i < cfg->sbj_num; ++i) g.params[i].ref_id = sbj_cid_list[i];      // gpu_aln_noref.cu:598-599
+    return g.params;
+}
+
+extern "C" void ref_free_alignment_2D(void)
+{
+    const int n = (int)g.num_particles;
+    if (run_alignment(0, n, false, true)) { fail("ref_free_alignment_2D"); return; }
+    // apply_alignment_param + fetch_averages (gpu_aln_noref.cu:771-775): class averages of the transformed images
+    g.par.resize((size_t)4 * n);
+    for (int i = 0; i < n; ++i) eman_params(g.params[i], &g.par[4 * i]);
+    if (cra_zero_sums(g.ctx) || cra_accumulate(g.ctx, 0, n, g.par.data(), g.cid.data(), 0) || cra_refs_from_sums(g.ctx, 0))
+        fail("ref_free_alignment_2D");
+}
+
+extern "C" void ref_free_alignment_2D_filter_references(const float cutoff_freq, const float falloff)
+{
+    if (!g.ctx) { fprintf(stderr, "[cryo_ralib] ref_free_alignment_2D_filter_references: not initialised\n"); return; }
+    if (cra_filter_refs(g.ctx, cutoff_freq, falloff, 0)) fail("ref_free_alignment_2D_filter_references");
 }

@@ -91,6 +91,10 @@ def load_library(path=None):
     L.cra_compose_result.argtypes = [C.c_int, vp, vp, vp, vp]
     L.cra_set_refs.argtypes = [vp, vp, C.c_int, C.c_int]
     L.cra_align.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    L.cra_align_bound.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
+    L.cra_refs_from_sums.argtypes = [vp, C.c_int]
+    L.cra_filter_refs.argtypes = [vp, C.c_float, C.c_float, C.c_int]
+    L.cra_get_refs.argtypes = [vp, vp]
     L.cra_accumulate.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_long]
     L.cra_zero_sums.argtypes = [vp]
     L.cra_sums_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
@@ -124,6 +128,14 @@ def load_library(path=None):
     L.pre_align_run.argtypes = [C.c_int, C.c_int]
     L.pre_align_run_m.restype = C.c_ulonglong
     L.pre_align_run_m.argtypes = [C.c_int, C.c_int]
+    # gpu_isac's class-bound variant (gpu_aln_noref.h:94-109)
+    L.ref_free_alignment_2D_init.restype = C.c_ulonglong
+    L.ref_free_alignment_2D_init.argtypes = [C.POINTER(AlignConfig), C.POINTER(C.POINTER(C.c_float)),
+                                             C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int), C.c_uint]
+    L.ref_free_alignment_2D_size_check.restype = C.c_bool
+    L.ref_free_alignment_2D_size_check.argtypes = [C.POINTER(AlignConfig), C.c_uint, C.c_float, C.c_bool]
+    L.ref_free_alignment_2D.argtypes = []
+    L.ref_free_alignment_2D_filter_references.argtypes = [C.c_float, C.c_float]
     if path == SO_PATH:
         _LIB = L
     return L
@@ -198,6 +210,29 @@ class Engine(object):
         assert search.shape[0] == stop - start
         out = np.zeros(stop - start, RESULT_DTYPE)
         self._ck(self.L.cra_align(self.h, int(start), int(stop), search.ctypes.data, out.ctypes.data))
+        return out
+
+    def align_bound(self, start, stop, search, class_of):
+        """Class-bound alignment (gpu_isac ref_free_alignment_2D): particle p against reference class_of[p] only."""
+        search = np.ascontiguousarray(search, SEARCH_DTYPE)
+        class_of = np.ascontiguousarray(class_of, np.int32)
+        assert search.shape[0] == stop - start and class_of.shape[0] == stop - start
+        out = np.zeros(stop - start, RESULT_DTYPE)
+        self._ck(self.L.cra_align_bound(self.h, int(start), int(stop), search.ctypes.data, class_of.ctypes.data,
+                                        out.ctypes.data))
+        return out
+
+    def refs_from_sums(self, normalize_mask=False):
+        """References <- class averages of the accumulated sums, on the device."""
+        self._ck(self.L.cra_refs_from_sums(self.h, int(normalize_mask)))
+
+    def filter_refs(self, cutoff, falloff, normalize_mask=False):
+        """Tangent low-pass (filt_tanl) of the current references, on the device."""
+        self._ck(self.L.cra_filter_refs(self.h, float(cutoff), float(falloff), int(normalize_mask)))
+
+    def get_refs(self):
+        out = np.zeros((self.R, self.nx, self.nx), np.float32)
+        self._ck(self.L.cra_get_refs(self.h, out.ctypes.data))
         return out
 
     def accumulate(self, start, stop, params, iref, global_offset=0):

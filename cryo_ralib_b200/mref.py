@@ -219,3 +219,48 @@ def ali2d_base(images, ir=1, ou=-1, rs=1, xr=0, yr=0, ts=1, center=-1, maxit=10,
     if own_engine:
         engine.close()
     return params, tavg, history
+
+
+def ref_free_alignment_2d(images, class_of, refs, ir=1, ou=-1, rs=1, xr=0, yr=0, ts=1, maxit=1, filt=None, comm=None,
+                          global_offset=0, engine=None, device=0, on_iteration=None):
+    """gpu_isac's class-bound reference-free alignment (ref_free_alignment_2D, cuda/gpu_aln_noref.cu:559-782):
+    every particle is aligned to the average of its own class only (class_of = sbj_cid_list), the class
+    averages are rebuilt ON THE DEVICE from the transformed particles after every pass and optionally
+    low-passed with the tangent filter (filt = (cutoff, falloff)).  ormq semantics as in ali2d_base.
+    With N > 1 ranks the particles are sharded, the references replicated and the class sums allreduced,
+    so every rank rebuilds the same averages.  Returns (params [n][4], refs [R][nx][nx], history)."""
+    from .lib import Engine
+    comm = comm or LocalComm()
+    n, nx = images.shape[0], images.shape[-1]
+    refs = np.ascontiguousarray(refs, np.float32)
+    class_of = np.ascontiguousarray(class_of, np.int32)
+    R = refs.shape[0]
+    if ou == -1:
+        ou = nx // 2 - 2
+    own_engine = engine is None
+    if own_engine:
+        engine = Engine(nx, ou, xr, yr, ts=ts, ir=ir, rs=rs, max_particles=n, max_refs=R, normalize_ring=False,
+                        device=device)
+    engine.upload_particles(images, subtract_mask_mean=True)
+    engine.set_refs(refs, normalize_mask=False)
+    params = np.zeros((n, 4))
+    history = []
+    for it in range(int(maxit)):
+        search, sxi, syi = al.reffree_search_request(params, (0.0, 0.0), nx, ou, xr, yr)
+        res = engine.align_bound(0, n, search, class_of)
+        params = al.compose_result(sxi, syi, res)
+        engine.zero_sums()
+        engine.accumulate(0, n, params, class_of, global_offset)
+        if comm.world > 1:
+            comm.allreduce_device(engine)
+        engine.refs_from_sums(normalize_mask=False)
+        if filt is not None:
+            engine.filter_refs(filt[0], filt[1], normalize_mask=False)
+        info = dict(peak=res["peak"].copy(), stats=engine.stats())
+        history.append(info)
+        if on_iteration:
+            on_iteration(it, params, info)
+    out_refs = engine.get_refs()
+    if own_engine:
+        engine.close()
+    return params, out_refs, history

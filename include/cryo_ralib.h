@@ -96,6 +96,23 @@ int  cra_set_refs(CraCtx* ctx, const float* host_refs, int R, int normalize_mask
  * are host arrays indexed from 0 for particle `start`.                      */
 int  cra_align(CraCtx* ctx, int start, int stop, const CraSearch* search, CraResult* out);
 
+/* Class-bound alignment: particle p is matched against reference class_of[p] only, over the same
+ * shift window and with the same arithmetic as cra_align.  This is the alignment step of gpu_isac's
+ * ref_free_alignment_2D (cuda/gpu_aln_noref.cu:743-770: every image of a class against that class's
+ * average); class_of is the reference's sbj_cid_list (gpu_aln_noref.cu:566-571), host int[stop-start].
+ * out[p].iref = class_of[p].                                                                     */
+int  cra_align_bound(CraCtx* ctx, int start, int stop, const CraSearch* search, const int* class_of, CraResult* out);
+/* References rebuilt ON THE DEVICE from the accumulated class sums: ref[r] = (even[r] + odd[r]) / count[r]
+ * (classes without members keep their reference), then prepared like cra_set_refs.  Replaces
+ * BatchHandler::fetch_averages (gpu_aln_noref.cu:772-775).  After N > 1 ranks allreduce the sums buffer
+ * every rank gets the same references.                                                          */
+int  cra_refs_from_sums(CraCtx* ctx, int normalize_mask);
+/* Tangent low-pass of the current references in place (EMAN2 filt_tanl semantics; replaces
+ * ref_free_alignment_2D_filter_references, gpu_aln_noref.cu:777-814), then prepared again.     */
+int  cra_filter_refs(CraCtx* ctx, float cutoff_freq, float falloff, int normalize_mask);
+/* Current reference images [R][nx][nx] to the host (as prepared: after normalize.mask when that was asked). */
+int  cra_get_refs(CraCtx* ctx, float* host_refs);
+
 /* Host bookkeeping of the reference's per-particle Python loop, batched (no device work):
  * cra_mref_search_request = get_params2D -> inverse_transform2 -> mashi reset -> search_range x2
  * (test_mref.py:184-198); params [n][4] double (alpha, sx, sy, mirror) is reset in place where the
@@ -195,6 +212,17 @@ int*        get_num_ref(void);                                                  
 void        pre_align_run(const int start_idx, const int stop_idx);                 /* gpu_aln_noref.cu:520 */
 void*       pre_align_run_m(const int start_idx, const int stop_idx);               /* gpu_aln_noref.cu:489 */
 void        gpu_clear(void);                                                        /* gpu_aln_noref.cu:141 */
+/* gpu_isac's class-bound reference-free alignment (gpu_aln_noref.h:94-109; restype-only in the shipped
+ * drivers).  sbj_cid_list[i] = class of particle i (runs of equal classes, as the reference
+ * requires); every call of ref_free_alignment_2D() aligns each particle to its class average with ormq
+ * semantics, accumulates the shifts in the returned AlignParam[] and rebuilds the averages on the device. */
+AlignParam* ref_free_alignment_2D_init(const AlignConfig* aln_cfg, const float** sbj_data_list,
+                                       const float** ref_data_list, const int* sbj_cid_list,
+                                       const unsigned int cuda_device_id);          /* gpu_aln_noref.cu:559 */
+bool        ref_free_alignment_2D_size_check(const AlignConfig* cfg, const unsigned int cuda_device_id,
+                                             const float request, const bool verbose); /* gpu_aln_noref.cu:625 */
+void        ref_free_alignment_2D(void);                                            /* gpu_aln_noref.cu:743 */
+void        ref_free_alignment_2D_filter_references(const float cutoff_freq, const float falloff); /* gpu_aln_noref.cu:777 */
 
 #ifdef __cplusplus
 }

@@ -570,3 +570,56 @@ def ali2d_base(images, ir=1, ou=-1, rs=1, xr=0, yr=0, ts=1, center=-1, maxit=10,
             sy_sum += sy
         history[-1]["peak"] = out[:, 5].copy()
     return params, tavg, history
+
+
+def ref_free_alignment_2d(images, class_of, refs, ir=1, ou=-1, rs=1, xr=0, yr=0, ts=1, maxit=1, filt=None, nthreads=1):
+    """Class-bound reference-free alignment, CPU twin of gpu_isac's ref_free_alignment_2D
+    (cuda/gpu_aln_noref.cu:559-782): every particle is matched against the average of its own class
+    only (sbj_cid_list, :566-571), the averages are rebuilt from the transformed particles after every
+    pass (:771-775) and optionally low-passed with the tangent filter (:777-814).  The per-particle step
+    has EMAN2 ormq semantics (ali2d_single_iter: no ring normalisation, clamped shifts), as in ali2d_base
+    above.  filt = (cutoff, falloff) or None.  Returns (params [P][4], refs [R][nx][nx], peaks)."""
+    images = np.array(images, np.float32)
+    class_of = np.asarray(class_of, np.int64)
+    refs = np.array(refs, np.float32)
+    P, nx = images.shape[0], images.shape[-1]
+    R = refs.shape[0]
+    if ou == -1:
+        ou = nx // 2 - 2
+    mask = model_circle(ou, nx)
+    numr = numrinit(ir, ou, rs)
+    wr = ringwe(numr)
+    imgs = np.stack([normalize_mask(im, mask, 0) for im in images])
+    params = np.zeros((P, 4))
+    cnx = nx // 2 + 1
+    mashi = cnx - ou - 2
+    peaks = np.zeros(P, np.float32)
+    for it in range(int(maxit)):
+        cref = np.stack([applyws(frngs(polar2dm(refs[r], float(cnx), float(cnx), numr), numr), numr, wr) for r in range(R)])
+        centres = np.zeros((P, 2), np.float32); win = np.zeros((P, 4), np.float32)
+        sxi = np.zeros(P); syi = np.zeros(P)
+        for i in range(P):
+            _, x, y, _ = inverse_transform2(params[i, 0], params[i, 1], params[i, 2])
+            x = min(max(x, -mashi), mashi); y = min(max(y, -mashi), mashi)
+            sxi[i], syi[i] = x, y
+            tx = search_range(nx, ou, x, xr); ty = search_range(nx, ou, y, yr)
+            centres[i] = (cnx + x, cnx + y); win[i] = (tx[0], tx[1], ty[0], ty[1])
+        out = np.zeros((P, 8), np.float32)
+        for r in range(R):
+            idx = np.nonzero(class_of == r)[0]
+            if idx.size:
+                out[idx] = align_batch(imgs[idx], cref[r:r + 1], numr, centres[idx], win[idx], ts, False, nthreads)
+        sums = np.zeros((R, nx, nx), np.float32)
+        counts = np.zeros(R)
+        for i in range(P):
+            a, sx, sy, m = combine_params2(0.0, -sxi[i], -syi[i], 0, out[i, 0], out[i, 1], out[i, 2], int(out[i, 3]))
+            params[i] = (a, sx, sy, m)
+            sums[class_of[i]] += rot_shift2d(imgs[i], a, sx, sy, int(m))
+            counts[class_of[i]] += 1
+        peaks = out[:, 5].copy()
+        for r in range(R):
+            if counts[r] > 0:
+                refs[r] = sums[r] / np.float32(counts[r])
+            if filt is not None:                                 # the reference filters the whole reference batch
+                refs[r] = filt_tanl(refs[r], filt[0], filt[1])
+    return params, refs, peaks

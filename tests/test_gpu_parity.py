@@ -426,3 +426,150 @@ def test_reffree_multi_step_schedule_matches_oracle(oracle, small_set):
     same = (np.abs(p_g[:, 3] - p_o[:, 3]) < 0.5) & (np.abs(p_g[:, 1] - p_o[:, 1]) < 0.05) & (np.abs(p_g[:, 2] - p_o[:, 2]) < 0.05)
     assert same.mean() >= 0.85
     assert np.abs(t_g - t_o).sum() / np.abs(t_o).sum() < 0.05
+
+
+def _class_runs(P, R, seed=3):
+    """Runs of consecutive particles per class, as gpu_isac lays the stack out (gpu_aln_noref.cu:548-556);
+    deliberately ragged, with one empty class."""
+    rng = np.random.default_rng(seed)
+    cuts = np.sort(rng.choice(np.arange(1, P), size=R - 2, replace=False))
+    sizes = np.diff(np.concatenate([[0], cuts, [P]]))            # R - 1 non-empty runs
+    cls = np.concatenate([np.full(s, k, np.int32) for k, s in enumerate(sizes)])
+    cls[cls >= 4] += 1                                           # class 4 has no members
+    return cls
+
+
+def test_class_bound_alignment_matches_oracle(oracle, small_set):
+    """cra_align_bound (gpu_isac ref_free_alignment_2D): each particle against its own class
+    reference only; results equal the oracle's single-reference ormq of that class, particle by particle."""
+    from cryo_ralib_b200 import alignment as al
+    images, refs, _ = small_set
+    P, R = 64, 10
+    cls = _class_runs(P, R)
+    imgs, mask, numr, _, _ = _prep(oracle, images, refs, 36)
+    wr = oracle.ringwe(numr)
+    cref = np.stack([oracle.applyws(oracle.frngs(oracle.polar2dm(refs[r], 46.0, 46.0, numr), numr), numr, wr) for r in range(R)])
+    rng = np.random.default_rng(11)
+    prev = np.zeros((P, 4)); prev[:, 1:3] = rng.uniform(-2.5, 2.5, (P, 2)); prev[:, 0] = rng.uniform(0, 360, P)
+    search, sxi, syi = al.reffree_search_request(prev, (0.0, 0.0), 90, 36, 3, 3)
+    e = _engine(90, 36, 3, P=P, R=R, normalize=False)
+    e.upload_particles(images, subtract_mask_mean=True)
+    e.set_refs(refs, normalize_mask=False)
+    got = e.align_bound(0, P, search, cls)
+    st = e.stats()
+    assert st["alignments"] == st["rows"]                        # one reference per row
+    e.close()
+    assert np.array_equal(got["iref"], cls)
+    centres = np.stack([search["cx"], search["cy"]], 1)
+    win = np.stack([search["xl"], search["xr"], search["yl"], search["yr"]], 1)
+    nbad = 0
+    for r in range(R):
+        idx = np.nonzero(cls == r)[0]
+        if not idx.size:
+            continue
+        want = oracle.align_batch(imgs[idx], cref[r:r + 1], numr, centres[idx], win[idx], 1.0, False, nthreads=8)
+        for k, i in enumerate(idx):
+            rel = abs(got["peak"][i] - want[k][5]) / abs(want[k][5])
+            assert rel < PEAK_RTOL, (i, rel)
+            same = int(got["mirror"][i]) == int(want[k][3]) and got["sx"][i] == want[k][6] and got["sy"][i] == want[k][7]
+            if not same:
+                assert rel < TIE_BAND, (i, rel)
+                nbad += 1
+                continue
+            assert abs((got["ang"][i] - want[k][0] + 180) % 360 - 180) <= 0.5 * 360 / 256
+    assert nbad <= 2
+
+
+def test_tangent_filter_and_device_class_averages(oracle, small_set):
+    """cra_refs_from_sums + cra_filter_refs: class averages rebuilt on the device equal (even + odd) / count,
+    the empty class keeps its reference, and the shared-memory DFT filter equals filt_tanl (numpy FFT)."""
+    images, refs, _ = small_set
+    P, R = 64, 10
+    cls = _class_runs(P, R)
+    rng = np.random.default_rng(5)
+    params = np.zeros((P, 4), np.float32)
+    params[:, 0] = rng.uniform(0, 360, P); params[:, 1:3] = rng.uniform(-3, 3, (P, 2)); params[:, 3] = rng.integers(0, 2, P)
+    e = _engine(90, 36, 3, P=P, R=R, normalize=False)
+    e.upload_particles(images, subtract_mask_mean=True)
+    e.set_refs(refs, normalize_mask=False)
+    e.zero_sums()
+    e.accumulate(0, P, params, cls, 0)
+    sums, counts = e.get_sums()
+    e.refs_from_sums(normalize_mask=False)
+    avg = e.get_refs()
+    for r in range(R):
+        if counts[r] > 0:
+            want = (sums[r, 0] + sums[r, 1]) / np.float32(counts[r])
+            assert np.abs(avg[r] - want).max() <= 1e-6 * np.abs(want).max()
+        else:
+            assert r == 4 and np.array_equal(avg[r], refs[r])
+    for fl, aa in ((0.12, 0.2), (0.3, 0.1), (0.05, 0.4)):
+        e.set_refs(avg, normalize_mask=False)
+        e.filter_refs(fl, aa, normalize_mask=False)
+        got = e.get_refs()
+        for r in range(R):
+            want = oracle.filt_tanl(avg[r], fl, aa)
+            assert np.abs(got[r] - want).max() <= 2e-5 * np.abs(avg[r]).max(), (fl, aa, r)
+    # the filtered references are the ones the next alignment uses
+    spec = e.ref_spectrum(2)
+    numr = oracle.numrinit(1, 36, 1)
+    want = oracle.applyws(oracle.frngs(oracle.polar2dm(got[2], 46.0, 46.0, numr), numr), numr, oracle.ringwe(numr))
+    assert np.abs(spec - want).max() <= 2e-5 * np.abs(want).max()
+    e.close()
+    # odd box: the Hermitian reconstruction has no Nyquist column
+    e = _engine(45, 16, 1, P=1, R=2, normalize=False)
+    small = np.ascontiguousarray(images[:2, 20:65, 20:65])
+    e.set_refs(small, normalize_mask=False)
+    e.filter_refs(0.2, 0.15)
+    got = e.get_refs()
+    for r in range(2):
+        want = oracle.filt_tanl(small[r], 0.2, 0.15)
+        assert np.abs(got[r] - want).max() <= 2e-5 * np.abs(small[r]).max()
+    e.close()
+
+
+def test_ref_free_alignment_2d_matches_oracle(oracle, small_set):
+    """The whole class-bound loop (align to own class average -> transformed class averages on the device ->
+    tangent filter) for two passes, host loop and legacy ABI alike, against the oracle twin."""
+    import ctypes as C
+    from cryo_ralib_b200.mref import ref_free_alignment_2d
+    from cryo_ralib_b200.lib import load_library, AlignConfig, AlignParam
+    images, refs, _ = small_set
+    P, R = 64, 10
+    cls = _class_runs(P, R)
+    filt = (0.25, 0.2)
+    p_o, r_o, k_o = oracle.ref_free_alignment_2d(images, cls, refs, ou=36, xr=2, yr=2, ts=1, maxit=2, filt=filt, nthreads=8)
+    p_g, r_g, h_g = ref_free_alignment_2d(images, cls, refs, ou=36, xr=2, yr=2, ts=1, maxit=2, filt=filt)
+    same = (np.abs(p_g[:, 3] - p_o[:, 3]) < 0.5) & (np.abs(p_g[:, 1] - p_o[:, 1]) < 0.05) & (np.abs(p_g[:, 2] - p_o[:, 2]) < 0.05)
+    assert same.mean() >= 0.9, same.mean()
+    rel = np.abs(h_g[-1]["peak"] - k_o) / np.abs(k_o)
+    assert np.median(rel) < PEAK_RTOL
+    assert np.abs(r_g - r_o).sum() / np.abs(r_o).sum() < 0.05
+    assert np.abs(r_g[4] - r_o[4]).max() <= 1e-4 * np.abs(refs[4]).max()     # empty class: only filtered, twice
+    # legacy symbols, first pass (gpu_aln_noref.h:94-109)
+    mask = oracle.model_circle(36, 90)
+    imgs = np.stack([oracle.normalize_mask(im, mask, 0) for im in images])
+    L = load_library()
+    cfg = AlignConfig(P, R, 90, 36, 256, 1.0, 2.0, 2.0)
+    assert L.ref_free_alignment_2D_size_check(C.byref(cfg), 0, 0.9, False)
+    fp = C.POINTER(C.c_float)
+    data = [np.ascontiguousarray(imgs[i]) for i in range(P)]
+    rdata = [np.ascontiguousarray(refs[j]) for j in range(R)]
+    cid = np.ascontiguousarray(cls, np.int32)
+    ptr = L.ref_free_alignment_2D_init(C.byref(cfg), (fp * P)(*[d.ctypes.data_as(fp) for d in data]),
+                                       (fp * R)(*[d.ctypes.data_as(fp) for d in rdata]), cid.ctypes.data_as(C.POINTER(C.c_int)), 0)
+    assert ptr
+    par = C.cast(ptr, C.POINTER(AlignParam))
+    L.ref_free_alignment_2D()
+    L.ref_free_alignment_2D_filter_references(filt[0], filt[1])
+    p1, _, _ = oracle.ref_free_alignment_2d(images, cls, refs, ou=36, xr=2, yr=2, ts=1, maxit=1, filt=filt, nthreads=8)
+    ok = 0
+    for i in range(P):
+        assert par[i].ref_id == cls[i]
+        a = np.deg2rad(par[i].angle)
+        sx = -par[i].shift_x * np.cos(a) + (-par[i].shift_y) * np.sin(a)      # the a19 conversion
+        sy = par[i].shift_x * np.sin(a) - par[i].shift_y * np.cos(a)
+        if int(par[i].mirror) == int(p1[i, 3]) and abs(sx - p1[i, 1]) < 0.05 and abs(sy - p1[i, 2]) < 0.05:
+            ok += 1
+    assert ok >= P - 3, ok
+    L.gpu_clear()

@@ -175,3 +175,31 @@ def test_reference_update_pieces(oracle):
     assert abs(cs[0] - 3.5) < 0.05 and abs(cs[1] + 2.75) < 0.05
     lp = oracle.filt_tanl(x, 0.12, 0.2)
     assert abs(lp.mean() - x.mean()) < 1e-4 and lp.std() < x.std()
+
+
+def test_class_bound_oracle_recovers_rotations(oracle):
+    """oracle.ref_free_alignment_2d (twin of gpu_isac's ref_free_alignment_2D): particles that are exact
+    ring-step rotations of their class reference come back with the inverse rotation, and the rebuilt class
+    average equals the reference again; an empty class keeps its reference."""
+    from cryo_ralib_b200 import synth
+    images, _ = synth.make_particles(3, 64, 3, max_shift=0, seed=21)
+    refs = np.stack([images[0], images[1], images[2]]).astype(np.float32)
+    mask = oracle.model_circle(24, 64)
+    base = np.stack([oracle.normalize_mask(r, mask, 0) for r in refs])
+    parts, cls, angs = [], [], []
+    for c in (0, 2):                                             # class 1 stays empty
+        for k in (16, 48, 96):
+            a = 360.0 * k / 128.0                                # maxrin = 128 at ou = 24
+            parts.append(oracle.rot_shift2d(base[c], a, 0.0, 0.0, 0)); cls.append(c); angs.append(a)
+    parts = np.stack(parts).astype(np.float32)
+    p, r, pk = oracle.ref_free_alignment_2d(parts, np.array(cls), base, ou=24, xr=1, yr=1, ts=1, maxit=1)
+    for i, a in enumerate(angs):
+        d = (p[i, 0] + a + 180.0) % 360.0 - 180.0
+        assert abs(d) < 0.75, (i, p[i], a)
+        assert abs(p[i, 1]) < 0.5 and abs(p[i, 2]) < 0.5 and p[i, 3] == 0
+    assert np.array_equal(r[1], base[1])
+    inside = mask > 0.5
+    for c in (0, 2):
+        a, b = r[c][inside], base[c][inside]                     # noisy images rotated twice: compare by correlation
+        cc = float(np.corrcoef(a, b)[0, 1])
+        assert cc > 0.85, cc
