@@ -222,7 +222,7 @@ def ali2d_base(images, ir=1, ou=-1, rs=1, xr=0, yr=0, ts=1, center=-1, maxit=10,
 
 
 def ref_free_alignment_2d(images, class_of, refs, ir=1, ou=-1, rs=1, xr=0, yr=0, ts=1, maxit=1, filt=None, comm=None,
-                          global_offset=0, engine=None, device=0, on_iteration=None):
+                          global_offset=0, engine=None, device=0, device_allreduce=True, on_iteration=None):
     """gpu_isac's class-bound reference-free alignment (ref_free_alignment_2D, cuda/gpu_aln_noref.cu:559-782):
     every particle is aligned to the average of its own class only (class_of = sbj_cid_list), the class
     averages are rebuilt ON THE DEVICE from the transformed particles after every pass and optionally
@@ -232,7 +232,7 @@ def ref_free_alignment_2d(images, class_of, refs, ir=1, ou=-1, rs=1, xr=0, yr=0,
     from .lib import Engine
     comm = comm or LocalComm()
     n, nx = images.shape[0], images.shape[-1]
-    refs = np.ascontiguousarray(refs, np.float32)
+    refs = np.array(refs, np.float32)
     class_of = np.ascontiguousarray(class_of, np.int32)
     R = refs.shape[0]
     if ou == -1:
@@ -251,16 +251,26 @@ def ref_free_alignment_2d(images, class_of, refs, ir=1, ou=-1, rs=1, xr=0, yr=0,
         params = al.compose_result(sxi, syi, res)
         engine.zero_sums()
         engine.accumulate(0, n, params, class_of, global_offset)
-        if comm.world > 1:
-            comm.allreduce_device(engine)
-        engine.refs_from_sums(normalize_mask=False)
-        if filt is not None:
-            engine.filter_refs(filt[0], filt[1], normalize_mask=False)
+        if device_allreduce:
+            if comm.world > 1:
+                comm.allreduce_device(engine)
+            engine.refs_from_sums(normalize_mask=False)
+            if filt is not None:
+                engine.filter_refs(filt[0], filt[1], normalize_mask=False)
+        else:
+            # host exchange (gloo / no NCCL): same arithmetic on the reduced sums, references re-uploaded
+            sums, counts = _reduce_sums(engine, comm, False)
+            for r in range(R):
+                if counts[r] > 0.5:
+                    refs[r] = (sums[r, 0] + sums[r, 1]) / np.float32(counts[r])
+                if filt is not None:
+                    refs[r] = ru.filt_tanl(refs[r], filt[0], filt[1])
+            engine.set_refs(refs, normalize_mask=False)
         info = dict(peak=res["peak"].copy(), stats=engine.stats())
         history.append(info)
         if on_iteration:
             on_iteration(it, params, info)
-    out_refs = engine.get_refs()
+    out_refs = engine.get_refs() if device_allreduce else refs
     if own_engine:
         engine.close()
     return params, out_refs, history

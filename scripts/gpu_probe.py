@@ -1,5 +1,5 @@
 """Quick device probe: FP32 peak micro-benchmark + stage timings on a config-2-shaped slice.
-usage: gpu_probe.py [P] [R] [nx] [ou] [xr]"""
+usage: gpu_probe.py [P] [R] [nx] [ou] [xr] [ts]"""
 import json
 import sys
 import time
@@ -14,9 +14,10 @@ R = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 nx = int(sys.argv[3]) if len(sys.argv) > 3 else 90
 ou = int(sys.argv[4]) if len(sys.argv) > 4 else 36
 xr = int(sys.argv[5]) if len(sys.argv) > 5 else 3
+ts = float(sys.argv[6]) if len(sys.argv) > 6 else 1.0
 images, _ = synth.make_particles(P, nx, 64, seed=2025)
-refs = synth.initial_references(images, R, seed=99)
-e = Engine(nx, ou, xr, max_particles=P, max_refs=R)
+refs = synth.initial_references(images, R, per_ref=max(1, min(200, P // R)), seed=99)
+e = Engine(nx, ou, xr, ts=ts, max_particles=P, max_refs=R)
 print("fp32 peak (ffma, ffma2) TFLOP/s:", e.measure_fp32_peak())
 e.upload_particles(images)
 e.set_refs(refs)

@@ -23,7 +23,26 @@ class OracleEngine(object):
         self.imgs = np.stack([self.o.normalize_mask(im, self.mask, 0) for im in images])
 
     def set_refs(self, refs, normalize_mask=True):
-        _, self.cref = self.o.prepare_refs(refs, self.mask, self.numr)
+        o = self.o
+        if normalize_mask:
+            _, self.cref = o.prepare_refs(refs, self.mask, self.numr)
+        else:
+            c = float(self.nx // 2 + 1)
+            wr = o.ringwe(self.numr)
+            self.cref = np.stack([o.applyws(o.frngs(o.polar2dm(r, c, c, self.numr), self.numr), self.numr, wr) for r in refs])
+
+    def align_bound(self, start, stop, search, class_of):
+        from cryo_ralib_b200.lib import RESULT_DTYPE
+        r = np.zeros(stop - start, RESULT_DTYPE)
+        cen = np.stack([search["cx"], search["cy"]], 1)
+        win = np.stack([search["xl"], search["xr"], search["yl"], search["yr"]], 1)
+        for c in np.unique(class_of):
+            idx = np.nonzero(class_of == c)[0]
+            out = self.o.align_batch(self.imgs[start:stop][idx], self.cref[c:c + 1], self.numr, cen[idx], win[idx], self.ts, False, 2)
+            for k, col in zip(("ang", "sxs", "sys", "mirror", "iref", "peak", "sx", "sy"), range(8)):
+                r[k][idx] = out[:, col]
+        r["iref"] = class_of
+        return r
 
     def align(self, start, stop, search):
         from cryo_ralib_b200.lib import RESULT_DTYPE
@@ -102,3 +121,53 @@ def test_two_rank_gloo_equals_single_rank():
     assert np.abs(got[0][5] - r1).max() <= 1e-5 * np.abs(r1).max()   # allreduce order only
     assert all(np.array_equal(c0, c1) for c0, c1 in zip(got[0][6], [x["counts"] for x in h1]))
     assert sum(got[0][6][-1]) == images.shape[0]
+
+
+def _bound_case():
+    images, refs = _case()
+    cls = np.array([0] * 9 + [2] * 13, np.int32)                    # runs of classes; class 1 empty; a run spans the rank split
+    return images, refs, cls
+
+
+def _bound_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cryo_ralib_b200 import alignment as al
+    from cryo_ralib_b200.mref import ref_free_alignment_2d, TorchComm
+    images, refs, cls = _bound_case()
+    s, e = al.mpi_start_end(images.shape[0], world, rank)
+    eng = OracleEngine(64, 28, 3, 1, 1.0)
+    p, r, h = ref_free_alignment_2d(images[s:e], cls[s:e], refs, ou=28, xr=1, yr=1, ts=1, maxit=2, filt=(0.3, 0.2),
+                                    comm=TorchComm(), global_offset=s, engine=eng, device_allreduce=False)
+    q.put((rank, p, r))
+    dist.destroy_process_group()
+
+
+def test_two_rank_class_bound_alignment_equals_single_rank_and_oracle():
+    """ref_free_alignment_2d (gpu_isac's class-bound variant) sharded over two ranks: same parameters as one
+    rank, identical references on every rank, and both equal the oracle twin."""
+    import torch.multiprocessing as mp
+    from oracle import oracle as o
+    from cryo_ralib_b200.mref import ref_free_alignment_2d
+    images, refs, cls = _bound_case()
+    eng = OracleEngine(64, 28, 3, 1, 1.0)
+    p1, r1, _ = ref_free_alignment_2d(images, cls, refs, ou=28, xr=1, yr=1, ts=1, maxit=2, filt=(0.3, 0.2), engine=eng,
+                                      device_allreduce=False)
+    p0, r0, _ = o.ref_free_alignment_2d(images, cls, refs, ou=28, xr=1, yr=1, ts=1, maxit=2, filt=(0.3, 0.2), nthreads=2)
+    assert np.allclose(p1, p0, atol=1e-5) and np.abs(r1 - r0).max() <= 1e-5 * np.abs(r0).max()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bound_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    got = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert np.array_equal(got[0][2], got[1][2])
+    assert np.allclose(np.concatenate([got[0][1], got[1][1]]), p1, atol=1e-5)
+    assert np.abs(got[0][2] - r1).max() <= 1e-5 * np.abs(r1).max()
