@@ -58,12 +58,15 @@ RESULT_DTYPE = np.dtype([("ang", "f4"), ("sxs", "f4"), ("sys", "f4"), ("mirror",
 
 CORE_SYMBOLS = ["cra_create", "cra_destroy", "cra_last_error", "cra_ring_info", "cra_upload_particles",
                 "cra_upload_particles_dev", "cra_upload_particles_async", "cra_upload_wait", "cra_mref_search_request",
-                "cra_compose_result", "cra_set_refs", "cra_align", "cra_accumulate", "cra_zero_sums",
+                "cra_compose_result", "cra_set_refs", "cra_align", "cra_align_bound", "cra_refs_from_sums", "cra_filter_refs",
+                "cra_get_refs", "cra_accumulate", "cra_zero_sums",
                 "cra_sums_device_ptr", "cra_get_sums", "cra_transform", "cra_polar_spectrum", "cra_ref_spectrum", "cra_batch_row_spectrum",
                 "cra_ccf_curves", "cra_last_align_stats", "cra_set_timing", "cra_set_normalize_ring", "cra_set_step",
                 "cra_row_batch", "cra_device_images_ptr", "cra_stream", "cra_measure_fp32_peak"]
 LEGACY_SYMBOLS = ["print_gpu_info", "pre_align_size_check", "pre_align_init", "pre_align_fetch", "reset_shifts",
-                  "mref_align_run", "mref_align_run_m", "get_num_ref", "pre_align_run", "pre_align_run_m", "gpu_clear"]
+                  "mref_align_run", "mref_align_run_m", "get_num_ref", "pre_align_run", "pre_align_run_m", "gpu_clear",
+                  "ref_free_alignment_2D_init", "ref_free_alignment_2D_size_check", "ref_free_alignment_2D",
+                  "ref_free_alignment_2D_filter_references"]
 
 _LIB = None
 
