@@ -42,10 +42,7 @@ constexpr int kPfDist = 40;             // row blocks between an L2 prefetch and
 __device__ int g_items[kWarps][kMaxItems];
 __device__ int g_nitems[kWarps];
 __device__ int g_flush[kWarps][kMaxFreq];
-__device__ int g_res[4][8];
-// SM pairing of the persistent grid (zeroed before every launch): [0] SMs ranked so far, [1 + smid] rank + 1 of
-// that SM, [1025 + smid] CTAs started on it
-__device__ int g_pairtab[2049];             // residues n2 of quadrant q, in TMEM order (N2 / 4 of them)
+__device__ int g_res[4][8];             // residues n2 of quadrant q, in TMEM order (N2 / 4 of them)
 
 using crafft::fft_reg;
 
@@ -133,7 +130,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned char* __restrict__ refspec, int R,
               size_t row_bytes, const float2* __restrict__ twid, CraCand* __restrict__ cand,
               int nquad, int ncta_n, const float2* __restrict__ norm, const float* __restrict__ tref, int istride, int fstride,
-              long ntiles, int paired)
+              long ntiles)
 {
     using S = TShape<LOG2N>;
     constexpr int N = S::N, N1 = S::N1, N2 = S::N2, PS = S::PS, NJ = S::NJ, RQ = S::RQ, JCOLS = S::JCOLS;
@@ -170,32 +167,8 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
     // Persistent CTA: the work lists, the twiddles and the TMEM allocation above are set up once, then
     // the CTA walks the tiles with the grid stride.  Reference tile fastest, so that the CTAs resident
     // at any moment share the row spectra in L2.
-    // paired: the two CTAs of an SM take adjacent tiles (same row block, neighbouring reference tiles) at the same
-    // time, so the row operands the first one pulls through L1 serve the second.  The SM's first CTA draws a dense
-    // rank for the SM, the second one reads it (its partner is resident, so the wait is short).
-    int tile_first = blockIdx.x, tile_step = gridDim.x;
-    if (paired) {
-        __shared__ int s_pr[2];
-        if (tid == 0) {
-            unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            smid &= 1023u;
-            const int slot = atomicAdd(&g_pairtab[1025 + smid], 1);
-            int rank;
-            if (slot == 0) {
-                rank = atomicAdd(&g_pairtab[0], 1);
-                __threadfence();
-                atomicExch(&g_pairtab[1 + smid], rank + 1);
-            } else {
-                while ((rank = atomicAdd(&g_pairtab[1 + smid], 0)) == 0) __nanosleep(64);
-                rank -= 1;
-            }
-            s_pr[0] = rank; s_pr[1] = slot & 1;
-        }
-        __syncthreads();
-        tile_first = 2 * s_pr[0] + s_pr[1];
-    }
 #pragma unroll 1
-    for (int tile = tile_first; tile < (int)ntiles; tile += tile_step) {
+    for (int tile = blockIdx.x; tile < (int)ntiles; tile += gridDim.x) {
     {
     const int cm = tile / ncta_n, cn = tile - cm * ncta_n;
     const int nj = qbase + (cn < qrem ? 1 : 0);                 // reference quads of this tile (<= NJ)
@@ -526,20 +499,10 @@ int launch_t(const unsigned char* spec, int nrows, const unsigned char* refspec,
         resident = nsm * per;
     }
     const char* np = getenv("CRA_TM_PERSIST");
-    const char* pp = getenv("CRA_TM_PAIR");
     const long grid = (np && np[0] == '0') ? nblk : std::min<long>(nblk, resident);
-    static int nsm_cached = 0;
-    if (!nsm_cached) { int dev = 0; CRA_CUDA(cudaGetDevice(&dev)); CRA_CUDA(cudaDeviceGetAttribute(&nsm_cached, cudaDevAttrMultiProcessorCount, dev)); }
-    // pairing needs exactly two CTAs on every SM: the full persistent grid, registers and TMEM allowing no third
-    const int paired = (grid == resident && resident == 2 * nsm_cached && !(pp && pp[0] == '0')) ? 1 : 0;
-    if (paired) {
-        void* tab = nullptr;
-        CRA_CUDA(cudaGetSymbolAddress(&tab, g_pairtab));
-        CRA_CUDA(cudaMemsetAsync(tab, 0, sizeof(int) * 2049, st));
-    }
     if (getenv("CRA_TM_DEBUG")) fprintf(stderr, "ccf_tm: tiles %ld grid %ld resident %d smem %zu\n", nblk, grid, resident, smem);
     ccf_tm_kernel<LOG2N><<<(unsigned)grid, kThreads, smem, st>>>(spec, nrows, refspec, R, row_bytes, twid, cand, nquad, ntile_n,
-                                                                norm, tref, g_sched.istride, g_sched.fstride, nblk, paired);
+                                                                norm, tref, g_sched.istride, g_sched.fstride, nblk);
     CRA_CUDA(cudaGetLastError());
     return 0;
 }
