@@ -215,9 +215,15 @@ def main():
     goff = rank * P
     params0 = np.zeros((P, 4))
 
-    NCHUNK = 8        # e2e: the stack is uploaded in chunks on the copy stream, each aligned as soon as it landed
-    bounds = [al.mpi_start_end(P, NCHUNK, i) for i in range(NCHUNK)]
-    bounds = [(s, e) for s, e in bounds if e > s]
+    # e2e: the stack is uploaded in chunks on the copy stream, each aligned as soon as it landed.  Chunks are whole
+    # row batches of the engine (no partial launches in between); the first one is small so the alignment starts early.
+    S = (2 * int(xr / ts) + 1) * (2 * int(yr / ts) + 1)
+    per_batch = max(1, eng.L.cra_row_batch(eng.h) // S)
+    bounds, s0, nb = [], 0, 1
+    while s0 < P:
+        e0 = min(P, s0 + nb * per_batch)
+        bounds.append((s0, e0))
+        s0, nb = e0, min(8, nb * 2)
 
     def step(resident, params):
         """One iteration of the per-particle section; returns (new params, assign, stats)."""

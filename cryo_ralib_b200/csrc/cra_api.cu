@@ -812,6 +812,28 @@ extern "C" int cra_get_sums(CraCtx* c, float* host_sums, float* host_counts)
     return 0;
 }
 
+extern "C" int cra_transform_dev(CraCtx* c, int start, int stop, const float* params, float* dev_out)
+{
+    Bind b(c); if (b.ok()) return 1;
+    const int n = stop - start;
+    if (start < 0 || n < 0 || stop > c->cfg.max_particles) { cra_set_error("particle range exceeds max_particles"); return 1; }
+    if (n == 0) return 0;
+    if (!dev_out) { cra_set_error("null output buffer"); return 1; }
+    if (wait_uploads(c, start, n)) return 1;
+    const int chunk = std::min(n, 65536);
+    if (ensure_par(c, chunk)) return 1;
+    for (int s = 0; s < n; s += chunk) {
+        const int m = std::min(chunk, n - s);
+        for (int i = 0; i < m; ++i)
+            c->h_par[i] = make_float4(params[4 * (s + i)], params[4 * (s + i) + 1], params[4 * (s + i) + 2], params[4 * (s + i) + 3]);
+        CRA_CUDA(cudaMemcpyAsync(c->d_par, c->h_par, sizeof(float4) * m, cudaMemcpyHostToDevice, c->st));
+        if (cra_launch_rotsum(c->d_images, c->nx, start + s, m, c->d_par, nullptr, 0, nullptr, nullptr,
+                              dev_out + (size_t)s * c->npix, c->st)) return 1;
+        CRA_CUDA(cudaStreamSynchronize(c->st));       // h_par is reused by the next chunk
+    }
+    return 0;
+}
+
 extern "C" int cra_transform(CraCtx* c, int start, int stop, const float* params, float* host_out)
 {
     Bind b(c); if (b.ok()) return 1;

@@ -205,7 +205,9 @@ extern "C" void pre_align_fetch(const float** img_data, const unsigned int img_n
         if (cudaMallocHost(&g.h_stage, need * sizeof(float)) != cudaSuccess) { fprintf(stderr, "[cryo_ralib] pinned alloc failed\n"); g.h_stage = nullptr; g.stage_n = 0; return; }
         g.stage_n = need;
     }
-    for (unsigned i = 0; i < img_num; ++i) memcpy(g.h_stage + (size_t)i * npix, img_data[i], npix * sizeof(float));
+    // gather of the borrowed per-image host pointers into the pinned staging buffer, all host threads
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)img_num; ++i) memcpy(g.h_stage + (size_t)i * npix, img_data[i], npix * sizeof(float));
     int rc;
     if (strcmp(batch_type, "sbj_batch") == 0) rc = cra_upload_particles(g.ctx, g.h_stage, 0, (int)img_num, 0);
     else if (strcmp(batch_type, "ref_batch") == 0) rc = cra_set_refs(g.ctx, g.h_stage, (int)img_num, 0);
@@ -235,9 +237,7 @@ static int transform_batch(int start, int stop, bool want_images, bool want_sums
             if (cudaMalloc(&g.d_trans, (size_t)n * npix * sizeof(float)) != cudaSuccess) { cra_set_error("transformed-image alloc failed"); g.d_trans = nullptr; g.trans_n = 0; return 1; }
             g.trans_n = (size_t)n * npix;
         }
-        std::vector<float> host((size_t)n * npix);
-        if (cra_transform(g.ctx, 0, n, g.par.data(), host.data())) return 1;
-        if (cudaMemcpy(g.d_trans, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) { cra_set_error("copy of transformed images failed"); return 1; }
+        if (cra_transform_dev(g.ctx, 0, n, g.par.data(), g.d_trans)) return 1;      // stays on the device
     }
     if (want_sums) {
         const int R = (int)g.cfg.ref_num;

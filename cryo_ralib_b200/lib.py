@@ -60,7 +60,7 @@ CORE_SYMBOLS = ["cra_create", "cra_destroy", "cra_last_error", "cra_ring_info", 
                 "cra_upload_particles_dev", "cra_upload_particles_async", "cra_upload_wait", "cra_mref_search_request",
                 "cra_compose_result", "cra_set_refs", "cra_align", "cra_align_bound", "cra_refs_from_sums", "cra_filter_refs",
                 "cra_get_refs", "cra_accumulate", "cra_zero_sums",
-                "cra_sums_device_ptr", "cra_get_sums", "cra_transform", "cra_polar_spectrum", "cra_ref_spectrum", "cra_batch_row_spectrum",
+                "cra_sums_device_ptr", "cra_get_sums", "cra_transform", "cra_transform_dev", "cra_polar_spectrum", "cra_ref_spectrum", "cra_batch_row_spectrum",
                 "cra_ccf_curves", "cra_last_align_stats", "cra_set_timing", "cra_set_normalize_ring", "cra_set_step",
                 "cra_row_batch", "cra_device_images_ptr", "cra_stream", "cra_measure_fp32_peak"]
 LEGACY_SYMBOLS = ["print_gpu_info", "pre_align_size_check", "pre_align_init", "pre_align_fetch", "reset_shifts",
@@ -103,6 +103,7 @@ def load_library(path=None):
     L.cra_sums_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.cra_get_sums.argtypes = [vp, vp, vp]
     L.cra_transform.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    L.cra_transform_dev.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     L.cra_polar_spectrum.argtypes = [vp, C.c_int, C.c_float, C.c_float, vp]
     L.cra_ref_spectrum.argtypes = [vp, C.c_int, vp]
     L.cra_batch_row_spectrum.argtypes = [vp, C.c_int, vp, ip]

@@ -138,6 +138,9 @@ int  cra_get_sums(CraCtx* ctx, float* host_sums /*[R][2][nx][nx]*/, float* host_
 /* rot_shift2D only: transformed images of [start,stop) to a host buffer
  * (ref-free sum_oe / apply-transform export).                               */
 int  cra_transform(CraCtx* ctx, int start, int stop, const float* params, float* host_out);
+/* The same into a caller-owned DEVICE buffer [stop-start][nx][nx] (what mref_align_run hands back,
+ * gpu_aln_noref.cu:389-416: the transformed images never leave the GPU).                       */
+int  cra_transform_dev(CraCtx* ctx, int start, int stop, const float* params, float* dev_out);
 
 /* Stage-level entry points used by the parity tests. */
 int  cra_polar_spectrum(CraCtx* ctx, int particle, float cx, float cy, float* host_out /*lcirc*/);

@@ -23,11 +23,14 @@ def oracle():
 
 @pytest.fixture(scope="session")
 def small_set():
-    """64 synthetic 90x90 particles + 10 initial references (config-1 geometry)."""
+    """64 synthetic 90x90 particles + 10 initial references (config-1 geometry).  The references are averages
+    of OTHER particles of the same data set (a particle that is part of a reference matches it at angle 0, shift 0,
+    which would leave the angular search untested)."""
     from cryo_ralib_b200 import synth
-    images, truth = synth.make_particles(64, 90, 16, max_shift=3, seed=7)
-    refs = synth.initial_references(images, 10, per_ref=6, seed=5)
-    return images, refs, truth
+    allp, truth = synth.make_particles(64 + 60, 90, 16, max_shift=3, seed=7)
+    refs = synth.initial_references(allp[64:], 10, per_ref=6, seed=5)
+    truth = {k: v[:64] for k, v in truth.items()}
+    return np.ascontiguousarray(allp[:64]), refs, truth
 
 
 def has_gpu():

@@ -375,6 +375,21 @@ def test_legacy_abi_roundtrip(oracle, small_set):
     assert counts.sum() == P
     assert abs(sums.sum()) >= 0   # layout: R even sums then R odd sums
     ev = sum(1 for i in range(0, P, 2)); assert ev == (P + 1) // 2
+    # mref_align_run: device pointer to the transformed images (they never leave the GPU); read a few back
+    dptr = L.mref_align_run(0, P)
+    assert dptr
+    rt = C.CDLL("/usr/local/cuda/lib64/libcudart.so")
+    rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    got = np.zeros((P, 90, 90), np.float32)
+    assert rt.cudaMemcpy(got.ctypes.data, C.c_void_p(dptr), got.nbytes, 2) == 0
+    for i in (0, 7, P - 1):
+        if min(par[i].angle % 90.0, 90.0 - par[i].angle % 90.0) < 0.5:
+            continue          # sample positions within rounding of the pixel grid: quadri's cell choice is a tie
+        a = np.deg2rad(par[i].angle)
+        sx = -par[i].shift_x * np.cos(a) - par[i].shift_y * np.sin(a)        # the a19 conversion
+        sy = par[i].shift_x * np.sin(a) - par[i].shift_y * np.cos(a)
+        want_img = oracle.rot_shift2d(imgs[i], par[i].angle, sx, sy, int(par[i].mirror))
+        assert np.abs(got[i] - want_img).max() <= 1e-4 * np.abs(want_img).max(), i
     L.gpu_clear()
 
 
