@@ -290,11 +290,14 @@ def test_rot_shift_accumulate_matches_oracle(oracle, small_set):
     e = _engine(90, 36, 3, P=P, R=R)
     e.upload_particles(images[:P])
     e.zero_sums()
+    iref[5] = -1; iref[17] = -1                                    # skipped particles
     e.accumulate(0, P, params, iref, global_offset=1001)
     sums, counts = e.get_sums()
     want = np.zeros((R, 2, 90, 90), np.float64)
     cnt = np.zeros(R)
     for i in range(P):
+        if iref[i] < 0:
+            continue
         want[iref[i], (1001 + i) % 2] += oracle.rot_shift2d(imgs[i], *params[i])
         cnt[iref[i]] += 1
     assert np.array_equal(counts, cnt)
