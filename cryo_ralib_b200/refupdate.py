@@ -111,7 +111,7 @@ def amoeba(var, scale, func, ftolerance=1.e-4, xtolerance=1.e-4, itmax=500, data
         iteration += 1
 
 
-def fit_tanh(dres, low=0.1):
+def fit_tanh(dres, low=0.1, native=True):
     """sp_filter.fit_tanh: (cut-off, fall-off) of the tanh low-pass that best fits 2f/(1+f)."""
     freq = np.array(dres[0], np.float64)
     val = np.array(dres[1], np.float64)
@@ -139,6 +139,14 @@ def fit_tanh(dres, low=0.1):
         qt = target - 0.5 * (np.tanh(c * (freq + args[0])) - np.tanh(c * (freq - args[0])))
         return -float(np.sum(qt * qt))
 
+    L = _native() if native else None
+    if L is not None:
+        # the same simplex in native code (csrc/cra_host.cu: cra_fit_tanh): ~1500 cost evaluations
+        f = np.ascontiguousarray(freq, np.float64); t = np.ascontiguousarray(target, np.float64)
+        out = np.zeros(4, np.float64)
+        if L.cra_fit_tanh(len(f), f.ctypes.data, t.ctypes.data, float(fl), 0.1, 0.05, 0.05, out.ctypes.data) != 0:
+            raise RuntimeError(L.cra_last_error().decode())
+        return float(out[0]), float(out[1])
     best, _, _ = amoeba([fl, 0.1], [0.05, 0.05], cost)
     return best[0], best[1]
 
@@ -189,8 +197,18 @@ def model_circle(r, nx):
     return ((x2 * x2) / (rr * rr) + (y2 * y2) / (rr * rr) <= 1).astype(np.float32)
 
 
-def ref_ali2d(avg, frsc, center):
-    fl, aa = fit_tanh(frsc)
+def _native():
+    try:
+        from .lib import load_library
+        return load_library()
+    except Exception:
+        return None
+
+
+def ref_ali2d(avg, frsc, center, fit=None):
+    """sp_user_functions.ref_ali2d.  fit: a (fl, aa) already fitted to this frsc (mref_ali2d hands every class the
+    same class-averaged FSC, test_mref.py:258-276, so update_refs fits it once)."""
+    fl, aa = fit if fit is not None else fit_tanh(frsc)
     aa = min(aa, 0.2)
     fl = max(min(0.4, fl), 0.12)
     out = filt_tanl(avg, fl, aa)
@@ -226,8 +244,9 @@ def update_refs(sums, counts, mask, center=1, reseed=None):
     if acc.sum() != 0:
         frsc[1] = list(acc / float(nfsc))
     info = dict(frsc=[list(frsc[0]), list(frsc[1]), list(frsc[2])], reseeded=reseeded, cs=[], filter=None)
+    fit = fit_tanh(frsc)                      # the same FSC curve for every class: one fit
     for j in range(R):
-        refs[j], cs, info["filter"] = ref_ali2d(refs[j], frsc, center)
+        refs[j], cs, info["filter"] = ref_ali2d(refs[j], frsc, center, fit=fit)
         info["cs"].append(cs)
         refs[j] = normalize_mask(refs[j], mask, 1)
     return refs, info

@@ -122,6 +122,14 @@ int  cra_mref_search_request(int n, double* params, int nx, int ou, double xr, d
                              CraSearch* search, double* sxi_out, double* syi_out);
 int  cra_compose_result(int n, const double* sxi, const double* syi, const CraResult* res, double* params_out);
 
+/* sp_filter.fit_tanh's optimisation (host arithmetic, no device work): Nelder-Mead fit (sp_utilities.amoeba, same
+ * simplex, tolerances 1e-4, 500 iterations at most) of 0.5 (tanh(c (f + fl)) - tanh(c (f - fl))), c = pi / (2 aa fl), to
+ * target[i] = 2 FSC / (1 + FSC) at freq[i]; start (fl0, aa0), simplex scale (scale_fl, scale_aa).  The user
+ * function ref_ali2d runs it for every reference update (test_mref.py:273-276, test_reffree.py:733).
+ * out4 = fl, aa, -sum of squares, iterations.                                                            */
+int  cra_fit_tanh(int n, const double* freq, const double* target, double fl0, double aa0,
+                  double scale_fl, double scale_aa, double* out4);
+
 /* rot_shift2D(img, alpha, sx, sy, mirror) + add into class sums
  * sums[iref][global_index % 2] and counts[iref] (test_mref.py:210-215).
  * params: host [n][4] float (alpha, sx, sy, mirror); iref: host int[n]; iref<0

@@ -149,3 +149,39 @@ def test_reference_update_matches_oracle(oracle):
     f = ru.fsc(sums[0, 0], sums[0, 1]); g = oracle.fsc(sums[0, 0], sums[0, 1])
     assert f[0] == g[0] and f[2] == g[2] and np.allclose(f[1], g[1], atol=1e-7)
     assert ru.fit_tanh(copy.deepcopy(f)) == pytest.approx(oracle.fit_tanh(copy.deepcopy(g)), rel=1e-9)
+
+
+def test_native_fit_tanh_follows_the_python_simplex():
+    """cra_fit_tanh (csrc/cra_host.cu) against refupdate.fit_tanh's interpreted amoeba (sp_filter.fit_tanh ->
+    sp_utilities.amoeba) on random FSC curves, and the oracle's own restatement on one of them."""
+    from cryo_ralib_b200 import refupdate as ru
+    from oracle import oracle as o
+    rng = np.random.default_rng(3)
+    freq = np.arange(46) / 90.0
+    for trial in range(40):
+        fc = rng.uniform(0.08, 0.35); w = rng.uniform(0.02, 0.15)
+        val = np.clip(1 / (1 + np.exp((freq - fc) / w * 4)) + rng.normal(0, 0.03, 46), -0.2, 0.999)
+        fr = [list(freq), list(val), [1] * 46]
+        a = ru.fit_tanh(fr, native=True); b = ru.fit_tanh(fr, native=False)
+        assert abs(a[0] - b[0]) <= 1e-9 and abs(a[1] - b[1]) <= 1e-9, (trial, a, b)
+    c = o.fit_tanh(fr)
+    assert abs(a[0] - c[0]) <= 1e-6 and abs(a[1] - c[1]) <= 1e-6
+
+
+def test_update_refs_fits_the_shared_fsc_once(monkeypatch):
+    """Every class gets the same class-averaged FSC (test_mref.py:258-276): one fit per update, same references."""
+    from cryo_ralib_b200 import refupdate as ru, synth
+    images, _ = synth.make_particles(60, 64, 8, seed=4)
+    R = 5
+    sums = np.zeros((R, 2, 64, 64), np.float32); counts = np.zeros(R, np.float32)
+    for i in range(60):
+        sums[i % R, i % 2] += images[i]; counts[i % R] += 1
+    mask = ru.model_circle(28, 64)
+    calls = []
+    real = ru.fit_tanh
+    monkeypatch.setattr(ru, "fit_tanh", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    refs, info = ru.update_refs(sums, counts, mask, center=1)
+    assert len(calls) == 1
+    per_class = np.stack([ru.normalize_mask(ru.ref_ali2d((sums[j, 0] + sums[j, 1]) * np.float32(1.0 / counts[j]), info["frsc"], 1)[0], mask, 1)
+                          for j in range(R)])
+    assert np.array_equal(per_class, refs)
