@@ -140,10 +140,20 @@ def mref_search_request(params, nx, ou, xr, yr, native=True):
     return s, sxi, syi, params
 
 
-def reffree_search_request(params, cs, nx, ou, xr, yr):
+def reffree_search_request(params, cs, nx, ou, xr, yr, native=True):
     """ali2d_single_iter's per-particle prologue (test_reffree.py:780-783 -> Sphire):
     fold the average's centre shift cs into the parameters, invert, clamp to +-mashi."""
-    params = np.array(params, np.float64)
+    params = np.array(params, np.float64, order="C").reshape(-1, 4)
+    L = _native() if native else None
+    if L is not None:
+        n = params.shape[0]
+        s = np.zeros(n, SEARCH_DTYPE)
+        sxi = np.zeros(n, np.float64)
+        syi = np.zeros(n, np.float64)
+        if L.cra_reffree_search_request(n, params.ctypes.data, float(cs[0]), float(cs[1]), int(nx), int(ou), float(xr),
+                                        float(yr), s.ctypes.data, sxi.ctypes.data, syi.ctypes.data) != 0:
+            raise RuntimeError(L.cra_last_error().decode())
+        return s, sxi, syi
     cnx = nx // 2 + 1
     mashi = cnx - ou - 2
     a, sx, sy, _ = combine_params2(params[:, 0], params[:, 1], params[:, 2], params[:, 3].astype(int),

@@ -94,6 +94,30 @@ extern "C" int cra_mref_search_request(int n, double* params, int nx, int ou, do
     return 0;
 }
 
+// ali2d_single_iter's prologue for n particles (test_reffree.py:780-783 -> Sphire): fold the average's centre
+// shift cs into the parameters (combine_params2(p, 0, -cs)), invert, clamp the shift to +-mashi.
+extern "C" int cra_reffree_search_request(int n, const double* params, double csx, double csy, int nx, int ou,
+                                          double xr, double yr, CraSearch* search, double* sxi_out, double* syi_out)
+{
+    if (n < 0 || !params || !search || !sxi_out || !syi_out) { cra_set_error("null argument"); return 1; }
+    const int cnx = nx / 2 + 1, mashi = cnx - ou - 2;
+    const M23 t2 = make_t(0.0, -csx, -csy, 0);
+#pragma omp parallel for schedule(static) if (n > 4096)
+    for (int i = 0; i < n; ++i) {
+        double a, sx, sy, a2, sxi, syi; int mir, mir2;
+        params_t(mul_t(t2, make_t(params[4 * i], params[4 * i + 1], params[4 * i + 2], (int)params[4 * i + 3])), &a, &sx, &sy, &mir);
+        params_t(invert_t(make_t(a, sx, sy, 0)), &a2, &sxi, &syi, &mir2);
+        if (sxi < -mashi) sxi = -mashi; if (sxi > mashi) sxi = mashi;
+        if (syi < -mashi) syi = -mashi; if (syi > mashi) syi = mashi;
+        CraSearch s;
+        search_range(nx, ou, sxi, xr, &s.xl, &s.xr);
+        search_range(nx, ou, syi, yr, &s.yl, &s.yr);
+        s.cx = (float)(cnx + sxi); s.cy = (float)(cnx + syi);
+        search[i] = s; sxi_out[i] = sxi; syi_out[i] = syi;
+    }
+    return 0;
+}
+
 // test_mref.py:206: combine_params2(0, -sxi, -syi, 0, ang, sxs, sys, mirror) -> params_out [n][4] double
 extern "C" int cra_compose_result(int n, const double* sxi, const double* syi, const CraResult* res, double* params_out)
 {

@@ -58,7 +58,7 @@ RESULT_DTYPE = np.dtype([("ang", "f4"), ("sxs", "f4"), ("sys", "f4"), ("mirror",
 
 CORE_SYMBOLS = ["cra_create", "cra_destroy", "cra_last_error", "cra_ring_info", "cra_upload_particles",
                 "cra_upload_particles_dev", "cra_upload_particles_async", "cra_upload_wait", "cra_mref_search_request",
-                "cra_compose_result", "cra_fit_tanh", "cra_set_refs", "cra_align", "cra_align_bound", "cra_refs_from_sums", "cra_filter_refs",
+                "cra_compose_result", "cra_reffree_search_request", "cra_fit_tanh", "cra_set_refs", "cra_align", "cra_align_bound", "cra_refs_from_sums", "cra_filter_refs",
                 "cra_get_refs", "cra_accumulate", "cra_zero_sums",
                 "cra_sums_device_ptr", "cra_get_sums", "cra_transform", "cra_transform_dev", "cra_polar_spectrum", "cra_ref_spectrum", "cra_batch_row_spectrum",
                 "cra_ccf_curves", "cra_last_align_stats", "cra_set_timing", "cra_set_normalize_ring", "cra_set_step",
@@ -92,6 +92,8 @@ def load_library(path=None):
     L.cra_upload_wait.argtypes = [vp]
     L.cra_mref_search_request.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_double, C.c_double, vp, vp, vp]
     L.cra_compose_result.argtypes = [C.c_int, vp, vp, vp, vp]
+    L.cra_reffree_search_request.argtypes = [C.c_int, vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double,
+                                             vp, vp, vp]
     L.cra_fit_tanh.argtypes = [C.c_int, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, vp]
     L.cra_set_refs.argtypes = [vp, vp, C.c_int, C.c_int]
     L.cra_align.argtypes = [vp, C.c_int, C.c_int, vp, vp]

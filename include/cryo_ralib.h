@@ -121,6 +121,10 @@ int  cra_get_refs(CraCtx* ctx, float* host_refs);
 int  cra_mref_search_request(int n, double* params, int nx, int ou, double xr, double yr,
                              CraSearch* search, double* sxi_out, double* syi_out);
 int  cra_compose_result(int n, const double* sxi, const double* syi, const CraResult* res, double* params_out);
+/* The reference-free twin (ali2d_single_iter, test_reffree.py:780-783): combine_params2(params, 0, -cs_x, -cs_y, 0)
+ * -> inverse_transform2 -> shift clamped to +-mashi -> search_range x2.  params [n][4] is not modified.        */
+int  cra_reffree_search_request(int n, const double* params, double cs_x, double cs_y, int nx, int ou,
+                                double xr, double yr, CraSearch* search, double* sxi_out, double* syi_out);
 
 /* sp_filter.fit_tanh's optimisation (host arithmetic, no device work): Nelder-Mead fit (sp_utilities.amoeba, same
  * simplex, tolerances 1e-4, 500 iterations at most) of 0.5 (tanh(c (f + fl)) - tanh(c (f - fl))), c = pi / (2 aa fl), to

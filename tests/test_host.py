@@ -119,6 +119,14 @@ def test_native_bookkeeping_equals_numpy_restatement():
     d = al.compose_result(a[1], a[2], res, native=False)
     assert np.array_equal(c[:, 1:], d[:, 1:])
     assert np.abs(c[:, 0] - d[:, 0]).max() < 1e-12
+    # the reference-free prologue (centre shift folded in, shifts clamped instead of reset)
+    for cs in ((0.0, 0.0), (0.37, -1.21)):
+        e = al.reffree_search_request(params, cs, 90, 36, 3, 2, native=True)
+        f = al.reffree_search_request(params, cs, 90, 36, 3, 2, native=False)
+        for name in e[0].dtype.names:
+            assert np.array_equal(e[0][name], f[0][name]), (cs, name)
+        assert np.array_equal(e[1], f[1]) and np.array_equal(e[2], f[2])
+        assert np.abs(e[1]).max() <= 8 and np.abs(e[2]).max() <= 8          # mashi = 46 - 36 - 2
 
 
 def test_mpi_start_end_partitions():
