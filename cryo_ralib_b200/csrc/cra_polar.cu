@@ -409,14 +409,14 @@ polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __r
                 re[j] = v.x; im[j] = v.y;
             }
             uint4* o = reinterpret_cast<uint4*>(base + (size_t)r * nch * 128 + (size_t)gc * 128 + t * 32);
+            uint4 a, b;
             if (MODE == 1 || frag.unit_rows) {           // reference (B operand) layout: [re unit | im unit]
-                o[0] = split_bf16x4(re[0], re[1], re[2], re[3]);
-                o[1] = split_bf16x4(im[0], im[1], im[2], im[3]);
-            } else {                   // particle row (A operand) layout: hi words then lo words
-                uint4 hi, lo;
-                split_row_unit(re, im, hi, lo);
-                o[0] = hi; o[1] = lo;
-            }
+                a = split_bf16x4(re[0], re[1], re[2], re[3]);
+                b = split_bf16x4(im[0], im[1], im[2], im[3]);
+            } else split_row_unit(re, im, a, b);         // particle row (A operand) layout: hi words then lo words
+            // one 256-bit store per lane (the lanes of a warp write different lines: store count loads the LSU)
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                         :: "l"(o), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
         }
         if (MODE == 0 && norm != nullptr && tid < ck.nrow) norm[ck.row0 + tid] = make_float2(0.f, 1.f);   // normalised above
         if (MODE == 1 && tref != nullptr && tid < 32) {

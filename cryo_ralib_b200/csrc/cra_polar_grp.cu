@@ -68,14 +68,15 @@ __device__ __forceinline__ uint4 split_bf16x4(float v0, float v1, float v2, floa
 // one 32-byte quad of a particle row in the active row layout (cra_common.cuh)
 __device__ __forceinline__ void store_row_quad(uint4* o4, const float (&re)[4], const float (&im)[4], int unit_rows)
 {
+    uint4 a, b;
     if (unit_rows) {
-        o4[0] = split_bf16x4(re[0], re[1], re[2], re[3]);
-        o4[1] = split_bf16x4(im[0], im[1], im[2], im[3]);
-    } else {
-        uint4 hi, lo;
-        split_row_unit(re, im, hi, lo);
-        o4[0] = hi; o4[1] = lo;
-    }
+        a = split_bf16x4(re[0], re[1], re[2], re[3]);
+        b = split_bf16x4(im[0], im[1], im[2], im[3]);
+    } else split_row_unit(re, im, a, b);
+    // one 256-bit store per lane: the 32 lanes of a warp write 32 different lines (the units of a chunk belong to
+    // different phases), so the store count, not the byte count, is what loads the LSU
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "l"(o4), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
 }
 
 template <int NA, int NB>
