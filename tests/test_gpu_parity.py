@@ -591,3 +591,33 @@ def test_ref_free_alignment_2d_matches_oracle(oracle, small_set):
             ok += 1
     assert ok >= P - 3, ok
     L.gpu_clear()
+
+
+@pytest.mark.parametrize("R,xr,P", [(1, 0, 1), (3, 1, 5), (5, 0, 7), (9, 2, 3), (13, 1, 9), (50, 3, 2)])
+def test_ragged_reference_counts_and_tiny_batches(oracle, small_set, R, xr, P):
+    """Reference counts that leave partly filled 4-reference quads and 8-reference tiles, a single search position
+    (xr = 0), row blocks with fewer than 8 rows, one particle; and an empty range."""
+    from cryo_ralib_b200 import alignment as al, synth
+    images, refs10, _ = small_set
+    rng = np.random.default_rng(R)
+    refs = np.stack([refs10[i % 10] if i < 10 else np.roll(refs10[i % 10], (i // 10, -(i // 10)), (0, 1)) for i in range(R)]).astype(np.float32)
+    imgs, mask, numr, refs_n, cref = _prep(oracle, images[:P], refs, 36)
+    e = _engine(90, 36, max(xr, 1), P=max(P, 1), R=R)
+    e.upload_particles(images[:P], subtract_mask_mean=True)
+    e.set_refs(refs, normalize_mask=True)
+    search, sxi, syi, _ = al.mref_search_request(np.zeros((P, 4)), 90, 36, xr, xr)
+    assert e.align(0, 0, search[:0]).shape[0] == 0                       # empty range
+    got = e.align(0, P, search)
+    st = e.stats()
+    assert st["rows"] == P * (2 * xr + 1) ** 2 and st["alignments"] == st["rows"] * R
+    e.close()
+    want = oracle.align_batch(imgs, cref, numr, np.stack([search["cx"], search["cy"]], 1),
+                              np.stack([search["xl"], search["xr"], search["yl"], search["yr"]], 1), 1.0, True, nthreads=4)
+    for i in range(P):
+        rel = abs(got["peak"][i] - want[i][5]) / abs(want[i][5])
+        assert rel < PEAK_RTOL, (i, rel)
+        same = (got["iref"][i] == int(want[i][4]) and got["mirror"][i] == int(want[i][3])
+                and got["sx"][i] == want[i][6] and got["sy"][i] == want[i][7])
+        assert same or rel < TIE_BAND, (i, got[i], want[i])
+        if same:
+            assert abs((got["ang"][i] - want[i][0] + 180) % 360 - 180) <= 0.5 * 360 / 256
