@@ -601,7 +601,8 @@ static int align_impl(CraCtx* c, int start, int stop, const CraSearch* search, c
     long total_rows = 0;
     // the grouped row kernel needs a whole-pixel step and every sample in [1, nx + 1) (its tile has a
     // one-pixel periodic border; search_range keeps samples in [2, nx])
-    const bool group_cfg = c->fmt == CRA_FMT_FRAG && c->use_group && c->plan.rmax > 0 && step == floorf(step) && step < 1024.f;
+    const int sub = cra_group_sub(step);                       // phase classes per axis (0: the general kernel)
+    const bool group_cfg = c->fmt == CRA_FMT_FRAG && c->use_group && c->plan.rmax > 0 && sub > 0;
     const float rmaxf = (float)c->htab.rad[c->htab.nring - 1], lo_ok = 1.0f + rmaxf, hi_ok = (float)c->nx + 0.5f - rmaxf;
     for (size_t bi = 0; bi < nb; ++bi) {
         int* rs = h_rs + bfirst[bi] + bi;
@@ -621,7 +622,14 @@ static int align_impl(CraCtx* c, int start, int stop, const CraSearch* search, c
             window_of(search[p], step, &h_win[p]);
             rs[q] = acc; cs[q] = cacc;
             const int rows = (h_win[p].x + h_win[p].y + 1) * (h_win[p].z + h_win[p].w + 1);
-            if (grp) cacc += (rows + c->plan.rmax - 1) / c->plan.rmax;   // balanced row blocks of <= rmax rows
+            if (grp) {                                                    // balanced row blocks of <= rmax rows per phase class
+                const int wx = h_win[p].x + h_win[p].y + 1, wy = h_win[p].z + h_win[p].w + 1;
+                for (int cy = 0; cy < sub; ++cy)
+                    for (int cx = 0; cx < sub; ++cx) {
+                        const int rc = ((wx - cx + sub - 1) / sub) * ((wy - cy + sub - 1) / sub);
+                        cacc += (rc + c->plan.rmax - 1) / c->plan.rmax;
+                    }
+            }
             else cacc += (acc + rows - 1) / rpb - acc / rpb + 1;          // aligned sub-groups this particle touches
             acc += rows;
         }

@@ -22,6 +22,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <math.h>
 #include <string>
 #include <vector>
 #include "../../include/cryo_ralib.h"
@@ -76,6 +77,16 @@ struct CraGroupPlan {
     int rmax;                  // rows per CTA (<= CRA_GRP_RMAX), chosen for shared-memory fit
     int nring;
 };
+
+// Phase classes per axis of the grouped row kernel: 1 for a whole-pixel step, 2 or 4 for a step of 1/2 or 1/4
+// pixel, 0 when the step has no such structure (the general per-row kernel serves it).
+__host__ __device__ __forceinline__ int cra_group_sub(float step)
+{
+    if (step >= 1.0f) return (step == floorf(step) && step < 1024.f) ? 1 : 0;
+    if (step == 0.5f) return 2;
+    if (step == 0.25f) return 4;
+    return 0;
+}
 
 struct CraRowMap {             // how rows of the current batch map to particles
     const int*       row_start;  // [np+1] first row of each batch-local particle

@@ -127,6 +127,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
     int* s_unk = s_koff + (maxrin / 2 + 2);                   // units : longest half length of unit u
     __shared__ float s_red[kThreads / 32][2 * RMAX];
     __shared__ int s_rowoff[RMAX];
+    __shared__ int s_grow[RMAX];                               // row of the batch (spectrum / norm index) of block row r
     __shared__ unsigned s_samemask;                            // bit r: row r sits one pixel right of row r-1
     __shared__ float2 s_rowc[RMAX];
     __shared__ float s_fix[2 * RMAX];
@@ -140,26 +141,39 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
         const int b = blockIdx.x;
         int lo = 0, hi = map.np;               // last p with chunk_start[p] <= b
         while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (map.chunk_start[mid] <= b) lo = mid; else hi = mid; }
-        const int rows = map.row_start[lo + 1] - map.row_start[lo];
-        const int nblk = map.chunk_start[lo + 1] - map.chunk_start[lo];
         const int bi = b - map.chunk_start[lo];
-        const int r_lo = (int)(((long)bi * rows) / nblk), r_hi = (int)(((long)(bi + 1) * rows) / nblk);
-        s_blk[0] = lo; s_blk[1] = r_lo; s_blk[2] = r_hi - r_lo; s_blk[3] = map.row_start[lo] + r_lo;
         const int4 w = map.win[lo];
-        const int wx = w.x + w.y + 1;
-        const int istep = (int)map.step;
-        s_base[0] = map.search[lo].cx - (float)w.x * map.step;
-        s_base[1] = map.search[lo].cy - (float)w.z * map.step;
-        unsigned same = 0;
-        for (int r = 1; r < r_hi - r_lo; ++r)
-            if (istep == 1 && (r_lo + r) % wx != 0) same |= 1u << r;
-        s_samemask = same;
-        for (int r = 0; r < r_hi - r_lo; ++r) {
-            const int li = r_lo + r;
-            s_rowoff[r] = (li / wx) * istep * pitch + (li % wx) * istep;
-            s_rowc[r] = make_float2(map.search[lo].cx + (float)(li % wx - w.x) * map.step,
-                                    map.search[lo].cy + (float)(li / wx - w.z) * map.step);
+        const int wx = w.x + w.y + 1, wy = w.z + w.w + 1;
+        // A step of 1/sub pixel (sub = 2, 4) splits the window into sub x sub phase classes: the positions
+        // (cx + sub i, cy + sub j) of a class lie one whole pixel apart and share their tap weights.  Blocks
+        // never cross a class; with a whole-pixel step there is one class and the rows are consecutive.
+        const int sub = cra_group_sub(map.step);
+        const int pxs = (sub > 1) ? 1 : (int)map.step;         // pixels between neighbouring rows of a class
+        int cx = 0, cy = 0, ncx = wx, rows_c = wx * wy, nblk_c = 1, left = bi;
+        for (int c = 0; c < sub * sub; ++c) {
+            cy = c / sub; cx = c - cy * sub;
+            ncx = (wx - cx + sub - 1) / sub;
+            const int ncy = (wy - cy + sub - 1) / sub;
+            rows_c = ncx * ncy;
+            nblk_c = (rows_c + plan.rmax - 1) / plan.rmax;
+            if (left < nblk_c) break;
+            left -= nblk_c;
         }
+        const int r_lo = (int)(((long)left * rows_c) / nblk_c), r_hi = (int)(((long)(left + 1) * rows_c) / nblk_c);
+        s_blk[0] = lo; s_blk[1] = r_lo; s_blk[2] = r_hi - r_lo; s_blk[3] = (sub == 1) ? 1 : 0;
+        s_base[0] = map.search[lo].cx + (float)(cx - w.x) * map.step;
+        s_base[1] = map.search[lo].cy + (float)(cy - w.z) * map.step;
+        unsigned same = 0;
+        for (int r = 0; r < r_hi - r_lo; ++r) {
+            const int t = r_lo + r, ty = t / ncx, tx = t - ty * ncx;
+            const int lix = cx + tx * sub, liy = cy + ty * sub;
+            if (r > 0 && pxs == 1 && tx != 0) same |= 1u << r;
+            s_grow[r] = map.row_start[lo] + liy * wx + lix;
+            s_rowoff[r] = ty * pxs * pitch + tx * pxs;
+            s_rowc[r] = make_float2(map.search[lo].cx + (float)(lix - w.x) * map.step,
+                                    map.search[lo].cy + (float)(liy - w.z) * map.step);
+        }
+        s_samemask = same;
     }
     for (int i = tid; i < maxrin; i += kThreads) s_tw[i] = twid[i];
     if (tid < 2 * RMAX) s_fix[tid] = 0.f;
@@ -172,7 +186,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
     }
     __syncthreads();
     const int nr = s_blk[2];
-    const int grow0 = s_blk[3];                                // first row of this block in the batch
+    const bool contig = s_blk[3] != 0;                         // block rows are consecutive rows of the batch
     {
         // padded (Y, X), 0 <= X, Y <= nx+1, holds pixel ((Y-1) mod nx, (X-1) mod nx): 1-based pixel (i, j) sits at (j, i)
         const float* img = images + (size_t)(map.p0 + s_blk[0]) * npix;
@@ -418,7 +432,8 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                         }
                     }
                 }
-                unsigned char* o = spec + (size_t)(grow0 + set) * rb + (size_t)(s_koff[k] + (u >> 2)) * 128 + (u & 3) * 32;
+                unsigned char* const o0 = spec + (size_t)(s_koff[k] + (u >> 2)) * 128 + (u & 3) * 32;
+                unsigned char* o = o0 + (size_t)s_grow[set] * rb;
                 const float2* z = reinterpret_cast<const float2*>(s_buf + set * stride);
                 for (int r = set; r < nr; r += nset) {
                     float re[4], im[4];
@@ -429,7 +444,8 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                         im[j] = v.y * mi[j];
                     }
                     store_row_quad(reinterpret_cast<uint4*>(o), re, im, frag.unit_rows);
-                    o += (size_t)nset * rb;
+                    if (contig) o += (size_t)nset * rb;
+                    else if (r + nset < nr) o = o0 + (size_t)s_grow[r + nset] * rb;
                     z += nset * (stride >> 1);
                 }
             }
@@ -445,7 +461,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                     re[j] = 0.f; im[j] = 0.f;
                     if (ring >= 0) { const int4 rp = s_ring[ring]; if (rp.z * 2 == k) re[j] = z[rp.x].y; }
                 }
-                store_row_quad(reinterpret_cast<uint4*>(spec + (size_t)(grow0 + r) * rb + (size_t)(s_koff[k] + (u >> 2)) * 128 + (u & 3) * 32),
+                store_row_quad(reinterpret_cast<uint4*>(spec + (size_t)s_grow[r] * rb + (size_t)(s_koff[k] + (u >> 2)) * 128 + (u & 3) * 32),
                                re, im, frag.unit_rows);
             }
         }
@@ -471,7 +487,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
             avg = a / nn;
             isg = 1.0f / sqrtf((s - a * a / nn) / nn);
         }
-        norm[grow0 + tid] = make_float2(avg, isg);
+        norm[s_grow[tid]] = make_float2(avg, isg);
     }
 }
 

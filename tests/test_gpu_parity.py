@@ -49,9 +49,11 @@ def test_polar_spectrum_matches_oracle(oracle, small_set):
         e.close()
 
 
-def test_grouped_row_kernel_spectra_match_oracle(oracle, small_set):
+@pytest.mark.parametrize("ts", [1.0, 0.5, 0.25, 2.0])
+def test_grouped_row_kernel_spectra_match_oracle(oracle, small_set, ts):
     """Every shift row the production (grouped, weight-sharing) row kernel writes, against the oracle's
-    Polar2Dm + Normalize_ring + Frngs at that centre; ragged windows and off-grid centres included."""
+    Polar2Dm + Normalize_ring + Frngs at that centre; ragged windows and off-grid centres included.  Steps of
+    1/2 and 1/4 pixel run as 4 / 16 phase classes whose rows interleave in the batch; step 2 as one class."""
     import os
     from cryo_ralib_b200.lib import SEARCH_DTYPE
     if os.environ.get("CRA_CCF") == "simt" or os.environ.get("CRA_POLAR") == "general":
@@ -60,23 +62,26 @@ def test_grouped_row_kernel_spectra_match_oracle(oracle, small_set):
     imgs, mask, numr, _, _ = _prep(oracle, images, refs, 36)
     P = 6
     for normalize in (True, False):
-        e = _engine(90, 36, 3, P=P, R=4, normalize=normalize)
+        xr = 3.0 if ts <= 1 else 4.0
+        e = _engine(90, 36, xr if ts >= 0.5 else 1.5, ts=ts, P=P, R=4, normalize=normalize)
         e.upload_particles(images[:P], subtract_mask_mean=True)
         e.set_refs(refs[:4], normalize_mask=True)
         search = np.zeros(P, SEARCH_DTYPE)
         search["cx"] = [46, 46.37, 44.2, 48.75, 46, 43.5]
         search["cy"] = [46, 44.81, 47.9, 45.25, 46, 48.5]
-        search["xl"] = [3, 3, 2, 3, 0, 1]; search["xr"] = [3, 3, 3, 1, 0, 3]
-        search["yl"] = [3, 3, 3, 2, 0, 3]; search["yr"] = [3, 2, 3, 3, 0, 0]
+        # window limits in pixels; the engine turns them into int(limit / step) positions per side
+        lim = 1.0 if ts >= 0.5 else 0.5
+        search["xl"] = np.array([3, 3, 2, 3, 0, 1]) * lim; search["xr"] = np.array([3, 3, 3, 1, 0, 3]) * lim
+        search["yl"] = np.array([3, 3, 3, 2, 0, 3]) * lim; search["yr"] = np.array([3, 2, 3, 3, 0, 0]) * lim
         e.align(0, P, search)
         row = 0
         for p in range(P):
             s = search[p]
-            for iy in range(-int(s["yl"]), int(s["yr"]) + 1):
-                for ix in range(-int(s["xl"]), int(s["xr"]) + 1):
+            for iy in range(-int(s["yl"] / ts), int(s["yr"] / ts) + 1):
+                for ix in range(-int(s["xl"] / ts), int(s["xr"] / ts) + 1):
                     got, kern = e.batch_row_spectrum(row)
                     assert kern == 1, "the grouped row kernel should have handled this batch"
-                    c = oracle.polar2dm(imgs[p], float(s["cx"]) + ix, float(s["cy"]) + iy, numr)
+                    c = oracle.polar2dm(imgs[p], float(s["cx"]) + ix * ts, float(s["cy"]) + iy * ts, numr)
                     if normalize:
                         c = oracle.normalize_ring(c, numr)
                     want = oracle.frngs(c, numr)
