@@ -198,11 +198,9 @@ def model_circle(r, nx):
 
 
 def _native():
-    try:
-        from .lib import load_library
-        return load_library()
-    except Exception:
-        return None
+    """libcryo_ralib.so (cra_fit_tanh); a missing library raises LibraryMissing, there is no silent fallback."""
+    from .lib import load_library
+    return load_library()
 
 
 def ref_ali2d(avg, frsc, center, fit=None):
