@@ -219,20 +219,28 @@ def main():
     # row batches of the engine (no partial launches in between); the first one is small so the alignment starts early.
     S = (2 * int(xr / ts) + 1) * (2 * int(yr / ts) + 1)
     per_batch = max(1, eng.L.cra_row_batch(eng.h) // S)
-    bounds, s0, nb = [], 0, 1
+    # chunk sizes 1, 1, 2, 4, ... row batches: the host link (~22 GB/s measured here) delivers a chunk no bigger than
+    # everything before it while those are aligned (~8 GB/s of images), so only the first batch's upload is exposed
+    bounds, s0, nb, done = [], 0, 1, 0
     while s0 < P:
         e0 = min(P, s0 + nb * per_batch)
         bounds.append((s0, e0))
-        s0, nb = e0, min(32, nb * 2)          # doubling chunks: the upload (~55 GB/s) stays ahead of the alignment (~8 GB/s)
+        done += nb
+        s0, nb = e0, min(32, done)
+
+    trace = os.environ.get("CRA_BENCH_TRACE") and rank == 0
 
     def step(resident, params):
         """One iteration of the per-particle section; returns (new params, assign, stats)."""
+        tr = [("start", time.perf_counter())]
+        eng.set_refs(refs, normalize_mask=True)      # before the stack is queued: a copy from pageable memory waits behind it
         if not resident:
             base = host_images.data_ptr()
             for s, e in bounds:
                 eng.upload_particles_async(base + s * nx * nx * 4, e - s, first=s, subtract_mask_mean=True)
-        eng.set_refs(refs, normalize_mask=True)
+            tr.append(("queued", time.perf_counter()))
         search, sxi, syi, params = al.mref_search_request(params, nx, ou, xr, yr)
+        tr.append(("refs+request", time.perf_counter()))
         if resident:
             res = eng.align(0, P, search)
             st = eng.stats()
@@ -241,8 +249,10 @@ def main():
             for s, e in bounds:
                 parts.append(eng.align(s, e, search[s:e]))
                 t = eng.stats()
+                tr.append(("align %d (kernels %.1f ms)" % (e - s, t["ms_total"]), time.perf_counter()))
                 st = t if st is None else {k: st[k] + t[k] for k in st}
             res = np.concatenate(parts)
+        tr.append(("align", time.perf_counter()))
         newp = al.compose_result(sxi, syi, res)
         eng.zero_sums()
         eng.accumulate(0, P, newp, res["iref"], goff)
@@ -250,6 +260,10 @@ def main():
             comm.allreduce_device(eng)
         if not resident:
             eng.get_sums()
+        tr.append(("sums", time.perf_counter()))
+        if trace:
+            sys.stderr.write("trace %s: " % ("resident" if resident else "e2e") +
+                             ", ".join("%s +%.1f" % (n, 1e3 * (t - tr[i][1])) for i, (n, t) in enumerate(tr[1:])) + "\n")
         return newp, res, st
 
     def timed(resident, nsteps, params):

@@ -20,7 +20,7 @@ struct CraCtx {
     int device = 0;
     cudaStream_t st = nullptr;
     cudaStream_t st_copy = nullptr;                            // asynchronous particle uploads
-    struct Pending { int first, n; cudaEvent_t ev; };
+    struct Pending { int first, n, sub; cudaEvent_t ev; };       // sub: mask mean still to be subtracted (on the main stream)
     std::vector<Pending> pending;                              // uploads not yet ordered before the main stream
     std::vector<cudaEvent_t> ev_pool;
     int nx = 0, npix = 0, R = 0;
@@ -282,6 +282,13 @@ int build_tables(CraCtx* c)
     return build_group_plan(c);
 }
 
+// dst (device) <- src (pinned host memory, read over the bus by the SMs), n 16-byte words
+__global__ void pull_host_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
 int window_of(const CraSearch& s, float step, int4* w)
 {
     w->x = (int)(s.xl / step); w->y = (int)(s.xr / step);
@@ -297,6 +304,9 @@ int wait_uploads(CraCtx* c, int first, int n)
         CraCtx::Pending& p = c->pending[i];
         if (p.first < first + n && first < p.first + p.n) {
             CRA_CUDA(cudaStreamWaitEvent(c->st, p.ev, 0));
+            // normalize.mask of the whole uploaded range, once, in order with its first consumer.  On the copy stream
+            // the kernel would wait for an SM slot behind the persistent CCF grid and hold back the next copy.
+            if (p.sub && cra_launch_mask_normalize(c->d_images + (size_t)p.first * c->npix, p.n, c->nx, c->d_mask, 0, c->st)) return 1;
             c->ev_pool.push_back(p.ev);
             c->pending.erase(c->pending.begin() + i);
         } else ++i;
@@ -490,9 +500,10 @@ extern "C" int cra_upload_particles_async(CraCtx* c, const float* h, int first, 
     CRA_CUDA(cudaStreamWaitEvent(c->st_copy, e0, 0));
     float* dst = c->d_images + (size_t)first * c->npix;
     CRA_CUDA(cudaMemcpyAsync(dst, h, (size_t)n * c->npix * sizeof(float), cudaMemcpyHostToDevice, c->st_copy));
-    if (sub && cra_launch_mask_normalize(dst, n, c->nx, c->d_mask, 0, c->st_copy)) return 1;
     CRA_CUDA(cudaEventRecord(e0, c->st_copy));
-    c->pending.push_back({first, n, e0});
+    // an older pending upload that this one overwrites completely no longer needs its mask subtraction
+    for (auto& p : c->pending) if (p.first >= first && p.first + p.n <= first + n) p.sub = 0;
+    c->pending.push_back({first, n, sub ? 1 : 0, e0});
     return 0;
 }
 
@@ -500,6 +511,8 @@ extern "C" int cra_upload_wait(CraCtx* c)
 {
     Bind b(c); if (b.ok()) return 1;
     if (c->st_copy) CRA_CUDA(cudaStreamSynchronize(c->st_copy));
+    if (wait_uploads(c, 0, c->cfg.max_particles)) return 1;         // pending mask subtractions
+    CRA_CUDA(cudaStreamSynchronize(c->st));
     return 0;
 }
 extern "C" int cra_upload_particles_dev(CraCtx* c, const float* d, int first, int n, int sub)
@@ -638,7 +651,12 @@ static int align_impl(CraCtx* c, int start, int stop, const CraSearch* search, c
         total_rows += acc;
     }
     const size_t used = (size_t)n * (sizeof(CraSearch) + sizeof(int4)) + 2 * (n + nb) * sizeof(int);
-    CRA_CUDA(cudaMemcpyAsync(c->d_meta, c->h_meta, used, cudaMemcpyHostToDevice, c->st));
+    // The request tables go to the device through a kernel that reads the pinned host buffer directly, not
+    // through the copy engine: a cudaMemcpyAsync would queue behind every particle upload already submitted
+    // (cra_upload_particles_async) and hold the first alignment back by the whole stack's transfer time.
+    pull_host_kernel<<<(unsigned)((used / 16 + 1 + 255) / 256), 256, 0, c->st>>>(
+        reinterpret_cast<uint4*>(c->d_meta), reinterpret_cast<const uint4*>(c->h_meta), used / 16 + 1);
+    CRA_CUDA(cudaGetLastError());
     const int4* d_win = reinterpret_cast<const int4*>(c->d_meta);
     const CraSearch* d_search = reinterpret_cast<const CraSearch*>(c->d_meta + (size_t)n * sizeof(int4));
     const int* d_rs = reinterpret_cast<const int*>(c->d_meta + (size_t)n * (sizeof(CraSearch) + sizeof(int4)));
