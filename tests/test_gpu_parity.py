@@ -626,3 +626,36 @@ def test_ragged_reference_counts_and_tiny_batches(oracle, small_set, R, xr, P):
         assert same or rel < TIE_BAND, (i, got[i], want[i])
         if same:
             assert abs((got["ang"][i] - want[i][0] + 180) % 360 - 180) <= 0.5 * 360 / 256
+
+
+def test_streaming_upload_equals_synchronous_upload(small_set):
+    """cra_upload_particles_async in chunks, consumed by alignment calls whose ranges cut across the chunks, a chunk
+    re-uploaded before anyone read it, cra_upload_wait: bit-identical to the synchronous upload (the mask-mean
+    subtraction is deferred to the first consumer and must happen exactly once per uploaded range)."""
+    import torch
+    from cryo_ralib_b200 import alignment as al
+    images, refs, _ = small_set
+    P, R = 64, 10
+    search, sxi, syi, _ = al.mref_search_request(np.zeros((P, 4)), 90, 36, 2, 2)
+    e1 = _engine(90, 36, 2, P=P, R=R)
+    e1.upload_particles(images, subtract_mask_mean=True)
+    e1.set_refs(refs)
+    want = e1.align(0, P, search)
+    want_spec = e1.polar_spectrum(50, 46.3, 45.1)
+    e1.close()
+    host = torch.from_numpy(images.copy()).pin_memory()
+    junk = torch.zeros_like(host[:25]).pin_memory()
+    e2 = _engine(90, 36, 2, P=P, R=R)
+    e2.set_refs(refs)
+    base, sz = host.data_ptr(), 90 * 90 * 4
+    e2.upload_particles_async(junk.data_ptr(), 25, first=20, subtract_mask_mean=True)      # overwritten below, never read
+    for s, t in ((0, 20), (20, 45), (45, 64)):
+        e2.upload_particles_async(base + s * sz, t - s, first=s, subtract_mask_mean=True)
+    got = np.concatenate([e2.align(0, 30, search[:30]), e2.align(30, 64, search[30:])])
+    assert got.tobytes() == want.tobytes()
+    again = e2.align(0, P, search)                      # nothing pending any more: no second subtraction
+    assert again.tobytes() == want.tobytes()
+    e2.upload_particles_async(base + 45 * sz, 19, first=45, subtract_mask_mean=True)
+    e2.upload_wait()
+    assert np.array_equal(e2.polar_spectrum(50, 46.3, 45.1), want_spec)
+    e2.close()
