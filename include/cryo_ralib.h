@@ -78,11 +78,13 @@ int  cra_upload_particles(CraCtx* ctx, const float* host_images, int first, int 
 /* Same, source already on this device. */
 int  cra_upload_particles_dev(CraCtx* ctx, const float* dev_images, int first, int n, int subtract_mask_mean);
 
-/* Asynchronous variant: the copy (and the mask-mean subtraction) is queued on the context's copy
- * stream and returns at once; cra_align / cra_accumulate / cra_transform on a particle range wait,
- * on the device, only for the uploads that overlap it, so the upload of the next chunk runs under
- * the alignment of the current one.  host_images must be pinned and stay valid until
- * cra_upload_wait (or a later call that consumed the range) returns.                            */
+/* Asynchronous variant: the copy is queued on the context's copy stream and returns at once;
+ * cra_align / cra_accumulate / cra_transform on a particle range wait, on the device, only for the
+ * uploads that overlap it, so the upload of the next chunk runs under the alignment of the current
+ * one.  The mask-mean subtraction of an uploaded range runs on the main stream in front of its first
+ * consumer (or in cra_upload_wait), once for the whole range: a borrowed cra_device_images_ptr shows
+ * the raw pixels until then.  host_images must be pinned and stay valid until cra_upload_wait (or a
+ * later call that consumed the range) returns.                                                   */
 int  cra_upload_particles_async(CraCtx* ctx, const float* host_images, int first, int n, int subtract_mask_mean);
 int  cra_upload_wait(CraCtx* ctx);
 
