@@ -57,3 +57,14 @@ def write_params(path, params, assign=None, first_index=0):
         for i, p in enumerate(params):
             cls = int(assign[i]) if assign is not None else 0
             f.write("%d %.6f %.6f %.6f %d %d\n" % (first_index + i, p[0], p[1], p[2], int(p[3]), cls))
+
+
+def read_params(path):
+    """Rows 'idx angle sx sy mirror class' (write_params; src/utils_ralib.py:31-32) or the 4-column
+    'angle sx sy mirror' rows of initial2Dparams.txt -> (params [n][4] float64, classes [n] int or None)."""
+    rows = np.loadtxt(path, ndmin=2)
+    if rows.shape[1] >= 6:
+        return rows[:, 1:5].astype(np.float64), rows[:, 5].astype(np.int64)
+    if rows.shape[1] == 4:
+        return rows.astype(np.float64), None
+    raise ValueError("parameter file must have 4 or 6 columns, got %d" % rows.shape[1])

@@ -193,3 +193,21 @@ def test_update_refs_fits_the_shared_fsc_once(monkeypatch):
     per_class = np.stack([ru.normalize_mask(ru.ref_ali2d((sums[j, 0] + sums[j, 1]) * np.float32(1.0 / counts[j]), info["frsc"], 1)[0], mask, 1)
                           for j in range(R)])
     assert np.array_equal(per_class, refs)
+
+
+def test_params_files_round_trip(tmp_path):
+    """params.txt ('idx angle sx sy mirror class', src/utils_ralib.py:31-32) and initial2Dparams.txt rows."""
+    from cryo_ralib_b200 import stackio
+    rng = np.random.default_rng(2)
+    p = np.stack([rng.uniform(0, 360, 9), rng.uniform(-4, 4, 9), rng.uniform(-4, 4, 9), rng.integers(0, 2, 9)], 1)
+    c = rng.integers(0, 5, 9)
+    f = str(tmp_path / "params.txt")
+    stackio.write_params(f, p, c, first_index=3)
+    q, d = stackio.read_params(f)
+    assert np.allclose(q, p, atol=1e-6) and np.array_equal(d, c)
+    g = str(tmp_path / "initial2Dparams.txt")
+    with open(g, "w") as fh:
+        for r in p:
+            fh.write("%14.6f %14.6f %14.6f %d\n" % (r[0], r[1], r[2], int(r[3])))
+    q, d = stackio.read_params(g)
+    assert np.allclose(q, p, atol=1e-6) and d is None
