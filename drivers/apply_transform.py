@@ -35,7 +35,7 @@ def main(argv=None):
         raise SystemExit("parameter file has %d rows for %d particles" % (params.shape[0], P))
     ou = args.ou if args.ou != -1 else nx // 2 - 2
     R = int(cls.max()) + 1 if (cls is not None and args.averages) else 1
-    e = Engine(nx, ou, 0, max_particles=P, max_refs=R, device=args.gpu)
+    e = Engine(nx, ou, 1, max_particles=P, max_refs=R, device=args.gpu)      # no alignment here: the search range is unused
     e.upload_particles(images, subtract_mask_mean=not args.no_mask_mean)
     out = e.transform(0, P, params)
     stackio.write_stack(args.out_stack, out)
