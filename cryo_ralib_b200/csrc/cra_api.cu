@@ -10,17 +10,34 @@
 #include <stdlib.h>
 #include <algorithm>
 #include <mutex>
+#include <map>
+#include <utility>
 
 static thread_local std::string g_err;
 void cra_set_error(const std::string& msg) { g_err = msg; }
 extern "C" const char* cra_last_error(void) { return g_err.c_str(); }
+
+int cra_ensure_dyn_smem(const void* func, size_t bytes)
+{
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> done;
+    int dev = 0;
+    CRA_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& cur = done[std::make_pair(dev, func)];
+    if (bytes > cur) {
+        CRA_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        cur = bytes;
+    }
+    return 0;
+}
 
 struct CraCtx {
     CraConfig cfg{};
     int device = 0;
     cudaStream_t st = nullptr;
     cudaStream_t st_copy = nullptr;                            // asynchronous particle uploads
-    struct Pending { int first, n, sub; cudaEvent_t ev; };       // sub: mask mean still to be subtracted (on the main stream)
+    struct Pending { int first, n, sub; cudaEvent_t ev; };       // sub: 1 mask mean still to be subtracted, 0 to be measured (on the main stream), -1 superseded
     std::vector<Pending> pending;                              // uploads not yet ordered before the main stream
     std::vector<cudaEvent_t> ev_pool;
     int nx = 0, npix = 0, R = 0;
@@ -35,8 +52,10 @@ struct CraCtx {
     CraRingTab* d_tab = nullptr;
     float4* d_samp = nullptr; float* d_sampw = nullptr;
     float2* d_twf = nullptr;  float2* d_twi = nullptr;
+    double2* d_twd = nullptr;    // (cos, sin)(2 pi j / maxrin) in double (finalize_kernel)
     int* d_items = nullptr; CraPolarItems items{};
     float* d_mask = nullptr;
+    float* d_dc = nullptr;       // [max_particles] in-mask mean a particle uploaded WITHOUT mean subtraction still carries
     float* d_images = nullptr; float* d_refs = nullptr; float* d_refspec = nullptr;
     float* d_spec = nullptr; CraCand* d_cand = nullptr;
     float* d_sums = nullptr;     // [R][2][npix] + [R]
@@ -53,6 +72,7 @@ struct CraCtx {
     // CRA_FMT_F32 = FP32 FMA kernel on the float2 spectrum (CRA_CCF=simt)
     int fmt = CRA_FMT_FRAG;
     bool use_tm = true;          // W staged in tensor memory (cra_ccf_tm.cu); CRA_CCF=mma keeps it in shared memory
+    void* tm_sched = nullptr;    // work lists of the tensor-memory CCF kernel (cra_ccf_tm.cu)
     bool use_um = false;         // contraction on tcgen05.mma (cra_ccf_um.cu); CRA_CCF=um, maxrin 256
     unsigned char* d_refimg = nullptr;   // UMMA reference operand images
     CraFragTab frag{};
@@ -277,6 +297,12 @@ int build_tables(CraCtx* c)
     CRA_CUDA(cudaMemcpy(c->d_twf, twf.data(), sizeof(float2) * twf.size(), cudaMemcpyHostToDevice));
     CRA_CUDA(cudaMalloc(&c->d_twi, sizeof(float2) * twi.size()));
     CRA_CUDA(cudaMemcpy(c->d_twi, twi.data(), sizeof(float2) * twi.size(), cudaMemcpyHostToDevice));
+    {
+        std::vector<double2> twd(t.maxrin);
+        for (int j = 0; j < t.maxrin; ++j) { const double a = 2.0 * M_PI * j / t.maxrin; twd[j] = make_double2(cos(a), sin(a)); }
+        CRA_CUDA(cudaMalloc(&c->d_twd, sizeof(double2) * twd.size()));
+        CRA_CUDA(cudaMemcpy(c->d_twd, twd.data(), sizeof(double2) * twd.size(), cudaMemcpyHostToDevice));
+    }
     CRA_CUDA(cudaMalloc(&c->d_mask, sizeof(float) * c->npix));
     CRA_CUDA(cudaMemcpy(c->d_mask, mask.data(), sizeof(float) * c->npix, cudaMemcpyHostToDevice));
     return build_group_plan(c);
@@ -306,7 +332,8 @@ int wait_uploads(CraCtx* c, int first, int n)
             CRA_CUDA(cudaStreamWaitEvent(c->st, p.ev, 0));
             // normalize.mask of the whole uploaded range, once, in order with its first consumer.  On the copy stream
             // the kernel would wait for an SM slot behind the persistent CCF grid and hold back the next copy.
-            if (p.sub && cra_launch_mask_normalize(c->d_images + (size_t)p.first * c->npix, p.n, c->nx, c->d_mask, 0, c->st)) return 1;
+            if (p.sub >= 0 && cra_launch_mask_normalize(c->d_images + (size_t)p.first * c->npix, p.n, c->nx, c->d_mask, p.sub ? 0 : 2,
+                                                        c->d_dc + p.first, c->st)) return 1;
             c->ev_pool.push_back(p.ev);
             c->pending.erase(c->pending.begin() + i);
         } else ++i;
@@ -416,6 +443,8 @@ extern "C" int cra_create(const CraConfig* cfg, int device, CraCtx** out)
     const size_t nsum = (size_t)cfg->max_refs * 2 * c->npix + cfg->max_refs;
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = cudaMalloc(&c->d_images, (size_t)cfg->max_particles * c->npix * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_dc, (size_t)cfg->max_particles * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(c->d_dc, 0, (size_t)cfg->max_particles * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_refs, (size_t)cfg->max_refs * c->npix * sizeof(float));
     const size_t ref_groups = ((size_t)cfg->max_refs + 3) / 4, row_groups = ((size_t)c->row_batch + 3) / 4;
     // one extra quad: a class-bound launch (cra_align_bound) bases the 4-reference operand loads at any reference
@@ -447,9 +476,10 @@ extern "C" int cra_destroy(CraCtx* c)
     for (auto& p : c->pending) cudaEventDestroy(p.ev);
     for (auto& e : c->ev_pool) cudaEventDestroy(e);
     if (c->st_copy) cudaStreamDestroy(c->st_copy);
+    cra_ccf_tm_sched_free(c->tm_sched); c->tm_sched = nullptr;
     cudaFree(c->d_items); cudaFree(c->d_fragtab); cudaFree(c->d_norm); cudaFree(c->d_tref); cudaFree(c->d_plan); cudaFree(c->d_refimg);
-    cudaFree(c->d_tab); cudaFree(c->d_samp); cudaFree(c->d_sampw); cudaFree(c->d_twf); cudaFree(c->d_twi);
-    cudaFree(c->d_mask); cudaFree(c->d_images); cudaFree(c->d_refs); cudaFree(c->d_refspec);
+    cudaFree(c->d_tab); cudaFree(c->d_samp); cudaFree(c->d_sampw); cudaFree(c->d_twf); cudaFree(c->d_twi); cudaFree(c->d_twd);
+    cudaFree(c->d_mask); cudaFree(c->d_dc); cudaFree(c->d_images); cudaFree(c->d_refs); cudaFree(c->d_refspec);
     cudaFree(c->d_spec); cudaFree(c->d_cand); cudaFree(c->d_sums); cudaFree(c->d_meta); cudaFree(c->d_res);
     cudaFree(c->d_par); cudaFree(c->d_iref); cudaFree(c->d_tmpimg); cudaFree(c->d_curves);
     if (c->h_meta) cudaFreeHost(c->h_meta);
@@ -474,13 +504,14 @@ extern "C" int cra_ring_info(CraCtx* c, int* nring, int* lcirc, int* maxrin, int
 
 static int upload_particles(CraCtx* c, const float* src, int first, int n, int sub, cudaMemcpyKind kind)
 {
+    CraNvtx range("cra_upload_particles");
     Bind b(c); if (b.ok()) return 1;
     if (first < 0 || n < 0 || first + n > c->cfg.max_particles) { cra_set_error("particle range exceeds max_particles"); return 1; }
     if (n == 0) return 0;
     if (wait_uploads(c, first, n)) return 1;
     float* dst = c->d_images + (size_t)first * c->npix;
     CRA_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * c->npix * sizeof(float), kind, c->st));
-    if (sub && cra_launch_mask_normalize(dst, n, c->nx, c->d_mask, 0, c->st)) return 1;
+    if (cra_launch_mask_normalize(dst, n, c->nx, c->d_mask, sub ? 0 : 2, c->d_dc + first, c->st)) return 1;
     CRA_CUDA(cudaStreamSynchronize(c->st));
     return 0;
 }
@@ -489,6 +520,7 @@ extern "C" int cra_upload_particles(CraCtx* c, const float* h, int first, int n,
 
 extern "C" int cra_upload_particles_async(CraCtx* c, const float* h, int first, int n, int sub)
 {
+    CraNvtx range("cra_upload_particles_async");
     Bind b(c); if (b.ok()) return 1;
     if (first < 0 || n < 0 || first + n > c->cfg.max_particles) { cra_set_error("particle range exceeds max_particles"); return 1; }
     if (n == 0) return 0;
@@ -502,7 +534,7 @@ extern "C" int cra_upload_particles_async(CraCtx* c, const float* h, int first, 
     CRA_CUDA(cudaMemcpyAsync(dst, h, (size_t)n * c->npix * sizeof(float), cudaMemcpyHostToDevice, c->st_copy));
     CRA_CUDA(cudaEventRecord(e0, c->st_copy));
     // an older pending upload that this one overwrites completely no longer needs its mask subtraction
-    for (auto& p : c->pending) if (p.first >= first && p.first + p.n <= first + n) p.sub = 0;
+    for (auto& p : c->pending) if (p.first >= first && p.first + p.n <= first + n) p.sub = -1;
     c->pending.push_back({first, n, sub ? 1 : 0, e0});
     return 0;
 }
@@ -521,7 +553,8 @@ extern "C" int cra_upload_particles_dev(CraCtx* c, const float* d, int first, in
 // d_refs[0..R) -> (normalize.mask no_sigma=1) -> Polar2Dm + Frngs + Applyws -> refspec, tref
 static int prepare_refs(CraCtx* c, int R, int normalize_mask)
 {
-    if (normalize_mask && cra_launch_mask_normalize(c->d_refs, R, c->nx, c->d_mask, 1, c->st)) return 1;
+    CraNvtx range("cra_prepare_refs");
+    if (normalize_mask && cra_launch_mask_normalize(c->d_refs, R, c->nx, c->d_mask, 1, nullptr, c->st)) return 1;
     if (cra_launch_polar_refs(c->d_refs, R, c->nx, c->d_tab, c->htab, c->d_samp, c->d_twf, c->items, c->d_refspec,
                               c->fmt, c->frag, c->d_tref, c->st)) return 1;
     if (c->use_um && cra_ccf_um_pack_refs(reinterpret_cast<const unsigned char*>(c->d_refspec), R, c->frag, c->d_refimg, c->st)) return 1;
@@ -571,6 +604,7 @@ extern "C" int cra_get_refs(CraCtx* c, float* host_refs)
 // run's rows and with the reference operands based at that class.
 static int align_impl(CraCtx* c, int start, int stop, const CraSearch* search, const int* class_of, CraResult* out)
 {
+    CraNvtx range(class_of ? "cra_align_bound" : "cra_align");
     Bind b(c); if (b.ok()) return 1;
     const int n = stop - start;
     if (start < 0 || n < 0 || stop > c->cfg.max_particles) { cra_set_error("particle range exceeds max_particles"); return 1; }
@@ -677,13 +711,15 @@ static int align_impl(CraCtx* c, int start, int stop, const CraSearch* search, c
         map.chunk_start = d_cs + bfirst[bi] + bi; map.nchunks = bchunks[bi];
         map.search = d_search + bfirst[bi];
         map.win = d_win + bfirst[bi];
-        map.np = bcount[bi]; map.nrows = brows[bi]; map.p0 = start + bfirst[bi]; map.step = step;
+        map.np = bcount[bi]; map.nrows = brows[bi]; map.p0 = start + bfirst[bi]; map.step = step; map.dc = c->d_dc;
         if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 0], c->st));
+        nvtxRangePushA("row kernel (Polar2Dm + Frngs)");
         if (bgroup[bi]) {
             if (cra_launch_polar_group(c->d_images, c->nx, c->d_tab, c->htab, c->d_samp, c->d_twf, c->items, c->plan, map,
-                                       c->cfg.normalize_ring, c->d_spec, c->frag, c->d_norm, c->st)) return 1;
+                                       c->cfg.normalize_ring, c->d_spec, c->frag, c->d_norm, c->st)) { nvtxRangePop(); return 1; }
         } else if (cra_launch_polar_rows(c->d_images, c->nx, c->d_tab, c->htab, c->d_samp, c->d_sampw, c->d_twf, c->items, map,
-                                         c->cfg.normalize_ring, c->d_spec, c->fmt, c->frag, c->d_norm, c->st)) return 1;
+                                         c->cfg.normalize_ring, c->d_spec, c->fmt, c->frag, c->d_norm, c->st)) { nvtxRangePop(); return 1; }
+        nvtxRangePop();
         if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 1], c->st));
         if (class_of) {
             const unsigned char* specb = reinterpret_cast<const unsigned char*>(c->d_spec);
@@ -698,14 +734,14 @@ static int align_impl(CraCtx* c, int start, int stop, const CraSearch* search, c
                 if (nr > 0) {
                     if (c->use_tm) {
                         if (cra_launch_ccf_tm(specb + (size_t)r0 * c->row_bytes, nr, ref1, 1, c->htab, c->frag, c->h_koff, c->d_twi,
-                                              c->d_cand + r0, 1, c->d_norm + r0, c->d_tref + cls, c->st)) return 1;
+                                              c->d_cand + r0, 1, c->d_norm + r0, c->d_tref + cls, &c->tm_sched, c->st)) return 1;
                     } else if (cra_launch_ccf_mma(specb + (size_t)r0 * c->row_bytes, nr, ref1, 1, c->htab, c->frag, c->h_koff, c->d_twi,
                                                   c->d_cand + r0, 1, c->d_norm + r0, c->d_tref + cls, c->st)) return 1;
                 }
                 CraRowMap sub = map;
                 sub.row_start += a; sub.search += a; sub.win += a; sub.np = e - a; sub.p0 += a;
                 if (cra_launch_finalize(c->d_spec, reinterpret_cast<const float*>(ref1), 1, c->d_tab, c->htab, c->d_cand, 1, sub,
-                                        c->d_res + bfirst[bi] + a, c->fmt, c->frag, c->st)) return 1;
+                                        c->d_res + bfirst[bi] + a, c->fmt, c->frag, c->d_twd, c->d_norm, c->d_tref + cls, c->st)) return 1;
                 launches += 2;
                 a = e;
             }
@@ -714,13 +750,14 @@ static int align_impl(CraCtx* c, int start, int stop, const CraSearch* search, c
             c->last_rows = map.nrows; c->last_group = bgroup[bi];
             continue;
         }
+        CraNvtx ccf_range("CCF (Crosrng_ms + inverse FFT + peak) + finalize");
         if (c->fmt == CRA_FMT_FRAG && c->use_um) {
             if (cra_launch_ccf_um(reinterpret_cast<const unsigned char*>(c->d_spec), map.nrows, c->d_refimg, c->R, c->htab, c->frag,
                                   c->h_koff, c->d_twi, c->d_cand, ntile_n, c->d_norm, c->d_tref, c->st)) return 1;
         } else if (c->fmt == CRA_FMT_FRAG && c->use_tm) {
             if (cra_launch_ccf_tm(reinterpret_cast<const unsigned char*>(c->d_spec), map.nrows,
                                   reinterpret_cast<const unsigned char*>(c->d_refspec), c->R, c->htab, c->frag, c->h_koff,
-                                  c->d_twi, c->d_cand, ntile_n, c->d_norm, c->d_tref, c->st)) return 1;
+                                  c->d_twi, c->d_cand, ntile_n, c->d_norm, c->d_tref, &c->tm_sched, c->st)) return 1;
         } else if (c->fmt == CRA_FMT_FRAG) {
             if (cra_launch_ccf_mma(reinterpret_cast<const unsigned char*>(c->d_spec), map.nrows,
                                    reinterpret_cast<const unsigned char*>(c->d_refspec), c->R, c->htab, c->frag, c->h_koff,
@@ -728,7 +765,7 @@ static int align_impl(CraCtx* c, int start, int stop, const CraSearch* search, c
         } else if (cra_launch_ccf(c->d_spec, map.nrows, c->d_refspec, c->R, c->d_tab, c->htab, c->d_twi, c->d_cand, ntile_n, c->st)) return 1;
         if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 2], c->st));
         if (cra_launch_finalize(c->d_spec, c->d_refspec, c->R, c->d_tab, c->htab, c->d_cand, ntile_n, map,
-                                c->d_res + bfirst[bi], c->fmt, c->frag, c->st)) return 1;
+                                c->d_res + bfirst[bi], c->fmt, c->frag, c->d_twd, c->d_norm, c->d_tref, c->st)) return 1;
         if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 3], c->st));
         launches += 3;
         c->last_rows = map.nrows; c->last_group = bgroup[bi];
@@ -801,6 +838,7 @@ extern "C" int cra_zero_sums(CraCtx* c)
 
 extern "C" int cra_accumulate(CraCtx* c, int start, int stop, const float* params, const int* iref, long goff)
 {
+    CraNvtx range("cra_accumulate (rot_shift2D + class sums)");
     Bind b(c); if (b.ok()) return 1;
     const int n = stop - start;
     if (start < 0 || n < 0 || stop > c->cfg.max_particles) { cra_set_error("particle range exceeds max_particles"); return 1; }

@@ -420,15 +420,73 @@ __device__ void pair_freq_frag(const unsigned char* __restrict__ rowp, const uns
     zq_r = A + B; zq_i = D - C; zt_r = A - B; zt_i = -C - D;
 }
 
+// A, B, C, D ring sums of one (row, ref) pair at frequency k in DOUBLE precision (the operands are exact
+// in FP32, so every product is exact in double): q_k = (A+B) + i(D-C), t_k = (A-B) - i(C+D)
+__device__ void pair_freq_d(const float2* __restrict__ spec, int row, const float2* __restrict__ refspec, int ref,
+                            const CraRingTab* __restrict__ tab, int k, double& zq_r, double& zq_i, double& zt_r, double& zt_i)
+{
+    double A = 0., B = 0., C = 0., D = 0.;
+    for (int i = tab->nring - 1; i >= 0 && k <= (tab->len[i] >> 1); --i) {
+        const int co = tab->coff[i], hf = tab->len[i] >> 1;
+        const float2 c = spec_at(refspec, tab->nc, ref, co, hf, k), d = spec_at(spec, tab->nc, row, co, hf, k);
+        A += (double)c.x * d.x; B += (double)c.y * d.y; C += (double)c.x * d.y; D += (double)c.y * d.x;
+    }
+    zq_r = A + B; zq_i = D - C; zt_r = A - B; zt_i = -C - D;
+}
+__device__ void pair_freq_frag_d(const unsigned char* __restrict__ rowp, const unsigned char* __restrict__ refp,
+                                 const CraFragTab& frag, int k, double& zq_r, double& zq_i, double& zt_r, double& zt_i)
+{
+    double A = 0., B = 0., C = 0., D = 0.;
+    const int c1 = frag.koff[k + 1];
+    for (int gc = frag.koff[k]; gc < c1; ++gc)
+        for (int t = 0; t < 4; ++t) {
+            const uint4* dp = reinterpret_cast<const uint4*>(rowp + (size_t)gc * 128 + t * 32);
+            const uint4* cp = reinterpret_cast<const uint4*>(refp + (size_t)gc * 128 + t * 32);
+            const uint4 dhi = dp[0], dlo = dp[1], cre = cp[0], cim = cp[1];
+            const uint4 dre = frag.unit_rows ? dhi : make_uint4(dhi.x, dhi.z, dlo.x, dlo.z);
+            const uint4 dim = frag.unit_rows ? dlo : make_uint4(dhi.y, dhi.w, dlo.y, dlo.w);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double dx = frag_val(dre, j), dy = frag_val(dim, j), cx = frag_val(cre, j), cy = frag_val(cim, j);
+                A += cx * dx; B += cy * dy; C += cx * dy; D += cy * dx;
+            }
+        }
+    zq_r = A + B; zq_i = D - C; zt_r = A - B; zt_i = -C - D;
+}
+
+// value at lag m (0-based) of the straight (.x) and the mirrored (.y) correlation, from the pair's spectrum z
+// (per frequency: q_r, q_i, t_r, t_i) and the double twiddle table twd[j] = (cos, sin)(2 pi j / N)
+__device__ __forceinline__ double2 lag_value(const double4* __restrict__ z, const double2* __restrict__ twd, int N, int m)
+{
+    double aq = 0., at = 0.;
+    for (int k = 0; k <= N / 2; ++k) {
+        const double2 w = twd[(k * m) & (N - 1)];
+        const double4 v = z[k];
+        const double wgt = (k == 0 || k == N / 2) ? 1.0 : 2.0;
+        aq += wgt * (v.x * w.x - v.y * w.y);
+        at += wgt * (v.z * w.x - v.w * w.y);
+    }
+    return make_double2(aq / N, at / N);
+}
+
+// One warp per particle: the winner over (row, reference) in the reference's visit order from the candidates of
+// the CCF kernel, then BOTH correlation curves of that pair in double precision straight from the spectra -- the
+// arithmetic of EMAN2's Crosrng_ms (double accumulation, fftr_d): ">=" argmax over the lags (the last maximum
+// wins), "qn >= qm" for the mirror, prb1d on the 7 samples around the maximum, ang_n, and the final rotation of
+// the shift.  norm / tref: deferred Normalize_ring of the fragment kernels (null: the spectra are normalised).
 template <int FMT>
 __global__ void __launch_bounds__(128)
 finalize_kernel(const float2* __restrict__ spec, const float2* __restrict__ refspec, int R,
                 const CraRingTab* __restrict__ tab, const CraCand* __restrict__ cand, int ntile_n,
-                CraRowMap map, CraResult* __restrict__ out, CraFragTab frag)
+                CraRowMap map, CraResult* __restrict__ out, CraFragTab frag, const double2* __restrict__ twd,
+                const float2* __restrict__ norm, const float* __restrict__ tref)
 {
-    const int lane = threadIdx.x & 31;
-    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    extern __shared__ __align__(16) double4 s_zd[];           // per warp: N/2 + 1 frequencies
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int p = blockIdx.x * (blockDim.x >> 5) + wib;
     if (p >= map.np) return;
+    const int N = tab->maxrin;
+    double4* z = s_zd + (size_t)wib * (N / 2 + 1);
     const int r0 = map.row_start[p], r1 = map.row_start[p + 1];
     const int ncand = (r1 - r0) * ntile_n;
     float bv = -INFINITY; int bc = -1, bcode = -1;
@@ -451,37 +509,44 @@ finalize_kernel(const float2* __restrict__ spec, const float2* __restrict__ refs
     }
     const int row = r0 + bc / ntile_n;
     const int iref = bcode / 8192;
-    const int mirror = (bcode >> 12) & 1;
-    const int jtot = bcode & 4095;              // 1-based lag of the maximum
-    const int N = tab->maxrin;
 
-    double t7[7] = {0, 0, 0, 0, 0, 0, 0};
     for (int k = lane; k <= N / 2; k += 32) {
-        float qr, qi, tr, ti;
+        double4 v;
         if (FMT == CRA_FMT_FRAG) {
             const size_t rb = cra_frag_row_bytes(frag.nch);
-            pair_freq_frag(reinterpret_cast<const unsigned char*>(spec) + (size_t)row * rb,
-                           reinterpret_cast<const unsigned char*>(refspec) + (size_t)iref * rb, frag, k, qr, qi, tr, ti);
-        } else pair_freq(spec, row, refspec, iref, tab, k, qr, qi, tr, ti);
-        const double zr = mirror ? tr : qr, zi = mirror ? ti : qi;
-        const double wgt = (k == 0 || k == N / 2) ? 1.0 : 2.0;
-#pragma unroll
-        for (int s = 0; s < 7; ++s) {
-            const int m = (jtot - 1 + s - 3 + N) % N;                 // 0-based lag
-            const int ph = (int)(((long long)k * m) % N);
-            double sn, cs; sincospi(2.0 * (double)ph / (double)N, &sn, &cs);
-            t7[s] += wgt * (zr * cs - zi * sn);
-        }
+            pair_freq_frag_d(reinterpret_cast<const unsigned char*>(spec) + (size_t)row * rb,
+                             reinterpret_cast<const unsigned char*>(refspec) + (size_t)iref * rb, frag, k, v.x, v.y, v.z, v.w);
+        } else pair_freq_d(spec, row, refspec, iref, tab, k, v.x, v.y, v.z, v.w);
+        z[k] = v;
+    }
+    __syncwarp();
+    // every lag of both curves; scan order j = 1..maxrin with ">=": the later lag wins a tie
+    double bq = -INFINITY, bt = -INFINITY; int mq = -1, mt = -1;
+    for (int m = lane; m < N; m += 32) {
+        const double2 v = lag_value(z, twd, N, m);
+        if (v.x >= bq) { bq = v.x; mq = m; }
+        if (v.y >= bt) { bt = v.y; mt = m; }
     }
 #pragma unroll
-    for (int s = 0; s < 7; ++s)
+    for (int o = 16; o > 0; o >>= 1) {
+        const double oq = __shfl_xor_sync(0xffffffffu, bq, o); const int omq = __shfl_xor_sync(0xffffffffu, mq, o);
+        const double ot = __shfl_xor_sync(0xffffffffu, bt, o); const int omt = __shfl_xor_sync(0xffffffffu, mt, o);
+        if (oq > bq || (oq == bq && omq > mq)) { bq = oq; mq = omq; }
+        if (ot > bt || (ot == bt && omt > mt)) { bt = ot; mt = omt; }
+    }
+    const int mirror = (bq >= bt) ? 0 : 1;
+    const int jtot = (mirror ? mt : mq) + 1;                    // 1-based lag of the maximum
+    double t7 = 0.;
+    if (lane < 7) {
+        const double2 v = lag_value(z, twd, N, (jtot - 1 + lane - 3 + N) & (N - 1));
+        t7 = mirror ? v.y : v.x;
+    }
+    double b[7];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t7[s] += __shfl_xor_sync(0xffffffffu, t7[s], o);
+    for (int s = 0; s < 7; ++s) b[s] = __shfl_sync(0xffffffffu, t7, s);
     if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < 7; ++s) t7[s] /= (double)N;
-        const double c2 = 49. * t7[0] + 6. * t7[1] - 21. * t7[2] - 32. * t7[3] - 27. * t7[4] - 6. * t7[5] + 31. * t7[6];
-        const double c3 = 5. * t7[0] - 3. * t7[2] - 4. * t7[3] - 3. * t7[4] + 5. * t7[6];
+        const double c2 = 49. * b[0] + 6. * b[1] - 21. * b[2] - 32. * b[3] - 27. * b[4] - 6. * b[5] + 31. * b[6];
+        const double c3 = 5. * b[0] - 3. * b[2] - 4. * b[3] - 3. * b[4] + 5. * b[6];
         float pos = 0.0f;
         if (c3 != 0.0) pos = (float)((c2 / (2.0 * c3)) - 4);
         const float tot = (float)jtot + pos;
@@ -493,8 +558,13 @@ finalize_kernel(const float2* __restrict__ spec, const float2* __restrict__ refs
         const float sx = -ix, sy = -iy;
         const float co = (float)cos((double)ang * 3.14159265358979323846 / 180.0);
         const float so = (float)(-sin((double)ang * 3.14159265358979323846 / 180.0));
+        double peak = mirror ? bt : bq;
+        if (norm) {           // deferred Normalize_ring: every lag moves by -avg * tref / N, then 1/sigma
+            const float2 nm = norm[row];
+            peak = (peak - (double)nm.x * (double)tref[iref] / N) * (double)nm.y;
+        }
         res.ang = ang; res.sxs = sx * co - sy * so; res.sys = sx * so + sy * co;
-        res.mirror = mirror; res.iref = iref; res.peak = bv; res.sx = sx; res.sy = sy;
+        res.mirror = mirror; res.iref = iref; res.peak = (float)peak; res.sx = sx; res.sy = sy;
         out[p] = res;
     }
 }
@@ -543,6 +613,9 @@ int bind_ring_table(const CraRingTab& h, cudaStream_t st)
     CRA_CUDA(cudaStreamSynchronize(st));
     CRA_CUDA(cudaMemcpyToSymbol(c_coff, h.coff, sizeof(int) * h.nring));
     CRA_CUDA(cudaMemcpyToSymbol(c_half, half, sizeof(int) * h.nring));
+    // the copies come from pageable memory on the legacy stream and the kernel runs on a non-blocking stream:
+    // make sure they have landed (diagnostic path; one-off per geometry and device)
+    CRA_CUDA(cudaDeviceSynchronize());
     memcpy(cur_coff, h.coff, sizeof(int) * h.nring); memcpy(cur_half, half, sizeof(int) * h.nring);
     cur_n = h.nring; cur_dev = dev;
     return 0;
@@ -555,11 +628,7 @@ int launch_ccf_t(const float* spec, int nrows, const float* refspec, int R, cons
     using S = Shape<LOG2N>;
     constexpr int SUBM = S::SUBM, SUBN = S::SUBN, NSUB = S::NSUB;
     const size_t smem = ((size_t)NSUB * NP * S::PS + S::N) * sizeof(float2);
-    static bool configured = false;
-    if (!configured) {
-        CRA_CUDA(cudaFuncSetAttribute(ccf_peak_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    if (cra_ensure_dyn_smem(reinterpret_cast<const void*>(&ccf_peak_kernel<LOG2N>), smem)) return 1;
     const long ntile_m = (nrows + TM - 1) / TM;
     const long ncta_m = (ntile_m + SUBM - 1) / SUBM, ncta_n = (ntile_n + SUBN - 1) / SUBN;
     const long nblk = ncta_m * ncta_n;
@@ -593,13 +662,6 @@ int cra_launch_ccf(const float* spec, int nrows, const float* refspec, int R, co
                    const CraRingTab& htab, const float2* twid, CraCand* cand, int ntile_n, cudaStream_t st)
 {
     (void)tab;
-    // reference-resident persistent variant (cra_ccf_rr.cu): experimental, off by default (slower)
-    static const int use_rr = getenv("CRA_CCF_RR") ? atoi(getenv("CRA_CCF_RR")) : 0;
-    if (use_rr && TM == 4) {
-        bool ran = false;
-        if (cra_launch_ccf_rr(spec, nrows, refspec, R, htab, twid, cand, ntile_n, st, &ran)) return 1;
-        if (ran) return 0;
-    }
     if (bind_ring_table(htab, st)) return 1;
     switch (htab.log2n) {
         case 5:  return launch_ccf_t<5>(spec, nrows, refspec, R, htab, twid, cand, ntile_n, st);
@@ -614,16 +676,18 @@ int cra_launch_ccf(const float* spec, int nrows, const float* refspec, int R, co
 
 int cra_launch_finalize(const float* spec, const float* refspec, int R, const CraRingTab* tab, const CraRingTab& htab,
                         const CraCand* cand, int ntile_n, CraRowMap map, CraResult* out, int fmt, const CraFragTab& frag,
-                        cudaStream_t st)
+                        const double2* twd, const float2* norm, const float* tref, cudaStream_t st)
 {
-    (void)htab;
     if (map.np <= 0) return 0;
     const int wpb = 4;
+    const size_t smem = (size_t)wpb * (htab.maxrin / 2 + 1) * sizeof(double4);
     const float2* s2 = reinterpret_cast<const float2*>(spec); const float2* r2 = reinterpret_cast<const float2*>(refspec);
+    if (smem > 48 * 1024 && cra_ensure_dyn_smem(fmt == CRA_FMT_FRAG ? reinterpret_cast<const void*>(&finalize_kernel<CRA_FMT_FRAG>)
+                                                                     : reinterpret_cast<const void*>(&finalize_kernel<CRA_FMT_F32>), smem)) return 1;
     if (fmt == CRA_FMT_FRAG)
-        finalize_kernel<CRA_FMT_FRAG><<<(map.np + wpb - 1) / wpb, wpb * 32, 0, st>>>(s2, r2, R, tab, cand, ntile_n, map, out, frag);
+        finalize_kernel<CRA_FMT_FRAG><<<(map.np + wpb - 1) / wpb, wpb * 32, smem, st>>>(s2, r2, R, tab, cand, ntile_n, map, out, frag, twd, norm, tref);
     else
-        finalize_kernel<CRA_FMT_F32><<<(map.np + wpb - 1) / wpb, wpb * 32, 0, st>>>(s2, r2, R, tab, cand, ntile_n, map, out, frag);
+        finalize_kernel<CRA_FMT_F32><<<(map.np + wpb - 1) / wpb, wpb * 32, smem, st>>>(s2, r2, R, tab, cand, ntile_n, map, out, frag, twd, nullptr, nullptr);
     CRA_CUDA(cudaGetLastError());
     return 0;
 }

@@ -324,6 +324,9 @@ int bind_schedule(const CraRingTab& h, const std::vector<int>& koff, cudaStream_
     CRA_CUDA(cudaMemcpyToSymbol(g_items, h_items, sizeof(h_items)));
     CRA_CUDA(cudaMemcpyToSymbol(g_nitems, h_n, sizeof(h_n)));
     CRA_CUDA(cudaMemcpyToSymbol(g_flush, h_flush, sizeof(h_flush)));
+    // the copies come from pageable memory on the legacy stream and the kernel runs on a non-blocking stream:
+    // make sure they have landed (diagnostic path; one-off per geometry and device)
+    CRA_CUDA(cudaDeviceSynchronize());
     g_sched.istride = 0; g_sched.fstride = 0;
     for (int w = 0; w < kWarps; ++w) {
         g_sched.istride = std::max(g_sched.istride, (int)lists[w].size());
@@ -339,11 +342,7 @@ int launch_t(const unsigned char* spec, int nrows, const unsigned char* refspec,
 {
     using S = MShape<LOG2N>;
     const size_t smem = ((size_t)S::NP * S::PS + S::N) * sizeof(float2) + (size_t)kWarps * (g_sched.istride + g_sched.fstride) * sizeof(int);
-    static size_t configured = 0;
-    if (smem > configured) {
-        CRA_CUDA(cudaFuncSetAttribute(ccf_mma_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    if (cra_ensure_dyn_smem(reinterpret_cast<const void*>(&ccf_mma_kernel<LOG2N>), smem)) return 1;
     const int nquad = (R + 3) / 4;
     const long ncta_m = (nrows + S::ROWS - 1) / S::ROWS;
     const long nblk = ncta_m * ntile_n;

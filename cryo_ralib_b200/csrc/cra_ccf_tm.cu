@@ -4,19 +4,29 @@
 // replaces cu_ccf_mult_m + cuFFT C2R + cu_max_idx_batch, cuda/gpu_aln_noref.cu:1009-1143,
 // :2198-2206, :1305-1346).
 //
-// Same arithmetic as cra_ccf_mma.cu (mma.sync.m16n8k16 split-bf16 x3, W = q + i t, one complex
-// inverse FFT per pair, ">=" argmax).  What changes is where W lives.  The 2 KB of W per
-// (row, reference) pair cap a shared-memory tile at ~100 pairs and ONE resident CTA per SM, so the
-// L2-latency-bound contraction and the FP32-bound inverse FFT can never overlap.  Here a warp writes
-// its finished frequencies to TMEM with tcgen05.st: in the mma accumulator layout lane (g, t) owns
-// the pairs (row g, reference 4j + t) in EVERY warp, and a thread may only touch the TMEM lanes of its
-// warp's quadrant (warp % 4), so the frequencies are dealt to the quadrants by residue
-// n2 = k mod N2 (and N2 - n2: the Hermitian partner W[N-k] of the same MMA result).  Pass 1 of the
-// inverse FFT (N1-point DFTs over k = n1 N2 + n2 at fixed n2) then reads nothing but the thread's own
-// TMEM lane (tcgen05.ld .32x32b), and only its output goes to shared memory, one 4-reference
-// batch (32 pairs, 70 KB) at a time, for pass 2 and the argmax.  A CTA is 8 warps, 8 rows x 8
-// references, 256 TMEM columns and 74 KB of shared memory: TWO CTAs are resident per SM and the
-// contraction of one runs under the inverse FFT of the other.
+// Arithmetic: mma.sync.m16n8k16 split-bf16 x3 (a_hi b_lo + a_lo b_hi + a_hi b_hi, FP32 accumulate),
+// W = q + i t Hermitian-extended, one complex inverse FFT per (row, reference) pair, maximum of q and
+// of t.  Where W lives: a warp writes its finished frequencies to TMEM with tcgen05.st: in the mma
+// accumulator layout lane (g, t) owns the pairs (row g, reference 4j + t) in EVERY warp, and a thread
+// may only touch the TMEM lanes of its warp's quadrant (warp % 4), so the frequencies are dealt to the
+// quadrants by residue n2 = k mod N2 (and N2 - n2: the Hermitian partner W[N-k] of the same MMA
+// result).  Pass 1 of the inverse FFT (N1-point DFTs over k = n1 N2 + n2 at fixed n2) then reads
+// nothing but the thread's own TMEM lane (tcgen05.ld .32x32b), and only its output goes to shared
+// memory, one 4-reference batch (32 pairs) at a time, for pass 2 and the maxima.
+//
+// maxrin <= 256: a CTA is 8 warps, 8 rows x 8 references, 256 TMEM columns and ~76 KB of shared memory:
+// TWO CTAs are resident per SM and the contraction of one runs under the inverse FFT of the other.
+// maxrin = 512: tensor memory holds 64 pairs (one pair = 1024 words), so there is one CTA per SM; it
+// runs 16 warps (4 per quadrant) to double the operand loads in flight.
+//
+// Round 2: (1) the kernel keeps only the maximum VALUE of q and of t per pair (FMNMX) -- the lag of a
+// particle's winner is re-derived in double precision by finalize_kernel from the spectra, as EMAN2's
+// own double-precision Crosrng_ms would; (2) the per-warp work list is one stream of (chunk offset, flush
+// descriptor) pairs read with 128-bit shared loads and padded to whole groups of four with the all-zero
+// chunk of the fragment layout (cra_common.cuh), so the inner loop has no tail conditionals and spends one
+// hardware scoreboard on its bookkeeping instead of five, which leaves scoreboards for the operand loads of
+// the four register sets (scripts/sass_ctrl.py prints the assignment); (3) the work lists live in
+// per-context device buffers, not in __device__ globals.
 #include "cra_common.cuh"
 #include "cra_fft.cuh"
 #include <math.h>
@@ -27,22 +37,7 @@
 
 namespace {
 
-#ifndef CRA_TM_WARPS
-#define CRA_TM_WARPS 8
-#endif
-constexpr int kWarps = CRA_TM_WARPS;      // a multiple of 4: kWarps / 4 warps share each TMEM quadrant
-constexpr int kThreads = kWarps * 32;
-constexpr int kMaxItems = 640;          // chunk items per warp
-constexpr int kMaxFreq = 160;           // frequencies per warp
-constexpr int kPfDist = 40;             // row blocks between an L2 prefetch and its use
-
-// per-warp work lists (global, staged in shared memory by every CTA):
-//   items: gc | last << 23   (gc = chunk index within a row)
-//   flush: TMEM column (relative to the pair slot) of W[k] | column of W[N-k] << 12 | has_partner << 24
-__device__ int g_items[kWarps][kMaxItems];
-__device__ int g_nitems[kWarps];
-__device__ int g_flush[kWarps][kMaxFreq];
-__device__ int g_res[4][8];             // residues n2 of quadrant q, in TMEM order (N2 / 4 of them)
+constexpr int kMaxWarps = 16;
 
 using crafft::fft_reg;
 
@@ -54,10 +49,12 @@ struct TShape {
     static constexpr int N1 = 1 << L1;
     static constexpr int N2 = 1 << L2;
     static constexpr int PS = N1 * (N2 + 1) + ((N1 * (N2 + 1)) % 2 == 0 ? 1 : 0);   // odd float2 stride of one pair
-    static constexpr int NJ = 2;                        // reference quads per CTA (maxrin 512: all 512 columns, one CTA per SM)
+    static constexpr int NJ = 2;                        // reference quads per CTA
     static constexpr int RQ = N2 / 4;                   // residues per quadrant
     static constexpr int JCOLS = N / 2;                 // TMEM columns of one pair slot in one quadrant = RQ * N1 * 2
     static constexpr int COLS = (NJ * JCOLS < 32) ? 32 : NJ * JCOLS;
+    static constexpr int KW = (LOG2N >= 9) ? 16 : 8;    // warps per CTA (a multiple of 4: KW / 4 share a TMEM quadrant)
+    static constexpr int PER_SM = (COLS <= 256) ? 2 : 1;
 };
 
 __device__ __forceinline__ void mma_bf16(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1)
@@ -76,10 +73,11 @@ __device__ __forceinline__ Frag8 ldg256(const unsigned char* p)
                  : "l"(p));
     return f;
 }
-
-__device__ __forceinline__ bool better(float v, int m, float bv, int bm)
-{   // ">=" scan order semantics: larger value wins, ties go to the later index
-    return (v > bv) || (v == bv && m > bm);
+__device__ __forceinline__ uint4 ldg128(const unsigned char* p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
 }
 
 // ---- tensor memory -------------------------------------------------------------------------------
@@ -122,25 +120,29 @@ template <> __device__ __forceinline__ void tmem_ld<32>(unsigned taddr, float2 (
     for (int i = 0; i < 16; ++i) x[i] = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
 }
 
-template <int NJ>
-struct Operands { Frag8 a; uint4 b[NJ]; };
+struct Operands { Frag8 a; uint4 b0, b1; };
+
+// header of the per-context schedule (device): items per warp, residues n2 of quadrant q in TMEM order
+struct SchedHdr { int nit[kMaxWarps]; int res[4][8]; };
 
 template <int LOG2N>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(TShape<LOG2N>::KW * 32, TShape<LOG2N>::PER_SM)
 ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned char* __restrict__ refspec, int R,
               size_t row_bytes, const float2* __restrict__ twid, CraCand* __restrict__ cand,
-              int nquad, int ncta_n, const float2* __restrict__ norm, const float* __restrict__ tref, int istride, int fstride,
-              long ntiles)
+              int nquad, int ncta_n, const float2* __restrict__ norm, const float* __restrict__ tref,
+              const int2* __restrict__ g_items, const SchedHdr* __restrict__ g_hdr, int istride, long ntiles)
 {
     using S = TShape<LOG2N>;
-    constexpr int N = S::N, N1 = S::N1, N2 = S::N2, PS = S::PS, NJ = S::NJ, RQ = S::RQ, JCOLS = S::JCOLS;
+    constexpr int N = S::N, N1 = S::N1, N2 = S::N2, PS = S::PS, NJ = S::NJ, RQ = S::RQ, JCOLS = S::JCOLS, KW = S::KW;
+    constexpr int kThreads = KW * 32;
+    static_assert(NJ == 2, "the operand sets below hold two reference quads");
     extern __shared__ __align__(16) float2 s_dyn[];
     float2* s_y = s_dyn;                      // 32 pairs * PS : pass-1 output of one reference quad
     float2* s_tw = s_dyn + 32 * PS;           // N : s_tw[j*N2 + n2] = exp(+2 pi i n2 j / N)
-    int* s_items = reinterpret_cast<int*>(s_tw + N);            // kWarps * istride chunk items
-    int* s_flush = s_items + kWarps * istride;                  // kWarps * fstride completed frequencies
+    int2* s_items = reinterpret_cast<int2*>(s_tw + N);          // KW * istride items (16-byte aligned: 32 * PS + N is even)
     __shared__ CraCand s_pair[32 * NJ];
     __shared__ unsigned s_tmem;
+    __shared__ SchedHdr s_hdr;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -153,11 +155,9 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     for (int i = tid; i < N; i += kThreads) s_tw[i] = twid[i];
-    {
-        const int nit = g_nitems[warp];
-        for (int i = lane; i < nit; i += 32) s_items[warp * istride + i] = g_items[warp][i];
-        for (int i = lane; i < fstride; i += 32) s_flush[warp * fstride + i] = g_flush[warp][i];
-    }
+    for (int i = tid; i < (int)(sizeof(SchedHdr) / sizeof(int)); i += kThreads)
+        reinterpret_cast<int*>(&s_hdr)[i] = reinterpret_cast<const int*>(g_hdr)[i];
+    for (int i = tid; i < KW * istride; i += kThreads) s_items[i] = g_items[i];
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -174,16 +174,6 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
     const int nj = qbase + (cn < qrem ? 1 : 0);                 // reference quads of this tile (<= NJ)
     const int q0 = cn * qbase + min(cn, qrem);
     const int row0 = (int)(cm * 8);
-    if (cn == 0) {                            // pull a future row block into L2 (see cra_ccf_mma.cu)
-        const long r0 = (long)(cm + kPfDist) * 8;
-        if (r0 < nrows) {
-            const long r1 = min((long)nrows, r0 + 8);
-            const unsigned char* p0 = spec + (size_t)r0 * row_bytes;
-            const size_t nline = (size_t)(r1 - r0) * row_bytes / 128;
-            for (size_t i = tid; i < nline; i += kThreads)
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(p0 + i * 128));
-        }
-    }
     // the previous tile's tcgen05.ld (pass 1) were ordered before its barriers
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
@@ -192,97 +182,68 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
         int rrow = row0 + g;
         if (rrow >= nrows) rrow = nrows - 1;
         const unsigned char* pa = spec + (size_t)rrow * row_bytes + t * 32;
-        const unsigned char* pb[NJ];
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            const int jj = (j < nj) ? j : 0;
-            pb[j] = refspec + (size_t)(4 * (q0 + jj) + (g >> 1)) * row_bytes + t * 32 + (g & 1) * 16;
-        }
-        float acc[NJ][4];
-#pragma unroll
-        for (int j = 0; j < NJ; ++j)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+        const unsigned char* pb0 = refspec + (size_t)(4 * q0 + (g >> 1)) * row_bytes + t * 32 + (g & 1) * 16;
+        const unsigned char* pb1 = refspec + (size_t)(4 * (q0 + (nj > 1 ? 1 : 0)) + (g >> 1)) * row_bytes + t * 32 + (g & 1) * 16;
+        // keep the three operand bases in registers: re-deriving them from the parameter bank inside the loop
+        // costs an LDC scoreboard per base (see the header)
+        asm volatile("" : "+l"(pa), "+l"(pb0), "+l"(pb1));
+        float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
 
-        const int nit = g_nitems[warp];
-        const int* items = s_items + warp * istride;
-        const int* fl = s_flush + warp * fstride;
+        const int nit = s_hdr.nit[warp];                        // a multiple of 4, >= 4
+        const int4* it4 = reinterpret_cast<const int4*>(s_items + warp * istride);   // (off, flush) x 2 per int4
 
-#define CRA_LOAD_OPS(O, item)                                                            \
-        { const size_t off_ = (size_t)((item) & 8191) * 128;                             \
-          O.a = ldg256(pa + off_);                                                       \
-          _Pragma("unroll") for (int j_ = 0; j_ < NJ; ++j_)                              \
-              O.b[j_] = __ldg(reinterpret_cast<const uint4*>(pb[j_] + off_)); }
-#define CRA_COMPUTE(O, item)                                                             \
-        { _Pragma("unroll") for (int j_ = 0; j_ < NJ; ++j_)                              \
-              mma_bf16(acc[j_], O.a.w[0], O.a.w[1], O.a.w[2], O.a.w[3], O.b[j_].z, O.b[j_].w);   /* a_hi b_lo */ \
-          _Pragma("unroll") for (int j_ = 0; j_ < NJ; ++j_)                              \
-              mma_bf16(acc[j_], O.a.w[4], O.a.w[5], O.a.w[6], O.a.w[7], O.b[j_].x, O.b[j_].y);   /* a_lo b_hi */ \
-          _Pragma("unroll") for (int j_ = 0; j_ < NJ; ++j_)                              \
-              mma_bf16(acc[j_], O.a.w[0], O.a.w[1], O.a.w[2], O.a.w[3], O.b[j_].x, O.b[j_].y);   /* a_hi b_hi */ \
-          if ((item) >> 23) flush_freq(); }
+#define CRA_LOAD_OPS(O, off)                                                             \
+        { O.a = ldg256(pa + (unsigned)(off)); O.b0 = ldg128(pb0 + (unsigned)(off)); O.b1 = ldg128(pb1 + (unsigned)(off)); }
+#define CRA_COMPUTE(O, fl)                                                               \
+        { mma_bf16(acc0, O.a.w[0], O.a.w[1], O.a.w[2], O.a.w[3], O.b0.z, O.b0.w);   /* a_hi b_lo */ \
+          mma_bf16(acc1, O.a.w[0], O.a.w[1], O.a.w[2], O.a.w[3], O.b1.z, O.b1.w);       \
+          mma_bf16(acc0, O.a.w[4], O.a.w[5], O.a.w[6], O.a.w[7], O.b0.x, O.b0.y);   /* a_lo b_hi */ \
+          mma_bf16(acc1, O.a.w[4], O.a.w[5], O.a.w[6], O.a.w[7], O.b1.x, O.b1.y);       \
+          mma_bf16(acc0, O.a.w[0], O.a.w[1], O.a.w[2], O.a.w[3], O.b0.x, O.b0.y);   /* a_hi b_hi */ \
+          mma_bf16(acc1, O.a.w[0], O.a.w[1], O.a.w[2], O.a.w[3], O.b1.x, O.b1.y);       \
+          if (fl) flush_freq(fl); }
 
-        auto flush_freq = [&]() {
-            const int f = *fl++;
+        // a finished frequency: W[k] and its Hermitian partner W[N-k] to this lane's TMEM columns.  For k = 0 and
+        // k = N/2 both columns coincide and both values are equal (the imaginary parts of those bins are exact zeros).
+        auto flush_freq = [&](int f) {
             const unsigned c0 = f & 4095, c1 = (f >> 12) & 4095;
-            const bool two = (f >> 24) != 0;                    // warp-uniform
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                // c0 = A (re.re), c1 = D (row re . ref im), c2 = C (row im . ref re), c3 = B (im.im)
-                const float A = acc[j][0], D = acc[j][1], C = acc[j][2], B = acc[j][3];
+            {   // c0 = A (re.re), c1 = D (row re . ref im), c2 = C (row im . ref re), c3 = B (im.im)
+                const float A = acc0[0], D = acc0[1], C = acc0[2], B = acc0[3];
                 // s = (A+B, A-B), tv = (C+D, D-C);  W[k] = s + tv,  W[N-k] = s - tv
                 const float sx = A + B, sy = A - B, tx = C + D, ty = D - C;
-                tmem_st2(tbase + j * JCOLS + c0, sx + tx, sy + ty);
-                if (two) tmem_st2(tbase + j * JCOLS + c1, sx - tx, sy - ty);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+                tmem_st2(tbase + c0, sx + tx, sy + ty);
+                tmem_st2(tbase + c1, sx - tx, sy - ty);
+                acc0[0] = acc0[1] = acc0[2] = acc0[3] = 0.f;
+            }
+            {
+                const float A = acc1[0], D = acc1[1], C = acc1[2], B = acc1[3];
+                const float sx = A + B, sy = A - B, tx = C + D, ty = D - C;
+                tmem_st2(tbase + JCOLS + c0, sx + tx, sy + ty);
+                tmem_st2(tbase + JCOLS + c1, sx - tx, sy - ty);
+                acc1[0] = acc1[1] = acc1[2] = acc1[3] = 0.f;
             }
         };
 
-#if CRA_TM_WARPS <= 8
-        // Four operand sets, loaded two chunks at a time.  ptxas keeps every operand LDG on one hardware
-        // scoreboard and drains it before the oldest set is used (profiles/README.md), so what a load gets
-        // to hide behind is the work issued between its batch and the next drain: issuing the loads in
-        // pairs (drain, load chunks i+2 and i+3, multiply chunks i and i+1) doubles that window.
-        Operands<NJ> o0, o1, o2, o3;
-        if (nit > 0) CRA_LOAD_OPS(o0, items[0]);
-        if (nit > 1) CRA_LOAD_OPS(o1, items[1]);
-        for (int i = 0; i < nit; i += 4) {
-            const int e0 = items[i];
-            const int e1 = (i + 1 < nit) ? items[i + 1] : 0;
-            if (i + 2 < nit) CRA_LOAD_OPS(o2, items[i + 2]);
-            if (i + 3 < nit) CRA_LOAD_OPS(o3, items[i + 3]);
-            CRA_COMPUTE(o0, e0);
-            if (i + 1 >= nit) break;
-            CRA_COMPUTE(o1, e1);
-            if (i + 2 >= nit) break;
-            const int e2 = items[i + 2];
-            const int e3 = (i + 3 < nit) ? items[i + 3] : 0;
-            if (i + 4 < nit) CRA_LOAD_OPS(o0, items[i + 4]);
-            if (i + 5 < nit) CRA_LOAD_OPS(o1, items[i + 5]);
-            CRA_COMPUTE(o2, e2);
-            if (i + 3 >= nit) break;
-            CRA_COMPUTE(o3, e3);
+        // Four operand sets, one chunk each, every set reloaded right after its chunk was multiplied: a load
+        // has the multiplication of three other chunks to land in.
+        Operands o0, o1, o2, o3;
+        int4 ia = it4[0], ib = it4[1];
+        CRA_LOAD_OPS(o0, ia.x); CRA_LOAD_OPS(o1, ia.z); CRA_LOAD_OPS(o2, ib.x); CRA_LOAD_OPS(o3, ib.z);
+#pragma unroll 1
+        for (int i = 4; ; i += 4) {
+            const bool more = i < nit;
+            const int f0 = ia.y, f1 = ia.w, f2 = ib.y, f3 = ib.w;
+            if (more) { ia = it4[i >> 1]; ib = it4[(i >> 1) + 1]; }
+            CRA_COMPUTE(o0, f0);
+            if (more) CRA_LOAD_OPS(o0, ia.x);
+            CRA_COMPUTE(o1, f1);
+            if (more) CRA_LOAD_OPS(o1, ia.z);
+            CRA_COMPUTE(o2, f2);
+            if (more) CRA_LOAD_OPS(o2, ib.x);
+            CRA_COMPUTE(o3, f3);
+            if (!more) break;
+            CRA_LOAD_OPS(o3, ib.z);
         }
-#else
-        // three operand sets (register budget of the wider CTA)
-        Operands<NJ> o0, o1, o2;
-        if (nit > 0) CRA_LOAD_OPS(o0, items[0]);
-        if (nit > 1) CRA_LOAD_OPS(o1, items[1]);
-        for (int i = 0; i < nit; i += 3) {
-            const int e0 = items[i];
-            if (i + 2 < nit) CRA_LOAD_OPS(o2, items[i + 2]);
-            CRA_COMPUTE(o0, e0);
-            if (i + 1 >= nit) break;
-            const int e1 = items[i + 1];
-            if (i + 3 < nit) CRA_LOAD_OPS(o0, items[i + 3]);
-            CRA_COMPUTE(o1, e1);
-            if (i + 2 >= nit) break;
-            const int e2 = items[i + 2];
-            if (i + 4 < nit) CRA_LOAD_OPS(o1, items[i + 4]);
-            CRA_COMPUTE(o2, e2);
-        }
-#endif
 #undef CRA_LOAD_OPS
 #undef CRA_COMPUTE
     }
@@ -302,8 +263,8 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
     // ---- inverse FFT, one reference quad (32 pairs: lane = pair) at a time -----------------------
     for (int j = 0; j < nj; ++j) {
         // pass 1: (pair = lane, residue n2): N1-point DFT over n1 straight from this lane's TMEM, twiddle
-        for (int ri = warp >> 2; ri < RQ; ri += kWarps / 4) {
-            const int n2 = g_res[quad][ri];
+        for (int ri = warp >> 2; ri < RQ; ri += KW / 4) {
+            const int n2 = s_hdr.res[quad][ri];
             float2 x[N1];
             tmem_ld<2 * N1>(tbase + j * JCOLS + ri * (2 * N1), x);
             fft_reg<N1, 1>(x);
@@ -317,7 +278,8 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        // pass 2: (pair, k1): N2-point DFT over n2 -> X[k1 + N1*k2]; argmax over lags
+        // pass 2: (pair, k1): N2-point DFT over n2 -> X[k1 + N1*k2]; only the MAXIMA of q = Re X and t = Im X are
+        // kept -- finalize_kernel re-derives the lag of the particle's winner in double precision
         for (int item = tid; item < 32 * N1; item += kThreads) {
             const int pi = item / N1, k1 = item - pi * N1;
             const float2* w = s_y + pi * PS + k1 * (N2 + 1);
@@ -325,20 +287,14 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
 #pragma unroll
             for (int jj = 0; jj < N2; ++jj) x[jj] = w[jj];
             fft_reg<N2, 1>(x);
-            float bq = -INFINITY, bt = -INFINITY; int mq = -1, mt = -1;
+            float bq = x[0].x, bt = x[0].y;
 #pragma unroll
-            for (int jj = 0; jj < N2; ++jj) {
-                const int m = k1 + N1 * jj;
-                if (x[jj].x >= bq) { bq = x[jj].x; mq = m; }
-                if (x[jj].y >= bt) { bt = x[jj].y; mt = m; }
-            }
+            for (int jj = 1; jj < N2; ++jj) { bq = fmaxf(bq, x[jj].x); bt = fmaxf(bt, x[jj].y); }
             // the N1 lanes of one pair are consecutive and aligned inside a warp (N1 <= 32)
 #pragma unroll
             for (int o = N1 >> 1; o > 0; o >>= 1) {
-                float oq = __shfl_xor_sync(0xffffffffu, bq, o); int omq = __shfl_xor_sync(0xffffffffu, mq, o);
-                float ot = __shfl_xor_sync(0xffffffffu, bt, o); int omt = __shfl_xor_sync(0xffffffffu, mt, o);
-                if (better(oq, omq, bq, mq)) { bq = oq; mq = omq; }
-                if (better(ot, omt, bt, mt)) { bt = ot; mt = omt; }
+                bq = fmaxf(bq, __shfl_xor_sync(0xffffffffu, bq, o));
+                bt = fmaxf(bt, __shfl_xor_sync(0xffffffffu, bt, o));
             }
             if (k1 == 0) {
                 const int row = row0 + (pi >> 2), ref = 4 * (q0 + j) + (pi & 3);     // pair = lane (g, t)
@@ -348,8 +304,8 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
                     const float2 nm = norm[row];
                     const float sc = nm.y / (float)N, dc = nm.x * tref[ref];
                     const float qn = (bq - dc) * sc, qm = (bt - dc) * sc;
-                    if (qn >= qm) { cd.v = qn; cd.code = ref * 8192 + (mq + 1); }
-                    else          { cd.v = qm; cd.code = ref * 8192 + 4096 + (mt + 1); }
+                    if (qn >= qm) { cd.v = qn; cd.code = ref * 8192; }
+                    else          { cd.v = qm; cd.code = ref * 8192 + 4096; }
                 } else { cd.v = -INFINITY; cd.code = -1; }
                 s_pair[j * 32 + pi] = cd;
             }
@@ -376,20 +332,25 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
     }
 }
 
-struct Sched { int nring = -1, maxrin = -1, dev = -1, istride = 0, fstride = 0; std::vector<int> len; };
-Sched g_sched;
+// ---- per-context schedule ------------------------------------------------------------------------------
+struct TmSched {
+    int2* d_items = nullptr;
+    SchedHdr* d_hdr = nullptr;
+    int istride = 0;           // items per warp (a multiple of 4)
+    int kw = 0;
+    int resident = 0;          // CTAs the device holds at once
+};
 
 // Deal the frequencies to the TMEM quadrants by residue n2 = k mod N2 (a residue and its negative
-// together), balance each quadrant's frequencies over its two warps, and upload the lists.
-int bind_schedule(const CraRingTab& h, const std::vector<int>& koff, cudaStream_t st)
+// together), balance each quadrant's frequencies over its warps, and upload the lists.
+int build_schedule(const CraRingTab& h, const std::vector<int>& koff, int kw, cudaStream_t st, TmSched** out)
 {
-    int dev = 0; cudaGetDevice(&dev);
-    std::vector<int> len(h.len, h.len + h.nring);
-    if (g_sched.nring == h.nring && g_sched.maxrin == h.maxrin && g_sched.dev == dev && g_sched.len == len) return 0;
     const int N = h.maxrin, nk = N / 2 + 1;
     const int L1 = h.log2n / 2, L2 = h.log2n - L1, N1 = 1 << L1, N2 = 1 << L2, RQ = N2 / 4;
     if (RQ < 1 || RQ > 8) { cra_set_error("tensor-memory CCF kernel: unsupported maxrin"); return 1; }
+    if (N2 == 4) { cra_set_error("tensor-memory CCF kernel: maxrin too small"); return 1; }
     auto nch = [&](int k) { return koff[k + 1] - koff[k]; };
+    const int zero_chunk = koff[nk];                                   // chunk nch of every row: all zeros
     // residue classes {n2, N2 - n2} and their chunk loads
     std::vector<std::vector<int>> cls;
     for (int n2 = 0; n2 <= N2 / 2; ++n2) {
@@ -412,72 +373,74 @@ int bind_schedule(const CraRingTab& h, const std::vector<int>& koff, cudaStream_
         qres[best].push_back(cls[ci][0]); qres[best].push_back(cls[ci][1]);
         qload[best] += cls_load(cls[ci]);
     }
-    if (N2 == 4) { cra_set_error("tensor-memory CCF kernel: maxrin too small"); return 1; }
-    int h_res[4][8]; memset(h_res, 0, sizeof(h_res));
+    SchedHdr hdr; memset(&hdr, 0, sizeof(hdr));
     std::vector<int> ridx(N2, -1), rquad(N2, -1);
     for (int q = 0; q < 4; ++q) {
         if ((int)qres[q].size() != RQ) { cra_set_error("tensor-memory CCF kernel: residue assignment failed"); return 1; }
-        for (int i = 0; i < RQ; ++i) { h_res[q][i] = qres[q][i]; ridx[qres[q][i]] = i; rquad[qres[q][i]] = q; }
+        for (int i = 0; i < RQ; ++i) { hdr.res[q][i] = qres[q][i]; ridx[qres[q][i]] = i; rquad[qres[q][i]] = q; }
     }
     // frequencies of quadrant q -> its warps q, q + 4, ... (longest-processing-time first)
-    std::vector<std::vector<int>> lists(kWarps), flush(kWarps);
-    std::vector<int> load(kWarps, 0);
+    std::vector<std::vector<int2>> lists(kw);
+    std::vector<int> load(kw, 0);
     int maxc = 0;
     for (int k = 0; k < nk; ++k) maxc = std::max(maxc, nch(k));
+    if ((size_t)(zero_chunk + 1) * 128 >= ((size_t)1 << 31)) { cra_set_error("ring table too large for the tensor-memory CCF schedule"); return 1; }
     for (int c = maxc; c >= 1; --c)
         for (int k = 0; k < nk; ++k) {
             if (nch(k) != c) continue;
             const int n2 = k & (N2 - 1), q = rquad[n2];
             int w = q;
-            for (int ww = q + 4; ww < kWarps; ww += 4) if (load[ww] < load[w]) w = ww;
-            for (int j = 0; j < c; ++j) lists[w].push_back((koff[k] + j) | ((j == c - 1) ? (1 << 23) : 0));
+            for (int ww = q + 4; ww < kw; ww += 4) if (load[ww] < load[w]) w = ww;
             const int kk = (N - k) & (N - 1);
             const int col0 = (ridx[n2] * N1 + (k >> L2)) * 2;
             const int col1 = (ridx[kk & (N2 - 1)] * N1 + (kk >> L2)) * 2;
-            flush[w].push_back(col0 | (col1 << 12) | ((k != 0 && k != N / 2) ? (1 << 24) : 0));
+            const int fl = col0 | (col1 << 12) | (1 << 24);
+            for (int j = 0; j < c; ++j) lists[w].push_back(make_int2((koff[k] + j) * 128, (j == c - 1) ? fl : 0));
             load[w] += c;
         }
-    static int h_items[kWarps][kMaxItems]; int h_n[kWarps];
-    static int h_flush[kWarps][kMaxFreq];
-    memset(h_items, 0, sizeof(h_items)); memset(h_flush, 0, sizeof(h_flush));
-    g_sched.istride = 0; g_sched.fstride = 0;
-    for (int w = 0; w < kWarps; ++w) {
-        if ((int)lists[w].size() > kMaxItems || (int)flush[w].size() > kMaxFreq || koff[nk] > 8191) {
-            cra_set_error("ring table too large for the tensor-memory CCF schedule"); return 1;
-        }
-        h_n[w] = (int)lists[w].size();
-        for (size_t i = 0; i < lists[w].size(); ++i) h_items[w][i] = lists[w][i];
-        for (size_t i = 0; i < flush[w].size(); ++i) h_flush[w][i] = flush[w][i];
-        g_sched.istride = std::max(g_sched.istride, (int)lists[w].size());
-        g_sched.fstride = std::max(g_sched.fstride, (int)flush[w].size());
+    TmSched* s = new TmSched();
+    s->kw = kw;
+    for (int w = 0; w < kw; ++w) {
+        while (lists[w].size() < 4 || (lists[w].size() & 3)) lists[w].push_back(make_int2(zero_chunk * 128, 0));
+        hdr.nit[w] = (int)lists[w].size();
+        s->istride = std::max(s->istride, (int)lists[w].size());
     }
-    CRA_CUDA(cudaStreamSynchronize(st));
-    CRA_CUDA(cudaMemcpyToSymbol(g_items, h_items, sizeof(h_items)));
-    CRA_CUDA(cudaMemcpyToSymbol(g_nitems, h_n, sizeof(h_n)));
-    CRA_CUDA(cudaMemcpyToSymbol(g_flush, h_flush, sizeof(h_flush)));
-    CRA_CUDA(cudaMemcpyToSymbol(g_res, h_res, sizeof(h_res)));
-    g_sched.nring = h.nring; g_sched.maxrin = h.maxrin; g_sched.dev = dev; g_sched.len = len;
+    std::vector<int2> flat((size_t)kw * s->istride, make_int2(zero_chunk * 128, 0));
+    for (int w = 0; w < kw; ++w) std::copy(lists[w].begin(), lists[w].end(), flat.begin() + (size_t)w * s->istride);
+    cudaError_t e = cudaMalloc(&s->d_items, flat.size() * sizeof(int2));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_hdr, sizeof(SchedHdr));
+    // stream-ordered copies (pageable source: staged by the runtime before the call returns), ordered before the kernels on st
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_items, flat.data(), flat.size() * sizeof(int2), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_hdr, &hdr, sizeof(SchedHdr), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        cra_set_error(std::string("tensor-memory CCF schedule: ") + cudaGetErrorString(e));
+        cudaFree(s->d_items); cudaFree(s->d_hdr); delete s; return 1;
+    }
+    *out = s;
     return 0;
 }
 
 template <int LOG2N>
 int launch_t(const unsigned char* spec, int nrows, const unsigned char* refspec, int R, size_t row_bytes,
-             const float2* twid, CraCand* cand, int ntile_n, const float2* norm, const float* tref, cudaStream_t st)
+             const float2* twid, CraCand* cand, int ntile_n, const float2* norm, const float* tref,
+             const CraRingTab& htab, const std::vector<int>& h_koff, void** slot, cudaStream_t st)
 {
     using S = TShape<LOG2N>;
-    const size_t smem = ((size_t)32 * S::PS + S::N) * sizeof(float2) + (size_t)kWarps * (g_sched.istride + g_sched.fstride) * sizeof(int);
-    static size_t configured = 0;
-    if (smem > configured) {
-        CRA_CUDA(cudaFuncSetAttribute(ccf_tm_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    constexpr int kThreads = S::KW * 32;
+    TmSched* sc = static_cast<TmSched*>(*slot);
+    if (!sc) {
+        if (build_schedule(htab, h_koff, S::KW, st, &sc)) return 1;
+        *slot = sc;
     }
+    const size_t smem = ((size_t)32 * S::PS + S::N) * sizeof(float2) + (size_t)S::KW * sc->istride * sizeof(int2);
+    if (cra_ensure_dyn_smem(reinterpret_cast<const void*>(&ccf_tm_kernel<LOG2N>), smem)) return 1;
     const int nquad = (R + 3) / 4;
     const long ncta_m = (nrows + 7) / 8;
     const long nblk = ncta_m * ntile_n;
     if (nblk <= 0) return 0;
     if (nblk > 2147483647L) { cra_set_error("ccf grid too large; lower row_batch"); return 1; }
-    static int resident = 0;                     // CTAs the device holds at once (2 per SM: TMEM and shared memory)
-    if (!resident) {
+    if (!sc->resident) {                         // CTAs the device holds at once (2 per SM: TMEM and shared memory)
         int dev = 0, nsm = 0, per = 0;
         CRA_CUDA(cudaGetDevice(&dev));
         CRA_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
@@ -491,18 +454,17 @@ int launch_t(const unsigned char* spec, int nrows, const unsigned char* refspec,
         CRA_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
         const int by_regs = regs_sm / (((fa.numRegs + 7) / 8 * 8) * kThreads);
         const int by_smem = (int)((size_t)smem_sm / (smem + fa.sharedSizeBytes + 1024));
-        per = std::max(per, std::min(std::min(by_regs, by_smem), 2));
+        per = std::max(per, std::min(std::min(by_regs, by_smem), S::PER_SM));
         if (getenv("CRA_TM_DEBUG")) fprintf(stderr, "ccf_tm: CTAs per SM %d (regs %d -> %d, smem -> %d)\n", per, fa.numRegs, by_regs, by_smem);
         if (getenv("CRA_TM_PER")) per = atoi(getenv("CRA_TM_PER"));
         if (per < 1) per = 1;
         if (per * S::COLS > 512) per = 512 / S::COLS;      // tensor memory: 512 columns per SM
-        resident = nsm * per;
+        sc->resident = nsm * per;
     }
-    const char* np = getenv("CRA_TM_PERSIST");
-    const long grid = (np && np[0] == '0') ? nblk : std::min<long>(nblk, resident);
-    if (getenv("CRA_TM_DEBUG")) fprintf(stderr, "ccf_tm: tiles %ld grid %ld resident %d smem %zu\n", nblk, grid, resident, smem);
+    const long grid = std::min<long>(nblk, sc->resident);
+    if (getenv("CRA_TM_DEBUG")) fprintf(stderr, "ccf_tm: tiles %ld grid %ld resident %d smem %zu\n", nblk, grid, sc->resident, smem);
     ccf_tm_kernel<LOG2N><<<(unsigned)grid, kThreads, smem, st>>>(spec, nrows, refspec, R, row_bytes, twid, cand, nquad, ntile_n,
-                                                                norm, tref, g_sched.istride, g_sched.fstride, nblk);
+                                                                norm, tref, sc->d_items, sc->d_hdr, sc->istride, nblk);
     CRA_CUDA(cudaGetLastError());
     return 0;
 }
@@ -521,18 +483,25 @@ int cra_ccf_tm_num_tiles(int R, int log2n)
     }
 }
 
+void cra_ccf_tm_sched_free(void* sched)
+{
+    TmSched* s = static_cast<TmSched*>(sched);
+    if (!s) return;
+    cudaFree(s->d_items); cudaFree(s->d_hdr);
+    delete s;
+}
+
 int cra_launch_ccf_tm(const unsigned char* spec, int nrows, const unsigned char* refspec, int R, const CraRingTab& htab,
                       const CraFragTab& frag, const std::vector<int>& h_koff, const float2* twid, CraCand* cand,
-                      int ntile_n, const float2* norm, const float* tref, cudaStream_t st)
+                      int ntile_n, const float2* norm, const float* tref, void** sched, cudaStream_t st)
 {
-    if (bind_schedule(htab, h_koff, st)) return 1;
     const size_t rb = cra_frag_row_bytes(frag.nch);
     switch (htab.log2n) {
-        case 5:  return launch_t<5>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, norm, tref, st);
-        case 6:  return launch_t<6>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, norm, tref, st);
-        case 7:  return launch_t<7>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, norm, tref, st);
-        case 8:  return launch_t<8>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, norm, tref, st);
-        case 9:  return launch_t<9>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, norm, tref, st);
+        case 5:  return launch_t<5>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, norm, tref, htab, h_koff, sched, st);
+        case 6:  return launch_t<6>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, norm, tref, htab, h_koff, sched, st);
+        case 7:  return launch_t<7>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, norm, tref, htab, h_koff, sched, st);
+        case 8:  return launch_t<8>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, norm, tref, htab, h_koff, sched, st);
+        case 9:  return launch_t<9>(spec, nrows, refspec, R, rb, twid, cand, ntile_n, norm, tref, htab, h_koff, sched, st);
         default: cra_set_error("tensor-memory CCF kernel: maxrin must be a power of two in [32, 512]"); return 1;
     }
 }

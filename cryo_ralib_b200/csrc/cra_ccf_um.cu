@@ -582,6 +582,9 @@ int bind_schedule(const CraRingTab& h, const std::vector<int>& koff, cudaStream_
     CRA_CUDA(cudaStreamSynchronize(st));
     CRA_CUDA(cudaMemcpyToSymbol(g_items, h_items, sizeof(h_items)));
     CRA_CUDA(cudaMemcpyToSymbol(g_nitems, h_n, sizeof(h_n)));
+    // the copies come from pageable memory on the legacy stream and the kernel runs on a non-blocking stream:
+    // make sure they have landed (diagnostic path; one-off per geometry and device)
+    CRA_CUDA(cudaDeviceSynchronize());
     g_sched.nring = h.nring; g_sched.maxrin = h.maxrin; g_sched.dev = dev; g_sched.len = len;
     g_sched.istride = istride; g_sched.lo = lo; g_sched.hi = hi;
     return 0;
@@ -610,11 +613,7 @@ int cra_launch_ccf_um(const unsigned char* spec, int nrows, const unsigned char*
     if (bind_schedule(htab, h_koff, st)) return 1;
     const size_t smem = (size_t)kPipes * kStages * kStageBytes + (size_t)(N2 - kYT) * N1 * 128 * sizeof(float2) + N * sizeof(float2) +
                         (size_t)kPipes * g_sched.istride * sizeof(int);
-    static size_t configured = 0;
-    if (smem > configured) {
-        CRA_CUDA(cudaFuncSetAttribute(ccf_um_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    if (cra_ensure_dyn_smem(reinterpret_cast<const void*>(&ccf_um_kernel), smem)) return 1;
     const long ncta_m = (nrows + 31) / 32;
     const long nblk = ncta_m * ntile_n;
     if (nblk <= 0) return 0;

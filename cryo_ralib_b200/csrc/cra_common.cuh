@@ -26,6 +26,7 @@
 #include <string>
 #include <vector>
 #include "../../include/cryo_ralib.h"
+#include <nvtx3/nvToolsExt.h>
 
 #define CRA_MAX_RINGS 192
 
@@ -97,6 +98,7 @@ struct CraRowMap {             // how rows of the current batch map to particles
     int              np;
     int              nrows;
     int              p0;         // slot of batch-local particle 0 in the resident stack
+    const float*     dc;         // [max_particles] in-mask mean each resident image still carries (may be null)
     float            step;
 };
 
@@ -116,7 +118,9 @@ __host__ __device__ __forceinline__ size_t cra_spec_idx(int coff, int half, int 
 // order instead: the 32 bytes of quad t are 8 words  hi{re s0s1, im s0s1, re s2s3, im s2s3} then
 // lo{same}  (s0..s3 = slots 16c+4t..+3, first slot in the low half-word), so that one 256-bit load
 // is a thread's A fragment with the hi and lo registers already in mma operand order.
-// Chunks are stored k-major: chunk index koff[k] + c; a row is nch * 128 bytes.
+// Chunks are stored k-major: chunk index koff[k] + c; a row is (nch + 1) * 128 bytes: chunk nch is never
+// written and stays ZERO (the buffers are cleared at allocation) -- the contraction pads its per-warp
+// work lists to whole groups with it, so the inner loop has no tail conditionals.
 //
 // Deferred Normalize_ring: the row kernels may store the spectrum of the RAW polar image and put
 // (avg, 1/sigma) of Normalize_ring into norm[row].  (x - avg)/sigma only changes the DC bin of each
@@ -133,9 +137,13 @@ struct CraFragTab {
     int unit_rows;               // 1: particle rows use the reference layout [re unit | im unit] (tcgen05 kernel,
                                  // a unit = one UMMA core-matrix row); 0: the mma.sync A-operand order above
 };
-__host__ __device__ __forceinline__ size_t cra_frag_row_bytes(int nch) { return (size_t)nch * 128; }
+__host__ __device__ __forceinline__ size_t cra_frag_row_bytes(int nch) { return (size_t)(nch + 1) * 128; }
 
 struct CraCand { float v; int code; };   // code = iref*8192 + mirror*4096 + j   (j = 1-based lag index)
+
+// NVTX range around a host-side phase (the reference marks the same phases from Python with
+// cupy.cuda.nvtx.RangePush/Pop, test_mref_gpu_align.py:89, :329, :416, :448); free when no tool is attached
+struct CraNvtx { explicit CraNvtx(const char* name) { nvtxRangePushA(name); } ~CraNvtx() { nvtxRangePop(); } };
 
 // error plumbing -------------------------------------------------------------
 void cra_set_error(const std::string& msg);
@@ -144,8 +152,12 @@ void cra_set_error(const std::string& msg);
         cra_set_error(std::string(#call) + ": " + cudaGetErrorString(e__) + " @" +   \
                       __FILE__ + ":" + std::to_string(__LINE__)); return 1; } } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE function attribute: raise it for `func` on the
+// current device when `bytes` exceeds what was set there before (thread-safe; cra_api.cu)
+int cra_ensure_dyn_smem(const void* func, size_t bytes);
+
 // launchers (each defined in its own .cu; all asynchronous on `st`) ----------
-int cra_launch_mask_normalize(float* imgs, int n, int nx, const float* mask, int mode, cudaStream_t st);
+int cra_launch_mask_normalize(float* imgs, int n, int nx, const float* mask, int mode, float* dc_out, cudaStream_t st);
 // particle rows described by map -> spec[row]; references -> refspec (weights applied)
 // twid_fwd[j] = exp(-2 pi i j / maxrin), j < maxrin
 int cra_polar_rows_per_block();
@@ -174,9 +186,11 @@ int cra_ccf_mma_num_tiles(int R, int log2n);
 // the same contraction with W staged in tensor memory, two CTAs per SM (cra_ccf_tm.cu)
 bool cra_ccf_tm_supported(int log2n);
 int cra_ccf_tm_num_tiles(int R, int log2n);
+// *sched: the context's work lists (built on the first launch, released with cra_ccf_tm_sched_free)
 int cra_launch_ccf_tm(const unsigned char* spec, int nrows, const unsigned char* refspec, int R, const CraRingTab& htab,
                       const CraFragTab& frag, const std::vector<int>& h_koff, const float2* twid, CraCand* cand,
-                      int ntile_n, const float2* norm, const float* tref, cudaStream_t st);
+                      int ntile_n, const float2* norm, const float* tref, void** sched, cudaStream_t st);
+void cra_ccf_tm_sched_free(void* sched);
 // the contraction on tcgen05.mma, W streamed through tensor memory class by class (cra_ccf_um.cu; maxrin 256)
 bool cra_ccf_um_supported(int log2n);
 int cra_ccf_um_num_tiles(int R);
@@ -188,11 +202,10 @@ int cra_launch_ccf_um(const unsigned char* spec, int nrows, const unsigned char*
 int cra_launch_ccf(const float* spec, int nrows, const float* refspec, int R, const CraRingTab* tab,
                    const CraRingTab& htab, const float2* twid, CraCand* cand, int ntile_n, cudaStream_t st);
 int cra_ccf_tile_n();
-int cra_launch_ccf_rr(const float* spec, int nrows, const float* refspec, int R, const CraRingTab& htab,
-                      const float2* twid, CraCand* cand, int ntile_n, cudaStream_t st, bool* ran);
+// twd: [maxrin] (cos, sin)(2 pi j / maxrin) in double; norm / tref: deferred Normalize_ring (fragment format), else null
 int cra_launch_finalize(const float* spec, const float* refspec, int R, const CraRingTab* tab, const CraRingTab& htab,
                         const CraCand* cand, int ntile_n, CraRowMap map, CraResult* out, int fmt, const CraFragTab& frag,
-                        cudaStream_t st);
+                        const double2* twd, const float2* norm, const float* tref, cudaStream_t st);
 int cra_launch_ccf_curves(const float* spec, int row, const float* refspec, int ref, const CraRingTab* tab,
                           const CraRingTab& htab, float* q, float* t, int fmt, const CraFragTab& frag, cudaStream_t st);
 void cra_ccf_twiddles(int log2n, std::vector<float2>& tw);

@@ -383,7 +383,7 @@ polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __r
         __syncthreads();
         const int nch = frag.nch, nring = tab->nring;
         const int per_row = nch * 4;
-        unsigned char* const base = reinterpret_cast<unsigned char*>(spec) + (size_t)ck.row0 * nch * 128;
+        unsigned char* const base = reinterpret_cast<unsigned char*>(spec) + (size_t)ck.row0 * cra_frag_row_bytes(nch);
         for (int it = tid; it < per_row * ck.nrow; it += kPolarThreads) {
             const int r = it / per_row, u = it - r * per_row;
             const int gc = u >> 2, t = u & 3;
@@ -408,7 +408,7 @@ polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __r
                 }
                 re[j] = v.x; im[j] = v.y;
             }
-            uint4* o = reinterpret_cast<uint4*>(base + (size_t)r * nch * 128 + (size_t)gc * 128 + t * 32);
+            uint4* o = reinterpret_cast<uint4*>(base + (size_t)r * cra_frag_row_bytes(nch) + (size_t)gc * 128 + t * 32);
             uint4 a, b;
             if (MODE == 1 || frag.unit_rows) {           // reference (B operand) layout: [re unit | im unit]
                 a = split_bf16x4(re[0], re[1], re[2], re[3]);
@@ -430,9 +430,11 @@ polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __r
     }
 }
 
-// normalize.mask: mode 0 -> x - mean_mask ; mode 1 -> (x - mean_mask)/sigma_mask(n-1)
+// normalize.mask: mode 0 -> x - mean_mask ; mode 1 -> (x - mean_mask)/sigma_mask(n-1) ; mode 2 -> image untouched.
+// dc_out (optional): the in-mask mean the image still carries afterwards (mode 2: the mean; else 0) -- the grouped
+// row kernel removes it before the ring FFTs when Normalize_ring is on (cra_polar_grp.cu).
 __global__ void __launch_bounds__(256)
-mask_normalize_kernel(float* __restrict__ imgs, int npix, const float* __restrict__ mask, int mode)
+mask_normalize_kernel(float* __restrict__ imgs, int npix, const float* __restrict__ mask, int mode, float* __restrict__ dc_out)
 {
     float* img = imgs + (size_t)blockIdx.x * npix;
     double sum = 0.0, sq2 = 0.0; int cnt = 0;
@@ -452,10 +454,12 @@ mask_normalize_kernel(float* __restrict__ imgs, int npix, const float* __restric
         double a = 0, b = 0; int c = 0;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += s_a[w]; b += s_b[w]; c += s_c[w]; }
         s_mean = (c == 0) ? 0.f : (float)a / (float)c;
-        s_sig = (mode == 0) ? 1.0f : sqrtf((float)((b - a * a / c) / (c - 1)));
+        s_sig = (mode != 1) ? 1.0f : sqrtf((float)((b - a * a / c) / (c - 1)));
     }
     __syncthreads();
     const float mean = s_mean, sig = s_sig;
+    if (dc_out && threadIdx.x == 0) dc_out[blockIdx.x] = (mode == 2) ? mean : 0.f;
+    if (mode == 2) return;
     for (int i = threadIdx.x; i < npix; i += blockDim.x) img[i] = (img[i] - mean) / sig;
 }
 
@@ -475,11 +479,7 @@ int launch_polar_f(const float* images, int nx, const CraRingTab* tab, const Cra
 {
     if (nblocks <= 0) return 0;
     size_t smem = polar_smem_bytes<RPB>(nx, htab);
-    static size_t configured = 0;
-    if (smem > configured) {
-        CRA_CUDA(cudaFuncSetAttribute(polar_fft_kernel<MODE, RPB, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    if (cra_ensure_dyn_smem(reinterpret_cast<const void*>(&polar_fft_kernel<MODE, RPB, FMT>), smem)) return 1;
     polar_fft_kernel<MODE, RPB, FMT><<<nblocks, kPolarThreads, smem, st>>>(images, nx, tab, samp, sampw, twid, items, map,
                                                                           cx, cy, normalize_ring, spec, frag, norm, tref);
     CRA_CUDA(cudaGetLastError());
@@ -506,10 +506,10 @@ int cra_polar_rows_per_block() { return CRA_POLAR_RPB; }
 // dynamic shared memory the general kernel needs for one row (references, test entries)
 size_t cra_polar_general_smem(int nx, const CraRingTab& htab) { return polar_smem_bytes<1>(nx, htab); }
 
-int cra_launch_mask_normalize(float* imgs, int n, int nx, const float* mask, int mode, cudaStream_t st)
+int cra_launch_mask_normalize(float* imgs, int n, int nx, const float* mask, int mode, float* dc_out, cudaStream_t st)
 {
     if (n <= 0) return 0;
-    mask_normalize_kernel<<<n, 256, 0, st>>>(imgs, nx * nx, mask, mode);
+    mask_normalize_kernel<<<n, 256, 0, st>>>(imgs, nx * nx, mask, mode, dc_out);
     CRA_CUDA(cudaGetLastError());
     return 0;
 }

@@ -30,7 +30,7 @@ using crafft::fft_reg;
 
 constexpr int kThreads = 256;
 constexpr int RMAX = CRA_GRP_RMAX;
-constexpr int kFragCap = 24;    // per warp and phase; beyond it a sample keeps its shared-weight value (<0.1 expected)
+constexpr int kFragCap = 24;    // per warp and phase; beyond it the lane repairs its sample itself (exact either way)
 
 __device__ __forceinline__ float warp_sum(float v)
 {
@@ -107,6 +107,38 @@ __device__ __forceinline__ void pass_b(float2* __restrict__ z, int ka)
 
 // floor(w / d) for w * magic < 2^32, magic = floor(2^24 / d) + 1 (host side, exact for the ranges used here)
 __device__ __forceinline__ int fastdiv(int w, int magic) { return (int)(((unsigned)w * (unsigned)magic) >> 24); }
+
+// One fragile sample (code = q * 4 + m) of block row r, positioned exactly as the reference does it
+// (x = offset + the row's own centre) and interpolated with quadri's own expression; the Normalize_ring
+// sums of the row are corrected through s_fix.
+__device__ __forceinline__ void repair_sample(int code, int r, const float4* __restrict__ samp, const int4* s_ring,
+                                              const float2* s_rowc, const float* s_img, int pitch, float* s_buf,
+                                              int stride, float* s_fix)
+{
+    const int q = code >> 2, m = code & 3;
+    const float4 e = __ldg(samp + q);
+    const int4 rp = s_ring[__float_as_int(e.z)];
+    const float wn = __int_as_float(rp.w);
+    const float fx = (m == 0) ? e.x : (m == 1) ? e.y : (m == 2) ? -e.x : -e.y;
+    const float fy = (m == 0) ? e.y : (m == 1) ? -e.x : (m == 2) ? -e.y : e.x;
+    const int j = __float_as_int(e.w) + m * rp.z, pp = j >> 1;
+    const int sl = 2 * (rp.x + pp + (pp >> rp.y)) + (j & 1);
+    const float2 c = s_rowc[r];
+    const float X = fx + c.x, Y = fy + c.y;
+    const int ix = (int)X, iy = (int)Y;
+    const float dx = X - (float)ix, dy = Y - (float)iy;
+    const float* p = s_img + iy * pitch + ix;
+    const float f0 = p[0];
+    const float c1 = p[1] - f0, c2 = (c1 - f0 + p[-1]) * 0.5f;
+    const float c3 = p[pitch] - f0, c4 = (c3 - f0 + p[-pitch]) * 0.5f;
+    const float c5 = p[pitch + 1] - f0 - c1 - c3;
+    const float v = f0 + dx * (c1 + (dx - 1.0f) * c2 + dy * c5) + dy * (c3 + (dy - 1.0f) * c4);
+    float* dst = s_buf + r * stride;
+    const float old = dst[sl];
+    dst[sl] = v;
+    atomicAdd(&s_fix[2 * r], (v - old) * wn);
+    atomicAdd(&s_fix[2 * r + 1], (v * v - old * old) * wn);
+}
 
 __global__ void __launch_bounds__(kThreads, 2)
 polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* __restrict__ tab,
@@ -190,11 +222,15 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
     {
         // padded (Y, X), 0 <= X, Y <= nx+1, holds pixel ((Y-1) mod nx, (X-1) mod nx): 1-based pixel (i, j) sits at (j, i)
         const float* img = images + (size_t)(map.p0 + s_blk[0]) * npix;
+        // A particle uploaded without normalize.mask still carries its in-mask mean.  Normalize_ring cancels any
+        // constant exactly in exact arithmetic, but here it is deferred past the split-bf16 contraction, where a large
+        // ring DC term would cost digits: remove the constant up front.
+        const float dcv = (normalize_ring && map.dc) ? __ldg(map.dc + map.p0 + s_blk[0]) : 0.f;
         if ((npix & 3) == 0) {                 // interior: the image as one stream of 128-bit loads
             const float4* g4 = reinterpret_cast<const float4*>(img);
             for (int i = tid; i < (npix >> 2); i += kThreads) {
                 const float4 v = __ldg(g4 + i);
-                const float e[4] = {v.x, v.y, v.z, v.w};
+                const float e[4] = {v.x - dcv, v.y - dcv, v.z - dcv, v.w - dcv};
                 int y = (4 * i) / nx, x = 4 * i - y * nx;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -203,7 +239,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                 }
             }
         } else {
-            for (int i = tid; i < npix; i += kThreads) { const int y = i / nx; s_img[(y + 1) * pitch + (i - y * nx) + 1] = __ldg(img + i); }
+            for (int i = tid; i < npix; i += kThreads) { const int y = i / nx; s_img[(y + 1) * pitch + (i - y * nx) + 1] = __ldg(img + i) - dcv; }
         }
         for (int b = tid; b < 2 * pitch + 2 * nx; b += kThreads) {      // the periodic border, straight from global
             int Y, X;
@@ -211,7 +247,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
             else { const int c = b - 2 * pitch; Y = 1 + (c >> 1); X = (c & 1) ? nx + 1 : 0; }
             const int sy = (Y == 0) ? nx - 1 : ((Y == nx + 1) ? 0 : Y - 1);
             const int sx = (X == 0) ? nx - 1 : ((X == nx + 1) ? 0 : X - 1);
-            s_img[Y * pitch + X] = __ldg(img + sy * nx + sx);
+            s_img[Y * pitch + X] = __ldg(img + sy * nx + sx) - dcv;
         }
     }
     const float bx = s_base[0], by = s_base[1];
@@ -282,6 +318,9 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                     if (fragile & (1 << m)) {
                         const int at = atomicAdd(&s_nfrag[tid >> 5], 1);
                         if (at < kFragCap) s_frag[tid >> 5][at] = q * 4 + m;
+                        else                // queue full (an integer or half-integer centre puts whole rings on cell
+                            for (int r = 0; r < nr; ++r)    // boundaries): this lane repairs its own sample right away
+                                repair_sample(q * 4 + m, r, samp, s_ring, s_rowc, s_img, pitch, s_buf, stride, s_fix);
                     }
             }
         }
@@ -293,29 +332,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
             const int nf = min(s_nfrag[wid], kFragCap);
             for (int x = tid & 31; x < nf * nr; x += 32) {
                 const int en = x / nr, r = x - en * nr;
-                const int code = s_frag[wid][en], q = code >> 2, m = code & 3;
-                const float4 e = __ldg(samp + q);
-                const int4 rp = s_ring[__float_as_int(e.z)];
-                const float wn = __int_as_float(rp.w);
-                const float fx = (m == 0) ? e.x : (m == 1) ? e.y : (m == 2) ? -e.x : -e.y;
-                const float fy = (m == 0) ? e.y : (m == 1) ? -e.x : (m == 2) ? -e.y : e.x;
-                const int j = __float_as_int(e.w) + m * rp.z, pp = j >> 1;
-                const int sl = 2 * (rp.x + pp + (pp >> rp.y)) + (j & 1);
-                const float2 c = s_rowc[r];
-                const float X = fx + c.x, Y = fy + c.y;
-                const int ix = (int)X, iy = (int)Y;
-                const float dx = X - (float)ix, dy = Y - (float)iy;
-                const float* p = s_img + iy * pitch + ix;
-                const float f0 = p[0];
-                const float c1 = p[1] - f0, c2 = (c1 - f0 + p[-1]) * 0.5f;
-                const float c3 = p[pitch] - f0, c4 = (c3 - f0 + p[-pitch]) * 0.5f;
-                const float c5 = p[pitch + 1] - f0 - c1 - c3;
-                const float v = f0 + dx * (c1 + (dx - 1.0f) * c2 + dy * c5) + dy * (c3 + (dy - 1.0f) * c4);
-                float* dst = s_buf + r * stride;
-                const float old = dst[sl];
-                dst[sl] = v;
-                atomicAdd(&s_fix[2 * r], (v - old) * wn);
-                atomicAdd(&s_fix[2 * r + 1], (v * v - old * old) * wn);
+                repair_sample(s_frag[wid][en], r, samp, s_ring, s_rowc, s_img, pitch, s_buf, stride, s_fix);
             }
         }
         __syncthreads();
@@ -408,7 +425,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
         {
             const int upr = P.upr;
             const int nset = __ldg(&plan.phases[ph].nsetD[nr]);
-            const size_t rb = (size_t)frag.nch * 128;
+            const size_t rb = cra_frag_row_bytes(frag.nch);
             for (int x = tid; x < upr * nset; x += kThreads) {
                 const int set = fastdiv(x, P.magicD);
                 int k = x - set * upr, u = P.u0;
@@ -507,11 +524,7 @@ int cra_launch_polar_group(const float* images, int nx, const CraRingTab* tab, c
 {
     if (map.nchunks <= 0) return 0;
     const size_t smem = cra_polar_group_smem(nx, htab.maxrin, plan);
-    static size_t configured = 0;
-    if (smem > configured) {
-        CRA_CUDA(cudaFuncSetAttribute(polar_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    if (cra_ensure_dyn_smem(reinterpret_cast<const void*>(&polar_group_kernel), smem)) return 1;
     polar_group_kernel<<<map.nchunks, kThreads, smem, st>>>(images, nx, tab, samp, twid, items, plan, map, normalize_ring,
                                                            reinterpret_cast<unsigned char*>(spec), frag, norm);
     CRA_CUDA(cudaGetLastError());

@@ -130,11 +130,7 @@ int cra_launch_tanl_filter(float* imgs, int n, int nx, float fl, float aa, cudaS
     CRA_CUDA(cudaGetDevice(&dev));
     CRA_CUDA(cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     if (smem > (size_t)lim) { cra_set_error("tangent filter: image too large for the shared-memory transform"); return 1; }
-    static size_t configured = 0;
-    if (smem > configured) {
-        CRA_CUDA(cudaFuncSetAttribute(tanl_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    if (cra_ensure_dyn_smem(reinterpret_cast<const void*>(&tanl_filter_kernel), smem)) return 1;
     tanl_filter_kernel<<<n, 256, smem, st>>>(imgs, nx, fl, aa);
     CRA_CUDA(cudaGetLastError());
     return 0;

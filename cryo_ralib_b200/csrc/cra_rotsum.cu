@@ -146,11 +146,7 @@ int cra_launch_rotsum(const float* images, int nx, int p0, int n, const float4* 
 {
     if (n <= 0) return 0;
     const size_t smem = (((size_t)nx * nx + 3) & ~(size_t)3) * sizeof(float);
-    static size_t configured = 0;
-    if (smem > configured) {
-        CRA_CUDA(cudaFuncSetAttribute(rotsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    if (cra_ensure_dyn_smem(reinterpret_cast<const void*>(&rotsum_kernel), smem)) return 1;
     rotsum_kernel<<<n, 256, smem, st>>>(images, nx, p0, params, iref, global_offset, sums, counts, out_images);
     CRA_CUDA(cudaGetLastError());
     return 0;

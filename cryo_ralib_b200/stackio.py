@@ -7,27 +7,39 @@ import struct
 import numpy as np
 
 
-def read_stack(path):
+def _open_stack(path):
+    """Memory-mapped view [n][ny][nx] of a stack file (nothing is read until it is sliced)."""
     ext = os.path.splitext(path)[1].lower()
     if ext == ".npy":
-        a = np.load(path)
+        a = np.load(path, mmap_mode="r")
     elif ext in (".mrc", ".mrcs", ".st"):
         with open(path, "rb") as f:
             hdr = f.read(1024)
-            nx, ny, nz, mode = struct.unpack("<4i", hdr[:16])
-            nsymbt = struct.unpack("<i", hdr[92:96])[0]
-            if mode != 2:
-                raise ValueError("only MRC mode 2 (float32) stacks are supported, got mode %d" % mode)
-            f.seek(1024 + nsymbt)
-            a = np.frombuffer(f.read(4 * nx * ny * nz), "<f4").reshape(nz, ny, nx)
+        nx, ny, nz, mode = struct.unpack("<4i", hdr[:16])
+        nsymbt = struct.unpack("<i", hdr[92:96])[0]
+        if mode != 2:
+            raise ValueError("only MRC mode 2 (float32) stacks are supported, got mode %d" % mode)
+        a = np.memmap(path, dtype="<f4", mode="r", offset=1024 + nsymbt, shape=(nz, ny, nx))
     else:
         raise ValueError("unsupported stack format '%s' (use .npy or .mrcs)" % ext)
-    a = np.ascontiguousarray(a, np.float32)
     if a.ndim == 2:
         a = a[None]
     if a.ndim != 3 or a.shape[1] != a.shape[2]:
         raise ValueError("stack must be [n][nx][nx] with square images")
     return a
+
+
+def stack_shape(path):
+    """(number of images, nx) without reading the pixel data."""
+    a = _open_stack(path)
+    return int(a.shape[0]), int(a.shape[2])
+
+
+def read_stack(path, start=None, stop=None):
+    """Images [start, stop) of the stack as a contiguous float32 array.  Each rank of a multi-GPU run reads only its
+    own share (the reference ships images between ranks instead, test_mref_gpu_align.py:1380-1415)."""
+    a = _open_stack(path)
+    return np.ascontiguousarray(a[slice(start, stop)], np.float32)
 
 
 def write_stack(path, a):

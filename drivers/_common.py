@@ -33,27 +33,35 @@ def add_alignment_flags(p, reffree=False):
     p.add_argument("--gpu_info", action="store_true", help="print GPU information and exit")
 
 
-def init_distributed():
-    """Returns (comm, rank, world, device index)."""
+def resolve_device(args, local):
+    """CUDA device of this rank: entry LOCAL_RANK of --gpu_devices (test_mref_gpu_align.py:1155), else LOCAL_RANK."""
+    if getattr(args, "gpu_devices", ""):
+        ids = [int(x) for x in args.gpu_devices.split(",") if x != ""]
+        return ids[local % len(ids)]
+    return local
+
+
+def init_distributed(args=None):
+    """Returns (comm, rank, world, device index).  The device is resolved BEFORE the process group is bound, so the
+    NCCL communicator, torch's current device and the engine all sit on the same GPU (--gpu_devices included)."""
     from cryo_ralib_b200.mref import LocalComm, TorchComm
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    device = resolve_device(args, local)
     if world > 1:
         import torch
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        return TorchComm(), rank, world, local
-    return LocalComm(), 0, 1, local
+        torch.cuda.set_device(device)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", device))
+        return TorchComm(), rank, world, device
+    return LocalComm(), 0, 1, device
 
 
-def pick_device(args, local):
-    if args.gpu_devices:
-        ids = [int(x) for x in args.gpu_devices.split(",") if x != ""]
-        return ids[local % len(ids)]
-    return local
+def pick_device(args, device):
+    """Kept for the drivers' call sites: init_distributed(args) already resolved the device."""
+    return device
 
 
 class Log(object):

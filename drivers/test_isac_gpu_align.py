@@ -35,7 +35,7 @@ def main(argv=None):
     if args.gpu_info:
         load_library().print_gpu_info(0)
         return 0
-    comm, rank, world, local = init_distributed()
+    comm, rank, world, local = init_distributed(args)
     if rank == 0:
         if os.path.exists(args.outdir):
             raise SystemExit("Output directory exists, please change the name and restart the program")
@@ -44,10 +44,11 @@ def main(argv=None):
         import torch.distributed as dist
         dist.barrier()
     log = Log(args.outdir, rank)
-    images = stackio.read_stack(args.stack)
+    P, nx = stackio.stack_shape(args.stack)
+    s, e = al.mpi_start_end(P, world, rank)
+    images = stackio.read_stack(args.stack, s, e)          # this rank's share only (memory-mapped read)
     refs = stackio.read_stack(args.refstack)
     cls = np.loadtxt(args.classes, dtype=np.int64).reshape(-1)
-    P, nx = images.shape[0], images.shape[-1]
     if cls.shape[0] != P:
         raise SystemExit("classes file has %d entries for %d particles" % (cls.shape[0], P))
     if cls.min() < 0 or cls.max() >= refs.shape[0]:
@@ -58,7 +59,6 @@ def main(argv=None):
     maxit = args.maxit if args.maxit > 0 else 4
     if ou + max(xr, yr) > (nx - 1) // 2:
         raise SystemExit("Shift or radius is too large - particle crosses image boundary")
-    s, e = al.mpi_start_end(P, world, rank)
     filt = (args.fl, args.aa) if args.fl > 0 else None
     log.add("ref_free_alignment_2D: %d particles %dx%d in %d classes, ou=%d xr=%g yr=%g ts=%g maxit=%d filter=%s, %d GPU(s)"
             % (P, nx, nx, refs.shape[0], ou, xr, yr, ts, maxit, filt, world))
@@ -69,7 +69,7 @@ def main(argv=None):
             dt = time.time() - t0[0]; t0[0] = time.time()
             log.add("Pass #%4d   %.3f s   mean peak = %15.8e" % (it + 1, dt, float(np.mean(info["peak"]))))
 
-    params, new_refs, hist = ref_free_alignment_2d(images[s:e], cls[s:e], refs, ir=args.ir, ou=ou, rs=args.rs, xr=xr, yr=yr,
+    params, new_refs, hist = ref_free_alignment_2d(images, cls[s:e], refs, ir=args.ir, ou=ou, rs=args.rs, xr=xr, yr=yr,
                                                    ts=ts, maxit=maxit, filt=filt, comm=comm, global_offset=s,
                                                    device=pick_device(args, local), on_iteration=on_iteration)
     if world > 1:

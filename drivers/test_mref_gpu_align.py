@@ -34,7 +34,7 @@ def main(argv=None):
         raise SystemExit("user masks are not on the accelerated path; the default model_circle(ou) mask is used")
     if args.function != "ref_ali2d":
         raise SystemExit("only --function=ref_ali2d is supported")
-    comm, rank, world, local = init_distributed()
+    comm, rank, world, local = init_distributed(args)
     if rank == 0:
         if os.path.exists(args.outdir):
             raise SystemExit("Output directory exists, please change the name and restart the program")
@@ -43,15 +43,15 @@ def main(argv=None):
         import torch.distributed as dist
         dist.barrier()
     log = Log(args.outdir, rank)
-    images = stackio.read_stack(args.stack)
+    P, nx = stackio.stack_shape(args.stack)
+    s, e = al.mpi_start_end(P, world, rank)
+    images = stackio.read_stack(args.stack, s, e)          # this rank's share only (memory-mapped read)
     refs = stackio.read_stack(args.refstack)
-    P, nx = images.shape[0], images.shape[-1]
     xr = first_of(args.xr); yr = first_of(args.yr) if first_of(args.yr) >= 0 else xr; ts = first_of(args.ts)
     ou = args.ou if args.ou != -1 else nx // 2 - 2
     maxit = args.maxit if args.maxit > 0 else 10
     if ou + max(xr, yr) > (nx - 1) // 2:
         log.add("note: ou + range exceeds (nx-1)//2; windows are clipped per particle by search_range (test_mref.py:195-198)")
-    s, e = al.mpi_start_end(P, world, rank)
     log.add("mref_ali2d_gpu: %d particles %dx%d, %d references, ir=%d ou=%d rs=%d xr=%g yr=%g ts=%g center=%d maxit=%d, %d GPU(s)"
             % (P, nx, nx, refs.shape[0], args.ir, ou, args.rs, xr, yr, ts, args.center, maxit, world))
 
@@ -62,13 +62,13 @@ def main(argv=None):
             stackio.write_stack(os.path.join(args.outdir, "aqm%03d.mrcs" % it), new_refs)
             dt = time.time() - t0[0]; t0[0] = time.time()
             st = info.get("stats", {})
-            log.add("ITERATION #%3d   %.3f s   %.3e alignments/s (device)   filter cut-off %.3f fall-off %.3f"
-                    % (it + 1, dt, (st.get("alignments", 0) * world) / max(st.get("ms_total", 0) * 1e-3, 1e-9) if st else 0.0,
+            log.add("ITERATION #%3d   %.3f s   %.3e alignments/s (whole iteration, wall clock)   filter cut-off %.3f fall-off %.3f"
+                    % (it + 1, dt, (st.get("alignments", 0) * world) / max(dt, 1e-9) if st else 0.0,
                        info["filter"][0], info["filter"][1]))
             for j, c in enumerate(info["counts"]):
                 log.add("   group #%3d   number of particles = %7d" % (j, int(c)))
 
-    params, assign, new_refs, hist = mref_ali2d(images[s:e], refs, ir=args.ir, ou=ou, rs=args.rs, xr=xr, yr=yr, ts=ts,
+    params, assign, new_refs, hist = mref_ali2d(images, refs, ir=args.ir, ou=ou, rs=args.rs, xr=xr, yr=yr, ts=ts,
                                                 center=args.center, maxit=maxit, rand_seed=args.rand_seed, comm=comm,
                                                 total_particles=P, global_offset=s, device=pick_device(args, local),
                                                 on_iteration=on_iteration)

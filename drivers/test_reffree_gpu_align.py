@@ -33,7 +33,7 @@ def main(argv=None):
         return 0
     if args.maskfile:
         raise SystemExit("user masks are not on the accelerated path; the default model_circle(ou) mask is used")
-    comm, rank, world, local = init_distributed()
+    comm, rank, world, local = init_distributed(args)
     if rank == 0:
         if os.path.exists(args.outdir):
             raise SystemExit("Output directory exists, please change the name and restart the program")
@@ -42,8 +42,9 @@ def main(argv=None):
         import torch.distributed as dist
         dist.barrier()
     log = Log(args.outdir, rank)
-    images = stackio.read_stack(args.stack)
-    P, nx = images.shape[0], images.shape[-1]
+    P, nx = stackio.stack_shape(args.stack)
+    s, e = al.mpi_start_end(P, world, rank)
+    images = stackio.read_stack(args.stack, s, e)          # this rank's share only (memory-mapped read)
     from cryo_ralib_b200.mref import search_schedule
     # the whole "--xr 4 2 1 --ts 2 1 0.5" schedule (Sphire ali2d_base); --first_step_only reproduces the
     # reference driver, which pins N_step = 0 (test_reffree.py:310, :686)
@@ -55,7 +56,6 @@ def main(argv=None):
     maxit = args.maxit if args.maxit > 0 else 10
     if ou + max(max(xr), max(yr)) > (nx - 1) // 2:
         raise SystemExit("Shift or radius is too large - particle crosses image boundary")   # test_reffree.py:603
-    s, e = al.mpi_start_end(P, world, rank)
     log.add("ali2d_base: %d particles %dx%d, ir=%d ou=%d rs=%d xr=%s yr=%s ts=%s center=%d maxit=%d per step, %d GPU(s)"
             % (P, nx, nx, args.ir, ou, args.rs, xr, yr, ts, args.center, maxit, world))
     raw, filt = [], []
@@ -68,7 +68,7 @@ def main(argv=None):
             log.add("Iteration #%4d   %.3f s   Criterion = %15.8e   Average center x = %10.3f y = %10.3f"
                     % (it + 1, dt, info["criterion"], info["cs"][0], info["cs"][1]))
 
-    params, tavg, hist = ali2d_base(images[s:e], ir=args.ir, ou=ou, rs=args.rs, xr=xr, yr=yr, ts=ts, center=args.center,
+    params, tavg, hist = ali2d_base(images, ir=args.ir, ou=ou, rs=args.rs, xr=xr, yr=yr, ts=ts, center=args.center,
                                     maxit=maxit, comm=comm, total_particles=P, global_offset=s,
                                     device=pick_device(args, local), on_iteration=on_iteration)
     if world > 1:
