@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libcryo_ralib.so")
-SOURCES = ["cra_api.cu", "cra_polar.cu", "cra_polar_grp.cu", "cra_ccf.cu", "cra_ccf_mma.cu", "cra_ccf_tm.cu", "cra_ccf_um.cu", "cra_rotsum.cu", "cra_refavg.cu", "cra_compat.cu", "cra_host.cu"]
+SOURCES = ["cra_api.cu", "cra_polar.cu", "cra_polar_grp.cu", "cra_ccf.cu", "cra_ccf_mma.cu", "cra_ccf_tm.cu", "cra_ccf_um.cu", "cra_rotsum.cu", "cra_refavg.cu", "cra_refupdate.cu", "cra_compat.cu", "cra_host.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 EXTRA = os.environ.get("CRA_NVCC_EXTRA", "").split()
 FLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

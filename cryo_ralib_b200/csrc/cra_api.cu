@@ -85,6 +85,12 @@ struct CraCtx {
     int last_rows = 0, last_group = 0;   // rows / kernel of the last batch (cra_batch_row_spectrum)
     float2* d_norm = nullptr;    // [row_batch] deferred Normalize_ring (avg, 1/sigma), cra_common.cuh
     float* d_tref = nullptr;     // [max_refs]  sum_rings len * weighted reference DC
+    // device reference update (cra_refupdate.cu), allocated on first use
+    short* d_shell = nullptr;    // [nx][nx/2+1] fsc shell of a half-complex coefficient, -1 = skipped
+    int nsh = 0;                 // shells = nx/2 + 1
+    std::vector<double> shell_count;   // coefficients per shell (x2: the "n" column of sp_statistics.fsc)
+    double* d_fsc = nullptr;     // [max_refs][3][nsh]
+    float* d_cs = nullptr;       // [max_refs][2]
 };
 
 namespace {
@@ -482,6 +488,7 @@ extern "C" int cra_destroy(CraCtx* c)
     cudaFree(c->d_mask); cudaFree(c->d_dc); cudaFree(c->d_images); cudaFree(c->d_refs); cudaFree(c->d_refspec);
     cudaFree(c->d_spec); cudaFree(c->d_cand); cudaFree(c->d_sums); cudaFree(c->d_meta); cudaFree(c->d_res);
     cudaFree(c->d_par); cudaFree(c->d_iref); cudaFree(c->d_tmpimg); cudaFree(c->d_curves);
+    cudaFree(c->d_shell); cudaFree(c->d_fsc); cudaFree(c->d_cs);
     if (c->h_meta) cudaFreeHost(c->h_meta);
     if (c->h_res) cudaFreeHost(c->h_res);
     if (c->h_par) cudaFreeHost(c->h_par);
@@ -595,6 +602,101 @@ extern "C" int cra_get_refs(CraCtx* c, float* host_refs)
     CRA_CUDA(cudaMemcpyAsync(host_refs, c->d_refs, (size_t)c->R * c->npix * sizeof(float), cudaMemcpyDeviceToHost, c->st));
     CRA_CUDA(cudaStreamSynchronize(c->st));
     return 0;
+}
+
+// ---- reference update on the device (cra_refupdate.cu) -------------------------------------------------
+// fsc's shell of every half-complex coefficient, exactly as EMData::calc_fourier_shell_correlation bins them
+// (float32 argument of the square root, round half away from zero; Friedel mates on the kx = 0 column skipped)
+static int ensure_fsc_tables(CraCtx* c)
+{
+    if (c->d_shell) return 0;
+    const int nx = c->nx, nh = nx / 2 + 1, nx2 = nx / 2;
+    const int inc = (int)(nx2 + 0.5);
+    c->nsh = inc + 1;
+    std::vector<short> sh((size_t)nx * nh);
+    c->shell_count.assign(c->nsh, 0.0);
+    for (int iy = 0; iy < nx; ++iy) {
+        const int ky = iy > nx / 2 ? iy - nx : iy;
+        for (int kx = 0; kx < nh; ++kx) {
+            const float arg = (float)((double)(ky * ky) / (double)(nx2 * nx2) + (double)(kx * kx) / (double)(nx2 * nx2));
+            const float argx = 0.5f * sqrtf(arg);
+            const double v = (double)inc * 2.0 * (double)argx;
+            const long r = (long)(v >= 0 ? floor(v + 0.5) : ceil(v - 0.5));
+            const bool use = (kx > 0 || ky >= 0) && r <= inc;
+            sh[(size_t)iy * nh + kx] = use ? (short)r : (short)-1;
+            if (use) c->shell_count[r] += 1.0;
+        }
+    }
+    CRA_CUDA(cudaMalloc(&c->d_shell, sh.size() * sizeof(short)));
+    CRA_CUDA(cudaMemcpy(c->d_shell, sh.data(), sh.size() * sizeof(short), cudaMemcpyHostToDevice));
+    CRA_CUDA(cudaMalloc(&c->d_fsc, (size_t)c->cfg.max_refs * 3 * c->nsh * sizeof(double)));
+    CRA_CUDA(cudaMalloc(&c->d_cs, (size_t)c->cfg.max_refs * 2 * sizeof(float)));
+    return 0;
+}
+
+extern "C" int cra_class_fsc(CraCtx* c, int masked, int min_members, int write_avg, float avg_div, int* nshell,
+                             double* freq_out, double* fsc_out, double* n_out, float* counts_out)
+{
+    CraNvtx range("cra_class_fsc");
+    Bind b(c); if (b.ok()) return 1;
+    if (c->R < 1) { cra_set_error("cra_set_refs has not been called"); return 1; }
+    if (ensure_fsc_tables(c)) return 1;
+    const int R = c->R, nsh = c->nsh;
+    if (nshell) *nshell = nsh;
+    if (!fsc_out) return 0;                                    // size query
+    const float* counts = c->d_sums + (size_t)c->cfg.max_refs * 2 * c->npix;
+    if (cra_launch_class_fsc(c->d_sums, counts, c->d_refs, c->d_shell, c->d_mask, R, c->nx, nsh, masked, min_members,
+                             write_avg, avg_div, c->d_fsc, c->st)) return 1;
+    std::vector<double> h((size_t)R * 3 * nsh);
+    std::vector<float> hc(R);
+    CRA_CUDA(cudaMemcpyAsync(h.data(), c->d_fsc, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    CRA_CUDA(cudaMemcpyAsync(hc.data(), counts, R * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    CRA_CUDA(cudaStreamSynchronize(c->st));
+    for (int r = 0; r < R; ++r) {
+        if (counts_out) counts_out[r] = hc[r];
+        for (int i = 0; i < nsh; ++i) {
+            const double num = h[((size_t)r * 3 + 0) * nsh + i], n1 = h[((size_t)r * 3 + 1) * nsh + i], n2 = h[((size_t)r * 3 + 2) * nsh + i];
+            const double den = sqrt(n1 * n2);
+            // the curve is a float in EMAN2 (calc_fourier_shell_correlation returns vector<float>)
+            fsc_out[(size_t)r * nsh + i] = (hc[r] >= (float)min_members && den > 0.0) ? (double)(float)(num / den) : 0.0;
+        }
+    }
+    for (int i = 0; i < nsh; ++i) {
+        if (freq_out) freq_out[i] = (double)i / (double)(2 * (nsh - 1));
+        if (n_out) n_out[i] = 2.0 * c->shell_count[i];
+    }
+    return 0;
+}
+
+extern "C" int cra_put_ref(CraCtx* c, int iref, const float* host_img)
+{
+    Bind b(c); if (b.ok()) return 1;
+    if (iref < 0 || iref >= c->R || !host_img) { cra_set_error("cra_put_ref: reference index outside the current set"); return 1; }
+    CRA_CUDA(cudaMemcpyAsync(c->d_refs + (size_t)iref * c->npix, host_img, (size_t)c->npix * sizeof(float), cudaMemcpyHostToDevice, c->st));
+    CRA_CUDA(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+extern "C" int cra_filter_center_refs(CraCtx* c, float cutoff, float falloff, int mode, float sx, float sy,
+                                      int normalize_mask, float* cs_out)
+{
+    CraNvtx range("cra_filter_center_refs");
+    Bind b(c); if (b.ok()) return 1;
+    if (c->R < 1) { cra_set_error("cra_set_refs has not been called"); return 1; }
+    if (mode < 0 || mode > 2) { cra_set_error("cra_filter_center_refs: mode must be 0 (filter), 1 (phase centre) or 2 (given shift)"); return 1; }
+    if (ensure_fsc_tables(c)) return 1;
+    if (cra_launch_filter_center(c->d_refs, c->R, c->nx, cutoff, falloff, mode, sx, sy, c->d_cs, c->st)) return 1;
+    if (normalize_mask && cra_launch_mask_normalize(c->d_refs, c->R, c->nx, c->d_mask, 1, nullptr, c->st)) return 1;
+    if (cs_out) CRA_CUDA(cudaMemcpyAsync(cs_out, c->d_cs, (size_t)c->R * 2 * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    CRA_CUDA(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+extern "C" int cra_prepare_refs(CraCtx* c, int normalize_mask)
+{
+    Bind b(c); if (b.ok()) return 1;
+    if (c->R < 1) { cra_set_error("no references on the device"); return 1; }
+    return prepare_refs(c, c->R, normalize_mask);
 }
 
 // class_of == nullptr: every particle against every reference (Util.multiref_polar_ali_2d).

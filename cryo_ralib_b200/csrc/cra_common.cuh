@@ -215,3 +215,9 @@ int cra_fp32_peak(double* tf_ffma, double* tf_ffma2);
 // references from class sums, tangent low-pass of nx x nx images in place (cra_refavg.cu)
 int cra_launch_class_average(const float* sums, const float* counts, float* refs, int R, int nx, cudaStream_t st);
 int cra_launch_tanl_filter(float* imgs, int n, int nx, float fl, float aa, cudaStream_t st);
+// reference update on the device (cra_refupdate.cu): class averages + ring-binned FSC sums; filt_tanl + centring
+int cra_launch_class_fsc(const float* sums, const float* counts, float* refs, const short* shell, const float* mask, int R,
+                         int nx, int nsh, int masked, int min_members, int write_avg, float avg_div, double* fsc_out,
+                         cudaStream_t st);
+int cra_launch_filter_center(float* imgs, int n, int nx, float fl, float aa, int mode, float sx, float sy, float* cs_out,
+                             cudaStream_t st);

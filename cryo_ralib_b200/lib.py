@@ -59,6 +59,7 @@ RESULT_DTYPE = np.dtype([("ang", "f4"), ("sxs", "f4"), ("sys", "f4"), ("mirror",
 CORE_SYMBOLS = ["cra_create", "cra_destroy", "cra_last_error", "cra_ring_info", "cra_upload_particles",
                 "cra_upload_particles_dev", "cra_upload_particles_async", "cra_upload_wait", "cra_mref_search_request",
                 "cra_compose_result", "cra_reffree_search_request", "cra_fit_tanh", "cra_set_refs", "cra_align", "cra_align_bound", "cra_refs_from_sums", "cra_filter_refs",
+                "cra_class_fsc", "cra_put_ref", "cra_filter_center_refs", "cra_prepare_refs",
                 "cra_get_refs", "cra_accumulate", "cra_zero_sums",
                 "cra_sums_device_ptr", "cra_get_sums", "cra_transform", "cra_transform_dev", "cra_polar_spectrum", "cra_ref_spectrum", "cra_batch_row_spectrum",
                 "cra_ccf_curves", "cra_last_align_stats", "cra_set_timing", "cra_set_normalize_ring", "cra_set_step",
@@ -101,6 +102,10 @@ def load_library(path=None):
     L.cra_refs_from_sums.argtypes = [vp, C.c_int]
     L.cra_filter_refs.argtypes = [vp, C.c_float, C.c_float, C.c_int]
     L.cra_get_refs.argtypes = [vp, vp]
+    L.cra_class_fsc.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_int), vp, vp, vp, vp]
+    L.cra_put_ref.argtypes = [vp, C.c_int, vp]
+    L.cra_filter_center_refs.argtypes = [vp, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_int, vp]
+    L.cra_prepare_refs.argtypes = [vp, C.c_int]
     L.cra_accumulate.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_long]
     L.cra_zero_sums.argtypes = [vp]
     L.cra_sums_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
@@ -237,6 +242,64 @@ class Engine(object):
         """Tangent low-pass (filt_tanl) of the current references, on the device."""
         self._ck(self.L.cra_filter_refs(self.h, float(cutoff), float(falloff), int(normalize_mask)))
 
+    def class_fsc(self, masked=False, min_members=4, write_avg=True, avg_div=0.0):
+        """Device half of the reference update: class averages into the reference slots and fsc(even, odd) per class
+        (test_mref.py:252-256).  Returns (freq [nsh], fsc [R][nsh], n [nsh], counts [R])."""
+        nsh = C.c_int()
+        self._ck(self.L.cra_class_fsc(self.h, int(masked), int(min_members), int(write_avg), float(avg_div), C.byref(nsh),
+                                      None, None, None, None))
+        freq = np.zeros(nsh.value); n = np.zeros(nsh.value)
+        fsc = np.zeros((self.R, nsh.value)); counts = np.zeros(self.R, np.float32)
+        self._ck(self.L.cra_class_fsc(self.h, int(masked), int(min_members), int(write_avg), float(avg_div), C.byref(nsh),
+                                      freq.ctypes.data, fsc.ctypes.data, n.ctypes.data, counts.ctypes.data))
+        return freq, fsc, n, counts
+
+    def put_ref(self, iref, img):
+        img = np.ascontiguousarray(img, np.float32)
+        assert img.shape == (self.nx, self.nx)
+        self._ck(self.L.cra_put_ref(self.h, int(iref), img.ctypes.data))
+
+    def filter_center_refs(self, cutoff, falloff, mode=1, shift=(0.0, 0.0), normalize_mask=True):
+        """filt_tanl + centring (mode 1: phase centre of gravity; 2: the given shift; 0: none) + normalize.mask of every
+        reference on the device (ref_ali2d, test_mref.py:273-284).  Returns the shifts removed, [R][2]."""
+        cs = np.zeros((self.R, 2), np.float32)
+        self._ck(self.L.cra_filter_center_refs(self.h, float(cutoff), float(falloff), int(mode), float(shift[0]), float(shift[1]),
+                                               int(normalize_mask), cs.ctypes.data))
+        return cs
+
+    def prepare_refs(self, normalize_mask=True):
+        """Reference preparation (test_mref.py:170-175) of the references already on the device."""
+        self._ck(self.L.cra_prepare_refs(self.h, int(normalize_mask)))
+
+    def update_refs_device(self, center=1, reseed=None, fetch=True):
+        """The whole mref reference update (test_mref.py:238-286) with the class sums staying on the GPU: the host sees
+        only R FSC curves of nx/2+1 numbers and fits the tangent filter (refupdate.fit_tanh -> cra_fit_tanh).
+        Returns (refs or None, info) like refupdate.update_refs."""
+        from . import refupdate as ru
+        freq, fsc, n, counts = self.class_fsc(masked=False, min_members=4, write_avg=True)
+        alive = counts >= 4
+        if not alive.any():
+            raise RuntimeError("every reference vanished (all classes have < 4 members)")
+        reseeded = [int(j) for j in np.nonzero(~alive)[0]]
+        for j in reseeded:
+            self.put_ref(j, reseed(j))
+        keep = n > 0
+        last = int(np.nonzero(alive)[0][-1])
+        acc = fsc[alive].sum(axis=0)
+        # the reference hands ref_ali2d the LAST surviving class's fsc lists with the class-averaged curve written into
+        # them (test_mref.py:258-271); the curve stays that class's own when the averaged one sums to zero
+        curve = acc / float(alive.sum()) if acc.sum() != 0 else fsc[last]
+        frsc = [list(freq[keep]), list(curve[keep]), list(n[keep])]
+        fl, aa = ru.fit_tanh(frsc)
+        aa = min(aa, 0.2)
+        fl = max(min(0.4, fl), 0.12)
+        if center not in (0, 1):
+            raise NotImplementedError("center methods other than 0/1 are off the path")
+        cs = self.filter_center_refs(fl, aa, mode=int(center), normalize_mask=True)
+        info = dict(frsc=frsc, reseeded=reseeded, cs=[list(map(float, c)) for c in cs], filter=(fl, aa),
+                    class_fsc={int(j): [list(freq[keep]), list(fsc[j][keep]), list(n[keep])] for j in np.nonzero(alive)[0]})
+        return (self.get_refs() if fetch else None), info
+
     def get_refs(self):
         out = np.zeros((self.R, self.nx, self.nx), np.float32)
         self._ck(self.L.cra_get_refs(self.h, out.ctypes.data))
@@ -258,6 +321,12 @@ class Engine(object):
         counts = np.zeros(R, np.float32)
         self._ck(self.L.cra_get_sums(self.h, sums.ctypes.data, counts.ctypes.data))
         return sums, counts
+
+    def get_sums_counts(self):
+        """The class sizes only (the [R] tail of the sums buffer)."""
+        counts = np.zeros(self.max_refs, np.float32)
+        self._ck(self.L.cra_get_sums(self.h, None, counts.ctypes.data))
+        return counts
 
     def sums_device_ptr(self):
         p, n = C.c_void_p(), C.c_size_t()

@@ -91,11 +91,13 @@ def _reduce_sums(engine, comm, device_allreduce):
 
 def mref_ali2d(images, refs, ir=1, ou=-1, rs=1, xr=0, yr=0, ts=1, center=1, maxit=10, rand_seed=1000,
                params=None, comm=None, total_particles=None, global_offset=0, engine=None,
-               device=0, device_allreduce=True, on_iteration=None, upload=True):
+               device=0, device_allreduce=True, on_iteration=None, upload=True, device_update=None):
     """2D multi-reference alignment of this rank's particles.
 
     images  [n][nx][nx] float32: this rank's share (global indices global_offset..+n)
     refs    [R][nx][nx] initial references (replicated)
+    device_update: run the reference update on the GPU (Engine.update_refs_device: the all-reduced class sums never
+    leave the device; default whenever the sums are reduced on the device) instead of host numpy (refupdate.update_refs).
     Returns (params [n][4] alpha,sx,sy,mirror; assign [n]; refs [R][nx][nx]; history)
     """
     from .lib import Engine
@@ -119,16 +121,30 @@ def mref_ali2d(images, refs, ir=1, ou=-1, rs=1, xr=0, yr=0, ts=1, center=1, maxi
     reseed = ru.make_reseeder(rand_seed, P, lambda k: comm.fetch_image(k, owner, masked_local, (nx, nx)))
     history = []
     assign = np.zeros(n, np.int32)
+    if device_update is None:
+        device_update = bool(device_allreduce) and hasattr(engine, "update_refs_device")
     for it in range(int(maxit)):
-        engine.set_refs(refs, normalize_mask=True)                    # test_mref.py:170-175
+        if it == 0 or not device_update:
+            engine.set_refs(refs, normalize_mask=True)                # test_mref.py:170-175
+        else:
+            engine.prepare_refs(normalize_mask=True)                  # the references are already on the device
         search, sxi, syi, params = al.mref_search_request(params, nx, ou, xr, yr)
         res = engine.align(0, n, search)                              # test_mref.py:200
         params = al.compose_result(sxi, syi, res)                     # test_mref.py:206
         assign = res["iref"].copy()
         engine.zero_sums()
         engine.accumulate(0, n, params, assign, global_offset)        # test_mref.py:210-215
-        sums, counts = _reduce_sums(engine, comm, device_allreduce)   # test_mref.py:219-223
-        refs, info = ru.update_refs(sums[:R], counts[:R], mask, center, reseed)   # test_mref.py:238-286
+        if device_update:
+            if comm.world > 1:
+                comm.allreduce_device(engine)                         # test_mref.py:219-223
+            last = it == int(maxit) - 1
+            refs_d, info = engine.update_refs_device(center, reseed, fetch=bool(on_iteration) or last)   # test_mref.py:238-286
+            if refs_d is not None:
+                refs = refs_d
+            counts = engine.get_sums_counts() if hasattr(engine, "get_sums_counts") else engine.get_sums()[1]
+        else:
+            sums, counts = _reduce_sums(engine, comm, device_allreduce)   # test_mref.py:219-223
+            refs, info = ru.update_refs(sums[:R], counts[:R], mask, center, reseed)   # test_mref.py:238-286
         info.update(counts=counts[:R].copy(), peak=res["peak"].copy(), stats=engine.stats())
         history.append(info)
         if on_iteration:

@@ -228,12 +228,14 @@ def update_refs(sums, counts, mask, center=1, reseed=None):
     nfsc = 0
     frsc = None
     reseeded = []
+    class_fsc = {}
     for j in range(R):
         if counts[j] < 4:
             refs[j] = reseed(j)
             reseeded.append(j)
         else:
             frsc = fsc(sums[j, 0], sums[j, 1])
+            class_fsc[j] = [list(frsc[0]), list(frsc[1]), list(frsc[2])]
             refs[j] = (sums[j, 0] + sums[j, 1]) * np.float32(1.0 / float(counts[j]))
             acc = np.array(frsc[1]) if acc is None else acc + np.array(frsc[1])
             nfsc += 1
@@ -241,7 +243,7 @@ def update_refs(sums, counts, mask, center=1, reseed=None):
         raise RuntimeError("every reference vanished (all classes have < 4 members)")
     if acc.sum() != 0:
         frsc[1] = list(acc / float(nfsc))
-    info = dict(frsc=[list(frsc[0]), list(frsc[1]), list(frsc[2])], reseeded=reseeded, cs=[], filter=None)
+    info = dict(frsc=[list(frsc[0]), list(frsc[1]), list(frsc[2])], reseeded=reseeded, cs=[], filter=None, class_fsc=class_fsc)
     fit = fit_tanh(frsc)                      # the same FSC curve for every class: one fit
     for j in range(R):
         refs[j], cs, info["filter"] = ref_ali2d(refs[j], frsc, center, fit=fit)

@@ -80,3 +80,11 @@ def read_params(path):
     if rows.shape[1] == 4:
         return rows.astype(np.float64), None
     raise ValueError("parameter file must have 4 or 6 columns, got %d" % rows.shape[1])
+
+
+def write_fsc(path, frsc):
+    """The text file sp_statistics.fsc writes when given a name (write_text_file of [freq, fsc, n]; the reference's
+    drm%03d%04d.txt, test_mref.py:254): one row per shell."""
+    with open(path, "w") as f:
+        for fr, v, n in zip(*frsc):
+            f.write("%12.5g  %12.5g  %12.5g\n" % (fr, v, n))

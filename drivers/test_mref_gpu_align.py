@@ -6,7 +6,8 @@ test_mref_gpu_align.py / test_mref.py entry point, same positional arguments and
     torchrun --nproc-per-node 8 --master-addr 127.0.0.1 drivers/test_mref_gpu_align.py stack refstack outdir ...
 
 Stacks are .npy or MRC float32 stacks.  Outputs (rank 0): aqm%03d.mrcs per iteration
-(test_mref.py:240, :285), params.txt with 'idx angle sx sy mirror class' rows, logfile.
+(test_mref.py:240, :285), drm%03d%04d.txt = the even/odd FSC of every class of that iteration
+(test_mref.py:254), params.txt with 'idx angle sx sy mirror class' rows, logfile.
 """
 import argparse
 import os
@@ -60,6 +61,8 @@ def main(argv=None):
     def on_iteration(it, params, assign, new_refs, info):
         if rank == 0:
             stackio.write_stack(os.path.join(args.outdir, "aqm%03d.mrcs" % it), new_refs)
+            for j, frsc in sorted(info.get("class_fsc", {}).items()):
+                stackio.write_fsc(os.path.join(args.outdir, "drm%03d%04d.txt" % (it, j)), frsc)
             dt = time.time() - t0[0]; t0[0] = time.time()
             st = info.get("stats", {})
             log.add("ITERATION #%3d   %.3f s   %.3e alignments/s (whole iteration, wall clock)   filter cut-off %.3f fall-off %.3f"

@@ -115,6 +115,31 @@ int  cra_filter_refs(CraCtx* ctx, float cutoff_freq, float falloff, int normaliz
 /* Current reference images [R][nx][nx] to the host (as prepared: after normalize.mask when that was asked). */
 int  cra_get_refs(CraCtx* ctx, float* host_refs);
 
+/* The per-iteration reference update ON THE DEVICE (the rank-0 section of the reference's loop, test_mref.py:238-286;
+ * reference-free twin test_reffree.py:695-755).  The class sums never leave the GPU; the host keeps what the reference
+ * keeps in Python: the class average of the FSC curves and the 2-parameter tangent fit (cra_fit_tanh).
+ *
+ * cra_class_fsc: for every class r with counts[r] >= min_members (test_mref.py:244: 4):
+ *   write_avg != 0: reference slot r <- (even[r] + odd[r]) / (avg_div > 0 ? avg_div : counts[r])   (test_mref.py:255-256;
+ *                   the reference-free driver divides by the particle count, test_reffree.py:697)
+ *   fsc_out[r][i] = fsc(even[r], odd[r]) at shell i (EMData::calc_fourier_shell_correlation, w = 1; test_mref.py:254);
+ *                   masked != 0: fsc_mask -- in-mask mean removed and masked first (test_reffree.py:708).
+ *   Classes below min_members get a zero curve and keep their slot: the caller reseeds them with cra_put_ref.
+ *   nshell = nx/2 + 1; freq_out [nshell], n_out [nshell] are the other two columns sp_statistics.fsc returns;
+ *   counts_out [R].  fsc_out == NULL only reports nshell.
+ * cra_put_ref: overwrite one reference slot from the host (the <4-member reseed, test_mref.py:244-249).
+ * cra_filter_center_refs: every reference <- filt_tanl(ref, cutoff, falloff), then mode 1: center_2D(., 1) = phase_cog +
+ *   fshift(-cs) (sp_user_functions.ref_ali2d, test_mref.py:273-276); mode 2: fshift(ref, -sx, -sy) (test_reffree.py:741-745);
+ *   mode 0: no shift; then normalize.mask(no_sigma = 1) when normalize_mask (test_mref.py:284).  cs_out [R][2] (may be NULL).
+ * cra_prepare_refs: the reference preparation of the next iteration (test_mref.py:170-175) on the references already
+ *   on the device -- cra_set_refs without the upload.                                                             */
+int  cra_class_fsc(CraCtx* ctx, int masked, int min_members, int write_avg, float avg_div, int* nshell,
+                   double* freq_out, double* fsc_out, double* n_out, float* counts_out);
+int  cra_put_ref(CraCtx* ctx, int iref, const float* host_img);
+int  cra_filter_center_refs(CraCtx* ctx, float cutoff_freq, float falloff, int mode, float sx, float sy,
+                            int normalize_mask, float* cs_out);
+int  cra_prepare_refs(CraCtx* ctx, int normalize_mask);
+
 /* Host bookkeeping of the reference's per-particle Python loop, batched (no device work):
  * cra_mref_search_request = get_params2D -> inverse_transform2 -> mashi reset -> search_range x2
  * (test_mref.py:184-198); params [n][4] double (alpha, sx, sy, mirror) is reset in place where the

@@ -1,0 +1,410 @@
+"""Parity at the sizes and geometries BASELINE.json names (through the C ABI, against the CPU oracle):
+
+* configs[0] itself -- 10k particles x 10 references, maxit=6 (test_mref.py:167-296) -- iteration by iteration
+  from IDENTICAL inputs (the oracle's own trajectory is fed to the engine every iteration), counting the
+  discrete answers that differ outside the 2e-5 tie band;
+* the ring geometry and windows of configs[3] (nx=128, ou=60, xr=6: search_range clips the window) and
+  configs[4] (ts=0.5, xr=8: 1089 positions in 4 phase classes);
+* the reference-free legacy entry points pre_align_run / pre_align_run_m in the order test_reffree.py:292-426 calls them;
+* the even/odd class sums mref_align_run_m returns, with an odd global start index;
+* a stack that still carries a large DC offset (deferred Normalize_ring must not lose the peak digits);
+* sample positions on pixel boundaries (integer and half-integer centres at ou=60) in the grouped row kernel.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+PEAK_RTOL = 1e-4
+TIE_BAND = 2e-5
+
+
+def _engine(nx, ou, xr, ts=1.0, P=1, R=1, normalize=True, **kw):
+    from cryo_ralib_b200 import Engine
+    return Engine(nx, ou, xr, ts=ts, max_particles=P, max_refs=R, normalize_ring=normalize, **kw)
+
+
+def _oracle_align(oracle, imgs, cref, numr, search, ts, normalize=True):
+    centres = np.stack([search["cx"], search["cy"]], 1)
+    win = np.stack([search["xl"], search["xr"], search["yl"], search["yr"]], 1)
+    return oracle.align_batch(imgs, cref, numr, centres, win, ts, normalize, nthreads=oracle.max_threads())
+
+
+def _classify(res, want, maxrin):
+    """-> (same mask, rel peak error, angle error): `same` = reference, mirror and grid position identical."""
+    same = (res["iref"] == want[:, 4].astype(int)) & (res["mirror"] == want[:, 3].astype(int)) \
+        & (res["sx"] == want[:, 6]) & (res["sy"] == want[:, 7])
+    rel = np.abs(res["peak"] - want[:, 5]) / np.maximum(np.abs(want[:, 5]), 1e-30)
+    dang = np.abs((res["ang"] - want[:, 0] + 180.0) % 360.0 - 180.0)
+    return same, rel, dang
+
+
+def _angle_is_tie(oracle, img, cref, numr, search_row, r, maxrin, normalize=True):
+    """A particle whose reference, mirror and grid position agree with the oracle but whose angle does not: a tie
+    between two lags of the same correlation curve?  True when the oracle's own curve, at the lag the engine chose
+    (or a neighbour: the angle carries the sub-sample refinement), reaches the oracle's maximum within TIE_BAND."""
+    cx, cy = float(search_row["cx"]) - float(r["sx"]), float(search_row["cy"]) - float(r["sy"])      # res.sx = -ix
+    c = oracle.polar2dm(img, cx, cy, numr)
+    if normalize:
+        c = oracle.normalize_ring(c, numr)
+    cur = oracle.crosrng_ms(cref[int(r["iref"])], oracle.frngs(c, numr), numr)
+    curve = cur["t"] if int(r["mirror"]) else cur["q"]
+    lag = int(round(float(r["ang"]) / 360.0 * maxrin)) % maxrin           # ang_n: ang = (tot - 1) / maxrin * 360
+    near = max(curve[(lag + d) % maxrin] for d in (-1, 0, 1))
+    return near >= curve.max() - TIE_BAND * abs(curve.max())
+
+
+def test_config1_full_size_six_iterations(oracle):
+    """BASELINE configs[0]: 10k x 90x90 particles, 10 references, ou=36, xr=yr=3, maxit=6."""
+    from cryo_ralib_b200 import synth, alignment as al, refupdate as ru
+    import random
+    P, R, nx, ou, xr, maxit = 10000, 10, 90, 36, 3, 6
+    images, _ = synth.make_particles(P, nx, 64, max_shift=xr, seed=2025)
+    refs_o = synth.initial_references(images, R, seed=99)
+    mask = oracle.model_circle(ou, nx)
+    numr = oracle.numrinit(1, ou, 1)
+    nth = oracle.max_threads()
+    e = _engine(nx, ou, xr, P=P, R=R)
+    e.upload_particles(images, subtract_mask_mean=True)
+    imgs_o = images.copy()
+    imgs_n = np.stack([oracle.normalize_mask(im, mask, 0) for im in images])     # normalize.mask no_sigma=0 (idempotent)
+    params_o = np.zeros((P, 4))
+    rng = random.Random(1000)
+    report = []
+    cnx = nx // 2 + 1
+    for it in range(maxit):
+        # ---- the oracle's iteration (test_mref.py:170-215)
+        _, cref = oracle.prepare_refs(refs_o, mask, numr)
+        search, sxi, syi, params_in = al.mref_search_request(params_o, nx, ou, xr, xr)
+        want = _oracle_align(oracle, imgs_n, cref, numr, search, 1.0)
+        p_new, a_o, pk_o, s_o, c_o = oracle.mref_iteration(imgs_o, mask, cref, numr, xr, xr, 1, ou, params_o, 0, True, nth)
+        assert np.array_equal(a_o, want[:, 4].astype(int))          # the two oracle entry points agree
+        # ---- the engine from the same references and the same previous parameters
+        e.set_refs(refs_o, normalize_mask=True)
+        res = e.align(0, P, search)
+        same, rel, dang = _classify(res, want, 256)
+        outside = (~same) & (rel >= TIE_BAND)
+        # same reference / mirror / position but another angle: two lags of one curve within the tie band?
+        off = np.where(same & (dang > 0.5 * 360.0 / 256))[0]
+        lag_ties = [i for i in off if _angle_is_tie(oracle, imgs_n[i], cref, numr, search[i], res[i], 256)]
+        ok_ang = same & (dang <= 0.5 * 360.0 / 256)
+        rec = dict(iteration=it + 1, particles=P, identical=int(ok_ang.sum()), flips_in_tie_band=int(((~same) & (rel < TIE_BAND)).sum()),
+                   flips_outside_tie_band=int(outside.sum()), angle_ties_in_band=len(lag_ties), angle_outside_band=len(off) - len(lag_ties),
+                   max_rel_peak_err=float(rel[same].max()), max_angle_err_deg=float(dang[ok_ang].max()),
+                   fractional_centres=int((np.abs(search["cx"] - np.round(search["cx"])) > 1e-6).sum()))
+        report.append(rec)
+        assert outside.sum() == 0, (rec, np.where(outside)[0][:10])
+        assert rel[same].max() <= PEAK_RTOL, rec
+        assert len(off) == len(lag_ties), (rec, off[:10])
+        assert (~same).sum() <= P // 500, rec                        # ties are rare
+        # ---- class sums from the oracle's own new parameters: identical inputs to rot_shift2D
+        e.zero_sums()
+        e.accumulate(0, P, p_new, a_o, 0)
+        sums, counts = e.get_sums()
+        assert np.array_equal(counts[:R], c_o)
+        err = np.abs(sums[:R] - s_o).max() / np.abs(s_o).max()
+        rec["class_sum_max_err_rel"] = float(err)
+        assert err <= PEAK_RTOL, rec
+        # ---- reference update: host logic of the product against the oracle's, then the oracle's refs go on
+        refs_new, info = oracle.update_refs(s_o, c_o, imgs_o, mask, 1, rng)
+        assert not info["reseeded"]
+        refs_g, info_g = ru.update_refs(s_o, c_o, mask, 1, None)
+        uerr = np.abs(refs_g - refs_new).max() / np.abs(refs_new).max()
+        rec["ref_update_max_err_rel"] = float(uerr)
+        assert uerr <= 1e-4, rec
+        refs_d = e.update_refs_device(center=1) if hasattr(e, "update_refs_device") else None
+        if refs_d is not None:
+            # the device update works on the engine's own sums (same parameters -> sums within 1e-4 of the oracle's)
+            derr = np.abs(refs_d[0] - refs_new).max() / np.abs(refs_new).max()
+            rec["device_ref_update_max_err_rel"] = float(derr)
+            assert derr <= 2e-4, rec
+        params_o, refs_o = p_new, refs_new
+    e.close()
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    json.dump(report, open(os.path.join(out, "config1_parity_report.json"), "w"), indent=1)
+    print(json.dumps(report))
+
+
+@pytest.mark.parametrize("name,nx,ou,xr,ts,R,P", [
+    ("config4 (ou=60: clipped windows)", 128, 60, 6, 1.0, 12, 32),
+    ("config4 variant ou=56 (full 169-position grid)", 128, 56, 6, 1.0, 9, 32),
+    ("config5 (ts=0.5, xr=8: 1089 positions)", 90, 36, 8, 0.5, 16, 32),
+])
+def test_named_config_geometries(oracle, name, nx, ou, xr, ts, R, P):
+    """Two iterations at the geometry of BASELINE configs[3] / configs[4]: zero parameters first (symmetric, clipped
+    window), then the composed parameters of that pass (fractional centres, ragged per-particle windows)."""
+    from cryo_ralib_b200 import synth, alignment as al
+    allp, _ = synth.make_particles(P + 8 * R, nx, 16, max_shift=min(int(xr), 4), seed=11)
+    images = np.ascontiguousarray(allp[:P])
+    refs = synth.initial_references(allp[P:], R, per_ref=8, seed=5)
+    mask = oracle.model_circle(ou, nx)
+    numr = oracle.numrinit(1, ou, 1)
+    maxrin = int(numr[-1])
+    imgs = np.stack([oracle.normalize_mask(im, mask, 0) for im in images])
+    _, cref = oracle.prepare_refs(refs, mask, numr)
+    e = _engine(nx, ou, xr, ts=ts, P=P, R=R)
+    e.upload_particles(images); e.set_refs(refs)
+    params = np.zeros((P, 4))
+    for it in range(2):
+        search, sxi, syi, params = al.mref_search_request(params, nx, ou, xr, xr)
+        if it == 0:
+            # the window search_range leaves at zero shift: clipped to +-3 for ou=60, full otherwise
+            lim = min(xr, nx // 2 + 1 - ou - 2 if nx // 2 + 1 - ou - 2 < xr else xr)
+            assert np.all(search["xl"] == min(float(xr), float(nx // 2 + 1 - ou - 2))) and lim >= 0
+        res = e.align(0, P, search)
+        want = _oracle_align(oracle, imgs, cref, numr, search, ts)
+        same, rel, dang = _classify(res, want, maxrin)
+        bad = (~same) & (rel >= TIE_BAND)
+        assert not bad.any(), (name, it, np.where(bad)[0], rel[bad])
+        assert rel[same].max() <= PEAK_RTOL, (name, it, rel[same].max())
+        assert dang[same].max() <= 0.5 * 360.0 / maxrin, (name, it, dang[same].max())
+        nwin = ((search["xl"] / ts).astype(int) + (search["xr"] / ts).astype(int) + 1) * \
+               ((search["yl"] / ts).astype(int) + (search["yr"] / ts).astype(int) + 1)
+        assert e.stats()["alignments"] == int(nwin.sum()) * R
+        params = al.compose_result(sxi, syi, res)
+    e.close()
+
+
+def _legacy_setup(oracle, images, refs, P, R, ou=36, xr=3.0):
+    from cryo_ralib_b200.lib import load_library, AlignConfig, AlignParam
+    nx = images.shape[-1]
+    L = load_library()
+    cfg = AlignConfig(P, R, nx, ou, 256, 1.0, xr, xr)
+    assert L.pre_align_size_check(P, C.byref(cfg), 0, 0.9, False)
+    ptr = L.pre_align_init(P, C.byref(cfg), 0)
+    assert ptr
+    par = C.cast(ptr, C.POINTER(AlignParam))
+    return L, cfg, par
+
+
+def _fetch(L, arrs, which):
+    fp = C.POINTER(C.c_float)
+    keep = [np.ascontiguousarray(a, np.float32) for a in arrs]
+    L.pre_align_fetch((fp * len(keep))(*[d.ctypes.data_as(fp) for d in keep]), len(keep), which)
+    return keep
+
+
+def _read_device(dptr, shape):
+    rt = C.CDLL("/usr/local/cuda/lib64/libcudart.so")
+    rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    got = np.zeros(shape, np.float32)
+    assert rt.cudaMemcpy(got.ctypes.data, C.c_void_p(dptr), got.nbytes, 2) == 0
+    return got
+
+
+def test_legacy_pre_align_run_sequence(oracle, small_set):
+    """test_reffree.py:292-426 / test_reffree_gpu_align.py:476: pre_align_init, fetch the stack once, then per iteration
+    fetch the current average as the one reference and call pre_align_run (parameters only) or pre_align_run_m
+    (parameters + transformed images on the device).  ormq semantics: no Normalize_ring, shifts clamped; the library
+    accumulates the shifts in AlignParam across the calls (gpu_aln_noref.cu:1476-1479)."""
+    images, _, _ = small_set
+    P, nx, ou, xr = 48, 90, 36, 3
+    mask = oracle.model_circle(ou, nx)
+    numr = oracle.numrinit(1, ou, 1)
+    wr = oracle.ringwe(numr)
+    imgs = np.stack([oracle.normalize_mask(im, mask, 0) for im in images[:P]])
+    L, cfg, par = _legacy_setup(oracle, imgs, None, P, 1)
+    _fetch(L, imgs, b"sbj_batch")
+    L.reset_shifts(float(xr), 1.0)
+    cnx = nx // 2 + 1
+    mashi = cnx - ou - 2
+    sh = np.zeros((P, 2))
+    tavg = imgs.mean(axis=0)
+    for it, run_m in enumerate((False, True, False)):
+        _fetch(L, [tavg], b"ref_batch")
+        # what the oracle's ormq answers for the same centres and windows
+        cref = oracle.applyws(oracle.frngs(oracle.polar2dm(tavg.astype(np.float32), float(cnx), float(cnx), numr), numr), numr, wr)[None]
+        sh = np.clip(sh, -mashi, mashi)
+        centres = (cnx + sh).astype(np.float32)
+        win = np.zeros((P, 4), np.float32)
+        for i in range(P):
+            win[i, 0:2] = oracle.search_range(nx, ou, sh[i, 0], xr)
+            win[i, 2:4] = oracle.search_range(nx, ou, sh[i, 1], xr)
+        want = oracle.align_batch(imgs, cref, numr, centres, win, 1.0, False, nthreads=8)
+        if run_m:
+            L.pre_align_run_m.restype = C.c_void_p
+            dptr = L.pre_align_run_m(5, P)                 # a sub-range first, as a batched driver would
+            assert dptr
+            L.pre_align_run(0, 5)
+        else:
+            L.pre_align_run(0, P)
+        n_same = 0
+        for i in range(P):
+            w = want[i]
+            if int(par[i].mirror) == int(w[3]) and par[i].shift_x == np.float32(sh[i, 0] - w[6]) and par[i].shift_y == np.float32(sh[i, 1] - w[7]):
+                n_same += 1
+                assert abs((par[i].angle - w[0] + 180) % 360 - 180) <= 0.5 * 360 / 256
+                assert par[i].ref_id == 0
+        assert n_same >= P - 2, (it, n_same)
+        if run_m:
+            got = _read_device(dptr, (P - 5, nx, nx))
+            for k in (0, 11, P - 6):
+                i = 5 + k
+                if min(par[i].angle % 90.0, 90.0 - par[i].angle % 90.0) < 0.5:
+                    continue
+                a = np.deg2rad(par[i].angle)
+                sx = -par[i].shift_x * np.cos(a) - par[i].shift_y * np.sin(a)
+                sy = par[i].shift_x * np.sin(a) - par[i].shift_y * np.cos(a)
+                wimg = oracle.rot_shift2d(imgs[i], par[i].angle, sx, sy, int(par[i].mirror))
+                assert np.abs(got[k] - wimg).max() <= 1e-4 * np.abs(wimg).max(), (it, i)
+        # next iteration: accumulated shifts as the library keeps them; a new average from the oracle's transform
+        sh = np.array([[par[i].shift_x, par[i].shift_y] for i in range(P)], np.float64)
+        acc = np.zeros((nx, nx), np.float32)
+        for i in range(P):
+            a = np.deg2rad(par[i].angle)
+            sx = -par[i].shift_x * np.cos(a) - par[i].shift_y * np.sin(a)
+            sy = par[i].shift_x * np.sin(a) - par[i].shift_y * np.cos(a)
+            acc += oracle.rot_shift2d(imgs[i], par[i].angle, sx, sy, int(par[i].mirror))
+        tavg = acc / np.float32(P)
+    L.gpu_clear()
+
+
+def test_legacy_mref_align_run_m_even_odd_layout(oracle, small_set):
+    """mref_align_run_m returns [2R][nx][nx]: the R even sums, then the R odd sums, parity taken from the GLOBAL index
+    start+i (test_mref.py:211; gpu_aln_noref.cu:1232-1274), and get_num_ref the class sizes -- compared image by image
+    with the oracle's rot_shift2D accumulation of the parameters the call wrote, for an odd start index."""
+    images, refs, _ = small_set
+    nx, ou, R = 90, 36, refs.shape[0]
+    mask = oracle.model_circle(ou, nx)
+    numr = oracle.numrinit(1, ou, 1)
+    imgs = np.stack([oracle.normalize_mask(im, mask, 0) for im in images])
+    refs_n, cref = oracle.prepare_refs(refs, mask, numr)
+    Ptot, start, stop = 40, 7, 40
+    n = stop - start
+    L, cfg, par = _legacy_setup(oracle, imgs, refs, Ptot, R)
+    L.reset_shifts(3.0, 1.0)
+    _fetch(L, refs_n, b"ref_batch")
+    _fetch(L, imgs[start:stop], b"sbj_batch")            # a batched driver re-fetches every batch into slot 0
+    L.mref_align_run_m.restype = C.POINTER(C.c_float)
+    L.get_num_ref.restype = C.POINTER(C.c_int)
+    sums_ptr = L.mref_align_run_m(start, stop)
+    assert sums_ptr
+    counts = np.ctypeslib.as_array(L.get_num_ref(), (R,)).copy()
+    sums = np.ctypeslib.as_array(sums_ptr, (2 * R, nx, nx)).copy()
+    want = np.zeros((2 * R, nx, nx), np.float32)
+    wcount = np.zeros(R, int)
+    for i in range(start, stop):
+        p = par[i]
+        a = np.deg2rad(p.angle)
+        sx = -p.shift_x * np.cos(a) - p.shift_y * np.sin(a)          # a19 (test_mref_gpu_align.py:578-588)
+        sy = p.shift_x * np.sin(a) - p.shift_y * np.cos(a)
+        img = oracle.rot_shift2d(imgs[i], p.angle, np.float32(sx), np.float32(sy), int(p.mirror))
+        want[(i % 2) * R + p.ref_id] += img
+        wcount[p.ref_id] += 1
+    assert np.array_equal(counts, wcount)
+    scale = np.abs(want).max()
+    for r in range(2 * R):
+        assert np.abs(sums[r] - want[r]).max() <= 1e-5 * scale * max(1, wcount[r % R]), r
+    # the even block of a class that only received odd-indexed particles is exactly zero, and vice versa
+    for r in range(R):
+        ids = [i for i in range(start, stop) if par[i].ref_id == r]
+        if ids and all(i % 2 == 1 for i in ids):
+            assert not sums[r].any() and sums[R + r].any()
+    L.gpu_clear()
+
+
+@pytest.mark.parametrize("offset", [50.0, -300.0])
+def test_dc_offset_stack_keeps_peak_digits(oracle, small_set, offset):
+    """A stack whose mean is far from zero (mean >> sigma), uploaded WITHOUT the mask-mean subtraction as the legacy
+    ABI does: the deferred Normalize_ring must give the same answers as for the centred stack."""
+    from cryo_ralib_b200 import alignment as al
+    images, refs, _ = small_set
+    P, R = 32, refs.shape[0]
+    mask = oracle.model_circle(36, 90)
+    numr = oracle.numrinit(1, 36, 1)
+    raw = (images[:P] + np.float32(offset)).astype(np.float32)
+    _, cref = oracle.prepare_refs(refs, mask, numr)
+    e = _engine(90, 36, 3, P=P, R=R)
+    e.upload_particles(raw, subtract_mask_mean=False)
+    e.set_refs(refs)
+    search, sxi, syi, _ = al.mref_search_request(np.zeros((P, 4)), 90, 36, 3, 3)
+    res = e.align(0, P, search)
+    want = _oracle_align(oracle, raw, cref, numr, search, 1.0)      # Normalize_ring removes the offset in the oracle too
+    same, rel, dang = _classify(res, want, 256)
+    bad = (~same) & (rel >= TIE_BAND)
+    assert not bad.any(), (np.where(bad)[0], rel[bad])
+    assert rel[same].max() <= PEAK_RTOL, rel[same].max()
+    e.close()
+
+
+def test_pixel_boundary_samples_ou60(oracle):
+    """Integer and half-integer centres at ou=60: hundreds of ring samples fall exactly on pixel boundaries, where the
+    grouped row kernel redoes them row by row with Polar2Dm's own arithmetic (more such samples than its first queue
+    holds).  Every spectrum row must still match the oracle."""
+    from cryo_ralib_b200 import synth
+    from cryo_ralib_b200.lib import SEARCH_DTYPE
+    nx, ou, P = 128, 60, 6
+    images, _ = synth.make_particles(P, nx, 8, max_shift=1, seed=3)
+    mask = oracle.model_circle(ou, nx)
+    numr = oracle.numrinit(1, ou, 1)
+    imgs = np.stack([oracle.normalize_mask(im, mask, 0) for im in images])
+    refs = images[:2].copy()
+    e = _engine(nx, ou, 1, P=P, R=2)
+    e.upload_particles(images); e.set_refs(refs)
+    search = np.zeros(P, SEARCH_DTYPE)
+    centres = [(65.0, 65.0), (64.5, 65.5), (65.5, 64.0), (64.0, 66.0), (65.25, 64.75), (66.0, 64.5)]
+    for p, (cx, cy) in enumerate(centres):
+        search[p] = (cx, cy, 1, 1, 1, 1)
+    e.align(0, P, search)
+    row = 0
+    for p, (cx, cy) in enumerate(centres):
+        for iy in (-1, 0, 1):
+            for ix in (-1, 0, 1):
+                got, kernel = e.batch_row_spectrum(row)
+                c = oracle.normalize_ring(oracle.polar2dm(imgs[p], cx + ix, cy + iy, numr), numr)
+                want = oracle.frngs(c, numr)
+                scale = np.abs(want).max()
+                assert np.abs(got - want).max() <= 2e-5 * scale, (p, ix, iy, kernel, np.abs(got - want).max() / scale)
+                row += 1
+    e.close()
+
+
+def test_device_reference_update_matches_oracle(oracle, small_set):
+    """The mref reference update on the device (cra_class_fsc + host tangent fit + cra_filter_center_refs,
+    test_mref.py:238-286) against oracle.update_refs on the same class sums: per-class FSC curves, the fitted filter,
+    the centring shifts and the new references; one class is left with < 4 members and is reseeded."""
+    import random
+    from cryo_ralib_b200 import alignment as al
+    images, refs, _ = small_set
+    P, R, nx, ou = images.shape[0], refs.shape[0], 90, 36
+    mask = oracle.model_circle(ou, nx)
+    numr = oracle.numrinit(1, ou, 1)
+    imgs = np.stack([oracle.normalize_mask(im, mask, 0) for im in images])
+    rng = np.random.default_rng(4)
+    params = np.stack([rng.uniform(0, 360, P), rng.uniform(-3, 3, P), rng.uniform(-3, 3, P), rng.integers(0, 2, P)], 1)
+    assign = rng.integers(0, R - 2, P).astype(np.int32)           # class R-1 stays empty, class R-2 gets 3 members: both reseed
+    assign[:3] = R - 2
+    e = _engine(nx, ou, 3, P=P, R=R)
+    e.upload_particles(images); e.set_refs(refs)
+    e.zero_sums(); e.accumulate(0, P, params, assign, 0)
+    sums, counts = e.get_sums()
+    assert (counts[:R] < 4).any() and (counts[:R] >= 4).sum() >= 4
+    pick = lambda j: imgs[(7 * j + 3) % P]
+    class _Rng(object):                                           # the oracle draws randint(0, P - 1) per vanished class
+        def __init__(self): self.j = [int(j) for j in np.nonzero(counts[:R] < 4)[0]]
+        def randint(self, a, b): return (7 * self.j.pop(0) + 3) % P
+    want, winfo = oracle.update_refs(sums[:R], counts[:R].astype(np.float64), imgs, mask, 1, _Rng())
+    got, ginfo = e.update_refs_device(center=1, reseed=pick)
+    assert sorted(ginfo["reseeded"]) == sorted(winfo["reseeded"].keys())
+    # per-class FSC curves against sp_statistics.fsc on the same sums
+    for j, cur in ginfo["class_fsc"].items():
+        w = oracle.fsc(sums[j, 0], sums[j, 1], 1.0)
+        assert np.allclose(cur[0], w[0]) and np.allclose(cur[2], w[2])
+        assert np.abs(np.array(cur[1]) - np.array(w[1])).max() <= 2e-5, j
+    assert np.allclose(ginfo["filter"], winfo["filter"], rtol=2e-4), (ginfo["filter"], winfo["filter"])
+    assert np.abs(np.array(ginfo["cs"]) - np.array(winfo["cs"])).max() <= 2e-3
+    err = np.abs(got - want).max() / np.abs(want).max()
+    print("device reference update: max error %.2e of max" % err)
+    assert err <= 5e-5, err
+    # the prepared spectra of the next iteration equal those of an upload of the same references
+    e.prepare_refs(normalize_mask=True)
+    a = np.stack([e.ref_spectrum(j) for j in range(R)])
+    e.set_refs(got, normalize_mask=True)
+    b = np.stack([e.ref_spectrum(j) for j in range(R)])
+    assert np.array_equal(a, b)
+    e.close()
