@@ -938,7 +938,18 @@ extern "C" int cra_zero_sums(CraCtx* c)
     return 0;
 }
 
-extern "C" int cra_accumulate(CraCtx* c, int start, int stop, const float* params, const int* iref, long goff)
+// (alpha [deg], sx, sy, mirror) -> what rotsum_kernel takes: the angle in radians as a float, formed the way EMAN2
+// does: EMData::rot_scale_trans2D_background(float angDeg, ...) receives the degrees ALREADY rounded to float (the
+// Python double passes through a float parameter) and computes  float ang = angDeg * M_PI / 180.0f  in double.
+template <typename T>
+static inline float4 pack_par(const T* p)
+{
+    const float deg = (float)p[0];
+    return make_float4((float)((double)deg * 3.14159265358979323846 / 180.0), (float)p[1], (float)p[2], (float)p[3]);
+}
+
+template <typename T>
+static int accumulate_impl(CraCtx* c, int start, int stop, const T* params, const int* iref, long goff)
 {
     CraNvtx range("cra_accumulate (rot_shift2D + class sums)");
     Bind b(c); if (b.ok()) return 1;
@@ -949,7 +960,7 @@ extern "C" int cra_accumulate(CraCtx* c, int start, int stop, const float* param
     if (ensure_par(c, n)) return 1;
     for (int i = 0; i < n; ++i) {
         if (iref[i] >= c->cfg.max_refs) { cra_set_error("iref exceeds max_refs"); return 1; }
-        c->h_par[i] = make_float4(params[4 * i], params[4 * i + 1], params[4 * i + 2], params[4 * i + 3]);
+        c->h_par[i] = pack_par(params + 4 * (size_t)i);
         c->h_iref[i] = iref[i];
     }
     CRA_CUDA(cudaMemcpyAsync(c->d_par, c->h_par, sizeof(float4) * n, cudaMemcpyHostToDevice, c->st));
@@ -959,6 +970,11 @@ extern "C" int cra_accumulate(CraCtx* c, int start, int stop, const float* param
     CRA_CUDA(cudaStreamSynchronize(c->st));
     return 0;
 }
+
+extern "C" int cra_accumulate(CraCtx* c, int start, int stop, const float* params, const int* iref, long goff)
+{ return accumulate_impl(c, start, stop, params, iref, goff); }
+extern "C" int cra_accumulate_d(CraCtx* c, int start, int stop, const double* params, const int* iref, long goff)
+{ return accumulate_impl(c, start, stop, params, iref, goff); }
 
 extern "C" int cra_sums_device_ptr(CraCtx* c, void** dev_ptr, size_t* n_floats)
 {
@@ -978,7 +994,8 @@ extern "C" int cra_get_sums(CraCtx* c, float* host_sums, float* host_counts)
     return 0;
 }
 
-extern "C" int cra_transform_dev(CraCtx* c, int start, int stop, const float* params, float* dev_out)
+template <typename T>
+static int transform_dev_impl(CraCtx* c, int start, int stop, const T* params, float* dev_out)
 {
     Bind b(c); if (b.ok()) return 1;
     const int n = stop - start;
@@ -990,8 +1007,7 @@ extern "C" int cra_transform_dev(CraCtx* c, int start, int stop, const float* pa
     if (ensure_par(c, chunk)) return 1;
     for (int s = 0; s < n; s += chunk) {
         const int m = std::min(chunk, n - s);
-        for (int i = 0; i < m; ++i)
-            c->h_par[i] = make_float4(params[4 * (s + i)], params[4 * (s + i) + 1], params[4 * (s + i) + 2], params[4 * (s + i) + 3]);
+        for (int i = 0; i < m; ++i) c->h_par[i] = pack_par(params + 4 * (size_t)(s + i));
         CRA_CUDA(cudaMemcpyAsync(c->d_par, c->h_par, sizeof(float4) * m, cudaMemcpyHostToDevice, c->st));
         if (cra_launch_rotsum(c->d_images, c->nx, start + s, m, c->d_par, nullptr, 0, nullptr, nullptr,
                               dev_out + (size_t)s * c->npix, c->st)) return 1;
@@ -1000,7 +1016,11 @@ extern "C" int cra_transform_dev(CraCtx* c, int start, int stop, const float* pa
     return 0;
 }
 
-extern "C" int cra_transform(CraCtx* c, int start, int stop, const float* params, float* host_out)
+extern "C" int cra_transform_dev(CraCtx* c, int start, int stop, const float* params, float* dev_out)
+{ return transform_dev_impl(c, start, stop, params, dev_out); }
+
+template <typename T>
+static int transform_impl(CraCtx* c, int start, int stop, const T* params, float* host_out)
 {
     Bind b(c); if (b.ok()) return 1;
     const int n = stop - start;
@@ -1016,8 +1036,7 @@ extern "C" int cra_transform(CraCtx* c, int start, int stop, const float* params
     if (ensure_par(c, chunk)) return 1;
     for (int s = 0; s < n; s += chunk) {
         const int m = std::min(chunk, n - s);
-        for (int i = 0; i < m; ++i)
-            c->h_par[i] = make_float4(params[4 * (s + i)], params[4 * (s + i) + 1], params[4 * (s + i) + 2], params[4 * (s + i) + 3]);
+        for (int i = 0; i < m; ++i) c->h_par[i] = pack_par(params + 4 * (size_t)(s + i));
         CRA_CUDA(cudaMemcpyAsync(c->d_par, c->h_par, sizeof(float4) * m, cudaMemcpyHostToDevice, c->st));
         if (cra_launch_rotsum(c->d_images, c->nx, start + s, m, c->d_par, nullptr, 0, nullptr, nullptr, c->d_tmpimg, c->st)) return 1;
         CRA_CUDA(cudaMemcpyAsync(host_out + (size_t)s * c->npix, c->d_tmpimg, (size_t)m * c->npix * sizeof(float), cudaMemcpyDeviceToHost, c->st));
@@ -1025,6 +1044,11 @@ extern "C" int cra_transform(CraCtx* c, int start, int stop, const float* params
     }
     return 0;
 }
+
+extern "C" int cra_transform(CraCtx* c, int start, int stop, const float* params, float* host_out)
+{ return transform_impl(c, start, stop, params, host_out); }
+extern "C" int cra_transform_d(CraCtx* c, int start, int stop, const double* params, float* host_out)
+{ return transform_impl(c, start, stop, params, host_out); }
 
 // device spectrum staged in h_group -> SPIDER packed layout.  F32: row `lane4` of the 4-row group;
 // FRAG: the staged row itself (value = bf16 hi + bf16 lo).

@@ -145,6 +145,8 @@ struct CraCand { float v; int code; };   // code = iref*8192 + mirror*4096 + j  
 // cupy.cuda.nvtx.RangePush/Pop, test_mref_gpu_align.py:89, :329, :416, :448); free when no tool is attached
 struct CraNvtx { explicit CraNvtx(const char* name) { nvtxRangePushA(name); } ~CraNvtx() { nvtxRangePop(); } };
 
+int cra_host_threads();       // team size of the host-side OpenMP loops (cra_host.cu)
+
 // error plumbing -------------------------------------------------------------
 void cra_set_error(const std::string& msg);
 #define CRA_CUDA(call)                                                               \

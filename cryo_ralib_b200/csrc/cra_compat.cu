@@ -206,7 +206,7 @@ extern "C" void pre_align_fetch(const float** img_data, const unsigned int img_n
         g.stage_n = need;
     }
     // gather of the borrowed per-image host pointers into the pinned staging buffer, all host threads
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(cra_host_threads())
     for (long i = 0; i < (long)img_num; ++i) memcpy(g.h_stage + (size_t)i * npix, img_data[i], npix * sizeof(float));
     int rc;
     if (strcmp(batch_type, "sbj_batch") == 0) rc = cra_upload_particles(g.ctx, g.h_stage, 0, (int)img_num, 0);

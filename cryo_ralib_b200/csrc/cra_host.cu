@@ -8,6 +8,31 @@
 // libm's cos/sin/atan2 agree with numpy's.
 #include "cra_common.cuh"
 #include <math.h>
+#include <sched.h>
+#include <stdlib.h>
+
+// Threads of the host loops (bookkeeping, pinned gathers).  torchrun exports OMP_NUM_THREADS=1 to every rank, which
+// would serialise ~30 ms of per-iteration trigonometry at 100k particles per GPU (the +10 ms of a step at N >= 2 in
+// round 1's scaling run): the loops therefore name their own team size -- CRA_HOST_THREADS, else the cores this
+// process may run on divided among the ranks of the node (LOCAL_WORLD_SIZE), at most 16.
+int cra_host_threads()
+{
+    static int cached = 0;
+    if (cached) return cached;
+    int n = 0;
+    if (const char* e = getenv("CRA_HOST_THREADS")) n = atoi(e);
+    if (n <= 0) {
+        cpu_set_t set; CPU_ZERO(&set);
+        int cores = (sched_getaffinity(0, sizeof(set), &set) == 0) ? CPU_COUNT(&set) : 1;
+        int ranks = 1;
+        if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(e) > 0 ? atoi(e) : 1;
+        n = cores / ranks;
+        if (n > 16) n = 16;
+    }
+    if (n < 1) n = 1;
+    cached = n;
+    return n;
+}
 
 namespace {
 
@@ -77,7 +102,7 @@ extern "C" int cra_mref_search_request(int n, double* params, int nx, int ou, do
 {
     if (n < 0 || !params || !search || !sxi_out || !syi_out) { cra_set_error("null argument"); return 1; }
     const int cnx = nx / 2 + 1, mashi = cnx - ou - 2;
-#pragma omp parallel for schedule(static) if (n > 4096)
+#pragma omp parallel for schedule(static) num_threads(cra_host_threads()) if (n > 4096)
     for (int i = 0; i < n; ++i) {
         double a, sxi, syi; int mir;
         params_t(invert_t(make_t(params[4 * i], params[4 * i + 1], params[4 * i + 2], 0)), &a, &sxi, &syi, &mir);
@@ -102,7 +127,7 @@ extern "C" int cra_reffree_search_request(int n, const double* params, double cs
     if (n < 0 || !params || !search || !sxi_out || !syi_out) { cra_set_error("null argument"); return 1; }
     const int cnx = nx / 2 + 1, mashi = cnx - ou - 2;
     const M23 t2 = make_t(0.0, -csx, -csy, 0);
-#pragma omp parallel for schedule(static) if (n > 4096)
+#pragma omp parallel for schedule(static) num_threads(cra_host_threads()) if (n > 4096)
     for (int i = 0; i < n; ++i) {
         double a, sx, sy, a2, sxi, syi; int mir, mir2;
         params_t(mul_t(t2, make_t(params[4 * i], params[4 * i + 1], params[4 * i + 2], (int)params[4 * i + 3])), &a, &sx, &sy, &mir);
@@ -122,7 +147,7 @@ extern "C" int cra_reffree_search_request(int n, const double* params, double cs
 extern "C" int cra_compose_result(int n, const double* sxi, const double* syi, const CraResult* res, double* params_out)
 {
     if (n < 0 || !sxi || !syi || !res || !params_out) { cra_set_error("null argument"); return 1; }
-#pragma omp parallel for schedule(static) if (n > 4096)
+#pragma omp parallel for schedule(static) num_threads(cra_host_threads()) if (n > 4096)
     for (int i = 0; i < n; ++i) {
         const M23 t1 = make_t(0.0, -sxi[i], -syi[i], 0);
         const M23 t2 = make_t((double)res[i].ang, (double)res[i].sxs, (double)res[i].sys, res[i].mirror);

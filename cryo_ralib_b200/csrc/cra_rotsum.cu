@@ -64,25 +64,29 @@ rotsum_kernel(const float* __restrict__ images, int nx, int p0, const float4* __
     }
     __syncthreads();
     const float4 pr = params[p];
-    const float ang = (float)((double)pr.x * 3.14159265358979323846 / 180.0);
+    const float ang = pr.x;                    // radians, rounded to float by the host (cra_api.cu: pack_par)
     const float delx = restrict2(pr.y, nx), dely = restrict2(pr.z, nx);
     const int mirror = pr.w > 0.5f;
     const int xc = nx / 2, yc = nx / 2;
     const float shiftxc = xc + delx, shiftyc = yc + dely;
-    const float cang = cosf(ang), sang = sinf(ang);
+    // Source coordinates exactly as the host library forms them: a correctly rounded float cosine / sine (the
+    // device's cosf is 1-2 ulp) and separately rounded products and sums (no FMA contraction).  quadri_background is
+    // discontinuous across cell borders (its c2 / c4 terms belong to the cell), so a last-ulp difference of xold on a
+    // pixel boundary would move that output pixel by O(1) -- seen on 5 % of the particles before this.
+    const float cang = (float)cos((double)ang), sang = (float)sin((double)ang);
     const int x_start = 1 - nx % 2;
     const int parity = (int)((global_offset + p) & 1);
     float* dst = sums ? sums + ((size_t)ref * 2 + parity) * npix : nullptr;
     float* oimg = out_images ? out_images + (size_t)p * npix : nullptr;
     for (int idx = threadIdx.x; idx < npix; idx += blockDim.x) {
         const int iy = idx / nx, ix = idx - iy * nx;
-        const float y = (float)iy - shiftyc;
-        const float ycang = y * cang + yc;
-        const float ysang = -y * sang + xc;
-        const float x = (float)ix - shiftxc;
-        const float xold = x * cang + ysang;
-        const float yold = x * sang + ycang;
-        const float v = quadri_bg(xold + 1.0f, yold + 1.0f, nx, s_img, ix + 1, iy + 1);
+        const float y = __fsub_rn((float)iy, shiftyc);
+        const float ycang = __fadd_rn(__fmul_rn(y, cang), (float)yc);
+        const float ysang = __fadd_rn(__fmul_rn(-y, sang), (float)xc);
+        const float x = __fsub_rn((float)ix, shiftxc);
+        const float xold = __fadd_rn(__fmul_rn(x, cang), ysang);
+        const float yold = __fadd_rn(__fmul_rn(x, sang), ycang);
+        const float v = quadri_bg(__fadd_rn(xold, 1.0f), __fadd_rn(yold, 1.0f), nx, s_img, ix + 1, iy + 1);
         const int ixd = (mirror && ix >= x_start) ? (x_start + nx - 1 - ix) : ix;
         const int o = iy * nx + ixd;
         if (dst) atomicAdd(dst + o, v);

@@ -60,7 +60,7 @@ CORE_SYMBOLS = ["cra_create", "cra_destroy", "cra_last_error", "cra_ring_info", 
                 "cra_upload_particles_dev", "cra_upload_particles_async", "cra_upload_wait", "cra_mref_search_request",
                 "cra_compose_result", "cra_reffree_search_request", "cra_fit_tanh", "cra_set_refs", "cra_align", "cra_align_bound", "cra_refs_from_sums", "cra_filter_refs",
                 "cra_class_fsc", "cra_put_ref", "cra_filter_center_refs", "cra_prepare_refs",
-                "cra_get_refs", "cra_accumulate", "cra_zero_sums",
+                "cra_get_refs", "cra_accumulate", "cra_accumulate_d", "cra_transform_d", "cra_zero_sums",
                 "cra_sums_device_ptr", "cra_get_sums", "cra_transform", "cra_transform_dev", "cra_polar_spectrum", "cra_ref_spectrum", "cra_batch_row_spectrum",
                 "cra_ccf_curves", "cra_last_align_stats", "cra_set_timing", "cra_set_normalize_ring", "cra_set_step",
                 "cra_row_batch", "cra_device_images_ptr", "cra_stream", "cra_measure_fp32_peak"]
@@ -107,10 +107,12 @@ def load_library(path=None):
     L.cra_filter_center_refs.argtypes = [vp, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_int, vp]
     L.cra_prepare_refs.argtypes = [vp, C.c_int]
     L.cra_accumulate.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_long]
+    L.cra_accumulate_d.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_long]
     L.cra_zero_sums.argtypes = [vp]
     L.cra_sums_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.cra_get_sums.argtypes = [vp, vp, vp]
     L.cra_transform.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    L.cra_transform_d.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     L.cra_transform_dev.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     L.cra_polar_spectrum.argtypes = [vp, C.c_int, C.c_float, C.c_float, vp]
     L.cra_ref_spectrum.argtypes = [vp, C.c_int, vp]
@@ -306,11 +308,11 @@ class Engine(object):
         return out
 
     def accumulate(self, start, stop, params, iref, global_offset=0):
-        params = np.ascontiguousarray(params, np.float32)
+        params = np.ascontiguousarray(params, np.float64)       # doubles, as the reference's Python holds them
         iref = np.ascontiguousarray(iref, np.int32)
         assert params.shape == (stop - start, 4) and iref.shape[0] == stop - start
-        self._ck(self.L.cra_accumulate(self.h, int(start), int(stop), params.ctypes.data, iref.ctypes.data,
-                                       int(global_offset)))
+        self._ck(self.L.cra_accumulate_d(self.h, int(start), int(stop), params.ctypes.data, iref.ctypes.data,
+                                         int(global_offset)))
 
     def zero_sums(self):
         self._ck(self.L.cra_zero_sums(self.h))
@@ -334,9 +336,9 @@ class Engine(object):
         return p.value, n.value
 
     def transform(self, start, stop, params):
-        params = np.ascontiguousarray(params, np.float32)
+        params = np.ascontiguousarray(params, np.float64)
         out = np.zeros((stop - start, self.nx, self.nx), np.float32)
-        self._ck(self.L.cra_transform(self.h, int(start), int(stop), params.ctypes.data, out.ctypes.data))
+        self._ck(self.L.cra_transform_d(self.h, int(start), int(stop), params.ctypes.data, out.ctypes.data))
         return out
 
     # ---- stage-level (tests)

@@ -167,6 +167,12 @@ int  cra_fit_tanh(int n, const double* freq, const double* target, double fl0, d
  * skips the particle.  global_offset is the global index of particle `start`. */
 int  cra_accumulate(CraCtx* ctx, int start, int stop, const float* params, const int* iref,
                     long global_offset);
+/* The same with the parameters in double, as the reference's Python holds them (test_mref.py:206-210).  They are
+ * rounded to float exactly where EMAN2 does it -- rot_scale_trans2D_background takes float arguments -- and the angle is
+ * then converted to radians in double and rounded once (float ang = angDeg * M_PI / 180.0f), which pins the quadri
+ * cell of every output pixel.                                                                                      */
+int  cra_accumulate_d(CraCtx* ctx, int start, int stop, const double* params, const int* iref,
+                      long global_offset);
 int  cra_zero_sums(CraCtx* ctx);
 /* Device pointers (owned by ctx) of the packed [R][2][nx][nx] f32 sums followed
  * by [R] f32 counts: one contiguous buffer so a single NCCL allreduce covers
@@ -177,6 +183,7 @@ int  cra_get_sums(CraCtx* ctx, float* host_sums /*[R][2][nx][nx]*/, float* host_
 /* rot_shift2D only: transformed images of [start,stop) to a host buffer
  * (ref-free sum_oe / apply-transform export).                               */
 int  cra_transform(CraCtx* ctx, int start, int stop, const float* params, float* host_out);
+int  cra_transform_d(CraCtx* ctx, int start, int stop, const double* params, float* host_out);
 /* The same into a caller-owned DEVICE buffer [stop-start][nx][nx] (what mref_align_run hands back,
  * gpu_aln_noref.cu:389-416: the transformed images never leave the GPU).                       */
 int  cra_transform_dev(CraCtx* ctx, int start, int stop, const float* params, float* dev_out);
