@@ -748,11 +748,12 @@ static int align_impl(CraCtx* c, int start, int stop, const CraSearch* search, c
     std::vector<char> bgroup(nb, 0);
     memcpy(h_search, search, (size_t)n * sizeof(CraSearch));
     long total_rows = 0;
-    // the grouped row kernel needs a whole-pixel step and every sample in [1, nx + 1) (its tile has a
-    // one-pixel periodic border; search_range keeps samples in [2, nx])
+    // the grouped row kernel needs a step its phase classes cover and every sample in [2, nx] (1-based), which is
+    // what search_range guarantees: its tile is the bare image, and only a sample exactly on the last column / row
+    // (a pixel boundary: redone with quadri's circular closure) may touch the wrap-around neighbour
     const int sub = cra_group_sub(step);                       // phase classes per axis (0: the general kernel)
     const bool group_cfg = c->fmt == CRA_FMT_FRAG && c->use_group && c->plan.rmax > 0 && sub > 0;
-    const float rmaxf = (float)c->htab.rad[c->htab.nring - 1], lo_ok = 1.0f + rmaxf, hi_ok = (float)c->nx + 0.5f - rmaxf;
+    const float rmaxf = (float)c->htab.rad[c->htab.nring - 1], lo_ok = 2.0f + rmaxf, hi_ok = (float)c->nx - rmaxf;
     for (size_t bi = 0; bi < nb; ++bi) {
         int* rs = h_rs + bfirst[bi] + bi;
         int* cs = h_cs + bfirst[bi] + bi;

@@ -15,12 +15,15 @@
 //   -> real-FFT split (index math shared by the rows) -> split-bf16 + 32-byte unit stores.
 // Normalize_ring is deferred (cra_common.cuh): the spectrum of the raw polar image is stored and
 // (avg, 1/sigma) goes to norm[row]; the CCF kernel applies it when it emits a candidate.
-// The shared-memory tile carries a one-pixel periodic border (quadri's circular closure), so any
-// sample with 1 <= x, y < nx + 1 needs no wrap logic; search_range keeps every sample in [2, nx].
-// Requirements checked by the host (cra_api.cu): integral step and that sample range; otherwise
+// The shared-memory tile is the image itself, dense, filled by ONE bulk asynchronous copy (TMA, cra_tma.cuh)
+// that runs under the CTA's table set-up.  search_range keeps every sample in [2, nx] (1-based), so the six taps
+// of a sample stay inside the image except for a sample exactly on the last column / row -- which sits on a pixel
+// boundary and is therefore redone by repair_sample, with quadri's circular closure written out.
+// Requirements checked by the host (cra_api.cu): a step the phase classes cover and that sample range; otherwise
 // the general kernel of cra_polar.cu runs.
 #include "cra_common.cuh"
 #include "cra_fft.cuh"
+#include "cra_tma.cuh"
 #include <cuda_bf16.h>
 
 namespace {
@@ -112,7 +115,7 @@ __device__ __forceinline__ int fastdiv(int w, int magic) { return (int)(((unsign
 // (x = offset + the row's own centre) and interpolated with quadri's own expression; the Normalize_ring
 // sums of the row are corrected through s_fix.
 __device__ __forceinline__ void repair_sample(int code, int r, const float4* __restrict__ samp, const int4* s_ring,
-                                              const float2* s_rowc, const float* s_img, int pitch, float* s_buf,
+                                              const float2* s_rowc, const float* s_img, int nx, float* s_buf,
                                               int stride, float* s_fix)
 {
     const int q = code >> 2, m = code & 3;
@@ -125,13 +128,15 @@ __device__ __forceinline__ void repair_sample(int code, int r, const float4* __r
     const int sl = 2 * (rp.x + pp + (pp >> rp.y)) + (j & 1);
     const float2 c = s_rowc[r];
     const float X = fx + c.x, Y = fy + c.y;
-    const int ix = (int)X, iy = (int)Y;
+    const int ix = (int)X, iy = (int)Y;                       // 1-based cell, 1 <= ix, iy <= nx
     const float dx = X - (float)ix, dy = Y - (float)iy;
-    const float* p = s_img + iy * pitch + ix;
-    const float f0 = p[0];
-    const float c1 = p[1] - f0, c2 = (c1 - f0 + p[-1]) * 0.5f;
-    const float c3 = p[pitch] - f0, c4 = (c3 - f0 + p[-pitch]) * 0.5f;
-    const float c5 = p[pitch + 1] - f0 - c1 - c3;
+    // quadri's circular closure of the neighbours (Util::quadri: ip1 > nx -> ip1 - nx, im1 < 1 -> im1 + nx)
+    const int x0 = ix - 1, xp = (ix + 1 > nx) ? 0 : ix, xm = (ix - 1 < 1) ? nx - 1 : ix - 2;
+    const int y0 = iy - 1, yp = (iy + 1 > nx) ? 0 : iy, ym = (iy - 1 < 1) ? nx - 1 : iy - 2;
+    const float f0 = s_img[y0 * nx + x0];
+    const float c1 = s_img[y0 * nx + xp] - f0, c2 = (c1 - f0 + s_img[y0 * nx + xm]) * 0.5f;
+    const float c3 = s_img[yp * nx + x0] - f0, c4 = (c3 - f0 + s_img[ym * nx + x0]) * 0.5f;
+    const float c5 = s_img[yp * nx + xp] - f0 - c1 - c3;
     const float v = f0 + dx * (c1 + (dx - 1.0f) * c2 + dy * c5) + dy * (c3 + (dy - 1.0f) * c4);
     float* dst = s_buf + r * stride;
     const float old = dst[sl];
@@ -150,9 +155,9 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
     const int npix = nx * nx;
     const int maxrin = tab->maxrin, nring = tab->nring;
     const int stride = plan.stride;                            // floats per row of the phase buffer
-    const int pitch = nx + 2;                                  // tile with a one-pixel periodic border
-    float* s_img = smem;                                       // pitch * pitch (padded to 4)
-    float* s_buf = smem + ((pitch * pitch + 3) & ~3);          // rmax * stride
+    const int pitch = nx;                                      // dense tile: 1-based pixel (i, j) sits at (j - 1) * nx + (i - 1)
+    float* s_img = smem;                                       // nx * nx (padded to 4)
+    float* s_buf = smem + ((npix + 3) & ~3);                   // rmax * stride
     float2* s_tw = reinterpret_cast<float2*>(s_buf + plan.rmax * stride);   // maxrin : exp(-2 pi i j / maxrin)
     int4* s_ring = reinterpret_cast<int4*>(s_tw + maxrin);    // nring : phase-local float2 offset, log2 NB, len/4, wn
     int* s_koff = reinterpret_cast<int*>(s_ring + nring);     // maxrin/2 + 2 : first chunk of frequency k
@@ -167,12 +172,23 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
     __shared__ int s_nfrag[kThreads / 32];                          // Normalize_ring sum corrections of the fragile samples                            // the reference's own centre of every row
     __shared__ int s_blk[4];                                   // particle (batch local), first local row, rows
     __shared__ float s_base[2];
+    __shared__ __align__(8) unsigned long long s_bar;          // completion of the image tile's bulk copy
 
     const int tid = threadIdx.x;
     if (tid == 0) {
         const int b = blockIdx.x;
         int lo = 0, hi = map.np;               // last p with chunk_start[p] <= b
         while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (map.chunk_start[mid] <= b) lo = mid; else hi = mid; }
+        // the image tile: one bulk asynchronous copy, in flight while the tables below are set up
+        {
+            const float* img = images + (size_t)(map.p0 + lo) * npix;
+            const bool bulk = cratma::bulk_ok(img, (size_t)npix * sizeof(float));
+            s_blk[3] = bulk ? 2 : 0;
+            if (bulk) {
+                cratma::mbar_init(&s_bar, 1);
+                cratma::bulk_load(s_img, img, (unsigned)(npix * sizeof(float)), &s_bar);
+            }
+        }
         const int bi = b - map.chunk_start[lo];
         const int4 w = map.win[lo];
         const int wx = w.x + w.y + 1, wy = w.z + w.w + 1;
@@ -192,7 +208,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
             left -= nblk_c;
         }
         const int r_lo = (int)(((long)left * rows_c) / nblk_c), r_hi = (int)(((long)(left + 1) * rows_c) / nblk_c);
-        s_blk[0] = lo; s_blk[1] = r_lo; s_blk[2] = r_hi - r_lo; s_blk[3] = (sub == 1) ? 1 : 0;
+        s_blk[0] = lo; s_blk[1] = r_lo; s_blk[2] = r_hi - r_lo; s_blk[3] |= (sub == 1) ? 1 : 0;
         s_base[0] = map.search[lo].cx + (float)(cx - w.x) * map.step;
         s_base[1] = map.search[lo].cy + (float)(cy - w.z) * map.step;
         unsigned same = 0;
@@ -218,36 +234,19 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
     }
     __syncthreads();
     const int nr = s_blk[2];
-    const bool contig = s_blk[3] != 0;                         // block rows are consecutive rows of the batch
+    const bool contig = (s_blk[3] & 1) != 0;                   // block rows are consecutive rows of the batch
     {
-        // padded (Y, X), 0 <= X, Y <= nx+1, holds pixel ((Y-1) mod nx, (X-1) mod nx): 1-based pixel (i, j) sits at (j, i)
         const float* img = images + (size_t)(map.p0 + s_blk[0]) * npix;
         // A particle uploaded without normalize.mask still carries its in-mask mean.  Normalize_ring cancels any
         // constant exactly in exact arithmetic, but here it is deferred past the split-bf16 contraction, where a large
         // ring DC term would cost digits: remove the constant up front.
         const float dcv = (normalize_ring && map.dc) ? __ldg(map.dc + map.p0 + s_blk[0]) : 0.f;
-        if ((npix & 3) == 0) {                 // interior: the image as one stream of 128-bit loads
-            const float4* g4 = reinterpret_cast<const float4*>(img);
-            for (int i = tid; i < (npix >> 2); i += kThreads) {
-                const float4 v = __ldg(g4 + i);
-                const float e[4] = {v.x - dcv, v.y - dcv, v.z - dcv, v.w - dcv};
-                int y = (4 * i) / nx, x = 4 * i - y * nx;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    s_img[(y + 1) * pitch + x + 1] = e[k];
-                    if (++x == nx) { x = 0; ++y; }
-                }
-            }
+        if (s_blk[3] & 2) {
+            cratma::mbar_wait(&s_bar, 0);                      // the bulk copy has landed
+            if (dcv != 0.f)                                    // every waiting thread sees the whole tile
+                for (int i = tid; i < npix; i += kThreads) s_img[i] -= dcv;
         } else {
-            for (int i = tid; i < npix; i += kThreads) { const int y = i / nx; s_img[(y + 1) * pitch + (i - y * nx) + 1] = __ldg(img + i) - dcv; }
-        }
-        for (int b = tid; b < 2 * pitch + 2 * nx; b += kThreads) {      // the periodic border, straight from global
-            int Y, X;
-            if (b < 2 * pitch) { Y = (b < pitch) ? 0 : nx + 1; X = (b < pitch) ? b : b - pitch; }
-            else { const int c = b - 2 * pitch; Y = 1 + (c >> 1); X = (c & 1) ? nx + 1 : 0; }
-            const int sy = (Y == 0) ? nx - 1 : ((Y == nx + 1) ? 0 : Y - 1);
-            const int sx = (X == 0) ? nx - 1 : ((X == nx + 1) ? 0 : X - 1);
-            s_img[Y * pitch + X] = __ldg(img + sy * nx + sx) - dcv;
+            for (int i = tid; i < npix; i += kThreads) s_img[i] = __ldg(img + i) - dcv;
         }
     }
     const float bx = s_base[0], by = s_base[1];
@@ -287,7 +286,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                 const float w4 = b2;                    // (i, j-1)
                 const float w5 = ab;                    // (i+1, j+1)
                 const float w0 = 1.0f - dx - dy - 2.0f * a2 - 2.0f * b2 + ab;
-                const float* p0 = s_img + (iy * pitch + ix);
+                const float* p0 = s_img + (iy * pitch + ix) - (pitch + 1);     // 1-based cell (ix, iy)
                 float* dst = s_buf + slot;
                 // a row that continues the window line of the previous one (one pixel to the right) reuses
                 // three of its taps: (i-1,j) <- (i,j), (i,j) <- (i+1,j), (i,j+1) <- (i+1,j+1)
@@ -320,7 +319,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                         if (at < kFragCap) s_frag[tid >> 5][at] = q * 4 + m;
                         else                // queue full (an integer or half-integer centre puts whole rings on cell
                             for (int r = 0; r < nr; ++r)    // boundaries): this lane repairs its own sample right away
-                                repair_sample(q * 4 + m, r, samp, s_ring, s_rowc, s_img, pitch, s_buf, stride, s_fix);
+                                repair_sample(q * 4 + m, r, samp, s_ring, s_rowc, s_img, nx, s_buf, stride, s_fix);
                     }
             }
         }
@@ -332,7 +331,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
             const int nf = min(s_nfrag[wid], kFragCap);
             for (int x = tid & 31; x < nf * nr; x += 32) {
                 const int en = x / nr, r = x - en * nr;
-                repair_sample(s_frag[wid][en], r, samp, s_ring, s_rowc, s_img, pitch, s_buf, stride, s_fix);
+                repair_sample(s_frag[wid][en], r, samp, s_ring, s_rowc, s_img, nx, s_buf, stride, s_fix);
             }
         }
         __syncthreads();
@@ -512,7 +511,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
 
 size_t cra_polar_group_smem(int nx, int maxrin, const CraGroupPlan& plan)
 {
-    const size_t npix = ((size_t)(nx + 2) * (nx + 2) + 3) & ~(size_t)3;     // tile with the periodic border
+    const size_t npix = ((size_t)nx * nx + 3) & ~(size_t)3;                 // the dense image tile
     // + twiddles, ring table (<= CRA_MAX_RINGS int4), chunk offsets, unit lengths
     return (npix + (size_t)plan.rmax * plan.stride) * sizeof(float) + (size_t)maxrin * sizeof(float2)
          + (size_t)plan.nring * sizeof(int4) + (size_t)(maxrin / 2 + 2 + (plan.nring + 3) / 4) * sizeof(int);

@@ -12,6 +12,7 @@
 // Also holds the FP32 FMA peak micro-benchmark used as the roofline denominator of
 // the CCF kernel.
 #include "cra_common.cuh"
+#include "cra_tma.cuh"
 
 namespace {
 
@@ -55,15 +56,20 @@ rotsum_kernel(const float* __restrict__ images, int nx, int p0, const float4* __
     if (iref && ref < 0) return;
     const int npix = nx * nx;
     const float* img = images + (size_t)(p0 + p) * npix;
-    if ((npix & 3) == 0) {
-        const float4* g4 = reinterpret_cast<const float4*>(img);
-        float4* s4 = reinterpret_cast<float4*>(s_img);
-        for (int i = threadIdx.x; i < (npix >> 2); i += blockDim.x) s4[i] = __ldg(g4 + i);
+    // the image tile: one bulk asynchronous copy (TMA) when the image is 16-byte granular, else a cooperative load
+    __shared__ __align__(8) unsigned long long s_bar;
+    const bool bulk = cratma::bulk_ok(img, (size_t)npix * sizeof(float));
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            cratma::mbar_init(&s_bar, 1);
+            cratma::bulk_load(s_img, img, (unsigned)(npix * sizeof(float)), &s_bar);
+        }
     } else {
         for (int i = threadIdx.x; i < npix; i += blockDim.x) s_img[i] = __ldg(img + i);
     }
-    __syncthreads();
     const float4 pr = params[p];
+    __syncthreads();                           // the barrier's initialisation (or the cooperative load) is visible
+    if (bulk) cratma::mbar_wait(&s_bar, 0);
     const float ang = pr.x;                    // radians, rounded to float by the host (cra_api.cu: pack_par)
     const float delx = restrict2(pr.y, nx), dely = restrict2(pr.z, nx);
     const int mirror = pr.w > 0.5f;

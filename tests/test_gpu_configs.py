@@ -377,7 +377,7 @@ def test_pixel_boundary_samples_ou60(oracle):
     holds).  Every spectrum row must still match the oracle."""
     from cryo_ralib_b200 import synth
     from cryo_ralib_b200.lib import SEARCH_DTYPE
-    nx, ou, P = 128, 60, 6
+    nx, ou, P = 128, 60, 8
     images, _ = synth.make_particles(P, nx, 8, max_shift=1, seed=3)
     mask = oracle.model_circle(ou, nx)
     numr = oracle.numrinit(1, ou, 1)
@@ -386,15 +386,20 @@ def test_pixel_boundary_samples_ou60(oracle):
     e = _engine(nx, ou, 1, P=P, R=2)
     e.upload_particles(images); e.set_refs(refs)
     search = np.zeros(P, SEARCH_DTYPE)
-    centres = [(65.0, 65.0), (64.5, 65.5), (65.5, 64.0), (64.0, 66.0), (65.25, 64.75), (66.0, 64.5)]
+    centres = [(65.0, 65.0), (64.5, 65.5), (65.5, 64.0), (64.0, 66.0), (65.25, 64.75), (66.0, 64.5), (68.0, 68.0), (63.0, 68.0)]
+    wins = [(1, 1, 1, 1)] * 6 + [(1, 0, 1, 0), (0, 1, 1, 0)]
+    # the last two touch the frame as far as search_range lets a particle go (cx + ou = nx, cx - ou = 2 + 1): samples
+    # exactly on the last column / row, whose right / upper neighbour is quadri's wrap-around pixel
     for p, (cx, cy) in enumerate(centres):
-        search[p] = (cx, cy, 1, 1, 1, 1)
+        search[p] = (cx, cy) + wins[p]
     e.align(0, P, search)
     row = 0
     for p, (cx, cy) in enumerate(centres):
-        for iy in (-1, 0, 1):
-            for ix in (-1, 0, 1):
+        xl, xr_, yl, yr_ = wins[p]
+        for iy in range(-yl, yr_ + 1):
+            for ix in range(-xl, xr_ + 1):
                 got, kernel = e.batch_row_spectrum(row)
+                assert kernel == 1, "the grouped row kernel should have handled this batch"
                 c = oracle.normalize_ring(oracle.polar2dm(imgs[p], cx + ix, cy + iy, numr), numr)
                 want = oracle.frngs(c, numr)
                 scale = np.abs(want).max()
