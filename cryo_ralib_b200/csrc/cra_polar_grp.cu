@@ -250,6 +250,8 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
         }
     }
     const float bx = s_base[0], by = s_base[1];
+    // whole-pixel centres in every row of the block: the base centre is a whole number and the rows lie whole pixels apart
+    const bool cint_x = bx == rintf(bx), cint_y = by == rintf(by);
     const unsigned samemask = s_samemask;
     float av[RMAX], sq[RMAX];
 #pragma unroll
@@ -277,7 +279,12 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                 const float X = ox[m] + bx, Y = oy[m] + by;
                 const int ix = (int)X, iy = (int)Y;
                 const float dx = X - (float)ix, dy = Y - (float)iy;
-                if (dx < 1e-4f || dx > 0.9999f || dy < 1e-4f || dy > 0.9999f) fragile |= 1 << m;
+                // A coordinate that is a whole number because BOTH its ring offset and the block's centre are whole
+                // numbers (the axis points of every ring under an integer centre: all of mref_ali2d) is exact in every
+                // row -- offset + centre is an integer sum -- so it cannot round into another cell.
+                const bool xf = (dx < 1e-4f || dx > 0.9999f) && !(cint_x && ox[m] == rintf(ox[m]));
+                const bool yf = (dy < 1e-4f || dy > 0.9999f) && !(cint_y && oy[m] == rintf(oy[m]));
+                if (xf || yf) fragile |= 1 << m;
                 // quadri: f0 + dx (c1 + (dx-1) c2 + dy c5) + dy (c3 + (dy-1) c4) as six tap weights
                 const float a2 = 0.5f * dx * (dx - 1.0f), b2 = 0.5f * dy * (dy - 1.0f), ab = dx * dy;
                 const float w1 = dx + a2 - ab;          // (i+1, j)
