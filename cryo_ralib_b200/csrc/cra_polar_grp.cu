@@ -172,56 +172,55 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
     __shared__ int s_nfrag[kThreads / 32];                          // Normalize_ring sum corrections of the fragile samples                            // the reference's own centre of every row
     __shared__ int s_blk[4];                                   // particle (batch local), first local row, rows
     __shared__ float s_base[2];
+    __shared__ int s_cls[4];                                   // phase class of the block: cx, cy, rows per window line, sub
     __shared__ __align__(8) unsigned long long s_bar;          // completion of the image tile's bulk copy
 
     const int tid = threadIdx.x;
-    if (tid == 0) {
+    if (tid < 32) {
+        // Which particle this CTA belongs to: the last p with chunk_start[p] <= blockIdx.x, by a 32-ary search of
+        // warp 0 (three rounds of one load per lane for ~1600 particles, against eleven dependent loads of a binary
+        // search: the whole CTA waits for this).
         const int b = blockIdx.x;
-        int lo = 0, hi = map.np;               // last p with chunk_start[p] <= b
-        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (map.chunk_start[mid] <= b) lo = mid; else hi = mid; }
-        // the image tile: one bulk asynchronous copy, in flight while the tables below are set up
-        {
+        int lo = 0, hi = map.np;                               // chunk_start[lo] <= b < chunk_start[hi]
+        while (hi - lo > 1) {
+            const int stepw = (hi - lo + 31) >> 5;
+            const int pos = lo + (tid + 1) * stepw;
+            const bool le = (pos < hi) && (__ldg(map.chunk_start + pos) <= b);
+            const int k = __popc(__ballot_sync(0xffffffffu, le));  // the probes are monotone: a prefix answers "<="
+            hi = min(lo + (k + 1) * stepw, hi);
+            lo = lo + k * stepw;
+        }
+        if (tid == 0) {
+            // the image tile: one bulk asynchronous copy, in flight while the tables below are set up
             const float* img = images + (size_t)(map.p0 + lo) * npix;
             const bool bulk = cratma::bulk_ok(img, (size_t)npix * sizeof(float));
-            s_blk[3] = bulk ? 2 : 0;
             if (bulk) {
                 cratma::mbar_init(&s_bar, 1);
                 cratma::bulk_load(s_img, img, (unsigned)(npix * sizeof(float)), &s_bar);
             }
+            const int bi = b - map.chunk_start[lo];
+            const int4 w = map.win[lo];
+            const int wx = w.x + w.y + 1, wy = w.z + w.w + 1;
+            // A step of 1/sub pixel (sub = 2, 4) splits the window into sub x sub phase classes: the positions
+            // (cx + sub i, cy + sub j) of a class lie one whole pixel apart and share their tap weights.  Blocks
+            // never cross a class; with a whole-pixel step there is one class and the rows are consecutive.
+            const int sub = cra_group_sub(map.step);
+            int cx = 0, cy = 0, ncx = wx, rows_c = wx * wy, nblk_c = 1, left = bi;
+            for (int c = 0; c < sub * sub; ++c) {
+                cy = c / sub; cx = c - cy * sub;
+                ncx = (wx - cx + sub - 1) / sub;
+                const int ncy = (wy - cy + sub - 1) / sub;
+                rows_c = ncx * ncy;
+                nblk_c = (rows_c + plan.rmax - 1) / plan.rmax;
+                if (left < nblk_c) break;
+                left -= nblk_c;
+            }
+            const int r_lo = (int)(((long)left * rows_c) / nblk_c), r_hi = (int)(((long)(left + 1) * rows_c) / nblk_c);
+            s_blk[0] = lo; s_blk[1] = r_lo; s_blk[2] = r_hi - r_lo; s_blk[3] = (bulk ? 2 : 0) | ((sub == 1) ? 1 : 0);
+            s_cls[0] = cx; s_cls[1] = cy; s_cls[2] = ncx; s_cls[3] = sub;
+            s_base[0] = map.search[lo].cx + (float)(cx - w.x) * map.step;
+            s_base[1] = map.search[lo].cy + (float)(cy - w.z) * map.step;
         }
-        const int bi = b - map.chunk_start[lo];
-        const int4 w = map.win[lo];
-        const int wx = w.x + w.y + 1, wy = w.z + w.w + 1;
-        // A step of 1/sub pixel (sub = 2, 4) splits the window into sub x sub phase classes: the positions
-        // (cx + sub i, cy + sub j) of a class lie one whole pixel apart and share their tap weights.  Blocks
-        // never cross a class; with a whole-pixel step there is one class and the rows are consecutive.
-        const int sub = cra_group_sub(map.step);
-        const int pxs = (sub > 1) ? 1 : (int)map.step;         // pixels between neighbouring rows of a class
-        int cx = 0, cy = 0, ncx = wx, rows_c = wx * wy, nblk_c = 1, left = bi;
-        for (int c = 0; c < sub * sub; ++c) {
-            cy = c / sub; cx = c - cy * sub;
-            ncx = (wx - cx + sub - 1) / sub;
-            const int ncy = (wy - cy + sub - 1) / sub;
-            rows_c = ncx * ncy;
-            nblk_c = (rows_c + plan.rmax - 1) / plan.rmax;
-            if (left < nblk_c) break;
-            left -= nblk_c;
-        }
-        const int r_lo = (int)(((long)left * rows_c) / nblk_c), r_hi = (int)(((long)(left + 1) * rows_c) / nblk_c);
-        s_blk[0] = lo; s_blk[1] = r_lo; s_blk[2] = r_hi - r_lo; s_blk[3] |= (sub == 1) ? 1 : 0;
-        s_base[0] = map.search[lo].cx + (float)(cx - w.x) * map.step;
-        s_base[1] = map.search[lo].cy + (float)(cy - w.z) * map.step;
-        unsigned same = 0;
-        for (int r = 0; r < r_hi - r_lo; ++r) {
-            const int t = r_lo + r, ty = t / ncx, tx = t - ty * ncx;
-            const int lix = cx + tx * sub, liy = cy + ty * sub;
-            if (r > 0 && pxs == 1 && tx != 0) same |= 1u << r;
-            s_grow[r] = map.row_start[lo] + liy * wx + lix;
-            s_rowoff[r] = ty * pxs * pitch + tx * pxs;
-            s_rowc[r] = make_float2(map.search[lo].cx + (float)(lix - w.x) * map.step,
-                                    map.search[lo].cy + (float)(liy - w.z) * map.step);
-        }
-        s_samemask = same;
     }
     for (int i = tid; i < maxrin; i += kThreads) s_tw[i] = twid[i];
     if (tid < 2 * RMAX) s_fix[tid] = 0.f;
@@ -235,6 +234,25 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
     __syncthreads();
     const int nr = s_blk[2];
     const bool contig = (s_blk[3] & 1) != 0;                   // block rows are consecutive rows of the batch
+    if (tid < 32) {                                            // the block's rows, one lane each (published by the barrier below)
+        const int lo = s_blk[0], r = tid;
+        const int cx = s_cls[0], cy = s_cls[1], ncx = s_cls[2], sub = s_cls[3];
+        const int pxs = (sub > 1) ? 1 : (int)map.step;         // pixels between neighbouring rows of a class
+        bool cont = false;
+        if (r < nr) {
+            const int4 w = map.win[lo];
+            const int wx = w.x + w.y + 1;
+            const int t = s_blk[1] + r, ty = t / ncx, tx = t - ty * ncx;
+            const int lix = cx + tx * sub, liy = cy + ty * sub;
+            cont = r > 0 && pxs == 1 && tx != 0;               // one pixel right of the previous row
+            s_grow[r] = map.row_start[lo] + liy * wx + lix;
+            s_rowoff[r] = ty * pxs * pitch + tx * pxs;
+            s_rowc[r] = make_float2(map.search[lo].cx + (float)(lix - w.x) * map.step,
+                                    map.search[lo].cy + (float)(liy - w.z) * map.step);
+        }
+        const unsigned same = __ballot_sync(0xffffffffu, cont);
+        if (tid == 0) s_samemask = same;
+    }
     {
         const float* img = images + (size_t)(map.p0 + s_blk[0]) * npix;
         // A particle uploaded without normalize.mask still carries its in-mask mean.  Normalize_ring cancels any
@@ -252,11 +270,11 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
     const float bx = s_base[0], by = s_base[1];
     // whole-pixel centres in every row of the block: the base centre is a whole number and the rows lie whole pixels apart
     const bool cint_x = bx == rintf(bx), cint_y = by == rintf(by);
-    const unsigned samemask = s_samemask;
     float av[RMAX], sq[RMAX];
 #pragma unroll
     for (int r = 0; r < RMAX; ++r) { av[r] = 0.f; sq[r] = 0.f; }
     __syncthreads();
+    const unsigned samemask = s_samemask;
 
     for (int ph = 0; ph < plan.nphase; ++ph) {
         const CraPhase P = plan.phases[ph];
