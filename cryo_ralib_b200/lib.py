@@ -77,7 +77,7 @@ def load_library(path=None):
     global _LIB
     if _LIB is not None and path is None:
         return _LIB
-    path = path or SO_PATH
+    path = path or os.environ.get("CRA_LIBRARY") or SO_PATH        # CRA_LIBRARY: another build of the same library (experiments)
     if not os.path.exists(path):
         raise LibraryMissing("%s not found: build it with `python -m cryo_ralib_b200.build` "
                              "(there is no CPU fallback)" % path)
@@ -150,7 +150,7 @@ def load_library(path=None):
     L.ref_free_alignment_2D_size_check.argtypes = [C.POINTER(AlignConfig), C.c_uint, C.c_float, C.c_bool]
     L.ref_free_alignment_2D.argtypes = []
     L.ref_free_alignment_2D_filter_references.argtypes = [C.c_float, C.c_float]
-    if path == SO_PATH:
+    if path == SO_PATH or path == os.environ.get("CRA_LIBRARY"):
         _LIB = L
     return L
 
