@@ -452,3 +452,34 @@ def test_device_reference_update_matches_oracle(oracle, small_set):
     b = np.stack([e.ref_spectrum(j) for j in range(R)])
     assert np.array_equal(a, b)
     e.close()
+
+
+def test_engine_against_golden_fixture():
+    """The committed fixture tests/golden/oracle_mref_case.npz (inputs + oracle outputs, written by
+    tests/golden/make_oracle_case.py): alignment rows, one spectrum, class sums and the updated references through
+    the C ABI -- without building or calling the oracle."""
+    from cryo_ralib_b200 import alignment as al
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_mref_case.npz"))
+    nx, ou, xr = int(g["nx"]), int(g["ou"]), int(g["xr"])
+    images, refs, want = g["images"], g["refs"], g["align_rows"]
+    P, R = images.shape[0], refs.shape[0]
+    e = _engine(nx, ou, xr, P=P, R=R)
+    e.upload_particles(images); e.set_refs(refs)
+    search, sxi, syi, _ = al.mref_search_request(np.zeros((P, 4)), nx, ou, xr, xr)
+    res = e.align(0, P, search)
+    maxrin = int(g["numr"][-1])
+    same, rel, dang = _classify(res, want, maxrin)
+    assert np.all(same | (rel < TIE_BAND)) and rel[same].max() <= PEAK_RTOL
+    assert (dang[same] <= 0.5 * 360.0 / maxrin).all()
+    cnx = nx // 2 + 1
+    spec = e.polar_spectrum(0, cnx + 1.0, cnx - 2.0)
+    assert np.abs(spec - g["spec0"]).max() <= 2e-5 * np.abs(g["spec0"]).max()
+    e.zero_sums(); e.accumulate(0, P, g["params1"], g["assign"], 0)
+    sums, counts = e.get_sums()
+    assert np.array_equal(counts[:R], g["counts"])
+    assert np.abs(sums[:R] - g["sums"]).max() <= 1e-5 * np.abs(g["sums"]).max()
+    if (g["counts"] >= 4).all():
+        got, info = e.update_refs_device(center=1, reseed=None)
+        assert np.allclose(info["filter"], g["filter"], rtol=2e-4)
+        assert np.abs(got - g["new_refs"]).max() <= 5e-5 * np.abs(g["new_refs"]).max()
+    e.close()

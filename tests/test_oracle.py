@@ -203,3 +203,31 @@ def test_class_bound_oracle_recovers_rotations(oracle):
         a, b = r[c][inside], base[c][inside]                     # noisy images rotated twice: compare by correlation
         cc = float(np.corrcoef(a, b)[0, 1])
         assert cc > 0.85, cc
+
+
+def test_oracle_reproduces_golden_case(oracle):
+    """tests/golden/oracle_mref_case.npz (written by tests/golden/make_oracle_case.py): the oracle still gives the stored
+    outputs bit for bit -- a guard against drift of the checker itself."""
+    import os
+    import random
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_mref_case.npz"))
+    nx, ou, xr = int(g["nx"]), int(g["ou"]), int(g["xr"])
+    images, refs = g["images"], g["refs"]
+    mask = oracle.model_circle(ou, nx)
+    numr = oracle.numrinit(1, ou, 1)
+    assert np.array_equal(numr, g["numr"])
+    _, cref = oracle.prepare_refs(refs, mask, numr)
+    assert np.array_equal(cref, g["cref"])
+    P = images.shape[0]
+    p1, assign, peak, sums, counts = oracle.mref_iteration(images.copy(), mask, cref, numr, xr, xr, 1, ou, np.zeros((P, 4)), 0, True, 1)
+    assert np.array_equal(assign, g["assign"]) and np.array_equal(p1, g["params1"])
+    assert np.array_equal(peak, g["peak"]) and np.array_equal(sums, g["sums"]) and np.array_equal(counts, g["counts"])
+    imgs = np.stack([oracle.normalize_mask(im, mask, 0) for im in images])
+    cnx = nx // 2 + 1
+    rows = oracle.align_batch(imgs, cref, numr, np.full((P, 2), float(cnx), np.float32), np.full((P, 4), float(xr), np.float32), 1.0, True, 1)
+    assert np.array_equal(rows, g["align_rows"])
+    spec0 = oracle.frngs(oracle.normalize_ring(oracle.polar2dm(imgs[0], cnx + 1.0, cnx - 2.0, numr), numr), numr)
+    assert np.array_equal(spec0, g["spec0"])
+    new_refs, info = oracle.update_refs(sums, counts, imgs, mask, 1, random.Random(1000))
+    assert np.allclose(new_refs, g["new_refs"], rtol=0, atol=1e-6 * np.abs(g["new_refs"]).max())
+    assert np.allclose(info["filter"], g["filter"])
