@@ -169,6 +169,74 @@ int build_group_plan(CraCtx* c)
     c->plan.stride = (2 * cap + 3) & ~3;
     c->plan.nring = nring;
     c->plan.nphase = (int)phases.size();
+    // Item order of the real-FFT split (list Cg) and of the unit gather (list D): consecutive k of one ring sit at
+    // (k % NA) * (NB + 1) + k / NA in the padded ring buffer, whose shared-memory bank depends only on
+    // (k % NA + k / NA) mod 16 -- a half-warp of consecutive k replays 2.4x.  Nothing ties a lane to a particular k, so
+    // the items of a phase are regrouped greedily into runs of 16 whose float2 addresses fall into 16 different banks
+    // (for the unit gather: of every ring slot of the unit), a host-side permutation of the work lists only.
+    std::vector<int> cg_new, d_list;
+    {
+        auto geom = [&](int ring, int& NA, int& NB1, int& la) {
+            const int n = t.len[ring] >> 1, lg = ilog2_floor(n); NA = 1 << (lg / 2); NB1 = n / NA + 1; la = lg / 2; };
+        auto zpos = [&](int ring, int k) { int NA, NB1, la; geom(ring, NA, NB1, la); return ppoff[ring] + (k & (NA - 1)) * NB1 + (k >> la); };
+        // greedy grouping: keys[i] = bank sets an item occupies (one per constraint); a run takes items whose banks are free
+        auto regroup = [&](const std::vector<int>& items, const std::vector<std::vector<int>>& banks, std::vector<int>& out) {
+            const size_t n = items.size(), nc = n ? banks[0].size() : 0;
+            std::vector<char> used(n, 0);
+            size_t done = 0, first = 0;
+            while (done < n) {
+                std::vector<unsigned> busy(nc, 0u);
+                int taken = 0;
+                while (first < n && used[first]) ++first;
+                for (size_t i = first; i < n && taken < 16; ++i) {
+                    if (used[i]) continue;
+                    bool ok = true;
+                    for (size_t q = 0; q < nc && ok; ++q) if (banks[i][q] >= 0 && (busy[q] >> banks[i][q]) & 1u) ok = false;
+                    if (!ok) continue;
+                    for (size_t q = 0; q < nc; ++q) if (banks[i][q] >= 0) busy[q] |= 1u << banks[i][q];
+                    used[i] = 1; out.push_back(items[i]); ++taken; ++done;
+                }
+                // a run shorter than 16 is padded by what is left, conflicts accepted (the tail of a phase)
+                for (size_t i = first; i < n && taken < 16 && done < n; ++i)
+                    if (!used[i]) { used[i] = 1; out.push_back(items[i]); ++taken; ++done; }
+            }
+        };
+        for (auto& ph : phases) {
+            // Cg items of the phase: (ring, k), k = 1 .. n/2; banks of Z_k and of its partner Z_{n-k}
+            std::vector<int> items; std::vector<std::vector<int>> banks;
+            const int s0 = 4 * ph.u0, s1 = std::min(4 * ph.u1, nring);
+            for (int sl = s0; sl < s1; ++sl) {
+                const int ring = nring - 1 - sl, n = t.len[ring] >> 1;
+                for (int k = 1; k <= n / 2; ++k) {
+                    items.push_back((ring << 16) | k);
+                    const int bk = zpos(ring, k) & 15, bm = zpos(ring, n - k) & 15;
+                    banks.push_back({bk, (n - k == k) ? -1 : bm});
+                }
+            }
+            if ((int)items.size() != ph.c1 - ph.c0) { cra_set_error("grouped row kernel: item list mismatch"); return 1; }
+            ph.c0 = (int)cg_new.size();
+            regroup(items, banks, cg_new);
+            ph.c1 = (int)cg_new.size();
+            // D items: (unit, k), k < the unit's longest half length; banks of the complex value each ring slot reads
+            items.clear(); banks.clear();
+            for (int uu = ph.u0; uu < ph.u1; ++uu)
+                for (int k = 0; k < unk[uu]; ++k) {
+                    items.push_back((uu << 16) | k);
+                    std::vector<int> b(4, -1);
+                    for (int j = 0; j < 4; ++j) {
+                        const int ring = nring - 1 - (4 * uu + j);
+                        if (ring < 0) continue;
+                        const int n = t.len[ring] >> 1;
+                        if (k > n) continue;
+                        b[j] = ((k == 0 || k == n) ? ppoff[ring] : zpos(ring, k)) & 15;
+                    }
+                    banks.push_back(b);
+                }
+            ph.d0 = (int)d_list.size();
+            regroup(items, banks, d_list);
+            if ((int)d_list.size() - ph.d0 != ph.upr) { cra_set_error("grouped row kernel: unit list mismatch"); return 1; }
+        }
+    }
     // rows per CTA: as many as fit two CTAs per SM (fewer image reloads, shared index math), else one CTA
     int dev = 0; cudaGetDevice(&dev);
     int smem_sm = 0, smem_blk = 0;
@@ -184,16 +252,21 @@ int build_group_plan(CraCtx* c)
     for (int r = CRA_GRP_RMAX; r >= 1 && !rmax; --r) if (fits(r, 1)) rmax = r;
     c->plan.rmax = rmax;
     if (!rmax) return 0;
-    const size_t bytes = sizeof(CraPhase) * phases.size() + sizeof(int) * (nring + nunit);
+    const size_t bytes = sizeof(CraPhase) * phases.size() + sizeof(int) * (nring + nunit + cg_new.size() + d_list.size());
     std::vector<char> blob(bytes);
-    memcpy(blob.data(), phases.data(), sizeof(CraPhase) * phases.size());
-    memcpy(blob.data() + sizeof(CraPhase) * phases.size(), ppoff.data(), sizeof(int) * nring);
-    memcpy(blob.data() + sizeof(CraPhase) * phases.size() + sizeof(int) * nring, unk.data(), sizeof(int) * nunit);
+    char* w = blob.data();
+    memcpy(w, phases.data(), sizeof(CraPhase) * phases.size()); w += sizeof(CraPhase) * phases.size();
+    memcpy(w, ppoff.data(), sizeof(int) * nring); w += sizeof(int) * nring;
+    memcpy(w, unk.data(), sizeof(int) * nunit); w += sizeof(int) * nunit;
+    memcpy(w, cg_new.data(), sizeof(int) * cg_new.size()); w += sizeof(int) * cg_new.size();
+    memcpy(w, d_list.data(), sizeof(int) * d_list.size());
     CRA_CUDA(cudaMalloc(&c->d_plan, bytes));
     CRA_CUDA(cudaMemcpy(c->d_plan, blob.data(), bytes, cudaMemcpyHostToDevice));
     c->plan.phases = reinterpret_cast<const CraPhase*>(c->d_plan);
     c->plan.ppoff = reinterpret_cast<const int*>(reinterpret_cast<const char*>(c->d_plan) + sizeof(CraPhase) * phases.size());
     c->plan.unit_nk = c->plan.ppoff + nring;
+    c->items.Cg = c->plan.unit_nk + nunit; c->items.nCg = (int)cg_new.size();      // the regrouped lists replace build_tables' Cg
+    c->items.D = c->items.Cg + cg_new.size(); c->items.nD = (int)d_list.size();
     return 0;
 }
 

@@ -52,7 +52,9 @@ struct CraPolarItems {         // flat work lists of the ring FFT passes (device
     const int* A; int nA;      // (ring << 16 | column b)   pass A: NA-point DFTs
     const int* B; int nB;      // (ring << 16 | row ka)     pass B: NB-point DFTs
     const int* C; int nC;      // (ring << 16 | k)          pass C: split + store, k <= len/4
-    const int* Cg; int nCg;    // same without the k = 0 items (grouped row kernel)
+    const int* Cg; int nCg;    // same without the k = 0 items (grouped row kernel), per phase in an order whose
+                               // half-warps hit 16 distinct shared-memory banks (build_group_plan)
+    const int* D; int nD;      // (unit << 16 | k)          pass D of the grouped kernel: unit gather, same ordering rule
 };
 
 // ---- grouped row kernel (cra_polar_grp.cu) -----------------------------------------------------
@@ -62,6 +64,7 @@ struct CraPolarItems {         // flat work lists of the ring FFT passes (device
 struct CraPhase {              // one walk of the CTA over a set of consecutive 4-ring units
     int q0, q1;                // quarter-ring sample range in samp[]
     int a0, a1, b0, b1, c0, c1;// item ranges in CraPolarItems A / B / Cg
+    int d0;                    // first item of the phase in CraPolarItems D (upr items)
     int u0, u1;                // ring units [u0, u1): unit u = slots 4u..4u+3, slot s <-> ring nring-1-s
     int upr;                   // pass-D lanes per row = sum over the units of their longest half length
     int magicA, magicB, magicC, magicD;   // floor(2^24 / n) + 1 for n = items A, B, C, upr (fastdiv)

@@ -451,9 +451,8 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
             const int nset = __ldg(&plan.phases[ph].nsetD[nr]);
             const size_t rb = cra_frag_row_bytes(frag.nch);
             for (int x = tid; x < upr * nset; x += kThreads) {
-                const int set = fastdiv(x, P.magicD);
-                int k = x - set * upr, u = P.u0;
-                while (k >= s_unk[u]) { k -= s_unk[u]; ++u; }
+                const int set = fastdiv(x, P.magicD), ditem = __ldg(items.D + P.d0 + (x - set * upr));
+                const int k = ditem & 0xffff, u = ditem >> 16;
                 // value of slot j = (v.x * mx + v.y * my, v.y * mi) of z[idx]: complex (1,0,1), F_0 = .x of
                 // pos(0) (1,0,0), F_n = .y of pos(0) (0,1,0), ring too short or absent (0,0,0)
                 int idx[4]; float mx[4], my[4], mi[4];
