@@ -201,9 +201,10 @@ def run_reference(args, rank, world):
     images, _ = synth.make_particles(nsample, cfg["nx"], min(cfg["nviews"], 64), max_shift=int(cfg["xr"]), seed=2025)
     refs = synth.initial_references(images, cfg["R"], seed=99)
     run = oracle_runner(images, refs, cfg, nth)
-    probe = min(nsample, nth)
+    probe = min(nsample, 2 * nth)
+    run(min(nsample, nth))                          # thread start-up and first-touch costs stay out of the probe
     t_probe = run(probe)
-    n = int(max(probe, min(nsample, probe * 6.0 / max(t_probe, 1e-6))))
+    n = int(max(probe, min(nsample, probe * 5.0 / max(t_probe, 1e-6))))
     times = []
     for it in range(args.warmup + args.steps):
         dt = run(n)

@@ -145,7 +145,10 @@ __device__ __forceinline__ void repair_sample(int code, int r, const float4* __r
     atomicAdd(&s_fix[2 * r + 1], (v * v - old * old) * wn);
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+#ifndef CRA_GRP_MINB
+#define CRA_GRP_MINB 2              // resident CTAs per SM the register allocation aims for
+#endif
+__global__ void __launch_bounds__(kThreads, CRA_GRP_MINB)
 polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* __restrict__ tab,
                    const float4* __restrict__ samp, const float2* __restrict__ twid, CraPolarItems items,
                    CraGroupPlan plan, CraRowMap map, int normalize_ring, unsigned char* __restrict__ spec,
