@@ -454,21 +454,6 @@ __device__ void pair_freq_frag_d(const unsigned char* __restrict__ rowp, const u
     zq_r = A + B; zq_i = D - C; zt_r = A - B; zt_i = -C - D;
 }
 
-// value at lag m (0-based) of the straight (.x) and the mirrored (.y) correlation, from the pair's spectrum z
-// (per frequency: q_r, q_i, t_r, t_i) and the double twiddle table twd[j] = (cos, sin)(2 pi j / N)
-__device__ __forceinline__ double2 lag_value(const double4* __restrict__ z, const double2* __restrict__ twd, int N, int m)
-{
-    double aq = 0., at = 0.;
-    for (int k = 0; k <= N / 2; ++k) {
-        const double2 w = twd[(k * m) & (N - 1)];
-        const double4 v = z[k];
-        const double wgt = (k == 0 || k == N / 2) ? 1.0 : 2.0;
-        aq += wgt * (v.x * w.x - v.y * w.y);
-        at += wgt * (v.z * w.x - v.w * w.y);
-    }
-    return make_double2(aq / N, at / N);
-}
-
 // One warp per particle: the winner over (row, reference) in the reference's visit order from the candidates of
 // the CCF kernel, then BOTH correlation curves of that pair in double precision straight from the spectra -- the
 // arithmetic of EMAN2's Crosrng_ms (double accumulation, fftr_d): ">=" argmax over the lags (the last maximum
@@ -481,12 +466,12 @@ finalize_kernel(const float2* __restrict__ spec, const float2* __restrict__ refs
                 CraRowMap map, CraResult* __restrict__ out, CraFragTab frag, const double2* __restrict__ twd,
                 const float2* __restrict__ norm, const float* __restrict__ tref)
 {
-    extern __shared__ __align__(16) double4 s_zd[];           // per warp: N/2 + 1 frequencies
+    extern __shared__ __align__(16) double2 s_xd[];           // per warp: N points, W = q + i t, then the two curves
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int p = blockIdx.x * (blockDim.x >> 5) + wib;
     if (p >= map.np) return;
-    const int N = tab->maxrin;
-    double4* z = s_zd + (size_t)wib * (N / 2 + 1);
+    const int N = tab->maxrin, LN = 31 - __clz(N);
+    double2* x = s_xd + (size_t)wib * N;
     const int r0 = map.row_start[p], r1 = map.row_start[p + 1];
     const int ncand = (r1 - r0) * ntile_n;
     float bv = -INFINITY; int bc = -1, bcode = -1;
@@ -517,13 +502,32 @@ finalize_kernel(const float2* __restrict__ spec, const float2* __restrict__ refs
             pair_freq_frag_d(reinterpret_cast<const unsigned char*>(spec) + (size_t)row * rb,
                              reinterpret_cast<const unsigned char*>(refspec) + (size_t)iref * rb, frag, k, v.x, v.y, v.z, v.w);
         } else pair_freq_d(spec, row, refspec, iref, tab, k, v.x, v.y, v.z, v.w);
-        z[k] = v;
+        // Hermitian extension of W = Q + i T (q and t are real sequences), stored bit-reversed for the in-place FFT:
+        // W[k] = (Qr - Ti, Qi + Tr), W[N-k] = conj(Q) + i conj(T) = (Qr + Ti, Tr - Qi)
+        x[__brev((unsigned)k) >> (32 - LN)] = make_double2(v.x - v.w, v.y + v.z);
+        if (k != 0 && k != N / 2) x[__brev((unsigned)(N - k)) >> (32 - LN)] = make_double2(v.x + v.w, v.z - v.y);
     }
     __syncwarp();
-    // every lag of both curves; scan order j = 1..maxrin with ">=": the later lag wins a tie
+    // One complex inverse FFT of length N in double (radix 2, decimation in time, in place) gives both curves at
+    // every lag: x[m] = (q[m], t[m]) * N -- EMAN2's fftr_d works in double as well; this replaces the direct
+    // N x (N/2 + 1) sums (8.2 -> ~2 ms per 100k particles).
+    for (int s = 0; s < LN; ++s) {
+        const int half = 1 << s;
+        for (int j = lane; j < N / 2; j += 32) {
+            const int pos = j & (half - 1), i0 = ((j >> s) << (s + 1)) + pos, i1 = i0 + half;
+            const double2 w = twd[pos << (LN - 1 - s)];          // exp(+2 pi i pos / (2 half))
+            const double2 a = x[i0], b = x[i1];
+            const double2 bw = make_double2(b.x * w.x - b.y * w.y, b.x * w.y + b.y * w.x);
+            x[i0] = make_double2(a.x + bw.x, a.y + bw.y);
+            x[i1] = make_double2(a.x - bw.x, a.y - bw.y);
+        }
+        __syncwarp();
+    }
+    const double invN = 1.0 / (double)N;
+    // scan order j = 1..maxrin with ">=": the later lag wins a tie
     double bq = -INFINITY, bt = -INFINITY; int mq = -1, mt = -1;
     for (int m = lane; m < N; m += 32) {
-        const double2 v = lag_value(z, twd, N, m);
+        const double2 v = make_double2(x[m].x * invN, x[m].y * invN);
         if (v.x >= bq) { bq = v.x; mq = m; }
         if (v.y >= bt) { bt = v.y; mt = m; }
     }
@@ -538,8 +542,8 @@ finalize_kernel(const float2* __restrict__ spec, const float2* __restrict__ refs
     const int jtot = (mirror ? mt : mq) + 1;                    // 1-based lag of the maximum
     double t7 = 0.;
     if (lane < 7) {
-        const double2 v = lag_value(z, twd, N, (jtot - 1 + lane - 3 + N) & (N - 1));
-        t7 = mirror ? v.y : v.x;
+        const double2 v = x[(jtot - 1 + lane - 3 + N) & (N - 1)];
+        t7 = (mirror ? v.y : v.x) * invN;
     }
     double b[7];
 #pragma unroll
@@ -680,7 +684,7 @@ int cra_launch_finalize(const float* spec, const float* refspec, int R, const Cr
 {
     if (map.np <= 0) return 0;
     const int wpb = 4;
-    const size_t smem = (size_t)wpb * (htab.maxrin / 2 + 1) * sizeof(double4);
+    const size_t smem = (size_t)wpb * htab.maxrin * sizeof(double2);
     const float2* s2 = reinterpret_cast<const float2*>(spec); const float2* r2 = reinterpret_cast<const float2*>(refspec);
     if (smem > 48 * 1024 && cra_ensure_dyn_smem(fmt == CRA_FMT_FRAG ? reinterpret_cast<const void*>(&finalize_kernel<CRA_FMT_FRAG>)
                                                                      : reinterpret_cast<const void*>(&finalize_kernel<CRA_FMT_F32>), smem)) return 1;
