@@ -150,7 +150,8 @@ int build_group_plan(CraCtx* c)
         auto pick = [](int n, int nr, int setup, int per_row) {
             int best = 1; long bestc = 1L << 40;
             for (int sset = 1; sset <= nr; ++sset) {
-                const long cst = (long)((n * sset + 255) / 256) * (setup + (long)((nr + sset - 1) / sset) * per_row);
+                const int lanes = 256 / CRA_GRP_NH;              // threads of one group (cra_polar_grp.cu)
+                const long cst = (long)((n * sset + lanes - 1) / lanes) * (setup + (long)((nr + sset - 1) / sset) * per_row);
                 if (cst < bestc) { bestc = cst; best = sset; }
             }
             return (unsigned char)best;

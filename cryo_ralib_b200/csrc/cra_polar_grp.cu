@@ -33,6 +33,23 @@ using crafft::fft_reg;
 
 constexpr int kThreads = 256;
 constexpr int RMAX = CRA_GRP_RMAX;
+// The CTA works as NH independent thread groups: they share the image tile and the tables, each takes an equal share
+// of the block's rows through every phase and synchronises on its own named barrier.  Half as many warps wait for the
+// slowest one at each of the 42 barriers of a CTA, the groups drift apart so that one's interpolation (LSU) runs under
+// the other's FFT passes (FMA), and the per-row register arrays shrink from RMAX to RMAX / NH entries.
+constexpr int NH = CRA_GRP_NH;
+constexpr int GT = kThreads / NH;              // threads per group
+constexpr int HR = (RMAX + NH - 1) / NH;       // most rows per group
+static_assert(kThreads % (32 * NH) == 0 && NH >= 1 && NH <= 4, "groups are whole warps");
+__device__ __forceinline__ void group_sync(int g)
+{
+    if (NH == 1) { __syncthreads(); return; }
+    // immediate barrier numbers: a register operand makes ptxas reserve all 16 named barriers of the CTA
+    if (g == 0)      asm volatile("bar.sync 1, %0;" :: "n"(GT) : "memory");
+    else if (g == 1) asm volatile("bar.sync 2, %0;" :: "n"(GT) : "memory");
+    else if (g == 2) asm volatile("bar.sync 3, %0;" :: "n"(GT) : "memory");
+    else             asm volatile("bar.sync 4, %0;" :: "n"(GT) : "memory");
+}
 constexpr int kFragCap = 24;    // per warp and phase; beyond it the lane repairs its sample itself (exact either way)
 
 __device__ __forceinline__ float warp_sum(float v)
@@ -165,7 +182,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
     int4* s_ring = reinterpret_cast<int4*>(s_tw + maxrin);    // nring : phase-local float2 offset, log2 NB, len/4, wn
     int* s_koff = reinterpret_cast<int*>(s_ring + nring);     // maxrin/2 + 2 : first chunk of frequency k
     int* s_unk = s_koff + (maxrin / 2 + 2);                   // units : longest half length of unit u
-    __shared__ float s_red[kThreads / 32][2 * RMAX];
+    __shared__ float s_red[kThreads / 32][2 * HR];
     __shared__ int s_rowoff[RMAX];
     __shared__ int s_grow[RMAX];                               // row of the batch (spectrum / norm index) of block row r
     __shared__ unsigned s_samemask;                            // bit r: row r sits one pixel right of row r-1
@@ -235,10 +252,12 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
         s_ring[i] = make_int4(__ldg(plan.ppoff + i), lg - (lg >> 1), tab->len[i] >> 2, __float_as_int(tab->wn[i]));
     }
     __syncthreads();
-    const int nr = s_blk[2];
+    const int nr_all = s_blk[2];
+    const int grp = tid / GT, gt = tid - grp * GT;             // thread group and index inside it
+    const int rg0 = (grp * nr_all) / NH, nr = ((grp + 1) * nr_all) / NH - rg0;   // the group's rows [rg0, rg0 + nr)
     const bool contig = (s_blk[3] & 1) != 0;                   // block rows are consecutive rows of the batch
     if (tid < 32) {                                            // the block's rows, one lane each (published by the barrier below)
-        const int lo = s_blk[0], r = tid;
+        const int lo = s_blk[0], r = tid, nr = nr_all;
         const int cx = s_cls[0], cy = s_cls[1], ncx = s_cls[2], sub = s_cls[3];
         const int pxs = (sub > 1) ? 1 : (int)map.step;         // pixels between neighbouring rows of a class
         bool cont = false;
@@ -273,16 +292,24 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
     const float bx = s_base[0], by = s_base[1];
     // whole-pixel centres in every row of the block: the base centre is a whole number and the rows lie whole pixels apart
     const bool cint_x = bx == rintf(bx), cint_y = by == rintf(by);
-    float av[RMAX], sq[RMAX];
+    float av[HR], sq[HR];
 #pragma unroll
-    for (int r = 0; r < RMAX; ++r) { av[r] = 0.f; sq[r] = 0.f; }
+    for (int r = 0; r < HR; ++r) { av[r] = 0.f; sq[r] = 0.f; }
     __syncthreads();
-    const unsigned samemask = s_samemask;
+    const unsigned samemask = (s_samemask >> rg0) & ~1u;       // bit r: the group's row r continues row r - 1 (never its first)
+    // the group's view of the per-row tables and of the row buffers
+    const int* const g_rowoff = s_rowoff + rg0;
+    const int* const g_grow = s_grow + rg0;
+    const float2* const g_rowc = s_rowc + rg0;
+    float* const g_fix = s_fix + 2 * rg0;
+    float* const g_buf = s_buf + rg0 * stride;
+    int* const g_nfrag = s_nfrag + grp * (GT / 32);
+    int (*const g_frag)[kFragCap] = s_frag + grp * (GT / 32);
 
     for (int ph = 0; ph < plan.nphase; ++ph) {
         const CraPhase P = plan.phases[ph];
         // ---- interpolate the phase's rings for every row: weights once per sample ----------------
-        for (int q = P.q0 + tid; q < P.q1; q += kThreads) {
+        for (int q = P.q0 + gt; q < P.q1; q += GT) {
             const float4 e = __ldg(samp + q);                 // x, y, ring, jt (first quarter of the ring)
             const int4 rp = s_ring[__float_as_int(e.z)];
             const int jt = __float_as_int(e.w);
@@ -290,9 +317,9 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
             const float ox[4] = {e.x, e.y, -e.x, -e.y}, oy[4] = {e.y, -e.x, -e.y, e.x};
             int fragile = 0;       // samples so close to a pixel boundary that float rounding of the per-row
                                    // position (x = offset + centre, as Polar2Dm forms it) could pick another cell
-            int ro[RMAX];
+            int ro[HR];
 #pragma unroll
-            for (int r = 0; r < RMAX; ++r) ro[r] = (r < nr) ? s_rowoff[r] : 0;
+            for (int r = 0; r < HR; ++r) ro[r] = (r < nr) ? g_rowoff[r] : 0;
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
                 const int j = jt + m * rp.z, pj = j >> 1;
@@ -315,12 +342,12 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                 const float w5 = ab;                    // (i+1, j+1)
                 const float w0 = 1.0f - dx - dy - 2.0f * a2 - 2.0f * b2 + ab;
                 const float* p0 = s_img + (iy * pitch + ix) - (pitch + 1);     // 1-based cell (ix, iy)
-                float* dst = s_buf + slot;
+                float* dst = g_buf + slot;
                 // a row that continues the window line of the previous one (one pixel to the right) reuses
                 // three of its taps: (i-1,j) <- (i,j), (i,j) <- (i+1,j), (i,j+1) <- (i+1,j+1)
                 float fl = 0.f, fc = 0.f, fr = 0.f, uc = 0.f, ur = 0.f;
 #pragma unroll
-                for (int r = 0; r < RMAX; ++r) {
+                for (int r = 0; r < HR; ++r) {
                     if (r < nr) {
                         const float* p = p0 + ro[r];
                         const bool cont = (samemask >> r) & 1;
@@ -343,11 +370,11 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
 #pragma unroll
                 for (int m = 0; m < 4; ++m)
                     if (fragile & (1 << m)) {
-                        const int at = atomicAdd(&s_nfrag[tid >> 5], 1);
-                        if (at < kFragCap) s_frag[tid >> 5][at] = q * 4 + m;
+                        const int at = atomicAdd(&g_nfrag[gt >> 5], 1);
+                        if (at < kFragCap) g_frag[gt >> 5][at] = q * 4 + m;
                         else                // queue full (an integer or half-integer centre puts whole rings on cell
                             for (int r = 0; r < nr; ++r)    // boundaries): this lane repairs its own sample right away
-                                repair_sample(q * 4 + m, r, samp, s_ring, s_rowc, s_img, nx, s_buf, stride, s_fix);
+                                repair_sample(q * 4 + m, r, samp, s_ring, g_rowc, s_img, nx, g_buf, stride, g_fix);
                     }
             }
         }
@@ -355,23 +382,23 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
         // each warp repairs the samples it wrote itself, so no CTA barrier is needed in between ----
         __syncwarp();
         {
-            const int wid = tid >> 5;
-            const int nf = min(s_nfrag[wid], kFragCap);
-            for (int x = tid & 31; x < nf * nr; x += 32) {
+            const int wid = gt >> 5;
+            const int nf = min(g_nfrag[wid], kFragCap);
+            for (int x = gt & 31; x < nf * nr; x += 32) {
                 const int en = x / nr, r = x - en * nr;
-                repair_sample(s_frag[wid][en], r, samp, s_ring, s_rowc, s_img, nx, s_buf, stride, s_fix);
+                repair_sample(g_frag[wid][en], r, samp, s_ring, g_rowc, s_img, nx, g_buf, stride, g_fix);
             }
         }
-        __syncthreads();
+        group_sync(grp);
         // ---- ring FFTs, pass A: (row, ring, column b) flattened ---------------------------------
         {
             const int nA = P.a1 - P.a0;
-            for (int w = tid; w < nA * nr; w += kThreads) {
+            for (int w = gt; w < nA * nr; w += GT) {
                 const int r = fastdiv(w, P.magicA), item = __ldg(items.A + P.a0 + (w - r * nA));
                 const int ring = item >> 16, b = item & 0xffff;
                 const int4 rp = s_ring[ring];
                 const int half = rp.z * 2;                             // complex points of the ring
-                float2* z = reinterpret_cast<float2*>(s_buf + r * stride) + rp.x;
+                float2* z = reinterpret_cast<float2*>(g_buf + r * stride) + rp.x;
                 const int lg = 31 - __clz(half);
                 const float2 base = s_tw[b * (maxrin / half)];         // exp(-2 pi i b / n)
                 switch (lg) {
@@ -386,15 +413,15 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                 }
             }
         }
-        __syncthreads();
+        group_sync(grp);
         // ---- pass B ------------------------------------------------------------------------------
         {
             const int nB = P.b1 - P.b0;
-            for (int w = tid; w < nB * nr; w += kThreads) {
+            for (int w = gt; w < nB * nr; w += GT) {
                 const int r = fastdiv(w, P.magicB), item = __ldg(items.B + P.b0 + (w - r * nB));
                 const int ring = item >> 16, ka = item & 0xffff;
                 const int4 rp = s_ring[ring];
-                float2* z = reinterpret_cast<float2*>(s_buf + r * stride) + rp.x;
+                float2* z = reinterpret_cast<float2*>(g_buf + r * stride) + rp.x;
                 const int lg = 31 - __clz(rp.z * 2);
                 switch (lg) {
                     case 2: pass_b<2, 2>(z, ka); break;
@@ -408,7 +435,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                 }
             }
         }
-        __syncthreads();
+        group_sync(grp);
         // ---- pass C: real-FFT split in place; index math once per (ring, k), rows inside ---------
         // Z_k of the half-length complex FFT sits at z[(k % NA)*(NB+1) + k / NA];
         // F_k = E_k + w_k O_k, F_{n-k} = conj(E_k - w_k O_k), w_k = exp(-2 pi i k / len);
@@ -417,7 +444,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
         {
             const int nC = P.c1 - P.c0;
             const int nset = __ldg(&plan.phases[ph].nsetC[nr]);
-            for (int x = tid; x < nC * nset; x += kThreads) {
+            for (int x = gt; x < nC * nset; x += GT) {
                 const int set = fastdiv(x, P.magicC), item = __ldg(items.Cg + P.c0 + (x - set * nC));
                 const int ring = item >> 16, k = item & 0xffff;
                 const int4 rp = s_ring[ring];
@@ -426,7 +453,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                 const int m = n - k;
                 const int pk = rp.x + (k & (NA - 1)) * NB1 + (k >> la), pm = rp.x + (m & (NA - 1)) * NB1 + (m >> la);
                 const float2 wk = s_tw[k * (maxrin / len)];
-                float2* z = reinterpret_cast<float2*>(s_buf + set * stride);
+                float2* z = reinterpret_cast<float2*>(g_buf + set * stride);
                 for (int r = set; r < nr; r += nset) {
                     const float2 a = z[pk], b = z[pm];
                     const float2 E = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
@@ -438,14 +465,14 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                 }
             }
             const int s0 = 4 * P.u0, nsl = min(4 * P.u1, nring) - s0;          // ring slots of the phase
-            for (int x = tid; x < nsl * nr; x += kThreads) {
+            for (int x = gt; x < nsl * nr; x += GT) {
                 const int r = x / nsl, ring = nring - 1 - (s0 + (x - r * nsl));
-                float2* z = reinterpret_cast<float2*>(s_buf + r * stride) + s_ring[ring].x;
+                float2* z = reinterpret_cast<float2*>(g_buf + r * stride) + s_ring[ring].x;
                 const float2 a = z[0];
                 z[0] = make_float2(a.x + a.y, a.x - a.y);
             }
         }
-        __syncthreads();
+        group_sync(grp);
         // ---- pass D: one (k < longest half length, unit) per lane, rows inside: gather the 4 ring
         // slots, split to bf16 hi/lo, store the 32-byte unit.  The unit's top frequency (real, only
         // its longest rings reach it) is a short flat (unit, row) loop.
@@ -453,7 +480,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
             const int upr = P.upr;
             const int nset = __ldg(&plan.phases[ph].nsetD[nr]);
             const size_t rb = cra_frag_row_bytes(frag.nch);
-            for (int x = tid; x < upr * nset; x += kThreads) {
+            for (int x = gt; x < upr * nset; x += GT) {
                 const int set = fastdiv(x, P.magicD), ditem = __ldg(items.D + P.d0 + (x - set * upr));
                 const int k = ditem & 0xffff, u = ditem >> 16;
                 // value of slot j = (v.x * mx + v.y * my, v.y * mi) of z[idx]: complex (1,0,1), F_0 = .x of
@@ -476,8 +503,8 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                     }
                 }
                 unsigned char* const o0 = spec + (size_t)(s_koff[k] + (u >> 2)) * 128 + (u & 3) * 32;
-                unsigned char* o = o0 + (size_t)s_grow[set] * rb;
-                const float2* z = reinterpret_cast<const float2*>(s_buf + set * stride);
+                unsigned char* o = o0 + (size_t)g_grow[set] * rb;
+                const float2* z = reinterpret_cast<const float2*>(g_buf + set * stride);
                 for (int r = set; r < nr; r += nset) {
                     float re[4], im[4];
 #pragma unroll
@@ -488,15 +515,15 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                     }
                     store_row_quad(reinterpret_cast<uint4*>(o), re, im, frag.unit_rows);
                     if (contig) o += (size_t)nset * rb;
-                    else if (r + nset < nr) o = o0 + (size_t)s_grow[r + nset] * rb;
+                    else if (r + nset < nr) o = o0 + (size_t)g_grow[r + nset] * rb;
                     z += nset * (stride >> 1);
                 }
             }
             const int nu = P.u1 - P.u0;
-            for (int x = tid; x < nu * nr; x += kThreads) {
+            for (int x = gt; x < nu * nr; x += GT) {
                 const int r = x / nu, u = P.u0 + (x - r * nu);
                 const int k = s_unk[u];                                        // the unit's longest half length
-                const float2* z = reinterpret_cast<const float2*>(s_buf + r * stride);
+                const float2* z = reinterpret_cast<const float2*>(g_buf + r * stride);
                 float re[4], im[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -504,33 +531,33 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                     re[j] = 0.f; im[j] = 0.f;
                     if (ring >= 0) { const int4 rp = s_ring[ring]; if (rp.z * 2 == k) re[j] = z[rp.x].y; }
                 }
-                store_row_quad(reinterpret_cast<uint4*>(spec + (size_t)s_grow[r] * rb + (size_t)(s_koff[k] + (u >> 2)) * 128 + (u & 3) * 32),
+                store_row_quad(reinterpret_cast<uint4*>(spec + (size_t)g_grow[r] * rb + (size_t)(s_koff[k] + (u >> 2)) * 128 + (u & 3) * 32),
                                re, im, frag.unit_rows);
             }
         }
-        if (tid < kThreads / 32) s_nfrag[tid] = 0;             // read above before two barriers, next written after this phase's last one
-        __syncthreads();
+        if (gt < GT / 32) g_nfrag[gt] = 0;             // read above before two barriers, next written after this phase's last one
+        group_sync(grp);
     }
 
     // ---- Normalize_ring sums -> norm[row] = (avg, 1/sigma) ---------------------------------------
 #pragma unroll
-    for (int r = 0; r < RMAX; ++r) { av[r] = warp_sum(av[r]); sq[r] = warp_sum(sq[r]); }
+    for (int r = 0; r < HR; ++r) { av[r] = warp_sum(av[r]); sq[r] = warp_sum(sq[r]); }
     if ((tid & 31) == 0) {
 #pragma unroll
-        for (int r = 0; r < RMAX; ++r) { s_red[tid >> 5][2 * r] = av[r]; s_red[tid >> 5][2 * r + 1] = sq[r]; }
+        for (int r = 0; r < HR; ++r) { s_red[tid >> 5][2 * r] = av[r]; s_red[tid >> 5][2 * r + 1] = sq[r]; }
     }
     __syncthreads();
-    if (tid < nr) {
+    if (gt < nr) {                                             // one thread per row of its group
         float avg = 0.f, isg = 1.f;
         if (normalize_ring) {
-            float a = s_fix[2 * tid], s = s_fix[2 * tid + 1];
+            float a = g_fix[2 * gt], s = g_fix[2 * gt + 1];
 #pragma unroll
-            for (int w = 0; w < kThreads / 32; ++w) { a += s_red[w][2 * tid]; s += s_red[w][2 * tid + 1]; }
+            for (int w = 0; w < GT / 32; ++w) { a += s_red[grp * (GT / 32) + w][2 * gt]; s += s_red[grp * (GT / 32) + w][2 * gt + 1]; }
             const float nn = tab->nn;
             avg = a / nn;
             isg = 1.0f / sqrtf((s - a * a / nn) / nn);
         }
-        norm[s_grow[tid]] = make_float2(avg, isg);
+        norm[g_grow[gt]] = make_float2(avg, isg);
     }
 }
 
