@@ -35,9 +35,21 @@
 #include <stdio.h>
 #include <algorithm>
 
+#include <mutex>
+#include <set>
+
 namespace {
 
 constexpr int kMaxWarps = 16;
+#ifndef CRA_TM_CONST_TW
+#define CRA_TM_CONST_TW 1
+#endif
+
+// Pass-1 twiddles exp(+2 pi i n2 k1 / N) of every supported N (32 .. 1024), table of N at offset N - 32.  The index of a
+// load is uniform over the warp (n2 is the warp's residue, k1 a constant), so the constant cache serves it without an
+// LSU wavefront -- the shared-memory copy cost 15 broadcast wavefronts per 16-point transform on the pipe that the
+// operand loads of the co-resident CTA queue on.  Content depends on N only: written once per device.
+__constant__ float2 c_itw[2048];
 
 using crafft::fft_reg;
 
@@ -272,7 +284,7 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
 #pragma unroll
             for (int k1 = 0; k1 < N1; ++k1) {
                 if (k1 == 0) { w[0] = x[0]; continue; }
-                const float2 tw = s_tw[k1 * N2 + n2];
+                const float2 tw = CRA_TM_CONST_TW ? c_itw[(N - 32) + k1 * N2 + n2] : s_tw[k1 * N2 + n2];
                 w[k1 * (N2 + 1)] = crafft::cmul(x[k1], tw);
             }
         }
@@ -421,6 +433,28 @@ int build_schedule(const CraRingTab& h, const std::vector<int>& koff, int kw, cu
     return 0;
 }
 
+int ensure_const_twiddles(cudaStream_t st)
+{
+    static std::mutex mu;
+    static std::set<int> done;
+    static std::vector<float2> host;                 // stays alive: the copies below are asynchronous
+    int dev = 0;
+    CRA_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.count(dev)) return 0;
+    if (host.empty()) {
+        host.assign(2048, make_float2(0.f, 0.f));
+        for (int lg = 5; lg <= 10; ++lg) {
+            std::vector<float2> tw; cra_ccf_twiddles(lg, tw);
+            std::copy(tw.begin(), tw.end(), host.begin() + ((1 << lg) - 32));
+        }
+    }
+    CRA_CUDA(cudaMemcpyToSymbolAsync(c_itw, host.data(), host.size() * sizeof(float2), 0, cudaMemcpyHostToDevice, st));
+    CRA_CUDA(cudaStreamSynchronize(st));
+    done.insert(dev);
+    return 0;
+}
+
 template <int LOG2N>
 int launch_t(const unsigned char* spec, int nrows, const unsigned char* refspec, int R, size_t row_bytes,
              const float2* twid, CraCand* cand, int ntile_n, const float2* norm, const float* tref,
@@ -435,6 +469,7 @@ int launch_t(const unsigned char* spec, int nrows, const unsigned char* refspec,
     }
     const size_t smem = ((size_t)32 * S::PS + S::N) * sizeof(float2) + (size_t)S::KW * sc->istride * sizeof(int2);
     if (cra_ensure_dyn_smem(reinterpret_cast<const void*>(&ccf_tm_kernel<LOG2N>), smem)) return 1;
+    if (CRA_TM_CONST_TW && ensure_const_twiddles(st)) return 1;
     const int nquad = (R + 3) / 4;
     const long ncta_m = (nrows + 7) / 8;
     const long nblk = ncta_m * ntile_n;
