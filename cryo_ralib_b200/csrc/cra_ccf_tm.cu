@@ -204,15 +204,18 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
         const int nit = s_hdr.nit[warp];                        // a multiple of 4, >= 4
         const int4* it4 = reinterpret_cast<const int4*>(s_items + warp * istride);   // (off, flush) x 2 per int4
 
+        // a tile whose second reference quad is empty (the last tile of R = 50, every tile of R <= 4: reference-free
+        // and class-bound alignment) neither loads nor multiplies it
+        const bool two = nj > 1;
 #define CRA_LOAD_OPS(O, off)                                                             \
-        { O.a = ldg256(pa + (unsigned)(off)); O.b0 = ldg128(pb0 + (unsigned)(off)); O.b1 = ldg128(pb1 + (unsigned)(off)); }
+        { O.a = ldg256(pa + (unsigned)(off)); O.b0 = ldg128(pb0 + (unsigned)(off)); if (two) O.b1 = ldg128(pb1 + (unsigned)(off)); }
 #define CRA_COMPUTE(O, fl)                                                               \
         { mma_bf16(acc0, O.a.w[0], O.a.w[1], O.a.w[2], O.a.w[3], O.b0.z, O.b0.w);   /* a_hi b_lo */ \
-          mma_bf16(acc1, O.a.w[0], O.a.w[1], O.a.w[2], O.a.w[3], O.b1.z, O.b1.w);       \
+          if (two) mma_bf16(acc1, O.a.w[0], O.a.w[1], O.a.w[2], O.a.w[3], O.b1.z, O.b1.w);       \
           mma_bf16(acc0, O.a.w[4], O.a.w[5], O.a.w[6], O.a.w[7], O.b0.x, O.b0.y);   /* a_lo b_hi */ \
-          mma_bf16(acc1, O.a.w[4], O.a.w[5], O.a.w[6], O.a.w[7], O.b1.x, O.b1.y);       \
+          if (two) mma_bf16(acc1, O.a.w[4], O.a.w[5], O.a.w[6], O.a.w[7], O.b1.x, O.b1.y);       \
           mma_bf16(acc0, O.a.w[0], O.a.w[1], O.a.w[2], O.a.w[3], O.b0.x, O.b0.y);   /* a_hi b_hi */ \
-          mma_bf16(acc1, O.a.w[0], O.a.w[1], O.a.w[2], O.a.w[3], O.b1.x, O.b1.y);       \
+          if (two) mma_bf16(acc1, O.a.w[0], O.a.w[1], O.a.w[2], O.a.w[3], O.b1.x, O.b1.y);       \
           if (fl) flush_freq(fl); }
 
         // a finished frequency: W[k] and its Hermitian partner W[N-k] to this lane's TMEM columns.  For k = 0 and
@@ -227,7 +230,7 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
                 tmem_st2(tbase + c1, sx - tx, sy - ty);
                 acc0[0] = acc0[1] = acc0[2] = acc0[3] = 0.f;
             }
-            {
+            if (two) {
                 const float A = acc1[0], D = acc1[1], C = acc1[2], B = acc1[3];
                 const float sx = A + B, sy = A - B, tx = C + D, ty = D - C;
                 tmem_st2(tbase + JCOLS + c0, sx + tx, sy + ty);
