@@ -133,6 +133,29 @@ int build_group_plan(CraCtx* c)
         aoff[s + 1] = aoff[s] + NB; boff[s + 1] = boff[s] + NA; coff[s + 1] = coff[s] + n / 2;
     }
     for (int i = 0; i < nring; ++i) qoff[i + 1] = qoff[i] + t.len[i] / 4;
+    // rows per CTA: as many as fit two CTAs per SM (fewer image reloads, shared index math), else one CTA
+    c->plan.stride = (2 * cap + 3) & ~3;
+    c->plan.nring = nring;
+    int dev = 0; cudaGetDevice(&dev);
+    int smem_sm = 0, smem_blk = 0;
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    auto fits = [&](int rmax, int ncta) {
+        CraGroupPlan q = c->plan; q.rmax = rmax;
+        const size_t need = cra_polar_group_smem(c->nx, t.maxrin, q) + 3700;   // + static shared + 1 KB reserved per CTA
+        return need <= (size_t)smem_blk && need * ncta <= (size_t)smem_sm;
+    };
+    int rmax = 0;
+    for (int r = CRA_GRP_RMAX; r >= 7 && !rmax; --r) if (fits(r, 2)) rmax = r;
+    // Two independent thread groups per CTA (cra_polar_grp.cu) where two CTAs are resident and a group keeps >= 6 rows:
+    // measured 135.9 -> 125.7 ms per step at nx = 90 / ou = 36, but +11 % at nx = 128 / ou = 60, where one CTA of 17 rows
+    // fills the SM and its phases hold 2 x the samples per thread.
+    c->plan.nh = (rmax >= 12) ? 2 : 1;
+    if (const char* e = getenv("CRA_GRP_NH")) c->plan.nh = (atoi(e) == 2) ? 2 : 1;
+    for (int r = CRA_GRP_RMAX; r >= 1 && !rmax; --r) if (fits(r, 1)) rmax = r;
+    c->plan.rmax = rmax;
+    if (!rmax) return 0;
+    const int lanes = 256 / c->plan.nh;                    // threads of one group
     std::vector<CraPhase> phases;
     std::vector<int> ppoff(nring, 0);
     auto magic = [](int n) { return n > 0 ? (1 << 24) / n + 1 : 1; };
@@ -147,10 +170,9 @@ int build_group_plan(CraCtx* c)
         p.a0 = aoff[s0]; p.a1 = aoff[s1]; p.b0 = boff[s0]; p.b1 = boff[s1]; p.c0 = coff[s0]; p.c1 = coff[s1];
         p.q0 = qoff[nring - s1]; p.q1 = qoff[nring - s0];                   // rings nring-s1 .. nring-1-s0
         for (int uu = u; uu < u1; ++uu) p.upr += unk[uu];
-        auto pick = [](int n, int nr, int setup, int per_row) {
+        auto pick = [lanes](int n, int nr, int setup, int per_row) {
             int best = 1; long bestc = 1L << 40;
             for (int sset = 1; sset <= nr; ++sset) {
-                const int lanes = 256 / CRA_GRP_NH;              // threads of one group (cra_polar_grp.cu)
                 const long cst = (long)((n * sset + lanes - 1) / lanes) * (setup + (long)((nr + sset - 1) / sset) * per_row);
                 if (cst < bestc) { bestc = cst; best = sset; }
             }
@@ -167,8 +189,6 @@ int build_group_plan(CraCtx* c)
         phases.push_back(p);
         u = u1;
     }
-    c->plan.stride = (2 * cap + 3) & ~3;
-    c->plan.nring = nring;
     c->plan.nphase = (int)phases.size();
     // Item order of the real-FFT split (list Cg) and of the unit gather (list D): consecutive k of one ring sit at
     // (k % NA) * (NB + 1) + k / NA in the padded ring buffer, whose shared-memory bank depends only on
@@ -238,21 +258,6 @@ int build_group_plan(CraCtx* c)
             if ((int)d_list.size() - ph.d0 != ph.upr) { cra_set_error("grouped row kernel: unit list mismatch"); return 1; }
         }
     }
-    // rows per CTA: as many as fit two CTAs per SM (fewer image reloads, shared index math), else one CTA
-    int dev = 0; cudaGetDevice(&dev);
-    int smem_sm = 0, smem_blk = 0;
-    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-    cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    auto fits = [&](int rmax, int ncta) {
-        CraGroupPlan q = c->plan; q.rmax = rmax;
-        const size_t need = cra_polar_group_smem(c->nx, t.maxrin, q) + 3700;   // + static shared + 1 KB reserved per CTA
-        return need <= (size_t)smem_blk && need * ncta <= (size_t)smem_sm;
-    };
-    int rmax = 0;
-    for (int r = CRA_GRP_RMAX; r >= 7 && !rmax; --r) if (fits(r, 2)) rmax = r;
-    for (int r = CRA_GRP_RMAX; r >= 1 && !rmax; --r) if (fits(r, 1)) rmax = r;
-    c->plan.rmax = rmax;
-    if (!rmax) return 0;
     const size_t bytes = sizeof(CraPhase) * phases.size() + sizeof(int) * (nring + nunit + cg_new.size() + d_list.size());
     std::vector<char> blob(bytes);
     char* w = blob.data();

@@ -287,7 +287,7 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
 #pragma unroll
             for (int k1 = 0; k1 < N1; ++k1) {
                 if (k1 == 0) { w[0] = x[0]; continue; }
-                const float2 tw = CRA_TM_CONST_TW ? c_itw[(N - 32) + k1 * N2 + n2] : s_tw[k1 * N2 + n2];
+                const float2 tw = (CRA_TM_CONST_TW && LOG2N <= 8) ? c_itw[(N - 32) + k1 * N2 + n2] : s_tw[k1 * N2 + n2];   // 4 KB at N = 512 overflow the constant cache: +4 % there
                 w[k1 * (N2 + 1)] = crafft::cmul(x[k1], tw);
             }
         }

@@ -61,9 +61,6 @@ struct CraPolarItems {         // flat work lists of the ring FFT passes (device
 #ifndef CRA_GRP_RMAX
 #define CRA_GRP_RMAX 17        // most shift rows one CTA of the grouped row kernel resamples together
 #endif
-#ifndef CRA_GRP_NH
-#define CRA_GRP_NH 2           // independent thread groups of a CTA of the grouped row kernel (1, 2 or 4)
-#endif
 struct CraPhase {              // one walk of the CTA over a set of consecutive 4-ring units
     int q0, q1;                // quarter-ring sample range in samp[]
     int a0, a1, b0, b1, c0, c1;// item ranges in CraPolarItems A / B / Cg
@@ -82,6 +79,7 @@ struct CraGroupPlan {
     const int* unit_nk;        // [units] longest half length (len/2 of its first slot) of unit u (device)
     int stride;                // floats per row of the phase buffer
     int rmax;                  // rows per CTA (<= CRA_GRP_RMAX), chosen for shared-memory fit
+    int nh;                    // independent thread groups of a CTA: 2 when a group still has >= 6 rows, else 1
     int nring;
 };
 

@@ -33,16 +33,18 @@ using crafft::fft_reg;
 
 constexpr int kThreads = 256;
 constexpr int RMAX = CRA_GRP_RMAX;
-// The CTA works as NH independent thread groups: they share the image tile and the tables, each takes an equal share
+// The CTA works as NH (1 or 2) independent thread groups: they share the image tile and the tables, each takes an equal share
 // of the block's rows through every phase and synchronises on its own named barrier.  Half as many warps wait for the
 // slowest one at each of the 42 barriers of a CTA, the groups drift apart so that one's interpolation (LSU) runs under
 // the other's FFT passes (FMA), and the per-row register arrays shrink from RMAX to RMAX / NH entries.
-constexpr int NH = CRA_GRP_NH;
-constexpr int GT = kThreads / NH;              // threads per group
-constexpr int HR = (RMAX + NH - 1) / NH;       // most rows per group
-static_assert(kThreads % (32 * NH) == 0 && NH >= 1 && NH <= 4, "groups are whole warps");
+constexpr int kFragCap = 24;    // per warp and phase; beyond it the lane repairs its sample itself (exact either way)
+// NH is a template parameter of the kernel: two groups pay off when a group still has many rows to share a sample's
+// tap weights (rmax = 17 at nx = 90: 135.9 -> 125.7 ms per step); at nx = 128 / ou = 60 a CTA holds 5 rows and two groups
+// of 3 + 2 rows compute every weight twice for nothing (+11 %), so the launcher picks one group there.
+template <int NH>
 __device__ __forceinline__ void group_sync(int g)
 {
+    constexpr int GT = kThreads / NH;
     if (NH == 1) { __syncthreads(); return; }
     // immediate barrier numbers: a register operand makes ptxas reserve all 16 named barriers of the CTA
     if (g == 0)      asm volatile("bar.sync 1, %0;" :: "n"(GT) : "memory");
@@ -50,7 +52,6 @@ __device__ __forceinline__ void group_sync(int g)
     else if (g == 2) asm volatile("bar.sync 3, %0;" :: "n"(GT) : "memory");
     else             asm volatile("bar.sync 4, %0;" :: "n"(GT) : "memory");
 }
-constexpr int kFragCap = 24;    // per warp and phase; beyond it the lane repairs its sample itself (exact either way)
 
 __device__ __forceinline__ float warp_sum(float v)
 {
@@ -165,12 +166,16 @@ __device__ __forceinline__ void repair_sample(int code, int r, const float4* __r
 #ifndef CRA_GRP_MINB
 #define CRA_GRP_MINB 2              // resident CTAs per SM the register allocation aims for
 #endif
+template <int NH>
 __global__ void __launch_bounds__(kThreads, CRA_GRP_MINB)
 polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* __restrict__ tab,
                    const float4* __restrict__ samp, const float2* __restrict__ twid, CraPolarItems items,
                    CraGroupPlan plan, CraRowMap map, int normalize_ring, unsigned char* __restrict__ spec,
                    CraFragTab frag, float2* __restrict__ norm)
 {
+    static_assert(kThreads % (32 * NH) == 0 && NH >= 1 && NH <= 4, "groups are whole warps");
+    constexpr int GT = kThreads / NH;              // threads per group
+    constexpr int HR = (RMAX + NH - 1) / NH;       // most rows per group
     extern __shared__ __align__(16) float smem[];
     const int npix = nx * nx;
     const int maxrin = tab->maxrin, nring = tab->nring;
@@ -389,7 +394,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                 repair_sample(g_frag[wid][en], r, samp, s_ring, g_rowc, s_img, nx, g_buf, stride, g_fix);
             }
         }
-        group_sync(grp);
+        group_sync<NH>(grp);
         // ---- ring FFTs, pass A: (row, ring, column b) flattened ---------------------------------
         {
             const int nA = P.a1 - P.a0;
@@ -413,7 +418,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                 }
             }
         }
-        group_sync(grp);
+        group_sync<NH>(grp);
         // ---- pass B ------------------------------------------------------------------------------
         {
             const int nB = P.b1 - P.b0;
@@ -435,7 +440,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                 }
             }
         }
-        group_sync(grp);
+        group_sync<NH>(grp);
         // ---- pass C: real-FFT split in place; index math once per (ring, k), rows inside ---------
         // Z_k of the half-length complex FFT sits at z[(k % NA)*(NB+1) + k / NA];
         // F_k = E_k + w_k O_k, F_{n-k} = conj(E_k - w_k O_k), w_k = exp(-2 pi i k / len);
@@ -472,7 +477,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                 z[0] = make_float2(a.x + a.y, a.x - a.y);
             }
         }
-        group_sync(grp);
+        group_sync<NH>(grp);
         // ---- pass D: one (k < longest half length, unit) per lane, rows inside: gather the 4 ring
         // slots, split to bf16 hi/lo, store the 32-byte unit.  The unit's top frequency (real, only
         // its longest rings reach it) is a short flat (unit, row) loop.
@@ -536,7 +541,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
             }
         }
         if (gt < GT / 32) g_nfrag[gt] = 0;             // read above before two barriers, next written after this phase's last one
-        group_sync(grp);
+        group_sync<NH>(grp);
     }
 
     // ---- Normalize_ring sums -> norm[row] = (avg, 1/sigma) ---------------------------------------
@@ -577,9 +582,15 @@ int cra_launch_polar_group(const float* images, int nx, const CraRingTab* tab, c
 {
     if (map.nchunks <= 0) return 0;
     const size_t smem = cra_polar_group_smem(nx, htab.maxrin, plan);
-    if (cra_ensure_dyn_smem(reinterpret_cast<const void*>(&polar_group_kernel), smem)) return 1;
-    polar_group_kernel<<<map.nchunks, kThreads, smem, st>>>(images, nx, tab, samp, twid, items, plan, map, normalize_ring,
-                                                           reinterpret_cast<unsigned char*>(spec), frag, norm);
+    if (plan.nh == 2) {
+        if (cra_ensure_dyn_smem(reinterpret_cast<const void*>(&polar_group_kernel<2>), smem)) return 1;
+        polar_group_kernel<2><<<map.nchunks, kThreads, smem, st>>>(images, nx, tab, samp, twid, items, plan, map, normalize_ring,
+                                                                  reinterpret_cast<unsigned char*>(spec), frag, norm);
+    } else {
+        if (cra_ensure_dyn_smem(reinterpret_cast<const void*>(&polar_group_kernel<1>), smem)) return 1;
+        polar_group_kernel<1><<<map.nchunks, kThreads, smem, st>>>(images, nx, tab, samp, twid, items, plan, map, normalize_ring,
+                                                                  reinterpret_cast<unsigned char*>(spec), frag, norm);
+    }
     CRA_CUDA(cudaGetLastError());
     return 0;
 }
