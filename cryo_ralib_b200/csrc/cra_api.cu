@@ -146,7 +146,8 @@ int build_group_plan(CraCtx* c)
         return need <= (size_t)smem_blk && need * ncta <= (size_t)smem_sm;
     };
     int rmax = 0;
-    for (int r = CRA_GRP_RMAX; r >= 7 && !rmax; --r) if (fits(r, 2)) rmax = r;
+    const int min2 = getenv("CRA_GRP_MIN2") ? atoi(getenv("CRA_GRP_MIN2")) : 7;      // fewest rows worth a second resident CTA
+    for (int r = CRA_GRP_RMAX; r >= min2 && !rmax; --r) if (fits(r, 2)) rmax = r;
     // Two independent thread groups per CTA (cra_polar_grp.cu) where two CTAs are resident and a group keeps >= 6 rows:
     // measured 135.9 -> 125.7 ms per step at nx = 90 / ou = 36, but +11 % at nx = 128 / ou = 60, where one CTA of 17 rows
     // fills the SM and its phases hold 2 x the samples per thread.
