@@ -33,14 +33,14 @@ using crafft::fft_reg;
 
 constexpr int kThreads = 256;
 constexpr int RMAX = CRA_GRP_RMAX;
-// The CTA works as NH (1 or 2) independent thread groups: they share the image tile and the tables, each takes an equal share
-// of the block's rows through every phase and synchronises on its own named barrier.  Half as many warps wait for the
-// slowest one at each of the 42 barriers of a CTA, the groups drift apart so that one's interpolation (LSU) runs under
-// the other's FFT passes (FMA), and the per-row register arrays shrink from RMAX to RMAX / NH entries.
 constexpr int kFragCap = 24;    // per warp and phase; beyond it the lane repairs its sample itself (exact either way)
-// NH is a template parameter of the kernel: two groups pay off when a group still has many rows to share a sample's
-// tap weights (rmax = 17 at nx = 90: 135.9 -> 125.7 ms per step); at nx = 128 / ou = 60 a CTA holds 5 rows and two groups
-// of 3 + 2 rows compute every weight twice for nothing (+11 %), so the launcher picks one group there.
+// The CTA works as NH (1 or 2) independent thread groups: they share the image tile and the tables, each takes an equal
+// share of the block's rows through every phase and synchronises on its own named barrier.  Half as many warps wait
+// for the slowest one at each of the 42 barriers of a CTA, the groups drift apart so that one's interpolation (LSU)
+// runs under the other's FFT passes (FMA), and the per-row register arrays shrink from RMAX to RMAX / NH entries.
+// NH is a template parameter chosen by the host (cra_api.cu: build_group_plan): two groups where two CTAs of >= 12 rows
+// are resident (rmax = 17 at nx = 90: 135.9 -> 125.7 ms per step); at nx = 128 / ou = 60, where one CTA of 17 rows fills the
+// SM and every phase holds twice the samples per thread, two groups measured +12 % and the launcher takes one.
 template <int NH>
 __device__ __forceinline__ void group_sync(int g)
 {
