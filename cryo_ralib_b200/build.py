@@ -25,15 +25,24 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
+def build(force=False, verbose=False, variant=None, defines=()):
+    """variant: build a second copy of the library with extra -D flags into experiments/bin/libcryo_ralib_<variant>.so
+    (A/B measurements: CRA_LIBRARY=<that path> selects it, lib.py); the product library is not touched."""
+    so, objdir, flags = SO, os.path.join(HERE, "build"), FLAGS
+    if variant:
+        out = os.path.join(HERE, "..", "experiments", "bin")
+        os.makedirs(out, exist_ok=True)
+        so = os.path.abspath(os.path.join(out, "libcryo_ralib_%s.so" % variant))
+        objdir = os.path.join(HERE, "build", "variant_" + variant)
+        flags = list(defines) + FLAGS
+    elif not force and not _stale():
         return SO
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    os.makedirs(objdir, exist_ok=True)
     for s in SOURCES:
-        o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
+        o = os.path.join(objdir, s.replace(".cu", ".o"))
+        cmd = [NVCC] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)
     for s, p in procs:
@@ -42,10 +51,14 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed on %s" % s)
-    cmd = [NVCC, "-shared", "-o", SO] + objs + ["-ccbin", "/usr/bin/g++", "-lcudart", "-lgomp"]
+    cmd = [NVCC, "-shared", "-o", so] + objs + ["-ccbin", "/usr/bin/g++", "-lcudart", "-lgomp"]
     subprocess.check_call(cmd)
-    return SO
+    return so
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:          # python -m cryo_ralib_b200.build --variant NAME -DFLAG ...
+        i = sys.argv.index("--variant")
+        print(build(variant=sys.argv[i + 1], defines=[a for a in sys.argv[i + 2:] if a.startswith("-D")]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

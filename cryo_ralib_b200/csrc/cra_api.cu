@@ -82,6 +82,8 @@ struct CraCtx {
     CraGroupPlan plan{};         // grouped row kernel (cra_polar_grp.cu); plan.rmax == 0: unavailable
     void* d_plan = nullptr;
     bool use_group = true;       // CRA_POLAR=general forces the general kernel
+    float2* d_dft = nullptr; size_t dft_elems = 0;             // reference-update scratch (large boxes only)
+    int rpb = 2, gimg_rows = 0, gimg_one = 0;   // general row kernel: rows per CTA; image taps from global memory (large boxes)
     int last_rows = 0, last_group = 0;   // rows / kernel of the last batch (cra_batch_row_spectrum)
     float2* d_norm = nullptr;    // [row_batch] deferred Normalize_ring (avg, 1/sigma), cra_common.cuh
     float* d_tref = nullptr;     // [max_refs]  sum_rings len * weighted reference DC
@@ -499,13 +501,15 @@ extern "C" int cra_create(const CraConfig* cfg, int device, CraCtx** out)
         else if (pk && strcmp(pk, "group") != 0 && pk[0]) { cra_set_error("CRA_POLAR must be 'group' or 'general'"); cra_destroy(c); return 1; }
     }
     if (build_tables(c)) { cra_destroy(c); return 1; }
-    {   // the references (and sub-pixel steps) go through the general row kernel: image + one whole polar row in shared memory
+    {   // the references (and steps / centres the grouped kernel does not cover) go through the general row kernel:
+        // whole polar rows in shared memory, and the image beside them when it fits (boxes up to ~170 pixels)
         int smem_blk = 0;
         cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-        const size_t need = cra_polar_general_smem(c->nx, c->htab) + 4096;
-        if (need > (size_t)smem_blk) {
-            cra_set_error("box too large for this build: image + one polar row need " + std::to_string(need / 1024) +
-                          " KB of shared memory (limit " + std::to_string(smem_blk / 1024) + " KB); reduce nx or ou");
+        int one = 1;
+        if (cra_polar_general_layout(c->nx, c->htab, (size_t)smem_blk, cra_polar_default_rpb(), &c->rpb, &c->gimg_rows) ||
+            cra_polar_general_layout(c->nx, c->htab, (size_t)smem_blk, 1, &one, &c->gimg_one)) {
+            cra_set_error("ou too large for this build: one polar row (" + std::to_string((size_t)c->htab.lcpad * 4 / 1024) +
+                          " KB) does not fit into shared memory (limit " + std::to_string(smem_blk / 1024) + " KB); reduce ou");
             cra_destroy(c); return 1;
         }
     }
@@ -568,7 +572,7 @@ extern "C" int cra_destroy(CraCtx* c)
     cudaFree(c->d_mask); cudaFree(c->d_dc); cudaFree(c->d_images); cudaFree(c->d_refs); cudaFree(c->d_refspec);
     cudaFree(c->d_spec); cudaFree(c->d_cand); cudaFree(c->d_sums); cudaFree(c->d_meta); cudaFree(c->d_res);
     cudaFree(c->d_par); cudaFree(c->d_iref); cudaFree(c->d_tmpimg); cudaFree(c->d_curves);
-    cudaFree(c->d_shell); cudaFree(c->d_fsc); cudaFree(c->d_cs);
+    cudaFree(c->d_shell); cudaFree(c->d_fsc); cudaFree(c->d_cs); cudaFree(c->d_dft);
     if (c->h_meta) cudaFreeHost(c->h_meta);
     if (c->h_res) cudaFreeHost(c->h_res);
     if (c->h_par) cudaFreeHost(c->h_par);
@@ -638,12 +642,26 @@ extern "C" int cra_upload_particles_dev(CraCtx* c, const float* d, int first, in
 { return upload_particles(c, d, first, n, sub, cudaMemcpyDeviceToDevice); }
 
 // d_refs[0..R) -> (normalize.mask no_sigma=1) -> Polar2Dm + Frngs + Applyws -> refspec, tref
+// global scratch of the reference-update transforms, only for boxes whose spectra exceed shared memory
+static int ensure_dft_scratch(CraCtx* c, int n, int nsh, int nspec)
+{
+    const size_t per = cra_dft_scratch_elems(c->nx, nsh, nspec);
+    if (!per) return 0;
+    const size_t need = per * (size_t)n;
+    if (need <= c->dft_elems) return 0;
+    CRA_CUDA(cudaStreamSynchronize(c->st));
+    cudaFree(c->d_dft); c->d_dft = nullptr; c->dft_elems = 0;
+    if (cudaMalloc(&c->d_dft, need * sizeof(float2)) != cudaSuccess) { cra_set_error("device allocation failed: reference-update scratch"); return 1; }
+    c->dft_elems = need;
+    return 0;
+}
+
 static int prepare_refs(CraCtx* c, int R, int normalize_mask)
 {
     CraNvtx range("cra_prepare_refs");
     if (normalize_mask && cra_launch_mask_normalize(c->d_refs, R, c->nx, c->d_mask, 1, nullptr, c->st)) return 1;
     if (cra_launch_polar_refs(c->d_refs, R, c->nx, c->d_tab, c->htab, c->d_samp, c->d_twf, c->items, c->d_refspec,
-                              c->fmt, c->frag, c->d_tref, c->st)) return 1;
+                              c->fmt, c->frag, c->d_tref, c->gimg_one, c->st)) return 1;
     if (c->use_um && cra_ccf_um_pack_refs(reinterpret_cast<const unsigned char*>(c->d_refspec), R, c->frag, c->d_refimg, c->st)) return 1;
     CRA_CUDA(cudaStreamSynchronize(c->st));
     c->R = R;
@@ -671,7 +689,8 @@ extern "C" int cra_filter_refs(CraCtx* c, float cutoff, float falloff, int norma
 {
     Bind b(c); if (b.ok()) return 1;
     if (c->R < 1) { cra_set_error("cra_set_refs has not been called"); return 1; }
-    if (cra_launch_tanl_filter(c->d_refs, c->R, c->nx, cutoff, falloff, c->st)) return 1;
+    if (ensure_dft_scratch(c, c->R, 0, 2)) return 1;
+    if (cra_launch_tanl_filter(c->d_refs, c->R, c->nx, cutoff, falloff, c->d_dft, c->st)) return 1;
     return prepare_refs(c, c->R, normalize_mask);
 }
 
@@ -725,8 +744,9 @@ extern "C" int cra_class_fsc(CraCtx* c, int masked, int min_members, int write_a
     if (nshell) *nshell = nsh;
     if (!fsc_out) return 0;                                    // size query
     const float* counts = c->d_sums + (size_t)c->cfg.max_refs * 2 * c->npix;
+    if (ensure_dft_scratch(c, R, nsh, 3)) return 1;
     if (cra_launch_class_fsc(c->d_sums, counts, c->d_refs, c->d_shell, c->d_mask, R, c->nx, nsh, masked, min_members,
-                             write_avg, avg_div, c->d_fsc, c->st)) return 1;
+                             write_avg, avg_div, c->d_fsc, c->d_dft, c->st)) return 1;
     std::vector<double> h((size_t)R * 3 * nsh);
     std::vector<float> hc(R);
     CRA_CUDA(cudaMemcpyAsync(h.data(), c->d_fsc, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->st));
@@ -765,7 +785,8 @@ extern "C" int cra_filter_center_refs(CraCtx* c, float cutoff, float falloff, in
     if (c->R < 1) { cra_set_error("cra_set_refs has not been called"); return 1; }
     if (mode < 0 || mode > 2) { cra_set_error("cra_filter_center_refs: mode must be 0 (filter), 1 (phase centre) or 2 (given shift)"); return 1; }
     if (ensure_fsc_tables(c)) return 1;
-    if (cra_launch_filter_center(c->d_refs, c->R, c->nx, cutoff, falloff, mode, sx, sy, c->d_cs, c->st)) return 1;
+    if (ensure_dft_scratch(c, c->R, 0, 2)) return 1;
+    if (cra_launch_filter_center(c->d_refs, c->R, c->nx, cutoff, falloff, mode, sx, sy, c->d_cs, c->d_dft, c->st)) return 1;
     if (normalize_mask && cra_launch_mask_normalize(c->d_refs, c->R, c->nx, c->d_mask, 1, nullptr, c->st)) return 1;
     if (cs_out) CRA_CUDA(cudaMemcpyAsync(cs_out, c->d_cs, (size_t)c->R * 2 * sizeof(float), cudaMemcpyDeviceToHost, c->st));
     CRA_CUDA(cudaStreamSynchronize(c->st));
@@ -823,7 +844,7 @@ static int align_impl(CraCtx* c, int start, int stop, const CraSearch* search, c
     CraSearch* h_search = reinterpret_cast<CraSearch*>(c->h_meta + (size_t)n * sizeof(int4));
     int* h_rs = reinterpret_cast<int*>(c->h_meta + (size_t)n * (sizeof(CraSearch) + sizeof(int4)));
     int* h_cs = h_rs + n + nb;
-    const int rpb = cra_polar_rows_per_block();
+    const int rpb = c->rpb;
     std::vector<int> bchunks(nb);
     std::vector<char> bgroup(nb, 0);
     memcpy(h_search, search, (size_t)n * sizeof(CraSearch));
@@ -901,7 +922,7 @@ static int align_impl(CraCtx* c, int start, int stop, const CraSearch* search, c
             if (cra_launch_polar_group(c->d_images, c->nx, c->d_tab, c->htab, c->d_samp, c->d_twf, c->items, c->plan, map,
                                        c->cfg.normalize_ring, c->d_spec, c->frag, c->d_norm, c->st)) { nvtxRangePop(); return 1; }
         } else if (cra_launch_polar_rows(c->d_images, c->nx, c->d_tab, c->htab, c->d_samp, c->d_sampw, c->d_twf, c->items, map,
-                                         c->cfg.normalize_ring, c->d_spec, c->fmt, c->frag, c->d_norm, c->st)) { nvtxRangePop(); return 1; }
+                                         c->cfg.normalize_ring, c->d_spec, c->fmt, c->frag, c->d_norm, c->rpb, c->gimg_rows, c->st)) { nvtxRangePop(); return 1; }
         nvtxRangePop();
         if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 1], c->st));
         if (class_of) {
@@ -1168,7 +1189,7 @@ extern "C" int cra_polar_spectrum(CraCtx* c, int particle, float cx, float cy, f
     if (particle < 0 || particle >= c->cfg.max_particles) { cra_set_error("bad particle index"); return 1; }
     if (wait_uploads(c, particle, 1)) return 1;
     if (cra_launch_polar_single(c->d_images + (size_t)particle * c->npix, c->nx, c->d_tab, c->htab, c->d_samp, c->d_sampw,
-                                c->d_twf, c->items, cx, cy, c->cfg.normalize_ring, c->d_spec, c->fmt, c->frag, c->d_norm, c->st)) return 1;
+                                c->d_twf, c->items, cx, cy, c->cfg.normalize_ring, c->d_spec, c->fmt, c->frag, c->d_norm, c->gimg_one, c->st)) return 1;
     const size_t bytes = (c->fmt == CRA_FMT_FRAG) ? c->row_bytes : 4 * c->row_bytes;
     CRA_CUDA(cudaMemcpyAsync(c->h_group, c->d_spec, bytes, cudaMemcpyDeviceToHost, c->st));
     CRA_CUDA(cudaStreamSynchronize(c->st));
@@ -1215,7 +1236,7 @@ extern "C" int cra_ccf_curves(CraCtx* c, int particle, float cx, float cy, int i
     if (particle < 0 || particle >= c->cfg.max_particles || iref < 0 || iref >= c->R) { cra_set_error("bad index"); return 1; }
     if (wait_uploads(c, particle, 1)) return 1;
     if (cra_launch_polar_single(c->d_images + (size_t)particle * c->npix, c->nx, c->d_tab, c->htab, c->d_samp, c->d_sampw,
-                                c->d_twf, c->items, cx, cy, c->cfg.normalize_ring, c->d_spec, c->fmt, c->frag, c->d_norm, c->st)) return 1;
+                                c->d_twf, c->items, cx, cy, c->cfg.normalize_ring, c->d_spec, c->fmt, c->frag, c->d_norm, c->gimg_one, c->st)) return 1;
     if (cra_launch_ccf_curves(c->d_spec, 0, c->d_refspec, iref, c->d_tab, c->htab,
                               c->d_curves, c->d_curves + c->htab.maxrin, c->fmt, c->frag, c->st)) return 1;
     CRA_CUDA(cudaMemcpyAsync(q_out, c->d_curves, c->htab.maxrin * sizeof(float), cudaMemcpyDeviceToHost, c->st));

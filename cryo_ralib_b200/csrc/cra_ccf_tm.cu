@@ -44,6 +44,9 @@ constexpr int kMaxWarps = 16;
 #ifndef CRA_TM_CONST_TW
 #define CRA_TM_CONST_TW 1
 #endif
+#ifndef CRA_TM_P2_UNROLL
+#define CRA_TM_P2_UNROLL 0
+#endif
 
 // Pass-1 twiddles exp(+2 pi i n2 k1 / N) of every supported N (32 .. 1024), table of N at offset N - 32.  The index of a
 // load is uniform over the warp (n2 is the warp's residue, k1 a constant), so the constant cache serves it without an
@@ -76,11 +79,20 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], unsigned a0, unsigned a1
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// experiments (profiles/README.md): operand loads that do not allocate in L1 (its hit rate is 6 %)
+#ifndef CRA_TM_LD_NOALLOC
+#define CRA_TM_LD_NOALLOC 0
+#endif
+#if CRA_TM_LD_NOALLOC
+#define CRA_TM_LDQ "ld.global.nc.L1::no_allocate"
+#else
+#define CRA_TM_LDQ "ld.global.nc"
+#endif
 struct Frag8 { unsigned w[8]; };
 __device__ __forceinline__ Frag8 ldg256(const unsigned char* p)
 {
     Frag8 f;
-    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile(CRA_TM_LDQ ".v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(f.w[0]), "=r"(f.w[1]), "=r"(f.w[2]), "=r"(f.w[3]), "=r"(f.w[4]), "=r"(f.w[5]), "=r"(f.w[6]), "=r"(f.w[7])
                  : "l"(p));
     return f;
@@ -88,7 +100,7 @@ __device__ __forceinline__ Frag8 ldg256(const unsigned char* p)
 __device__ __forceinline__ uint4 ldg128(const unsigned char* p)
 {
     uint4 v;
-    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    asm volatile(CRA_TM_LDQ ".v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
 
@@ -295,6 +307,9 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
         __syncthreads();
         // pass 2: (pair, k1): N2-point DFT over n2 -> X[k1 + N1*k2]; only the MAXIMA of q = Re X and t = Im X are
         // kept -- finalize_kernel re-derives the lag of the particle's winner in double precision
+#if CRA_TM_P2_UNROLL
+#pragma unroll 2
+#endif
         for (int item = tid; item < 32 * N1; item += kThreads) {
             const int pi = item / N1, k1 = item - pi * N1;
             const float2* w = s_y + pi * PS + k1 * (N2 + 1);

@@ -166,21 +166,23 @@ int cra_ensure_dyn_smem(const void* func, size_t bytes);
 int cra_launch_mask_normalize(float* imgs, int n, int nx, const float* mask, int mode, float* dc_out, cudaStream_t st);
 // particle rows described by map -> spec[row]; references -> refspec (weights applied)
 // twid_fwd[j] = exp(-2 pi i j / maxrin), j < maxrin
-int cra_polar_rows_per_block();
-size_t cra_polar_general_smem(int nx, const CraRingTab& htab);
+// the general row kernel's variant for a geometry: rows per CTA (want_rpb or 1) and whether the image tile fits
+// into shared memory beside the polar rows (gimg = 1: taps read from global memory); 1 = not even one polar row fits
+int cra_polar_default_rpb();
+int cra_polar_general_layout(int nx, const CraRingTab& htab, size_t smem_limit, int want_rpb, int* rpb, int* gimg);
 // norm: [rows] (avg, 1/sigma) written by the row kernels (FRAG format only, may be null otherwise);
 // tref: [R] written by the reference kernel (FRAG format only)
 int cra_launch_polar_rows(const float* images, int nx, const CraRingTab* tab, const CraRingTab& htab,
                           const float4* samp, const float* sampw, const float2* twid_fwd, const CraPolarItems& items,
                           CraRowMap map, int normalize_ring, float* spec, int fmt, const CraFragTab& frag,
-                          float2* norm, cudaStream_t st);
+                          float2* norm, int rpb, int gimg, cudaStream_t st);
 int cra_launch_polar_refs(const float* refs, int R, int nx, const CraRingTab* tab, const CraRingTab& htab,
                           const float4* samp, const float2* twid_fwd, const CraPolarItems& items, float* refspec,
-                          int fmt, const CraFragTab& frag, float* tref, cudaStream_t st);
+                          int fmt, const CraFragTab& frag, float* tref, int gimg, cudaStream_t st);
 int cra_launch_polar_single(const float* image, int nx, const CraRingTab* tab, const CraRingTab& htab,
                             const float4* samp, const float* sampw, const float2* twid_fwd, const CraPolarItems& items,
                             float cx, float cy, int normalize_ring, float* spec, int fmt, const CraFragTab& frag,
-                            float2* norm, cudaStream_t st);
+                            float2* norm, int gimg, cudaStream_t st);
 size_t cra_polar_group_smem(int nx, int maxrin, const CraGroupPlan& plan);
 int cra_launch_polar_group(const float* images, int nx, const CraRingTab* tab, const CraRingTab& htab,
                            const float4* samp, const float2* twid_fwd, const CraPolarItems& items, const CraGroupPlan& plan,
@@ -220,10 +222,12 @@ int cra_launch_rotsum(const float* images, int nx, int p0, int n, const float4* 
 int cra_fp32_peak(double* tf_ffma, double* tf_ffma2);
 // references from class sums, tangent low-pass of nx x nx images in place (cra_refavg.cu)
 int cra_launch_class_average(const float* sums, const float* counts, float* refs, int R, int nx, cudaStream_t st);
-int cra_launch_tanl_filter(float* imgs, int n, int nx, float fl, float aa, cudaStream_t st);
+// scratch: global buffer for boxes whose spectra exceed shared memory (cra_dft_scratch_elems float2 per image; else unused)
+size_t cra_dft_scratch_elems(int nx, int nsh, int nspec);
+int cra_launch_tanl_filter(float* imgs, int n, int nx, float fl, float aa, float2* scratch, cudaStream_t st);
 // reference update on the device (cra_refupdate.cu): class averages + ring-binned FSC sums; filt_tanl + centring
 int cra_launch_class_fsc(const float* sums, const float* counts, float* refs, const short* shell, const float* mask, int R,
                          int nx, int nsh, int masked, int min_members, int write_avg, float avg_div, double* fsc_out,
-                         cudaStream_t st);
+                         float2* scratch, cudaStream_t st);
 int cra_launch_filter_center(float* imgs, int n, int nx, float fl, float aa, int mode, float sx, float sy, float* cs_out,
-                             cudaStream_t st);
+                             float2* scratch, cudaStream_t st);

@@ -132,7 +132,9 @@ struct Chunk { int part, row0, nrow; };
 
 // MODE: 0 = particle rows (optional Normalize_ring), 1 = references (Applyws)
 // FMT: CRA_FMT_F32 = planar-pair float2 device spectrum, CRA_FMT_FRAG = split-bf16 fragment layout
-template <int MODE, int RPB, int FMT>
+// GIMG: the image does not fit into shared memory beside the polar rows (boxes beyond ~170 pixels): the six taps of
+// every sample are read from global memory instead (L1 / L2; one particle is read by its few CTAs only), same arithmetic
+template <int MODE, int RPB, int FMT, bool GIMG>
 __global__ void __launch_bounds__(kPolarThreads)
 polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __restrict__ tab,
                  const float4* __restrict__ samp, const float* __restrict__ sampw,
@@ -145,8 +147,8 @@ polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __r
     const int lcirc = tab->lcirc;
     const int lcp = tab->lcpad;
     const int maxrin = tab->maxrin;
-    float* s_img = smem;                                     // npix (padded to 4)
-    float* s_circ = smem + ((npix + 3) & ~3);                // RPB * lcp
+    float* s_img = smem;                                     // npix (padded to 4); absent with GIMG
+    float* s_circ = smem + (GIMG ? 0 : ((npix + 3) & ~3));   // RPB * lcp
     float2* s_tw = reinterpret_cast<float2*>(s_circ + RPB * lcp);   // maxrin : exp(-2 pi i j / maxrin)
     __shared__ float s_red[kPolarThreads / 32][2 * RPB];
     __shared__ Chunk s_chunk;
@@ -190,14 +192,16 @@ polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __r
     __syncthreads();
     const Chunk ck = s_chunk;
     const float* img = images + (size_t)ck.part * npix;
-    if ((npix & 3) == 0) {
-        const float4* g4 = reinterpret_cast<const float4*>(img);
-        float4* s4 = reinterpret_cast<float4*>(s_img);
-        for (int i = tid; i < (npix >> 2); i += kPolarThreads) s4[i] = __ldg(g4 + i);
-    } else {
-        for (int i = tid; i < npix; i += kPolarThreads) s_img[i] = __ldg(img + i);
+    if (!GIMG) {
+        if ((npix & 3) == 0) {
+            const float4* g4 = reinterpret_cast<const float4*>(img);
+            float4* s4 = reinterpret_cast<float4*>(s_img);
+            for (int i = tid; i < (npix >> 2); i += kPolarThreads) s4[i] = __ldg(g4 + i);
+        } else {
+            for (int i = tid; i < npix; i += kPolarThreads) s_img[i] = __ldg(img + i);
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
     // ---- resample every row of the sub-group -------------------------------------------------
     // The table holds one quarter of every ring (alrl_ms builds the other three by symmetry:
@@ -234,8 +238,9 @@ polar_fft_kernel(const float* __restrict__ images, int nx, const CraRingTab* __r
                 float* circ = s_circ + r * lcp;
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
-                    const float v = all_inside ? quadri_inside(ox[m] + cx, oy[m] + cy, nx, s_img)
-                                               : quadri_smem(ox[m] + cx, oy[m] + cy, nx, s_img);
+                    float v;
+                    if (GIMG) v = all_inside ? quadri_inside(ox[m] + cx, oy[m] + cy, nx, img) : quadri_smem(ox[m] + cx, oy[m] + cy, nx, img);
+                    else      v = all_inside ? quadri_inside(ox[m] + cx, oy[m] + cy, nx, s_img) : quadri_smem(ox[m] + cx, oy[m] + cy, nx, s_img);
                     circ[slot[m]] = v;
                     if (MODE == 0) { av[r] += v * wn; sq[r] += v * v * wn; }
                 }
@@ -463,48 +468,68 @@ mask_normalize_kernel(float* __restrict__ imgs, int npix, const float* __restric
     for (int i = threadIdx.x; i < npix; i += blockDim.x) img[i] = (img[i] - mean) / sig;
 }
 
-template <int RPB>
-size_t polar_smem_bytes(int nx, const CraRingTab& h)
+size_t polar_smem_bytes(int rpb, bool gimg, int nx, const CraRingTab& h)
 {
-    size_t npix = ((size_t)nx * nx + 3) & ~(size_t)3;
+    size_t npix = gimg ? 0 : (((size_t)nx * nx + 3) & ~(size_t)3);
     size_t lc = (size_t)h.lcpad;
-    return (npix + RPB * lc) * sizeof(float) + (size_t)h.maxrin * sizeof(float2);
+    return (npix + rpb * lc) * sizeof(float) + (size_t)h.maxrin * sizeof(float2);
+}
+
+template <int MODE, int RPB, int FMT, bool GIMG>
+int launch_polar_g(const float* images, int nx, const CraRingTab* tab, const CraRingTab& htab,
+                   const float4* samp, const float* sampw, const float2* twid, const CraPolarItems& items,
+                   CraRowMap map, float cx, float cy, int normalize_ring, float* spec, const CraFragTab& frag,
+                   float2* norm, float* tref, int nblocks, cudaStream_t st)
+{
+    if (nblocks <= 0) return 0;
+    size_t smem = polar_smem_bytes(RPB, GIMG, nx, htab);
+    if (cra_ensure_dyn_smem(reinterpret_cast<const void*>(&polar_fft_kernel<MODE, RPB, FMT, GIMG>), smem)) return 1;
+    polar_fft_kernel<MODE, RPB, FMT, GIMG><<<nblocks, kPolarThreads, smem, st>>>(images, nx, tab, samp, sampw, twid, items, map,
+                                                                                cx, cy, normalize_ring, spec, frag, norm, tref);
+    CRA_CUDA(cudaGetLastError());
+    return 0;
 }
 
 template <int MODE, int RPB, int FMT>
 int launch_polar_f(const float* images, int nx, const CraRingTab* tab, const CraRingTab& htab,
                    const float4* samp, const float* sampw, const float2* twid, const CraPolarItems& items,
                    CraRowMap map, float cx, float cy, int normalize_ring, float* spec, const CraFragTab& frag,
-                   float2* norm, float* tref, int nblocks, cudaStream_t st)
+                   float2* norm, float* tref, int nblocks, bool gimg, cudaStream_t st)
 {
-    if (nblocks <= 0) return 0;
-    size_t smem = polar_smem_bytes<RPB>(nx, htab);
-    if (cra_ensure_dyn_smem(reinterpret_cast<const void*>(&polar_fft_kernel<MODE, RPB, FMT>), smem)) return 1;
-    polar_fft_kernel<MODE, RPB, FMT><<<nblocks, kPolarThreads, smem, st>>>(images, nx, tab, samp, sampw, twid, items, map,
-                                                                          cx, cy, normalize_ring, spec, frag, norm, tref);
-    CRA_CUDA(cudaGetLastError());
-    return 0;
+    if (gimg)
+        return launch_polar_g<MODE, RPB, FMT, true>(images, nx, tab, htab, samp, sampw, twid, items, map, cx, cy, normalize_ring,
+                                                    spec, frag, norm, tref, nblocks, st);
+    return launch_polar_g<MODE, RPB, FMT, false>(images, nx, tab, htab, samp, sampw, twid, items, map, cx, cy, normalize_ring,
+                                                 spec, frag, norm, tref, nblocks, st);
 }
 
 template <int MODE, int RPB>
 int launch_polar(const float* images, int nx, const CraRingTab* tab, const CraRingTab& htab,
                  const float4* samp, const float* sampw, const float2* twid, const CraPolarItems& items,
                  CraRowMap map, float cx, float cy, int normalize_ring, float* spec, int fmt, const CraFragTab& frag,
-                 float2* norm, float* tref, int nblocks, cudaStream_t st)
+                 float2* norm, float* tref, int nblocks, bool gimg, cudaStream_t st)
 {
     if (fmt == CRA_FMT_FRAG)
         return launch_polar_f<MODE, RPB, CRA_FMT_FRAG>(images, nx, tab, htab, samp, sampw, twid, items, map, cx, cy,
-                                                       normalize_ring, spec, frag, norm, tref, nblocks, st);
+                                                       normalize_ring, spec, frag, norm, tref, nblocks, gimg, st);
     return launch_polar_f<MODE, RPB, CRA_FMT_F32>(images, nx, tab, htab, samp, sampw, twid, items, map, cx, cy,
-                                                  normalize_ring, spec, frag, nullptr, nullptr, nblocks, st);
+                                                  normalize_ring, spec, frag, nullptr, nullptr, nblocks, gimg, st);
 }
 
 }  // namespace
 
-int cra_polar_rows_per_block() { return CRA_POLAR_RPB; }
-
-// dynamic shared memory the general kernel needs for one row (references, test entries)
-size_t cra_polar_general_smem(int nx, const CraRingTab& htab) { return polar_smem_bytes<1>(nx, htab); }
+// Which variant of the general kernel a geometry gets: rows per CTA and whether the image is staged in shared memory.
+// Preference: RPB rows + image tile, one row + image tile, RPB rows from global memory, one row from global memory.
+// Returns 1 when not even one polar row fits (ou beyond ~108 with maxrin 1024).
+int cra_polar_general_layout(int nx, const CraRingTab& htab, size_t smem_limit, int want_rpb, int* rpb, int* gimg)
+{
+    const int cand_rpb[2] = {want_rpb, 1};
+    for (int g = 0; g < 2; ++g)
+        for (int i = 0; i < 2; ++i)
+            if (polar_smem_bytes(cand_rpb[i], g != 0, nx, htab) + 4096 <= smem_limit) { *rpb = cand_rpb[i]; *gimg = g; return 0; }
+    return 1;
+}
+int cra_polar_default_rpb() { return CRA_POLAR_RPB; }
 
 int cra_launch_mask_normalize(float* imgs, int n, int nx, const float* mask, int mode, float* dc_out, cudaStream_t st)
 {
@@ -517,28 +542,32 @@ int cra_launch_mask_normalize(float* imgs, int n, int nx, const float* mask, int
 int cra_launch_polar_rows(const float* images, int nx, const CraRingTab* tab, const CraRingTab& htab,
                           const float4* samp, const float* sampw, const float2* twid, const CraPolarItems& items,
                           CraRowMap map, int normalize_ring, float* spec, int fmt, const CraFragTab& frag,
-                          float2* norm, cudaStream_t st)
+                          float2* norm, int rpb, int gimg, cudaStream_t st)
 {
+    if (rpb == 1)
+        return launch_polar<0, 1>(images, nx, tab, htab, samp, sampw, twid, items, map, 0.f, 0.f,
+                                  normalize_ring, spec, fmt, frag, norm, nullptr, map.nchunks, gimg != 0, st);
+    if (rpb != CRA_POLAR_RPB) { cra_set_error("general row kernel: unsupported rows per block"); return 1; }
     return launch_polar<0, CRA_POLAR_RPB>(images, nx, tab, htab, samp, sampw, twid, items, map, 0.f, 0.f,
-                                          normalize_ring, spec, fmt, frag, norm, nullptr, map.nchunks, st);
+                                          normalize_ring, spec, fmt, frag, norm, nullptr, map.nchunks, gimg != 0, st);
 }
 
 int cra_launch_polar_refs(const float* refs, int R, int nx, const CraRingTab* tab, const CraRingTab& htab,
                           const float4* samp, const float2* twid, const CraPolarItems& items, float* refspec,
-                          int fmt, const CraFragTab& frag, float* tref, cudaStream_t st)
+                          int fmt, const CraFragTab& frag, float* tref, int gimg, cudaStream_t st)
 {
     CraRowMap map{};
     return launch_polar<1, 1>(refs, nx, tab, htab, samp, nullptr, twid, items, map, 0.f, 0.f, 0, refspec, fmt, frag,
-                              nullptr, tref, R, st);
+                              nullptr, tref, R, gimg != 0, st);
 }
 
 int cra_launch_polar_single(const float* image, int nx, const CraRingTab* tab, const CraRingTab& htab,
                             const float4* samp, const float* sampw, const float2* twid, const CraPolarItems& items,
                             float cx, float cy, int normalize_ring, float* spec, int fmt, const CraFragTab& frag,
-                            float2* norm, cudaStream_t st)
+                            float2* norm, int gimg, cudaStream_t st)
 {
     CraRowMap map{};
     map.row_start = nullptr; map.p0 = 0;
     return launch_polar<0, 1>(image, nx, tab, htab, samp, sampw, twid, items, map, cx, cy, normalize_ring, spec, fmt, frag,
-                              norm, nullptr, 1, st);
+                              norm, nullptr, 1, gimg != 0, st);
 }

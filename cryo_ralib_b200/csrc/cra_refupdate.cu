@@ -62,21 +62,24 @@ __device__ __forceinline__ float2 dft_col(const float2* B, const float2* tw, int
 }
 
 // One CTA per class.  shared: A [nx][nh] float2 (first the image), B [nx][nh], E [nx][nh], tw [nx], then the shell sums.
+// GS: boxes whose three spectra exceed shared memory (nx beyond ~136) keep A, B, E in a global scratch buffer
+// (3 nx nh float2 per class, L2-resident); the arithmetic and its order are the same.
 //   shell [nx][nh]: shell index of the half-complex coefficient (ky, kx), or -1 where fsc skips it (host table:
 //   Friedel mates on the kx = 0 column, shells beyond nx/2)
 //   fsc_out [R][3][nsh] double: num, |E|^2, |O|^2
 //   masked: subtract the in-mask mean and multiply by the mask first (fsc_mask)
+template <bool GS>
 __global__ void __launch_bounds__(256)
 class_fsc_kernel(const float* __restrict__ sums, const float* __restrict__ counts, float* __restrict__ refs,
                  const short* __restrict__ shell, const float* __restrict__ mask, int nx, int nsh, int masked, int min_members,
-                 int write_avg, float avg_div, double* __restrict__ fsc_out)
+                 int write_avg, float avg_div, double* __restrict__ fsc_out, float2* __restrict__ scratch)
 {
     extern __shared__ __align__(16) float2 s_f[];
     const int nh = nx / 2 + 1, nf = nx * nh, npix = nx * nx;
-    float2* A = s_f;
+    float2* A = GS ? scratch + (size_t)blockIdx.x * 3 * nf : s_f;
     float2* B = A + nf;
     float2* E = B + nf;
-    float2* tw = E + nf;
+    float2* tw = GS ? s_f : E + nf;
     double* acc = reinterpret_cast<double*>(tw + nx + (nx & 1));        // 3 * nsh doubles (8-byte aligned)
     __shared__ double s_red[2][8];
     float* img = reinterpret_cast<float*>(A);
@@ -134,14 +137,16 @@ class_fsc_kernel(const float* __restrict__ sums, const float* __restrict__ count
 
 // One CTA per reference, in place.  mode 0: filter only; 1: filter, then centre by the phase centre of gravity;
 // 2: filter, then shift by (-shift.x, -shift.y) (the same shift for every image).  cs_out [n][2]: the shift removed.
+template <bool GS>
 __global__ void __launch_bounds__(256)
-filter_center_kernel(float* __restrict__ imgs, int nx, float fl, float aa, int mode, float2 shift, float* __restrict__ cs_out)
+filter_center_kernel(float* __restrict__ imgs, int nx, float fl, float aa, int mode, float2 shift, float* __restrict__ cs_out,
+                     float2* __restrict__ scratch)
 {
     extern __shared__ __align__(16) float2 s_f[];
     const int nh = nx / 2 + 1, nf = nx * nh;
-    float2* A = s_f;
-    float2* B = s_f + nf;
-    float2* tw = B + nf;
+    float2* A = GS ? scratch + (size_t)blockIdx.x * 2 * nf : s_f;
+    float2* B = A + nf;
+    float2* tw = GS ? s_f : B + nf;
     __shared__ float s_cs[2];
     float* img = reinterpret_cast<float*>(A);
     float* g = imgs + (size_t)blockIdx.x * nx * nx;
@@ -231,35 +236,50 @@ size_t cra_class_fsc_smem(int nx, int nsh)
     return (3 * (size_t)nx * nh + nx + (nx & 1)) * sizeof(float2) + 3 * (size_t)nsh * sizeof(double);
 }
 
+// float2 elements of global scratch one image needs when its spectra do not fit into shared memory (0: they fit)
+size_t cra_dft_scratch_elems(int nx, int nsh, int nspec)
+{
+    const size_t nh = (size_t)nx / 2 + 1;
+    const size_t smem = ((size_t)nspec * nx * nh + nx + (nx & 1)) * sizeof(float2) + 3 * (size_t)nsh * sizeof(double);
+    int dev = 0, lim = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 0;
+    return (smem + 1024 > (size_t)lim) ? (size_t)nspec * nx * nh : 0;
+}
+
 int cra_launch_class_fsc(const float* sums, const float* counts, float* refs, const short* shell, const float* mask, int R,
                          int nx, int nsh, int masked, int min_members, int write_avg, float avg_div, double* fsc_out,
-                         cudaStream_t st)
+                         float2* scratch, cudaStream_t st)
 {
     if (R <= 0) return 0;
-    const size_t smem = cra_class_fsc_smem(nx, nsh);
-    int dev = 0, lim = 0;
-    CRA_CUDA(cudaGetDevice(&dev));
-    CRA_CUDA(cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    if (smem > (size_t)lim) { cra_set_error("device reference update: image too large for the shared-memory transform"); return 1; }
-    if (cra_ensure_dyn_smem(reinterpret_cast<const void*>(&class_fsc_kernel), smem)) return 1;
-    class_fsc_kernel<<<R, 256, smem, st>>>(sums, counts, refs, shell, mask, nx, nsh, masked, min_members, write_avg, avg_div, fsc_out);
+    if (cra_dft_scratch_elems(nx, nsh, 3)) {
+        if (!scratch) { cra_set_error("device reference update: no scratch buffer for a box this large"); return 1; }
+        const size_t smem = ((size_t)nx + (nx & 1)) * sizeof(float2) + 3 * (size_t)nsh * sizeof(double);
+        class_fsc_kernel<true><<<R, 256, smem, st>>>(sums, counts, refs, shell, mask, nx, nsh, masked, min_members, write_avg,
+                                                     avg_div, fsc_out, scratch);
+    } else {
+        const size_t smem = cra_class_fsc_smem(nx, nsh);
+        if (cra_ensure_dyn_smem(reinterpret_cast<const void*>(&class_fsc_kernel<false>), smem)) return 1;
+        class_fsc_kernel<false><<<R, 256, smem, st>>>(sums, counts, refs, shell, mask, nx, nsh, masked, min_members, write_avg,
+                                                      avg_div, fsc_out, nullptr);
+    }
     CRA_CUDA(cudaGetLastError());
     return 0;
 }
 
 int cra_launch_filter_center(float* imgs, int n, int nx, float fl, float aa, int mode, float sx, float sy, float* cs_out,
-                             cudaStream_t st)
+                             float2* scratch, cudaStream_t st)
 {
     if (n <= 0) return 0;
     if (!(fl > 0.f) || !(aa > 0.f)) { cra_set_error("tangent filter: cut-off and fall-off must be positive"); return 1; }
     const size_t nh = (size_t)nx / 2 + 1;
-    const size_t smem = (2 * (size_t)nx * nh + nx) * sizeof(float2);
-    int dev = 0, lim = 0;
-    CRA_CUDA(cudaGetDevice(&dev));
-    CRA_CUDA(cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    if (smem > (size_t)lim) { cra_set_error("device reference update: image too large for the shared-memory transform"); return 1; }
-    if (cra_ensure_dyn_smem(reinterpret_cast<const void*>(&filter_center_kernel), smem)) return 1;
-    filter_center_kernel<<<n, 256, smem, st>>>(imgs, nx, fl, aa, mode, make_float2(sx, sy), cs_out);
+    if (cra_dft_scratch_elems(nx, 0, 2)) {
+        if (!scratch) { cra_set_error("tangent filter: no scratch buffer for a box this large"); return 1; }
+        filter_center_kernel<true><<<n, 256, (size_t)nx * sizeof(float2), st>>>(imgs, nx, fl, aa, mode, make_float2(sx, sy), cs_out, scratch);
+    } else {
+        const size_t smem = (2 * (size_t)nx * nh + nx) * sizeof(float2);
+        if (cra_ensure_dyn_smem(reinterpret_cast<const void*>(&filter_center_kernel<false>), smem)) return 1;
+        filter_center_kernel<false><<<n, 256, smem, st>>>(imgs, nx, fl, aa, mode, make_float2(sx, sy), cs_out, nullptr);
+    }
     CRA_CUDA(cudaGetLastError());
     return 0;
 }

@@ -45,6 +45,8 @@ __device__ __forceinline__ float restrict2(float x, int nx)
     return x;
 }
 
+// GIMG: the image does not fit into shared memory (boxes beyond ~238 pixels): the taps come from global memory
+template <bool GIMG>
 __global__ void __launch_bounds__(256)
 rotsum_kernel(const float* __restrict__ images, int nx, int p0, const float4* __restrict__ params,
               const int* __restrict__ iref, long global_offset, float* __restrict__ sums,
@@ -58,8 +60,9 @@ rotsum_kernel(const float* __restrict__ images, int nx, int p0, const float4* __
     const float* img = images + (size_t)(p0 + p) * npix;
     // the image tile: one bulk asynchronous copy (TMA) when the image is 16-byte granular, else a cooperative load
     __shared__ __align__(8) unsigned long long s_bar;
-    const bool bulk = cratma::bulk_ok(img, (size_t)npix * sizeof(float));
-    if (bulk) {
+    const bool bulk = !GIMG && cratma::bulk_ok(img, (size_t)npix * sizeof(float));
+    if (GIMG) {
+    } else if (bulk) {
         if (threadIdx.x == 0) {
             cratma::mbar_init(&s_bar, 1);
             cratma::bulk_load(s_img, img, (unsigned)(npix * sizeof(float)), &s_bar);
@@ -92,7 +95,8 @@ rotsum_kernel(const float* __restrict__ images, int nx, int p0, const float4* __
         const float x = __fsub_rn((float)ix, shiftxc);
         const float xold = __fadd_rn(__fmul_rn(x, cang), ysang);
         const float yold = __fadd_rn(__fmul_rn(x, sang), ycang);
-        const float v = quadri_bg(__fadd_rn(xold, 1.0f), __fadd_rn(yold, 1.0f), nx, s_img, ix + 1, iy + 1);
+        const float v = GIMG ? quadri_bg(__fadd_rn(xold, 1.0f), __fadd_rn(yold, 1.0f), nx, img, ix + 1, iy + 1)
+                             : quadri_bg(__fadd_rn(xold, 1.0f), __fadd_rn(yold, 1.0f), nx, s_img, ix + 1, iy + 1);
         const int ixd = (mirror && ix >= x_start) ? (x_start + nx - 1 - ix) : ix;
         const int o = iy * nx + ixd;
         if (dst) atomicAdd(dst + o, v);
@@ -156,8 +160,15 @@ int cra_launch_rotsum(const float* images, int nx, int p0, int n, const float4* 
 {
     if (n <= 0) return 0;
     const size_t smem = (((size_t)nx * nx + 3) & ~(size_t)3) * sizeof(float);
-    if (cra_ensure_dyn_smem(reinterpret_cast<const void*>(&rotsum_kernel), smem)) return 1;
-    rotsum_kernel<<<n, 256, smem, st>>>(images, nx, p0, params, iref, global_offset, sums, counts, out_images);
+    int dev = 0, lim = 0;
+    CRA_CUDA(cudaGetDevice(&dev));
+    CRA_CUDA(cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (smem + 1024 > (size_t)lim) {
+        rotsum_kernel<true><<<n, 256, 0, st>>>(images, nx, p0, params, iref, global_offset, sums, counts, out_images);
+    } else {
+        if (cra_ensure_dyn_smem(reinterpret_cast<const void*>(&rotsum_kernel<false>), smem)) return 1;
+        rotsum_kernel<false><<<n, 256, smem, st>>>(images, nx, p0, params, iref, global_offset, sums, counts, out_images);
+    }
     CRA_CUDA(cudaGetLastError());
     return 0;
 }
