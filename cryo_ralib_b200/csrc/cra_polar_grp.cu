@@ -163,6 +163,9 @@ __device__ __forceinline__ void repair_sample(int code, int r, const float4* __r
     atomicAdd(&s_fix[2 * r + 1], (v * v - old * old) * wn);
 }
 
+#ifndef CRA_GRP_MUNROLL
+#define CRA_GRP_MUNROLL 4           // quadrants of a sample quartet unrolled in the interpolation loop (code size against ILP)
+#endif
 #ifndef CRA_GRP_MINB
 #define CRA_GRP_MINB 2              // resident CTAs per SM the register allocation aims for
 #endif
@@ -319,24 +322,31 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
             const int4 rp = s_ring[__float_as_int(e.z)];
             const int jt = __float_as_int(e.w);
             const float wn = __int_as_float(rp.w);
-            const float ox[4] = {e.x, e.y, -e.x, -e.y}, oy[4] = {e.y, -e.x, -e.y, e.x};
+            float oxm = e.x, oym = e.y;                       // quadrant m of the quartet: (x, y) -> (y, -x) -> (-x, -y) -> (-y, x)
             int fragile = 0;       // samples so close to a pixel boundary that float rounding of the per-row
                                    // position (x = offset + centre, as Polar2Dm forms it) could pick another cell
             int ro[HR];
 #pragma unroll
             for (int r = 0; r < HR; ++r) ro[r] = (r < nr) ? g_rowoff[r] : 0;
+#if CRA_GRP_MUNROLL == 4
 #pragma unroll
+#elif CRA_GRP_MUNROLL == 2
+#pragma unroll 2
+#else
+#pragma unroll 1
+#endif
             for (int m = 0; m < 4; ++m) {
                 const int j = jt + m * rp.z, pj = j >> 1;
                 const int slot = 2 * (rp.x + pj + (pj >> rp.y)) + (j & 1);
-                const float X = ox[m] + bx, Y = oy[m] + by;
+                const float X = oxm + bx, Y = oym + by;
                 const int ix = (int)X, iy = (int)Y;
                 const float dx = X - (float)ix, dy = Y - (float)iy;
                 // A coordinate that is a whole number because BOTH its ring offset and the block's centre are whole
                 // numbers (the axis points of every ring under an integer centre: all of mref_ali2d) is exact in every
                 // row -- offset + centre is an integer sum -- so it cannot round into another cell.
-                const bool xf = (dx < 1e-4f || dx > 0.9999f) && !(cint_x && ox[m] == rintf(ox[m]));
-                const bool yf = (dy < 1e-4f || dy > 0.9999f) && !(cint_y && oy[m] == rintf(oy[m]));
+                const bool xf = (dx < 1e-4f || dx > 0.9999f) && !(cint_x && oxm == rintf(oxm));
+                const bool yf = (dy < 1e-4f || dy > 0.9999f) && !(cint_y && oym == rintf(oym));
+                { const float tq = oxm; oxm = oym; oym = -tq; }
                 if (xf || yf) fragile |= 1 << m;
                 // quadri: f0 + dx (c1 + (dx-1) c2 + dy c5) + dy (c3 + (dy-1) c4) as six tap weights
                 const float a2 = 0.5f * dx * (dx - 1.0f), b2 = 0.5f * dy * (dy - 1.0f), ab = dx * dy;

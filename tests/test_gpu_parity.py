@@ -248,11 +248,12 @@ def test_align_other_ring_geometries(oracle, nx, ou, xr):
     e.close()
 
 
-def test_box_beyond_shared_memory_is_refused_cleanly():
-    """nx=180, ou=84 (maxrin 1024): image + one polar row exceed a CTA's shared memory; cra_create says so."""
+def test_ring_set_beyond_shared_memory_is_refused_cleanly():
+    """nx=300, ou=140: ONE polar row (345 KB) exceeds a CTA's shared memory; cra_create says so.  (A box whose image
+    does not fit beside the polar rows is served from global memory: tests/test_gpu_largebox.py.)"""
     from cryo_ralib_b200.lib import CraError
-    with pytest.raises(CraError, match="box too large"):
-        _engine(180, 84, 1)
+    with pytest.raises(CraError, match="ou too large"):
+        _engine(300, 140, 1)
 
 
 def test_closed_loop_recovers_known_pose(oracle):
