@@ -47,6 +47,12 @@ constexpr int kMaxWarps = 16;
 #ifndef CRA_TM_P2_UNROLL
 #define CRA_TM_P2_UNROLL 1          // pass 2: both items of a thread in one body (3.87 -> 3.82 ms per 5.0M alignments)
 #endif
+#ifndef CRA_TM_LAZY
+#define CRA_TM_LAZY 1               // a tile ends without a barrier (config 4: 9.76 -> 9.58 ms per 5.0M alignments; config 2 unchanged)
+#endif
+#ifndef CRA_TM_EXP_NOLOAD
+#define CRA_TM_EXP_NOLOAD 0
+#endif
 #ifndef CRA_TM_P1_PIPE
 #define CRA_TM_P1_PIPE 1            // pass 1: the second residue's tensor-memory load in flight under the first transform (3.81 -> 3.77)
 #endif
@@ -243,6 +249,28 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
     // Persistent CTA: the work lists, the twiddles and the TMEM allocation above are set up once, then
     // the CTA walks the tiles with the grid stride.  Reference tile fastest, so that the CTAs resident
     // at any moment share the row spectra in L2.
+    // The best candidate of every row of a finished tile, from the pairs pass 2 left in s_pair.  With CRA_TM_LAZY a tile
+    // ends WITHOUT a barrier: a warp that has finished its share of the last pass 2 goes straight on to the operand loads
+    // of the next tile (pass 2 works from shared memory only; tensor memory was drained by pass 1), and the candidates
+    // of tile T are written after the first barrier of tile T + 1, which every warp reaches after its pass 2 of tile T
+    // and before any warp writes s_pair again.
+    auto emit_cand = [&](int tl) {
+        if (tid < 8) {
+            const int cm = tl / ncta_n, cn = tl - cm * ncta_n;
+            const int nj = qbase + (cn < qrem ? 1 : 0);
+            const int row = cm * 8 + tid;
+            if (row < nrows) {
+                CraCand best; best.v = -INFINITY; best.code = -1;
+                for (int j = 0; j < nj; ++j)
+                    for (int c = 0; c < 4; ++c) {
+                        const CraCand cd = s_pair[j * 32 + tid * 4 + c];
+                        if (cd.code >= 0 && cd.v >= best.v) best = cd;
+                    }
+                cand[(size_t)row * ncta_n + cn] = best;
+            }
+        }
+    };
+    int prev_tile = -1;
 #pragma unroll 1
     for (int tile = blockIdx.x; tile < (int)ntiles; tile += gridDim.x) {
     {
@@ -271,8 +299,13 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
         // a tile whose second reference quad is empty (the last tile of R = 50, every tile of R <= 4: reference-free
         // and class-bound alignment) neither loads nor multiplies it
         const bool two = nj > 1;
-#define CRA_LOAD_OPS(O, off)                                                             \
+#define CRA_LOAD_OPS_(O, off)                                                            \
         { O.a = ldg256(pa + (unsigned)(off)); O.b0 = ldg128(pb0 + (unsigned)(off)); if (two) O.b1 = ldg128(pb1 + (unsigned)(off)); }
+#if CRA_TM_EXP_NOLOAD      /* timing experiment, not a valid kernel: the steady-state loads are skipped, operands reused */
+#define CRA_LOAD_OPS(O, off) { if ((off) == 0x7fffffff) CRA_LOAD_OPS_(O, off) }
+#else
+#define CRA_LOAD_OPS(O, off) CRA_LOAD_OPS_(O, off)
+#endif
 #define CRA_COMPUTE(O, fl)                                                               \
         { mma_bf16(acc0, O.a.w[0], O.a.w[1], O.a.w[2], O.a.w[3], O.b0.z, O.b0.w);   /* a_hi b_lo */ \
           if (two) mma_bf16(acc1, O.a.w[0], O.a.w[1], O.a.w[2], O.a.w[3], O.b1.z, O.b1.w);       \
@@ -307,7 +340,7 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
         // has the multiplication of three other chunks to land in.
         Operands o0, o1, o2, o3;
         int4 ia = it4[0], ib = it4[1];
-        CRA_LOAD_OPS(o0, ia.x); CRA_LOAD_OPS(o1, ia.z); CRA_LOAD_OPS(o2, ib.x); CRA_LOAD_OPS(o3, ib.z);
+        CRA_LOAD_OPS_(o0, ia.x); CRA_LOAD_OPS_(o1, ia.z); CRA_LOAD_OPS_(o2, ib.x); CRA_LOAD_OPS_(o3, ib.z);
 #pragma unroll 1
         for (int i = 4; ; i += 4) {
             const bool more = i < nit;
@@ -324,12 +357,16 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
             CRA_LOAD_OPS(o3, ib.z);
         }
 #undef CRA_LOAD_OPS
+#undef CRA_LOAD_OPS_
 #undef CRA_COMPUTE
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#if CRA_TM_LAZY
+    if (prev_tile >= 0) emit_cand(prev_tile);
+#endif
     }
     {
     // tile scalars re-derived here instead of kept in registers across the contraction
@@ -409,22 +446,24 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
                 s_pair[j * 32 + pi] = cd;
             }
         }
+#if CRA_TM_LAZY
+        if (j + 1 < nj) __syncthreads();         // the next quad's pass 1 overwrites s_y
+#else
         __syncthreads();
+#endif
     }
-    if (tid < 8) {
-        const int row = row0 + tid;
-        if (row < nrows) {
-            CraCand best; best.v = -INFINITY; best.code = -1;
-            for (int j = 0; j < nj; ++j)
-                for (int c = 0; c < 4; ++c) {
-                    const CraCand cd = s_pair[j * 32 + tid * 4 + c];
-                    if (cd.code >= 0 && cd.v >= best.v) best = cd;
-                }
-            cand[(size_t)row * ncta_n + cn] = best;
-        }
-    }
+#if CRA_TM_LAZY
+    prev_tile = tile;
+#else
+    (void)cn;
+    emit_cand(tile);
+#endif
     }
     }   // tile loop
+#if CRA_TM_LAZY
+    __syncthreads();
+    if (prev_tile >= 0) emit_cand(prev_tile);
+#endif
     // every tcgen05.ld has completed (wait::ld) before the barriers above
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(s_tmem), "n"(S::COLS) : "memory");
