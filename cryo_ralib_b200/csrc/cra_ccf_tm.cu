@@ -53,6 +53,9 @@ constexpr int kMaxWarps = 16;
 #ifndef CRA_TM_EXP_NOLOAD
 #define CRA_TM_EXP_NOLOAD 0
 #endif
+#ifndef CRA_TM_EXP                  // timing experiments (not valid kernels): 2 no inverse FFT, 4 no contraction, 16 no pass 2, 32 no pass 1
+#define CRA_TM_EXP 0
+#endif
 #ifndef CRA_TM_P1_PIPE
 #define CRA_TM_P1_PIPE 1            // pass 1: the second residue's tensor-memory load in flight under the first transform (3.81 -> 3.77)
 #endif
@@ -282,7 +285,7 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     // ---- contraction: this warp's frequencies, chunk by chunk ---------------------------------
-    {
+    if (!(CRA_TM_EXP & 4)) {
         int rrow = row0 + g;
         if (rrow >= nrows) rrow = nrows - 1;
         const unsigned char* pa = spec + (size_t)rrow * row_bytes + t * 32;
@@ -378,8 +381,10 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
 
     // ---- inverse FFT, one reference quad (32 pairs: lane = pair) at a time -----------------------
     for (int j = 0; j < nj; ++j) {
+        if (CRA_TM_EXP & 2) break;
         // pass 1: (pair = lane, residue n2): N1-point DFT over n1 straight from this lane's TMEM, twiddle
 #if CRA_TM_P1_PIPE
+        if (!(CRA_TM_EXP & 32)) {
         constexpr int P1IT = (RQ + KW / 4 - 1) / (KW / 4);       // residues per warp (1 or 2)
         TmRegs<2 * N1> tr[2];
         tmem_issue(tbase + j * JCOLS + (warp >> 2) * (2 * N1), tr[0]);
@@ -409,6 +414,9 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
                 w[k1 * (N2 + 1)] = crafft::cmul(x[k1], tw);
             }
         }
+#if CRA_TM_P1_PIPE
+        }
+#endif
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         // pass 2: (pair, k1): N2-point DFT over n2 -> X[k1 + N1*k2]; only the MAXIMA of q = Re X and t = Im X are
@@ -417,6 +425,7 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
 #pragma unroll 2
 #endif
         for (int item = tid; item < 32 * N1; item += kThreads) {
+            if (CRA_TM_EXP & 16) break;
             const int pi = item / N1, k1 = item - pi * N1;
             const float2* w = s_y + pi * PS + k1 * (N2 + 1);
             float2 x[N2];

@@ -163,6 +163,9 @@ __device__ __forceinline__ void repair_sample(int code, int r, const float4* __r
     atomicAdd(&s_fix[2 * r + 1], (v * v - old * old) * wn);
 }
 
+#ifndef CRA_GRP_EXP                 // timing experiments (not valid kernels): 1 no interpolation, 2 no FFT passes, 4 no split, 8 no unit gather / stores
+#define CRA_GRP_EXP 0
+#endif
 #ifndef CRA_GRP_MUNROLL
 #define CRA_GRP_MUNROLL 4           // quadrants of a sample quartet unrolled in the interpolation loop (code size against ILP)
 #endif
@@ -318,6 +321,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
         const CraPhase P = plan.phases[ph];
         // ---- interpolate the phase's rings for every row: weights once per sample ----------------
         for (int q = P.q0 + gt; q < P.q1; q += GT) {
+            if (CRA_GRP_EXP & 1) break;
             const float4 e = __ldg(samp + q);                 // x, y, ring, jt (first quarter of the ring)
             const int4 rp = s_ring[__float_as_int(e.z)];
             const int jt = __float_as_int(e.w);
@@ -409,6 +413,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
         {
             const int nA = P.a1 - P.a0;
             for (int w = gt; w < nA * nr; w += GT) {
+                if (CRA_GRP_EXP & 2) break;
                 const int r = fastdiv(w, P.magicA), item = __ldg(items.A + P.a0 + (w - r * nA));
                 const int ring = item >> 16, b = item & 0xffff;
                 const int4 rp = s_ring[ring];
@@ -433,6 +438,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
         {
             const int nB = P.b1 - P.b0;
             for (int w = gt; w < nB * nr; w += GT) {
+                if (CRA_GRP_EXP & 2) break;
                 const int r = fastdiv(w, P.magicB), item = __ldg(items.B + P.b0 + (w - r * nB));
                 const int ring = item >> 16, ka = item & 0xffff;
                 const int4 rp = s_ring[ring];
@@ -460,6 +466,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
             const int nC = P.c1 - P.c0;
             const int nset = __ldg(&plan.phases[ph].nsetC[nr]);
             for (int x = gt; x < nC * nset; x += GT) {
+                if (CRA_GRP_EXP & 4) break;
                 const int set = fastdiv(x, P.magicC), item = __ldg(items.Cg + P.c0 + (x - set * nC));
                 const int ring = item >> 16, k = item & 0xffff;
                 const int4 rp = s_ring[ring];
@@ -496,6 +503,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
             const int nset = __ldg(&plan.phases[ph].nsetD[nr]);
             const size_t rb = cra_frag_row_bytes(frag.nch);
             for (int x = gt; x < upr * nset; x += GT) {
+                if (CRA_GRP_EXP & 8) break;
                 const int set = fastdiv(x, P.magicD), ditem = __ldg(items.D + P.d0 + (x - set * upr));
                 const int k = ditem & 0xffff, u = ditem >> 16;
                 // value of slot j = (v.x * mx + v.y * my, v.y * mi) of z[idx]: complex (1,0,1), F_0 = .x of
