@@ -383,29 +383,8 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
     for (int j = 0; j < nj; ++j) {
         if (CRA_TM_EXP & 2) break;
         // pass 1: (pair = lane, residue n2): N1-point DFT over n1 straight from this lane's TMEM, twiddle
-#if CRA_TM_P1_PIPE
         if (!(CRA_TM_EXP & 32)) {
-        constexpr int P1IT = (RQ + KW / 4 - 1) / (KW / 4);       // residues per warp (1 or 2)
-        TmRegs<2 * N1> tr[2];
-        tmem_issue(tbase + j * JCOLS + (warp >> 2) * (2 * N1), tr[0]);
-#pragma unroll
-        for (int pit = 0; pit < P1IT; ++pit) {
-            const int ri = (warp >> 2) + pit * (KW / 4);
-            if (ri >= RQ) break;
-            const int n2 = s_hdr.res[quad][ri];
-            float2 x[N1];
-            tmem_complete(tr[pit & 1]);
-            if (pit + 1 < P1IT && ri + KW / 4 < RQ) tmem_issue(tbase + j * JCOLS + (ri + KW / 4) * (2 * N1), tr[(pit + 1) & 1]);
-#pragma unroll
-            for (int i = 0; i < N1; ++i) x[i] = make_float2(__uint_as_float(tr[pit & 1].r[2 * i]), __uint_as_float(tr[pit & 1].r[2 * i + 1]));
-            fft_reg<N1, 1>(x);
-#else
-        for (int ri = warp >> 2; ri < RQ; ri += KW / 4) {
-            const int n2 = s_hdr.res[quad][ri];
-            float2 x[N1];
-            tmem_ld<2 * N1>(tbase + j * JCOLS + ri * (2 * N1), x);
-            fft_reg<N1, 1>(x);
-#endif
+        auto p1_emit = [&](float2 (&x)[N1], int n2) {            // twiddle and park the transform of residue n2
             float2* w = s_y + lane * PS + n2;
 #pragma unroll
             for (int k1 = 0; k1 < N1; ++k1) {
@@ -413,10 +392,34 @@ ccf_tm_kernel(const unsigned char* __restrict__ spec, int nrows, const unsigned 
                 const float2 tw = (CRA_TM_CONST_TW && LOG2N <= 8) ? c_itw[(N - 32) + k1 * N2 + n2] : s_tw[k1 * N2 + n2];   // 4 KB at N = 512 overflow the constant cache: +4 % there
                 w[k1 * (N2 + 1)] = crafft::cmul(x[k1], tw);
             }
-        }
+        };
+        constexpr int P1IT = (RQ + KW / 4 - 1) / (KW / 4);       // residues per warp (1 or 2)
 #if CRA_TM_P1_PIPE
+        {
+        TmRegs<2 * N1> tr[2];
+        tmem_issue(tbase + j * JCOLS + (warp >> 2) * (2 * N1), tr[0]);
+#pragma unroll
+        for (int pit = 0; pit < P1IT; ++pit) {
+            const int ri = (warp >> 2) + pit * (KW / 4);
+            if (ri >= RQ) break;
+            float2 x[N1];
+            tmem_complete(tr[pit & 1]);
+            if (pit + 1 < P1IT && ri + KW / 4 < RQ) tmem_issue(tbase + j * JCOLS + (ri + KW / 4) * (2 * N1), tr[(pit + 1) & 1]);
+#pragma unroll
+            for (int i = 0; i < N1; ++i) x[i] = make_float2(__uint_as_float(tr[pit & 1].r[2 * i]), __uint_as_float(tr[pit & 1].r[2 * i + 1]));
+            fft_reg<N1, 1>(x);
+            p1_emit(x, s_hdr.res[quad][ri]);
+        }
+        }
+#else
+        for (int ri = warp >> 2; ri < RQ; ri += KW / 4) {
+            float2 x[N1];
+            tmem_ld<2 * N1>(tbase + j * JCOLS + ri * (2 * N1), x);
+            fft_reg<N1, 1>(x);
+            p1_emit(x, s_hdr.res[quad][ri]);
         }
 #endif
+        }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         // pass 2: (pair, k1): N2-point DFT over n2 -> X[k1 + N1*k2]; only the MAXIMA of q = Re X and t = Im X are
