@@ -46,10 +46,20 @@ q_n, f_n, _ = ref_free_alignment_2d(images[s:e], cls[s:e], refs, ou=36, xr=2, yr
 q_n = gather(q_n)
 if rank == 0:
     q_1, f_1, _ = ref_free_alignment_2d(images, cls, refs, ou=36, xr=2, yr=2, ts=1, maxit=2, filt=(0.25, 0.2), device=local)
-    same = float((np.abs(q_n - q_1).max(axis=1) < 1e-3).mean()); dr = float(np.abs(f_n - f_1).max() / np.abs(f_1).max())
-    good = same > 0.995 and dr < 1e-3
+    differ = np.abs(q_n - q_1).max(axis=1) >= 1e-3
+    same = float((~differ).mean()); dr = float(np.abs(f_n - f_1).max() / np.abs(f_1).max())
+    # The class sums are float reductions (atomics, then NCCL), so the averages of the first pass differ in the last
+    # bits between ANY two runs; a particle sitting on a tie of the second pass may then take the other answer, and that
+    # particle moves its class average by up to ~2 max / (class size).  The averages of the classes WITHOUT such a
+    # particle must agree to the reduction-order bar.
+    touched = np.unique(cls[differ])
+    clean = np.setdiff1d(np.arange(R), touched)
+    dr_clean = float(np.abs(f_n[clean] - f_1[clean]).max() / np.abs(f_1).max()) if clean.size else 0.0
+    bar = 1e-3 + sum(2.0 * int((differ & (cls == c)).sum()) / max(int((cls == c).sum()), 1) for c in touched)
+    good = same > 0.995 and dr_clean < 1e-3 and dr < bar
     ok &= good
-    print("ref_free_2d   %d GPUs vs 1: parameters equal %.4f, references max rel diff %.2e  %s" % (world, same, dr, "OK" if good else "FAIL"))
+    print("ref_free_2d   %d GPUs vs 1: parameters equal %.4f (%d particles on a tie, classes %s), references max rel diff %.2e "
+          "(classes without such a particle: %.2e)  %s" % (world, same, int(differ.sum()), touched.tolist(), dr, dr_clean, "OK" if good else "FAIL"))
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
