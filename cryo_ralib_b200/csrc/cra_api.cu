@@ -138,6 +138,12 @@ int build_group_plan(CraCtx* c)
     // rows per CTA: as many as fit two CTAs per SM (fewer image reloads, shared index math), else one CTA
     c->plan.stride = (2 * cap + 3) & ~3;
     c->plan.nring = nring;
+    {   // Image tile: the whole image, or -- where that saves shared memory -- a square window around the particle's
+        // search window: ring radius + taps on both sides, the window's span, and the slack of a 16-byte aligned origin.
+        const int T = (2 * t.rad[nring - 1] + 2 * (int)ceilf(c->cfg.max_range) + 9 + 3) & ~3;
+        c->plan.tile = (T + 8 <= c->nx) ? T : 0;
+        if (const char* e = getenv("CRA_GRP_TILE")) { if (atoi(e) == 0) c->plan.tile = 0; }
+    }
     int dev = 0; cudaGetDevice(&dev);
     int smem_sm = 0, smem_blk = 0;
     cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
@@ -854,7 +860,8 @@ static int align_impl(CraCtx* c, int start, int stop, const CraSearch* search, c
     // (a pixel boundary: redone with quadri's circular closure) may touch the wrap-around neighbour
     const int sub = cra_group_sub(step);                       // phase classes per axis (0: the general kernel)
     const bool group_cfg = c->fmt == CRA_FMT_FRAG && c->use_group && c->plan.rmax > 0 && sub > 0;
-    const float rmaxf = (float)c->htab.rad[c->htab.nring - 1], lo_ok = 2.0f + rmaxf, hi_ok = (float)c->nx - rmaxf;
+    // (a windowed tile holds no wrap-around neighbours: its samples must also stay off the last column / row)
+    const float rmaxf = (float)c->htab.rad[c->htab.nring - 1], lo_ok = 2.0f + rmaxf, hi_ok = (float)c->nx - rmaxf - (c->plan.tile ? 1.0f : 0.0f);
     for (size_t bi = 0; bi < nb; ++bi) {
         int* rs = h_rs + bfirst[bi] + bi;
         int* cs = h_cs + bfirst[bi] + bi;

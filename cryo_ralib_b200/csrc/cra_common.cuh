@@ -81,6 +81,8 @@ struct CraGroupPlan {
     int rmax;                  // rows per CTA (<= CRA_GRP_RMAX), chosen for shared-memory fit
     int nh;                    // independent thread groups of a CTA: 2 when a group still has >= 6 rows, else 1
     int nring;
+    int tile;                  // 0: the shared-memory tile is the whole image; else the side (a multiple of 4) of a square
+                               // window around the particle's search window (boxes too large for, or much larger than, the ring set)
 };
 
 // Phase classes per axis of the grouped row kernel: 1 for a whole-pixel step, 2 or 4 for a step of 1/2 or 1/4

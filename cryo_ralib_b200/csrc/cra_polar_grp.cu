@@ -133,7 +133,7 @@ __device__ __forceinline__ int fastdiv(int w, int magic) { return (int)(((unsign
 // (x = offset + the row's own centre) and interpolated with quadri's own expression; the Normalize_ring
 // sums of the row are corrected through s_fix.
 __device__ __forceinline__ void repair_sample(int code, int r, const float4* __restrict__ samp, const int4* s_ring,
-                                              const float2* s_rowc, const float* s_img, int nx, float* s_buf,
+                                              const float2* s_rowc, const float* s_img, int nx, int pitch, float* s_buf,
                                               int stride, float* s_fix)
 {
     const int q = code >> 2, m = code & 3;
@@ -151,10 +151,11 @@ __device__ __forceinline__ void repair_sample(int code, int r, const float4* __r
     // quadri's circular closure of the neighbours (Util::quadri: ip1 > nx -> ip1 - nx, im1 < 1 -> im1 + nx)
     const int x0 = ix - 1, xp = (ix + 1 > nx) ? 0 : ix, xm = (ix - 1 < 1) ? nx - 1 : ix - 2;
     const int y0 = iy - 1, yp = (iy + 1 > nx) ? 0 : iy, ym = (iy - 1 < 1) ? nx - 1 : iy - 2;
-    const float f0 = s_img[y0 * nx + x0];
-    const float c1 = s_img[y0 * nx + xp] - f0, c2 = (c1 - f0 + s_img[y0 * nx + xm]) * 0.5f;
-    const float c3 = s_img[yp * nx + x0] - f0, c4 = (c3 - f0 + s_img[ym * nx + x0]) * 0.5f;
-    const float c5 = s_img[yp * nx + xp] - f0 - c1 - c3;
+    // s_img: pixel (0, 0) of the image (a windowed tile passes its origin-adjusted base; its samples never wrap)
+    const float f0 = s_img[y0 * pitch + x0];
+    const float c1 = s_img[y0 * pitch + xp] - f0, c2 = (c1 - f0 + s_img[y0 * pitch + xm]) * 0.5f;
+    const float c3 = s_img[yp * pitch + x0] - f0, c4 = (c3 - f0 + s_img[ym * pitch + x0]) * 0.5f;
+    const float c5 = s_img[yp * pitch + xp] - f0 - c1 - c3;
     const float v = f0 + dx * (c1 + (dx - 1.0f) * c2 + dy * c5) + dy * (c3 + (dy - 1.0f) * c4);
     float* dst = s_buf + r * stride;
     const float old = dst[sl];
@@ -186,9 +187,12 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
     const int npix = nx * nx;
     const int maxrin = tab->maxrin, nring = tab->nring;
     const int stride = plan.stride;                            // floats per row of the phase buffer
-    const int pitch = nx;                                      // dense tile: 1-based pixel (i, j) sits at (j - 1) * nx + (i - 1)
-    float* s_img = smem;                                       // nx * nx (padded to 4)
-    float* s_buf = smem + ((npix + 3) & ~3);                   // rmax * stride
+    // dense tile: the whole image (1-based pixel (i, j) at (j - 1) * nx + (i - 1)) or, with plan.tile, a square window of
+    // that side around the particle's search window whose origin (s_org) the CTA's first thread places
+    const int pitch = plan.tile ? plan.tile : nx;
+    const int tpix = plan.tile ? plan.tile * plan.tile : npix;
+    float* s_img = smem;                                       // pitch * pitch (padded to 4)
+    float* s_buf = smem + ((tpix + 3) & ~3);                   // rmax * stride
     float2* s_tw = reinterpret_cast<float2*>(s_buf + plan.rmax * stride);   // maxrin : exp(-2 pi i j / maxrin)
     int4* s_ring = reinterpret_cast<int4*>(s_tw + maxrin);    // nring : phase-local float2 offset, log2 NB, len/4, wn
     int* s_koff = reinterpret_cast<int*>(s_ring + nring);     // maxrin/2 + 2 : first chunk of frequency k
@@ -204,6 +208,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
     __shared__ int s_blk[4];                                   // particle (batch local), first local row, rows
     __shared__ float s_base[2];
     __shared__ int s_cls[4];                                   // phase class of the block: cx, cy, rows per window line, sub
+    __shared__ int s_org2[2];                                  // windowed tile: image pixel (x, y) of its first element
     __shared__ __align__(8) unsigned long long s_bar;          // completion of the image tile's bulk copy
 
     const int tid = threadIdx.x;
@@ -224,13 +229,33 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
         if (tid == 0) {
             // the image tile: one bulk asynchronous copy, in flight while the tables below are set up
             const float* img = images + (size_t)(map.p0 + lo) * npix;
-            const bool bulk = cratma::bulk_ok(img, (size_t)npix * sizeof(float));
-            if (bulk) {
-                cratma::mbar_init(&s_bar, 1);
-                cratma::bulk_load(s_img, img, (unsigned)(npix * sizeof(float)), &s_bar);
+            const int4 w = map.win[lo];
+            bool bulk;
+            if (plan.tile) {
+                // the window every shift row of this particle samples (taps included), origin on a 16-byte boundary and
+                // inside the frame (the host admits a windowed batch only if all its samples stay clear of the border)
+                const int T = plan.tile;
+                const bool al4 = (nx & 3) == 0;                    // lines of the image start on 16-byte boundaries
+                const int ro = (int)tab->rad[tab->nring - 1];
+                int x0 = (int)floorf(map.search[lo].cx - (float)w.x * map.step) - ro - 2;
+                int y0 = (int)floorf(map.search[lo].cy - (float)w.z * map.step) - ro - 2;
+                if (al4) x0 &= ~3;
+                x0 = max(0, min(x0, nx - T)); y0 = max(0, min(y0, nx - T));
+                s_org2[0] = x0; s_org2[1] = y0;
+                bulk = al4 && cratma::bulk_ok(img, 16);
+                if (bulk) {                                        // one bulk copy per tile line, all completing on one barrier
+                    cratma::mbar_init(&s_bar, T);
+                    for (int r = 0; r < T; ++r)
+                        cratma::bulk_load(s_img + r * T, img + (size_t)(y0 + r) * nx + x0, (unsigned)(T * sizeof(float)), &s_bar);
+                }
+            } else {
+                bulk = cratma::bulk_ok(img, (size_t)npix * sizeof(float));
+                if (bulk) {
+                    cratma::mbar_init(&s_bar, 1);
+                    cratma::bulk_load(s_img, img, (unsigned)(npix * sizeof(float)), &s_bar);
+                }
             }
             const int bi = b - map.chunk_start[lo];
-            const int4 w = map.win[lo];
             const int wx = w.x + w.y + 1, wy = w.z + w.w + 1;
             // A step of 1/sub pixel (sub = 2, 4) splits the window into sub x sub phase classes: the positions
             // (cx + sub i, cy + sub j) of a class lie one whole pixel apart and share their tap weights.  Blocks
@@ -295,11 +320,16 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
         if (s_blk[3] & 2) {
             cratma::mbar_wait(&s_bar, 0);                      // the bulk copy has landed
             if (dcv != 0.f)                                    // every waiting thread sees the whole tile
-                for (int i = tid; i < npix; i += kThreads) s_img[i] -= dcv;
+                for (int i = tid; i < tpix; i += kThreads) s_img[i] -= dcv;
+        } else if (plan.tile) {
+            const int T = plan.tile, x0 = s_org2[0], y0 = s_org2[1];
+            for (int i = tid; i < tpix; i += kThreads) { const int r = i / T, cx = i - r * T; s_img[i] = __ldg(img + (size_t)(y0 + r) * nx + x0 + cx) - dcv; }
         } else {
             for (int i = tid; i < npix; i += kThreads) s_img[i] = __ldg(img + i) - dcv;
         }
     }
+    // image pixel (0, 0) as seen through the tile (outside the tile's storage when the tile is a window)
+    const float* const s_org = plan.tile ? s_img - (s_org2[1] * pitch + s_org2[0]) : s_img;
     const float bx = s_base[0], by = s_base[1];
     // whole-pixel centres in every row of the block: the base centre is a whole number and the rows lie whole pixels apart
     const bool cint_x = bx == rintf(bx), cint_y = by == rintf(by);
@@ -360,7 +390,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                 const float w4 = b2;                    // (i, j-1)
                 const float w5 = ab;                    // (i+1, j+1)
                 const float w0 = 1.0f - dx - dy - 2.0f * a2 - 2.0f * b2 + ab;
-                const float* p0 = s_img + (iy * pitch + ix) - (pitch + 1);     // 1-based cell (ix, iy)
+                const float* p0 = s_org + (iy * pitch + ix) - (pitch + 1);     // 1-based cell (ix, iy)
                 float* dst = g_buf + slot;
                 // a row that continues the window line of the previous one (one pixel to the right) reuses
                 // three of its taps: (i-1,j) <- (i,j), (i,j) <- (i+1,j), (i,j+1) <- (i+1,j+1)
@@ -393,7 +423,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
                         if (at < kFragCap) g_frag[gt >> 5][at] = q * 4 + m;
                         else                // queue full (an integer or half-integer centre puts whole rings on cell
                             for (int r = 0; r < nr; ++r)    // boundaries): this lane repairs its own sample right away
-                                repair_sample(q * 4 + m, r, samp, s_ring, g_rowc, s_img, nx, g_buf, stride, g_fix);
+                                repair_sample(q * 4 + m, r, samp, s_ring, g_rowc, s_org, nx, pitch, g_buf, stride, g_fix);
                     }
             }
         }
@@ -405,7 +435,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
             const int nf = min(g_nfrag[wid], kFragCap);
             for (int x = gt & 31; x < nf * nr; x += 32) {
                 const int en = x / nr, r = x - en * nr;
-                repair_sample(g_frag[wid][en], r, samp, s_ring, g_rowc, s_img, nx, g_buf, stride, g_fix);
+                repair_sample(g_frag[wid][en], r, samp, s_ring, g_rowc, s_org, nx, pitch, g_buf, stride, g_fix);
             }
         }
         group_sync<NH>(grp);
@@ -588,7 +618,8 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
 
 size_t cra_polar_group_smem(int nx, int maxrin, const CraGroupPlan& plan)
 {
-    const size_t npix = ((size_t)nx * nx + 3) & ~(size_t)3;                 // the dense image tile
+    const size_t side = plan.tile ? (size_t)plan.tile : (size_t)nx;
+    const size_t npix = (side * side + 3) & ~(size_t)3;                     // the dense image tile (whole image or window)
     // + twiddles, ring table (<= CRA_MAX_RINGS int4), chunk offsets, unit lengths
     return (npix + (size_t)plan.rmax * plan.stride) * sizeof(float) + (size_t)maxrin * sizeof(float2)
          + (size_t)plan.nring * sizeof(int4) + (size_t)(maxrin / 2 + 2 + (plan.nring + 3) / 4) * sizeof(int);
