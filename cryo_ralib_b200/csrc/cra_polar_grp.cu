@@ -173,7 +173,9 @@ __device__ __forceinline__ void repair_sample(int code, int r, const float4* __r
 #ifndef CRA_GRP_MINB
 #define CRA_GRP_MINB 2              // resident CTAs per SM the register allocation aims for
 #endif
-template <int NH>
+// WIN: the tile is a window of the image (plan.tile) instead of the whole image; a template parameter so that the
+// whole-image instantiation of the named configurations keeps its constant pitch and tile base
+template <int NH, bool WIN>
 __global__ void __launch_bounds__(kThreads, CRA_GRP_MINB)
 polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* __restrict__ tab,
                    const float4* __restrict__ samp, const float2* __restrict__ twid, CraPolarItems items,
@@ -189,8 +191,8 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
     const int stride = plan.stride;                            // floats per row of the phase buffer
     // dense tile: the whole image (1-based pixel (i, j) at (j - 1) * nx + (i - 1)) or, with plan.tile, a square window of
     // that side around the particle's search window whose origin (s_org) the CTA's first thread places
-    const int pitch = plan.tile ? plan.tile : nx;
-    const int tpix = plan.tile ? plan.tile * plan.tile : npix;
+    const int pitch = WIN ? plan.tile : nx;
+    const int tpix = WIN ? plan.tile * plan.tile : npix;
     float* s_img = smem;                                       // pitch * pitch (padded to 4)
     float* s_buf = smem + ((tpix + 3) & ~3);                   // rmax * stride
     float2* s_tw = reinterpret_cast<float2*>(s_buf + plan.rmax * stride);   // maxrin : exp(-2 pi i j / maxrin)
@@ -231,7 +233,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
             const float* img = images + (size_t)(map.p0 + lo) * npix;
             const int4 w = map.win[lo];
             bool bulk;
-            if (plan.tile) {
+            if (WIN) {
                 // the window every shift row of this particle samples (taps included), origin on a 16-byte boundary and
                 // inside the frame (the host admits a windowed batch only if all its samples stay clear of the border)
                 const int T = plan.tile;
@@ -321,7 +323,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
             cratma::mbar_wait(&s_bar, 0);                      // the bulk copy has landed
             if (dcv != 0.f)                                    // every waiting thread sees the whole tile
                 for (int i = tid; i < tpix; i += kThreads) s_img[i] -= dcv;
-        } else if (plan.tile) {
+        } else if (WIN) {
             const int T = plan.tile, x0 = s_org2[0], y0 = s_org2[1];
             for (int i = tid; i < tpix; i += kThreads) { const int r = i / T, cx = i - r * T; s_img[i] = __ldg(img + (size_t)(y0 + r) * nx + x0 + cx) - dcv; }
         } else {
@@ -329,7 +331,7 @@ polar_group_kernel(const float* __restrict__ images, int nx, const CraRingTab* _
         }
     }
     // image pixel (0, 0) as seen through the tile (outside the tile's storage when the tile is a window)
-    const float* const s_org = plan.tile ? s_img - (s_org2[1] * pitch + s_org2[0]) : s_img;
+    const float* const s_org = WIN ? s_img - (s_org2[1] * pitch + s_org2[0]) : s_img;
     const float bx = s_base[0], by = s_base[1];
     // whole-pixel centres in every row of the block: the base centre is a whole number and the rows lie whole pixels apart
     const bool cint_x = bx == rintf(bx), cint_y = by == rintf(by);
@@ -631,15 +633,13 @@ int cra_launch_polar_group(const float* images, int nx, const CraRingTab* tab, c
 {
     if (map.nchunks <= 0) return 0;
     const size_t smem = cra_polar_group_smem(nx, htab.maxrin, plan);
-    if (plan.nh == 2) {
-        if (cra_ensure_dyn_smem(reinterpret_cast<const void*>(&polar_group_kernel<2>), smem)) return 1;
-        polar_group_kernel<2><<<map.nchunks, kThreads, smem, st>>>(images, nx, tab, samp, twid, items, plan, map, normalize_ring,
-                                                                  reinterpret_cast<unsigned char*>(spec), frag, norm);
-    } else {
-        if (cra_ensure_dyn_smem(reinterpret_cast<const void*>(&polar_group_kernel<1>), smem)) return 1;
-        polar_group_kernel<1><<<map.nchunks, kThreads, smem, st>>>(images, nx, tab, samp, twid, items, plan, map, normalize_ring,
-                                                                  reinterpret_cast<unsigned char*>(spec), frag, norm);
-    }
+#define CRA_GRP_LAUNCH(NH_, WIN_)                                                                                         \
+    { if (cra_ensure_dyn_smem(reinterpret_cast<const void*>(&polar_group_kernel<NH_, WIN_>), smem)) return 1;             \
+      polar_group_kernel<NH_, WIN_><<<map.nchunks, kThreads, smem, st>>>(images, nx, tab, samp, twid, items, plan, map,     \
+                                                                        normalize_ring, reinterpret_cast<unsigned char*>(spec), frag, norm); }
+    if (plan.nh == 2) { if (plan.tile) CRA_GRP_LAUNCH(2, true) else CRA_GRP_LAUNCH(2, false) }
+    else              { if (plan.tile) CRA_GRP_LAUNCH(1, true) else CRA_GRP_LAUNCH(1, false) }
+#undef CRA_GRP_LAUNCH
     CRA_CUDA(cudaGetLastError());
     return 0;
 }
