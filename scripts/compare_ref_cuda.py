@@ -1,0 +1,118 @@
+"""Drop-in check at the behaviour level: ONE ctypes harness, written the way the reference's driver drives its library
+(test_mref_gpu_align.py:365-449: AlignConfig -> pre_align_init -> pre_align_fetch x2 -> reset_shifts -> mref_align_run ->
+read AlignParam[]), run once with the reference's own CUDA library (baseline/_ref/gpu_aln_pack.so, built for sm_100 by
+baseline/build_ref_cuda.sh) and once with this repository's libcryo_ralib.so -- a one-line change of the CDLL path
+ -- on the same synthetic stack with known poses.
+
+It is NOT a parity test: the reference library is gpu_isac's arithmetic (256 bilinear samples per ring, ring weight r, no
+Normalize_ring, integer shifts) while this engine follows EMAN2's.  What it shows is that both
+libraries answer the same question through the same ABI with the same conventions: class (reference) chosen, mirror flag,
+in-plane angle and the accumulated shift of AlignParam, each against the ground truth and against each other.
+
+usage (GPU box): python scripts/compare_ref_cuda.py [P] [views] [snr]
+Each library runs in its own child process (same symbol names; the reference answers CUDA errors with exit(1))."""
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF_SO = os.path.join(ROOT, "baseline", "_ref", "gpu_aln_pack.so")
+OUR_SO = os.path.join(ROOT, "cryo_ralib_b200", "libcryo_ralib.so")
+NX, OU, XR = 90, 36, 3
+
+
+class AlignConfig(C.Structure):                      # test_mref_gpu_align.py:112-123
+    _fields_ = [("sbj_num", C.c_uint), ("ref_num", C.c_uint), ("img_dim", C.c_uint), ("ring_num", C.c_uint),
+                ("ring_len", C.c_uint), ("shift_step", C.c_float), ("shift_rng_x", C.c_float), ("shift_rng_y", C.c_float)]
+
+
+class AlignParam(C.Structure):                       # test_mref_gpu_align.py:125-131
+    _fields_ = [("sbj_id", C.c_int), ("ref_id", C.c_int), ("shift_x", C.c_float), ("shift_y", C.c_float),
+                ("angle", C.c_float), ("mirror", C.c_bool)]
+
+
+def worker(so, data, out):
+    d = np.load(data)
+    images, refs = np.ascontiguousarray(d["images"], np.float32), np.ascontiguousarray(d["refs"], np.float32)
+    P, R = images.shape[0], refs.shape[0]
+    L = C.CDLL(so)
+    L.pre_align_init.restype = C.c_ulonglong
+    L.mref_align_run.restype = C.c_ulonglong
+    fp = C.POINTER(C.c_float)
+    ptrs = lambda a: (fp * a.shape[0])(*[a[i].ctypes.data_as(fp) for i in range(a.shape[0])])
+    cfg = AlignConfig(P, R, NX, OU, 256, 1.0, float(XR), float(XR))
+    par = C.cast(C.c_void_p(L.pre_align_init(C.c_uint(P), C.byref(cfg), C.c_uint(0))), C.POINTER(AlignParam))
+    L.pre_align_fetch(ptrs(images), C.c_uint(P), C.c_char_p(b"sbj_batch"))
+    L.pre_align_fetch(ptrs(refs), C.c_int(R), C.c_char_p(b"ref_batch"))
+    L.reset_shifts(C.c_float(XR), C.c_float(1.0))
+    L.mref_align_run(C.c_int(0), C.c_int(P))
+    rt = C.CDLL("/usr/local/cuda/lib64/libcudart.so")
+    rt.cudaDeviceSynchronize()
+    res = np.array([(par[i].ref_id, par[i].shift_x, par[i].shift_y, par[i].angle, int(par[i].mirror)) for i in range(P)], np.float64)
+    np.save(out, res)
+    sys.stdout.flush()
+    os._exit(0)
+
+
+def circ(a, b):
+    return np.abs((a - b + 180.0) % 360.0 - 180.0)
+
+
+def main():
+    from cryo_ralib_b200 import synth
+    P = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+    V = int(sys.argv[2]) if len(sys.argv) > 2 else 12
+    snr = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
+    tmp = os.path.join(ROOT, "gpurun_out", "cmp")
+    os.makedirs(tmp, exist_ok=True)
+    images, truth = synth.make_particles(P, NX, V, max_shift=XR, snr=snr, seed=31)
+    # references: the noise-free views at psi = 0, no shift, no mirror (what a converged class average looks like)
+    pos, sigma, amp = synth.make_density(NX)
+    rots = synth.random_rotations(V, np.random.default_rng(31))
+    proj = np.einsum("vij,bj->vbi", rots, pos)[:, :, :2]
+    refs = synth.render(NX, proj[:, :, 0], proj[:, :, 1], sigma, amp).astype(np.float32)
+    # what the driver does on the host before it fetches (test_mref_gpu_align.py: normalize.mask with model_circle(ou)):
+    # particles x - mean_mask, references (x - mean_mask) / sigma_mask
+    yy, xx = np.mgrid[0:NX, 0:NX]
+    mask = ((xx - NX // 2) ** 2 + (yy - NX // 2) ** 2) <= OU * OU
+    images = (images - images[:, mask].mean(axis=1)[:, None, None]).astype(np.float32)
+    refs = ((refs - refs[:, mask].mean(axis=1)[:, None, None]) / refs[:, mask].std(axis=1, ddof=1)[:, None, None]).astype(np.float32)
+    np.savez(os.path.join(tmp, "data.npz"), images=images, refs=refs)
+    res = {}
+    for tag, so in (("reference", REF_SO), ("this", OUR_SO)):
+        if not os.path.exists(so):
+            print("%s library missing: %s" % (tag, so)); return 1
+        out = os.path.join(tmp, tag + ".npy")
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--worker", so, os.path.join(tmp, "data.npz"), out],
+                           capture_output=True, text=True, timeout=600)
+        if r.returncode != 0 or not os.path.exists(out):
+            print("%s library failed (rc %d): %s" % (tag, r.returncode, (r.stdout + r.stderr)[-400:])); return 1
+        res[tag] = np.load(out)
+    a, b = res["reference"], res["this"]
+    rep = dict(particles=P, views=V, snr=snr, nx=NX, ou=OU, xr=XR)
+    for tag, x in (("reference", a), ("this", b)):
+        rep[tag] = dict(view_recovered=float((x[:, 0] == truth["view"]).mean()), mirror_recovered=float((x[:, 4] == truth["mirror"]).mean()))
+    same_cls = a[:, 0] == b[:, 0]
+    both = same_cls & (a[:, 4] == b[:, 4])
+    da = circ(a[both, 3], b[both, 3])
+    ds = np.hypot(a[both, 1] - b[both, 1], a[both, 2] - b[both, 2])
+    rep["between"] = dict(same_class=float(same_cls.mean()), same_class_and_mirror=float(both.mean()),
+                          angle_diff_deg=dict(median=float(np.median(da)), p90=float(np.percentile(da, 90)), p99=float(np.percentile(da, 99))),
+                          shift_diff_px=dict(median=float(np.median(ds)), p90=float(np.percentile(ds, 90)), within_1px=float((ds <= 1.0).mean())))
+    print(json.dumps(rep, indent=1))
+    json.dump(rep, open(os.path.join(ROOT, "gpurun_out", "compare_ref_cuda_P%d_V%d_snr%g.json" % (P, V, snr)), "w"), indent=1)
+    for f in ("data.npz", "reference.npy", "this.npy"):       # scratch (the stack is 130 MB at 4096 particles)
+        os.remove(os.path.join(tmp, f))
+    return 0
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "--worker":
+        worker(sys.argv[2], sys.argv[3], sys.argv[4])
+    else:
+        sys.exit(main())
