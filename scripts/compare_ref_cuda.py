@@ -9,7 +9,10 @@ Normalize_ring, integer shifts) while this engine follows 
 libraries answer the same question through the same ABI with the same conventions: class (reference) chosen, mirror flag,
 in-plane angle and the accumulated shift of AlignParam, each against the ground truth and against each other.
 
-usage (GPU box): python scripts/compare_ref_cuda.py [P] [views] [snr]
+usage (GPU box): python scripts/compare_ref_cuda.py [P] [views] [snr] [mref|reffree]
+reffree: the reference-free entry point pre_align_run(0, P) instead (test_reffree.py:292-426), with ONE reference.  The
+first average of a real reference-free run is a featureless blob (flat correlation landscape: the two arithmetics then
+disagree on ties), so the check uses a stack of one view and its noise-free projection as the reference.
 Each library runs in its own child process (same symbol names; the reference answers CUDA errors with exit(1))."""
 import ctypes as C
 import json
@@ -36,7 +39,7 @@ class AlignParam(C.Structure):                       # test_mref_gpu_align.py:12
                 ("angle", C.c_float), ("mirror", C.c_bool)]
 
 
-def worker(so, data, out):
+def worker(so, data, out, mode="mref"):
     d = np.load(data)
     images, refs = np.ascontiguousarray(d["images"], np.float32), np.ascontiguousarray(d["refs"], np.float32)
     P, R = images.shape[0], refs.shape[0]
@@ -50,7 +53,10 @@ def worker(so, data, out):
     L.pre_align_fetch(ptrs(images), C.c_uint(P), C.c_char_p(b"sbj_batch"))
     L.pre_align_fetch(ptrs(refs), C.c_int(R), C.c_char_p(b"ref_batch"))
     L.reset_shifts(C.c_float(XR), C.c_float(1.0))
-    L.mref_align_run(C.c_int(0), C.c_int(P))
+    if mode == "reffree":
+        L.pre_align_run(C.c_int(0), C.c_int(P))
+    else:
+        L.mref_align_run(C.c_int(0), C.c_int(P))
     rt = C.CDLL("/usr/local/cuda/lib64/libcudart.so")
     rt.cudaDeviceSynchronize()
     res = np.array([(par[i].ref_id, par[i].shift_x, par[i].shift_y, par[i].angle, int(par[i].mirror)) for i in range(P)], np.float64)
@@ -68,6 +74,9 @@ def main():
     P = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
     V = int(sys.argv[2]) if len(sys.argv) > 2 else 12
     snr = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
+    mode = sys.argv[4] if len(sys.argv) > 4 else "mref"
+    if mode == "reffree":
+        V = 1
     tmp = os.path.join(ROOT, "gpurun_out", "cmp")
     os.makedirs(tmp, exist_ok=True)
     images, truth = synth.make_particles(P, NX, V, max_shift=XR, snr=snr, seed=31)
@@ -82,19 +91,21 @@ def main():
     mask = ((xx - NX // 2) ** 2 + (yy - NX // 2) ** 2) <= OU * OU
     images = (images - images[:, mask].mean(axis=1)[:, None, None]).astype(np.float32)
     refs = ((refs - refs[:, mask].mean(axis=1)[:, None, None]) / refs[:, mask].std(axis=1, ddof=1)[:, None, None]).astype(np.float32)
+    if mode == "reffree":
+        refs = refs[:1]                                                   # one reference (run with views = 1)
     np.savez(os.path.join(tmp, "data.npz"), images=images, refs=refs)
     res = {}
     for tag, so in (("reference", REF_SO), ("this", OUR_SO)):
         if not os.path.exists(so):
             print("%s library missing: %s" % (tag, so)); return 1
         out = os.path.join(tmp, tag + ".npy")
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--worker", so, os.path.join(tmp, "data.npz"), out],
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--worker", so, os.path.join(tmp, "data.npz"), out, mode],
                            capture_output=True, text=True, timeout=600)
         if r.returncode != 0 or not os.path.exists(out):
             print("%s library failed (rc %d): %s" % (tag, r.returncode, (r.stdout + r.stderr)[-400:])); return 1
         res[tag] = np.load(out)
     a, b = res["reference"], res["this"]
-    rep = dict(particles=P, views=V, snr=snr, nx=NX, ou=OU, xr=XR)
+    rep = dict(mode=mode, particles=P, views=V, snr=snr, nx=NX, ou=OU, xr=XR)
     for tag, x in (("reference", a), ("this", b)):
         rep[tag] = dict(view_recovered=float((x[:, 0] == truth["view"]).mean()), mirror_recovered=float((x[:, 4] == truth["mirror"]).mean()))
     same_cls = a[:, 0] == b[:, 0]
@@ -105,7 +116,7 @@ def main():
                           angle_diff_deg=dict(median=float(np.median(da)), p90=float(np.percentile(da, 90)), p99=float(np.percentile(da, 99))),
                           shift_diff_px=dict(median=float(np.median(ds)), p90=float(np.percentile(ds, 90)), within_1px=float((ds <= 1.0).mean())))
     print(json.dumps(rep, indent=1))
-    json.dump(rep, open(os.path.join(ROOT, "gpurun_out", "compare_ref_cuda_P%d_V%d_snr%g.json" % (P, V, snr)), "w"), indent=1)
+    json.dump(rep, open(os.path.join(ROOT, "gpurun_out", "compare_ref_cuda_%s_P%d_V%d_snr%g.json" % (mode, P, V, snr)), "w"), indent=1)
     for f in ("data.npz", "reference.npy", "this.npy"):       # scratch (the stack is 130 MB at 4096 particles)
         os.remove(os.path.join(tmp, f))
     return 0
@@ -113,6 +124,6 @@ def main():
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--worker":
-        worker(sys.argv[2], sys.argv[3], sys.argv[4])
+        worker(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5] if len(sys.argv) > 5 else "mref")
     else:
         sys.exit(main())
