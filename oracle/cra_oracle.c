@@ -17,9 +17,16 @@
  * (cuda/EMAN2_test.ipynb cells 23-25).
  *
  * PARITY STATUS: the Transform algebra is pinned by the reference's three golden
- * tuples; everything at the multiref_polar_ali_2d boundary is "parity unpinned"
- * (the reference holds no vectors for it and EMAN2 cannot be run here) and is
- * carried by the self-consistency tests in tests/test_oracle_*.py.
+ * tuples.  At the multiref_polar_ali_2d boundary the reference holds no EMAN2
+ * vectors and EMAN2 cannot be run here: the DIGITS of this restatement are
+ * "parity unpinned" and carried by the self-consistency tests of
+ * tests/test_oracle.py.  Its CONVENTIONS and discrete answers (class, mirror flag,
+ * integer shift, angle direction and origin) are pinned to output of the
+ * reference itself: AlignParam[] as the reference's own CUDA library, compiled
+ * unchanged for sm_100, left it for a deterministic stack
+ * (tests/golden/refcuda_mref_outputs.npz, tests/golden/make_refcuda_case.py):
+ * 512 / 512 particles identical, angles within 0.12 degrees.  That library is
+ * gpu_isac's arithmetic, not EMAN2's, so this is not a last-digit pin.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load this library.  The product (cryo_ralib_b200)

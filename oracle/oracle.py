@@ -5,8 +5,13 @@ EMAN2 pieces of the reference's per-iteration reference update
 (test_mref.py:238-296; test_reffree.py:695-755).  The arithmetic follows EMAN2
 2.31 / Sphire (un-vendored dependency, README.md:43) as specified in SURVEY.md
 Appendix A.  Parity status: Transform algebra pinned by the reference's golden
-tuples (cuda/EMAN2_test.ipynb cells 23-25); everything else "parity unpinned"
-(no reference vectors exist, EMAN2 cannot run here).
+tuples (cuda/EMAN2_test.ipynb cells 23-25); the conventions and discrete answers
+of the alignment (class, mirror, integer shift, angle) pinned to AlignParam[] as
+the reference's own CUDA library left it for a deterministic stack
+(tests/golden/refcuda_mref_outputs.npz: 512 / 512 identical, angles within
+0.12 degrees); the digits at the multiref_polar_ali_2d boundary remain "parity
+unpinned" (no EMAN2 vectors exist, EMAN2 cannot run here, and the reference's
+CUDA is gpu_isac's arithmetic).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 ``--impl reference`` legs may import this module.

@@ -69,16 +69,9 @@ def circ(a, b):
     return np.abs((a - b + 180.0) % 360.0 - 180.0)
 
 
-def main():
+def make_inputs(P, V, snr):
+    """-> (images, refs, truth): the stack and the references exactly as they are handed to pre_align_fetch."""
     from cryo_ralib_b200 import synth
-    P = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
-    V = int(sys.argv[2]) if len(sys.argv) > 2 else 12
-    snr = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
-    mode = sys.argv[4] if len(sys.argv) > 4 else "mref"
-    if mode == "reffree":
-        V = 1
-    tmp = os.path.join(ROOT, "gpurun_out", "cmp")
-    os.makedirs(tmp, exist_ok=True)
     images, truth = synth.make_particles(P, NX, V, max_shift=XR, snr=snr, seed=31)
     # references: the noise-free views at psi = 0, no shift, no mirror (what a converged class average looks like)
     pos, sigma, amp = synth.make_density(NX)
@@ -91,6 +84,19 @@ def main():
     mask = ((xx - NX // 2) ** 2 + (yy - NX // 2) ** 2) <= OU * OU
     images = (images - images[:, mask].mean(axis=1)[:, None, None]).astype(np.float32)
     refs = ((refs - refs[:, mask].mean(axis=1)[:, None, None]) / refs[:, mask].std(axis=1, ddof=1)[:, None, None]).astype(np.float32)
+    return images, refs, truth
+
+
+def main():
+    P = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+    V = int(sys.argv[2]) if len(sys.argv) > 2 else 12
+    snr = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
+    mode = sys.argv[4] if len(sys.argv) > 4 else "mref"
+    if mode == "reffree":
+        V = 1
+    tmp = os.path.join(ROOT, "gpurun_out", "cmp")
+    os.makedirs(tmp, exist_ok=True)
+    images, refs, truth = make_inputs(P, V, snr)
     if mode == "reffree":
         refs = refs[:1]                                                   # one reference (run with views = 1)
     np.savez(os.path.join(tmp, "data.npz"), images=images, refs=refs)
@@ -117,6 +123,9 @@ def main():
                           shift_diff_px=dict(median=float(np.median(ds)), p90=float(np.percentile(ds, 90)), within_1px=float((ds <= 1.0).mean())))
     print(json.dumps(rep, indent=1))
     json.dump(rep, open(os.path.join(ROOT, "gpurun_out", "compare_ref_cuda_%s_P%d_V%d_snr%g.json" % (mode, P, V, snr)), "w"), indent=1)
+    # the reference library's own answers (ref_id, shift_x, shift_y, angle, mirror per particle): small, kept -- the golden
+    # fixture tests/golden/refcuda_mref_outputs.npz is one of these (tests/golden/make_refcuda_case.py)
+    np.save(os.path.join(ROOT, "gpurun_out", "refcuda_outputs_%s_P%d_V%d_snr%g.npy" % (mode, P, V, snr)), a)
     for f in ("data.npz", "reference.npy", "this.npy"):       # scratch (the stack is 130 MB at 4096 particles)
         os.remove(os.path.join(tmp, f))
     return 0
