@@ -233,18 +233,20 @@ def test_oracle_reproduces_golden_case(oracle):
     assert np.allclose(info["filter"], g["filter"])
 
 
-def test_oracle_against_vectors_produced_by_the_reference_cuda_library(oracle):
-    """tests/golden/refcuda_mref_outputs.npz: AlignParam[] as the reference's OWN CUDA library (compiled unchanged for
-    sm_100, stock entry points) left it for a deterministic stack (tests/golden/make_refcuda_case.py; the inputs are
-    regenerated from seeds).  The reference library's arithmetic is gpu_isac's, not EMAN2's, so the last digits differ; at
-    this noise level the discrete answers must not: class, mirror flag, integer shift identical, angle within half a ring
-    sample.  This pins the oracle's conventions (angle direction and origin, sign of the shift, mirror, visit order of the
-    references) to output of the reference itself."""
+@pytest.mark.parametrize("fixture,normalize", [("refcuda_mref_outputs.npz", True), ("refcuda_reffree_outputs.npz", False)])
+def test_oracle_against_vectors_produced_by_the_reference_cuda_library(oracle, fixture, normalize):
+    """tests/golden/refcuda_*_outputs.npz: AlignParam[] as the reference's OWN CUDA library (compiled unchanged for
+    sm_100, stock entry points) left it for a deterministic stack after mref_align_run (12 references) and after
+    pre_align_run (the reference-free entry point: one reference, ormq semantics without Normalize_ring) --
+    tests/golden/make_refcuda_case.py; the inputs are regenerated from seeds.  The reference library's arithmetic is
+    gpu_isac's, not EMAN2's, so the last digits differ; at this noise level the discrete answers must not: class, mirror
+    flag, integer shift identical, angle within half a ring sample.  This pins the oracle's conventions (angle direction
+    and origin, sign of the shift, mirror, visit order of the references) to output of the reference itself."""
     import os, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, os.path.join(root, "scripts"))
     import compare_ref_cuda as crc
-    g = np.load(os.path.join(root, "tests", "golden", "refcuda_mref_outputs.npz"))
+    g = np.load(os.path.join(root, "tests", "golden", fixture))
     P, V = int(g["particles"]), int(g["views"])
     assert (int(g["nx"]), int(g["ou"]), int(g["xr"])) == (crc.NX, crc.OU, crc.XR)
     images, refs, truth = crc.make_inputs(P, V, float(g["snr"]))
@@ -254,7 +256,7 @@ def test_oracle_against_vectors_produced_by_the_reference_cuda_library(oracle):
     cref = np.stack([oracle.applyws(oracle.frngs(oracle.polar2dm(r, float(cnx), float(cnx), numr), numr), numr, wr) for r in refs])
     centres = np.full((P, 2), float(cnx), np.float32)
     win = np.full((P, 4), float(crc.XR), np.float32)
-    want = oracle.align_batch(images, cref, numr, centres, win, 1.0, True, nthreads=oracle.max_threads())
+    want = oracle.align_batch(images, cref, numr, centres, win, 1.0, normalize, nthreads=oracle.max_threads())
     # AlignParam conventions (gpu_aln_noref.cu:1476-1479; cra_compat.cu): ref_id, mirror, angle as multiref_polar_ali_2d
     # returns them; shift_x / shift_y = the polar-centre offset of the winning grid position = -(sx, sy) of the search
     same = (want[:, 4].astype(int) == g["ref_id"]) & (want[:, 3].astype(int) == g["mirror"]) \
@@ -264,3 +266,4 @@ def test_oracle_against_vectors_produced_by_the_reference_cuda_library(oracle):
     assert np.percentile(dang, 99) <= 0.5 * 360.0 / int(numr[-1]), np.percentile(dang, 99)
     # and both found the truth
     assert (g["ref_id"] == truth["view"]).mean() >= 0.99 and (want[:, 4].astype(int) == truth["view"]).mean() >= 0.99
+    assert (g["mirror"] == truth["mirror"]).mean() >= 0.99 and (want[:, 3].astype(int) == truth["mirror"]).mean() >= 0.99
