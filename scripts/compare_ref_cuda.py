@@ -9,7 +9,9 @@ Normalize_ring, integer shifts) while this engine follows 
 libraries answer the same question through the same ABI with the same conventions: class (reference) chosen, mirror flag,
 in-plane angle and the accumulated shift of AlignParam, each against the ground truth and against each other.
 
-usage (GPU box): python scripts/compare_ref_cuda.py [P] [views] [snr] [mref|reffree]
+usage (GPU box): python scripts/compare_ref_cuda.py [P] [views] [snr] [mref|mref_m|reffree]
+mref_m: mref_align_run_m instead (test_mref_cheng_yu_bdb_cuda.py:546-556): additionally the [2R][nx][nx] even / odd class
+sums and get_num_ref of the two libraries (class sizes; correlation of the sums and of even - odd per class).
 reffree: the reference-free entry point pre_align_run(0, P) instead (test_reffree.py:292-426), with ONE reference.  The
 first average of a real reference-free run is a featureless blob (flat correlation landscape: the two arithmetics then
 disagree on ties), so the check uses a stack of one view and its noise-free projection as the reference.
@@ -53,11 +55,20 @@ def worker(so, data, out, mode="mref"):
     L.pre_align_fetch(ptrs(images), C.c_uint(P), C.c_char_p(b"sbj_batch"))
     L.pre_align_fetch(ptrs(refs), C.c_int(R), C.c_char_p(b"ref_batch"))
     L.reset_shifts(C.c_float(XR), C.c_float(1.0))
+    rt = C.CDLL("/usr/local/cuda/lib64/libcudart.so")
     if mode == "reffree":
         L.pre_align_run(C.c_int(0), C.c_int(P))
+    elif mode == "mref_m":
+        # test_mref_cheng_yu_bdb_cuda.py:546-556: managed [2R][nx][nx] -- R even sums, then R odd sums -- and the class sizes
+        L.mref_align_run_m.restype = C.POINTER(C.c_float)
+        L.get_num_ref.restype = C.POINTER(C.c_int)
+        sp = L.mref_align_run_m(C.c_int(0), C.c_int(P))
+        rt.cudaDeviceSynchronize()
+        sums = np.ctypeslib.as_array(sp, shape=(2 * R, NX, NX)).copy()
+        np.save(out.replace(".npy", "_sums.npy"), sums)
+        np.save(out.replace(".npy", "_counts.npy"), np.ctypeslib.as_array(L.get_num_ref(), shape=(R,)).copy())
     else:
         L.mref_align_run(C.c_int(0), C.c_int(P))
-    rt = C.CDLL("/usr/local/cuda/lib64/libcudart.so")
     rt.cudaDeviceSynchronize()
     res = np.array([(par[i].ref_id, par[i].shift_x, par[i].shift_y, par[i].angle, int(par[i].mirror)) for i in range(P)], np.float64)
     np.save(out, res)
@@ -121,6 +132,20 @@ def main():
     rep["between"] = dict(same_class=float(same_cls.mean()), same_class_and_mirror=float(both.mean()),
                           angle_diff_deg=dict(median=float(np.median(da)), p90=float(np.percentile(da, 90)), p99=float(np.percentile(da, 99))),
                           shift_diff_px=dict(median=float(np.median(ds)), p90=float(np.percentile(ds, 90)), within_1px=float((ds <= 1.0).mean())))
+    if mode == "mref_m":
+        ncc = lambda x, y: float((x * y).sum() / np.sqrt((x * x).sum() * (y * y).sum()))
+        sa, sb = np.load(os.path.join(tmp, "reference_sums.npy")), np.load(os.path.join(tmp, "this_sums.npy"))
+        ca, cb = np.load(os.path.join(tmp, "reference_counts.npy")), np.load(os.path.join(tmp, "this_counts.npy"))
+        R = sa.shape[0] // 2
+        same_par = [ncc(sa[i], sb[i]) for i in range(2 * R)]
+        # even - odd cancels the signal of a class: what is left is the noise of its members, which correlates between the
+        # libraries only if both put the same particles into the same half
+        dif = [ncc(sa[i] - sa[R + i], sb[i] - sb[R + i]) for i in range(R)]
+        rep["sums"] = dict(class_sizes_equal=bool(np.array_equal(ca, cb)), class_sizes=ca.tolist(),
+                           ncc_same_half=dict(min=min(same_par), median=float(np.median(same_par))),
+                           ncc_even_minus_odd=dict(min=min(dif), median=float(np.median(dif))))
+        for f in ("reference_sums.npy", "this_sums.npy", "reference_counts.npy", "this_counts.npy"):
+            os.remove(os.path.join(tmp, f))
     print(json.dumps(rep, indent=1))
     json.dump(rep, open(os.path.join(ROOT, "gpurun_out", "compare_ref_cuda_%s_P%d_V%d_snr%g.json" % (mode, P, V, snr)), "w"), indent=1)
     # the reference library's own answers (ref_id, shift_x, shift_y, angle, mirror per particle): small, kept -- the golden
