@@ -85,6 +85,12 @@ struct CraCtx {
     float2* d_dft = nullptr; size_t dft_elems = 0;             // reference-update scratch (large boxes only)
     int rpb = 2, gimg_rows = 0, gimg_one = 0;   // general row kernel: rows per CTA; image taps from global memory (large boxes)
     int last_rows = 0, last_group = 0;   // rows / kernel of the last batch (cra_batch_row_spectrum)
+    // second pipeline lane (align_impl): odd row batches run on their own stream with their own spectrum / candidate
+    // buffers, so that the tail of one batch's kernels is filled by the other batch's CTAs
+    cudaStream_t st2 = nullptr;
+    float* d_spec2 = nullptr; CraCand* d_cand2 = nullptr; float2* d_norm2 = nullptr;
+    cudaEvent_t ev_lane[2] = {nullptr, nullptr};
+    const float* last_spec = nullptr; const float2* last_norm = nullptr;     // buffers of the last batch
     float2* d_norm = nullptr;    // [row_batch] deferred Normalize_ring (avg, 1/sigma), cra_common.cuh
     float* d_tref = nullptr;     // [max_refs]  sum_rings len * weighted reference DC
     // device reference update (cra_refupdate.cu), allocated on first use
@@ -567,6 +573,7 @@ extern "C" int cra_destroy(CraCtx* c)
     if (!c) return 0;
     cudaSetDevice(c->device);
     if (c->st_copy) cudaStreamSynchronize(c->st_copy);
+    if (c->st2) cudaStreamSynchronize(c->st2);
     if (c->st) cudaStreamSynchronize(c->st);
     for (auto& e : c->ev) cudaEventDestroy(e);
     for (auto& p : c->pending) cudaEventDestroy(p.ev);
@@ -577,6 +584,9 @@ extern "C" int cra_destroy(CraCtx* c)
     cudaFree(c->d_tab); cudaFree(c->d_samp); cudaFree(c->d_sampw); cudaFree(c->d_twf); cudaFree(c->d_twi); cudaFree(c->d_twd);
     cudaFree(c->d_mask); cudaFree(c->d_dc); cudaFree(c->d_images); cudaFree(c->d_refs); cudaFree(c->d_refspec);
     cudaFree(c->d_spec); cudaFree(c->d_cand); cudaFree(c->d_sums); cudaFree(c->d_meta); cudaFree(c->d_res);
+    cudaFree(c->d_spec2); cudaFree(c->d_cand2); cudaFree(c->d_norm2);
+    for (auto& e : c->ev_lane) if (e) cudaEventDestroy(e);
+    if (c->st2) cudaStreamDestroy(c->st2);
     cudaFree(c->d_par); cudaFree(c->d_iref); cudaFree(c->d_tmpimg); cudaFree(c->d_curves);
     cudaFree(c->d_shell); cudaFree(c->d_fsc); cudaFree(c->d_cs); cudaFree(c->d_dft);
     if (c->h_meta) cudaFreeHost(c->h_meta);
@@ -811,6 +821,28 @@ extern "C" int cra_prepare_refs(CraCtx* c, int normalize_mask)
 // ref_free_alignment_2D, cuda/gpu_aln_noref.cu:743-782): the row kernel runs per batch as usual,
 // the CCF and finalize kernels run once per run of consecutive particles of one class, on that
 // run's rows and with the reference operands based at that class.
+// The second pipeline lane, built on first use (2 GB of spectra at the default row batch)
+static int ensure_lane2(CraCtx* c)
+{
+    if (c->st2) return 0;
+    const size_t row_groups = ((size_t)c->row_batch + 3) / 4;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_spec2, row_groups * 4 * c->row_bytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->d_spec2, 0, row_groups * 4 * c->row_bytes, c->st2);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_cand2, (size_t)c->row_batch * c->ntile_n_max * sizeof(CraCand));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_norm2, ((size_t)c->row_batch + 4) * sizeof(float2));
+    for (auto& ev : c->ev_lane) if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->st2);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(c->d_spec2); cudaFree(c->d_cand2); cudaFree(c->d_norm2); c->d_spec2 = nullptr; c->d_cand2 = nullptr; c->d_norm2 = nullptr;
+        for (auto& ev : c->ev_lane) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
+        if (c->st2) { cudaStreamDestroy(c->st2); c->st2 = nullptr; }
+        return 1;                                   // not an error of the call: the single-lane path serves it
+    }
+    return 0;
+}
+
 static int align_impl(CraCtx* c, int start, int stop, const CraSearch* search, const int* class_of, CraResult* out)
 {
     CraNvtx range(class_of ? "cra_align_bound" : "cra_align");
@@ -916,24 +948,39 @@ static int align_impl(CraCtx* c, int start, int stop, const CraSearch* search, c
         while (c->ev.size() < 4 * nb) { cudaEvent_t e; CRA_CUDA(cudaEventCreate(&e)); c->ev.push_back(e); }
     }
     long launches = 0;
+    // Two pipeline lanes (CRA_LANES=2; measured, NOT the default): odd batches run on a second stream with their own
+    // spectrum / candidate / norm buffers, so that the CTAs of one batch's row kernel fill the SM slots the other batch's
+    // persistent CCF grid frees at its tail (and the reverse); kernels of one lane stay in order on their stream.
+    // Identical results, but 55.2 against 52.6 ms per 16 384 particles of configuration 2 (scripts/lane_probe.py): a row
+    // CTA and a CCF CTA sharing an SM run slower than two CTAs of one kernel, which costs more than the kernel tails
+    // (~3 % each) give back.  Never with per-kernel timing or the class-bound variant.
+    static const bool lanes_env = getenv("CRA_LANES") && atoi(getenv("CRA_LANES")) == 2;
+    const bool two_lanes = lanes_env && !tm && !class_of && nb >= 2 && c->fmt == CRA_FMT_FRAG && !c->use_um && ensure_lane2(c) == 0;
+    if (two_lanes) {                                 // lane 2 starts after everything queued on the main stream so far
+        CRA_CUDA(cudaEventRecord(c->ev_lane[0], c->st));
+        CRA_CUDA(cudaStreamWaitEvent(c->st2, c->ev_lane[0], 0));
+    }
     for (size_t bi = 0; bi < nb; ++bi) {
+        const bool lane2 = two_lanes && (bi & 1);
+        struct Lane { cudaStream_t st; float* spec; CraCand* cand; float2* norm; };
+        const Lane L = lane2 ? Lane{c->st2, c->d_spec2, c->d_cand2, c->d_norm2} : Lane{c->st, c->d_spec, c->d_cand, c->d_norm};
         CraRowMap map;
         map.row_start = d_rs + bfirst[bi] + bi;
         map.chunk_start = d_cs + bfirst[bi] + bi; map.nchunks = bchunks[bi];
         map.search = d_search + bfirst[bi];
         map.win = d_win + bfirst[bi];
         map.np = bcount[bi]; map.nrows = brows[bi]; map.p0 = start + bfirst[bi]; map.step = step; map.dc = c->d_dc;
-        if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 0], c->st));
+        if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 0], L.st));
         nvtxRangePushA("row kernel (Polar2Dm + Frngs)");
         if (bgroup[bi]) {
             if (cra_launch_polar_group(c->d_images, c->nx, c->d_tab, c->htab, c->d_samp, c->d_twf, c->items, c->plan, map,
-                                       c->cfg.normalize_ring, c->d_spec, c->frag, c->d_norm, c->st)) { nvtxRangePop(); return 1; }
+                                       c->cfg.normalize_ring, L.spec, c->frag, L.norm, L.st)) { nvtxRangePop(); return 1; }
         } else if (cra_launch_polar_rows(c->d_images, c->nx, c->d_tab, c->htab, c->d_samp, c->d_sampw, c->d_twf, c->items, map,
-                                         c->cfg.normalize_ring, c->d_spec, c->fmt, c->frag, c->d_norm, c->rpb, c->gimg_rows, c->st)) { nvtxRangePop(); return 1; }
+                                         c->cfg.normalize_ring, L.spec, c->fmt, c->frag, L.norm, c->rpb, c->gimg_rows, L.st)) { nvtxRangePop(); return 1; }
         nvtxRangePop();
-        if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 1], c->st));
+        if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 1], L.st));
         if (class_of) {
-            const unsigned char* specb = reinterpret_cast<const unsigned char*>(c->d_spec);
+            const unsigned char* specb = reinterpret_cast<const unsigned char*>(L.spec);
             const unsigned char* refb = reinterpret_cast<const unsigned char*>(c->d_refspec);
             const int* rs = h_rs + bfirst[bi] + bi;                 // batch-local first row of each particle
             for (int a = 0; a < bcount[bi];) {
@@ -945,42 +992,47 @@ static int align_impl(CraCtx* c, int start, int stop, const CraSearch* search, c
                 if (nr > 0) {
                     if (c->use_tm) {
                         if (cra_launch_ccf_tm(specb + (size_t)r0 * c->row_bytes, nr, ref1, 1, c->htab, c->frag, c->h_koff, c->d_twi,
-                                              c->d_cand + r0, 1, c->d_norm + r0, c->d_tref + cls, &c->tm_sched, c->st)) return 1;
+                                              L.cand + r0, 1, L.norm + r0, c->d_tref + cls, &c->tm_sched, L.st)) return 1;
                     } else if (cra_launch_ccf_mma(specb + (size_t)r0 * c->row_bytes, nr, ref1, 1, c->htab, c->frag, c->h_koff, c->d_twi,
-                                                  c->d_cand + r0, 1, c->d_norm + r0, c->d_tref + cls, c->st)) return 1;
+                                                  L.cand + r0, 1, L.norm + r0, c->d_tref + cls, L.st)) return 1;
                 }
                 CraRowMap sub = map;
                 sub.row_start += a; sub.search += a; sub.win += a; sub.np = e - a; sub.p0 += a;
-                if (cra_launch_finalize(c->d_spec, reinterpret_cast<const float*>(ref1), 1, c->d_tab, c->htab, c->d_cand, 1, sub,
-                                        c->d_res + bfirst[bi] + a, c->fmt, c->frag, c->d_twd, c->d_norm, c->d_tref + cls, c->st)) return 1;
+                if (cra_launch_finalize(L.spec, reinterpret_cast<const float*>(ref1), 1, c->d_tab, c->htab, L.cand, 1, sub,
+                                        c->d_res + bfirst[bi] + a, c->fmt, c->frag, c->d_twd, L.norm, c->d_tref + cls, L.st)) return 1;
                 launches += 2;
                 a = e;
             }
-            if (tm) { CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 2], c->st)); CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 3], c->st)); }
+            if (tm) { CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 2], L.st)); CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 3], L.st)); }
             launches += 1;
-            c->last_rows = map.nrows; c->last_group = bgroup[bi];
+            c->last_rows = map.nrows; c->last_group = bgroup[bi]; c->last_spec = L.spec; c->last_norm = L.norm;
             continue;
         }
         CraNvtx ccf_range("CCF (Crosrng_ms + inverse FFT + peak) + finalize");
         if (c->fmt == CRA_FMT_FRAG && c->use_um) {
-            if (cra_launch_ccf_um(reinterpret_cast<const unsigned char*>(c->d_spec), map.nrows, c->d_refimg, c->R, c->htab, c->frag,
-                                  c->h_koff, c->d_twi, c->d_cand, ntile_n, c->d_norm, c->d_tref, c->st)) return 1;
+            if (cra_launch_ccf_um(reinterpret_cast<const unsigned char*>(L.spec), map.nrows, c->d_refimg, c->R, c->htab, c->frag,
+                                  c->h_koff, c->d_twi, L.cand, ntile_n, L.norm, c->d_tref, L.st)) return 1;
         } else if (c->fmt == CRA_FMT_FRAG && c->use_tm) {
-            if (cra_launch_ccf_tm(reinterpret_cast<const unsigned char*>(c->d_spec), map.nrows,
+            if (cra_launch_ccf_tm(reinterpret_cast<const unsigned char*>(L.spec), map.nrows,
                                   reinterpret_cast<const unsigned char*>(c->d_refspec), c->R, c->htab, c->frag, c->h_koff,
-                                  c->d_twi, c->d_cand, ntile_n, c->d_norm, c->d_tref, &c->tm_sched, c->st)) return 1;
+                                  c->d_twi, L.cand, ntile_n, L.norm, c->d_tref, &c->tm_sched, L.st)) return 1;
         } else if (c->fmt == CRA_FMT_FRAG) {
-            if (cra_launch_ccf_mma(reinterpret_cast<const unsigned char*>(c->d_spec), map.nrows,
+            if (cra_launch_ccf_mma(reinterpret_cast<const unsigned char*>(L.spec), map.nrows,
                                    reinterpret_cast<const unsigned char*>(c->d_refspec), c->R, c->htab, c->frag, c->h_koff,
-                                   c->d_twi, c->d_cand, ntile_n, c->d_norm, c->d_tref, c->st)) return 1;
-        } else if (cra_launch_ccf(c->d_spec, map.nrows, c->d_refspec, c->R, c->d_tab, c->htab, c->d_twi, c->d_cand, ntile_n, c->st)) return 1;
-        if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 2], c->st));
-        if (cra_launch_finalize(c->d_spec, c->d_refspec, c->R, c->d_tab, c->htab, c->d_cand, ntile_n, map,
-                                c->d_res + bfirst[bi], c->fmt, c->frag, c->d_twd, c->d_norm, c->d_tref, c->st)) return 1;
-        if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 3], c->st));
+                                   c->d_twi, L.cand, ntile_n, L.norm, c->d_tref, L.st)) return 1;
+        } else if (cra_launch_ccf(L.spec, map.nrows, c->d_refspec, c->R, c->d_tab, c->htab, c->d_twi, L.cand, ntile_n, L.st)) return 1;
+        if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 2], L.st));
+        if (cra_launch_finalize(L.spec, c->d_refspec, c->R, c->d_tab, c->htab, L.cand, ntile_n, map,
+                                c->d_res + bfirst[bi], c->fmt, c->frag, c->d_twd, L.norm, c->d_tref, L.st)) return 1;
+        if (tm) CRA_CUDA(cudaEventRecord(c->ev[4 * bi + 3], L.st));
         launches += 3;
-        c->last_rows = map.nrows; c->last_group = bgroup[bi];
+        c->last_rows = map.nrows; c->last_group = bgroup[bi]; c->last_spec = L.spec; c->last_norm = L.norm;
     }
+    if (two_lanes) {                                 // the main stream continues after lane 2 has drained
+        CRA_CUDA(cudaEventRecord(c->ev_lane[1], c->st2));
+        CRA_CUDA(cudaStreamWaitEvent(c->st, c->ev_lane[1], 0));
+    }
+
     CRA_CUDA(cudaMemcpyAsync(c->h_res, c->d_res, (size_t)n * sizeof(CraResult), cudaMemcpyDeviceToHost, c->st));
     CRA_CUDA(cudaStreamSynchronize(c->st));
     memcpy(out, c->h_res, (size_t)n * sizeof(CraResult));
@@ -1210,9 +1262,9 @@ extern "C" int cra_batch_row_spectrum(CraCtx* c, int row, float* host_out, int* 
     if (c->fmt != CRA_FMT_FRAG) { cra_set_error("cra_batch_row_spectrum needs the fragment format"); return 1; }
     if (row < 0 || row >= c->last_rows) { cra_set_error("row outside the last batch"); return 1; }
     float2 nm;
-    CRA_CUDA(cudaMemcpyAsync(c->h_group, reinterpret_cast<const unsigned char*>(c->d_spec) + (size_t)row * c->row_bytes,
+    CRA_CUDA(cudaMemcpyAsync(c->h_group, reinterpret_cast<const unsigned char*>(c->last_spec ? c->last_spec : c->d_spec) + (size_t)row * c->row_bytes,
                              c->row_bytes, cudaMemcpyDeviceToHost, c->st));
-    CRA_CUDA(cudaMemcpyAsync(&nm, c->d_norm + row, sizeof(float2), cudaMemcpyDeviceToHost, c->st));
+    CRA_CUDA(cudaMemcpyAsync(&nm, (c->last_norm ? c->last_norm : c->d_norm) + row, sizeof(float2), cudaMemcpyDeviceToHost, c->st));
     CRA_CUDA(cudaStreamSynchronize(c->st));
     unpack_spectrum(c, 0, host_out, true);
     // deferred Normalize_ring: DC bin of every ring -= avg * len, everything * 1/sigma
