@@ -1,7 +1,7 @@
 """Drop-in check at the behaviour level: ONE ctypes harness, written the way the reference's driver drives its library
 (test_mref_gpu_align.py:365-449: AlignConfig -> pre_align_init -> pre_align_fetch x2 -> reset_shifts -> mref_align_run ->
-read AlignParam[]), run once with the reference's own CUDA library (baseline/_ref/gpu_aln_pack.so, built for sm_100 by
-baseline/build_ref_cuda.sh) and once with this repository's libcryo_ralib.so -- a one-line change of the CDLL path
+read AlignParam[]), run once with the reference's own CUDA library (oracle/_ref/gpu_aln_pack.so, built unchanged for sm_100 by
+`make -C oracle ref`) and once with this repository's libcryo_ralib.so -- a one-line change of the CDLL path
  -- on the same synthetic stack with known poses.
 
 It is NOT a parity test: the reference library is gpu_isac's arithmetic (256 bilinear samples per ring, ring weight r, no
@@ -26,7 +26,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-REF_SO = os.path.join(ROOT, "baseline", "_ref", "gpu_aln_pack.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "gpu_aln_pack.so")                 # make -C oracle ref
+if not os.path.exists(REF_SO):
+    REF_SO = os.path.join(ROOT, "baseline", "_ref", "gpu_aln_pack.so")          # the same build (baseline/build_ref_cuda.sh)
 OUR_SO = os.path.join(ROOT, "cryo_ralib_b200", "libcryo_ralib.so")
 NX, OU, XR = 90, 36, 3
 

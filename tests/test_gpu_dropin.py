@@ -1,5 +1,5 @@
 """Drop-in check at the ABI level (scripts/compare_ref_cuda.py): ONE ctypes harness in the reference driver's call order,
-run with the reference's own CUDA library (baseline/_ref/gpu_aln_pack.so: the sm_100 build of the reference's sources, a
+run with the reference's own CUDA library (oracle/_ref/gpu_aln_pack.so: the sm_100 build of the reference's sources, a
 built artefact that travels to the GPU box) and with libcryo_ralib.so, each in a child process, on the same synthetic stack
 with known poses.  Not parity (gpu_isac's arithmetic against EMAN2's): the two libraries must agree on the class, the mirror
 flag, the accumulated shift and the angle CONVENTIONS of AlignParam.  Skipped where the reference library was not built."""
@@ -16,8 +16,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.parametrize("mode,views", [("mref", 12), ("mref_m", 12), ("reffree", 1)])
 def test_same_harness_same_answers(mode, views):
-    if not os.path.exists(os.path.join(ROOT, "baseline", "_ref", "gpu_aln_pack.so")):
-        pytest.skip("baseline/_ref/gpu_aln_pack.so not built (baseline/build_ref_cuda.sh needs the reference's sources)")
+    if not any(os.path.exists(os.path.join(ROOT, d, "_ref", "gpu_aln_pack.so")) for d in ("oracle", "baseline")):
+        pytest.skip("oracle/_ref/gpu_aln_pack.so not built (`make -C oracle ref` needs the reference's sources)")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "compare_ref_cuda.py"), "1024", str(views), "1.0", mode],
                          cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-500:] + out.stderr[-500:]
