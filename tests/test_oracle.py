@@ -233,7 +233,8 @@ def test_oracle_reproduces_golden_case(oracle):
     assert np.allclose(info["filter"], g["filter"])
 
 
-@pytest.mark.parametrize("fixture,normalize", [("refcuda_mref_outputs.npz", True), ("refcuda_reffree_outputs.npz", False)])
+@pytest.mark.parametrize("fixture,normalize", [("refcuda_mref_outputs.npz", True), ("refcuda_reffree_outputs.npz", False),
+                                               ("refcuda_mref_snr0.1_outputs.npz", True)])
 def test_oracle_against_vectors_produced_by_the_reference_cuda_library(oracle, fixture, normalize):
     """tests/golden/refcuda_*_outputs.npz: AlignParam[] as the reference's OWN CUDA library (compiled unchanged for
     sm_100, stock entry points) left it for a deterministic stack after mref_align_run (12 references) and after
@@ -261,6 +262,18 @@ def test_oracle_against_vectors_produced_by_the_reference_cuda_library(oracle, f
     # returns them; shift_x / shift_y = the polar-centre offset of the winning grid position = -(sx, sy) of the search
     same = (want[:, 4].astype(int) == g["ref_id"]) & (want[:, 3].astype(int) == g["mirror"]) \
         & (-want[:, 6] == g["shift_x"]) & (-want[:, 7] == g["shift_y"])
+    if float(g["snr"]) < 1.0:
+        # ten times the noise: the two arithmetics (256 bilinear samples per ring against EMAN2's quadratic interpolation
+        # on Numrinit rings) still choose the same class and mirror flag, but a third of the winning grid positions move
+        # to a neighbouring pixel and the angles spread; both find the true view equally often
+        cls = (want[:, 4].astype(int) == g["ref_id"]) & (want[:, 3].astype(int) == g["mirror"])
+        assert cls.mean() >= 0.98, cls.mean()
+        near = np.maximum(np.abs(-want[:, 6] - g["shift_x"]), np.abs(-want[:, 7] - g["shift_y"])) <= 1.0
+        assert (cls & near).mean() >= 0.95, (cls & near).mean()
+        dang = np.abs((want[cls, 0] - g["angle"][cls] + 180.0) % 360.0 - 180.0)
+        assert np.percentile(dang, 90) <= 360.0 / int(numr[-1]), np.percentile(dang, 90)
+        assert abs((g["ref_id"] == truth["view"]).mean() - (want[:, 4].astype(int) == truth["view"]).mean()) <= 0.01
+        return
     assert same.mean() >= 0.995, (same.mean(), np.where(~same)[0][:10])
     dang = np.abs((want[same, 0] - g["angle"][same] + 180.0) % 360.0 - 180.0)
     assert np.percentile(dang, 99) <= 0.5 * 360.0 / int(numr[-1]), np.percentile(dang, 99)
