@@ -904,6 +904,8 @@ static int align_impl(CraCtx* c, int start, int stop, const CraSearch* search, c
             const CraSearch& sp = search[p];
             grp = (sp.cx - w.x * step >= lo_ok) && (sp.cx + w.y * step <= hi_ok) &&
                   (sp.cy - w.z * step >= lo_ok) && (sp.cy + w.w * step <= hi_ok);
+            // a windowed tile is sized for windows of up to 2 ceil(max_range) pixels: a wider request takes the general kernel
+            if (c->plan.tile && (float)std::max(w.x + w.y, w.z + w.w) * step > 2.0f * ceilf(c->cfg.max_range)) grp = false;
         }
         bgroup[bi] = grp;
         int acc = 0, cacc = 0;
