@@ -476,6 +476,15 @@ def main():
                                              frac=ccf_tflops / fp32 if fp32 else None,
                                              note="same algorithmic flops over the FFMA micro-benchmark measured in this run "
                                                   "(what an FP32 SIMT implementation could reach at best)"),
+                    roofline_composite=dict(kernel="ccf_tm_kernel", bound="tensor + fp32",
+                                            floor_ms_per_step=(agg["alignments"] * (4.0 * eng.lcirc * 3.0 / (tensor_peak * 1e12)
+                                                               + 5.0 * eng.maxrin * np.log2(eng.maxrin) / (fp32 * 1e12 if fp32 else float("inf")))) * 1e3 / args.steps,
+                                            measured_ms_per_step=agg["ms_ccf"] / args.steps,
+                                            frac=(agg["alignments"] * (4.0 * eng.lcirc * 3.0 / (tensor_peak * 1e12)
+                                                  + 5.0 * eng.maxrin * np.log2(eng.maxrin) / (fp32 * 1e12 if fp32 else float("inf")))) / ccf_s,
+                                            note="time floor of the kernel as it computes: the ring contraction's 4*lcirc flops three times "
+                                                 "(split-bf16) at the measured dense bf16 peak, plus the inverse FFT's 5*maxrin*log2(maxrin) "
+                                                 "flops at the FFMA peak of this run, over the measured kernel time"),
                     roofline_polar=dict(kernel="polar_group_kernel (Polar2Dm + Normalize_ring sums + Frngs)", bound="hbm",
                                         achieved=polar_gbs, peak=hbm_peak, unit="GB/s", frac=polar_gbs / hbm_peak,
                                         traffic=prof.get("polar_dram_bytes_per_launch"),
